@@ -1,0 +1,115 @@
+"""Generate the committed golden fixtures under ``tests/golden/`` by running the UNMODIFIED
+reference (``/root/reference``) in the build container.
+
+    python -m oracle.make_golden
+
+TEST INFRASTRUCTURE.  The reference ships no golden vectors, so parity is
+pinned on outputs of the reference itself:
+
+* ``model_<init>.npz``   - `UformerAudio.forward` / `wm_decode` (`uformerWM/model.py:2384-2511,
+                           2379-2382`) of the reference nn.Module on seeded inputs with weights
+                           from ``synthetic.init_state_dict`` (regenerated, not stored).
+* ``pipeline_cfg1_<attack>.npz`` - the reference driver `reconstruct_audio`
+                           (`uformerWM/audio_test.py:528-785`) executed unmodified (CPU proxy for
+                           the hard-coded 'cuda' device) on BASELINE config 1: one 1 s utterance,
+                           32x32 binary image, with the reference's own numpy attacks.
+* ``signal.npz``         - reference attack / metric functions on a seeded waveform.
+"""
+import os
+import random
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import shims, uformer as O, pipeline as P           # noqa: E402
+from image_in_speech_watermarking_b200 import synthetic as SY   # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def reference_module(kind, seed):
+    m = shims.build_reference_uformer_audio(0)
+    sd = SY.init_state_dict(O.state_dict_schema(), kind, seed)
+    m.load_state_dict(sd, strict=True)
+    return m.eval(), sd
+
+
+def model_fixture(kind, seed):
+    m, sd = reference_module(kind, seed)
+    wave = SY.synth_speech(0, 1.0)[None]
+    data = P.prepare_data(wave)
+    x = torch.cat(data[1], 0)                                   # (2,2,128,128) real STFT clips
+    msg = torch.stack([SY.synth_image_binary(0), SY.synth_image_binary(1)])
+    g = torch.Generator().manual_seed(99)
+    x_att = x + 0.05 * torch.randn(x.shape, generator=g)
+    with torch.no_grad(), shims.legacy_torch_spectral():
+        stft_new, noise, wm_pred, wm = m(x, msg)
+        wm_att = m.wm_decode(x_att)
+    np.savez_compressed(os.path.join(OUT, "model_%s.npz" % kind), seed=seed, x=x.numpy(), msg=msg.numpy(),
+                        x_att=x_att.numpy(), stft_new=stft_new.numpy(), noise=noise.numpy(),
+                        wm_pred=wm_pred.numpy(), wm=wm.numpy(), wm_att=wm_att.numpy())
+    print("model_%s: wm range %.4f..%.4f" % (kind, wm.min(), wm.max()))
+
+
+def pipeline_fixture(kind, seed, attack):
+    m, sd = reference_module(kind, seed)
+    run = shims.reference_reconstruct_audio()
+    wave = SY.synth_speech(0, 1.0)[None]
+    data = P.prepare_data(wave)
+    msg = SY.synth_image_binary(0)[None]
+    np.random.seed(2024)
+    random.seed(2024)
+    state = np.random.get_state()
+    with torch.no_grad():
+        out = run(data, msg, m, attack=attack)
+    draws = {}
+    if attack.startswith("awgn"):
+        np.random.set_state(state)
+        draws["awgn"] = np.random.normal(0, 1.0, wave.shape[-1])
+    audio_att, recon, wmk, wms, wms_att, mse, wml, wml_att, snr_o, snr_r = out
+    name = "pipeline_cfg1_%s.npz" % attack.replace("-", "_")
+    np.savez_compressed(os.path.join(OUT, name), seed=seed, kind=kind, attack=attack,
+                        audio_att=np.asarray(audio_att), recon=recon.numpy(), wms=np.stack(wms),
+                        wms_att=np.stack(wms_att), mse=mse, wm_loss=wml, wm_loss_att=wml_att,
+                        snr_ori=snr_o, snr_recon=snr_r, awgn_unit=draws.get("awgn", np.zeros(0)))
+    print(name, "mse %.3e wm_loss %.4f wm_loss_att %.4f" % (mse, wml, wml_att))
+
+
+def signal_fixture():
+    att = shims.reference_attack_functions()
+    met = shims.reference_metric_functions()
+    x = SY.synth_speech(3, 1.0).numpy()
+    np.random.seed(7)
+    st = np.random.get_state()
+    a = att["awgn"](x, snr=20)
+    np.random.set_state(st)
+    unit = np.random.normal(0, 1.0, x.shape)
+    random.seed(11)
+    jit = att["jittering_2"](x.copy(), 200)
+    random.seed(11)
+    idx = np.array([random.randint(0, len(x) - 1) for _ in range(200)])
+    lp = att["low_pass_filter"](x)
+    np.savez_compressed(os.path.join(OUT, "signal.npz"), x=x, awgn20=a, awgn_unit=unit,
+                        low_pass=lp, echo=att["echo_addition"](x), scale07=att["amplitude_scaling"](x, 0.7),
+                        jitter=jit, jitter_idx=idx, cal_snr=met["cal_snr"](x, lp),
+                        signaltonoise=met["signaltonoise"](x),
+                        snr_singlech=met["SNR_singlech"](x.astype(np.float64), lp))
+    print("signal.npz")
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(os.cpu_count())
+    signal_fixture()
+    model_fixture("stress", 0)
+    model_fixture("reference", 0)
+    pipeline_fixture("stress", 0, "awgn-20")
+    pipeline_fixture("stress", 0, "low_pass")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,80 @@
+"""The CPU oracle against the committed golden fixtures (outputs of the unmodified reference,
+made by ``oracle/make_golden.py``).  Runs everywhere; no GPU, no /root/reference."""
+import numpy as np
+import torch
+
+from oracle import uformer as O, signal as S, pipeline as P
+from image_in_speech_watermarking_b200 import synthetic as SY
+
+
+def _t(a):
+    return torch.from_numpy(a)
+
+
+def test_model_forward_matches_reference(golden, weights):
+    for kind in ("stress", "reference"):
+        g = golden("model_%s.npz" % kind)
+        sd = weights(kind, int(g["seed"]))
+        with torch.no_grad():
+            s, n, wp, wm = O.forward(sd, _t(g["x"]), _t(g["msg"]))
+            wa = O.wm_decode(sd, _t(g["x_att"]))
+        # same torch build => bit-exact; 1e-5 leaves room for a different CPU's GEMM blocking
+        for got, ref in ((s, "stft_new"), (n, "noise"), (wp, "wm_pred"), (wm, "wm"), (wa, "wm_att")):
+            np.testing.assert_allclose(got.numpy(), g[ref], rtol=0, atol=2e-5, err_msg=kind + ":" + ref)
+
+
+def test_signal_functions_match_reference(golden):
+    g = golden("signal.npz")
+    x = g["x"]
+    np.testing.assert_allclose(S.awgn(x, 20, noise_unit=g["awgn_unit"]), g["awgn20"], rtol=0, atol=1e-15)
+    np.testing.assert_allclose(S.low_pass_filter(x), g["low_pass"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(S.echo_addition(x), g["echo"], rtol=0, atol=0)
+    np.testing.assert_allclose(S.amplitude_scaling(x, 0.7), g["scale07"], rtol=0, atol=0)
+    np.testing.assert_allclose(S.jittering_2(x, 200, indices=g["jitter_idx"]), g["jitter"], rtol=0, atol=0)
+    assert abs(S.cal_snr(x, g["low_pass"]) - float(g["cal_snr"])) < 1e-9
+    assert abs(S.signaltonoise(x) - float(g["signaltonoise"])) < 1e-9
+    assert abs(S.SNR_singlech(x.astype(np.float64), g["low_pass"]) - float(g["snr_singlech"])) < 1e-9
+
+
+def test_numpy_stft_istft_match_torch():
+    x = SY.synth_speech(5, 1.0)
+    ref = torch.view_as_real(torch.stft(x.double()[None], 255, return_complex=True)).numpy()
+    got = S.stft(x.numpy()[None])
+    assert got.shape == (1, 128, 254, 2)
+    np.testing.assert_allclose(got, ref, rtol=0, atol=1e-12)
+    z = torch.view_as_complex(torch.from_numpy(ref))
+    np.testing.assert_allclose(S.istft(ref, length=16000), torch.istft(z, 255, length=16000).numpy(), atol=1e-13)
+    np.testing.assert_allclose(S.istft(ref), torch.istft(z, 255).numpy(), atol=1e-13)
+
+
+def test_pipeline_matches_reference_driver(golden, weights):
+    for name in ("pipeline_cfg1_awgn_20.npz", "pipeline_cfg1_low_pass.npz"):
+        g = golden(name)
+        sd = weights(str(g["kind"]), int(g["seed"]))
+        wave = SY.synth_speech(0, 1.0)[None]
+        msg = SY.synth_image_binary(0)[None]
+        draws = {"awgn": g["awgn_unit"]} if g["awgn_unit"].size else None
+        out, _ = P.reconstruct_audio(P.prepare_data(wave), msg, sd, attack=str(g["attack"]), draws=draws)
+        np.testing.assert_allclose(out[1].numpy(), g["recon"], rtol=0, atol=1e-6)
+        np.testing.assert_allclose(out[0], g["audio_att"], rtol=0, atol=1e-6)
+        np.testing.assert_allclose(np.stack(out[3]), g["wms"], rtol=0, atol=1e-5)
+        np.testing.assert_allclose(np.stack(out[4]), g["wms_att"], rtol=0, atol=1e-5)
+        assert abs(out[5] - float(g["mse"])) < 1e-7
+        assert abs(out[6] - float(g["wm_loss"])) < 1e-6
+        assert abs(out[7] - float(g["wm_loss_att"])) < 1e-6
+        assert abs(out[8] - float(g["snr_ori"])) < 1e-6
+        assert abs(out[9] - float(g["snr_recon"])) < 1e-4
+
+
+def test_edge_cases_clip_quirks():
+    # quirk B-6: T % 128 == 0 appends an empty clip and len_last_clip == 0
+    L = 63 * 127 + 1                                # T = 1 + (L-1)//63 = 128
+    spec = S.stft(np.zeros((1, L)))
+    clips, last = S.clip_spectrogram(spec)
+    assert spec.shape[2] == 128 and len(clips) == 2 and last == 0
+    # quirk B-7: attacked clips = (T + 126) // 128
+    for L in (16000, 63 * 127, 63 * 127 + 1, 63 * 128, 48000):
+        T = 1 + (L - 1) // 63
+        assert len(S.attacked_clips(np.zeros(L))) == (T + 126) // 128
+    # BER: numpy round is half-to-even
+    assert S.bit_error_rate(np.array([0.5, 1.5, 0.49, 0.51]), np.array([0, 1, 0, 1])) == 0.0
