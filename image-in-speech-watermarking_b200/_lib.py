@@ -1,0 +1,87 @@
+"""ctypes binding of ``csrc/libwmk.so`` (the C ABI of ``include/wmk.h``).
+
+Fails loudly: a missing library or a failing call raises; nothing falls back to the CPU."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libwmk.so")
+
+c_f32p = ctypes.c_void_p
+_i, _f, _vp, _u64, _sz = ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_size_t
+_dp = ctypes.POINTER(ctypes.c_double)
+
+# name -> (restype, argtypes); must list every symbol include/wmk.h declares
+SIGNATURES = {
+    "wmk_version": (_i, []),
+    "wmk_last_error": (ctypes.c_char_p, []),
+    "wmk_launch_count": (_u64, []),
+    "wmk_stft_num_frames": (_i, [_i]),
+    "wmk_stft_clips_f32": (_i, [_vp, _i, _i, _vp, _i, _vp]),
+    "wmk_istft_clips_f32": (_i, [_vp, _i, _i, _i, _vp, _i, _vp]),
+    "wmk_attack_awgn_f32": (_i, [_vp, _vp, _i, _i, _f, _vp, _u64, _vp]),
+    "wmk_attack_scale_f32": (_i, [_vp, _vp, _i, _i, _f, _vp]),
+    "wmk_attack_echo_f32": (_i, [_vp, _vp, _i, _i, _i, _f, _vp]),
+    "wmk_attack_lowpass_f32": (_i, [_vp, _vp, _i, _i, _i, _dp, _dp, _dp, _vp]),
+    "wmk_attack_jitter_zero_f32": (_i, [_vp, _i, _i, _vp, _i, _vp]),
+    "wmk_attack_requant8_f32": (_i, [_vp, _vp, _i, _i, _vp]),
+    "wmk_attack_resample2_f32": (_i, [_vp, _vp, _i, _i, _dp, _i, _vp]),
+    "wmk_wave_stats_f64": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
+    "wmk_wm_stats_f64": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
+    "wmk_uformer_plan_create": (_i, [_i, ctypes.POINTER(_vp)]),
+    "wmk_plan_destroy": (_i, [_vp]),
+    "wmk_plan_set_tensor": (_i, [_vp, ctypes.c_char_p, _vp, ctypes.POINTER(ctypes.c_int64), _i]),
+    "wmk_plan_finalize": (_i, [_vp]),
+    "wmk_plan_set_chunk": (_i, [_vp, _i]),
+    "wmk_plan_workspace_bytes": (_sz, [_vp]),
+    "wmk_uformer_forward": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "wmk_uformer_extract": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
+    "wmk_plan_enable_taps": (_i, [_vp, _i]),
+    "wmk_plan_get_tap": (_i, [_vp, ctypes.c_char_p, _vp, _sz, ctypes.POINTER(_sz)]),
+    "wmk_linear_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+}
+
+PREC_FP32, PREC_BF16 = 0, 1
+_lib = None
+
+
+class WmkError(RuntimeError):
+    pass
+
+
+def load():
+    """Load libwmk.so (once).  Raises if it has not been built (``__graft_entry__.build()`` /
+    ``make -C image-in-speech-watermarking_b200/csrc``)."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise WmkError("libwmk.so not built at %s: run `python -c 'import __graft_entry__ as g; g.build()'`; "
+                           "there is no CPU fallback" % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)          # AttributeError if the library does not export it
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(status):
+    if status != 0:
+        raise WmkError("libwmk call failed (%d): %s" % (status, load().wmk_last_error().decode()))
+
+
+def stream_ptr():
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    """Device pointer of a contiguous CUDA tensor (or None)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise WmkError("expected a CUDA tensor (the hot path has no CPU implementation)")
+    if not t.is_contiguous():
+        raise WmkError("expected a contiguous tensor")
+    return ctypes.c_void_p(t.data_ptr())

@@ -1,0 +1,76 @@
+"""STFT / ISTFT front end of the uformer trainer / evaluator, on the GPU.
+
+Drop-in for the `torch.stft(x, n_fft=255)` / `torch.istft(spec, n_fft=255, length=L)` call
+sites of the reference (`uformerWM/audio_test.py:315-316,598-600,677-678`,
+`uformerWM/model.py:2458,2463`; the model they serve is named by
+`uformerWM/audio_uformer_stft.py:452`) fused with the 128-frame clip split
+(`uformerWM/audio_test.py:319-343`)."""
+import torch
+
+from . import _lib
+
+N_FFT, HOP, BINS, CLIP = 255, 63, 128, 128
+
+
+def num_frames(L):
+    return 1 + (L - 1) // HOP
+
+
+def stft_clips(wave, n_clips=None):
+    """wave (B, L) float32 CUDA -> clips (B, n_clips, 2, 128, 128).  Default n_clips is the
+    reference's `T // 128 + 1` (`audio_test.py:319-325`, incl. the empty clip when T % 128 == 0)."""
+    lib = _lib.load()
+    if wave.dim() == 1:
+        wave = wave[None]
+    wave = wave.contiguous().float()
+    B, L = wave.shape
+    T = num_frames(L)
+    if n_clips is None:
+        n_clips = T // CLIP + 1
+    out = torch.empty((B, n_clips, 2, BINS, CLIP), device=wave.device, dtype=torch.float32)
+    _lib.check(lib.wmk_stft_clips_f32(_lib.ptr(wave), B, L, _lib.ptr(out), n_clips, _lib.stream_ptr()))
+    return out
+
+
+def istft_clips(clips, T, length=None):
+    """clips (B, n_clips, 2, 128, 128) -> wave (B, length): `torch.istft(n_fft=255, length=...)` of
+    the first T frames of the concatenated clips (`audio_test.py:595-600`)."""
+    lib = _lib.load()
+    clips = clips.contiguous().float()
+    B, n_clips = clips.shape[0], clips.shape[1]
+    if length is None:
+        length = HOP * (T - 1) + 1
+    out = torch.empty((B, length), device=clips.device, dtype=torch.float32)
+    _lib.check(lib.wmk_istft_clips_f32(_lib.ptr(clips), B, n_clips, T, _lib.ptr(out), length, _lib.stream_ptr()))
+    return out
+
+
+def stft(x, n_fft=N_FFT, return_complex=False):
+    """`torch.stft(x, n_fft=255)` legacy layout: (B, L) -> (B, 128, T, 2) (or complex)."""
+    if n_fft != N_FFT:
+        raise ValueError("the CUDA front end implements n_fft=255 (hop 63) only")
+    squeeze = x.dim() == 1
+    xs = x[None] if squeeze else x
+    T = num_frames(xs.shape[-1])
+    c = stft_clips(xs, (T + CLIP - 1) // CLIP)                      # (B, nc, 2, F, 128)
+    s = c.permute(0, 3, 1, 4, 2).reshape(c.shape[0], BINS, -1, 2)[:, :, :T, :].contiguous()
+    if squeeze:
+        s = s[0]
+    return torch.view_as_complex(s) if return_complex else s
+
+
+def istft(spec, n_fft=N_FFT, length=None, return_complex=False):
+    """`torch.istft(spec, n_fft=255[, length])` on the legacy (…, 128, T, 2) layout (or complex)."""
+    if n_fft != N_FFT:
+        raise ValueError("the CUDA front end implements n_fft=255 (hop 63) only")
+    if torch.is_complex(spec):
+        spec = torch.view_as_real(spec)
+    squeeze = spec.dim() == 3
+    s = spec[None] if squeeze else spec
+    B, F, T, _ = s.shape
+    nc = (T + CLIP - 1) // CLIP
+    pad = nc * CLIP - T
+    s = torch.nn.functional.pad(s.float(), (0, 0, 0, pad))
+    clips = s.reshape(B, F, nc, CLIP, 2).permute(0, 2, 4, 1, 3).contiguous()
+    w = istft_clips(clips, T, length)
+    return w[0] if squeeze else w

@@ -1,0 +1,360 @@
+// Waveform attacks (uformerWM/audio_attack.py) and the SNR / MSE / BER reductions
+// (uformerWM/evaluate.py:139-144, uformerWM/audio_test.py:522-526,618,625,712,
+// hidden/test_model.py:60-64) as fused, memory-bound kernels over a batch of utterances that
+// stays resident in HBM (the reference moves every utterance to the host for these steps).
+#include <math.h>
+#include <vector>
+
+#include "uformer_kernels.cuh"
+
+namespace wmk {
+
+namespace {
+
+// ---------------------------------------------------------------------------- reductions
+__device__ __forceinline__ void block_atomic_add(double v, double* dst) {
+  __shared__ double red[32];
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    v = lane < (int)(blockDim.x >> 5) ? red[lane] : 0.0;
+    v = warp_sum(v);
+    if (lane == 0) atomicAdd(dst, v);
+  }
+}
+
+// power[b] += sum x^2 (fp64 accumulation of fp32 squares, as numpy's mean(signal**2) on a
+// float32 array accumulates pairwise in float32; fp64 is at least as accurate)
+__global__ void __launch_bounds__(256) power_kernel(const float* __restrict__ x, int L, double* __restrict__ power) {
+  const int b = blockIdx.y;
+  const float* xr = x + (size_t)b * L;
+  double s = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < L; i += gridDim.x * blockDim.x) {
+    const float v = xr[i];
+    s += (double)v * v;
+  }
+  block_atomic_add(s, power + b);
+}
+
+// Philox4x32-10 counter RNG + Box-Muller: N(0,1) draws for the throughput path.
+__device__ __forceinline__ void philox4x32(uint32_t c[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+    c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
+
+// awgn (audio_attack.py:112-123): sigma = sqrt(mean(x^2) * 10^(-snr/10)); y = x + sigma * n
+__global__ void __launch_bounds__(256)
+awgn_apply_kernel(const float* __restrict__ src, float* __restrict__ dst, int L, const double* __restrict__ power,
+                  float snr_db, const float* __restrict__ unit, uint64_t seed) {
+  const int b = blockIdx.y;
+  const double p = power[b] / (double)L;
+  const double p_db = 10.0 * log10(p);
+  const float sigma = (float)sqrt(pow(10.0, (p_db - (double)snr_db) / 10.0));
+  const size_t base = (size_t)b * L;
+  for (int i4 = blockIdx.x * blockDim.x + threadIdx.x; i4 * 4 < L; i4 += gridDim.x * blockDim.x) {
+    float n[4];
+    if (unit) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) n[j] = i4 * 4 + j < L ? unit[base + i4 * 4 + j] : 0.f;
+    } else {
+      uint32_t c[4] = {(uint32_t)i4, (uint32_t)b, 0u, 0u};
+      philox4x32(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+      const float u0 = (c[0] + 1.0f) * 2.3283064e-10f, u1 = c[1] * 2.3283064e-10f;
+      const float u2 = (c[2] + 1.0f) * 2.3283064e-10f, u3 = c[3] * 2.3283064e-10f;
+      const float r0 = sqrtf(-2.0f * __logf(fminf(u0, 1.0f))), r1 = sqrtf(-2.0f * __logf(fminf(u2, 1.0f)));
+      float s0, c0, s1, c1;
+      __sincosf(6.2831853f * u1, &s0, &c0);
+      __sincosf(6.2831853f * u3, &s1, &c1);
+      n[0] = r0 * c0; n[1] = r0 * s0; n[2] = r1 * c1; n[3] = r1 * s1;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (i4 * 4 + j < L) dst[base + i4 * 4 + j] = src[base + i4 * 4 + j] + sigma * n[j];
+  }
+}
+
+enum { EW_SCALE = 0, EW_ECHO = 1, EW_REQUANT8 = 2 };
+template <int OP>
+__global__ void __launch_bounds__(256)
+elementwise_kernel(const float* __restrict__ src, float* __restrict__ dst, int L, float p0, int p1) {
+  const size_t base = (size_t)blockIdx.y * L;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < L; i += gridDim.x * blockDim.x) {
+    const float v = src[base + i];
+    float r;
+    if (OP == EW_SCALE) r = v * p0;                                               // audio_attack.py:55-58
+    else if (OP == EW_ECHO) r = v + (i >= p1 ? p0 * src[base + i - p1] : 0.f);    // audio_attack.py:47-51
+    else r = rintf(fminf(fmaxf(v, -1.f), 1.f) * 127.0f) * (1.0f / 128.0f);         // PCM_U8 round trip
+    dst[base + i] = r;
+  }
+}
+
+__global__ void jitter_zero_kernel(float* __restrict__ wave, int L, const int32_t* __restrict__ idx, int n_idx) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_idx) return;
+  const int k = idx[(size_t)blockIdx.y * n_idx + i];
+  if (k >= 0 && k < L) wave[(size_t)blockIdx.y * L + k] = 0.f;                    // audio_attack.py:187
+}
+
+// ---------------------------------------------------------------------------- zero-phase IIR
+// scipy.signal.filtfilt(b, a, x) (audio_attack.py:29): odd extension by padlen samples, forward
+// lfilter (transposed direct form II, state zi * first sample), the same on the reversed signal.
+// The recurrence is sequential in time; it is cut into chunks of CH outputs, one per thread, each
+// started `warm` samples early from a zero state: the filter's impulse response has decayed below
+// 1e-18 by then, so every chunk reproduces the sequential result to fp64 rounding.  Chunks that
+// reach the start of the extended signal use the exact zi state instead.
+constexpr int MAXORD = 16;
+struct IirCoef {
+  double b[MAXORD + 1], a[MAXORD + 1], zi[MAXORD];
+  int order, padlen, warm;
+};
+constexpr int CH = 128;
+
+__device__ __forceinline__ double ext_sample(const float* x, int L, int padlen, int i) {
+  // odd extension: ext[i], i in [0, L + 2*padlen)
+  const int q = i - padlen;
+  if (q < 0) return 2.0 * (double)x[0] - (double)x[-q];
+  if (q >= L) return 2.0 * (double)x[L - 1] - (double)x[2 * (L - 1) - q];
+  return (double)x[q];
+}
+
+template <bool BACKWARD>
+__global__ void __launch_bounds__(128)
+iir_pass_kernel(const float* __restrict__ x, double* __restrict__ tmp, float* __restrict__ out, int L, IirCoef cf) {
+  const int Le = L + 2 * cf.padlen;
+  const int chunk = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c0 = chunk * CH;
+  if (c0 >= Le) return;
+  const int b = blockIdx.y;
+  const float* xr = x + (size_t)b * L;
+  double* tr = tmp + (size_t)b * Le;
+  // logical time index n runs over the (possibly reversed) extended signal
+  auto in_at = [&](int n) -> double {
+    return BACKWARD ? tr[Le - 1 - n] : ext_sample(xr, L, cf.padlen, n);
+  };
+  int start = c0 - cf.warm;
+  double z[MAXORD];
+  if (start <= 0) {
+    start = 0;
+    const double x0 = in_at(0);
+    for (int i = 0; i < cf.order; ++i) z[i] = cf.zi[i] * x0;
+  } else {
+    for (int i = 0; i < cf.order; ++i) z[i] = 0.0;
+  }
+  const int end = min(c0 + CH, Le);
+  for (int n = start; n < end; ++n) {
+    const double xn = in_at(n);
+    const double yn = cf.b[0] * xn + z[0];
+    for (int i = 0; i < cf.order - 1; ++i) z[i] = cf.b[i + 1] * xn + z[i + 1] - cf.a[i + 1] * yn;
+    z[cf.order - 1] = cf.b[cf.order] * xn - cf.a[cf.order] * yn;
+    if (n >= c0) {
+      if (!BACKWARD) {
+        tr[n] = yn;
+      } else {
+        const int pos = Le - 1 - n - cf.padlen;       // back to forward time, strip the padding
+        if (pos >= 0 && pos < L) out[(size_t)b * L + pos] = (float)yn;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------- 2:1 / 1:2 resample
+__global__ void __launch_bounds__(256)
+resample_down_kernel(const float* __restrict__ x, float* __restrict__ d, int L, int Ld, const float* __restrict__ h, int nt) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= Ld) return;
+  const float* xr = x + (size_t)blockIdx.y * L;
+  const int c = (nt - 1) / 2;
+  double a = 0.0;
+  for (int k = 0; k < nt; ++k) {
+    const int q = 2 * m + c - k;
+    if (q >= 0 && q < L) a += (double)h[k] * xr[q];
+  }
+  d[(size_t)blockIdx.y * Ld + m] = (float)a;
+}
+__global__ void __launch_bounds__(256)
+resample_up_kernel(const float* __restrict__ d, float* __restrict__ y, int L, int Ld, const float* __restrict__ h, int nt) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= L) return;
+  const float* dr = d + (size_t)blockIdx.y * Ld;
+  const int c = (nt - 1) / 2;
+  double a = 0.0;
+  for (int k = 0; k < nt; ++k) {
+    const int q = n + c - k;            // index into the zero-stuffed signal
+    if (q >= 0 && !(q & 1) && (q >> 1) < Ld) a += 2.0 * (double)h[k] * dr[q >> 1];
+  }
+  y[(size_t)blockIdx.y * L + n] = (float)a;
+}
+
+// ---------------------------------------------------------------------------- metrics
+__global__ void __launch_bounds__(256)
+wave_stats_kernel(const float* __restrict__ orig, const float* __restrict__ test, int L, double* __restrict__ stats) {
+  const int b = blockIdx.y;
+  const float* o = orig + (size_t)b * L;
+  const float* t = test + (size_t)b * L;
+  double s_oo = 0, s_dd = 0, s_t = 0, s_tt = 0, s_o = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < L; i += gridDim.x * blockDim.x) {
+    const double ov = o[i], tv = t[i], d = ov - tv;
+    s_oo += ov * ov; s_dd += d * d; s_t += tv; s_tt += tv * tv; s_o += ov;
+  }
+  double* st = stats + (size_t)b * 6;
+  block_atomic_add(s_oo, st + 0);
+  block_atomic_add(s_dd, st + 1);
+  block_atomic_add(s_t, st + 2);
+  block_atomic_add(s_tt, st + 3);
+  block_atomic_add(s_o, st + 4);
+  if (blockIdx.x == 0 && threadIdx.x == 0) st[5] = (double)L;
+}
+
+__global__ void __launch_bounds__(256)
+wm_stats_kernel(const float* __restrict__ wm, const float* __restrict__ msg, int msg_stride, double* __restrict__ stats) {
+  const size_t r = blockIdx.x;
+  const float* w = wm + r * 1024;
+  const float* m = msg + r * msg_stride;
+  double err = 0, se = 0;
+  for (int i = threadIdx.x; i < 1024; i += 256) {
+    const float v = w[i], mv = m[i];
+    const float bit = fminf(fmaxf(rintf(v), 0.f), 1.f);      // np.round is half-to-even == rintf
+    err += fabsf(bit - mv);
+    const double d = (double)v - (double)mv;
+    se += d * d;
+  }
+  block_atomic_add(err, stats + r * 2);
+  block_atomic_add(se, stats + r * 2 + 1);
+}
+
+dim3 wave_grid(int L, int B, int per_thread = 4) { return dim3(cdiv(L, 256 * per_thread), B); }
+
+}  // namespace
+
+}  // namespace wmk
+
+using namespace wmk;
+
+extern "C" int wmk_attack_awgn_f32(const float* src, float* dst, int B, int L, float snr_db,
+                                   const float* noise_unit, uint64_t seed, void* stream) {
+  WMK_REQUIRE(src && dst && B > 0 && L > 0, "awgn: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  double* power = nullptr;
+  WMK_CHECK_CUDA(cudaMallocAsync(&power, sizeof(double) * B, st));
+  WMK_CHECK_CUDA(cudaMemsetAsync(power, 0, sizeof(double) * B, st));
+  power_kernel<<<wave_grid(L, B, 8), 256, 0, st>>>(src, L, power);
+  WMK_CHECK_LAUNCH("power_kernel");
+  awgn_apply_kernel<<<dim3(cdiv(L, 1024), B), 256, 0, st>>>(src, dst, L, power, snr_db, noise_unit, seed);
+  WMK_CHECK_LAUNCH("awgn_apply_kernel");
+  WMK_CHECK_CUDA(cudaFreeAsync(power, st));
+  return 0;
+}
+
+extern "C" int wmk_attack_scale_f32(const float* src, float* dst, int B, int L, float factor, void* stream) {
+  WMK_REQUIRE(src && dst && B > 0 && L > 0, "scale: bad arguments");
+  elementwise_kernel<EW_SCALE><<<wave_grid(L, B), 256, 0, (cudaStream_t)stream>>>(src, dst, L, factor, 0);
+  WMK_CHECK_LAUNCH("elementwise_kernel<scale>");
+  return 0;
+}
+
+extern "C" int wmk_attack_echo_f32(const float* src, float* dst, int B, int L, int delay, float gain, void* stream) {
+  WMK_REQUIRE(src && dst && src != dst && B > 0 && L > 0 && delay >= 0, "echo: bad arguments (in-place not allowed)");
+  elementwise_kernel<EW_ECHO><<<wave_grid(L, B), 256, 0, (cudaStream_t)stream>>>(src, dst, L, gain, delay);
+  WMK_CHECK_LAUNCH("elementwise_kernel<echo>");
+  return 0;
+}
+
+extern "C" int wmk_attack_requant8_f32(const float* src, float* dst, int B, int L, void* stream) {
+  WMK_REQUIRE(src && dst && B > 0 && L > 0, "requant8: bad arguments");
+  elementwise_kernel<EW_REQUANT8><<<wave_grid(L, B), 256, 0, (cudaStream_t)stream>>>(src, dst, L, 0.f, 0);
+  WMK_CHECK_LAUNCH("elementwise_kernel<requant8>");
+  return 0;
+}
+
+extern "C" int wmk_attack_jitter_zero_f32(float* wave, int B, int L, const int32_t* idx, int n_idx, void* stream) {
+  WMK_REQUIRE(wave && idx && B > 0 && L > 0 && n_idx > 0, "jitter: bad arguments");
+  jitter_zero_kernel<<<dim3(cdiv(n_idx, 256), B), 256, 0, (cudaStream_t)stream>>>(wave, L, idx, n_idx);
+  WMK_CHECK_LAUNCH("jitter_zero_kernel");
+  return 0;
+}
+
+extern "C" int wmk_attack_lowpass_f32(const float* src, float* dst, int B, int L, int order, const double* b_host,
+                                      const double* a_host, const double* zi_host, void* stream) {
+  WMK_REQUIRE(src && dst && src != dst && B > 0 && order >= 1 && order <= MAXORD && b_host && a_host && zi_host,
+              "lowpass: bad arguments (order <= %d, in-place not allowed)", MAXORD);
+  IirCoef cf;
+  cf.order = order;
+  cf.padlen = 3 * (order + 1);
+  WMK_REQUIRE(L > cf.padlen, "lowpass: signal of %d samples is shorter than padlen %d", L, cf.padlen);
+  for (int i = 0; i <= order; ++i) { cf.b[i] = b_host[i] / a_host[0]; cf.a[i] = a_host[i] / a_host[0]; }
+  for (int i = 0; i < order; ++i) cf.zi[i] = zi_host[i];
+  {  // warm-up length: samples until the recursive part's impulse response stays below 1e-18
+    std::vector<double> h(order + 1, 0.0);
+    int quiet = 0, n = 0;
+    double y = 1.0;
+    for (n = 0; n < 8192 && quiet < 2 * order; ++n) {
+      double v = n == 0 ? 1.0 : 0.0;
+      for (int i = 1; i <= order; ++i) v -= cf.a[i] * h[i - 1];
+      for (int i = order - 1; i > 0; --i) h[i] = h[i - 1];
+      h[0] = v;
+      y = fabs(v);
+      quiet = y < 1e-18 ? quiet + 1 : 0;
+    }
+    cf.warm = n;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Le = L + 2 * cf.padlen;
+  double* tmp = nullptr;
+  WMK_CHECK_CUDA(cudaMallocAsync(&tmp, sizeof(double) * (size_t)B * Le, st));
+  dim3 grid(cdiv(cdiv(Le, CH), 128), B);
+  iir_pass_kernel<false><<<grid, 128, 0, st>>>(src, tmp, nullptr, L, cf);
+  WMK_CHECK_LAUNCH("iir_pass_kernel<fwd>");
+  iir_pass_kernel<true><<<grid, 128, 0, st>>>(src, tmp, dst, L, cf);
+  WMK_CHECK_LAUNCH("iir_pass_kernel<bwd>");
+  WMK_CHECK_CUDA(cudaFreeAsync(tmp, st));
+  return 0;
+}
+
+extern "C" int wmk_attack_resample2_f32(const float* src, float* dst, int B, int L, const double* taps_host, int n_taps,
+                                        void* stream) {
+  WMK_REQUIRE(src && dst && src != dst && B > 0 && L > 0 && taps_host && n_taps > 0 && n_taps <= 1024 && (n_taps & 1),
+              "resample2: bad arguments (odd n_taps <= 1024, in-place not allowed)");
+  cudaStream_t st = (cudaStream_t)stream;
+  std::vector<float> hf(n_taps);
+  for (int i = 0; i < n_taps; ++i) hf[i] = (float)taps_host[i];
+  const int Ld = (L + 1) / 2;
+  float *h = nullptr, *d = nullptr;
+  WMK_CHECK_CUDA(cudaMallocAsync(&h, sizeof(float) * n_taps, st));
+  WMK_CHECK_CUDA(cudaMallocAsync(&d, sizeof(float) * (size_t)B * Ld, st));
+  WMK_CHECK_CUDA(cudaMemcpyAsync(h, hf.data(), sizeof(float) * n_taps, cudaMemcpyHostToDevice, st));
+  WMK_CHECK_CUDA(cudaStreamSynchronize(st));   // hf is a stack-owned host buffer
+  resample_down_kernel<<<dim3(cdiv(Ld, 256), B), 256, 0, st>>>(src, d, L, Ld, h, n_taps);
+  WMK_CHECK_LAUNCH("resample_down_kernel");
+  resample_up_kernel<<<dim3(cdiv(L, 256), B), 256, 0, st>>>(d, dst, L, Ld, h, n_taps);
+  WMK_CHECK_LAUNCH("resample_up_kernel");
+  WMK_CHECK_CUDA(cudaFreeAsync(h, st));
+  WMK_CHECK_CUDA(cudaFreeAsync(d, st));
+  return 0;
+}
+
+extern "C" int wmk_wave_stats_f64(const float* orig, const float* test, int B, int L, double* stats, void* stream) {
+  WMK_REQUIRE(orig && test && stats && B > 0 && L > 0, "wave_stats: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  WMK_CHECK_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 6 * B, st));
+  wave_stats_kernel<<<wave_grid(L, B, 8), 256, 0, st>>>(orig, test, L, stats);
+  WMK_CHECK_LAUNCH("wave_stats_kernel");
+  return 0;
+}
+
+extern "C" int wmk_wm_stats_f64(const float* wm, const float* msg, int n, int msg_stride, double* stats, void* stream) {
+  WMK_REQUIRE(wm && msg && stats && n > 0 && (msg_stride == 0 || msg_stride == 1024), "wm_stats: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  WMK_CHECK_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * n, st));
+  wm_stats_kernel<<<n, 256, 0, st>>>(wm, msg, msg_stride, stats);
+  WMK_CHECK_LAUNCH("wm_stats_kernel");
+  return 0;
+}

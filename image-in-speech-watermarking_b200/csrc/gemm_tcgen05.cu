@@ -1,0 +1,340 @@
+// bf16 dense layer on the sm_100a 5th-generation tensor cores.
+//
+//   C[M][N] = epilogue( A[M][K] * W[N][K]^T + bias )       A, W bf16 K-major; fp32 accumulate
+//
+// One CTA computes one 128 x BN output tile:
+//   warp 0     TMA producer : cp.async.bulk.tensor 2-D tiles (128B swizzle) of A and W into a
+//                              ring of shared-memory stages, completion on mbarriers
+//   warp 1     MMA issuer   : one thread issues tcgen05.mma (M=128, N=BN, K=16) into a TMEM
+//                              accumulator; tcgen05.commit releases stages / signals the epilogue
+//   warps 2-5  epilogue     : tcgen05.ld the accumulator (one TMEM lane = one output row),
+//                              bias / GELU / residual / pixel-shuffle, 128-bit global stores
+// Several CTAs are resident per SM (TMEM columns and shared memory permitting), so one CTA's
+// epilogue overlaps another's main loop.  Replaces every nn.Linear of the LeWin blocks
+// (uformerWM/model.py:455-456,518,686,690) and, through im2col / pixel-shuffle, the 4x4-s2 and
+// transposed 2x2-s2 convolutions (model.py:763,789).
+#include <cuda.h>
+#include <mutex>
+
+#include "wmk_common.cuh"
+
+namespace wmk {
+
+namespace {
+
+constexpr int BM = 128;       // rows per tile = TMEM lanes
+constexpr int BK = 64;        // bf16 elements per k-block = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int kThreads = 192;
+
+// ------------------------------------------------------------------------------------- PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1,
+                                            uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tcgen05_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                                 uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+        "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory descriptor of a K-major, 128B-swizzled tile whose rows are 128 bytes
+// (64 bf16): 8-row swizzle atoms of 1024 B stacked along M/N (SBO = 1024 B); LBO unused.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);   // start address  [0,14)
+  d |= (uint64_t)1 << 16;                     // leading byte offset (ignored for swizzled K-major)
+  d |= (uint64_t)(1024u >> 4) << 32;          // stride byte offset [32,46)
+  d |= (uint64_t)1 << 46;                     // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                     // layout type: SWIZZLE_128B
+  return d;
+}
+
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=BN.
+__host__ __device__ constexpr uint32_t umma_idesc(int bn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+__host__ __device__ constexpr int tmem_cols(int bn) { return bn <= 32 ? 32 : bn <= 64 ? 64 : bn <= 128 ? 128 : 256; }
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                    EpiParams p, int K, int n_tiles, int n_stages) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;           // 128B swizzle needs 1024B alignment
+  constexpr uint32_t A_BYTES = BM * BK * 2;
+  constexpr uint32_t W_BYTES = BN * BK * 2;
+  constexpr uint32_t STAGE = A_BYTES + W_BYTES;
+  const uint32_t bars = base + (uint32_t)n_stages * STAGE;   // full[ns], empty[ns], tmem_full, tmem slot
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (n_stages + s); };
+  const uint32_t tmem_full_bar = bars + 16u * n_stages;
+  const uint32_t tmem_slot = tmem_full_bar + 8u;
+  volatile uint32_t* tmem_slot_ptr =
+      (volatile uint32_t*)(smem_raw + (tmem_slot - raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x;
+  const int bn_idx = tile % n_tiles, bm_idx = tile / n_tiles;
+  const int m0 = bm_idx * BM, n0 = bn_idx * BN;
+  const int kblocks = (K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+    for (int s = 0; s < n_stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                 "n"(tmem_cols(BN)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_acc = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < kblocks; ++kb) {
+        const int s = kb % n_stages;
+        const uint32_t ph = (uint32_t)(kb / n_stages) & 1u;
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        mbar_arrive_expect_tx(full_bar(s), STAGE);
+        const uint32_t sa = base + (uint32_t)s * STAGE;
+        tma_load_2d(sa, &tmA, kb * BK, m0, full_bar(s));
+        tma_load_2d(sa + A_BYTES, &tmW, kb * BK, n0, full_bar(s));
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc(BN);
+      for (int kb = 0; kb < kblocks; ++kb) {
+        const int s = kb % n_stages;
+        const uint32_t ph = (uint32_t)(kb / n_stages) & 1u;
+        mbar_wait(full_bar(s), ph);
+        tcgen05_fence_after();
+        const uint32_t sa = base + (uint32_t)s * STAGE;
+        const uint64_t adesc = umma_desc_sw128(sa);
+        const uint64_t bdesc = umma_desc_sw128(sa + A_BYTES);
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in 16-byte units
+          tcgen05_mma_bf16(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                           (uint32_t)((kb | k) != 0));
+        }
+        tcgen05_commit(empty_bar(s));          // frees the stage when these MMAs retire
+      }
+      tcgen05_commit(tmem_full_bar);           // accumulator complete
+    }
+  } else {
+    // epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31
+    const int q = warp & 3;
+    const int row = m0 + q * 32 + lane;
+    mbar_wait(tmem_full_bar, 0);
+    tcgen05_fence_after();
+    const bool row_ok = row < p.M;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t v[32];
+      tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+      if (!row_ok) continue;
+      const int n = n0 + c * 32;
+      const size_t off = epi_row_offset(p, row, n);
+      float f[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+      if (p.bias) {
+        const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 b = __ldg(b4 + j);
+          f[4 * j] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
+        }
+      }
+      if (p.epi == EPI_BIAS_GELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+      } else if (p.epi == EPI_BIAS_RESID) {
+        const float4* r4 = reinterpret_cast<const float4*>(p.resid + off);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 r = r4[j];
+          f[4 * j] += r.x; f[4 * j + 1] += r.y; f[4 * j + 2] += r.z; f[4 * j + 3] += r.w;
+        }
+      }
+      if (p.out_bf16) {
+        uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C) + off);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          __nv_bfloat162 h0 = __floats2bfloat162_rn(f[8 * j], f[8 * j + 1]);
+          __nv_bfloat162 h1 = __floats2bfloat162_rn(f[8 * j + 2], f[8 * j + 3]);
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(f[8 * j + 4], f[8 * j + 5]);
+          __nv_bfloat162 h3 = __floats2bfloat162_rn(f[8 * j + 6], f[8 * j + 7]);
+          uint4 u;
+          u.x = *reinterpret_cast<uint32_t*>(&h0);
+          u.y = *reinterpret_cast<uint32_t*>(&h1);
+          u.z = *reinterpret_cast<uint32_t*>(&h2);
+          u.w = *reinterpret_cast<uint32_t*>(&h3);
+          o[j] = u;
+        }
+      } else {
+        float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + off);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc),
+                 "n"(tmem_cols(BN)));
+  }
+}
+
+// ------------------------------------------------------------------------------------- host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// 2-D bf16 row-major [rows][K] tensor, box = 64 (K) x box_rows, 128B swizzle, zero OOB fill.
+int make_map(CUtensorMap* map, const void* ptr, int rows, int K, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
+    return WMK_ERR_CUDA;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box,
+                  es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) for [%d][%d] box %d", (int)r, rows, K, box_rows);
+    return WMK_ERR_CUDA;
+  }
+  return 0;
+}
+
+template <int BN>
+int launch(const GemmArgs& g, cudaStream_t st) {
+  CUtensorMap tmA, tmW;
+  WMK_TRY(make_map(&tmA, g.A, g.M, g.K, BM));
+  WMK_TRY(make_map(&tmW, g.W, g.N, g.K, BN));
+  const int kblocks = cdiv(g.K, BK);
+  constexpr int stage = (BM + BN) * BK * 2;
+  int n_stages = kblocks < 4 ? kblocks : 4;
+  while (n_stages > 2 && n_stages * stage > 96 * 1024) --n_stages;   // keep >= 2 CTAs per SM
+  const size_t smem = (size_t)n_stages * stage + 1024 /*align*/ + 16 * n_stages + 16;
+  static bool attr_set = false;
+  if (!attr_set) {
+    WMK_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        200 * 1024));
+    attr_set = true;
+  }
+  EpiParams p{g.bias, g.resid, g.C, g.M, g.N, g.ldc, g.epi, g.out_bf16, g.up_h, g.up_w, g.up_cout};
+  const int n_tiles = g.N / BN;
+  const long long grid = (long long)cdiv(g.M, BM) * n_tiles;
+  gemm_tcgen05_kernel<BN><<<(unsigned)grid, kThreads, smem, st>>>(tmA, tmW, p, g.K, n_tiles, n_stages);
+  WMK_CHECK_LAUNCH("gemm_tcgen05_kernel");
+  return 0;
+}
+
+}  // namespace
+
+int gemm_bf16_tcgen05(const GemmArgs& g, cudaStream_t st) {
+  WMK_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0, "gemm: empty problem %dx%dx%d", g.M, g.N, g.K);
+  WMK_REQUIRE(g.K % 8 == 0, "gemm_bf16: K=%d must be a multiple of 8 (16-byte TMA rows)", g.K);
+  WMK_REQUIRE(g.N % 32 == 0, "gemm_bf16: N=%d must be a multiple of 32", g.N);
+  WMK_REQUIRE(((uintptr_t)g.A & 15) == 0 && ((uintptr_t)g.W & 15) == 0 && ((uintptr_t)g.C & 15) == 0,
+              "gemm_bf16: operands must be 16-byte aligned");
+  WMK_REQUIRE(g.ldc % 8 == 0, "gemm_bf16: ldc=%d must be a multiple of 8", g.ldc);
+  if (g.epi == EPI_UPSAMPLE)
+    WMK_REQUIRE(g.up_cout % 32 == 0 && g.N == 4 * g.up_cout && g.M % (g.up_h * g.up_w) == 0,
+                "gemm_bf16: bad upsample geometry");
+  if (g.N % 128 == 0) return launch<128>(g, st);
+  if (g.N % 96 == 0) return launch<96>(g, st);
+  if (g.N % 64 == 0) return launch<64>(g, st);
+  return launch<32>(g, st);
+}
+
+}  // namespace wmk

@@ -1,0 +1,246 @@
+// Small direct kernels around the LeWin stacks: 3x3 projections, the image codec, pooling heads.
+// Each is a few MFLOP per clip; they exist so that no host round trip or PyTorch op sits inside
+// the embed / extract pass.
+#pragma once
+#include "uformer_kernels.cuh"
+
+namespace wmk {
+
+// InputProj (uformerWM/model.py:813-816,824-826): Conv2d(2,32,3,p=1) + LeakyReLU(0.01),
+// NCHW [B][2][128][128] in -> token layout [B*16384][32] out.  One thread per pixel.
+__global__ void __launch_bounds__(128)
+input_proj_kernel(const float* __restrict__ x, float* __restrict__ out, const float* __restrict__ w,
+                  const float* __restrict__ bias, int B) {
+  __shared__ float ws[32 * 18];
+  __shared__ float bs[32];
+  for (int i = threadIdx.x; i < 576; i += blockDim.x) ws[i] = w[i];
+  if (threadIdx.x < 32) bs[threadIdx.x] = bias[threadIdx.x];
+  __syncthreads();
+  const size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= (size_t)B * 16384) return;
+  const int wq = (int)(pix & 127), h = (int)((pix >> 7) & 127);
+  const size_t b = pix >> 14;
+  float in[18];
+#pragma unroll
+  for (int c = 0; c < 2; ++c)
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const int hh = h + dy - 1, wwp = wq + dx - 1;
+        in[c * 9 + dy * 3 + dx] =
+            (hh >= 0 && hh < 128 && wwp >= 0 && wwp < 128) ? x[((b * 2 + c) * 128 + hh) * 128 + wwp] : 0.f;
+      }
+  float4* o = reinterpret_cast<float4*>(out + pix * 32);
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    float r[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int co = g * 4 + j;
+      float a = bs[co];
+#pragma unroll
+      for (int t = 0; t < 18; ++t) a = fmaf(in[t], ws[co * 18 + t], a);
+      r[j] = a > 0.f ? a : 0.01f * a;
+    }
+    o[g] = make_float4(r[0], r[1], r[2], r[3]);
+  }
+}
+
+// OutputProj (uformerWM/model.py:845-847,857-862) Conv2d(64,2,3,p=1) on the token-layout decoder
+// output + the residual y = x + noise (model.py:2419-2421).  One warp per pixel.
+__global__ void __launch_bounds__(256)
+output_proj_kernel(const float* __restrict__ tokens, const float* __restrict__ x, float* __restrict__ noise,
+                   float* __restrict__ y, const float* __restrict__ w, const float* __restrict__ bias, int B) {
+  __shared__ float ws[9 * 2 * 64];          // [tap][o][c]
+  for (int i = threadIdx.x; i < 1152; i += blockDim.x) {
+    const int tap = i / 128, o = (i / 64) & 1, c = i & 63;
+    ws[i] = w[(o * 64 + c) * 9 + tap];
+  }
+  __syncthreads();
+  const size_t pix = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (pix >= (size_t)B * 16384) return;
+  const int wq = (int)(pix & 127), h = (int)((pix >> 7) & 127);
+  const size_t b = pix >> 14;
+  float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+  for (int dy = 0; dy < 3; ++dy) {
+    const int hh = h + dy - 1;
+    if (hh < 0 || hh >= 128) continue;
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx) {
+      const int wwp = wq + dx - 1;
+      if (wwp < 0 || wwp >= 128) continue;
+      const float2 v = *reinterpret_cast<const float2*>(tokens + ((b * 128 + hh) * 128 + wwp) * 64 + 2 * lane);
+      const float* wt = ws + (dy * 3 + dx) * 128 + 2 * lane;
+      a0 = fmaf(v.x, wt[0], fmaf(v.y, wt[1], a0));
+      a1 = fmaf(v.x, wt[64], fmaf(v.y, wt[65], a1));
+    }
+  }
+  a0 = warp_sum(a0);
+  a1 = warp_sum(a1);
+  if (lane < 2) {
+    const float n = (lane == 0 ? a0 : a1) + bias[lane];
+    const size_t o = ((b * 2 + lane) * 128 + h) * 128 + wq;
+    if (noise) noise[o] = n;
+    y[o] = x[o] + n;
+  }
+}
+
+// Generic tiny NCHW 3x3 conv (pad 1) on 128x128 maps: stft_layer (uformerWM/model.py:2305-2309).
+template <int CIN, int COUT, bool RELU>
+__global__ void __launch_bounds__(256)
+conv3x3_nchw_kernel(const float* __restrict__ in, float* __restrict__ out, const float* __restrict__ w,
+                    const float* __restrict__ bias, int B) {
+  __shared__ float ws[COUT * CIN * 9];
+  __shared__ float bs[COUT];
+  for (int i = threadIdx.x; i < COUT * CIN * 9; i += blockDim.x) ws[i] = w[i];
+  if (threadIdx.x < COUT) bs[threadIdx.x] = bias[threadIdx.x];
+  __syncthreads();
+  const size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= (size_t)B * 16384) return;
+  const int wq = (int)(pix & 127), h = (int)((pix >> 7) & 127);
+  const size_t b = pix >> 14;
+  float v[CIN * 9];
+#pragma unroll
+  for (int c = 0; c < CIN; ++c)
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const int hh = h + dy - 1, wwp = wq + dx - 1;
+        v[c * 9 + dy * 3 + dx] =
+            (hh >= 0 && hh < 128 && wwp >= 0 && wwp < 128) ? in[((b * CIN + c) * 128 + hh) * 128 + wwp] : 0.f;
+      }
+#pragma unroll
+  for (int co = 0; co < COUT; ++co) {
+    float a = bs[co];
+#pragma unroll
+    for (int t = 0; t < CIN * 9; ++t) a = fmaf(v[t], ws[co * CIN * 9 + t], a);
+    if (RELU) a = fmaxf(a, 0.f);
+    out[((b * COUT + co) * 128 + h) * 128 + wq] = a;
+  }
+}
+
+// ConvAutoencoder.encode (uformerWM/model.py:1720-1726): [1][32][32] -> [4][8][8]; one CTA per image.
+// msg_stride = 0 broadcasts one image to every clip.
+__global__ void __launch_bounds__(256)
+wm_encode_kernel(const float* __restrict__ msg, int msg_stride, float* __restrict__ feat,
+                 const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
+                 const float* __restrict__ b2) {
+  __shared__ float img[34][34];
+  __shared__ float hid[16][18][18];        // pooled conv1 output with a zero border
+  __shared__ float sw1[16 * 9], sb1[16], sw2[4 * 16 * 9], sb2[4];
+  const float* m = msg + (size_t)blockIdx.x * msg_stride;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 34 * 34; i += 256) {
+    const int r = i / 34 - 1, c = i % 34 - 1;
+    img[i / 34][i % 34] = (r >= 0 && r < 32 && c >= 0 && c < 32) ? m[r * 32 + c] : 0.f;
+  }
+  for (int i = tid; i < 16 * 18 * 18; i += 256) (&hid[0][0][0])[i] = 0.f;
+  for (int i = tid; i < 144; i += 256) sw1[i] = w1[i];
+  for (int i = tid; i < 576; i += 256) sw2[i] = w2[i];
+  if (tid < 16) sb1[tid] = b1[tid];
+  if (tid < 4) sb2[tid] = b2[tid];
+  __syncthreads();
+  for (int i = tid; i < 16 * 256; i += 256) {
+    const int co = i >> 8, ph = (i >> 4) & 15, pw = i & 15;
+    float best = -INFINITY;
+    for (int sy = 0; sy < 2; ++sy)
+      for (int sx = 0; sx < 2; ++sx) {
+        const int r = 2 * ph + sy, c = 2 * pw + sx;
+        float a = sb1[co];
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) a = fmaf(img[r + dy][c + dx], sw1[co * 9 + dy * 3 + dx], a);
+        best = fmaxf(best, a);
+      }
+    hid[co][ph + 1][pw + 1] = fmaxf(best, 0.f);
+  }
+  __syncthreads();
+  {
+    const int co = tid >> 6, ph = (tid >> 3) & 7, pw = tid & 7;
+    float best = -INFINITY;
+    for (int sy = 0; sy < 2; ++sy)
+      for (int sx = 0; sx < 2; ++sx) {
+        const int r = 2 * ph + sy, c = 2 * pw + sx;
+        float a = sb2[co];
+        for (int ci = 0; ci < 16; ++ci)
+#pragma unroll
+          for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx)
+              a = fmaf(hid[ci][r + dy][c + dx], sw2[(co * 16 + ci) * 9 + dy * 3 + dx], a);
+        best = fmaxf(best, a);
+      }
+    feat[(size_t)blockIdx.x * 256 + tid] = fmaxf(best, 0.f);
+  }
+}
+
+// ConvAutoencoder.decode (uformerWM/model.py:1711-1718) on feat (+ optional addend, the
+// `feature_wm_ori + conv4_downsample` of model.py:2403): [4][8][8] -> logits / sigmoid [32][32].
+__global__ void __launch_bounds__(256)
+wm_decode_kernel(const float* __restrict__ feat, const float* __restrict__ addend, float* __restrict__ wm,
+                 float* __restrict__ logits, const float* __restrict__ w1, const float* __restrict__ b1,
+                 const float* __restrict__ w2, const float* __restrict__ b2) {
+  __shared__ float f[4][8][8];
+  __shared__ float hid[16][16][16];
+  __shared__ float sw1[4 * 16 * 4], sb1[16], sw2[16 * 4];
+  const int tid = threadIdx.x;
+  const size_t b = blockIdx.x;
+  (&f[0][0][0])[tid] = feat[b * 256 + tid] + (addend ? addend[b * 256 + tid] : 0.f);
+  sw1[tid] = w1[tid];                       // [ci][co][i][j]
+  if (tid < 16) sb1[tid] = b1[tid];
+  if (tid < 64) sw2[tid] = w2[tid];         // [ci][0][i][j]
+  __syncthreads();
+  for (int e = tid; e < 4096; e += 256) {
+    const int co = e >> 8, r = (e >> 4) & 15, c = e & 15;
+    float a = sb1[co];
+#pragma unroll
+    for (int ci = 0; ci < 4; ++ci) a = fmaf(f[ci][r >> 1][c >> 1], sw1[((ci * 16 + co) * 2 + (r & 1)) * 2 + (c & 1)], a);
+    hid[co][r][c] = fmaxf(a, 0.f);
+  }
+  __syncthreads();
+  const float bias2 = b2[0];
+  for (int e = tid; e < 1024; e += 256) {
+    const int r = e >> 5, c = e & 31;
+    float a = bias2;
+#pragma unroll
+    for (int ci = 0; ci < 16; ++ci) a = fmaf(hid[ci][r >> 1][c >> 1], sw2[(ci * 2 + (r & 1)) * 2 + (c & 1)], a);
+    if (logits) logits[b * 1024 + e] = a;
+    if (wm) wm[b * 1024 + e] = 1.0f / (1.0f + expf(-a));
+  }
+}
+
+// MaxPool2d((16,8)) over the bottleneck token matrix [B][64][512] -> [B][4][64]
+// (uformerWM/model.py:2250,2398-2400).
+__global__ void __launch_bounds__(256)
+bottleneck_maxpool_kernel(const float* __restrict__ conv4, float* __restrict__ out, int B) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)B * 256) return;
+  const int j = (int)(idx & 63), i = (int)((idx >> 6) & 3);
+  const size_t b = idx >> 8;
+  float best = -INFINITY;
+  for (int r = 0; r < 16; ++r)
+    for (int c = 0; c < 8; ++c) best = fmaxf(best, conv4[(b * 64 + 16 * i + r) * 512 + 8 * j + c]);
+  out[idx] = best;
+}
+
+// EncoderTransformerWM.conv2 = Conv2d(1,1,8,stride=(16,8)) over [B][1][64][512] -> [B][4][64]
+// (uformerWM/model.py:1566,1580-1582).
+__global__ void __launch_bounds__(256)
+extract_head_kernel(const float* __restrict__ conv4, float* __restrict__ out, const float* __restrict__ w,
+                    const float* __restrict__ bias, int B) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)B * 256) return;
+  const int j = (int)(idx & 63), i = (int)((idx >> 6) & 3);
+  const size_t b = idx >> 8;
+  float a = bias[0];
+  for (int u = 0; u < 8; ++u)
+    for (int v = 0; v < 8; ++v) a = fmaf(conv4[(b * 64 + 16 * i + u) * 512 + 8 * j + v], __ldg(w + u * 8 + v), a);
+  out[idx] = a;
+}
+
+}  // namespace wmk

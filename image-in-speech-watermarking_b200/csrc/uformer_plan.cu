@@ -1,0 +1,573 @@
+// UformerAudio embedder / extractor executor (uformerWM/model.py:2225-2511, configuration
+// uformerWM/utils/model_utils.py:83-85): weight packing + the launch sequence of one pass.
+//
+// Data layout in HBM (per pass of `chunk` clips):
+//   residual streams E0..E4 (encoder stages / skips) and D0..D3 (decoder stages): fp32
+//   [clips*tokens][C]; operand buffers bufA (LayerNorm out), bufQKV, bufO (attention out),
+//   bufH1 / bufH2 (LeFF hidden, 4C wide): OpT = fp32 or bf16, reused by every block.
+// Weights are packed once: every nn.Linear / conv-as-GEMM weight as a K-major [N][K] matrix in
+// OpT, q/k/v fused into one [3C][C] matrix with the attention scale folded into the q rows, the
+// relative-position bias gathered to [heads][64][64], depthwise weights tap-major.
+#include <map>
+#include <string>
+#include <vector>
+
+#include "small_kernels.cuh"
+
+namespace wmk {
+
+int stft_clips(const float* wave, int B, int L, float* clips, int n_clips, cudaStream_t st);
+int istft_clips(const float* clips, int B, int n_clips, int T, float* wave, int length, cudaStream_t st);
+
+namespace {
+
+const int kDepths[9] = {1, 2, 8, 8, 2, 8, 8, 2, 1};
+const int kHeads[9] = {1, 2, 4, 8, 16, 16, 8, 4, 2};
+
+struct HostTensor {
+  std::vector<float> data;
+  std::vector<int64_t> shape;
+};
+
+struct BlockW {
+  int C = 0, heads = 0, H = 0, shift = 0;
+  float *ln1_w = nullptr, *ln1_b = nullptr, *ln2_w = nullptr, *ln2_b = nullptr, *mod = nullptr;
+  float* attn_bias = nullptr;
+  void *w_qkv = nullptr, *w_proj = nullptr, *w_l1 = nullptr, *w_l2 = nullptr;
+  float *b_qkv = nullptr, *b_proj = nullptr, *b_l1 = nullptr, *b_l2 = nullptr, *dw_w = nullptr, *dw_b = nullptr;
+};
+
+struct EncW {
+  float *in_w = nullptr, *in_b = nullptr;
+  std::vector<BlockW> stage[5];
+  void* down_w[4] = {};
+  float* down_b[4] = {};
+};
+
+}  // namespace
+}  // namespace wmk
+
+using namespace wmk;
+
+struct wmk_plan {
+  int precision = WMK_PREC_FP32;
+  bool finalized = false;
+  int chunk = 32;
+  int device = 0;
+  std::map<std::string, HostTensor> host;
+  std::vector<void*> allocs;      // weights
+  std::vector<void*> ws_allocs;   // workspace
+  size_t ws_bytes = 0;
+
+  EncW enc, ext;
+  std::vector<BlockW> dec[4];
+  void* up_w[4] = {};
+  float* up_b[4] = {};
+  float *out_w = nullptr, *out_b = nullptr;
+  float *codec_c1w = nullptr, *codec_c1b = nullptr, *codec_c2w = nullptr, *codec_c2b = nullptr;
+  float *codec_t1w = nullptr, *codec_t1b = nullptr, *codec_t2w = nullptr, *codec_t2b = nullptr;
+  float *head_w = nullptr, *head_b = nullptr;
+  float *sl0_w = nullptr, *sl0_b = nullptr, *sl2_w = nullptr, *sl2_b = nullptr;
+
+  // workspace
+  float *E[5] = {}, *D[4] = {};
+  void *bufA = nullptr, *bufQKV = nullptr, *bufO = nullptr, *bufH1 = nullptr, *bufH2 = nullptr;
+  float *feat = nullptr, *pool = nullptr, *headout = nullptr, *ybuf = nullptr, *wavebuf = nullptr, *rt = nullptr,
+        *rt2 = nullptr;
+  bool ws_ready = false;
+
+  bool taps_on = false;
+  std::map<std::string, std::pair<float*, size_t>> taps;
+
+  size_t op_size() const { return precision == WMK_PREC_BF16 ? 2 : 4; }
+};
+
+namespace wmk {
+namespace {
+
+// ------------------------------------------------------------------------------------ packing
+int upload_f32(wmk_plan* P, const std::vector<float>& v, float** out) {
+  float* d = nullptr;
+  if (cudaMalloc(&d, v.size() * 4) != cudaSuccess) { set_error("cudaMalloc of %zu bytes failed", v.size() * 4); return WMK_ERR_ALLOC; }
+  P->allocs.push_back(d);
+  WMK_CHECK_CUDA(cudaMemcpy(d, v.data(), v.size() * 4, cudaMemcpyHostToDevice));
+  *out = d;
+  return 0;
+}
+
+int upload_op(wmk_plan* P, const std::vector<float>& v, void** out) {
+  if (P->precision == WMK_PREC_FP32) return upload_f32(P, v, reinterpret_cast<float**>(out));
+  std::vector<__nv_bfloat16> h(v.size());
+  for (size_t i = 0; i < v.size(); ++i) h[i] = __float2bfloat16(v[i]);
+  void* d = nullptr;
+  if (cudaMalloc(&d, h.size() * 2) != cudaSuccess) { set_error("cudaMalloc of %zu bytes failed", h.size() * 2); return WMK_ERR_ALLOC; }
+  P->allocs.push_back(d);
+  WMK_CHECK_CUDA(cudaMemcpy(d, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
+  *out = d;
+  return 0;
+}
+
+int get(wmk_plan* P, const std::string& name, size_t numel, const HostTensor** out) {
+  auto it = P->host.find(name);
+  if (it == P->host.end()) { set_error("plan: missing tensor '%s'", name.c_str()); return WMK_ERR_STATE; }
+  if (it->second.data.size() != numel) {
+    set_error("plan: tensor '%s' has %zu elements, expected %zu", name.c_str(), it->second.data.size(), numel);
+    return WMK_ERR_STATE;
+  }
+  *out = &it->second;
+  return 0;
+}
+
+int get_f32(wmk_plan* P, const std::string& name, size_t numel, float** dev) {
+  const HostTensor* t;
+  WMK_TRY(get(P, name, numel, &t));
+  return upload_f32(P, t->data, dev);
+}
+
+int pack_block(wmk_plan* P, const std::string& p, int C, int heads, int H, int shift, bool mod, BlockW* w) {
+  w->C = C; w->heads = heads; w->H = H;
+  w->shift = (H <= 8) ? 0 : shift;                                    // model.py:892-894
+  WMK_TRY(get_f32(P, p + "norm1.weight", C, &w->ln1_w));
+  WMK_TRY(get_f32(P, p + "norm1.bias", C, &w->ln1_b));
+  WMK_TRY(get_f32(P, p + "norm2.weight", C, &w->ln2_w));
+  WMK_TRY(get_f32(P, p + "norm2.bias", C, &w->ln2_b));
+  if (mod) WMK_TRY(get_f32(P, p + "modulator.weight", 64 * (size_t)C, &w->mod));
+  const HostTensor *tab, *wq, *bq, *wkv, *bkv, *dw;
+  WMK_TRY(get(P, p + "attn.relative_position_bias_table", 225 * (size_t)heads, &tab));
+  std::vector<float> bias((size_t)heads * 4096);
+  for (int h = 0; h < heads; ++h)
+    for (int i = 0; i < 64; ++i)
+      for (int j = 0; j < 64; ++j) {
+        const int idx = ((i >> 3) - (j >> 3) + 7) * 15 + ((i & 7) - (j & 7) + 7);      // model.py:496-505
+        bias[((size_t)h * 64 + i) * 64 + j] = tab->data[(size_t)idx * heads + h];
+      }
+  WMK_TRY(upload_f32(P, bias, &w->attn_bias));
+  WMK_TRY(get(P, p + "attn.qkv.to_q.weight", (size_t)C * C, &wq));
+  WMK_TRY(get(P, p + "attn.qkv.to_q.bias", C, &bq));
+  WMK_TRY(get(P, p + "attn.qkv.to_kv.weight", 2 * (size_t)C * C, &wkv));
+  WMK_TRY(get(P, p + "attn.qkv.to_kv.bias", 2 * (size_t)C, &bkv));
+  const float scale = 1.0f / sqrtf((float)(C / heads));              // model.py:489,526
+  std::vector<float> wqkv(3 * (size_t)C * C), bqkv(3 * (size_t)C);
+  for (size_t i = 0; i < (size_t)C * C; ++i) wqkv[i] = wq->data[i] * scale;
+  for (size_t i = 0; i < 2 * (size_t)C * C; ++i) wqkv[(size_t)C * C + i] = wkv->data[i];
+  for (int i = 0; i < C; ++i) bqkv[i] = bq->data[i] * scale;
+  for (int i = 0; i < 2 * C; ++i) bqkv[C + i] = bkv->data[i];
+  WMK_TRY(upload_op(P, wqkv, &w->w_qkv));
+  WMK_TRY(upload_f32(P, bqkv, &w->b_qkv));
+  const HostTensor* t;
+  WMK_TRY(get(P, p + "attn.proj.weight", (size_t)C * C, &t));
+  WMK_TRY(upload_op(P, t->data, &w->w_proj));
+  WMK_TRY(get_f32(P, p + "attn.proj.bias", C, &w->b_proj));
+  WMK_TRY(get(P, p + "mlp.linear1.0.weight", 4 * (size_t)C * C, &t));
+  WMK_TRY(upload_op(P, t->data, &w->w_l1));
+  WMK_TRY(get_f32(P, p + "mlp.linear1.0.bias", 4 * (size_t)C, &w->b_l1));
+  WMK_TRY(get(P, p + "mlp.linear2.0.weight", 4 * (size_t)C * C, &t));
+  WMK_TRY(upload_op(P, t->data, &w->w_l2));
+  WMK_TRY(get_f32(P, p + "mlp.linear2.0.bias", C, &w->b_l2));
+  WMK_TRY(get(P, p + "mlp.dwconv.0.weight", 36 * (size_t)C, &dw));
+  std::vector<float> dwt(36 * (size_t)C);
+  for (int c = 0; c < 4 * C; ++c)
+    for (int tap = 0; tap < 9; ++tap) dwt[(size_t)tap * 4 * C + c] = dw->data[(size_t)c * 9 + tap];
+  WMK_TRY(upload_f32(P, dwt, &w->dw_w));
+  WMK_TRY(get_f32(P, p + "mlp.dwconv.0.bias", 4 * (size_t)C, &w->dw_b));
+  return 0;
+}
+
+int pack_encoder(wmk_plan* P, const std::string& p, const std::string& inproj, EncW* e) {
+  WMK_TRY(get_f32(P, inproj + "proj.0.weight", 32 * 2 * 9, &e->in_w));
+  WMK_TRY(get_f32(P, inproj + "proj.0.bias", 32, &e->in_b));
+  for (int s = 0; s < 5; ++s) {
+    const int C = 32 << s, H = 128 >> s;
+    e->stage[s].resize(kDepths[s]);
+    for (int i = 0; i < kDepths[s]; ++i) {
+      const std::string bp = p + (s < 4 ? "encoderlayer_" + std::to_string(s) : std::string("conv")) + ".blocks." +
+                             std::to_string(i) + ".";
+      WMK_TRY(pack_block(P, bp, C, kHeads[s], H, (i % 2) ? 4 : 0, false, &e->stage[s][i]));
+    }
+    if (s < 4) {
+      const HostTensor* t;
+      const std::string dp = p + "dowsample_" + std::to_string(s) + ".conv.0.";
+      WMK_TRY(get(P, dp + "weight", (size_t)2 * C * C * 16, &t));
+      std::vector<float> g((size_t)2 * C * 16 * C);                   // [co][(kh,kw,ci)]
+      for (int co = 0; co < 2 * C; ++co)
+        for (int ci = 0; ci < C; ++ci)
+          for (int tap = 0; tap < 16; ++tap)
+            g[((size_t)co * 16 + tap) * C + ci] = t->data[((size_t)co * C + ci) * 16 + tap];
+      WMK_TRY(upload_op(P, g, &e->down_w[s]));
+      WMK_TRY(get_f32(P, dp + "bias", 2 * (size_t)C, &e->down_b[s]));
+    }
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------ workspace
+template <typename T>
+int ws_alloc(wmk_plan* P, T** p, size_t bytes) {
+  void* d = nullptr;
+  if (cudaMalloc(&d, bytes) != cudaSuccess) { set_error("workspace cudaMalloc of %zu bytes failed", bytes); return WMK_ERR_ALLOC; }
+  P->ws_allocs.push_back(d);
+  P->ws_bytes += bytes;
+  *p = reinterpret_cast<T*>(d);
+  return 0;
+}
+
+int ensure_workspace(wmk_plan* P) {
+  if (P->ws_ready) return 0;
+  const size_t n = (size_t)P->chunk, os = P->op_size();
+  for (int s = 0; s < 5; ++s) WMK_TRY(ws_alloc(P, &P->E[s], n * (16384 >> (2 * s)) * (32 << s) * 4));
+  for (int s = 0; s < 4; ++s) WMK_TRY(ws_alloc(P, &P->D[s], n * (256 << (2 * s)) * (512 >> s) * 4));
+  const size_t tokC = 16384 * 64;           // widest stage: decoder stage 3 (C = 64 at 128x128)
+  WMK_TRY(ws_alloc(P, &P->bufA, n * tokC * os));
+  WMK_TRY(ws_alloc(P, &P->bufQKV, n * tokC * 3 * os));
+  WMK_TRY(ws_alloc(P, &P->bufO, n * tokC * os));
+  WMK_TRY(ws_alloc(P, &P->bufH1, n * tokC * 4 * os));
+  WMK_TRY(ws_alloc(P, &P->bufH2, n * tokC * 4 * os));
+  WMK_TRY(ws_alloc(P, &P->feat, n * 256 * 4));
+  WMK_TRY(ws_alloc(P, &P->pool, n * 256 * 4));
+  WMK_TRY(ws_alloc(P, &P->headout, n * 256 * 4));
+  WMK_TRY(ws_alloc(P, &P->ybuf, n * 32768 * 4));
+  WMK_TRY(ws_alloc(P, &P->wavebuf, n * 8002 * 4));
+  WMK_TRY(ws_alloc(P, &P->rt, n * 32768 * 4));
+  WMK_TRY(ws_alloc(P, &P->rt2, n * 65536 * 4));
+  P->ws_ready = true;
+  return 0;
+}
+
+int tap(wmk_plan* P, const std::string& name, const float* src, size_t n, cudaStream_t st) {
+  if (!P->taps_on) return 0;
+  auto& slot = P->taps[name];
+  if (slot.first && slot.second != n) { cudaFree(slot.first); slot.first = nullptr; }
+  if (!slot.first) WMK_CHECK_CUDA(cudaMalloc(&slot.first, n * 4));
+  slot.second = n;
+  WMK_CHECK_CUDA(cudaMemcpyAsync(slot.first, src, n * 4, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------ execution
+int gemm(wmk_plan* P, const GemmArgs& g, cudaStream_t st) {
+  return P->precision == WMK_PREC_BF16 ? gemm_bf16_tcgen05(g, st) : gemm_fp32_simt(g, st);
+}
+
+template <typename OpT>
+int run_block(wmk_plan* P, const BlockW& w, float* x, int n, cudaStream_t st) {
+  const int C = w.C, H = w.H;
+  const int M = n * H * H;
+  const int ob = sizeof(OpT) == 2;
+  OpT* A = reinterpret_cast<OpT*>(P->bufA);
+  OpT* QKV = reinterpret_cast<OpT*>(P->bufQKV);
+  OpT* O = reinterpret_cast<OpT*>(P->bufO);
+  OpT* H1 = reinterpret_cast<OpT*>(P->bufH1);
+  OpT* H2 = reinterpret_cast<OpT*>(P->bufH2);
+  layernorm_kernel<OpT><<<cdiv(M, 8), 256, 0, st>>>(x, A, w.ln1_w, w.ln1_b, w.mod, M, C, H, w.shift);
+  WMK_CHECK_LAUNCH("layernorm_kernel");
+  GemmArgs g;
+  g.A = A; g.W = w.w_qkv; g.bias = w.b_qkv; g.C = QKV; g.M = M; g.N = 3 * C; g.K = C; g.ldc = 3 * C;
+  g.epi = EPI_BIAS; g.out_bf16 = ob;
+  WMK_TRY(gemm(P, g, st));
+  window_attention_kernel<OpT><<<dim3(n * (H / 8) * (H / 8), w.heads), 128, 0, st>>>(QKV, O, w.attn_bias, C, H, w.shift);
+  WMK_CHECK_LAUNCH("window_attention_kernel");
+  g = GemmArgs();
+  g.A = O; g.W = w.w_proj; g.bias = w.b_proj; g.resid = x; g.C = x; g.M = M; g.N = C; g.K = C; g.ldc = C;
+  g.epi = EPI_BIAS_RESID; g.out_bf16 = 0;
+  WMK_TRY(gemm(P, g, st));
+  layernorm_kernel<OpT><<<cdiv(M, 8), 256, 0, st>>>(x, A, w.ln2_w, w.ln2_b, nullptr, M, C, H, 0);
+  WMK_CHECK_LAUNCH("layernorm_kernel");
+  g = GemmArgs();
+  g.A = A; g.W = w.w_l1; g.bias = w.b_l1; g.C = H1; g.M = M; g.N = 4 * C; g.K = C; g.ldc = 4 * C;
+  g.epi = EPI_BIAS_GELU; g.out_bf16 = ob;
+  WMK_TRY(gemm(P, g, st));
+  {
+    const size_t total = (size_t)M * C;     // (4C / 4) channel groups per pixel
+    dwconv3x3_gelu_kernel<OpT><<<cdiv(total, 256), 256, 0, st>>>(H1, H2, w.dw_w, w.dw_b, n, H, 4 * C);
+    WMK_CHECK_LAUNCH("dwconv3x3_gelu_kernel");
+  }
+  g = GemmArgs();
+  g.A = H2; g.W = w.w_l2; g.bias = w.b_l2; g.resid = x; g.C = x; g.M = M; g.N = C; g.K = 4 * C; g.ldc = C;
+  g.epi = EPI_BIAS_RESID; g.out_bf16 = 0;
+  WMK_TRY(gemm(P, g, st));
+  return 0;
+}
+
+// Encoder / EncoderTransformerWM stages (model.py:1381-1394, 1569-1579): x NCHW -> E[0..4].
+template <typename OpT>
+int run_encoder(wmk_plan* P, const EncW& e, const float* x_nchw, int n, const char* tag, cudaStream_t st) {
+  input_proj_kernel<<<cdiv((size_t)n * 16384, 128), 128, 0, st>>>(x_nchw, P->E[0], e.in_w, e.in_b, n);
+  WMK_CHECK_LAUNCH("input_proj_kernel");
+  const std::string t(tag);
+  if (t == "enc") WMK_TRY(tap(P, "emb.inproj", P->E[0], (size_t)n * 16384 * 32, st));
+  for (int s = 0; s < 5; ++s) {
+    const int C = 32 << s, H = 128 >> s;
+    for (const BlockW& b : e.stage[s]) WMK_TRY(run_block<OpT>(P, b, P->E[s], n, st));
+    WMK_TRY(tap(P, t + ".conv" + std::to_string(s), P->E[s], (size_t)n * H * H * C, st));
+    if (s == 4) break;
+    const int Ho = H / 2;
+    OpT* col = reinterpret_cast<OpT*>(P->bufH1);
+    const size_t total = (size_t)n * Ho * Ho * 16 * (C / 4);
+    im2col_4x4s2_kernel<OpT><<<cdiv(total, 256), 256, 0, st>>>(P->E[s], col, n, H, C);
+    WMK_CHECK_LAUNCH("im2col_4x4s2_kernel");
+    GemmArgs g;
+    g.A = col; g.W = e.down_w[s]; g.bias = e.down_b[s]; g.C = P->E[s + 1]; g.M = n * Ho * Ho; g.N = 2 * C;
+    g.K = 16 * C; g.ldc = 2 * C; g.epi = EPI_BIAS; g.out_bf16 = 0;
+    WMK_TRY(gemm(P, g, st));
+    WMK_TRY(tap(P, t + ".pool" + std::to_string(s), P->E[s + 1], (size_t)n * Ho * Ho * 2 * C, st));
+  }
+  return 0;
+}
+
+template <typename OpT>
+int run_extract(wmk_plan* P, const float* y, int n, float* wm, float* logits, cudaStream_t st) {
+  WMK_TRY(run_encoder<OpT>(P, P->ext, y, n, "ext", st));
+  extract_head_kernel<<<cdiv((size_t)n * 256, 256), 256, 0, st>>>(P->E[4], P->headout, P->head_w, P->head_b, n);
+  WMK_CHECK_LAUNCH("extract_head_kernel");
+  WMK_TRY(tap(P, "ext.feat", P->headout, (size_t)n * 256, st));
+  wm_decode_kernel<<<n, 256, 0, st>>>(P->headout, nullptr, wm, logits, P->codec_t1w, P->codec_t1b, P->codec_t2w,
+                                      P->codec_t2b);
+  WMK_CHECK_LAUNCH("wm_decode_kernel");
+  return 0;
+}
+
+template <typename OpT>
+int run_forward(wmk_plan* P, const float* x, const float* msg, int msg_stride, int n, float* stft_new, float* noise,
+                float* y_out, float* wm_pred, float* wm, float* wm_logits, cudaStream_t st) {
+  const int ob = sizeof(OpT) == 2;
+  wm_encode_kernel<<<n, 256, 0, st>>>(msg, msg_stride, P->feat, P->codec_c1w, P->codec_c1b, P->codec_c2w, P->codec_c2b);
+  WMK_CHECK_LAUNCH("wm_encode_kernel");
+  WMK_TRY(run_encoder<OpT>(P, P->enc, x, n, "enc", st));
+  if (wm_pred) {
+    bottleneck_maxpool_kernel<<<cdiv((size_t)n * 256, 256), 256, 0, st>>>(P->E[4], P->pool, n);
+    WMK_CHECK_LAUNCH("bottleneck_maxpool_kernel");
+    wm_decode_kernel<<<n, 256, 0, st>>>(P->feat, P->pool, wm_pred, nullptr, P->codec_t1w, P->codec_t1b, P->codec_t2w,
+                                        P->codec_t2b);
+    WMK_CHECK_LAUNCH("wm_decode_kernel");
+  }
+  // decoder (model.py:1221-1240)
+  OpT* A = reinterpret_cast<OpT*>(P->bufH1);
+  bottleneck_concat_kernel<OpT><<<cdiv((size_t)n * 65536, 256), 256, 0, st>>>(P->feat, P->E[4], A, n);
+  WMK_CHECK_LAUNCH("bottleneck_concat_kernel");
+  for (int s = 0; s < 4; ++s) {
+    const int Hin = 8 << s, Cin = (s == 0) ? 1024 : (1024 >> s), Cout = 256 >> s;
+    const int Hout = 2 * Hin, Cd = 2 * Cout;
+    if (s > 0) {
+      const size_t rows = (size_t)n * Hin * Hin;
+      copy_cols_kernel<OpT><<<cdiv(rows * (Cin / 4), 256), 256, 0, st>>>(P->D[s - 1], A, rows, Cin, Cin, 0);
+      WMK_CHECK_LAUNCH("copy_cols_kernel");
+    }
+    GemmArgs g;
+    g.A = A; g.W = P->up_w[s]; g.bias = P->up_b[s]; g.C = P->D[s]; g.M = n * Hin * Hin; g.N = 4 * Cout; g.K = Cin;
+    g.ldc = Cd; g.epi = EPI_UPSAMPLE; g.out_bf16 = 0; g.up_h = Hin; g.up_w = Hin; g.up_cout = Cout;
+    WMK_TRY(gemm(P, g, st));
+    {
+      const size_t rows = (size_t)n * Hout * Hout;
+      copy_cols_kernel<float><<<cdiv(rows * (Cout / 4), 256), 256, 0, st>>>(P->E[3 - s], P->D[s], rows, Cout, Cd, Cout);
+      WMK_CHECK_LAUNCH("copy_cols_kernel");
+    }
+    for (const BlockW& b : P->dec[s]) WMK_TRY(run_block<OpT>(P, b, P->D[s], n, st));
+    WMK_TRY(tap(P, "dec.deconv" + std::to_string(s), P->D[s], (size_t)n * Hout * Hout * Cd, st));
+  }
+  (void)ob;
+  float* y = y_out ? y_out : P->ybuf;
+  output_proj_kernel<<<cdiv((size_t)n * 16384 * 32, 256), 256, 0, st>>>(P->D[3], x, noise, y, P->out_w, P->out_b, n);
+  WMK_CHECK_LAUNCH("output_proj_kernel");
+  if (stft_new) {
+    // in-graph ISTFT -> STFT projection + stft_layer (model.py:2458-2465)
+    WMK_TRY(istft_clips(y, n, 1, 128, P->wavebuf, 8002, st));
+    WMK_TRY(tap(P, "emb.wave", P->wavebuf, (size_t)n * 8002, st));
+    WMK_TRY(stft_clips(P->wavebuf, n, 8002, P->rt, 1, st));
+    WMK_TRY(tap(P, "emb.roundtrip", P->rt, (size_t)n * 32768, st));
+    conv3x3_nchw_kernel<2, 4, true><<<cdiv((size_t)n * 16384, 256), 256, 0, st>>>(P->rt, P->rt2, P->sl0_w, P->sl0_b, n);
+    WMK_CHECK_LAUNCH("conv3x3_nchw_kernel<2,4>");
+    conv3x3_nchw_kernel<4, 2, false><<<cdiv((size_t)n * 16384, 256), 256, 0, st>>>(P->rt2, stft_new, P->sl2_w, P->sl2_b, n);
+    WMK_CHECK_LAUNCH("conv3x3_nchw_kernel<4,2>");
+  }
+  if (wm || wm_logits) WMK_TRY(run_extract<OpT>(P, y, n, wm, wm_logits, st));   // model.py:2508-2509 reads y
+  return 0;
+}
+
+int check_ready(wmk_plan* P) {
+  if (!P) { set_error("null plan"); return WMK_ERR_ARG; }
+  if (!P->finalized) { set_error("plan is not finalized"); return WMK_ERR_STATE; }
+  WMK_CHECK_CUDA(cudaSetDevice(P->device));
+  return ensure_workspace(P);
+}
+
+}  // namespace
+}  // namespace wmk
+
+// ------------------------------------------------------------------------------------ C ABI
+extern "C" int wmk_uformer_plan_create(int precision, wmk_plan** out) {
+  WMK_REQUIRE(out, "plan_create: null out");
+  WMK_REQUIRE(precision == WMK_PREC_FP32 || precision == WMK_PREC_BF16, "plan_create: unknown precision %d", precision);
+  int dev = 0;
+  WMK_CHECK_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  WMK_CHECK_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (precision == WMK_PREC_BF16 && prop.major != 10) {
+    set_error("bf16 precision needs an sm_100 device (tcgen05); found sm_%d%d", prop.major, prop.minor);
+    return WMK_ERR_UNSUPPORTED;
+  }
+  wmk_plan* P = new wmk_plan();
+  P->precision = precision;
+  P->device = dev;
+  *out = P;
+  return 0;
+}
+
+extern "C" int wmk_plan_destroy(wmk_plan* P) {
+  if (!P) return 0;
+  for (void* p : P->allocs) cudaFree(p);
+  for (void* p : P->ws_allocs) cudaFree(p);
+  for (auto& kv : P->taps) cudaFree(kv.second.first);
+  delete P;
+  return 0;
+}
+
+extern "C" int wmk_plan_set_tensor(wmk_plan* P, const char* name, const float* data_host, const int64_t* shape, int ndim) {
+  WMK_REQUIRE(P && name && data_host && shape && ndim >= 0 && ndim <= 8, "set_tensor: bad arguments");
+  WMK_REQUIRE(!P->finalized, "set_tensor: plan already finalized");
+  HostTensor t;
+  size_t n = 1;
+  for (int i = 0; i < ndim; ++i) { t.shape.push_back(shape[i]); n *= (size_t)shape[i]; }
+  t.data.assign(data_host, data_host + n);
+  P->host[name] = std::move(t);
+  return 0;
+}
+
+extern "C" int wmk_plan_set_chunk(wmk_plan* P, int clips_per_pass) {
+  WMK_REQUIRE(P, "set_chunk: null plan");
+  WMK_REQUIRE(!P->ws_ready, "set_chunk: workspace already allocated");
+  if (clips_per_pass > 0) P->chunk = clips_per_pass;
+  return 0;
+}
+
+extern "C" size_t wmk_plan_workspace_bytes(const wmk_plan* P) { return P ? P->ws_bytes : 0; }
+
+extern "C" int wmk_plan_finalize(wmk_plan* P) {
+  WMK_REQUIRE(P, "finalize: null plan");
+  if (P->finalized) return 0;
+  WMK_CHECK_CUDA(cudaSetDevice(P->device));
+  WMK_TRY(pack_encoder(P, "encoder.", "input_proj.", &P->enc));
+  WMK_TRY(pack_encoder(P, "decoder_wm.", "decoder_wm.input_proj.", &P->ext));
+  for (int s = 0; s < 4; ++s) {
+    const int Cin = (s == 0) ? 1024 : (1024 >> s), Cout = 256 >> s, Cd = 2 * Cout, H = 16 << s;
+    const std::string up = "decoder.upsample_" + std::to_string(s) + ".deconv.0.";
+    const HostTensor *t, *tb;
+    WMK_TRY(get(P, up + "weight", (size_t)Cin * Cout * 4, &t));
+    WMK_TRY(get(P, up + "bias", Cout, &tb));
+    std::vector<float> g((size_t)4 * Cout * Cin), b4((size_t)4 * Cout);      // [(i,j,co)][ci]
+    for (int ci = 0; ci < Cin; ++ci)
+      for (int co = 0; co < Cout; ++co)
+        for (int ij = 0; ij < 4; ++ij) g[((size_t)ij * Cout + co) * Cin + ci] = t->data[((size_t)ci * Cout + co) * 4 + ij];
+    for (int ij = 0; ij < 4; ++ij)
+      for (int co = 0; co < Cout; ++co) b4[(size_t)ij * Cout + co] = tb->data[co];
+    WMK_TRY(upload_op(P, g, &P->up_w[s]));
+    WMK_TRY(upload_f32(P, b4, &P->up_b[s]));
+    P->dec[s].resize(kDepths[5 + s]);
+    for (int i = 0; i < kDepths[5 + s]; ++i) {
+      const std::string bp = "decoder.decoderlayer_" + std::to_string(s) + ".blocks." + std::to_string(i) + ".";
+      WMK_TRY(pack_block(P, bp, Cd, kHeads[5 + s], H, (i % 2) ? 4 : 0, true, &P->dec[s][i]));
+    }
+  }
+  WMK_TRY(get_f32(P, "output_proj.proj.0.weight", 2 * 64 * 9, &P->out_w));
+  WMK_TRY(get_f32(P, "output_proj.proj.0.bias", 2, &P->out_b));
+  WMK_TRY(get_f32(P, "encoder_wm.conv1.weight", 144, &P->codec_c1w));
+  WMK_TRY(get_f32(P, "encoder_wm.conv1.bias", 16, &P->codec_c1b));
+  WMK_TRY(get_f32(P, "encoder_wm.conv2.weight", 576, &P->codec_c2w));
+  WMK_TRY(get_f32(P, "encoder_wm.conv2.bias", 4, &P->codec_c2b));
+  WMK_TRY(get_f32(P, "encoder_wm.t_conv1.weight", 256, &P->codec_t1w));
+  WMK_TRY(get_f32(P, "encoder_wm.t_conv1.bias", 16, &P->codec_t1b));
+  WMK_TRY(get_f32(P, "encoder_wm.t_conv2.weight", 64, &P->codec_t2w));
+  WMK_TRY(get_f32(P, "encoder_wm.t_conv2.bias", 1, &P->codec_t2b));
+  WMK_TRY(get_f32(P, "decoder_wm.conv2.weight", 64, &P->head_w));
+  WMK_TRY(get_f32(P, "decoder_wm.conv2.bias", 1, &P->head_b));
+  WMK_TRY(get_f32(P, "stft_layer.0.weight", 72, &P->sl0_w));
+  WMK_TRY(get_f32(P, "stft_layer.0.bias", 4, &P->sl0_b));
+  WMK_TRY(get_f32(P, "stft_layer.2.weight", 72, &P->sl2_w));
+  WMK_TRY(get_f32(P, "stft_layer.2.bias", 2, &P->sl2_b));
+  P->host.clear();
+  P->finalized = true;
+  return 0;
+}
+
+extern "C" int wmk_uformer_forward(wmk_plan* P, const float* x, const float* msg, int msg_stride, int B, float* stft_new,
+                                   float* noise, float* y, float* wm_pred, float* wm, float* wm_logits, void* stream) {
+  WMK_TRY(check_ready(P));
+  WMK_REQUIRE(x && msg && B > 0 && (msg_stride == 0 || msg_stride == 1024), "forward: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int b0 = 0; b0 < B; b0 += P->chunk) {
+    const int n = B - b0 < P->chunk ? B - b0 : P->chunk;
+    const size_t o = (size_t)b0;
+    auto off = [&](float* p, size_t per) { return p ? p + o * per : nullptr; };
+    int s;
+    if (P->precision == WMK_PREC_BF16)
+      s = run_forward<__nv_bfloat16>(P, x + o * 32768, msg + o * msg_stride, msg_stride, n, off(stft_new, 32768),
+                                     off(noise, 32768), off(y, 32768), off(wm_pred, 1024), off(wm, 1024),
+                                     off(wm_logits, 1024), st);
+    else
+      s = run_forward<float>(P, x + o * 32768, msg + o * msg_stride, msg_stride, n, off(stft_new, 32768),
+                             off(noise, 32768), off(y, 32768), off(wm_pred, 1024), off(wm, 1024), off(wm_logits, 1024), st);
+    if (s) return s;
+  }
+  return 0;
+}
+
+extern "C" int wmk_uformer_extract(wmk_plan* P, const float* y, int B, float* wm, float* wm_logits, void* stream) {
+  WMK_TRY(check_ready(P));
+  WMK_REQUIRE(y && B > 0 && (wm || wm_logits), "extract: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int b0 = 0; b0 < B; b0 += P->chunk) {
+    const int n = B - b0 < P->chunk ? B - b0 : P->chunk;
+    const size_t o = (size_t)b0;
+    int s;
+    if (P->precision == WMK_PREC_BF16)
+      s = run_extract<__nv_bfloat16>(P, y + o * 32768, n, wm ? wm + o * 1024 : nullptr,
+                                     wm_logits ? wm_logits + o * 1024 : nullptr, st);
+    else
+      s = run_extract<float>(P, y + o * 32768, n, wm ? wm + o * 1024 : nullptr,
+                             wm_logits ? wm_logits + o * 1024 : nullptr, st);
+    if (s) return s;
+  }
+  return 0;
+}
+
+extern "C" int wmk_plan_enable_taps(wmk_plan* P, int enable) {
+  WMK_REQUIRE(P, "enable_taps: null plan");
+  P->taps_on = enable != 0;
+  return 0;
+}
+
+extern "C" int wmk_plan_get_tap(wmk_plan* P, const char* name, float* out, size_t capacity, size_t* n_out) {
+  WMK_REQUIRE(P && name && n_out, "get_tap: bad arguments");
+  auto it = P->taps.find(name);
+  if (it == P->taps.end()) { set_error("get_tap: no tap named '%s'", name); return WMK_ERR_ARG; }
+  *n_out = it->second.second;
+  if (out) {
+    WMK_REQUIRE(capacity >= it->second.second, "get_tap: capacity %zu < %zu", capacity, it->second.second);
+    WMK_CHECK_CUDA(cudaMemcpy(out, it->second.first, it->second.second * 4, cudaMemcpyDeviceToDevice));
+  }
+  return 0;
+}
+
+extern "C" int wmk_linear_f32(const float* A, const float* W, const float* bias, float* C, int M, int N, int K,
+                              int precision, int gelu, void* stream) {
+  WMK_REQUIRE(A && W && C && M > 0 && N > 0 && K > 0, "linear: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  GemmArgs g;
+  g.bias = bias; g.C = C; g.M = M; g.N = N; g.K = K; g.ldc = N; g.epi = gelu ? EPI_BIAS_GELU : EPI_BIAS; g.out_bf16 = 0;
+  if (precision == WMK_PREC_FP32) {
+    g.A = A; g.W = W;
+    return gemm_fp32_simt(g, st);
+  }
+  WMK_REQUIRE(precision == WMK_PREC_BF16, "linear: unknown precision %d", precision);
+  __nv_bfloat16 *a16 = nullptr, *w16 = nullptr;
+  WMK_CHECK_CUDA(cudaMallocAsync(&a16, (size_t)M * K * 2, st));
+  WMK_CHECK_CUDA(cudaMallocAsync(&w16, (size_t)N * K * 2, st));
+  copy_cols_kernel<__nv_bfloat16><<<cdiv((size_t)M * (K / 4), 256), 256, 0, st>>>(A, a16, (size_t)M, K, K, 0);
+  WMK_CHECK_LAUNCH("copy_cols_kernel");
+  copy_cols_kernel<__nv_bfloat16><<<cdiv((size_t)N * (K / 4), 256), 256, 0, st>>>(W, w16, (size_t)N, K, K, 0);
+  WMK_CHECK_LAUNCH("copy_cols_kernel");
+  g.A = a16; g.W = w16;
+  int s = gemm_bf16_tcgen05(g, st);
+  cudaFreeAsync(a16, st);
+  cudaFreeAsync(w16, st);
+  return s;
+}

@@ -1,0 +1,112 @@
+// Shared declarations of libwmk.so (internal; the public ABI is include/wmk.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/wmk.h"
+
+namespace wmk {
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define WMK_CHECK_CUDA(expr)                                                              \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      ::wmk::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr,                 \
+                       cudaGetErrorString(_e));                                           \
+      return WMK_ERR_CUDA;                                                                \
+    }                                                                                     \
+  } while (0)
+
+#define WMK_CHECK_LAUNCH(name)                                                            \
+  do {                                                                                    \
+    ::wmk::count_launch();                                                                \
+    cudaError_t _e = cudaGetLastError();                                                  \
+    if (_e != cudaSuccess) {                                                              \
+      ::wmk::set_error("%s:%d: launch of %s failed: %s", __FILE__, __LINE__, name,        \
+                       cudaGetErrorString(_e));                                           \
+      return WMK_ERR_CUDA;                                                                \
+    }                                                                                     \
+  } while (0)
+
+#define WMK_REQUIRE(cond, ...)                                                            \
+  do {                                                                                    \
+    if (!(cond)) {                                                                        \
+      ::wmk::set_error(__VA_ARGS__);                                                      \
+      return WMK_ERR_ARG;                                                                 \
+    }                                                                                     \
+  } while (0)
+
+#define WMK_TRY(expr)                                                                     \
+  do {                                                                                    \
+    int _s = (expr);                                                                      \
+    if (_s != 0) return _s;                                                               \
+  } while (0)
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---------------------------------------------------------------------------------------------
+// Dense layer (GEMM) interface shared by the fp32 SIMT kernel and the bf16 tcgen05 kernel.
+//   C[m][n] = epilogue( sum_k A[m][k] * W[n][k] + bias[n] )
+// A is [M][K] and W is [N][K], both K-contiguous ("K-major"): PyTorch's nn.Linear weight layout.
+// ---------------------------------------------------------------------------------------------
+enum Epilogue {
+  EPI_BIAS = 0,       // C = acc + bias
+  EPI_BIAS_GELU = 1,  // C = gelu(acc + bias)                      (LeFF linear1, model.py:686-687)
+  EPI_BIAS_RESID = 2, // C = resid + acc + bias  (fp32 out; resid may alias C)  (model.py:1016-1017)
+  EPI_UPSAMPLE = 3    // ConvTranspose2d(k=2,s=2) pixel shuffle into the concat buffer (model.py:794-800,1225)
+};
+
+struct GemmArgs {
+  const void* A = nullptr;      // [M][K]   float (fp32 mode) or __nv_bfloat16 (bf16 mode)
+  const void* W = nullptr;      // [N][K]   same type as A
+  const float* bias = nullptr;  // [N] or nullptr
+  const float* resid = nullptr; // [M][ldc] fp32 (EPI_BIAS_RESID)
+  void* C = nullptr;            // [M][ldc] float or bf16 (out_bf16)
+  int M = 0, N = 0, K = 0;
+  int ldc = 0;                  // row stride of C / resid in elements
+  int epi = EPI_BIAS;
+  int out_bf16 = 0;
+  // EPI_UPSAMPLE: A rows are (b, h, w) over an up_h x up_w grid; columns are (i, j, co) with
+  // co < up_cout; element goes to token (b, 2h+i, 2w+j), channel co of a [.., ldc] buffer.
+  int up_h = 0, up_w = 0, up_cout = 0;
+};
+
+int gemm_fp32_simt(const GemmArgs& g, cudaStream_t st);
+int gemm_bf16_tcgen05(const GemmArgs& g, cudaStream_t st);
+
+__device__ __forceinline__ float gelu_erf(float x) {
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+
+// Where element (m, n) of a GEMM result is stored.
+struct EpiParams {
+  const float* bias;
+  const float* resid;
+  void* C;
+  int M, N, ldc, epi, out_bf16;
+  int up_h, up_w, up_cout;
+};
+
+__device__ __forceinline__ size_t epi_row_offset(const EpiParams& p, int m, int n_first) {
+  if (p.epi == EPI_UPSAMPLE) {
+    int hw = p.up_h * p.up_w;
+    int b = m / hw;
+    int r = m - b * hw;
+    int h = r / p.up_w;
+    int w = r - h * p.up_w;
+    int ij = n_first / p.up_cout;
+    int co = n_first - ij * p.up_cout;
+    int i = ij >> 1, j = ij & 1;
+    size_t tok = (size_t)b * 4 * hw + (size_t)(2 * h + i) * (2 * p.up_w) + (2 * w + j);
+    return tok * p.ldc + co;
+  }
+  return (size_t)m * p.ldc + n_first;
+}
+
+}  // namespace wmk

@@ -1,0 +1,81 @@
+"""Metrics and the report line of the reference's evaluator (`uformerWM/evaluate.py`), with the
+reductions running on the GPU (`wmk_wave_stats_f64`, `wmk_wm_stats_f64`)."""
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def wave_stats(orig, test):
+    """(B, L) CUDA waveforms -> (B, 6) float64 CUDA tensor
+    {sum o^2, sum (o-t)^2, sum t, sum t^2, sum o, n}."""
+    o = orig.float().contiguous()
+    t = test.float().contiguous()
+    if o.dim() == 1:
+        o, t = o[None], t[None]
+    L = min(o.shape[1], t.shape[1])
+    if o.shape[1] != L:
+        o = o[:, :L].contiguous()
+    if t.shape[1] != L:
+        t = t[:, :L].contiguous()
+    st = torch.empty((o.shape[0], 6), device=o.device, dtype=torch.float64)
+    _lib.check(_lib.load().wmk_wave_stats_f64(_lib.ptr(o), _lib.ptr(t), o.shape[0], L, _lib.ptr(st), _lib.stream_ptr()))
+    return st
+
+
+def wm_stats(wm, msg):
+    """wm (n,1,32,32) sigmoid outputs, msg (n or 1,1,32,32) -> (n, 2) float64 {bit errors, sum sq err}."""
+    w = wm.float().contiguous().reshape(-1, 1024)
+    m = msg.float().contiguous().reshape(-1, 1024)
+    stride = 0 if m.shape[0] == 1 and w.shape[0] > 1 else 1024
+    st = torch.empty((w.shape[0], 2), device=w.device, dtype=torch.float64)
+    _lib.check(_lib.load().wmk_wm_stats_f64(_lib.ptr(w), _lib.ptr(m), w.shape[0], stride, _lib.ptr(st), _lib.stream_ptr()))
+    return st
+
+
+def snr_from_stats(st):
+    """`cal_snr` (`uformerWM/evaluate.py:139-144`) per utterance from wave_stats."""
+    return 10.0 * torch.log10(st[:, 0] / st[:, 1])
+
+
+def signaltonoise_from_stats(st):
+    """`signaltonoise` (`evaluate.py:133-137`) of the *test* waveform: 20 log10 |mean/std|."""
+    n = st[:, 5]
+    mean = st[:, 2] / n
+    var = st[:, 3] / n - mean * mean
+    return 20.0 * torch.log10(torch.abs(mean / torch.sqrt(var)))
+
+
+def _cuda1d(a):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32).reshape(1, -1).cuda()
+
+
+def cal_snr(audio_ori, audio_recon):
+    """`uformerWM/evaluate.py:139-144` (numpy in, python float out)."""
+    n = min(len(audio_ori), len(audio_recon))
+    st = wave_stats(_cuda1d(audio_ori[:n]), _cuda1d(audio_recon[:n]))
+    return float(snr_from_stats(st)[0])
+
+
+def signaltonoise(a, axis=0, ddof=0):
+    """`uformerWM/evaluate.py:133-137` for 1-D input."""
+    x = _cuda1d(np.asanyarray(a).reshape(-1))
+    return float(signaltonoise_from_stats(wave_stats(x, x))[0])
+
+
+def bit_error_rate(decoded, message):
+    """`hidden/test_model.py:60-64`."""
+    st = wm_stats(torch.as_tensor(decoded).cuda(), torch.as_tensor(message).cuda())
+    return float(st[:, 0].sum() / (st.shape[0] * 1024))
+
+
+RESULT_LINE = ('Result on {} set, attack: {}: Total clips: {}, MSE loss {}, WM loss: {}, WM loss after attack: {}, '
+               'SNR score: {}, PESQ score: {}\n')
+
+
+def format_result(data_cat, attack, clips_total, mse, wm_loss, wm_loss_att, snr, pesq="N/A"):
+    """The `sample_result.txt` line of `uformerWM/evaluate.py:289-291` (parsed by result_extract.py:14).
+    PESQ needs the third-party pypesq and is reported as N/A."""
+    return RESULT_LINE.format(data_cat, attack, clips_total, mse, wm_loss, wm_loss_att, snr, pesq)

@@ -1,0 +1,230 @@
+"""Drop-in `UformerAudio` (reference `uformerWM/model.py:2225-2543`) whose forward / wm_decode
+run entirely in libwmk.so (hand-written sm_100a CUDA).
+
+Same constructor arguments, same ``state_dict`` keys and shapes (so
+``model.load_state_dict(torch.load(path))`` of a reference checkpoint works,
+`uformerWM/evaluate.py:347`), same call surface:
+
+    stft_new, noise, wm_pred, wm = model(x, message)         # model.py:2384,2511
+    wm = model.wm_decode(y)                                   # model.py:2379
+    y, wm_pred = model.feature_extract(x, message)            # model.py:2345
+
+Inference only: the CUDA path has no backward, tensors are returned detached."""
+import ctypes
+import math
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+DEPTHS = [1, 2, 8, 8, 2, 8, 8, 2, 1]
+HEADS = [1, 2, 4, 8, 16, 16, 8, 4, 2]
+
+
+def uformer_audio_schema(embed_dim=32, depths=DEPTHS, num_heads=HEADS, in_chans=2, dd_in=2):
+    """(name -> (shape, kind)) in the reference's registration order."""
+    out = {}
+    E = embed_dim
+
+    def conv(name, co, ci, kh, kw):
+        out[name + ".weight"] = ((co, ci, kh, kw), "conv_w")
+        out[name + ".bias"] = ((co,), "bias")
+
+    def block(p, C, heads, mod):
+        if mod:
+            out[p + "modulator.weight"] = ((64, C), "embed")
+        out[p + "norm1.weight"] = ((C,), "ln_w")
+        out[p + "norm1.bias"] = ((C,), "ln_b")
+        out[p + "attn.relative_position_bias_table"] = ((225, heads), "table")
+        out[p + "attn.relative_position_index"] = ((64, 64), "index")
+        for n, shp in (("attn.qkv.to_q", (C, C)), ("attn.qkv.to_kv", (2 * C, C)), ("attn.proj", (C, C))):
+            out[p + n + ".weight"] = (shp, "lin_w")
+            out[p + n + ".bias"] = ((shp[0],), "bias")
+        out[p + "norm2.weight"] = ((C,), "ln_w")
+        out[p + "norm2.bias"] = ((C,), "ln_b")
+        out[p + "mlp.linear1.0.weight"] = ((4 * C, C), "lin_w")
+        out[p + "mlp.linear1.0.bias"] = ((4 * C,), "bias")
+        out[p + "mlp.dwconv.0.weight"] = ((4 * C, 1, 3, 3), "conv_w")
+        out[p + "mlp.dwconv.0.bias"] = ((4 * C,), "bias")
+        out[p + "mlp.linear2.0.weight"] = ((C, 4 * C), "lin_w")
+        out[p + "mlp.linear2.0.bias"] = ((C,), "bias")
+
+    def enc(p):
+        conv(p + "input_proj.proj.0", E, dd_in, 3, 3)
+        for s in range(4):
+            C = E << s
+            for i in range(depths[s]):
+                block("%sencoderlayer_%d.blocks.%d." % (p, s, i), C, num_heads[s], False)
+            conv("%sdowsample_%d.conv.0" % (p, s), 2 * C, C, 4, 4)
+        for i in range(depths[4]):
+            block("%sconv.blocks.%d." % (p, i), E * 16, num_heads[4], False)
+
+    conv("input_proj.proj.0", E, dd_in, 3, 3)
+    conv("output_proj.proj.0", in_chans, 2 * E, 3, 3)
+    enc("encoder.")
+    ups = [(E * 32, E * 8), (E * 16, E * 4), (E * 8, E * 2), (E * 4, E)]
+    for s in range(4):
+        out["decoder.upsample_%d.deconv.0.weight" % s] = ((ups[s][0], ups[s][1], 2, 2), "conv_w")
+        out["decoder.upsample_%d.deconv.0.bias" % s] = ((ups[s][1],), "bias")
+        for i in range(depths[5 + s]):
+            block("decoder.decoderlayer_%d.blocks.%d." % (s, i), 2 * ups[s][1], num_heads[5 + s], True)
+    conv("encoder_wm.conv1", 16, 1, 3, 3)
+    conv("encoder_wm.conv2", 4, 16, 3, 3)
+    out["encoder_wm.t_conv1.weight"] = ((4, 16, 2, 2), "conv_w")
+    out["encoder_wm.t_conv1.bias"] = ((16,), "bias")
+    out["encoder_wm.t_conv2.weight"] = ((16, 1, 2, 2), "conv_w")
+    out["encoder_wm.t_conv2.bias"] = ((1,), "bias")
+    enc("decoder_wm.")
+    conv("decoder_wm.conv2", 1, 1, 8, 8)
+    conv("stft_layer.0", 4, in_chans, 3, 3)
+    conv("stft_layer.2", in_chans, 4, 3, 3)
+    return out
+
+
+class _Node(nn.Module):
+    """Anonymous container so parameters get the reference's dotted names."""
+
+
+def _attach(root, dotted, tensor, is_buffer):
+    parts = dotted.split(".")
+    mod = root
+    for p in parts[:-1]:
+        if p not in mod._modules:
+            mod.add_module(p, _Node())
+        mod = mod._modules[p]
+    if is_buffer:
+        mod.register_buffer(parts[-1], tensor)
+    else:
+        mod.register_parameter(parts[-1], nn.Parameter(tensor, requires_grad=False))
+
+
+class UformerAudio(nn.Module):
+    def __init__(self, img_size=128, in_chans=2, dd_in=2, embed_dim=32, depths=DEPTHS,
+                 num_heads=HEADS, win_size=8, mlp_ratio=4., qkv_bias=True, qk_scale=None,
+                 drop_rate=0., attn_drop_rate=0., drop_path_rate=0.1, norm_layer=nn.LayerNorm,
+                 patch_norm=True, use_checkpoint=False, token_projection='linear', token_mlp='leff',
+                 dowsample=None, upsample=None, shift_flag=True, modulator=True, cross_modulator=False,
+                 audio_scale=0, data_min=0, data_max=1, precision='bf16', clips_per_pass=0, **kwargs):
+        super().__init__()
+        if (img_size, embed_dim, win_size, list(depths), list(num_heads), in_chans, dd_in) != \
+                (128, 32, 8, DEPTHS, HEADS, 2, 2) or token_projection != 'linear' or token_mlp != 'leff' \
+                or not modulator or cross_modulator or not shift_flag or mlp_ratio != 4. or qk_scale is not None:
+            raise NotImplementedError(
+                "the CUDA path implements the 'Uformer_audio' configuration of "
+                "uformerWM/utils/model_utils.py:83-85 (img 128, embed 32, win 8, depths %s)" % DEPTHS)
+        self.reso, self.embed_dim, self.win_size = img_size, embed_dim, win_size
+        self.data_min, self.data_max, self.audio_scale = data_min, data_max, audio_scale
+        self.precision = precision
+        self.clips_per_pass = clips_per_pass
+        self._schema = uformer_audio_schema()
+        from .synthetic import init_state_dict
+        sd = init_state_dict(self._schema, "reference", 0)
+        for name, (shape, kind) in self._schema.items():
+            _attach(self, name, sd[name], kind == "index")
+        self._plan = None
+        self._plan_key = None
+
+    # ------------------------------------------------------------------ plan management
+    def _key(self):
+        dev = next(self.parameters()).device
+        return (str(dev), self.precision, tuple(p._version for p in self.parameters()),
+                tuple(p.data_ptr() for p in self.parameters()))
+
+    def _drop_plan(self):
+        if self._plan is not None:
+            _lib.load().wmk_plan_destroy(self._plan)
+            self._plan = None
+
+    def __del__(self):
+        try:
+            self._drop_plan()
+        except Exception:
+            pass
+
+    def plan(self):
+        """Pack the current weights into a wmk_plan (rebuilt when the weights change)."""
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise _lib.WmkError("UformerAudio has no CPU path: call .cuda() first")
+        key = self._key()
+        if self._plan is not None and key == self._plan_key:
+            return self._plan
+        self._drop_plan()
+        lib = _lib.load()
+        prec = {"bf16": _lib.PREC_BF16, "fp32": _lib.PREC_FP32}[self.precision]
+        handle = ctypes.c_void_p()
+        with torch.cuda.device(dev):
+            _lib.check(lib.wmk_uformer_plan_create(prec, ctypes.byref(handle)))
+            for name, t in self.state_dict().items():
+                if t.dtype != torch.float32:
+                    continue
+                h = t.detach().to("cpu", torch.float32).contiguous()
+                shape = (ctypes.c_int64 * max(1, h.dim()))(*h.shape)
+                _lib.check(lib.wmk_plan_set_tensor(handle, name.encode(), ctypes.c_void_p(h.data_ptr()), shape, h.dim()))
+            _lib.check(lib.wmk_plan_finalize(handle))
+            if self.clips_per_pass:
+                _lib.check(lib.wmk_plan_set_chunk(handle, int(self.clips_per_pass)))
+        self._plan, self._plan_key = handle, key
+        return handle
+
+    # ------------------------------------------------------------------ reference call surface
+    def _prep(self, x):
+        if not x.is_cuda:
+            raise _lib.WmkError("UformerAudio has no CPU path: inputs must be CUDA tensors")
+        return x.detach().contiguous().float()
+
+    def run(self, x, message, want=("stft_new", "noise", "wm_pred", "wm")):
+        """One fused pass; returns a dict with the requested outputs (+ 'y', 'wm_logits')."""
+        lib = _lib.load()
+        x = self._prep(x)
+        message = self._prep(message)
+        B = x.shape[0]
+        if x.shape[1:] != (2, 128, 128):
+            raise ValueError("x must be (B,2,128,128), got %s" % (tuple(x.shape),))
+        m = message.reshape(-1, 1024)
+        if m.shape[0] not in (1, B):
+            raise ValueError("message batch %d does not match %d clips" % (m.shape[0], B))
+        stride = 0 if m.shape[0] == 1 and B > 1 else 1024
+        o = {}
+        for k, shp in (("stft_new", (B, 2, 128, 128)), ("noise", (B, 2, 128, 128)), ("y", (B, 2, 128, 128)),
+                       ("wm_pred", (B, 1, 32, 32)), ("wm", (B, 1, 32, 32)), ("wm_logits", (B, 1, 32, 32))):
+            o[k] = torch.empty(shp, device=x.device, dtype=torch.float32) if k in want else None
+        if o["y"] is None:
+            o["y"] = torch.empty((B, 2, 128, 128), device=x.device, dtype=torch.float32)
+        with torch.cuda.device(x.device):
+            _lib.check(lib.wmk_uformer_forward(self.plan(), _lib.ptr(x), _lib.ptr(m), stride, B,
+                                               _lib.ptr(o["stft_new"]), _lib.ptr(o["noise"]), _lib.ptr(o["y"]),
+                                               _lib.ptr(o["wm_pred"]), _lib.ptr(o["wm"]), _lib.ptr(o["wm_logits"]),
+                                               _lib.stream_ptr()))
+        return o
+
+    def forward(self, x, message, mask=None):
+        o = self.run(x, message)
+        return o["stft_new"], o["noise"], o["wm_pred"], o["wm"]
+
+    def wm_decode(self, y, return_logits=False):
+        lib = _lib.load()
+        y = self._prep(y)
+        B = y.shape[0]
+        wm = torch.empty((B, 1, 32, 32), device=y.device, dtype=torch.float32)
+        lg = torch.empty_like(wm)
+        with torch.cuda.device(y.device):
+            _lib.check(lib.wmk_uformer_extract(self.plan(), _lib.ptr(y), B, _lib.ptr(wm), _lib.ptr(lg), _lib.stream_ptr()))
+        return (wm, lg) if return_logits else wm
+
+    def feature_extract(self, x, message):
+        o = self.run(x, message, want=("wm_pred", "y"))
+        return o["y"], o["wm_pred"]
+
+    # ------------------------------------------------------------------ debugging
+    def enable_taps(self, on=True):
+        _lib.check(_lib.load().wmk_plan_enable_taps(self.plan(), int(on)))
+
+    def get_tap(self, name):
+        lib = _lib.load()
+        n = ctypes.c_size_t()
+        _lib.check(lib.wmk_plan_get_tap(self.plan(), name.encode(), None, 0, ctypes.byref(n)))
+        out = torch.empty(n.value, device=next(self.parameters()).device, dtype=torch.float32)
+        _lib.check(lib.wmk_plan_get_tap(self.plan(), name.encode(), _lib.ptr(out), n.value, ctypes.byref(n)))
+        return out

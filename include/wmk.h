@@ -1,0 +1,167 @@
+/* wmk.h - C ABI of libwmk.so: the B200-native (sm_100a) embed -> attack -> extract hot path of
+ * image-in-speech watermarking.
+ *
+ * The reference is pure Python/PyTorch and has no FFI; the boundary it exposes is its Python call
+ * surface.  Each entry point below names the reference call it replaces
+ * (paths relative to the reference root).  The Python drop-in modules in
+ * image-in-speech-watermarking_b200/ bind these symbols with ctypes and pass raw device pointers
+ * of tensors that the caller (PyTorch) allocated.
+ *
+ * Conventions
+ *  - every function returns 0 on success and a negative wmk_status on failure; wmk_last_error()
+ *    returns a thread-local description of the last failure on the calling thread;
+ *  - all pointers are DEVICE pointers unless the name ends in _host; the caller owns every buffer;
+ *    a wmk_plan owns only its packed copy of the weights and its workspace;
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); calls are
+ *    asynchronous with respect to the host unless stated otherwise;
+ *  - "clip layout": float32 [n_clips][2 (re,im)][128 bins][128 frames]  (what
+ *    uformerWM/audio_test.py:343 hands to the model); "token layout": [tokens][channels].
+ *  - there is no CPU fallback: without a CUDA device every compute entry point fails with
+ *    WMK_ERR_CUDA.
+ */
+#ifndef WMK_H_
+#define WMK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum wmk_status {
+  WMK_OK = 0,
+  WMK_ERR_ARG = -1,      /* invalid argument */
+  WMK_ERR_CUDA = -2,     /* CUDA runtime / driver error, or no device */
+  WMK_ERR_ALLOC = -3,    /* device allocation failed */
+  WMK_ERR_STATE = -4,    /* plan missing a weight / wrong precision for this device */
+  WMK_ERR_UNSUPPORTED = -5
+} wmk_status;
+
+/* arithmetic of the dense contractions of the Uformer blocks */
+typedef enum wmk_precision {
+  WMK_PREC_FP32 = 0,     /* fp32 SIMT GEMMs: the 1e-3 parity mode */
+  WMK_PREC_BF16 = 1      /* bf16 operands on tcgen05 tensor cores, fp32 accumulate in TMEM,
+                            fp32 residual stream / LayerNorm / softmax */
+} wmk_precision;
+
+int wmk_version(void);
+const char* wmk_last_error(void);
+/* number of kernels this library has launched on the calling process since load (for bench.py's
+ * gpu_launches) */
+uint64_t wmk_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * STFT / ISTFT front end.
+ * Replaces torch.stft(x, n_fft=255) / torch.istft(spec, n_fft=255[, length]) at
+ * uformerWM/audio_test.py:315-316,598-600,677-678 and uformerWM/model.py:2458,2463, fused with
+ * the 128-frame clip split + zero padding of uformerWM/audio_test.py:319-343,681-688.
+ * n_fft = 255, hop = 63, rectangular window, centre reflect padding 127, 128 one-sided bins.
+ * ------------------------------------------------------------------------------------------ */
+
+/* frames of an L-sample waveform: 1 + (L - 1) / 63 */
+int wmk_stft_num_frames(int L);
+
+/* wave [B][L] -> clips [B][n_clips][2][128][128]; frames t >= T of the last clips are zero.
+ * n_clips >= ceil(T/128) (the caller chooses: the reference's quirks B-6/B-7 need T/128+1). */
+int wmk_stft_clips_f32(const float* wave, int B, int L, float* clips, int n_clips, void* stream);
+
+/* clips [B][n_clips][2][128][128] (first T frames used) -> wave [B][length].
+ * length <= 0 selects torch's default 63*(T-1)+1.  Samples past the overlap-add support are 0. */
+int wmk_istft_clips_f32(const float* clips, int B, int n_clips, int T, float* wave, int length,
+                        void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Waveform attacks (uformerWM/audio_attack.py), batched over B utterances of L samples, fp32 in
+ * HBM, fp64 arithmetic where the reference's numpy code promotes.  In-place (dst == src) allowed
+ * except for echo / lowpass / resample.
+ * ------------------------------------------------------------------------------------------ */
+/* awgn (audio_attack.py:99-125).  noise_unit [B][L] = N(0,1) draws, or NULL to draw them on the
+ * device (Philox, `seed`).  sigma^2 = mean(x^2) * 10^(-snr_db/10) per utterance. */
+int wmk_attack_awgn_f32(const float* src, float* dst, int B, int L, float snr_db,
+                        const float* noise_unit, uint64_t seed, void* stream);
+/* amplitude_scaling (audio_attack.py:55-58) */
+int wmk_attack_scale_f32(const float* src, float* dst, int B, int L, float factor, void* stream);
+/* echo_addition (audio_attack.py:33-52): y[n] = x[n] + gain * x[n - delay] */
+int wmk_attack_echo_f32(const float* src, float* dst, int B, int L, int delay, float gain,
+                        void* stream);
+/* low_pass_filter (audio_attack.py:21-30): zero-phase Butterworth.  b_host/a_host are the
+ * `order`+1 transfer-function coefficients and zi_host the `order` lfilter_zi states (host,
+ * float64), as scipy.signal.butter / lfilter_zi produce them; padlen = 3*(order+1). */
+int wmk_attack_lowpass_f32(const float* src, float* dst, int B, int L, int order,
+                           const double* b_host, const double* a_host, const double* zi_host,
+                           void* stream);
+/* jittering_2 (audio_attack.py:176-193): zero the samples idx[b][0..n_idx) of utterance b */
+int wmk_attack_jitter_zero_f32(float* wave, int B, int L, const int32_t* idx, int n_idx,
+                               void* stream);
+/* requantization (audio_attack.py:85-96), 8-bit unsigned PCM round trip (parity unpinned) */
+int wmk_attack_requant8_f32(const float* src, float* dst, int B, int L, void* stream);
+/* resampling (audio_attack.py:71-83): 2:1 down then 1:2 up with an n_taps polyphase FIR
+ * (taps_host float64, the scipy.signal.resample_poly design; parity unpinned) */
+int wmk_attack_resample2_f32(const float* src, float* dst, int B, int L, const double* taps_host,
+                             int n_taps, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Metrics (uformerWM/evaluate.py:139-144 cal_snr, audio_test.py:618 audio MSE,
+ * audio_test.py:522-526 signaltonoise; hidden/test_model.py:60-64 BER; audio_test.py:625,712
+ * watermark MSE).  Per-utterance float64 outputs, fused reductions with warp shuffles.
+ * ------------------------------------------------------------------------------------------ */
+/* stats [B][6] (float64) = { sum(orig^2), sum((orig-test)^2), sum(test), sum(test^2),
+ *                            sum(orig), count } over the first L samples */
+int wmk_wave_stats_f64(const float* orig, const float* test, int B, int L, double* stats,
+                       void* stream);
+/* wm [n][1024] sigmoid outputs, msg [n or 1][1024] -> stats [n][2] (float64) =
+ * { bit errors = sum |clip(rint(wm),0,1) - msg| , sum (wm - msg)^2 }.  msg_stride = 0 broadcasts
+ * one image, 1024 gives one image per row. */
+int wmk_wm_stats_f64(const float* wm, const float* msg, int n, int msg_stride, double* stats,
+                     void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * UformerAudio embedder / extractor (uformerWM/model.py:2225-2511, configuration
+ * uformerWM/utils/model_utils.py:83-85).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct wmk_plan wmk_plan;
+
+/* Create a plan on the current device. */
+int wmk_uformer_plan_create(int precision, wmk_plan** out);
+int wmk_plan_destroy(wmk_plan* plan);
+/* Register one state_dict tensor by its reference name (e.g.
+ * "decoder.decoderlayer_0.blocks.3.attn.qkv.to_kv.weight"); data_host is float32 host memory in
+ * the tensor's own (PyTorch-contiguous) layout.  int64 buffers (relative_position_index) are not
+ * needed and are ignored by the Python loader. */
+int wmk_plan_set_tensor(wmk_plan* plan, const char* name, const float* data_host,
+                        const int64_t* shape, int ndim);
+/* Pack all registered tensors into device layouts (bf16 K-major GEMM operands, gathered
+ * relative-position bias, fused QKV).  Fails with WMK_ERR_STATE naming the first missing tensor. */
+int wmk_plan_finalize(wmk_plan* plan);
+/* Largest number of clips processed per internal pass (activation workspace is sized for it;
+ * 0 = default).  Must be set before the first forward. */
+int wmk_plan_set_chunk(wmk_plan* plan, int clips_per_pass);
+size_t wmk_plan_workspace_bytes(const wmk_plan* plan);
+
+/* UformerAudio.forward (model.py:2384-2511).  x [B][2][128][128], msg [B or 1][1][32][32]
+ * (msg_stride 0 or 1024).  Outputs (any may be NULL): stft_new / noise / y [B][2][128][128]
+ * (y = x + noise, the spectrogram the in-model extractor reads, model.py:2421,2508),
+ * wm_pred / wm [B][1024] sigmoid, wm_logits [B][1024] pre-sigmoid (for the |logit| margin). */
+int wmk_uformer_forward(wmk_plan* plan, const float* x, const float* msg, int msg_stride, int B,
+                        float* stft_new, float* noise, float* y, float* wm_pred, float* wm,
+                        float* wm_logits, void* stream);
+/* UformerAudio.wm_decode (model.py:2379-2382). */
+int wmk_uformer_extract(wmk_plan* plan, const float* y, int B, float* wm, float* wm_logits,
+                        void* stream);
+/* Debug taps: copy a named intermediate of the LAST pass (e.g. "enc.conv0", "dec.deconv3",
+ * "ext.conv4", see oracle/uformer.py) to out (float32, token layout).  Only valid when B <=
+ * clips_per_pass.  Returns the element count through n_out. */
+int wmk_plan_enable_taps(wmk_plan* plan, int enable);
+int wmk_plan_get_tap(wmk_plan* plan, const char* name, float* out, size_t capacity, size_t* n_out);
+
+/* Stand-alone dense op used by the unit tests and the roofline bench:
+ * C[M][N] = A[M][K] * W[N][K]^T + bias[N], fp32 in HBM in and out; precision selects the fp32
+ * SIMT kernel or the bf16 tcgen05 kernel (operands converted on the fly by a cast kernel). */
+int wmk_linear_f32(const float* A, const float* W, const float* bias, float* C, int M, int N,
+                   int K, int precision, int gelu, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WMK_H_ */
