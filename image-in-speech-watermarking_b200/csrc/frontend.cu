@@ -57,8 +57,8 @@ int get_twiddles(Twiddles* out) {
 __global__ void __launch_bounds__(256)
 stft_clips_kernel(const float* __restrict__ wave, int L, int T, float* __restrict__ clips, int n_clips,
                   const float* __restrict__ tw) {
-  __shared__ float samp[63 * 63 + 256 + 8];
-  __shared__ float Bs[16][68];
+  __shared__ __align__(16) float samp[63 * 63 + 256 + 8];
+  __shared__ __align__(16) float Bs[16][68];
   __shared__ float Cs[64][65];
   const int b = blockIdx.z, j0 = blockIdx.y * 64, f0 = blockIdx.x * 64;
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;

@@ -22,8 +22,8 @@ __device__ __forceinline__ void epi_store1(const EpiParams& p, int m, int n, flo
 
 __global__ void __launch_bounds__(256)
 gemm_fp32_kernel(const float* __restrict__ A, const float* __restrict__ W, EpiParams p, int K, int n_tiles) {
-  __shared__ float As[TK][TM + 4];
-  __shared__ float Ws[TK][TN + 4];
+  __shared__ __align__(16) float As[TK][TM + 4];
+  __shared__ __align__(16) float Ws[TK][TN + 4];
   const int tile = blockIdx.x;
   const int m0 = (tile / n_tiles) * TM, n0 = (tile % n_tiles) * TN;
   const int tid = threadIdx.x;

@@ -36,10 +36,15 @@ def section(name, fn):
     print("    (%.1fs)" % (time.time() - t), flush=True)
 
 
+WHICH_LINEAR = []
+
+
 def linear():
     lib = _lib.load()
     g = torch.Generator().manual_seed(0)
     for prec, name in ((0, "fp32"), (1, "bf16")):
+        if WHICH_LINEAR and name not in WHICH_LINEAR:
+            continue
         for (M, N, K) in [(128, 32, 32), (256, 96, 32), (200, 64, 64), (1024, 128, 128), (64, 512, 2048),
                           (4096, 384, 128), (3000, 256, 512), (128, 1024, 64)]:
             A = torch.randn(M, K, generator=g).cuda(); W = (torch.randn(N, K, generator=g) / K ** 0.5).cuda()
@@ -171,7 +176,9 @@ def speed():
 if __name__ == "__main__":
     print(torch.cuda.get_device_name(0), "lib", _lib.load().wmk_version(), flush=True)
     which = sys.argv[1:] or ["linear", "frontend", "attacks", "fp32", "bf16", "pipeline", "batch", "speed"]
-    if "linear" in which: section("linear", linear)
+    if "linear_fp32" in which: WHICH_LINEAR.append("fp32")
+    if "linear_bf16" in which: WHICH_LINEAR.append("bf16")
+    if "linear" in which or WHICH_LINEAR: section("linear", linear)
     if "frontend" in which: section("frontend", frontend)
     if "attacks" in which: section("attacks", attacks)
     keep = {}
@@ -183,7 +190,6 @@ if __name__ == "__main__":
         section("model bf16 stress", lambda: keep.update(bf16=model("bf16", "stress")))
         section("model bf16 reference-init", lambda: model("bf16", "reference"))
     if "pipeline" in which and "bf16" in keep: section("pipeline bf16", lambda: pipeline(*keep["bf16"]))
-    if "batch" in which:
-        section("batch fp32", lambda: batch_consistency("fp32"))
-        section("batch bf16", lambda: batch_consistency("bf16"))
+    if "batch" in which or "batch_fp32" in which: section("batch fp32", lambda: batch_consistency("fp32"))
+    if "batch" in which or "batch_bf16" in which: section("batch bf16", lambda: batch_consistency("bf16"))
     if "speed" in which: section("speed", speed)
