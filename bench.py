@@ -1,0 +1,277 @@
+#!/usr/bin/env python
+"""Benchmark of the embed -> attack -> extract hot path (BASELINE.json metric: audio-seconds/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision bf16|fp32]
+
+One "step" = one pass of the hot path over one batch of synthetic utterances:
+STFT -> UformerAudio.forward (embed + in-model ISTFT/STFT projection + clean extract) -> ISTFT ->
+attack chain -> STFT -> UformerAudio.wm_decode -> SNR / MSE / BER statistics.
+Workload at every N (weak scaling, per-GPU work fixed): BASELINE.json configs[1] - 64 utterances
+x 3 s, 16 kHz, 32x32 binary images, 'awgn-20+low_pass' attack, random-init weights.
+Prints ONE JSON line (rank 0).  See DESIGN.md section "Measurement" for what each key means.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+import warnings
+
+warnings.filterwarnings("ignore")
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+B_UTT, SECONDS, SR = 64, 3.0, 16000
+ATTACK = "awgn-20+low_pass"
+GFLOP_PER_CLIP_FWD, GFLOP_PER_CLIP_EXT = 53.76, 10.43
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--utterances", type=int, default=B_UTT)
+    ap.add_argument("--chunk", type=int, default=0, help="clips per internal pass (0 = library default)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def config(args):
+    return {"workload": "BASELINE configs[1]: uformerWM embed+attack+extract, %d x %.0f s utterances per GPU, "
+                        "32x32 binary image, attacks %s, random-init Uformer_audio" % (args.utterances, SECONDS, ATTACK),
+            "utterances_per_gpu": args.utterances, "seconds_per_utterance": SECONDS, "sample_rate": SR,
+            "clips_per_utterance": 6, "attack": ATTACK, "precision": args.precision,
+            "l2": "per-step working set (%d clips x ~40 MB activations) exceeds the 126 MB L2; no flush needed"
+                  % (6 * args.utterances)}
+
+
+# ----------------------------------------------------------------------------- CPU baseline / reference arm
+def cpu_pipeline_step(sd, first_index, n_utt):
+    """The oracle port of the reference's CPU path on `n_utt` utterances; returns audio seconds done."""
+    import numpy as np
+    import torch
+    from oracle import pipeline as P
+    from image_in_speech_watermarking_b200 import synthetic as SY
+    for i in range(n_utt):
+        wave = SY.synth_speech(first_index + i, SECONDS)[None]
+        msg = SY.synth_image_binary(first_index + i)[None]
+        data = P.prepare_data(wave)
+        rng = np.random.default_rng(first_index + i)
+        P.reconstruct_audio(data, msg, sd, attack=ATTACK, draws={"awgn": rng.standard_normal(wave.shape[-1])})
+    return n_utt * SECONDS
+
+
+def cpu_state_dict():
+    from oracle import uformer as O
+    from image_in_speech_watermarking_b200 import synthetic as SY
+    return SY.init_state_dict(O.state_dict_schema(), "reference", 0)
+
+
+def cpu_baseline(budget_s=12.0, max_utt=4):
+    import torch
+    torch.set_num_threads(os.cpu_count())
+    sd = cpu_state_dict()
+    cpu_pipeline_step(sd, 1000, 1)                       # warm-up (allocator, MKL threads)
+    t0 = time.time()
+    done = 0
+    while done < max_utt and (time.time() - t0 < budget_s or done == 0):
+        cpu_pipeline_step(sd, done, 1)
+        done += 1
+    dt = time.time() - t0
+    return {"value": done * SECONDS / dt, "unit": "audio-s/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": "%d utterance(s) of %.0f s (6 clips each) of the same workload, oracle port of the reference's "
+                      "PyTorch-CPU path, fp32, torch threads=%d, %.1f s wall" % (done, SECONDS, os.cpu_count(), dt)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    torch.set_num_threads(os.cpu_count())
+    sd = cpu_state_dict()
+    n_utt = 1                                            # bounded sample per step
+    for w in range(max(1, min(args.warmup, 1))):
+        cpu_pipeline_step(sd, 1000 + w, n_utt)
+    t0 = time.time()
+    for k in range(args.steps):
+        cpu_pipeline_step(sd, k, n_utt)
+    dt = time.time() - t0
+    val = args.steps * n_utt * SECONDS / dt
+    cb = {"value": val, "unit": "audio-s/s", "cores": os.cpu_count(), "kind": "port",
+          "sample": "each step = %d utterance of %.0f s of the workload (of %d per GPU), oracle port of the "
+                    "reference's PyTorch-CPU path, torch threads=%d" % (n_utt, SECONDS, args.utterances, os.cpu_count())}
+    print(json.dumps({"impl": "reference", "metric": "embed+attack+extract audio-seconds per second", "value": val,
+                      "unit": "audio-s/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                      "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+                      "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config(args),
+                      "cpu_baseline": cb, "gpu_launches": 0,
+                      "e2e": {"value": val, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == "Active" for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from image_in_speech_watermarking_b200 import _lib, synthetic as SY
+    from image_in_speech_watermarking_b200.model import UformerAudio
+    from image_in_speech_watermarking_b200 import audio_test as PT
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+
+    B = args.utterances
+    model = UformerAudio(precision=args.precision, clips_per_pass=args.chunk).cuda().eval()   # reference-style random init
+    host_w = SY.synth_speech_batch(rank * B, B, SECONDS).pin_memory()
+    host_m = torch.stack([SY.synth_image_binary(rank * B + i) for i in range(B)]).pin_memory()
+    waves, msgs = host_w.to(dev), host_m.to(dev)
+    stats_sum = torch.zeros(8, device=dev, dtype=torch.float64)
+
+    def step(w, m):
+        r = PT.embed_attack_extract(w, m, model, ATTACK, seed=1, want_outputs=False)
+        s = r["stats"]
+        vec = torch.stack([s[:, 4].sum(), torch.tensor(1024.0 * B, device=dev, dtype=torch.float64), s[:, 5].sum(),
+                           s[:, 6].sum(), s[:, 0].sum(), s[:, 1].sum(), s[:, 3].sum(),
+                           torch.tensor(float(B), device=dev, dtype=torch.float64)])
+        if world > 1:
+            dist.all_reduce(vec)           # the path's only collective: BER / SNR statistics (NCCL)
+        return vec
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step(waves, msgs)
+    # ---- device-resident timing (value)
+    _lib.profile_enable(True)
+    _lib.profile_collect()
+    sampler = ClockSampler(local)
+    sync()
+    if rank == 0:
+        sampler.start()
+    l0 = lib.wmk_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        vec = step(waves, msgs)
+    e1.record()
+    sync()
+    launches = (lib.wmk_launch_count() - l0) // args.steps
+    ms = e0.elapsed_time(e1) / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+    fam = _lib.profile_collect()
+    _lib.profile_enable(False)
+    # ---- end to end through the public API with host buffers
+    sync()
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        w = host_w.to(dev, non_blocking=True)
+        m = host_m.to(dev, non_blocking=True)
+        out = step(w, m).cpu()
+    t1.record()
+    sync()
+    ms_e2e = t0.elapsed_time(t1) / args.steps
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    total_audio = B * SECONDS * world
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+    g = fam["gemm"]
+    ach = g["work"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] > 0 else 0.0
+    step_ms_families = {k: round(v["ms"] / args.steps, 3) for k, v in fam.items()}
+    roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel" if args.precision == "bf16" else "gemm_fp32_kernel",
+                "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
+                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks
+                else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)",
+                "traffic": None, "launches_per_step": g["launches"] // args.steps,
+                "avg_launch_ms": g["ms"] / max(1, g["launches"]), "algorithmic_gflop_per_launch": g["work"] / max(1, g["launches"]) / 1e9,
+                "share_of_step": g["ms"] / args.steps / ms, "family_ms_per_step": step_ms_families}
+    st = fam["stft"]
+    if st["ms"] > 0:
+        roofline["stft_gbs"] = st["work"] / (st["ms"] * 1e-3) / 1e9
+        roofline["stft_frac_of_hbm"] = roofline["stft_gbs"] / peaks.get("hbm_gbs", 6650.0)
+    line = {"metric": "embed+attack+extract audio-seconds per second", "value": total_audio / (ms * 1e-3),
+            "unit": "audio-s/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic", "config": config(args),
+            "e2e": {"value": total_audio / (ms_e2e * 1e-3), "unit": "audio-s/s",
+                    "h2d_bytes_per_step": host_w.numel() * 4 + host_m.numel() * 4, "d2h_bytes_per_step": 8 * 8,
+                    "ms_per_step": ms_e2e},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+            "stats": {"ber_clean": float(vec[0] / vec[1]), "ber_attacked": float(vec[2] / vec[3]),
+                      "mean_snr_db": float(vec[4] / vec[7])}}
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline()
+    else:
+        line["cpu_baseline"] = None
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

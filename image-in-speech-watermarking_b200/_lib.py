@@ -16,6 +16,10 @@ SIGNATURES = {
     "wmk_version": (_i, []),
     "wmk_last_error": (ctypes.c_char_p, []),
     "wmk_launch_count": (_u64, []),
+    "wmk_profile_enable": (_i, [_i]),
+    "wmk_profile_num_families": (_i, []),
+    "wmk_profile_family_name": (ctypes.c_char_p, [_i]),
+    "wmk_profile_collect": (_i, [_dp, _dp, ctypes.POINTER(ctypes.c_uint64)]),
     "wmk_stft_num_frames": (_i, [_i]),
     "wmk_stft_clips_f32": (_i, [_vp, _i, _i, _vp, _i, _vp]),
     "wmk_istft_clips_f32": (_i, [_vp, _i, _i, _i, _vp, _i, _vp]),
@@ -85,3 +89,19 @@ def ptr(t):
     if not t.is_contiguous():
         raise WmkError("expected a contiguous tensor")
     return ctypes.c_void_p(t.data_ptr())
+
+
+def profile_enable(on=True):
+    check(load().wmk_profile_enable(int(on)))
+
+
+def profile_collect():
+    """{family: {"ms", "work", "launches"}} accumulated since the last collect (synchronises)."""
+    lib = load()
+    n = lib.wmk_profile_num_families()
+    ms = (ctypes.c_double * n)()
+    work = (ctypes.c_double * n)()
+    cnt = (ctypes.c_uint64 * n)()
+    check(lib.wmk_profile_collect(ms, work, cnt))
+    return {lib.wmk_profile_family_name(i).decode(): {"ms": ms[i], "work": work[i], "launches": int(cnt[i])}
+            for i in range(n)}

@@ -242,6 +242,7 @@ using namespace wmk;
 extern "C" int wmk_attack_awgn_f32(const float* src, float* dst, int B, int L, float snr_db,
                                    const float* noise_unit, uint64_t seed, void* stream) {
   WMK_REQUIRE(src && dst && B > 0 && L > 0, "awgn: bad arguments");
+  ProfScope prof(FAM_ATTACK, 12.0 * B * L, (cudaStream_t)stream);
   cudaStream_t st = (cudaStream_t)stream;
   double* power = nullptr;
   WMK_CHECK_CUDA(cudaMallocAsync(&power, sizeof(double) * B, st));
@@ -256,6 +257,7 @@ extern "C" int wmk_attack_awgn_f32(const float* src, float* dst, int B, int L, f
 
 extern "C" int wmk_attack_scale_f32(const float* src, float* dst, int B, int L, float factor, void* stream) {
   WMK_REQUIRE(src && dst && B > 0 && L > 0, "scale: bad arguments");
+  ProfScope prof(FAM_ATTACK, 8.0 * B * L, (cudaStream_t)stream);
   elementwise_kernel<EW_SCALE><<<wave_grid(L, B), 256, 0, (cudaStream_t)stream>>>(src, dst, L, factor, 0);
   WMK_CHECK_LAUNCH("elementwise_kernel<scale>");
   return 0;
@@ -263,6 +265,7 @@ extern "C" int wmk_attack_scale_f32(const float* src, float* dst, int B, int L, 
 
 extern "C" int wmk_attack_echo_f32(const float* src, float* dst, int B, int L, int delay, float gain, void* stream) {
   WMK_REQUIRE(src && dst && src != dst && B > 0 && L > 0 && delay >= 0, "echo: bad arguments (in-place not allowed)");
+  ProfScope prof(FAM_ATTACK, 8.0 * B * L, (cudaStream_t)stream);
   elementwise_kernel<EW_ECHO><<<wave_grid(L, B), 256, 0, (cudaStream_t)stream>>>(src, dst, L, gain, delay);
   WMK_CHECK_LAUNCH("elementwise_kernel<echo>");
   return 0;
@@ -270,6 +273,7 @@ extern "C" int wmk_attack_echo_f32(const float* src, float* dst, int B, int L, i
 
 extern "C" int wmk_attack_requant8_f32(const float* src, float* dst, int B, int L, void* stream) {
   WMK_REQUIRE(src && dst && B > 0 && L > 0, "requant8: bad arguments");
+  ProfScope prof(FAM_ATTACK, 8.0 * B * L, (cudaStream_t)stream);
   elementwise_kernel<EW_REQUANT8><<<wave_grid(L, B), 256, 0, (cudaStream_t)stream>>>(src, dst, L, 0.f, 0);
   WMK_CHECK_LAUNCH("elementwise_kernel<requant8>");
   return 0;
@@ -277,6 +281,7 @@ extern "C" int wmk_attack_requant8_f32(const float* src, float* dst, int B, int 
 
 extern "C" int wmk_attack_jitter_zero_f32(float* wave, int B, int L, const int32_t* idx, int n_idx, void* stream) {
   WMK_REQUIRE(wave && idx && B > 0 && L > 0 && n_idx > 0, "jitter: bad arguments");
+  ProfScope prof(FAM_ATTACK, 8.0 * B * n_idx, (cudaStream_t)stream);
   jitter_zero_kernel<<<dim3(cdiv(n_idx, 256), B), 256, 0, (cudaStream_t)stream>>>(wave, L, idx, n_idx);
   WMK_CHECK_LAUNCH("jitter_zero_kernel");
   return 0;
@@ -286,6 +291,7 @@ extern "C" int wmk_attack_lowpass_f32(const float* src, float* dst, int B, int L
                                       const double* a_host, const double* zi_host, void* stream) {
   WMK_REQUIRE(src && dst && src != dst && B > 0 && order >= 1 && order <= MAXORD && b_host && a_host && zi_host,
               "lowpass: bad arguments (order <= %d, in-place not allowed)", MAXORD);
+  ProfScope prof(FAM_ATTACK, 8.0 * B * L, (cudaStream_t)stream);
   IirCoef cf;
   cf.order = order;
   cf.padlen = 3 * (order + 1);
@@ -323,6 +329,7 @@ extern "C" int wmk_attack_resample2_f32(const float* src, float* dst, int B, int
                                         void* stream) {
   WMK_REQUIRE(src && dst && src != dst && B > 0 && L > 0 && taps_host && n_taps > 0 && n_taps <= 1024 && (n_taps & 1),
               "resample2: bad arguments (odd n_taps <= 1024, in-place not allowed)");
+  ProfScope prof(FAM_ATTACK, 8.0 * B * L, (cudaStream_t)stream);
   cudaStream_t st = (cudaStream_t)stream;
   std::vector<float> hf(n_taps);
   for (int i = 0; i < n_taps; ++i) hf[i] = (float)taps_host[i];
@@ -343,6 +350,7 @@ extern "C" int wmk_attack_resample2_f32(const float* src, float* dst, int B, int
 
 extern "C" int wmk_wave_stats_f64(const float* orig, const float* test, int B, int L, double* stats, void* stream) {
   WMK_REQUIRE(orig && test && stats && B > 0 && L > 0, "wave_stats: bad arguments");
+  ProfScope prof(FAM_STATS, 8.0 * B * L, (cudaStream_t)stream);
   cudaStream_t st = (cudaStream_t)stream;
   WMK_CHECK_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 6 * B, st));
   wave_stats_kernel<<<wave_grid(L, B, 8), 256, 0, st>>>(orig, test, L, stats);
@@ -352,6 +360,7 @@ extern "C" int wmk_wave_stats_f64(const float* orig, const float* test, int B, i
 
 extern "C" int wmk_wm_stats_f64(const float* wm, const float* msg, int n, int msg_stride, double* stats, void* stream) {
   WMK_REQUIRE(wm && msg && stats && n > 0 && (msg_stride == 0 || msg_stride == 1024), "wm_stats: bad arguments");
+  ProfScope prof(FAM_STATS, 8.0 * 1024 * n, (cudaStream_t)stream);
   cudaStream_t st = (cudaStream_t)stream;
   WMK_CHECK_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * n, st));
   wm_stats_kernel<<<n, 256, 0, st>>>(wm, msg, msg_stride, stats);

@@ -183,6 +183,7 @@ int stft_clips(const float* wave, int B, int L, float* clips, int n_clips, cudaS
   WMK_REQUIRE(n_clips * 128 >= T, "stft: n_clips=%d cannot hold %d frames", n_clips, T);
   Twiddles tw;
   WMK_TRY(get_twiddles(&tw));
+  ProfScope prof(FAM_STFT, 1276.0 * T * B, st);
   dim3 grid(n_clips * 2, 4, B);
   stft_clips_kernel<<<grid, 256, 0, st>>>(wave, L, T, clips, n_clips, tw.fwd);
   WMK_CHECK_LAUNCH("stft_clips_kernel");
@@ -203,6 +204,7 @@ int istft_clips(const float* clips, int B, int n_clips, int T, float* wave, int 
     WMK_CHECK_CUDA(cudaFuncSetAttribute(istft_clips_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
+  ProfScope prof(FAM_ISTFT, 1276.0 * T * B, st);
   dim3 grid(cdiv(need, HOP * IFT), B);
   istft_clips_kernel<<<grid, 256, smem, st>>>(clips, n_clips, T, wave, length, tw.inv);
   WMK_CHECK_LAUNCH("istft_clips_kernel");

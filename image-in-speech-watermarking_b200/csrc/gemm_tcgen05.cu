@@ -333,6 +333,7 @@ int gemm_bf16_tcgen05(const GemmArgs& g, cudaStream_t st) {
   if (g.epi == EPI_UPSAMPLE)
     WMK_REQUIRE(g.up_cout % 32 == 0 && g.N == 4 * g.up_cout && g.M % (g.up_h * g.up_w) == 0,
                 "gemm_bf16: bad upsample geometry");
+  ProfScope prof(FAM_GEMM, 2.0 * g.M * g.N * g.K, st);
   if (g.N % 128 == 0) return launch<128>(g, st);
   if (g.N % 96 == 0) return launch<96>(g, st);
   if (g.N % 64 == 0) return launch<64>(g, st);

@@ -258,26 +258,36 @@ int run_block(wmk_plan* P, const BlockW& w, float* x, int n, cudaStream_t st) {
   OpT* O = reinterpret_cast<OpT*>(P->bufO);
   OpT* H1 = reinterpret_cast<OpT*>(P->bufH1);
   OpT* H2 = reinterpret_cast<OpT*>(P->bufH2);
-  layernorm_kernel<OpT><<<cdiv(M, 8), 256, 0, st>>>(x, A, w.ln1_w, w.ln1_b, w.mod, M, C, H, w.shift);
-  WMK_CHECK_LAUNCH("layernorm_kernel");
+  {
+    ProfScope prof(FAM_LAYERNORM, (double)M * C * (4 + sizeof(OpT)), st);
+    layernorm_kernel<OpT><<<cdiv(M, 8), 256, 0, st>>>(x, A, w.ln1_w, w.ln1_b, w.mod, M, C, H, w.shift);
+    WMK_CHECK_LAUNCH("layernorm_kernel");
+  }
   GemmArgs g;
   g.A = A; g.W = w.w_qkv; g.bias = w.b_qkv; g.C = QKV; g.M = M; g.N = 3 * C; g.K = C; g.ldc = 3 * C;
   g.epi = EPI_BIAS; g.out_bf16 = ob;
   WMK_TRY(gemm(P, g, st));
-  window_attention_kernel<OpT><<<dim3(n * (H / 8) * (H / 8), w.heads), 128, 0, st>>>(QKV, O, w.attn_bias, C, H, w.shift);
-  WMK_CHECK_LAUNCH("window_attention_kernel");
+  {
+    ProfScope prof(FAM_ATTENTION, 256.0 * C * M, st);
+    window_attention_kernel<OpT><<<dim3(n * (H / 8) * (H / 8), w.heads), 128, 0, st>>>(QKV, O, w.attn_bias, C, H, w.shift);
+    WMK_CHECK_LAUNCH("window_attention_kernel");
+  }
   g = GemmArgs();
   g.A = O; g.W = w.w_proj; g.bias = w.b_proj; g.resid = x; g.C = x; g.M = M; g.N = C; g.K = C; g.ldc = C;
   g.epi = EPI_BIAS_RESID; g.out_bf16 = 0;
   WMK_TRY(gemm(P, g, st));
-  layernorm_kernel<OpT><<<cdiv(M, 8), 256, 0, st>>>(x, A, w.ln2_w, w.ln2_b, nullptr, M, C, H, 0);
-  WMK_CHECK_LAUNCH("layernorm_kernel");
+  {
+    ProfScope prof(FAM_LAYERNORM, (double)M * C * (4 + sizeof(OpT)), st);
+    layernorm_kernel<OpT><<<cdiv(M, 8), 256, 0, st>>>(x, A, w.ln2_w, w.ln2_b, nullptr, M, C, H, 0);
+    WMK_CHECK_LAUNCH("layernorm_kernel");
+  }
   g = GemmArgs();
   g.A = A; g.W = w.w_l1; g.bias = w.b_l1; g.C = H1; g.M = M; g.N = 4 * C; g.K = C; g.ldc = 4 * C;
   g.epi = EPI_BIAS_GELU; g.out_bf16 = ob;
   WMK_TRY(gemm(P, g, st));
   {
     const size_t total = (size_t)M * C;     // (4C / 4) channel groups per pixel
+    ProfScope prof(FAM_DWCONV, 8.0 * M * C * sizeof(OpT), st);
     dwconv3x3_gelu_kernel<OpT><<<cdiv(total, 256), 256, 0, st>>>(H1, H2, w.dw_w, w.dw_b, n, H, 4 * C);
     WMK_CHECK_LAUNCH("dwconv3x3_gelu_kernel");
   }
@@ -303,6 +313,7 @@ int run_encoder(wmk_plan* P, const EncW& e, const float* x_nchw, int n, const ch
     const int Ho = H / 2;
     OpT* col = reinterpret_cast<OpT*>(P->bufH1);
     const size_t total = (size_t)n * Ho * Ho * 16 * (C / 4);
+    ProfScope prof_l(FAM_LAYOUT, (double)n * H * H * C * 4 + (double)n * Ho * Ho * 16 * C * sizeof(OpT), st);
     im2col_4x4s2_kernel<OpT><<<cdiv(total, 256), 256, 0, st>>>(P->E[s], col, n, H, C);
     WMK_CHECK_LAUNCH("im2col_4x4s2_kernel");
     GemmArgs g;

@@ -48,6 +48,21 @@ void count_launch(int n = 1);
     if (_s != 0) return _s;                                                               \
   } while (0)
 
+// ---------------------------------------------------------------------------------------------
+// Optional per-kernel-family timing with CUDA events on the launching stream (bench.py's live
+// roofline numbers; wmk_profile_* in wmk.h).  When disabled a scope costs one branch.
+// ---------------------------------------------------------------------------------------------
+enum Family {
+  FAM_GEMM = 0, FAM_ATTENTION, FAM_LAYERNORM, FAM_DWCONV, FAM_LAYOUT, FAM_SMALL, FAM_STFT, FAM_ISTFT,
+  FAM_ATTACK, FAM_STATS, FAM_COUNT
+};
+struct ProfScope {
+  ProfScope(int family, double work, cudaStream_t st);
+  ~ProfScope();
+  int slot;
+  cudaStream_t st;
+};
+
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // ---------------------------------------------------------------------------------------------

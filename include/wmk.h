@@ -51,6 +51,15 @@ const char* wmk_last_error(void);
  * gpu_launches) */
 uint64_t wmk_launch_count(void);
 
+/* Per-kernel-family device timing (CUDA events on the launching stream around every launch of the
+ * family).  collect() synchronises, fills ms / work / launches [wmk_profile_num_families()] with
+ * the totals since the last collect and resets them.  work = algorithmic FLOPs (gemm,
+ * window_attention) or algorithmic bytes (all other families). */
+int wmk_profile_enable(int on);
+int wmk_profile_num_families(void);
+const char* wmk_profile_family_name(int family);
+int wmk_profile_collect(double* ms, double* work, uint64_t* launches);
+
 /* ------------------------------------------------------------------------------------------
  * STFT / ISTFT front end.
  * Replaces torch.stft(x, n_fft=255) / torch.istft(spec, n_fft=255[, length]) at

@@ -144,7 +144,12 @@ def resampling(x):
 
 
 def apply_attack(x, attack, draws=None):
-    """Attack dispatch grammar `uformerWM/audio_test.py:631-660` ('name-p1[-p2]')."""
+    """Attack dispatch grammar `uformerWM/audio_test.py:631-660` ('name-p1[-p2]'); '+' chains
+    several attacks on the same waveform (BASELINE config 2: 'awgn-20+low_pass')."""
+    if "+" in attack:
+        for one in attack.split("+"):
+            x = apply_attack(x, one, draws)
+        return x
     p = attack.split("-")
     draws = draws or {}
     if p[0] == "echo_addition":
