@@ -32,41 +32,92 @@ __device__ __forceinline__ double warp_sum(double v) {
 // (cyclically shifted) 8x8 window, so the add commutes with roll + window_partition.
 // ------------------------------------------------------------------------------------------
 template <typename OpT>
+__device__ __forceinline__ void store4(OpT* p, float a, float b, float c, float d);
+template <>
+__device__ __forceinline__ void store4<float>(float* p, float a, float b, float c, float d) {
+  *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
+}
+template <>
+__device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* p, float a, float b, float c, float d) {
+  __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&lo);
+  u.y = *reinterpret_cast<uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+
+// One token is handled by G = min(32, C/4) lanes, each owning float4 chunks (C/4/G of them), so a
+// warp covers 32/G tokens and every global access is a 16-byte (fp32) / 8-byte (bf16) vector.
+template <typename OpT, int C>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, OpT* __restrict__ out, const float* __restrict__ gamma,
-                 const float* __restrict__ beta, const float* __restrict__ modulator, int M, int C, int H,
-                 int shift) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= M) return;
-  const float* xr = x + (size_t)warp * C;
-  const int per = C >> 5;                       // C in {32..512} -> 1..16 values per lane
-  float v[16];
+                 const float* __restrict__ beta, const float* __restrict__ modulator, int M, int H, int shift) {
+  constexpr int G = (C / 4 < 32) ? C / 4 : 32;      // lanes per token
+  constexpr int NV = C / 4 / G;                     // float4 chunks per lane
+  constexpr int TPW = 32 / G;                       // tokens per warp
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int sub = lane / G, gl = lane % G;
+  const int token = warp * TPW + sub;
+  const bool ok = token < M;
+  const float* xr = x + (size_t)(ok ? token : 0) * C;
+  float4 v[NV];
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < 16; ++i)
-    if (i < per) { v[i] = xr[i * 32 + lane]; s += v[i]; }
-  const float mean = warp_sum(s) / (float)C;
+  for (int i = 0; i < NV; ++i) {
+    v[i] = *reinterpret_cast<const float4*>(xr + (i * G + gl) * 4);
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s * (1.0f / C);
   float q = 0.f;
 #pragma unroll
-  for (int i = 0; i < 16; ++i)
-    if (i < per) { const float d = v[i] - mean; q += d * d; }
-  const float rstd = rsqrtf(warp_sum(q) / (float)C + 1e-5f);
+  for (int i = 0; i < NV; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q * (1.0f / C) + 1e-5f);
+  if (!ok) return;
   const float* mod = nullptr;
   if (modulator) {
-    const int hw = warp % (H * H);
+    const int hw = token % (H * H);
     const int h = hw / H, w = hw - h * H;
     const int hs = (h - shift + H) % H, ws = (w - shift + H) % H;
     mod = modulator + (size_t)(((hs & 7) << 3) | (ws & 7)) * C;
   }
-  OpT* o = out + (size_t)warp * C;
+  OpT* o = out + (size_t)token * C;
 #pragma unroll
-  for (int i = 0; i < 16; ++i)
-    if (i < per) {
-      const int c = i * 32 + lane;
-      float y = (v[i] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
-      if (mod) y += __ldg(mod + c);
-      o[c] = from_f<OpT>(y);
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * G + gl) * 4;
+    const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + c));
+    const float4 b4 = __ldg(reinterpret_cast<const float4*>(beta + c));
+    float y0 = (v[i].x - mean) * rstd * g4.x + b4.x, y1 = (v[i].y - mean) * rstd * g4.y + b4.y;
+    float y2 = (v[i].z - mean) * rstd * g4.z + b4.z, y3 = (v[i].w - mean) * rstd * g4.w + b4.w;
+    if (mod) {
+      const float4 m4 = __ldg(reinterpret_cast<const float4*>(mod + c));
+      y0 += m4.x; y1 += m4.y; y2 += m4.z; y3 += m4.w;
     }
+    store4<OpT>(o + c, y0, y1, y2, y3);
+  }
+}
+
+template <typename OpT>
+inline void launch_layernorm(const float* x, OpT* out, const float* gamma, const float* beta, const float* modulator,
+                             int M, int C, int H, int shift, cudaStream_t st) {
+  const int G = (C / 4 < 32) ? C / 4 : 32;
+  const int tpw = 32 / G;
+  const int warps = (M + tpw - 1) / tpw;
+  const int blocks = (warps + 7) / 8;
+  switch (C) {
+    case 32: layernorm_kernel<OpT, 32><<<blocks, 256, 0, st>>>(x, out, gamma, beta, modulator, M, H, shift); break;
+    case 64: layernorm_kernel<OpT, 64><<<blocks, 256, 0, st>>>(x, out, gamma, beta, modulator, M, H, shift); break;
+    case 128: layernorm_kernel<OpT, 128><<<blocks, 256, 0, st>>>(x, out, gamma, beta, modulator, M, H, shift); break;
+    case 256: layernorm_kernel<OpT, 256><<<blocks, 256, 0, st>>>(x, out, gamma, beta, modulator, M, H, shift); break;
+    default: layernorm_kernel<OpT, 512><<<blocks, 256, 0, st>>>(x, out, gamma, beta, modulator, M, H, shift); break;
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -151,54 +202,212 @@ window_attention_kernel(const OpT* __restrict__ qkv, OpT* __restrict__ out, cons
 }
 
 // ------------------------------------------------------------------------------------------
+// bf16 window attention on the tensor cores (mma.sync m16n8k16, fp32 accumulate): same math and
+// addressing as window_attention_kernel.  One CTA = one (window, head); warp w owns query rows
+// 16w..16w+15: S = Q K^T in registers (bias + shift mask + fp32 softmax), P re-used directly as the
+// A fragments of P V (no shared-memory round trip), O staged through smem for 16-byte stores.
+// The op is HBM-bound (8C bytes per token for ~256C FLOPs), so the legacy mma path is sufficient.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+constexpr int ATT_LD = 40;     // bf16 elements per smem row (80 B): conflict-free ldmatrix
+
+static __global__ void __launch_bounds__(128)
+window_attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
+                            const float* __restrict__ bias, int C, int H, int shift) {
+  __shared__ __align__(16) __nv_bfloat16 Qs[64 * ATT_LD], Ks[64 * ATT_LD], Vs[64 * ATT_LD];
+  __shared__ int tok[64], rid[64];
+  const int head = blockIdx.y;
+  const int nws = H >> 3;
+  const int win = blockIdx.x;
+  const int b = win / (nws * nws);
+  const int wrem = win - b * nws * nws;
+  const int wh = wrem / nws, ww = wrem - wh * nws;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid < 64) {
+    const int hs = wh * 8 + (tid >> 3), ws = ww * 8 + (tid & 7);
+    const int h = (hs + shift) % H, w = (ws + shift) % H;
+    tok[tid] = (b * H + h) * H + w;
+    const int rh = hs < H - 8 ? 0 : (hs < H - shift ? 1 : 2);
+    const int rw = ws < H - 8 ? 0 : (ws < H - shift ? 1 : 2);
+    rid[tid] = rh * 3 + rw;
+  }
+  __syncthreads();
+  // 64 rows x 4 chunks of 16 B for each of q, k, v
+  for (int e = tid; e < 64 * 4 * 3; e += 128) {
+    const int which = e >> 8, r = (e >> 2) & 63, ch = e & 3;
+    const uint4 v = *reinterpret_cast<const uint4*>(qkv + (size_t)tok[r] * (3 * C) + which * C + head * 32 + ch * 8);
+    __nv_bfloat16* dst = (which == 0 ? Qs : which == 1 ? Ks : Vs) + r * ATT_LD + ch * 8;
+    *reinterpret_cast<uint4*>(dst) = v;
+  }
+  __syncthreads();
+
+  const uint32_t qs = (uint32_t)__cvta_generic_to_shared(Qs), ks = (uint32_t)__cvta_generic_to_shared(Ks),
+                 vs = (uint32_t)__cvta_generic_to_shared(Vs);
+  const int r0 = warp * 16;
+  // ---- S = Q K^T
+  float sacc[8][4];
+#pragma unroll
+  for (int n = 0; n < 8; ++n) { sacc[n][0] = sacc[n][1] = sacc[n][2] = sacc[n][3] = 0.f; }
+#pragma unroll
+  for (int kk = 0; kk < 2; ++kk) {
+    uint32_t a[4];
+    ldmatrix_x4(a, qs + 2u * ((r0 + (lane & 7) + ((lane >> 3) & 1) * 8) * ATT_LD + kk * 16 + (lane >> 4) * 8));
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {           // two n-tiles (16 keys) per ldmatrix.x4
+      uint32_t bq[4];
+      ldmatrix_x4(bq, ks + 2u * ((np * 16 + (lane & 7) + (lane >> 4) * 8) * ATT_LD + kk * 16 + ((lane >> 3) & 1) * 8));
+      mma_bf16_16816(sacc[2 * np], a, bq[0], bq[1]);
+      mma_bf16_16816(sacc[2 * np + 1], a, bq[2], bq[3]);
+    }
+  }
+  // ---- + relative-position bias (+ shift mask), softmax over the 64 keys of each row
+  const int g = lane >> 2, t = lane & 3;
+  const int row0 = r0 + g, row1 = row0 + 8;
+  const float* bh = bias + (size_t)head * 4096;
+  const int rid0 = rid[row0], rid1 = rid[row1];
+  float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+  for (int n = 0; n < 8; ++n) {
+    const int col = n * 8 + 2 * t;
+    const float2 b0 = __ldg(reinterpret_cast<const float2*>(bh + row0 * 64 + col));
+    const float2 b1 = __ldg(reinterpret_cast<const float2*>(bh + row1 * 64 + col));
+    sacc[n][0] += b0.x; sacc[n][1] += b0.y; sacc[n][2] += b1.x; sacc[n][3] += b1.y;
+    if (shift > 0) {
+      const int c0 = rid[col], c1 = rid[col + 1];
+      if (c0 != rid0) sacc[n][0] -= 100.0f;
+      if (c1 != rid0) sacc[n][1] -= 100.0f;
+      if (c0 != rid1) sacc[n][2] -= 100.0f;
+      if (c1 != rid1) sacc[n][3] -= 100.0f;
+    }
+    m0 = fmaxf(m0, fmaxf(sacc[n][0], sacc[n][1]));
+    m1 = fmaxf(m1, fmaxf(sacc[n][2], sacc[n][3]));
+  }
+  m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+  m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+  for (int n = 0; n < 8; ++n) {
+    sacc[n][0] = __expf(sacc[n][0] - m0); sacc[n][1] = __expf(sacc[n][1] - m0);
+    sacc[n][2] = __expf(sacc[n][2] - m1); sacc[n][3] = __expf(sacc[n][3] - m1);
+    s0 += sacc[n][0] + sacc[n][1];
+    s1 += sacc[n][2] + sacc[n][3];
+  }
+  s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+  s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+  const float inv0 = 1.0f / s0, inv1 = 1.0f / s1;
+  // ---- O = P V   (P fragments come straight from the S accumulators)
+  float oacc[4][4];
+#pragma unroll
+  for (int n = 0; n < 4; ++n) { oacc[n][0] = oacc[n][1] = oacc[n][2] = oacc[n][3] = 0.f; }
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {             // 16 keys per step
+    uint32_t a[4];
+    a[0] = pack_bf16(sacc[2 * kk][0], sacc[2 * kk][1]);
+    a[1] = pack_bf16(sacc[2 * kk][2], sacc[2 * kk][3]);
+    a[2] = pack_bf16(sacc[2 * kk + 1][0], sacc[2 * kk + 1][1]);
+    a[3] = pack_bf16(sacc[2 * kk + 1][2], sacc[2 * kk + 1][3]);
+#pragma unroll
+    for (int np = 0; np < 2; ++np) {           // two n-tiles (16 dims) per ldmatrix.x4.trans
+      uint32_t bv[4];
+      ldmatrix_x4_trans(bv, vs + 2u * ((kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * ATT_LD + np * 16 + (lane >> 4) * 8));
+      mma_bf16_16816(oacc[2 * np], a, bv[0], bv[1]);
+      mma_bf16_16816(oacc[2 * np + 1], a, bv[2], bv[3]);
+    }
+  }
+  // ---- stage O (this warp's 16 rows) in the Q tile, then 16-byte stores to the token rows
+  __syncwarp();
+#pragma unroll
+  for (int n = 0; n < 4; ++n) {
+    *reinterpret_cast<uint32_t*>(Qs + row0 * ATT_LD + n * 8 + 2 * t) = pack_bf16(oacc[n][0] * inv0, oacc[n][1] * inv0);
+    *reinterpret_cast<uint32_t*>(Qs + row1 * ATT_LD + n * 8 + 2 * t) = pack_bf16(oacc[n][2] * inv1, oacc[n][3] * inv1);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int e = lane; e < 64; e += 32) {
+    const int r = r0 + (e >> 2), ch = e & 3;
+    const uint4 v = *reinterpret_cast<const uint4*>(Qs + r * ATT_LD + ch * 8);
+    *reinterpret_cast<uint4*>(out + (size_t)tok[r] * C + head * 32 + ch * 8) = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // LeFF depthwise 3x3 conv (pad 1) + GELU on the [B][H][W][Ch] hidden tensor
 // (uformerWM/model.py:688-689,706).  wt: [9][Ch] (tap-major), one thread = one pixel x 4 channels.
 // ------------------------------------------------------------------------------------------
+// One CTA = one 8x8 spatial tile x 32 channels: the 10x10 halo tile is staged in shared memory once
+// (1.56x read amplification instead of 9x through L2), each thread produces 1 pixel x 8 channels.
 template <typename OpT>
 __global__ void __launch_bounds__(256)
 dwconv3x3_gelu_kernel(const OpT* __restrict__ in, OpT* __restrict__ out, const float* __restrict__ wt,
                       const float* __restrict__ bias, int B, int H, int Ch) {
-  const int cg = Ch >> 2;
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t total = (size_t)B * H * H * cg;
-  if (idx >= total) return;
-  const int c = (int)(idx % cg) * 4;
-  const size_t pix = idx / cg;
-  const int w = (int)(pix % H);
-  const int h = (int)((pix / H) % H);
-  const size_t b = pix / ((size_t)H * H);
-  float acc[4];
-  {
-    const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c));
-    acc[0] = bb.x; acc[1] = bb.y; acc[2] = bb.z; acc[3] = bb.w;
-  }
-#pragma unroll
-  for (int dy = -1; dy <= 1; ++dy) {
-    const int hh = h + dy;
-    if (hh < 0 || hh >= H) continue;
-#pragma unroll
-    for (int dx = -1; dx <= 1; ++dx) {
-      const int wwp = w + dx;
-      if (wwp < 0 || wwp >= H) continue;
-      const OpT* src = in + ((b * H + hh) * H + wwp) * Ch + c;
-      const float4 k = __ldg(reinterpret_cast<const float4*>(wt + ((dy + 1) * 3 + (dx + 1)) * Ch + c));
-      float v0, v1, v2, v3;
+  __shared__ __align__(16) float tile[100][33];      // [halo pixel][channel], +1 pad
+  __shared__ float wsm[9][32], bsm[32];
+  const int c0 = blockIdx.y * 32;
+  const int tiles = H >> 3;
+  const int b = blockIdx.x / (tiles * tiles);
+  const int trem = blockIdx.x - b * tiles * tiles;
+  const int h0 = (trem / tiles) * 8, w0 = (trem % tiles) * 8;
+  const int tid = threadIdx.x;
+  for (int e = tid; e < 9 * 32; e += 256) wsm[e >> 5][e & 31] = __ldg(wt + (e >> 5) * Ch + c0 + (e & 31));
+  if (tid < 32) bsm[tid] = __ldg(bias + c0 + tid);
+  // halo load: 100 pixels x 4 chunks of 8 channels
+  for (int e = tid; e < 400; e += 256) {
+    const int px = e >> 2, ch = (e & 3) * 8;
+    const int hh = h0 + px / 10 - 1, wwp = w0 + px % 10 - 1;
+    float v[8];
+    if (hh >= 0 && hh < H && wwp >= 0 && wwp < H) {
+      const OpT* src = in + (((size_t)b * H + hh) * H + wwp) * Ch + c0 + ch;
       if constexpr (sizeof(OpT) == 4) {
-        const float4 v = *reinterpret_cast<const float4*>(src);
-        v0 = v.x; v1 = v.y; v2 = v.z; v3 = v.w;
+        const float4 a = *reinterpret_cast<const float4*>(src), c = *reinterpret_cast<const float4*>(src + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
       } else {
-        const uint2 u = *reinterpret_cast<const uint2*>(src);
-        const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&u.x);
-        const __nv_bfloat162 bq = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
-        v0 = __low2float(a); v1 = __high2float(a); v2 = __low2float(bq); v3 = __high2float(bq);
-      }
-      acc[0] = fmaf(v0, k.x, acc[0]); acc[1] = fmaf(v1, k.y, acc[1]);
-      acc[2] = fmaf(v2, k.z, acc[2]); acc[3] = fmaf(v3, k.w, acc[3]);
-    }
-  }
-  OpT* dst = out + pix * Ch + c;
+        const uint4 u = *reinterpret_cast<const uint4*>(src);
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
-  for (int j = 0; j < 4; ++j) dst[j] = from_f<OpT>(gelu_erf(acc[j]));
+        for (int j = 0; j < 4; ++j) { v[2 * j] = __low2float(h2[j]); v[2 * j + 1] = __high2float(h2[j]); }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) tile[px][ch + j] = v[j];
+  }
+  __syncthreads();
+  const int px = tid >> 2, ch = (tid & 3) * 8;
+  const int ph = px >> 3, pw = px & 7;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = bsm[ch + j];
+#pragma unroll
+  for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx) {
+      const float* tp = &tile[(ph + dy) * 10 + pw + dx][ch];
+      const float* wp = &wsm[dy * 3 + dx][ch];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaf(tp[j], wp[j], acc[j]);
+    }
+  OpT* dst = out + (((size_t)b * H + h0 + ph) * H + w0 + pw) * Ch + c0 + ch;
+  store4<OpT>(dst, gelu_erf(acc[0]), gelu_erf(acc[1]), gelu_erf(acc[2]), gelu_erf(acc[3]));
+  store4<OpT>(dst + 4, gelu_erf(acc[4]), gelu_erf(acc[5]), gelu_erf(acc[6]), gelu_erf(acc[7]));
 }
 
 // ------------------------------------------------------------------------------------------

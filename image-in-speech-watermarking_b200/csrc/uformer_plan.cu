@@ -260,7 +260,7 @@ int run_block(wmk_plan* P, const BlockW& w, float* x, int n, cudaStream_t st) {
   OpT* H2 = reinterpret_cast<OpT*>(P->bufH2);
   {
     ProfScope prof(FAM_LAYERNORM, (double)M * C * (4 + sizeof(OpT)), st);
-    layernorm_kernel<OpT><<<cdiv(M, 8), 256, 0, st>>>(x, A, w.ln1_w, w.ln1_b, w.mod, M, C, H, w.shift);
+    launch_layernorm<OpT>(x, A, w.ln1_w, w.ln1_b, w.mod, M, C, H, w.shift, st);
     WMK_CHECK_LAUNCH("layernorm_kernel");
   }
   GemmArgs g;
@@ -269,7 +269,10 @@ int run_block(wmk_plan* P, const BlockW& w, float* x, int n, cudaStream_t st) {
   WMK_TRY(gemm(P, g, st));
   {
     ProfScope prof(FAM_ATTENTION, 256.0 * C * M, st);
-    window_attention_kernel<OpT><<<dim3(n * (H / 8) * (H / 8), w.heads), 128, 0, st>>>(QKV, O, w.attn_bias, C, H, w.shift);
+    if constexpr (sizeof(OpT) == 2)
+      window_attention_mma_kernel<<<dim3(n * (H / 8) * (H / 8), w.heads), 128, 0, st>>>(QKV, O, w.attn_bias, C, H, w.shift);
+    else
+      window_attention_kernel<OpT><<<dim3(n * (H / 8) * (H / 8), w.heads), 128, 0, st>>>(QKV, O, w.attn_bias, C, H, w.shift);
     WMK_CHECK_LAUNCH("window_attention_kernel");
   }
   g = GemmArgs();
@@ -278,7 +281,7 @@ int run_block(wmk_plan* P, const BlockW& w, float* x, int n, cudaStream_t st) {
   WMK_TRY(gemm(P, g, st));
   {
     ProfScope prof(FAM_LAYERNORM, (double)M * C * (4 + sizeof(OpT)), st);
-    layernorm_kernel<OpT><<<cdiv(M, 8), 256, 0, st>>>(x, A, w.ln2_w, w.ln2_b, nullptr, M, C, H, 0);
+    launch_layernorm<OpT>(x, A, w.ln2_w, w.ln2_b, nullptr, M, C, H, 0, st);
     WMK_CHECK_LAUNCH("layernorm_kernel");
   }
   g = GemmArgs();
@@ -288,7 +291,8 @@ int run_block(wmk_plan* P, const BlockW& w, float* x, int n, cudaStream_t st) {
   {
     const size_t total = (size_t)M * C;     // (4C / 4) channel groups per pixel
     ProfScope prof(FAM_DWCONV, 8.0 * M * C * sizeof(OpT), st);
-    dwconv3x3_gelu_kernel<OpT><<<cdiv(total, 256), 256, 0, st>>>(H1, H2, w.dw_w, w.dw_b, n, H, 4 * C);
+    (void)total;
+    dwconv3x3_gelu_kernel<OpT><<<dim3(n * (H / 8) * (H / 8), (4 * C) / 32), 256, 0, st>>>(H1, H2, w.dw_w, w.dw_b, n, H, 4 * C);
     WMK_CHECK_LAUNCH("dwconv3x3_gelu_kernel");
   }
   g = GemmArgs();
