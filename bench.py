@@ -125,7 +125,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -189,13 +189,15 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()                       # started early: nvidia-smi start-up stalls the driver briefly
     for _ in range(max(args.warmup, 3)):
         step(waves, msgs)
-    # ---- device-resident timing (value): K steps, CUDA events on the launching stream
-    sampler = ClockSampler(local)
     sync()
-    if rank == 0:
-        sampler.start()
+    time.sleep(0.5)
+    n_before = len(sampler.rows)
+    # ---- device-resident timing (value): K steps, CUDA events on the launching stream
     l0 = lib.wmk_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -205,6 +207,8 @@ def run_ours(args):
     sync()
     launches = (lib.wmk_launch_count() - l0) // args.steps
     ms = e0.elapsed_time(e1) / args.steps
+    if rank == 0:
+        sampler.rows = sampler.rows[n_before:] if len(sampler.rows) > n_before + 1 else sampler.rows
     clocks = sampler.stop() if rank == 0 else None
     # ---- per-kernel-family durations: the same steps again with a CUDA-event pair around every
     # launch (kept out of the timed region above: ~8k extra event records per step cost host time)

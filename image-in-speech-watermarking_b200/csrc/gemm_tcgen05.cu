@@ -93,6 +93,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
 // UMMA shared-memory descriptor of a K-major, 128B-swizzled tile whose rows are 128 bytes
 // (64 bf16): 8-row swizzle atoms of 1024 B stacked along M/N (SBO = 1024 B); LBO unused.
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
@@ -216,7 +221,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       if (p.epi == EPI_BIAS_GELU) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+        for (int j = 0; j < 32; ++j) f[j] = gelu_fast(f[j]);
       } else if (p.epi == EPI_BIAS_RESID) {
         const float4* r4 = reinterpret_cast<const float4*>(p.resid + off);
 #pragma unroll
@@ -257,6 +262,224 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Persistent, warp-specialised version (all epilogues except the pixel-shuffle one):
+//   one CTA per SM loops over output tiles (n fastest, so CTAs that run together share A in L2);
+//   warp 0 TMA producer, warp 1 MMA issuer, warps 2-9 epilogue.  Two TMEM accumulators: the
+//   epilogue of tile i overlaps the main loop of tile i+1.  The epilogue stages each warp's
+//   32 rows x 128 B in swizzled shared memory and writes them with a TMA bulk-tensor store
+//   (coalesced, asynchronous, clips the M tail), double-buffered per warp.
+// ---------------------------------------------------------------------------------------------
+constexpr int kPThreads = 320;
+constexpr int kEpiWarps = 8;
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kPThreads, 1)
+gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                               const __grid_constant__ CUtensorMap tmC, EpiParams p, int K, int m_tiles,
+                               int n_tiles, int n_stages) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  constexpr uint32_t A_BYTES = BM * BK * 2;
+  constexpr uint32_t W_BYTES = BN * BK * 2;
+  constexpr uint32_t STAGE = A_BYTES + W_BYTES;
+  constexpr uint32_t STG_BYTES = 4096;                      // one staging box: 32 rows x 128 B
+  const uint32_t staging = base + (uint32_t)n_stages * STAGE;            // [8 warps][2][4096]
+  const uint32_t bars = staging + kEpiWarps * 2 * STG_BYTES;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (n_stages + s); };
+  const uint32_t tfull_bar = bars + 16u * n_stages;         // [2]
+  const uint32_t tempty_bar = tfull_bar + 16u;              // [2]
+  const uint32_t tmem_slot = tempty_bar + 16u;
+  volatile uint32_t* tmem_slot_ptr = (volatile uint32_t*)(smem_raw + (tmem_slot - raw));
+
+  constexpr int CPW = BN >= 128 ? BN / 2 : BN;              // accumulator columns per epilogue warp
+  constexpr int ACTIVE_EPI = (BN / CPW) * 4;                // epilogue warps with work
+  constexpr int TCOLS = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kblocks = (K + BK - 1) / BK;
+  const int total = m_tiles * n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
+    for (int s = 0; s < n_stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar + 8u * a, 1);
+      mbar_init(tempty_bar + 8u * a, ACTIVE_EPI);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TCOLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+        for (int kb = 0; kb < kblocks; ++kb, ++it) {
+          const int s = it % n_stages;
+          const uint32_t ph = (uint32_t)(it / n_stages) & 1u;
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          mbar_arrive_expect_tx(full_bar(s), STAGE);
+          const uint32_t sa = base + (uint32_t)s * STAGE;
+          tma_load_2d(sa, &tmA, kb * BK, m0, full_bar(s));
+          tma_load_2d(sa + A_BYTES, &tmW, kb * BK, n0, full_bar(s));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc(BN);
+      int it = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++lt) {
+        const int acc = lt & 1;
+        mbar_wait(tempty_bar + 8u * acc, ((uint32_t)(lt >> 1) & 1u) ^ 1u);      // epilogue drained this accumulator
+        tcgen05_fence_after();
+        const uint32_t tacc = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < kblocks; ++kb, ++it) {
+          const int s = it % n_stages;
+          const uint32_t ph = (uint32_t)(it / n_stages) & 1u;
+          mbar_wait(full_bar(s), ph);
+          tcgen05_fence_after();
+          const uint32_t sa = base + (uint32_t)s * STAGE;
+          const uint64_t adesc = umma_desc_sw128(sa);
+          const uint64_t bdesc = umma_desc_sw128(sa + A_BYTES);
+          const int krem = K - kb * BK;
+          const int ksteps = krem >= BK ? BK / UMMA_K : (krem + UMMA_K - 1) / UMMA_K;   // skip zero-filled K
+          for (int k = 0; k < ksteps; ++k)
+            tcgen05_mma_bf16(tacc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+          tcgen05_commit(empty_bar(s));
+        }
+        tcgen05_commit(tfull_bar + 8u * acc);
+      }
+    }
+  } else {
+    const int ew = warp - 2;
+    const int q = warp & 3;                       // TMEM lane quarter this warp may read
+    const int half = ew >> 2;                     // which CPW-wide column slab
+    if (half * CPW < BN) {
+      const uint32_t stg = staging + (uint32_t)ew * 2 * STG_BYTES;
+      const uint32_t sw = (uint32_t)(lane & 7);
+      int lt = 0, nstore = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++lt) {
+        const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+        const int acc = lt & 1;
+        const int row = m0 + q * 32 + lane;
+        const bool row_ok = row < p.M;
+        mbar_wait(tfull_bar + 8u * acc, (uint32_t)(lt >> 1) & 1u);
+        tcgen05_fence_after();
+        const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * CPW);
+#pragma unroll 1
+        for (int cc = 0; cc < CPW; cc += 32) {
+          uint32_t v[32];
+          tmem_ld32(tacc + (uint32_t)cc, v);
+          const int n = n0 + half * CPW + cc;
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (p.bias) {
+            const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b = __ldg(b4 + j);
+              f[4 * j] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
+            }
+          }
+          if (p.epi == EPI_BIAS_GELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = gelu_fast(f[j]);
+          } else if (p.epi == EPI_BIAS_RESID) {
+            if (row_ok) {
+              const float4* r4 = reinterpret_cast<const float4*>(p.resid + (size_t)row * p.ldc + n);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 r = r4[j];
+                f[4 * j] += r.x; f[4 * j + 1] += r.y; f[4 * j + 2] += r.z; f[4 * j + 3] += r.w;
+              }
+            }
+          }
+          if (p.out_bf16) {
+            // box = min(64, BN) bf16 columns; this 32-column piece is 4 of its 16-byte chunks
+            constexpr int BOXC = BN >= 64 ? 64 : 32;
+            const int piece = (cc % BOXC) / 32;                 // 0 or 1
+            const uint32_t buf = stg + (uint32_t)(nstore & 1) * STG_BYTES;
+            if (piece == 0) {
+              if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+              __syncwarp();
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t c16 = (uint32_t)(piece * 4 + j);
+              uint32_t off;
+              if (BOXC == 64) off = (uint32_t)lane * 128u + ((c16 ^ sw) << 4);                     // SWIZZLE_128B
+              else off = (uint32_t)lane * 64u + ((c16 ^ ((uint32_t)(lane >> 1) & 3u)) << 4);      // SWIZZLE_64B
+              st_shared_v4(buf + off, pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                           pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+            }
+            if ((cc % BOXC) + 32 == BOXC) {
+              asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+              __syncwarp();
+              if (lane == 0) tma_store_2d(&tmC, buf, n - (cc % BOXC), m0 + q * 32);
+              ++nstore;
+            }
+          } else {
+            const uint32_t buf = stg + (uint32_t)(nstore & 1) * STG_BYTES;
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              st_shared_v4(buf + (uint32_t)lane * 128u + (((uint32_t)j ^ sw) << 4), __float_as_uint(f[4 * j]),
+                           __float_as_uint(f[4 * j + 1]), __float_as_uint(f[4 * j + 2]), __float_as_uint(f[4 * j + 3]));
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) tma_store_2d(&tmC, buf, n, m0 + q * 32);
+            ++nstore;
+          }
+        }
+        // all tcgen05.ld of this accumulator have completed (tmem_ld32 waits): hand it back
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar + 8u * acc);
+      }
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TCOLS));
+  }
+}
+
 // ------------------------------------------------------------------------------------- host
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -276,24 +499,67 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// 2-D bf16 row-major [rows][K] tensor, box = 64 (K) x box_rows, 128B swizzle, zero OOB fill.
-int make_map(CUtensorMap* map, const void* ptr, int rows, int K, int box_rows) {
+// 2-D row-major [rows][cols] tensor of bf16 (or fp32), box = box_cols x box_rows, zero OOB fill.
+int make_map_ex(CUtensorMap* map, const void* ptr, int rows, int cols, int box_rows, int box_cols, bool f32) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
     return WMK_ERR_CUDA;
   }
-  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)K * 2};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  const int es_bytes = f32 ? 4 : 2;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * es_bytes};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t es[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box,
-                  es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+  const CUtensorMapSwizzle swz = box_cols * es_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUresult r = fn(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                  const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled failed (%d) for [%d][%d] box %d", (int)r, rows, K, box_rows);
+    set_error("cuTensorMapEncodeTiled failed (%d) for [%d][%d] box %dx%d", (int)r, rows, cols, box_rows, box_cols);
     return WMK_ERR_CUDA;
   }
+  return 0;
+}
+int make_map(CUtensorMap* map, const void* ptr, int rows, int K, int box_rows) {
+  return make_map_ex(map, ptr, rows, K, box_rows, BK, false);
+}
+
+int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+
+template <int BN>
+int launch_persistent(const GemmArgs& g, cudaStream_t st) {
+  CUtensorMap tmA, tmW, tmC;
+  WMK_TRY(make_map(&tmA, g.A, g.M, g.K, BM));
+  WMK_TRY(make_map(&tmW, g.W, g.N, g.K, BN));
+  const int box_cols = g.out_bf16 ? (BN >= 64 ? 64 : 32) : 32;
+  WMK_TRY(make_map_ex(&tmC, g.C, g.M, g.ldc, 32, box_cols, !g.out_bf16));
+  const int kblocks = cdiv(g.K, BK);
+  constexpr int stage = (BM + BN) * BK * 2;
+  constexpr int fixed = kEpiWarps * 2 * 4096 + 1024 + 256;
+  int n_stages = kblocks < 6 ? (kblocks < 2 ? 2 : kblocks) : 6;
+  while (n_stages > 2 && n_stages * stage + fixed > 220 * 1024) --n_stages;
+  const size_t smem = (size_t)n_stages * stage + fixed;
+  static bool attr_set = false;
+  if (!attr_set) {
+    WMK_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_persistent_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        224 * 1024));
+    attr_set = true;
+  }
+  EpiParams p{g.bias, g.resid, g.C, g.M, g.N, g.ldc, g.epi, g.out_bf16, g.up_h, g.up_w, g.up_cout};
+  const int n_tiles = g.N / BN, m_tiles = cdiv(g.M, BM);
+  const long long total = (long long)m_tiles * n_tiles;
+  const int grid = (int)(total < num_sms() ? total : num_sms());
+  gemm_tcgen05_persistent_kernel<BN><<<grid, kPThreads, smem, st>>>(tmA, tmW, tmC, p, g.K, m_tiles, n_tiles, n_stages);
+  WMK_CHECK_LAUNCH("gemm_tcgen05_persistent_kernel");
   return 0;
 }
 
@@ -334,6 +600,12 @@ int gemm_bf16_tcgen05(const GemmArgs& g, cudaStream_t st) {
     WMK_REQUIRE(g.up_cout % 32 == 0 && g.N == 4 * g.up_cout && g.M % (g.up_h * g.up_w) == 0,
                 "gemm_bf16: bad upsample geometry");
   ProfScope prof(FAM_GEMM, 2.0 * g.M * g.N * g.K, st);
+  if (g.epi != EPI_UPSAMPLE && g.ldc == g.N) {
+    if (g.N % 256 == 0 && g.N >= 512) return launch_persistent<256>(g, st);
+    if (g.N % 128 == 0) return launch_persistent<128>(g, st);
+    if (g.N % 64 == 0) return launch_persistent<64>(g, st);
+    return launch_persistent<32>(g, st);
+  }
   if (g.N % 128 == 0) return launch<128>(g, st);
   if (g.N % 96 == 0) return launch<96>(g, st);
   if (g.N % 64 == 0) return launch<64>(g, st);

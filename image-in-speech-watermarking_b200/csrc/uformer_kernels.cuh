@@ -406,8 +406,10 @@ dwconv3x3_gelu_kernel(const OpT* __restrict__ in, OpT* __restrict__ out, const f
       for (int j = 0; j < 8; ++j) acc[j] = fmaf(tp[j], wp[j], acc[j]);
     }
   OpT* dst = out + (((size_t)b * H + h0 + ph) * H + w0 + pw) * Ch + c0 + ch;
-  store4<OpT>(dst, gelu_erf(acc[0]), gelu_erf(acc[1]), gelu_erf(acc[2]), gelu_erf(acc[3]));
-  store4<OpT>(dst + 4, gelu_erf(acc[4]), gelu_erf(acc[5]), gelu_erf(acc[6]), gelu_erf(acc[7]));
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = sizeof(OpT) == 2 ? gelu_fast(acc[j]) : gelu_erf(acc[j]);
+  store4<OpT>(dst, acc[0], acc[1], acc[2], acc[3]);
+  store4<OpT>(dst + 4, acc[4], acc[5], acc[6], acc[7]);
 }
 
 // ------------------------------------------------------------------------------------------

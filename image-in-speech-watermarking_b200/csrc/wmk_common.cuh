@@ -98,6 +98,19 @@ int gemm_bf16_tcgen05(const GemmArgs& g, cudaStream_t st);
 __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
+// Same function with erf from Abramowitz-Stegun 7.1.26 (|error| < 1.5e-7, far below the bf16
+// rounding of the value it feeds): one MUFU.RCP + one MUFU.EX2 + 8 FMA instead of erff's ~40
+// instructions.  Used by every bf16-mode kernel; the fp32 parity mode keeps erff.
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float erf_abs = fmaf(-poly * t, __expf(-z * z), 1.0f);
+  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+}
 
 // Where element (m, n) of a GEMM result is stored.
 struct EpiParams {
