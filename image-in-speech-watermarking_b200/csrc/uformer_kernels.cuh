@@ -233,9 +233,10 @@ window_attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16
                             const float* __restrict__ bias, int C, int H, int shift) {
   __shared__ __align__(16) __nv_bfloat16 Qs[64 * ATT_LD], Ks[64 * ATT_LD], Vs[64 * ATT_LD];
   __shared__ int tok[64], rid[64];
-  const int head = blockIdx.y;
+  const int heads = C >> 5;
+  const int head = blockIdx.x % heads;      // heads fastest: neighbouring CTAs read adjacent 64-byte segments
   const int nws = H >> 3;
-  const int win = blockIdx.x;
+  const int win = blockIdx.x / heads;
   const int b = win / (nws * nws);
   const int wrem = win - b * nws * nws;
   const int wh = wrem / nws, ww = wrem - wh * nws;
@@ -352,64 +353,85 @@ window_attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16
 // (uformerWM/model.py:688-689,706).  wt: [9][Ch] (tap-major), one thread = one pixel x 4 channels.
 // ------------------------------------------------------------------------------------------
 // One CTA = one 8x8 spatial tile x 32 channels: the 10x10 halo tile is staged in shared memory once
-// (1.56x read amplification instead of 9x through L2), each thread produces 1 pixel x 8 channels.
+// (1.56x read amplification instead of 9x through L2); each thread produces 1 pixel x 8 channels
+// with its 72 weights in registers and 16-byte shared-memory reads (row stride 36 floats keeps them
+// conflict-free).  Channel slabs are the fastest-varying CTA index so neighbouring CTAs read
+// adjacent 64-byte segments of the same pixels.
 template <typename OpT>
 __global__ void __launch_bounds__(256)
 dwconv3x3_gelu_kernel(const OpT* __restrict__ in, OpT* __restrict__ out, const float* __restrict__ wt,
                       const float* __restrict__ bias, int B, int H, int Ch) {
-  __shared__ __align__(16) float tile[100][33];      // [halo pixel][channel], +1 pad
-  __shared__ float wsm[9][32], bsm[32];
-  const int c0 = blockIdx.y * 32;
+  __shared__ __align__(16) float tile[100 * 36];
+  const int ncg = Ch >> 5;
+  const int c0 = (blockIdx.x % ncg) * 32;
+  const int sp = blockIdx.x / ncg;
   const int tiles = H >> 3;
-  const int b = blockIdx.x / (tiles * tiles);
-  const int trem = blockIdx.x - b * tiles * tiles;
+  const int b = sp / (tiles * tiles);
+  const int trem = sp - b * tiles * tiles;
   const int h0 = (trem / tiles) * 8, w0 = (trem % tiles) * 8;
   const int tid = threadIdx.x;
-  for (int e = tid; e < 9 * 32; e += 256) wsm[e >> 5][e & 31] = __ldg(wt + (e >> 5) * Ch + c0 + (e & 31));
-  if (tid < 32) bsm[tid] = __ldg(bias + c0 + tid);
+  const int px = tid >> 2, ch = (tid & 3) * 8;
+  // this thread's 9 x 8 weights and bias (L1/L2 resident)
+  float wreg[9][8], acc[8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(wt + (size_t)t * Ch + c0 + ch));
+    const float4 c = __ldg(reinterpret_cast<const float4*>(wt + (size_t)t * Ch + c0 + ch + 4));
+    wreg[t][0] = a.x; wreg[t][1] = a.y; wreg[t][2] = a.z; wreg[t][3] = a.w;
+    wreg[t][4] = c.x; wreg[t][5] = c.y; wreg[t][6] = c.z; wreg[t][7] = c.w;
+  }
+  {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(bias + c0 + ch));
+    const float4 c = __ldg(reinterpret_cast<const float4*>(bias + c0 + ch + 4));
+    acc[0] = a.x; acc[1] = a.y; acc[2] = a.z; acc[3] = a.w; acc[4] = c.x; acc[5] = c.y; acc[6] = c.z; acc[7] = c.w;
+  }
   // halo load: 100 pixels x 4 chunks of 8 channels
   for (int e = tid; e < 400; e += 256) {
-    const int px = e >> 2, ch = (e & 3) * 8;
-    const int hh = h0 + px / 10 - 1, wwp = w0 + px % 10 - 1;
-    float v[8];
+    const int hp = e >> 2, hc = (e & 3) * 8;
+    const int hh = h0 + hp / 10 - 1, wwp = w0 + hp % 10 - 1;
+    float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
     if (hh >= 0 && hh < H && wwp >= 0 && wwp < H) {
-      const OpT* src = in + (((size_t)b * H + hh) * H + wwp) * Ch + c0 + ch;
+      const OpT* src = in + (((size_t)b * H + hh) * H + wwp) * Ch + c0 + hc;
       if constexpr (sizeof(OpT) == 4) {
-        const float4 a = *reinterpret_cast<const float4*>(src), c = *reinterpret_cast<const float4*>(src + 4);
-        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
+        lo = *reinterpret_cast<const float4*>(src);
+        hi = *reinterpret_cast<const float4*>(src + 4);
       } else {
         const uint4 u = *reinterpret_cast<const uint4*>(src);
         const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { v[2 * j] = __low2float(h2[j]); v[2 * j + 1] = __high2float(h2[j]); }
+        lo = make_float4(__low2float(h2[0]), __high2float(h2[0]), __low2float(h2[1]), __high2float(h2[1]));
+        hi = make_float4(__low2float(h2[2]), __high2float(h2[2]), __low2float(h2[3]), __high2float(h2[3]));
       }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = 0.f;
     }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) tile[px][ch + j] = v[j];
+    *reinterpret_cast<float4*>(&tile[hp * 36 + hc]) = lo;
+    *reinterpret_cast<float4*>(&tile[hp * 36 + hc + 4]) = hi;
   }
   __syncthreads();
-  const int px = tid >> 2, ch = (tid & 3) * 8;
   const int ph = px >> 3, pw = px & 7;
-  float acc[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = bsm[ch + j];
 #pragma unroll
   for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
     for (int dx = 0; dx < 3; ++dx) {
-      const float* tp = &tile[(ph + dy) * 10 + pw + dx][ch];
-      const float* wp = &wsm[dy * 3 + dx][ch];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = fmaf(tp[j], wp[j], acc[j]);
+      const float* tp = &tile[((ph + dy) * 10 + pw + dx) * 36 + ch];
+      const float4 lo = *reinterpret_cast<const float4*>(tp);
+      const float4 hi = *reinterpret_cast<const float4*>(tp + 4);
+      const float* w = wreg[dy * 3 + dx];
+      acc[0] = fmaf(lo.x, w[0], acc[0]); acc[1] = fmaf(lo.y, w[1], acc[1]);
+      acc[2] = fmaf(lo.z, w[2], acc[2]); acc[3] = fmaf(lo.w, w[3], acc[3]);
+      acc[4] = fmaf(hi.x, w[4], acc[4]); acc[5] = fmaf(hi.y, w[5], acc[5]);
+      acc[6] = fmaf(hi.z, w[6], acc[6]); acc[7] = fmaf(hi.w, w[7], acc[7]);
     }
   OpT* dst = out + (((size_t)b * H + h0 + ph) * H + w0 + pw) * Ch + c0 + ch;
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = sizeof(OpT) == 2 ? gelu_fast(acc[j]) : gelu_erf(acc[j]);
-  store4<OpT>(dst, acc[0], acc[1], acc[2], acc[3]);
-  store4<OpT>(dst + 4, acc[4], acc[5], acc[6], acc[7]);
+  if constexpr (sizeof(OpT) == 2) {
+    uint4 u;
+    u.x = pack_bf16(acc[0], acc[1]); u.y = pack_bf16(acc[2], acc[3]);
+    u.z = pack_bf16(acc[4], acc[5]); u.w = pack_bf16(acc[6], acc[7]);
+    *reinterpret_cast<uint4*>(dst) = u;
+  } else {
+    store4<OpT>(dst, acc[0], acc[1], acc[2], acc[3]);
+    store4<OpT>(dst + 4, acc[4], acc[5], acc[6], acc[7]);
+  }
 }
 
 // ------------------------------------------------------------------------------------------
