@@ -352,85 +352,75 @@ window_attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16
 // LeFF depthwise 3x3 conv (pad 1) + GELU on the [B][H][W][Ch] hidden tensor
 // (uformerWM/model.py:688-689,706).  wt: [9][Ch] (tap-major), one thread = one pixel x 4 channels.
 // ------------------------------------------------------------------------------------------
-// One CTA = one 8x8 spatial tile x 32 channels: the 10x10 halo tile is staged in shared memory once
-// (1.56x read amplification instead of 9x through L2); each thread produces 1 pixel x 8 channels
-// with its 72 weights in registers and 16-byte shared-memory reads (row stride 36 floats keeps them
-// conflict-free).  Channel slabs are the fastest-varying CTA index so neighbouring CTAs read
-// adjacent 64-byte segments of the same pixels.
+// Register sliding window: one thread owns a column strip of 8 pixels x 4 channels of an 8x8
+// tile, keeps its 36 weights and a 3x3x4 input window in registers and loads only the 3 new
+// pixels of each row step (3 loads per output instead of 9; no shared memory, no barrier).
+// A warp = 2 adjacent columns x 64 channels, so every load / store instruction covers full
+// 128-byte lines; channel slabs are the fastest CTA index, then tiles in raster order, so halo
+// pixels shared with neighbouring CTAs are L2 hits.
 template <typename OpT>
-__global__ void __launch_bounds__(256)
+__device__ __forceinline__ void dw_load4(const OpT* p, bool valid, float (&v)[4]) {
+  if (!valid) { v[0] = v[1] = v[2] = v[3] = 0.f; return; }
+  if constexpr (sizeof(OpT) == 4) {
+    const float4 a = *reinterpret_cast<const float4*>(p);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+  } else {
+    const uint2 u = *reinterpret_cast<const uint2*>(p);
+    const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&u.x);
+    const __nv_bfloat162 hi = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+    v[0] = __low2float(lo); v[1] = __high2float(lo); v[2] = __low2float(hi); v[3] = __high2float(hi);
+  }
+}
+
+template <typename OpT>
+__global__ void __launch_bounds__(128)
 dwconv3x3_gelu_kernel(const OpT* __restrict__ in, OpT* __restrict__ out, const float* __restrict__ wt,
                       const float* __restrict__ bias, int B, int H, int Ch) {
-  __shared__ __align__(16) float tile[100 * 36];
-  const int ncg = Ch >> 5;
-  const int c0 = (blockIdx.x % ncg) * 32;
-  const int sp = blockIdx.x / ncg;
+  const int ncs = Ch >> 6;
+  const int slab = blockIdx.x % ncs;
+  const int sp = blockIdx.x / ncs;
   const int tiles = H >> 3;
   const int b = sp / (tiles * tiles);
   const int trem = sp - b * tiles * tiles;
-  const int h0 = (trem / tiles) * 8, w0 = (trem % tiles) * 8;
-  const int tid = threadIdx.x;
-  const int px = tid >> 2, ch = (tid & 3) * 8;
-  // this thread's 9 x 8 weights and bias (L1/L2 resident)
-  float wreg[9][8], acc[8];
+  const int h0 = (trem / tiles) * 8;
+  const int w = (trem % tiles) * 8 + (threadIdx.x >> 4);
+  const int c = slab * 64 + (threadIdx.x & 15) * 4;
+  float wreg[9][4], bz[4];
 #pragma unroll
   for (int t = 0; t < 9; ++t) {
-    const float4 a = __ldg(reinterpret_cast<const float4*>(wt + (size_t)t * Ch + c0 + ch));
-    const float4 c = __ldg(reinterpret_cast<const float4*>(wt + (size_t)t * Ch + c0 + ch + 4));
+    const float4 a = __ldg(reinterpret_cast<const float4*>(wt + (size_t)t * Ch + c));
     wreg[t][0] = a.x; wreg[t][1] = a.y; wreg[t][2] = a.z; wreg[t][3] = a.w;
-    wreg[t][4] = c.x; wreg[t][5] = c.y; wreg[t][6] = c.z; wreg[t][7] = c.w;
   }
   {
-    const float4 a = __ldg(reinterpret_cast<const float4*>(bias + c0 + ch));
-    const float4 c = __ldg(reinterpret_cast<const float4*>(bias + c0 + ch + 4));
-    acc[0] = a.x; acc[1] = a.y; acc[2] = a.z; acc[3] = a.w; acc[4] = c.x; acc[5] = c.y; acc[6] = c.z; acc[7] = c.w;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(bias + c));
+    bz[0] = a.x; bz[1] = a.y; bz[2] = a.z; bz[3] = a.w;
   }
-  // halo load: 100 pixels x 4 chunks of 8 channels
-  for (int e = tid; e < 400; e += 256) {
-    const int hp = e >> 2, hc = (e & 3) * 8;
-    const int hh = h0 + hp / 10 - 1, wwp = w0 + hp % 10 - 1;
-    float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
-    if (hh >= 0 && hh < H && wwp >= 0 && wwp < H) {
-      const OpT* src = in + (((size_t)b * H + hh) * H + wwp) * Ch + c0 + hc;
-      if constexpr (sizeof(OpT) == 4) {
-        lo = *reinterpret_cast<const float4*>(src);
-        hi = *reinterpret_cast<const float4*>(src + 4);
-      } else {
-        const uint4 u = *reinterpret_cast<const uint4*>(src);
-        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
-        lo = make_float4(__low2float(h2[0]), __high2float(h2[0]), __low2float(h2[1]), __high2float(h2[1]));
-        hi = make_float4(__low2float(h2[2]), __high2float(h2[2]), __low2float(h2[3]), __high2float(h2[3]));
-      }
-    }
-    *reinterpret_cast<float4*>(&tile[hp * 36 + hc]) = lo;
-    *reinterpret_cast<float4*>(&tile[hp * 36 + hc + 4]) = hi;
-  }
-  __syncthreads();
-  const int ph = px >> 3, pw = px & 7;
+  const OpT* img = in + (size_t)b * H * H * Ch + c;
+  OpT* oimg = out + (size_t)b * H * H * Ch + c;
+  const bool lv = w > 0, rv = w < H - 1;
+  float win[3][3][4];
+  auto load_row = [&](int hh, float (&dst)[3][4]) {
+    const bool hv = hh >= 0 && hh < H;
+    const OpT* rowp = img + ((size_t)hh * H + w) * Ch;
+    dw_load4<OpT>(rowp - Ch, hv && lv, dst[0]);
+    dw_load4<OpT>(rowp, hv, dst[1]);
+    dw_load4<OpT>(rowp + Ch, hv && rv, dst[2]);
+  };
+  load_row(h0 - 1, win[0]);
+  load_row(h0, win[1]);
 #pragma unroll
-  for (int dy = 0; dy < 3; ++dy)
+  for (int r = 0; r < 8; ++r) {
+    load_row(h0 + r + 1, win[(r + 2) % 3]);
+    float acc[4] = {bz[0], bz[1], bz[2], bz[3]};
 #pragma unroll
-    for (int dx = 0; dx < 3; ++dx) {
-      const float* tp = &tile[((ph + dy) * 10 + pw + dx) * 36 + ch];
-      const float4 lo = *reinterpret_cast<const float4*>(tp);
-      const float4 hi = *reinterpret_cast<const float4*>(tp + 4);
-      const float* w = wreg[dy * 3 + dx];
-      acc[0] = fmaf(lo.x, w[0], acc[0]); acc[1] = fmaf(lo.y, w[1], acc[1]);
-      acc[2] = fmaf(lo.z, w[2], acc[2]); acc[3] = fmaf(lo.w, w[3], acc[3]);
-      acc[4] = fmaf(hi.x, w[4], acc[4]); acc[5] = fmaf(hi.y, w[5], acc[5]);
-      acc[6] = fmaf(hi.z, w[6], acc[6]); acc[7] = fmaf(hi.w, w[7], acc[7]);
-    }
-  OpT* dst = out + (((size_t)b * H + h0 + ph) * H + w0 + pw) * Ch + c0 + ch;
+    for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = sizeof(OpT) == 2 ? gelu_fast(acc[j]) : gelu_erf(acc[j]);
-  if constexpr (sizeof(OpT) == 2) {
-    uint4 u;
-    u.x = pack_bf16(acc[0], acc[1]); u.y = pack_bf16(acc[2], acc[3]);
-    u.z = pack_bf16(acc[4], acc[5]); u.w = pack_bf16(acc[6], acc[7]);
-    *reinterpret_cast<uint4*>(dst) = u;
-  } else {
-    store4<OpT>(dst, acc[0], acc[1], acc[2], acc[3]);
-    store4<OpT>(dst + 4, acc[4], acc[5], acc[6], acc[7]);
+      for (int dx = 0; dx < 3; ++dx)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] = fmaf(win[(r + dy) % 3][dx][j], wreg[dy * 3 + dx][j], acc[j]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[j] = sizeof(OpT) == 2 ? gelu_fast(acc[j]) : gelu_erf(acc[j]);
+    store4<OpT>(oimg + ((size_t)(h0 + r) * H + w) * Ch, acc[0], acc[1], acc[2], acc[3]);
   }
 }
 

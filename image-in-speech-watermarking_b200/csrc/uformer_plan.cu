@@ -292,7 +292,7 @@ int run_block(wmk_plan* P, const BlockW& w, float* x, int n, cudaStream_t st) {
     const size_t total = (size_t)M * C;     // (4C / 4) channel groups per pixel
     ProfScope prof(FAM_DWCONV, 8.0 * M * C * sizeof(OpT), st);
     (void)total;
-    dwconv3x3_gelu_kernel<OpT><<<n * (H / 8) * (H / 8) * ((4 * C) / 32), 256, 0, st>>>(H1, H2, w.dw_w, w.dw_b, n, H, 4 * C);
+    dwconv3x3_gelu_kernel<OpT><<<n * (H / 8) * (H / 8) * ((4 * C) / 64), 128, 0, st>>>(H1, H2, w.dw_w, w.dw_b, n, H, 4 * C);
     WMK_CHECK_LAUNCH("dwconv3x3_gelu_kernel");
   }
   g = GemmArgs();
