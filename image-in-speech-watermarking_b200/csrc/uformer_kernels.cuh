@@ -227,124 +227,161 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 }
 
 constexpr int ATT_LD = 40;     // bf16 elements per smem row (80 B): conflict-free ldmatrix
+constexpr int ATT_TILE = 64 * ATT_LD;   // one 64 x 32 operand tile
 
+struct AttGeom {
+  int C, H, shift, heads, nws;
+};
+// token index and shift-mask region of row r (0..63) of window `win`
+__device__ __forceinline__ void att_row(const AttGeom& g, int win, int r, int& token, int& region) {
+  const int b = win / (g.nws * g.nws);
+  const int wrem = win - b * g.nws * g.nws;
+  const int wh = wrem / g.nws, ww = wrem - wh * g.nws;
+  const int hs = wh * 8 + (r >> 3), ws = ww * 8 + (r & 7);
+  int h = hs + g.shift, w = ws + g.shift;
+  if (h >= g.H) h -= g.H;
+  if (w >= g.H) w -= g.H;
+  token = (b * g.H + h) * g.H + w;
+  const int rh = hs < g.H - 8 ? 0 : (hs < g.H - g.shift ? 1 : 2);
+  const int rw = ws < g.H - 8 ? 0 : (ws < g.H - g.shift ? 1 : 2);
+  region = rh * 3 + rw;
+}
+
+// Persistent: each CTA loops over (window, head) items (heads fastest) and prefetches the next
+// item's q/k/v tiles with cp.async while the tensor cores work on the current one.
 static __global__ void __launch_bounds__(128)
 window_attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
-                            const float* __restrict__ bias, int C, int H, int shift) {
-  __shared__ __align__(16) __nv_bfloat16 Qs[64 * ATT_LD], Ks[64 * ATT_LD], Vs[64 * ATT_LD];
-  __shared__ int tok[64], rid[64];
-  const int heads = C >> 5;
-  const int head = blockIdx.x % heads;      // heads fastest: neighbouring CTAs read adjacent 64-byte segments
-  const int nws = H >> 3;
-  const int win = blockIdx.x / heads;
-  const int b = win / (nws * nws);
-  const int wrem = win - b * nws * nws;
-  const int wh = wrem / nws, ww = wrem - wh * nws;
+                            const float* __restrict__ bias, int C, int H, int shift, int n_items) {
+  __shared__ __align__(16) __nv_bfloat16 sbuf[2][3 * ATT_TILE];
+  __shared__ int s_tok[2][64], s_rid[2][64];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (tid < 64) {
-    const int hs = wh * 8 + (tid >> 3), ws = ww * 8 + (tid & 7);
-    const int h = (hs + shift) % H, w = (ws + shift) % H;
-    tok[tid] = (b * H + h) * H + w;
-    const int rh = hs < H - 8 ? 0 : (hs < H - shift ? 1 : 2);
-    const int rw = ws < H - 8 ? 0 : (ws < H - shift ? 1 : 2);
-    rid[tid] = rh * 3 + rw;
-  }
-  __syncthreads();
-  // 64 rows x 4 chunks of 16 B for each of q, k, v
-  for (int e = tid; e < 64 * 4 * 3; e += 128) {
-    const int which = e >> 8, r = (e >> 2) & 63, ch = e & 3;
-    const uint4 v = *reinterpret_cast<const uint4*>(qkv + (size_t)tok[r] * (3 * C) + which * C + head * 32 + ch * 8);
-    __nv_bfloat16* dst = (which == 0 ? Qs : which == 1 ? Ks : Vs) + r * ATT_LD + ch * 8;
-    *reinterpret_cast<uint4*>(dst) = v;
-  }
-  __syncthreads();
+  AttGeom g{C, H, shift, C >> 5, H >> 3};
 
-  const uint32_t qs = (uint32_t)__cvta_generic_to_shared(Qs), ks = (uint32_t)__cvta_generic_to_shared(Ks),
-                 vs = (uint32_t)__cvta_generic_to_shared(Vs);
-  const int r0 = warp * 16;
-  // ---- S = Q K^T
-  float sacc[8][4];
-#pragma unroll
-  for (int n = 0; n < 8; ++n) { sacc[n][0] = sacc[n][1] = sacc[n][2] = sacc[n][3] = 0.f; }
-#pragma unroll
-  for (int kk = 0; kk < 2; ++kk) {
-    uint32_t a[4];
-    ldmatrix_x4(a, qs + 2u * ((r0 + (lane & 7) + ((lane >> 3) & 1) * 8) * ATT_LD + kk * 16 + (lane >> 4) * 8));
-#pragma unroll
-    for (int np = 0; np < 4; ++np) {           // two n-tiles (16 keys) per ldmatrix.x4
-      uint32_t bq[4];
-      ldmatrix_x4(bq, ks + 2u * ((np * 16 + (lane & 7) + (lane >> 4) * 8) * ATT_LD + kk * 16 + ((lane >> 3) & 1) * 8));
-      mma_bf16_16816(sacc[2 * np], a, bq[0], bq[1]);
-      mma_bf16_16816(sacc[2 * np + 1], a, bq[2], bq[3]);
+  auto prefetch = [&](int item, int buf) {
+    const int head = item % g.heads, win = item / g.heads;
+    if (tid < 64) {
+      int t, r;
+      att_row(g, win, tid, t, r);
+      s_tok[buf][tid] = t;
+      s_rid[buf][tid] = r;
     }
-  }
-  // ---- + relative-position bias (+ shift mask), softmax over the 64 keys of each row
-  const int g = lane >> 2, t = lane & 3;
-  const int row0 = r0 + g, row1 = row0 + 8;
-  const float* bh = bias + (size_t)head * 4096;
-  const int rid0 = rid[row0], rid1 = rid[row1];
-  float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
-  for (int n = 0; n < 8; ++n) {
-    const int col = n * 8 + 2 * t;
-    const float2 b0 = __ldg(reinterpret_cast<const float2*>(bh + row0 * 64 + col));
-    const float2 b1 = __ldg(reinterpret_cast<const float2*>(bh + row1 * 64 + col));
-    sacc[n][0] += b0.x; sacc[n][1] += b0.y; sacc[n][2] += b1.x; sacc[n][3] += b1.y;
-    if (shift > 0) {
-      const int c0 = rid[col], c1 = rid[col + 1];
-      if (c0 != rid0) sacc[n][0] -= 100.0f;
-      if (c1 != rid0) sacc[n][1] -= 100.0f;
-      if (c0 != rid1) sacc[n][2] -= 100.0f;
-      if (c1 != rid1) sacc[n][3] -= 100.0f;
+    for (int i = 0; i < 6; ++i) {
+      const int e = tid + i * 128;
+      const int which = e >> 8, r = (e >> 2) & 63, ch = e & 3;
+      int t, rr;
+      att_row(g, win, r, t, rr);
+      const __nv_bfloat16* src = qkv + (size_t)t * (3 * C) + which * C + head * 32 + ch * 8;
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&sbuf[buf][which * ATT_TILE + r * ATT_LD + ch * 8]);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
     }
-    m0 = fmaxf(m0, fmaxf(sacc[n][0], sacc[n][1]));
-    m1 = fmaxf(m1, fmaxf(sacc[n][2], sacc[n][3]));
-  }
-  m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
-  m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
-  float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-  for (int n = 0; n < 8; ++n) {
-    sacc[n][0] = __expf(sacc[n][0] - m0); sacc[n][1] = __expf(sacc[n][1] - m0);
-    sacc[n][2] = __expf(sacc[n][2] - m1); sacc[n][3] = __expf(sacc[n][3] - m1);
-    s0 += sacc[n][0] + sacc[n][1];
-    s1 += sacc[n][2] + sacc[n][3];
-  }
-  s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
-  s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
-  const float inv0 = 1.0f / s0, inv1 = 1.0f / s1;
-  // ---- O = P V   (P fragments come straight from the S accumulators)
-  float oacc[4][4];
-#pragma unroll
-  for (int n = 0; n < 4; ++n) { oacc[n][0] = oacc[n][1] = oacc[n][2] = oacc[n][3] = 0.f; }
-#pragma unroll
-  for (int kk = 0; kk < 4; ++kk) {             // 16 keys per step
-    uint32_t a[4];
-    a[0] = pack_bf16(sacc[2 * kk][0], sacc[2 * kk][1]);
-    a[1] = pack_bf16(sacc[2 * kk][2], sacc[2 * kk][3]);
-    a[2] = pack_bf16(sacc[2 * kk + 1][0], sacc[2 * kk + 1][1]);
-    a[3] = pack_bf16(sacc[2 * kk + 1][2], sacc[2 * kk + 1][3]);
-#pragma unroll
-    for (int np = 0; np < 2; ++np) {           // two n-tiles (16 dims) per ldmatrix.x4.trans
-      uint32_t bv[4];
-      ldmatrix_x4_trans(bv, vs + 2u * ((kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * ATT_LD + np * 16 + (lane >> 4) * 8));
-      mma_bf16_16816(oacc[2 * np], a, bv[0], bv[1]);
-      mma_bf16_16816(oacc[2 * np + 1], a, bv[2], bv[3]);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  int item = blockIdx.x;
+  if (item >= n_items) return;
+  prefetch(item, 0);
+  for (int it = 0; item < n_items; item += gridDim.x, ++it) {
+    const int buf = it & 1;
+    const int next = item + gridDim.x;
+    if (next < n_items) {
+      prefetch(next, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
-  }
-  // ---- stage O (this warp's 16 rows) in the Q tile, then 16-byte stores to the token rows
-  __syncwarp();
+    __syncthreads();
+    const int head = item % g.heads;
+    __nv_bfloat16* Qs = &sbuf[buf][0];
+    const int* tok = s_tok[buf];
+    const int* rid = s_rid[buf];
+    const uint32_t qs = (uint32_t)__cvta_generic_to_shared(Qs), ks = qs + 2u * ATT_TILE, vs = qs + 4u * ATT_TILE;
+    const int r0 = warp * 16;
+    // ---- S = Q K^T
+    float sacc[8][4];
 #pragma unroll
-  for (int n = 0; n < 4; ++n) {
-    *reinterpret_cast<uint32_t*>(Qs + row0 * ATT_LD + n * 8 + 2 * t) = pack_bf16(oacc[n][0] * inv0, oacc[n][1] * inv0);
-    *reinterpret_cast<uint32_t*>(Qs + row1 * ATT_LD + n * 8 + 2 * t) = pack_bf16(oacc[n][2] * inv1, oacc[n][3] * inv1);
-  }
-  __syncwarp();
+    for (int n = 0; n < 8; ++n) { sacc[n][0] = sacc[n][1] = sacc[n][2] = sacc[n][3] = 0.f; }
 #pragma unroll
-  for (int e = lane; e < 64; e += 32) {
-    const int r = r0 + (e >> 2), ch = e & 3;
-    const uint4 v = *reinterpret_cast<const uint4*>(Qs + r * ATT_LD + ch * 8);
-    *reinterpret_cast<uint4*>(out + (size_t)tok[r] * C + head * 32 + ch * 8) = v;
+    for (int kk = 0; kk < 2; ++kk) {
+      uint32_t a[4];
+      ldmatrix_x4(a, qs + 2u * ((r0 + (lane & 7) + ((lane >> 3) & 1) * 8) * ATT_LD + kk * 16 + (lane >> 4) * 8));
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {           // two n-tiles (16 keys) per ldmatrix.x4
+        uint32_t bq[4];
+        ldmatrix_x4(bq, ks + 2u * ((np * 16 + (lane & 7) + (lane >> 4) * 8) * ATT_LD + kk * 16 + ((lane >> 3) & 1) * 8));
+        mma_bf16_16816(sacc[2 * np], a, bq[0], bq[1]);
+        mma_bf16_16816(sacc[2 * np + 1], a, bq[2], bq[3]);
+      }
+    }
+    // ---- + relative-position bias (+ shift mask), softmax over the 64 keys of each row
+    const int gq = lane >> 2, t = lane & 3;
+    const int row0 = r0 + gq, row1 = row0 + 8;
+    const float* bh = bias + (size_t)head * 4096;
+    const int rid0 = rid[row0], rid1 = rid[row1];
+    float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      const int col = n * 8 + 2 * t;
+      const float2 b0 = __ldg(reinterpret_cast<const float2*>(bh + row0 * 64 + col));
+      const float2 b1 = __ldg(reinterpret_cast<const float2*>(bh + row1 * 64 + col));
+      sacc[n][0] += b0.x; sacc[n][1] += b0.y; sacc[n][2] += b1.x; sacc[n][3] += b1.y;
+      if (shift > 0) {
+        const int c0 = rid[col], c1 = rid[col + 1];
+        if (c0 != rid0) sacc[n][0] -= 100.0f;
+        if (c1 != rid0) sacc[n][1] -= 100.0f;
+        if (c0 != rid1) sacc[n][2] -= 100.0f;
+        if (c1 != rid1) sacc[n][3] -= 100.0f;
+      }
+      m0 = fmaxf(m0, fmaxf(sacc[n][0], sacc[n][1]));
+      m1 = fmaxf(m1, fmaxf(sacc[n][2], sacc[n][3]));
+    }
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      sacc[n][0] = __expf(sacc[n][0] - m0); sacc[n][1] = __expf(sacc[n][1] - m0);
+      sacc[n][2] = __expf(sacc[n][2] - m1); sacc[n][3] = __expf(sacc[n][3] - m1);
+      s0 += sacc[n][0] + sacc[n][1];
+      s1 += sacc[n][2] + sacc[n][3];
+    }
+    s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+    const float inv0 = 1.0f / s0, inv1 = 1.0f / s1;
+    // ---- O = P V   (P fragments come straight from the S accumulators)
+    float oacc[4][4];
+#pragma unroll
+    for (int n = 0; n < 4; ++n) { oacc[n][0] = oacc[n][1] = oacc[n][2] = oacc[n][3] = 0.f; }
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {             // 16 keys per step
+      uint32_t a[4];
+      a[0] = pack_bf16(sacc[2 * kk][0], sacc[2 * kk][1]);
+      a[1] = pack_bf16(sacc[2 * kk][2], sacc[2 * kk][3]);
+      a[2] = pack_bf16(sacc[2 * kk + 1][0], sacc[2 * kk + 1][1]);
+      a[3] = pack_bf16(sacc[2 * kk + 1][2], sacc[2 * kk + 1][3]);
+#pragma unroll
+      for (int np = 0; np < 2; ++np) {           // two n-tiles (16 dims) per ldmatrix.x4.trans
+        uint32_t bv[4];
+        ldmatrix_x4_trans(bv, vs + 2u * ((kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * ATT_LD + np * 16 + (lane >> 4) * 8));
+        mma_bf16_16816(oacc[2 * np], a, bv[0], bv[1]);
+        mma_bf16_16816(oacc[2 * np + 1], a, bv[2], bv[3]);
+      }
+    }
+    // ---- stage O (this warp's 16 rows) in the Q tile, then 16-byte stores to the token rows
+    __syncwarp();
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      *reinterpret_cast<uint32_t*>(Qs + row0 * ATT_LD + n * 8 + 2 * t) = pack_bf16(oacc[n][0] * inv0, oacc[n][1] * inv0);
+      *reinterpret_cast<uint32_t*>(Qs + row1 * ATT_LD + n * 8 + 2 * t) = pack_bf16(oacc[n][2] * inv1, oacc[n][3] * inv1);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int e = lane; e < 64; e += 32) {
+      const int r = r0 + (e >> 2), ch = e & 3;
+      const uint4 v = *reinterpret_cast<const uint4*>(Qs + r * ATT_LD + ch * 8);
+      *reinterpret_cast<uint4*>(out + (size_t)tok[r] * C + head * 32 + ch * 8) = v;
+    }
+    __syncthreads();        // everyone is done with this buffer before it is refilled
   }
 }
 
@@ -421,6 +458,68 @@ dwconv3x3_gelu_kernel(const OpT* __restrict__ in, OpT* __restrict__ out, const f
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[j] = sizeof(OpT) == 2 ? gelu_fast(acc[j]) : gelu_erf(acc[j]);
     store4<OpT>(oimg + ((size_t)(h0 + r) * H + w) * Ch, acc[0], acc[1], acc[2], acc[3]);
+  }
+}
+
+// bf16 specialisation: all 30 input loads of the thread's strip are issued before any math (memory
+// level parallelism: the sliding version above is latency bound at ~1 TB/s), channel pairs are
+// processed with packed fp32x2 FMAs (sm_100 FFMA2).
+__device__ __forceinline__ float2 bf16x2_to_float2(uint32_t u) {
+  return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+}
+
+static __global__ void __launch_bounds__(128)
+dwconv3x3_gelu_bf16_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                           const float* __restrict__ wt, const float* __restrict__ bias, int B, int H, int Ch) {
+  const int ncs = Ch >> 6;
+  const int slab = blockIdx.x % ncs;
+  const int sp = blockIdx.x / ncs;
+  const int tiles = H >> 3;
+  const int b = sp / (tiles * tiles);
+  const int trem = sp - b * tiles * tiles;
+  const int h0 = (trem / tiles) * 8;
+  const int w = (trem % tiles) * 8 + (threadIdx.x >> 4);
+  const int c = slab * 64 + (threadIdx.x & 15) * 4;
+  const __nv_bfloat16* img = in + (size_t)b * H * H * Ch + c;
+  __nv_bfloat16* oimg = out + (size_t)b * H * H * Ch + c;
+  const bool lv = w > 0, rv = w < H - 1;
+  uint2 raw[10][3];
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const int hh = h0 + r - 1;
+    const bool hv = hh >= 0 && hh < H;
+    const __nv_bfloat16* rowp = img + ((size_t)hh * H + w) * Ch;
+    raw[r][0] = (hv && lv) ? *reinterpret_cast<const uint2*>(rowp - Ch) : make_uint2(0u, 0u);
+    raw[r][1] = hv ? *reinterpret_cast<const uint2*>(rowp) : make_uint2(0u, 0u);
+    raw[r][2] = (hv && rv) ? *reinterpret_cast<const uint2*>(rowp + Ch) : make_uint2(0u, 0u);
+  }
+  float2 wreg[9][2], bz[2];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(wt + (size_t)t * Ch + c));
+    wreg[t][0] = make_float2(a.x, a.y);
+    wreg[t][1] = make_float2(a.z, a.w);
+  }
+  {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(bias + c));
+    bz[0] = make_float2(a.x, a.y);
+    bz[1] = make_float2(a.z, a.w);
+  }
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    float2 a0 = bz[0], a1 = bz[1];
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const uint2 u = raw[r + dy][dx];
+        a0 = __ffma2_rn(bf16x2_to_float2(u.x), wreg[dy * 3 + dx][0], a0);
+        a1 = __ffma2_rn(bf16x2_to_float2(u.y), wreg[dy * 3 + dx][1], a1);
+      }
+    uint2 o;
+    o.x = pack_bf16(gelu_fast(a0.x), gelu_fast(a0.y));
+    o.y = pack_bf16(gelu_fast(a1.x), gelu_fast(a1.y));
+    *reinterpret_cast<uint2*>(oimg + ((size_t)(h0 + r) * H + w) * Ch) = o;
   }
 }
 

@@ -270,7 +270,11 @@ int run_block(wmk_plan* P, const BlockW& w, float* x, int n, cudaStream_t st) {
   {
     ProfScope prof(FAM_ATTENTION, 256.0 * C * M, st);
     if constexpr (sizeof(OpT) == 2)
-      window_attention_mma_kernel<<<n * (H / 8) * (H / 8) * w.heads, 128, 0, st>>>(QKV, O, w.attn_bias, C, H, w.shift);
+    {
+      const int items = n * (H / 8) * (H / 8) * w.heads;
+      const int grid = items < 148 * 6 ? items : 148 * 6;
+      window_attention_mma_kernel<<<grid, 128, 0, st>>>(QKV, O, w.attn_bias, C, H, w.shift, items);
+    }
     else
       window_attention_kernel<OpT><<<dim3(n * (H / 8) * (H / 8), w.heads), 128, 0, st>>>(QKV, O, w.attn_bias, C, H, w.shift);
     WMK_CHECK_LAUNCH("window_attention_kernel");
@@ -292,7 +296,10 @@ int run_block(wmk_plan* P, const BlockW& w, float* x, int n, cudaStream_t st) {
     const size_t total = (size_t)M * C;     // (4C / 4) channel groups per pixel
     ProfScope prof(FAM_DWCONV, 8.0 * M * C * sizeof(OpT), st);
     (void)total;
-    dwconv3x3_gelu_kernel<OpT><<<n * (H / 8) * (H / 8) * ((4 * C) / 64), 128, 0, st>>>(H1, H2, w.dw_w, w.dw_b, n, H, 4 * C);
+    if constexpr (sizeof(OpT) == 2)
+      dwconv3x3_gelu_bf16_kernel<<<n * (H / 8) * (H / 8) * ((4 * C) / 64), 128, 0, st>>>(H1, H2, w.dw_w, w.dw_b, n, H, 4 * C);
+    else
+      dwconv3x3_gelu_kernel<OpT><<<n * (H / 8) * (H / 8) * ((4 * C) / 64), 128, 0, st>>>(H1, H2, w.dw_w, w.dw_b, n, H, 4 * C);
     WMK_CHECK_LAUNCH("dwconv3x3_gelu_kernel");
   }
   g = GemmArgs();
