@@ -413,8 +413,16 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __
             }
           }
           if (p.epi == EPI_BIAS_GELU) {
+            if (p.out_bf16) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = gelu_fast(f[j]);
+              for (int j = 0; j < 16; ++j) {
+                const float2 gq = gelu_poly2(make_float2(f[2 * j], f[2 * j + 1]));
+                f[2 * j] = gq.x; f[2 * j + 1] = gq.y;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = gelu_fast(f[j]);
+            }
           } else if (p.epi == EPI_BIAS_RESID) {
             if (row_ok) {
               const float4* r4 = reinterpret_cast<const float4*>(p.resid + (size_t)row * p.ldc + n);

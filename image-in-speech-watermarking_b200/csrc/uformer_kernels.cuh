@@ -468,7 +468,7 @@ __device__ __forceinline__ float2 bf16x2_to_float2(uint32_t u) {
   return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
 }
 
-static __global__ void __launch_bounds__(128)
+static __global__ void __launch_bounds__(128, 4)
 dwconv3x3_gelu_bf16_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
                            const float* __restrict__ wt, const float* __restrict__ bias, int B, int H, int Ch) {
   const int ncs = Ch >> 6;
@@ -516,9 +516,11 @@ dwconv3x3_gelu_bf16_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* 
         a0 = __ffma2_rn(bf16x2_to_float2(u.x), wreg[dy * 3 + dx][0], a0);
         a1 = __ffma2_rn(bf16x2_to_float2(u.y), wreg[dy * 3 + dx][1], a1);
       }
+    a0 = gelu_poly2(a0);
+    a1 = gelu_poly2(a1);
     uint2 o;
-    o.x = pack_bf16(gelu_fast(a0.x), gelu_fast(a0.y));
-    o.y = pack_bf16(gelu_fast(a1.x), gelu_fast(a1.y));
+    o.x = pack_bf16(a0.x, a0.y);
+    o.y = pack_bf16(a1.x, a1.y);
     *reinterpret_cast<uint2*>(oimg + ((size_t)(h0 + r) * H + w) * Ch) = o;
   }
 }
