@@ -233,6 +233,21 @@ wm_stats_kernel(const float* __restrict__ wm, const float* __restrict__ msg, int
 
 dim3 wave_grid(int L, int B, int per_thread = 4) { return dim3(cdiv(L, 256 * per_thread), B); }
 
+// Scratch buffers come from the stream-ordered pool; keep its memory across synchronisation points
+// (the default release threshold of 0 hands it back to the driver at every sync, which costs
+// milliseconds on the next call).
+void keep_pool_memory() {
+  static bool done[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || done[dev]) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    uint64_t keep = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  done[dev] = true;
+}
+
 }  // namespace
 
 }  // namespace wmk
@@ -244,6 +259,7 @@ extern "C" int wmk_attack_awgn_f32(const float* src, float* dst, int B, int L, f
   WMK_REQUIRE(src && dst && B > 0 && L > 0, "awgn: bad arguments");
   ProfScope prof(FAM_ATTACK, 12.0 * B * L, (cudaStream_t)stream);
   cudaStream_t st = (cudaStream_t)stream;
+  keep_pool_memory();
   double* power = nullptr;
   WMK_CHECK_CUDA(cudaMallocAsync(&power, sizeof(double) * B, st));
   WMK_CHECK_CUDA(cudaMemsetAsync(power, 0, sizeof(double) * B, st));
@@ -314,6 +330,7 @@ extern "C" int wmk_attack_lowpass_f32(const float* src, float* dst, int B, int L
   }
   cudaStream_t st = (cudaStream_t)stream;
   const int Le = L + 2 * cf.padlen;
+  keep_pool_memory();
   double* tmp = nullptr;
   WMK_CHECK_CUDA(cudaMallocAsync(&tmp, sizeof(double) * (size_t)B * Le, st));
   dim3 grid(cdiv(cdiv(Le, CH), 128), B);
@@ -334,6 +351,7 @@ extern "C" int wmk_attack_resample2_f32(const float* src, float* dst, int B, int
   std::vector<float> hf(n_taps);
   for (int i = 0; i < n_taps; ++i) hf[i] = (float)taps_host[i];
   const int Ld = (L + 1) / 2;
+  keep_pool_memory();
   float *h = nullptr, *d = nullptr;
   WMK_CHECK_CUDA(cudaMallocAsync(&h, sizeof(float) * n_taps, st));
   WMK_CHECK_CUDA(cudaMallocAsync(&d, sizeof(float) * (size_t)B * Ld, st));
