@@ -266,13 +266,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // ---------------------------------------------------------------------------------------------
 // Persistent, warp-specialised version (all epilogues except the pixel-shuffle one):
 //   one CTA per SM loops over output tiles (n fastest, so CTAs that run together share A in L2);
-//   warp 0 TMA producer, warp 1 MMA issuer, warps 2-9 epilogue.  Two TMEM accumulators: the
-//   epilogue of tile i overlaps the main loop of tile i+1.  The epilogue stages each warp's
-//   32 rows x 128 B in swizzled shared memory and writes them with a TMA bulk-tensor store
-//   (coalesced, asynchronous, clips the M tail), double-buffered per warp.
+//   warp 0 TMA producer, warp 1 MMA issuer, warps 2-17 epilogue (four per TMEM lane quarter, each
+//   owning a column slab - the GELU / residual epilogues are instruction-issue bound, so they get
+//   16 warps).  Two TMEM accumulators: the epilogue of tile i overlaps the main loop of tile i+1.
+//   Each epilogue warp stages its 32 rows x <=128 B in swizzled shared memory and writes them with a
+//   TMA bulk-tensor store (coalesced, asynchronous, clips the M tail).
 // ---------------------------------------------------------------------------------------------
-constexpr int kPThreads = 320;
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = 16;
+constexpr int kPThreads = 64 + 32 * kEpiWarps;
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -286,7 +287,13 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-template <int BN>
+// columns of the accumulator each epilogue warp owns, and the TMA-store box width
+__host__ __device__ constexpr int epi_cpw(int bn) { return bn >= 128 ? bn / 4 : 32; }
+__host__ __device__ constexpr int epi_box_cols(int bn, bool out_bf16) {
+  return out_bf16 ? (epi_cpw(bn) >= 64 ? 64 : 32) : 32;
+}
+
+template <int BN, int EPI, bool OUT_BF16>
 __global__ void __launch_bounds__(kPThreads, 1)
 gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                                const __grid_constant__ CUtensorMap tmC, EpiParams p, int K, int m_tiles,
@@ -297,9 +304,9 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __
   constexpr uint32_t A_BYTES = BM * BK * 2;
   constexpr uint32_t W_BYTES = BN * BK * 2;
   constexpr uint32_t STAGE = A_BYTES + W_BYTES;
-  constexpr uint32_t STG_BYTES = 4096;                      // one staging box: 32 rows x 128 B
-  const uint32_t staging = base + (uint32_t)n_stages * STAGE;            // [8 warps][2][4096]
-  const uint32_t bars = staging + kEpiWarps * 2 * STG_BYTES;
+  constexpr uint32_t STG_BYTES = 4096;                      // one staging box: 32 rows x <=128 B
+  const uint32_t staging = base + (uint32_t)n_stages * STAGE;            // [16 warps][4096]
+  const uint32_t bars = staging + kEpiWarps * STG_BYTES;
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (n_stages + s); };
   const uint32_t tfull_bar = bars + 16u * n_stages;         // [2]
@@ -307,8 +314,10 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __
   const uint32_t tmem_slot = tempty_bar + 16u;
   volatile uint32_t* tmem_slot_ptr = (volatile uint32_t*)(smem_raw + (tmem_slot - raw));
 
-  constexpr int CPW = BN >= 128 ? BN / 2 : BN;              // accumulator columns per epilogue warp
-  constexpr int ACTIVE_EPI = (BN / CPW) * 4;                // epilogue warps with work
+  constexpr int CPW = epi_cpw(BN);
+  constexpr int SLABS = BN / CPW;                           // epilogue warps per lane quarter with work
+  constexpr int ACTIVE_EPI = SLABS * 4;
+  constexpr int BOXC = epi_box_cols(BN, OUT_BF16);
   constexpr int TCOLS = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -383,24 +392,22 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __
   } else {
     const int ew = warp - 2;
     const int q = warp & 3;                       // TMEM lane quarter this warp may read
-    const int half = ew >> 2;                     // which CPW-wide column slab
-    if (half * CPW < BN) {
-      const uint32_t stg = staging + (uint32_t)ew * 2 * STG_BYTES;
-      const uint32_t sw = (uint32_t)(lane & 7);
-      int lt = 0, nstore = 0;
+    const int slab = ew >> 2;                     // which CPW-wide column slab
+    if (slab < SLABS) {
+      const uint32_t buf = staging + (uint32_t)ew * STG_BYTES;
+      int lt = 0;
       for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++lt) {
         const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
         const int acc = lt & 1;
         const int row = m0 + q * 32 + lane;
-        const bool row_ok = row < p.M;
         mbar_wait(tfull_bar + 8u * acc, (uint32_t)(lt >> 1) & 1u);
         tcgen05_fence_after();
-        const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * CPW);
+        const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + slab * CPW);
 #pragma unroll 1
         for (int cc = 0; cc < CPW; cc += 32) {
           uint32_t v[32];
           tmem_ld32(tacc + (uint32_t)cc, v);
-          const int n = n0 + half * CPW + cc;
+          const int n = n0 + slab * CPW + cc;
           float f[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
@@ -412,19 +419,14 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __
               f[4 * j] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
             }
           }
-          if (p.epi == EPI_BIAS_GELU) {
-            if (p.out_bf16) {
+          if constexpr (EPI == EPI_BIAS_GELU) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const float2 gq = gelu_poly2(make_float2(f[2 * j], f[2 * j + 1]));
-                f[2 * j] = gq.x; f[2 * j + 1] = gq.y;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = gelu_fast(f[j]);
+            for (int j = 0; j < 16; ++j) {
+              const float2 gq = gelu_poly2(make_float2(f[2 * j], f[2 * j + 1]));
+              f[2 * j] = gq.x; f[2 * j + 1] = gq.y;
             }
-          } else if (p.epi == EPI_BIAS_RESID) {
-            if (row_ok) {
+          } else if constexpr (EPI == EPI_BIAS_RESID) {
+            if (row < p.M) {
               const float4* r4 = reinterpret_cast<const float4*>(p.resid + (size_t)row * p.ldc + n);
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
@@ -433,21 +435,20 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __
               }
             }
           }
-          if (p.out_bf16) {
-            // box = min(64, BN) bf16 columns; this 32-column piece is 4 of its 16-byte chunks
-            constexpr int BOXC = BN >= 64 ? 64 : 32;
-            const int piece = (cc % BOXC) / 32;                 // 0 or 1
-            const uint32_t buf = stg + (uint32_t)(nstore & 1) * STG_BYTES;
-            if (piece == 0) {
-              if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-              __syncwarp();
-            }
+          // stage this 32-column piece (one warp-private buffer; the previous store must have been read)
+          const bool first_piece = OUT_BF16 ? (cc % BOXC) == 0 : true;
+          if (first_piece) {
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncwarp();
+          }
+          if constexpr (OUT_BF16) {
+            const int piece = (cc % BOXC) / 32;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const uint32_t c16 = (uint32_t)(piece * 4 + j);
               uint32_t off;
-              if (BOXC == 64) off = (uint32_t)lane * 128u + ((c16 ^ sw) << 4);                     // SWIZZLE_128B
-              else off = (uint32_t)lane * 64u + ((c16 ^ ((uint32_t)(lane >> 1) & 3u)) << 4);      // SWIZZLE_64B
+              if (BOXC == 64) off = (uint32_t)lane * 128u + ((c16 ^ (uint32_t)(lane & 7)) << 4);       // SWIZZLE_128B
+              else off = (uint32_t)lane * 64u + ((c16 ^ ((uint32_t)(lane >> 1) & 3u)) << 4);          // SWIZZLE_64B
               st_shared_v4(buf + off, pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
                            pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
             }
@@ -455,20 +456,16 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __
               asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
               __syncwarp();
               if (lane == 0) tma_store_2d(&tmC, buf, n - (cc % BOXC), m0 + q * 32);
-              ++nstore;
             }
           } else {
-            const uint32_t buf = stg + (uint32_t)(nstore & 1) * STG_BYTES;
-            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-            __syncwarp();
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-              st_shared_v4(buf + (uint32_t)lane * 128u + (((uint32_t)j ^ sw) << 4), __float_as_uint(f[4 * j]),
-                           __float_as_uint(f[4 * j + 1]), __float_as_uint(f[4 * j + 2]), __float_as_uint(f[4 * j + 3]));
+              st_shared_v4(buf + (uint32_t)lane * 128u + (((uint32_t)j ^ (uint32_t)(lane & 7)) << 4),
+                           __float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]), __float_as_uint(f[4 * j + 2]),
+                           __float_as_uint(f[4 * j + 3]));
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) tma_store_2d(&tmC, buf, n, m0 + q * 32);
-            ++nstore;
           }
         }
         // all tcgen05.ld of this accumulator have completed (tmem_ld32 waits): hand it back
@@ -543,32 +540,44 @@ int num_sms() {
   return n;
 }
 
-template <int BN>
-int launch_persistent(const GemmArgs& g, cudaStream_t st) {
+template <int BN, int EPI, bool OUT_BF16>
+int launch_persistent_t(const GemmArgs& g, cudaStream_t st) {
   CUtensorMap tmA, tmW, tmC;
   WMK_TRY(make_map(&tmA, g.A, g.M, g.K, BM));
   WMK_TRY(make_map(&tmW, g.W, g.N, g.K, BN));
-  const int box_cols = g.out_bf16 ? (BN >= 64 ? 64 : 32) : 32;
-  WMK_TRY(make_map_ex(&tmC, g.C, g.M, g.ldc, 32, box_cols, !g.out_bf16));
+  WMK_TRY(make_map_ex(&tmC, g.C, g.M, g.ldc, 32, epi_box_cols(BN, OUT_BF16), !OUT_BF16));
   const int kblocks = cdiv(g.K, BK);
   constexpr int stage = (BM + BN) * BK * 2;
-  constexpr int fixed = kEpiWarps * 2 * 4096 + 1024 + 256;
+  constexpr int fixed = kEpiWarps * 4096 + 1024 + 256;
   int n_stages = kblocks < 6 ? (kblocks < 2 ? 2 : kblocks) : 6;
   while (n_stages > 2 && n_stages * stage + fixed > 220 * 1024) --n_stages;
   const size_t smem = (size_t)n_stages * stage + fixed;
   static bool attr_set = false;
   if (!attr_set) {
-    WMK_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_persistent_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        224 * 1024));
+    WMK_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_persistent_kernel<BN, EPI, OUT_BF16>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
     attr_set = true;
   }
   EpiParams p{g.bias, g.resid, g.C, g.M, g.N, g.ldc, g.epi, g.out_bf16, g.up_h, g.up_w, g.up_cout};
   const int n_tiles = g.N / BN, m_tiles = cdiv(g.M, BM);
   const long long total = (long long)m_tiles * n_tiles;
   const int grid = (int)(total < num_sms() ? total : num_sms());
-  gemm_tcgen05_persistent_kernel<BN><<<grid, kPThreads, smem, st>>>(tmA, tmW, tmC, p, g.K, m_tiles, n_tiles, n_stages);
+  gemm_tcgen05_persistent_kernel<BN, EPI, OUT_BF16><<<grid, kPThreads, smem, st>>>(tmA, tmW, tmC, p, g.K, m_tiles,
+                                                                                   n_tiles, n_stages);
   WMK_CHECK_LAUNCH("gemm_tcgen05_persistent_kernel");
   return 0;
+}
+
+template <int BN>
+int launch_persistent(const GemmArgs& g, cudaStream_t st) {
+  if (g.epi == EPI_BIAS_GELU) {
+    if (g.out_bf16) return launch_persistent_t<BN, EPI_BIAS_GELU, true>(g, st);
+    set_error("gemm_bf16: the GELU epilogue writes bf16 only");
+    return WMK_ERR_UNSUPPORTED;
+  }
+  if (g.epi == EPI_BIAS_RESID) return launch_persistent_t<BN, EPI_BIAS_RESID, false>(g, st);
+  if (g.out_bf16) return launch_persistent_t<BN, EPI_BIAS, true>(g, st);
+  return launch_persistent_t<BN, EPI_BIAS, false>(g, st);
 }
 
 template <int BN>

@@ -569,6 +569,11 @@ extern "C" int wmk_plan_get_tap(wmk_plan* P, const char* name, float* out, size_
   return 0;
 }
 
+static __global__ void widen_kernel(const __nv_bfloat16* in, float* out, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __bfloat162float(in[i]);
+}
+
 extern "C" int wmk_linear_f32(const float* A, const float* W, const float* bias, float* C, int M, int N, int K,
                               int precision, int gelu, void* stream) {
   WMK_REQUIRE(A && W && C && M > 0 && N > 0 && K > 0, "linear: bad arguments");
@@ -588,7 +593,17 @@ extern "C" int wmk_linear_f32(const float* A, const float* W, const float* bias,
   copy_cols_kernel<__nv_bfloat16><<<cdiv((size_t)N * (K / 4), 256), 256, 0, st>>>(W, w16, (size_t)N, K, K, 0);
   WMK_CHECK_LAUNCH("copy_cols_kernel");
   g.A = a16; g.W = w16;
+  __nv_bfloat16* c16 = nullptr;
+  if (gelu) {        // the GELU epilogue stores bf16 (as inside the model): widen afterwards
+    WMK_CHECK_CUDA(cudaMallocAsync(&c16, (size_t)M * N * 2, st));
+    g.C = c16; g.out_bf16 = 1;
+  }
   int s = gemm_bf16_tcgen05(g, st);
+  if (gelu && s == 0) {
+    widen_kernel<<<cdiv((size_t)M * N, 256), 256, 0, st>>>(c16, C, (size_t)M * N);
+    count_launch();
+  }
+  if (c16) cudaFreeAsync(c16, st);
   cudaFreeAsync(a16, st);
   cudaFreeAsync(w16, st);
   return s;

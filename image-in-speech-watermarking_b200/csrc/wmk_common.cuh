@@ -112,14 +112,15 @@ __device__ __forceinline__ float gelu_fast(float x) {
   return 0.5f * x * (1.0f + copysignf(erf_abs, x));
 }
 
-// GELU for pairs on the packed fp32x2 pipe (sm_100 FFMA2), MUFU-free: erf(z) on [0,3] by an odd
-// degree-15 minimax polynomial (|error| < 8.1e-5, fitted against scipy.special.erf; 1 beyond 3).
-// |gelu error| < 2e-4 absolute, i.e. below the bf16 rounding of the value it produces; used only
-// where the result is stored as bf16.
+// GELU for pairs on the packed fp32x2 pipe (sm_100 FFMA2), MUFU-free: erf(z) on [-3,3] by an odd
+// degree-15 minimax polynomial (|error| < 8.1e-5, fitted against scipy.special.erf), argument
+// clamped to +-3 beyond.  |gelu error| < 2e-4 for |x| <= 4 (4e-5 * |x| beyond), i.e. below the
+// bf16 rounding of the value it produces; used only where the result is stored as bf16.
 __device__ __forceinline__ float2 gelu_poly2(float2 x) {
-  const float zx = fabsf(x.x) * 0.70710678118654752440f, zy = fabsf(x.y) * 0.70710678118654752440f;
-  const float2 zc = make_float2(fminf(zx, 3.0f), fminf(zy, 3.0f));
-  const float2 z2 = __fmul2_rn(zc, zc);
+  float2 z = __fmul2_rn(x, make_float2(0.70710678118654752440f, 0.70710678118654752440f));
+  z.x = fminf(fmaxf(z.x, -3.0f), 3.0f);
+  z.y = fminf(fmaxf(z.y, -3.0f), 3.0f);
+  const float2 z2 = __fmul2_rn(z, z);
   float2 p = make_float2(-4.055369516e-07f, -4.055369516e-07f);
   p = __ffma2_rn(p, z2, make_float2(1.715986036e-05f, 1.715986036e-05f));
   p = __ffma2_rn(p, z2, make_float2(-3.145957307e-04f, -3.145957307e-04f));
@@ -128,9 +129,7 @@ __device__ __forceinline__ float2 gelu_poly2(float2 x) {
   p = __ffma2_rn(p, z2, make_float2(1.077178344e-01f, 1.077178344e-01f));
   p = __ffma2_rn(p, z2, make_float2(-3.732314110e-01f, -3.732314110e-01f));
   p = __ffma2_rn(p, z2, make_float2(1.127895713e+00f, 1.127895713e+00f));
-  float2 e = __fmul2_rn(p, zc);
-  e.x = copysignf(zx < 3.0f ? e.x : 1.0f, x.x);
-  e.y = copysignf(zy < 3.0f ? e.y : 1.0f, x.y);
+  const float2 e = __fmul2_rn(p, z);                 // ~erf(x / sqrt 2), odd in x
   const float2 h = __fmul2_rn(x, make_float2(0.5f, 0.5f));
   return __ffma2_rn(h, e, h);
 }

@@ -69,7 +69,9 @@ def test_linear_matches_matmul(prec, shape):
         if gelu:
             ref = torch.nn.functional.gelu(ref)
         assert not torch.isnan(C).any()
-        assert maxrel(C.cpu(), ref.cpu()) < 2e-5, shape
+        # the tensor-core GELU epilogue stores bf16 (as inside the model): bf16 rounding dominates
+        tol = 6e-3 if (prec == 1 and gelu) else 2e-5
+        assert maxrel(C.cpu(), ref.cpu()) < tol, shape
 
 
 # --------------------------------------------------------------------------------- front end
