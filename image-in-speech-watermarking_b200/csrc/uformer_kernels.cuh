@@ -46,61 +46,74 @@ __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* p, float a,
   *reinterpret_cast<uint2*>(p) = u;
 }
 
-// One token is handled by G = min(32, C/4) lanes, each owning float4 chunks (C/4/G of them), so a
-// warp covers 32/G tokens and every global access is a 16-byte (fp32) / 8-byte (bf16) vector.
+// One token is handled by G = min(32, C/4) lanes, each owning float4 chunks (C/4/G of them); every
+// lane group processes TPT tokens with all of their loads issued up front (memory-level
+// parallelism), so a warp covers 32/G*TPT tokens and every global access is a 16-byte (fp32) /
+// 8-byte (bf16) vector.
 template <typename OpT, int C>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, OpT* __restrict__ out, const float* __restrict__ gamma,
                  const float* __restrict__ beta, const float* __restrict__ modulator, int M, int H, int shift) {
   constexpr int G = (C / 4 < 32) ? C / 4 : 32;      // lanes per token
-  constexpr int NV = C / 4 / G;                     // float4 chunks per lane
-  constexpr int TPW = 32 / G;                       // tokens per warp
+  constexpr int NV = C / 4 / G;                     // float4 chunks per lane per token
+  constexpr int TPT = NV >= 4 ? 1 : (NV == 2 ? 2 : 4);   // tokens per lane group
+  constexpr int GPW = 32 / G;                       // lane groups per warp
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int sub = lane / G, gl = lane % G;
-  const int token = warp * TPW + sub;
-  const bool ok = token < M;
-  const float* xr = x + (size_t)(ok ? token : 0) * C;
-  float4 v[NV];
-  float s = 0.f;
+  const int token0 = (warp * GPW + sub) * TPT;
+  float4 v[TPT][NV];
+#pragma unroll
+  for (int t = 0; t < TPT; ++t) {
+    const int token = token0 + t < M ? token0 + t : M - 1;
+    const float* xr = x + (size_t)token * C;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[t][i] = *reinterpret_cast<const float4*>(xr + (i * G + gl) * 4);
+  }
+  float4 g4[NV], b4[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    v[i] = *reinterpret_cast<const float4*>(xr + (i * G + gl) * 4);
-    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    g4[i] = __ldg(reinterpret_cast<const float4*>(gamma + (i * G + gl) * 4));
+    b4[i] = __ldg(reinterpret_cast<const float4*>(beta + (i * G + gl) * 4));
   }
 #pragma unroll
-  for (int o = G / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  const float mean = s * (1.0f / C);
-  float q = 0.f;
+  for (int t = 0; t < TPT; ++t) {
+    float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
-    q += (a * a + b * b) + (c * c + d * d);
-  }
+    for (int i = 0; i < NV; ++i) s += (v[t][i].x + v[t][i].y) + (v[t][i].z + v[t][i].w);
 #pragma unroll
-  for (int o = G / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-  const float rstd = rsqrtf(q * (1.0f / C) + 1e-5f);
-  if (!ok) return;
-  const float* mod = nullptr;
-  if (modulator) {
-    const int hw = token % (H * H);
-    const int h = hw / H, w = hw - h * H;
-    const int hs = (h - shift + H) % H, ws = (w - shift + H) % H;
-    mod = modulator + (size_t)(((hs & 7) << 3) | (ws & 7)) * C;
-  }
-  OpT* o = out + (size_t)token * C;
+    for (int o = G / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * (1.0f / C);
+    float q = 0.f;
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int c = (i * G + gl) * 4;
-    const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + c));
-    const float4 b4 = __ldg(reinterpret_cast<const float4*>(beta + c));
-    float y0 = (v[i].x - mean) * rstd * g4.x + b4.x, y1 = (v[i].y - mean) * rstd * g4.y + b4.y;
-    float y2 = (v[i].z - mean) * rstd * g4.z + b4.z, y3 = (v[i].w - mean) * rstd * g4.w + b4.w;
-    if (mod) {
-      const float4 m4 = __ldg(reinterpret_cast<const float4*>(mod + c));
-      y0 += m4.x; y1 += m4.y; y2 += m4.z; y3 += m4.w;
+    for (int i = 0; i < NV; ++i) {
+      const float a = v[t][i].x - mean, b = v[t][i].y - mean, c = v[t][i].z - mean, d = v[t][i].w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
     }
-    store4<OpT>(o + c, y0, y1, y2, y3);
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q * (1.0f / C) + 1e-5f);
+    const int token = token0 + t;
+    if (token >= M) continue;
+    const float* mod = nullptr;
+    if (modulator) {
+      const int hw = token % (H * H);
+      const int h = hw / H, w = hw - h * H;
+      const int hs = (h - shift + H) % H, ws = (w - shift + H) % H;
+      mod = modulator + (size_t)(((hs & 7) << 3) | (ws & 7)) * C;
+    }
+    OpT* o = out + (size_t)token * C;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * G + gl) * 4;
+      float y0 = (v[t][i].x - mean) * rstd * g4[i].x + b4[i].x, y1 = (v[t][i].y - mean) * rstd * g4[i].y + b4[i].y;
+      float y2 = (v[t][i].z - mean) * rstd * g4[i].z + b4[i].z, y3 = (v[t][i].w - mean) * rstd * g4[i].w + b4[i].w;
+      if (mod) {
+        const float4 m4 = __ldg(reinterpret_cast<const float4*>(mod + c));
+        y0 += m4.x; y1 += m4.y; y2 += m4.z; y3 += m4.w;
+      }
+      store4<OpT>(o + c, y0, y1, y2, y3);
+    }
   }
 }
 
@@ -108,7 +121,9 @@ template <typename OpT>
 inline void launch_layernorm(const float* x, OpT* out, const float* gamma, const float* beta, const float* modulator,
                              int M, int C, int H, int shift, cudaStream_t st) {
   const int G = (C / 4 < 32) ? C / 4 : 32;
-  const int tpw = 32 / G;
+  const int NV = C / 4 / G;
+  const int tpt = NV >= 4 ? 1 : (NV == 2 ? 2 : 4);
+  const int tpw = (32 / G) * tpt;
   const int warps = (M + tpw - 1) / tpw;
   const int blocks = (warps + 7) / 8;
   switch (C) {
@@ -265,15 +280,18 @@ window_attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16
       s_tok[buf][tid] = t;
       s_rid[buf][tid] = r;
     }
+    // thread -> rows (tid>>2) and 32+(tid>>2), 16-byte chunk tid&3, for each of q, k, v
+    int ta, tb, rr;
+    att_row(g, win, tid >> 2, ta, rr);
+    att_row(g, win, 32 + (tid >> 2), tb, rr);
+    const __nv_bfloat16* pa = qkv + (size_t)ta * (3 * C) + head * 32 + (tid & 3) * 8;
+    const __nv_bfloat16* pb = qkv + (size_t)tb * (3 * C) + head * 32 + (tid & 3) * 8;
+    const uint32_t da = (uint32_t)__cvta_generic_to_shared(&sbuf[buf][(tid >> 2) * ATT_LD + (tid & 3) * 8]);
+    const uint32_t db = da + 2u * 32 * ATT_LD;
 #pragma unroll
-    for (int i = 0; i < 6; ++i) {
-      const int e = tid + i * 128;
-      const int which = e >> 8, r = (e >> 2) & 63, ch = e & 3;
-      int t, rr;
-      att_row(g, win, r, t, rr);
-      const __nv_bfloat16* src = qkv + (size_t)t * (3 * C) + which * C + head * 32 + ch * 8;
-      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&sbuf[buf][which * ATT_TILE + r * ATT_LD + ch * 8]);
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+    for (int which = 0; which < 3; ++which) {
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(da + 2u * which * ATT_TILE), "l"(pa + which * C) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(db + 2u * which * ATT_TILE), "l"(pb + which * C) : "memory");
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
@@ -532,24 +550,46 @@ dwconv3x3_gelu_bf16_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* 
 template <typename OpT>
 __global__ void __launch_bounds__(256)
 im2col_4x4s2_kernel(const float* __restrict__ x, OpT* __restrict__ A, int B, int H, int C) {
-  const int cg = C >> 2;
+  // one thread = (output token, kh, 8 input channels): the 4 kw taps -> 8 independent 16-byte loads
+  const int cg = C >> 3;
   const int Ho = H >> 1;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t total = (size_t)B * Ho * Ho * 16 * cg;
+  const size_t total = (size_t)B * Ho * Ho * 4 * cg;
   if (idx >= total) return;
-  const int c = (int)(idx % cg) * 4;
+  const int c = (int)(idx % cg) * 8;
   size_t r = idx / cg;
-  const int tap = (int)(r % 16);
-  r /= 16;
+  const int kh = (int)(r & 3);
+  r >>= 2;
   const int ow = (int)(r % Ho);
   const int oh = (int)((r / Ho) % Ho);
   const size_t b = r / ((size_t)Ho * Ho);
-  const int ih = 2 * oh - 1 + (tap >> 2), iw = 2 * ow - 1 + (tap & 3);
-  float4 v = make_float4(0, 0, 0, 0);
-  if (ih >= 0 && ih < H && iw >= 0 && iw < H)
-    v = *reinterpret_cast<const float4*>(x + ((b * H + ih) * H + iw) * C + c);
-  OpT* dst = A + ((b * Ho + oh) * Ho + ow) * (size_t)(16 * C) + tap * C + c;
-  dst[0] = from_f<OpT>(v.x); dst[1] = from_f<OpT>(v.y); dst[2] = from_f<OpT>(v.z); dst[3] = from_f<OpT>(v.w);
+  const int ih = 2 * oh - 1 + kh;
+  const bool hv = ih >= 0 && ih < H;
+  float4 v[4][2];
+#pragma unroll
+  for (int kw = 0; kw < 4; ++kw) {
+    const int iw = 2 * ow - 1 + kw;
+    if (hv && iw >= 0 && iw < H) {
+      const float* src = x + ((b * H + ih) * H + iw) * C + c;
+      v[kw][0] = *reinterpret_cast<const float4*>(src);
+      v[kw][1] = *reinterpret_cast<const float4*>(src + 4);
+    } else {
+      v[kw][0] = v[kw][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  OpT* dst = A + ((b * Ho + oh) * Ho + ow) * (size_t)(16 * C) + (kh * 4) * C + c;
+#pragma unroll
+  for (int kw = 0; kw < 4; ++kw) {
+    if constexpr (sizeof(OpT) == 2) {
+      uint4 u;
+      u.x = pack_bf16(v[kw][0].x, v[kw][0].y); u.y = pack_bf16(v[kw][0].z, v[kw][0].w);
+      u.z = pack_bf16(v[kw][1].x, v[kw][1].y); u.w = pack_bf16(v[kw][1].z, v[kw][1].w);
+      *reinterpret_cast<uint4*>(dst + kw * C) = u;
+    } else {
+      *reinterpret_cast<float4*>(dst + kw * C) = v[kw][0];
+      *reinterpret_cast<float4*>(dst + kw * C + 4) = v[kw][1];
+    }
+  }
 }
 
 // fp32 -> OpT copy of a [rows][cols] matrix into a [rows][ld_dst] buffer at column offset col0

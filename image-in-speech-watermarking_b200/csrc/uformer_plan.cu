@@ -312,8 +312,11 @@ int run_block(wmk_plan* P, const BlockW& w, float* x, int n, cudaStream_t st) {
 // Encoder / EncoderTransformerWM stages (model.py:1381-1394, 1569-1579): x NCHW -> E[0..4].
 template <typename OpT>
 int run_encoder(wmk_plan* P, const EncW& e, const float* x_nchw, int n, const char* tag, cudaStream_t st) {
-  input_proj_kernel<<<cdiv((size_t)n * 16384, 128), 128, 0, st>>>(x_nchw, P->E[0], e.in_w, e.in_b, n);
-  WMK_CHECK_LAUNCH("input_proj_kernel");
+  {
+    ProfScope prof(FAM_SMALL, (double)n * 16384 * (8 + 128), st);
+    input_proj_kernel<<<cdiv((size_t)n * 16384, 128), 128, 0, st>>>(x_nchw, P->E[0], e.in_w, e.in_b, n);
+    WMK_CHECK_LAUNCH("input_proj_kernel");
+  }
   const std::string t(tag);
   if (t == "enc") WMK_TRY(tap(P, "emb.inproj", P->E[0], (size_t)n * 16384 * 32, st));
   for (int s = 0; s < 5; ++s) {
@@ -323,7 +326,7 @@ int run_encoder(wmk_plan* P, const EncW& e, const float* x_nchw, int n, const ch
     if (s == 4) break;
     const int Ho = H / 2;
     OpT* col = reinterpret_cast<OpT*>(P->bufH1);
-    const size_t total = (size_t)n * Ho * Ho * 16 * (C / 4);
+    const size_t total = (size_t)n * Ho * Ho * 4 * (C / 8);
     ProfScope prof_l(FAM_LAYOUT, (double)n * H * H * C * 4 + (double)n * Ho * Ho * 16 * C * sizeof(OpT), st);
     im2col_4x4s2_kernel<OpT><<<cdiv(total, 256), 256, 0, st>>>(P->E[s], col, n, H, C);
     WMK_CHECK_LAUNCH("im2col_4x4s2_kernel");
@@ -371,6 +374,7 @@ int run_forward(wmk_plan* P, const float* x, const float* msg, int msg_stride, i
     const int Hout = 2 * Hin, Cd = 2 * Cout;
     if (s > 0) {
       const size_t rows = (size_t)n * Hin * Hin;
+      ProfScope prof_cp(FAM_LAYOUT, (double)rows * Cin * 6, st);
       copy_cols_kernel<OpT><<<cdiv(rows * (Cin / 4), 256), 256, 0, st>>>(P->D[s - 1], A, rows, Cin, Cin, 0);
       WMK_CHECK_LAUNCH("copy_cols_kernel");
     }
@@ -380,6 +384,7 @@ int run_forward(wmk_plan* P, const float* x, const float* msg, int msg_stride, i
     WMK_TRY(gemm(P, g, st));
     {
       const size_t rows = (size_t)n * Hout * Hout;
+      ProfScope prof_cp(FAM_LAYOUT, (double)rows * Cout * 8, st);
       copy_cols_kernel<float><<<cdiv(rows * (Cout / 4), 256), 256, 0, st>>>(P->E[3 - s], P->D[s], rows, Cout, Cd, Cout);
       WMK_CHECK_LAUNCH("copy_cols_kernel");
     }
@@ -388,18 +393,24 @@ int run_forward(wmk_plan* P, const float* x, const float* msg, int msg_stride, i
   }
   (void)ob;
   float* y = y_out ? y_out : P->ybuf;
-  output_proj_kernel<<<cdiv((size_t)n * 16384 * 32, 256), 256, 0, st>>>(P->D[3], x, noise, y, P->out_w, P->out_b, n);
-  WMK_CHECK_LAUNCH("output_proj_kernel");
+  {
+    ProfScope prof(FAM_SMALL, (double)n * 16384 * (256 + 24), st);
+    output_proj_kernel<<<cdiv((size_t)n * 16384 * 32, 256), 256, 0, st>>>(P->D[3], x, noise, y, P->out_w, P->out_b, n);
+    WMK_CHECK_LAUNCH("output_proj_kernel");
+  }
   if (stft_new) {
     // in-graph ISTFT -> STFT projection + stft_layer (model.py:2458-2465)
     WMK_TRY(istft_clips(y, n, 1, 128, P->wavebuf, 8002, st));
     WMK_TRY(tap(P, "emb.wave", P->wavebuf, (size_t)n * 8002, st));
     WMK_TRY(stft_clips(P->wavebuf, n, 8002, P->rt, 1, st));
     WMK_TRY(tap(P, "emb.roundtrip", P->rt, (size_t)n * 32768, st));
-    conv3x3_nchw_kernel<2, 4, true><<<cdiv((size_t)n * 16384, 256), 256, 0, st>>>(P->rt, P->rt2, P->sl0_w, P->sl0_b, n);
-    WMK_CHECK_LAUNCH("conv3x3_nchw_kernel<2,4>");
-    conv3x3_nchw_kernel<4, 2, false><<<cdiv((size_t)n * 16384, 256), 256, 0, st>>>(P->rt2, stft_new, P->sl2_w, P->sl2_b, n);
-    WMK_CHECK_LAUNCH("conv3x3_nchw_kernel<4,2>");
+    {
+      ProfScope prof_sl(FAM_SMALL, (double)n * 16384 * 48, st);
+      conv3x3_nchw_kernel<2, 4, true><<<cdiv((size_t)n * 16384, 256), 256, 0, st>>>(P->rt, P->rt2, P->sl0_w, P->sl0_b, n);
+      WMK_CHECK_LAUNCH("conv3x3_nchw_kernel<2,4>");
+      conv3x3_nchw_kernel<4, 2, false><<<cdiv((size_t)n * 16384, 256), 256, 0, st>>>(P->rt2, stft_new, P->sl2_w, P->sl2_b, n);
+      WMK_CHECK_LAUNCH("conv3x3_nchw_kernel<4,2>");
+    }
   }
   if (wm || wm_logits) WMK_TRY(run_extract<OpT>(P, y, n, wm, wm_logits, st));   // model.py:2508-2509 reads y
   return 0;
