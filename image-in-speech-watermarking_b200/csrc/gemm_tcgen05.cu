@@ -297,21 +297,28 @@ template <int BN, int EPI, bool OUT_BF16>
 __global__ void __launch_bounds__(kPThreads, 1)
 gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                                const __grid_constant__ CUtensorMap tmC, EpiParams p, int K, int m_tiles,
-                               int n_tiles, int n_stages) {
+                               int n_tiles, int n_stages, int w_stationary) {
+  // w_stationary: the CTA keeps its whole BN x K weight tile resident in shared memory and walks
+  // down the M tiles of one N tile, so only A streams from L2 (for K <= 256 the weight tile would
+  // otherwise be re-fetched for every output tile and the L2 -> SM path becomes the bound).
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   constexpr uint32_t A_BYTES = BM * BK * 2;
   constexpr uint32_t W_BYTES = BN * BK * 2;
-  constexpr uint32_t STAGE = A_BYTES + W_BYTES;
+  const int kblocks = (K + BK - 1) / BK;
+  const uint32_t STAGE = w_stationary ? A_BYTES : A_BYTES + W_BYTES;
+  const uint32_t wres = base;                                // resident weights: kblocks x W_BYTES
+  const uint32_t stages = base + (w_stationary ? (uint32_t)kblocks * W_BYTES : 0u);
   constexpr uint32_t STG_BYTES = 4096;                      // one staging box: 32 rows x <=128 B
-  const uint32_t staging = base + (uint32_t)n_stages * STAGE;            // [16 warps][4096]
+  const uint32_t staging = stages + (uint32_t)n_stages * STAGE;          // [16 warps][4096]
   const uint32_t bars = staging + kEpiWarps * STG_BYTES;
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (n_stages + s); };
   const uint32_t tfull_bar = bars + 16u * n_stages;         // [2]
   const uint32_t tempty_bar = tfull_bar + 16u;              // [2]
-  const uint32_t tmem_slot = tempty_bar + 16u;
+  const uint32_t wfull_bar = tempty_bar + 16u;
+  const uint32_t tmem_slot = wfull_bar + 8u;
   volatile uint32_t* tmem_slot_ptr = (volatile uint32_t*)(smem_raw + (tmem_slot - raw));
 
   constexpr int CPW = epi_cpw(BN);
@@ -321,13 +328,27 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __
   constexpr int TCOLS = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kblocks = (K + BK - 1) / BK;
   const int total = m_tiles * n_tiles;
+  // i-th tile of this CTA -> (m0, n0); false when the CTA has no i-th tile
+  const int ws_groups = (int)gridDim.x / n_tiles;
+  auto tile_at = [&](int i, int& m0, int& n0) -> bool {
+    if (w_stationary) {
+      const int mt = (int)blockIdx.x / n_tiles + i * ws_groups;
+      m0 = mt * BM;
+      n0 = ((int)blockIdx.x % n_tiles) * BN;
+      return mt < m_tiles;
+    }
+    const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+    m0 = (tile / n_tiles) * BM;
+    n0 = (tile % n_tiles) * BN;
+    return tile < total;
+  };
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
+    mbar_init(wfull_bar, 1);
     for (int s = 0; s < n_stages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -349,25 +370,29 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __
 
   if (warp == 0) {
     if (lane == 0) {
-      int it = 0;
-      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-        const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+      int it = 0, m0, n0;
+      if (w_stationary && tile_at(0, m0, n0)) {
+        mbar_arrive_expect_tx(wfull_bar, (uint32_t)kblocks * W_BYTES);
+        for (int kb = 0; kb < kblocks; ++kb) tma_load_2d(wres + (uint32_t)kb * W_BYTES, &tmW, kb * BK, n0, wfull_bar);
+      }
+      for (int i = 0; tile_at(i, m0, n0); ++i) {
         for (int kb = 0; kb < kblocks; ++kb, ++it) {
           const int s = it % n_stages;
           const uint32_t ph = (uint32_t)(it / n_stages) & 1u;
           mbar_wait(empty_bar(s), ph ^ 1u);
           mbar_arrive_expect_tx(full_bar(s), STAGE);
-          const uint32_t sa = base + (uint32_t)s * STAGE;
+          const uint32_t sa = stages + (uint32_t)s * STAGE;
           tma_load_2d(sa, &tmA, kb * BK, m0, full_bar(s));
-          tma_load_2d(sa + A_BYTES, &tmW, kb * BK, n0, full_bar(s));
+          if (!w_stationary) tma_load_2d(sa + A_BYTES, &tmW, kb * BK, n0, full_bar(s));
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc(BN);
-      int it = 0, lt = 0;
-      for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++lt) {
+      int it = 0, m0, n0;
+      if (w_stationary && tile_at(0, m0, n0)) mbar_wait(wfull_bar, 0);
+      for (int lt = 0; tile_at(lt, m0, n0); ++lt) {
         const int acc = lt & 1;
         mbar_wait(tempty_bar + 8u * acc, ((uint32_t)(lt >> 1) & 1u) ^ 1u);      // epilogue drained this accumulator
         tcgen05_fence_after();
@@ -377,9 +402,9 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __
           const uint32_t ph = (uint32_t)(it / n_stages) & 1u;
           mbar_wait(full_bar(s), ph);
           tcgen05_fence_after();
-          const uint32_t sa = base + (uint32_t)s * STAGE;
+          const uint32_t sa = stages + (uint32_t)s * STAGE;
           const uint64_t adesc = umma_desc_sw128(sa);
-          const uint64_t bdesc = umma_desc_sw128(sa + A_BYTES);
+          const uint64_t bdesc = umma_desc_sw128(w_stationary ? wres + (uint32_t)kb * W_BYTES : sa + A_BYTES);
           const int krem = K - kb * BK;
           const int ksteps = krem >= BK ? BK / UMMA_K : (krem + UMMA_K - 1) / UMMA_K;   // skip zero-filled K
           for (int k = 0; k < ksteps; ++k)
@@ -395,11 +420,22 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __
     const int slab = ew >> 2;                     // which CPW-wide column slab
     if (slab < SLABS) {
       const uint32_t buf = staging + (uint32_t)ew * STG_BYTES;
-      int lt = 0;
-      for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++lt) {
-        const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+      int m0, n0;
+      for (int lt = 0; tile_at(lt, m0, n0); ++lt) {
         const int acc = lt & 1;
         const int row = m0 + q * 32 + lane;
+        // residual rows do not depend on the accumulator: fetch the first 32-column piece while the MMAs run
+        float4 rpre[8];
+        if constexpr (EPI == EPI_BIAS_RESID) {
+          if (row < p.M) {
+            const float4* r4 = reinterpret_cast<const float4*>(p.resid + (size_t)row * p.ldc + n0 + slab * CPW);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) rpre[j] = r4[j];
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) rpre[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
         mbar_wait(tfull_bar + 8u * acc, (uint32_t)(lt >> 1) & 1u);
         tcgen05_fence_after();
         const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + slab * CPW);
@@ -426,7 +462,12 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __
               f[2 * j] = gq.x; f[2 * j + 1] = gq.y;
             }
           } else if constexpr (EPI == EPI_BIAS_RESID) {
-            if (row < p.M) {
+            if (cc == 0) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                f[4 * j] += rpre[j].x; f[4 * j + 1] += rpre[j].y; f[4 * j + 2] += rpre[j].z; f[4 * j + 3] += rpre[j].w;
+              }
+            } else if (row < p.M) {
               const float4* r4 = reinterpret_cast<const float4*>(p.resid + (size_t)row * p.ldc + n);
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
@@ -547,23 +588,29 @@ int launch_persistent_t(const GemmArgs& g, cudaStream_t st) {
   WMK_TRY(make_map(&tmW, g.W, g.N, g.K, BN));
   WMK_TRY(make_map_ex(&tmC, g.C, g.M, g.ldc, 32, epi_box_cols(BN, OUT_BF16), !OUT_BF16));
   const int kblocks = cdiv(g.K, BK);
-  constexpr int stage = (BM + BN) * BK * 2;
   constexpr int fixed = kEpiWarps * 4096 + 1024 + 256;
-  int n_stages = kblocks < 6 ? (kblocks < 2 ? 2 : kblocks) : 6;
-  while (n_stages > 2 && n_stages * stage + fixed > 220 * 1024) --n_stages;
-  const size_t smem = (size_t)n_stages * stage + fixed;
+  constexpr int budget = 226 * 1024;
+  const int n_tiles = g.N / BN, m_tiles = cdiv(g.M, BM);
+  const int w_bytes = kblocks * BN * BK * 2;
+  // weight-stationary when the whole BN x K tile + >= 2 A stages fit and every N tile gets >= 1 CTA
+  const int ws = (kblocks <= 4 && w_bytes + 2 * BM * BK * 2 + fixed <= budget && n_tiles <= num_sms() &&
+                  m_tiles >= 2 * (num_sms() / n_tiles)) ? 1 : 0;
+  const int stage = ws ? BM * BK * 2 : (BM + BN) * BK * 2;
+  const int avail = budget - fixed - (ws ? w_bytes : 0);
+  int n_stages = ws ? 6 : (kblocks < 6 ? (kblocks < 2 ? 2 : kblocks) : 6);
+  while (n_stages > 2 && n_stages * stage > avail) --n_stages;
+  const size_t smem = (size_t)n_stages * stage + (ws ? w_bytes : 0) + fixed;
   static bool attr_set = false;
   if (!attr_set) {
     WMK_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_persistent_kernel<BN, EPI, OUT_BF16>,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   EpiParams p{g.bias, g.resid, g.C, g.M, g.N, g.ldc, g.epi, g.out_bf16, g.up_h, g.up_w, g.up_cout};
-  const int n_tiles = g.N / BN, m_tiles = cdiv(g.M, BM);
   const long long total = (long long)m_tiles * n_tiles;
-  const int grid = (int)(total < num_sms() ? total : num_sms());
+  const int grid = ws ? (num_sms() / n_tiles) * n_tiles : (int)(total < num_sms() ? total : num_sms());
   gemm_tcgen05_persistent_kernel<BN, EPI, OUT_BF16><<<grid, kPThreads, smem, st>>>(tmA, tmW, tmC, p, g.K, m_tiles,
-                                                                                   n_tiles, n_stages);
+                                                                                   n_tiles, n_stages, ws);
   WMK_CHECK_LAUNCH("gemm_tcgen05_persistent_kernel");
   return 0;
 }
@@ -618,7 +665,8 @@ int gemm_bf16_tcgen05(const GemmArgs& g, cudaStream_t st) {
                 "gemm_bf16: bad upsample geometry");
   ProfScope prof(FAM_GEMM, 2.0 * g.M * g.N * g.K, st);
   if (g.epi != EPI_UPSAMPLE && g.ldc == g.N) {
-    if (g.N % 256 == 0 && g.N >= 512) return launch_persistent<256>(g, st);
+    const bool wide_ok = g.epi != EPI_BIAS_RESID || g.K >= 1024;   // fp32 residual tiles: one 32-column piece per warp
+    if (g.N % 256 == 0 && g.N >= 256 && wide_ok) return launch_persistent<256>(g, st);
     if (g.N % 128 == 0) return launch_persistent<128>(g, st);
     if (g.N % 64 == 0) return launch_persistent<64>(g, st);
     return launch_persistent<32>(g, st);
