@@ -458,7 +458,7 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __
           if constexpr (EPI == EPI_BIAS_GELU) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              const float2 gq = gelu_poly2(make_float2(f[2 * j], f[2 * j + 1]));
+              const float2 gq = gelu_tanh2(make_float2(f[2 * j], f[2 * j + 1]));
               f[2 * j] = gq.x; f[2 * j + 1] = gq.y;
             }
           } else if constexpr (EPI == EPI_BIAS_RESID) {

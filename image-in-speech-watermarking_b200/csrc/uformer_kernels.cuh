@@ -534,8 +534,8 @@ dwconv3x3_gelu_bf16_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* 
         a0 = __ffma2_rn(bf16x2_to_float2(u.x), wreg[dy * 3 + dx][0], a0);
         a1 = __ffma2_rn(bf16x2_to_float2(u.y), wreg[dy * 3 + dx][1], a1);
       }
-    a0 = gelu_poly2(a0);
-    a1 = gelu_poly2(a1);
+    a0 = gelu_tanh2(a0);
+    a1 = gelu_tanh2(a1);
     uint2 o;
     o.x = pack_bf16(a0.x, a0.y);
     o.y = pack_bf16(a1.x, a1.y);

@@ -50,7 +50,10 @@ def models(weights):
 # --------------------------------------------------------------------------------- dense layer
 @pytest.mark.parametrize("prec", [0, 1])
 @pytest.mark.parametrize("shape", [(128, 32, 32), (256, 96, 32), (200, 64, 64), (64, 512, 2048), (3000, 256, 512),
-                                   (4096, 384, 128), (1, 32, 32), (129, 1536, 512)])
+                                   (4096, 384, 128), (1, 32, 32), (129, 1536, 512),
+                                   # large M: the weight-stationary schedule of the persistent kernel
+                                   (40000, 256, 64), (30001, 96, 32), (20000, 512, 256), (70000, 64, 256),
+                                   (50000, 1024, 256)])
 def test_linear_matches_matmul(prec, shape):
     from image_in_speech_watermarking_b200 import _lib
     lib = _lib.load()
