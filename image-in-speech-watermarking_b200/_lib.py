@@ -32,6 +32,13 @@ SIGNATURES = {
     "wmk_attack_resample2_f32": (_i, [_vp, _vp, _i, _i, _dp, _i, _vp]),
     "wmk_wave_stats_f64": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "wmk_wm_stats_f64": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
+    "wmk_conv3x3_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp]),
+    "wmk_convT2x2_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp]),
+    "wmk_maxpool2x2_f32": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "wmk_noise_mix_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "wmk_noise_crop_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "wmk_noise_resize_nearest_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _f, _vp]),
+    "wmk_noise_quantize_f32": (_i, [_vp, _vp, _sz, _vp]),
     "wmk_uformer_plan_create": (_i, [_i, ctypes.POINTER(_vp)]),
     "wmk_plan_destroy": (_i, [_vp]),
     "wmk_plan_set_tensor": (_i, [_vp, ctypes.c_char_p, _vp, ctypes.POINTER(ctypes.c_int64), _i]),

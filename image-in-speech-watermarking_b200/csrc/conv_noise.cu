@@ -1,0 +1,314 @@
+// CNN building blocks and spectrogram-domain noise layers:
+//   * 3x3 convolution / 2x2 transposed convolution / 2x2 max-pool on NCHW fp32 tensors with the
+//     BatchNorm (eval) affine and the activation fused - the layers of ModelA
+//     (uformerWM/model.py:3000-3066) and of the HiDDeN Decoder / ConvBNRelu
+//     (hidden/model/decoder.py:12-40, hidden/model/conv_bn_relu.py:7-18);
+//   * the HiDDeN noise layers (hidden/noise_layers/{crop,cropout,dropout,resize,quantization}.py).
+// Channel counts here are 1..64 and the tensors are small: these are memory-bound direct kernels
+// (input tile + halo staged in shared memory, weights in shared memory, 16 output channels per
+// thread in registers).
+#include "uformer_kernels.cuh"
+
+namespace wmk {
+namespace {
+
+enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY = 2, ACT_SIGMOID = 3 };
+
+__device__ __forceinline__ float apply_act(float v, int act, float slope) {
+  if (act == ACT_RELU) return fmaxf(v, 0.f);
+  if (act == ACT_LEAKY) return v > 0.f ? v : slope * v;
+  if (act == ACT_SIGMOID) return 1.0f / (1.0f + expf(-v));
+  return v;
+}
+
+constexpr int CT = 16;      // output tile edge
+constexpr int COB = 16;     // output channels per CTA
+constexpr int CIB = 8;      // input channels per shared-memory pass
+
+// y[b][co_off+co][h][w] = act( scale[co] * (sum_{ci,dy,dx} x[b][ci][h+dy-1][w+dx-1] w[co][ci][dy][dx] + bias[co]) + shift[co] )
+__global__ void __launch_bounds__(256)
+conv3x3_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ w,
+               const float* __restrict__ bias, const float* __restrict__ scale, const float* __restrict__ shift,
+               int Cin, int Cout, int H, int W, int co_off, int Ctot, int act, float slope) {
+  __shared__ float tile[CIB][CT + 2][CT + 2];
+  __shared__ float ws[CIB][9][COB];
+  const int tiles_w = (W + CT - 1) / CT;
+  const int th = blockIdx.x / tiles_w, tw = blockIdx.x % tiles_w;
+  const int co0 = blockIdx.y * COB;
+  const int b = blockIdx.z;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int h = th * CT + ty, wq = tw * CT + tx;
+  float acc[COB];
+#pragma unroll
+  for (int j = 0; j < COB; ++j) acc[j] = 0.f;
+  for (int c0 = 0; c0 < Cin; c0 += CIB) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < CIB * (CT + 2) * (CT + 2); e += 256) {
+      const int ci = e / ((CT + 2) * (CT + 2)), r = (e / (CT + 2)) % (CT + 2), c = e % (CT + 2);
+      const int hh = th * CT + r - 1, ww = tw * CT + c - 1;
+      float v = 0.f;
+      if (c0 + ci < Cin && hh >= 0 && hh < H && ww >= 0 && ww < W)
+        v = x[(((size_t)b * Cin + c0 + ci) * H + hh) * W + ww];
+      tile[ci][r][c] = v;
+    }
+    for (int e = threadIdx.x; e < CIB * 9 * COB; e += 256) {
+      const int ci = e / (9 * COB), t = (e / COB) % 9, j = e % COB;
+      float v = 0.f;
+      if (c0 + ci < Cin && co0 + j < Cout) v = w[((size_t)(co0 + j) * Cin + c0 + ci) * 9 + t];
+      ws[ci][t][j] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int ci = 0; ci < CIB; ++ci)
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const float v = tile[ci][ty + t / 3][tx + t % 3];
+#pragma unroll
+        for (int j = 0; j < COB; ++j) acc[j] = fmaf(v, ws[ci][t][j], acc[j]);
+      }
+  }
+  if (h >= H || wq >= W) return;
+#pragma unroll
+  for (int j = 0; j < COB; ++j) {
+    const int co = co0 + j;
+    if (co >= Cout) break;
+    float v = acc[j] + (bias ? bias[co] : 0.f);
+    if (scale) v = v * scale[co] + shift[co];
+    y[(((size_t)b * Ctot + co_off + co) * H + h) * W + wq] = apply_act(v, act, slope);
+  }
+}
+
+// ConvTranspose2d(k=2, s=2): y[b][co][2h+i][2w+j] = act(scale*(sum_ci x[b][ci][h][w] w[ci][co][i][j] + bias) + shift)
+__global__ void __launch_bounds__(256)
+convT2x2_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ w,
+                const float* __restrict__ bias, const float* __restrict__ scale, const float* __restrict__ shift,
+                int B, int Cin, int Cout, int H, int W, int act, float slope) {
+  extern __shared__ float wsm[];             // [Cin][Cout][4]
+  for (int e = threadIdx.x; e < Cin * Cout * 4; e += blockDim.x) wsm[e] = w[e];
+  __syncthreads();
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)B * H * W) return;
+  const int wq = (int)(idx % W), h = (int)((idx / W) % H);
+  const size_t b = idx / ((size_t)H * W);
+  for (int co = 0; co < Cout; ++co) {
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int ci = 0; ci < Cin; ++ci) {
+      const float v = x[((b * Cin + ci) * H + h) * W + wq];
+      const float* wp = wsm + ((size_t)ci * Cout + co) * 4;
+      a[0] = fmaf(v, wp[0], a[0]); a[1] = fmaf(v, wp[1], a[1]); a[2] = fmaf(v, wp[2], a[2]); a[3] = fmaf(v, wp[3], a[3]);
+    }
+#pragma unroll
+    for (int ij = 0; ij < 4; ++ij) {
+      float v = a[ij] + (bias ? bias[co] : 0.f);
+      if (scale) v = v * scale[co] + shift[co];
+      y[((b * Cout + co) * (2 * H) + 2 * h + (ij >> 1)) * (size_t)(2 * W) + 2 * wq + (ij & 1)] = apply_act(v, act, slope);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+maxpool2x2_kernel(const float* __restrict__ x, float* __restrict__ y, size_t planes, int H, int W) {
+  const int Ho = H >> 1, Wo = W >> 1;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= planes * Ho * Wo) return;
+  const int wq = (int)(idx % Wo), h = (int)((idx / Wo) % Ho);
+  const size_t p = idx / ((size_t)Ho * Wo);
+  const float* s = x + (p * H + 2 * h) * W + 2 * wq;
+  y[idx] = fmaxf(fmaxf(s[0], s[1]), fmaxf(s[W], s[W + 1]));
+}
+
+// ---------------------------------------------------------------------------- noise layers
+// Cropout (cropout.py:16-28) / Dropout (dropout.py:15-28): out = keep ? noised : cover.
+// mask == nullptr: keep inside the rectangle [h0,h1) x [w0,w1); else keep = mask[h][w] != 0.
+__global__ void __launch_bounds__(256)
+mix_kernel(const float* __restrict__ noised, const float* __restrict__ cover, float* __restrict__ out, size_t planes,
+           int H, int W, int h0, int h1, int w0, int w1, const float* __restrict__ mask) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= planes * H * W) return;
+  const int wq = (int)(idx % W), h = (int)((idx / W) % H);
+  const bool keep = mask ? mask[h * W + wq] != 0.f : (h >= h0 && h < h1 && wq >= w0 && wq < w1);
+  out[idx] = keep ? noised[idx] : cover[idx];
+}
+
+// Crop (crop.py:63-75): out = in[:, :, h0:h1, w0:w1];  Resize nearest (resize.py:17-26,
+// F.interpolate(mode='nearest', scale_factor=r)): src = floor(dst * (1/r)).
+__global__ void __launch_bounds__(256)
+resample_kernel(const float* __restrict__ in, float* __restrict__ out, size_t planes, int H, int W, int Ho, int Wo,
+                int h0, int w0, float inv_scale, int nearest) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= planes * Ho * Wo) return;
+  const int wq = (int)(idx % Wo), h = (int)((idx / Wo) % Ho);
+  const size_t p = idx / ((size_t)Ho * Wo);
+  int sh, sw;
+  if (nearest) {
+    sh = min((int)floorf(h * inv_scale), H - 1);
+    sw = min((int)floorf(wq * inv_scale), W - 1);
+  } else {
+    sh = h0 + h;
+    sw = w0 + wq;
+  }
+  out[idx] = in[(p * H + sh) * W + sw];
+}
+
+// Quantization (quantization.py:32-45): min-max to [0,255], x + sum_{n=1..10} (-1)^n/(pi n) sin(2 pi n x),
+// min-max of the result back to the input's range.  Three passes: range, transform + range, rescale.
+__device__ __forceinline__ float atomic_min_f(float* addr, float v) {
+  int* a = reinterpret_cast<int*>(addr);
+  int old = *a;
+  while (__int_as_float(old) > v) {
+    const int assumed = old;
+    old = atomicCAS(a, assumed, __float_as_int(v));
+    if (old == assumed) break;
+  }
+  return __int_as_float(old);
+}
+__device__ __forceinline__ float atomic_max_f(float* addr, float v) {
+  int* a = reinterpret_cast<int*>(addr);
+  int old = *a;
+  while (__int_as_float(old) < v) {
+    const int assumed = old;
+    old = atomicCAS(a, assumed, __float_as_int(v));
+    if (old == assumed) break;
+  }
+  return __int_as_float(old);
+}
+__global__ void __launch_bounds__(256) minmax_kernel(const float* __restrict__ x, size_t n, float* __restrict__ mm) {
+  float lo = INFINITY, hi = -INFINITY;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    lo = fminf(lo, v);
+    hi = fmaxf(hi, v);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomic_min_f(mm, lo);
+    atomic_max_f(mm + 1, hi);
+  }
+}
+__global__ void __launch_bounds__(256)
+quant_round_kernel(const float* __restrict__ x, float* __restrict__ t, size_t n, const float* __restrict__ mm) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float lo = mm[0], hi = mm[1];
+  float v = (x[i] - lo) / (hi - lo);
+  v = v * 255.0f;                                   // transform(tensor, (0, 255))
+  v = fminf(fmaxf(v, 0.f), 255.0f);
+  // the reference's weights / scales are float64 tensors, so the rounding term is evaluated in fp64
+  double z = 0.0;
+#pragma unroll
+  for (int k = 1; k <= 10; ++k) {
+    const double wk = ((k & 1) ? -1.0 : 1.0) / (3.14159265358979323846 * k);       // (-1)^(n+1)/(pi (n+1)), n = k-1
+    z += wk * sinpi(2.0 * k * (double)v);
+  }
+  t[i] = (float)((double)v + z);
+}
+__global__ void __launch_bounds__(256)
+rescale_kernel(const float* __restrict__ t, float* __restrict__ out, size_t n, const float* __restrict__ mm_t,
+               const float* __restrict__ mm_x) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = (t[i] - mm_t[0]) / (mm_t[1] - mm_t[0]);
+  out[i] = v * (mm_x[1] - mm_x[0]) + mm_x[0];
+}
+
+}  // namespace
+}  // namespace wmk
+
+using namespace wmk;
+
+extern "C" int wmk_conv3x3_f32(const float* x, float* y, const float* w, const float* bias, const float* scale,
+                               const float* shift, int B, int Cin, int Cout, int H, int W, int out_ch_offset,
+                               int out_ch_total, int act, float slope, void* stream) {
+  WMK_REQUIRE(x && y && w && B > 0 && Cin > 0 && Cout > 0 && H > 0 && W > 0 && out_ch_offset >= 0 &&
+                  out_ch_offset + Cout <= out_ch_total && act >= 0 && act <= 3 && (!scale == !shift) && B <= 65535,
+              "conv3x3: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  ProfScope prof(FAM_SMALL, 4.0 * B * H * W * (Cin + Cout), st);
+  dim3 grid(cdiv(H, CT) * cdiv(W, CT), cdiv(Cout, COB), B);
+  conv3x3_kernel<<<grid, 256, 0, st>>>(x, y, w, bias, scale, shift, Cin, Cout, H, W, out_ch_offset, out_ch_total, act, slope);
+  WMK_CHECK_LAUNCH("conv3x3_kernel");
+  return 0;
+}
+
+extern "C" int wmk_convT2x2_f32(const float* x, float* y, const float* w, const float* bias, const float* scale,
+                                const float* shift, int B, int Cin, int Cout, int H, int W, int act, float slope,
+                                void* stream) {
+  WMK_REQUIRE(x && y && w && B > 0 && Cin > 0 && Cout > 0 && H > 0 && W > 0 && act >= 0 && act <= 3 &&
+                  (!scale == !shift) && (size_t)Cin * Cout * 16 <= 96 * 1024,
+              "convT2x2: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  ProfScope prof(FAM_SMALL, 4.0 * B * H * W * (Cin + 4 * Cout), st);
+  const size_t smem = (size_t)Cin * Cout * 16;
+  if (smem > 48 * 1024) WMK_CHECK_CUDA(cudaFuncSetAttribute(convT2x2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  convT2x2_kernel<<<cdiv((size_t)B * H * W, 256), 256, smem, st>>>(x, y, w, bias, scale, shift, B, Cin, Cout, H, W, act, slope);
+  WMK_CHECK_LAUNCH("convT2x2_kernel");
+  return 0;
+}
+
+extern "C" int wmk_maxpool2x2_f32(const float* x, float* y, int planes, int H, int W, void* stream) {
+  WMK_REQUIRE(x && y && planes > 0 && H >= 2 && W >= 2, "maxpool2x2: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  ProfScope prof(FAM_SMALL, 5.0 * planes * H * W, st);
+  maxpool2x2_kernel<<<cdiv((size_t)planes * (H / 2) * (W / 2), 256), 256, 0, st>>>(x, y, (size_t)planes, H, W);
+  WMK_CHECK_LAUNCH("maxpool2x2_kernel");
+  return 0;
+}
+
+extern "C" int wmk_noise_mix_f32(const float* noised, const float* cover, float* out, int planes, int H, int W, int h0,
+                                 int h1, int w0, int w1, const float* mask_hw, void* stream) {
+  WMK_REQUIRE(noised && cover && out && planes > 0 && H > 0 && W > 0, "noise_mix: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  ProfScope prof(FAM_ATTACK, 12.0 * planes * H * W, st);
+  mix_kernel<<<cdiv((size_t)planes * H * W, 256), 256, 0, st>>>(noised, cover, out, (size_t)planes, H, W, h0, h1, w0, w1, mask_hw);
+  WMK_CHECK_LAUNCH("mix_kernel");
+  return 0;
+}
+
+extern "C" int wmk_noise_crop_f32(const float* in, float* out, int planes, int H, int W, int h0, int h1, int w0, int w1,
+                                  void* stream) {
+  WMK_REQUIRE(in && out && planes > 0 && 0 <= h0 && h0 < h1 && h1 <= H && 0 <= w0 && w0 < w1 && w1 <= W, "noise_crop: bad rectangle");
+  cudaStream_t st = (cudaStream_t)stream;
+  ProfScope prof(FAM_ATTACK, 8.0 * planes * (h1 - h0) * (w1 - w0), st);
+  resample_kernel<<<cdiv((size_t)planes * (h1 - h0) * (w1 - w0), 256), 256, 0, st>>>(in, out, (size_t)planes, H, W, h1 - h0,
+                                                                                      w1 - w0, h0, w0, 1.f, 0);
+  WMK_CHECK_LAUNCH("resample_kernel<crop>");
+  return 0;
+}
+
+extern "C" int wmk_noise_resize_nearest_f32(const float* in, float* out, int planes, int H, int W, int Ho, int Wo,
+                                            float scale, void* stream) {
+  WMK_REQUIRE(in && out && planes > 0 && H > 0 && W > 0 && Ho > 0 && Wo > 0 && scale > 0.f, "noise_resize: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  ProfScope prof(FAM_ATTACK, 8.0 * planes * Ho * Wo, st);
+  resample_kernel<<<cdiv((size_t)planes * Ho * Wo, 256), 256, 0, st>>>(in, out, (size_t)planes, H, W, Ho, Wo, 0, 0, 1.0f / scale, 1);
+  WMK_CHECK_LAUNCH("resample_kernel<nearest>");
+  return 0;
+}
+
+extern "C" int wmk_noise_quantize_f32(const float* in, float* out, size_t n, void* stream) {
+  WMK_REQUIRE(in && out && n > 0, "noise_quantize: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  ProfScope prof(FAM_ATTACK, 24.0 * n, st);
+  float *mm = nullptr, *tmp = nullptr;
+  WMK_CHECK_CUDA(cudaMallocAsync(&mm, 4 * sizeof(float), st));
+  WMK_CHECK_CUDA(cudaMallocAsync(&tmp, n * sizeof(float), st));
+  const float init[4] = {INFINITY, -INFINITY, INFINITY, -INFINITY};
+  WMK_CHECK_CUDA(cudaMemcpyAsync(mm, init, sizeof(init), cudaMemcpyHostToDevice, st));
+  WMK_CHECK_CUDA(cudaStreamSynchronize(st));          // `init` lives on this stack frame
+  const int rb = (int)(cdiv(n, 256) < 1184 ? cdiv(n, 256) : 1184);
+  minmax_kernel<<<rb, 256, 0, st>>>(in, n, mm);
+  WMK_CHECK_LAUNCH("minmax_kernel");
+  quant_round_kernel<<<cdiv(n, 256), 256, 0, st>>>(in, tmp, n, mm);
+  WMK_CHECK_LAUNCH("quant_round_kernel");
+  minmax_kernel<<<rb, 256, 0, st>>>(tmp, n, mm + 2);
+  WMK_CHECK_LAUNCH("minmax_kernel");
+  rescale_kernel<<<cdiv(n, 256), 256, 0, st>>>(tmp, out, n, mm + 2, mm);
+  WMK_CHECK_LAUNCH("rescale_kernel");
+  WMK_CHECK_CUDA(cudaFreeAsync(mm, st));
+  WMK_CHECK_CUDA(cudaFreeAsync(tmp, st));
+  return 0;
+}

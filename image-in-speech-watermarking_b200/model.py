@@ -228,3 +228,38 @@ class UformerAudio(nn.Module):
         out = torch.empty(n.value, device=next(self.parameters()).device, dtype=torch.float32)
         _lib.check(lib.wmk_plan_get_tap(self.plan(), name.encode(), _lib.ptr(out), n.value, ctypes.byref(n)))
         return out
+
+
+class ModelA(nn.Module):
+    """Drop-in for the reference CNN baseline `ModelA` (`uformerWM/model.py:3000-3066`): same layer
+    structure and state_dict keys; `forward` / `encode` / `decode` run on libwmk's conv kernels
+    (eval mode: BatchNorm uses running statistics, Dropout is the identity)."""
+
+    def __init__(self, in_chans=1):
+        super().__init__()
+        self.embedder_encoder = nn.Sequential(
+            nn.Conv2d(2, 16, 3, padding=1, stride=1), nn.BatchNorm2d(16), nn.LeakyReLU(0.2), nn.MaxPool2d(2, 2),
+            nn.Conv2d(16, 32, 3, padding=1, stride=1), nn.BatchNorm2d(32), nn.LeakyReLU(0.2), nn.MaxPool2d(2, 2))
+        self.embedder_decoder = nn.Sequential(
+            nn.ConvTranspose2d(33, 16, 2, 2), nn.BatchNorm2d(16), nn.ReLU(), nn.Dropout(0.5),
+            nn.ConvTranspose2d(16, 2, 2, 2), nn.BatchNorm2d(2), nn.Sigmoid())
+        self.detector = nn.Sequential(
+            nn.Conv2d(2, 16, 3, padding=1), nn.BatchNorm2d(16), nn.LeakyReLU(0.2), nn.MaxPool2d(2, 2),
+            nn.Conv2d(16, 64, 3, padding=1), nn.BatchNorm2d(64), nn.LeakyReLU(0.2), nn.MaxPool2d(2, 2),
+            nn.Conv2d(64, 1, 3, padding=1), nn.ReLU())
+        for p in self.parameters():
+            p.requires_grad_(False)
+
+    def decode(self, x):
+        from . import cnn
+        return cnn.run_sequential(self.detector, x)
+
+    def encode(self, stft, watermark):
+        from . import cnn
+        x = cnn.run_sequential(self.embedder_encoder, stft)
+        x = torch.cat([x, watermark.to(x.device, torch.float32)], 1)        # model.py:3057
+        return cnn.run_sequential(self.embedder_decoder, x)
+
+    def forward(self, stft, watermark):
+        encoded_stft = self.encode(stft, watermark)
+        return encoded_stft, self.decode(encoded_stft)

@@ -126,6 +126,41 @@ int wmk_wm_stats_f64(const float* wm, const float* msg, int n, int msg_stride, d
                      void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * CNN layers of ModelA (uformerWM/model.py:3000-3066) and of the HiDDeN Decoder / ConvBNRelu
+ * (hidden/model/decoder.py:12-40, hidden/model/conv_bn_relu.py:7-18), NCHW float32.
+ * act: 0 none, 1 ReLU, 2 LeakyReLU(slope), 3 sigmoid.  scale/shift (both or neither) carry the
+ * eval-mode BatchNorm affine: y = act(scale * (conv + bias) + shift).
+ * ------------------------------------------------------------------------------------------ */
+/* Conv2d(Cin, Cout, 3, padding=1); writes channels [out_ch_offset, out_ch_offset+Cout) of a
+ * [B][out_ch_total][H][W] tensor (lets the caller build a channel concatenation in place). */
+int wmk_conv3x3_f32(const float* x, float* y, const float* w, const float* bias, const float* scale,
+                    const float* shift, int B, int Cin, int Cout, int H, int W, int out_ch_offset,
+                    int out_ch_total, int act, float slope, void* stream);
+/* ConvTranspose2d(Cin, Cout, 2, stride=2): [B][Cin][H][W] -> [B][Cout][2H][2W]; w is [Cin][Cout][2][2] */
+int wmk_convT2x2_f32(const float* x, float* y, const float* w, const float* bias, const float* scale,
+                     const float* shift, int B, int Cin, int Cout, int H, int W, int act, float slope,
+                     void* stream);
+/* MaxPool2d(2, 2) over `planes` = B*C images of H x W */
+int wmk_maxpool2x2_f32(const float* x, float* y, int planes, int H, int W, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * HiDDeN noise layers (hidden/noise_layers/), `planes` = B*C images of H x W, float32.
+ * ------------------------------------------------------------------------------------------ */
+/* Cropout (cropout.py:16-28) with mask_hw == NULL: out = noised inside [h0,h1)x[w0,w1), cover
+ * elsewhere.  Dropout (dropout.py:15-28) with mask_hw [H][W]: out = mask ? noised : cover. */
+int wmk_noise_mix_f32(const float* noised, const float* cover, float* out, int planes, int H, int W,
+                      int h0, int h1, int w0, int w1, const float* mask_hw, void* stream);
+/* Crop (crop.py:63-75): out [planes][h1-h0][w1-w0] = in[:, h0:h1, w0:w1] */
+int wmk_noise_crop_f32(const float* in, float* out, int planes, int H, int W, int h0, int h1, int w0,
+                       int w1, void* stream);
+/* Resize (resize.py:17-26): F.interpolate(mode='nearest', scale_factor=scale) to Ho x Wo */
+int wmk_noise_resize_nearest_f32(const float* in, float* out, int planes, int H, int W, int Ho, int Wo,
+                                 float scale, void* stream);
+/* Quantization (quantization.py:32-45): min-max to [0,255], Fourier soft rounding (10 terms),
+ * min-max back to the input's range, over all n elements */
+int wmk_noise_quantize_f32(const float* in, float* out, size_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * UformerAudio embedder / extractor (uformerWM/model.py:2225-2511, configuration
  * uformerWM/utils/model_utils.py:83-85).
  * ------------------------------------------------------------------------------------------ */

@@ -101,10 +101,48 @@ def signal_fixture():
     print("signal.npz")
 
 
+def cnn_fixture():
+    """ModelA + HiDDeN Decoder of the unmodified reference, eval mode, randomised parameters and
+    BatchNorm running statistics; noise layers with numpy seeds."""
+    from oracle import cnn as C
+    ref = shims.import_reference_model()
+    ma = C.randomize_(ref.ModelA(), 11)
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(2, 2, 128, 128, generator=g)
+    wm = (torch.rand(2, 1, 32, 32, generator=g) > 0.5).float()
+    hid = shims.reference_hidden_modules()
+    cfg = hid["options"].HiDDenConfiguration(H=128, W=128, message_length=30, encoder_blocks=4, encoder_channels=64,
+                                             decoder_blocks=7, decoder_channels=64, use_discriminator=True,
+                                             use_vgg=False, discriminator_blocks=3, discriminator_channels=64,
+                                             decoder_loss=1, encoder_loss=0.7, adversarial_loss=1e-3)
+    dec = C.randomize_(hid["decoder"].Decoder(cfg), 12)
+    xd = torch.randn(2, 1, 128, 128, generator=g)
+    with torch.no_grad():
+        enc, ext = ma(x, wm)
+        dout = dec(xd)
+    out = dict(x=x.numpy(), wm=wm.numpy(), modelA_encoded=enc.numpy(), modelA_extracted=ext.numpy(),
+               modelA_decode_x=ma.decode(x).detach().numpy(), dec_x=xd.numpy(), dec_out=dout.numpy())
+    # noise layers: [noised, cover] on (2,2,64,64) tensors
+    noised = torch.randn(2, 2, 64, 64, generator=g)
+    cover = torch.randn(2, 2, 64, 64, generator=g)
+    out.update(noised=noised.numpy(), cover=cover.numpy())
+    layers = {"crop": hid["crop"].Crop((0.4, 0.55), (0.4, 0.55)), "cropout": hid["cropout"].Cropout((0.25, 0.35), (0.25, 0.35)),
+              "dropout": hid["dropout"].Dropout((0.25, 0.35)), "resize": hid["resize"].Resize((0.4, 0.6)),
+              "quant": hid["quantization"].Quantization(torch.device("cpu")), "identity": hid["identity"].Identity()}
+    for i, (name, layer) in enumerate(layers.items()):
+        np.random.seed(100 + i)
+        with torch.no_grad():
+            r = layer([noised.clone(), cover.clone()])
+        out["noise_" + name] = r[0].numpy().astype(np.float32)
+    np.savez_compressed(os.path.join(OUT, "cnn.npz"), **out)
+    print("cnn.npz", {k: v.shape for k, v in out.items() if k.startswith("noise_")})
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
     signal_fixture()
+    cnn_fixture()
     model_fixture("stress", 0)
     model_fixture("reference", 0)
     pipeline_fixture("stress", 0, "awgn-20")

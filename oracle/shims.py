@@ -192,3 +192,33 @@ def reference_reconstruct_audio():
         with legacy_torch_spectral():
             return fn(*a, **k)
     return run
+
+
+def reference_hidden_modules():
+    """The unmodified `hidden/model/decoder.py`, `hidden/options.py` and `hidden/noise_layers/*`.
+    `hidden/` uses top-level module names (`model`, `options`, `noise_layers`) that collide with
+    `uformerWM/model.py`, so they are imported with sys.modules temporarily swapped."""
+    import importlib
+    if not reference_available():
+        raise RuntimeError("reference tree not present at %s" % REFERENCE_ROOT)
+    hp = os.path.join(REFERENCE_ROOT, "hidden")
+    saved = {k: sys.modules.pop(k) for k in list(sys.modules) if k == "model" or k.startswith("model.")
+             or k in ("options", "noise_layers") or k.startswith("noise_layers.")}
+    up = os.path.join(REFERENCE_ROOT, "uformerWM")
+    removed = [q for q in sys.path if q == up]          # `model.py` there would shadow the `hidden/model/` package
+    sys.path[:] = [q for q in sys.path if q != up]
+    sys.path.insert(0, hp)
+    importlib.invalidate_caches()
+    try:
+        out = {"decoder": importlib.import_module("model.decoder"), "options": importlib.import_module("options")}
+        for n in ("identity", "crop", "cropout", "dropout", "resize", "quantization"):
+            out[n] = importlib.import_module("noise_layers." + n)
+    finally:
+        sys.path.remove(hp)
+        for q in removed:
+            sys.path.insert(0, q)
+        for k in list(sys.modules):
+            if k == "model" or k.startswith("model.") or k in ("options", "noise_layers") or k.startswith("noise_layers."):
+                sys.modules.pop(k)
+        sys.modules.update(saved)
+    return out

@@ -1,0 +1,110 @@
+"""ModelA, HiDDeN Decoder and the HiDDeN noise layers: CPU oracle against
+the reference golden (`tests/golden/cnn.npz`), and the CUDA drop-ins against both on the GPU."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cnn as C, noise as N
+
+HR = {"crop": ((0.4, 0.55), (0.4, 0.55)), "cropout": ((0.25, 0.35), (0.25, 0.35))}
+
+
+def _maxrel(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30))
+
+
+def test_cnn_oracles_match_reference_golden(golden):
+    g = golden("cnn.npz")
+    ma = C.randomize_(C.ModelAOracle(), 11)
+    dec = C.randomize_(C.HiddenDecoderOracle(), 12)
+    with torch.no_grad():
+        e, x = ma(torch.from_numpy(g["x"]), torch.from_numpy(g["wm"]))
+        d = dec(torch.from_numpy(g["dec_x"]))
+    assert _maxrel(e.numpy(), g["modelA_encoded"]) < 1e-5 and _maxrel(x.numpy(), g["modelA_extracted"]) < 1e-5
+    assert _maxrel(d.numpy(), g["dec_out"]) < 1e-5
+    assert d.shape == (2, 1, 32, 32) and sum(p.numel() for p in dec.parameters()) == 240747
+    assert sum(p.numel() for p in ma.parameters()) == 17655
+
+
+def test_noise_oracles_match_reference_golden(golden):
+    g = golden("cnn.npz")
+    nz, cv = torch.from_numpy(g["noised"]), torch.from_numpy(g["cover"])
+    fns = [("crop", lambda: N.crop(nz, *HR["crop"])), ("cropout", lambda: N.cropout(nz, cv, *HR["cropout"])),
+           ("dropout", lambda: N.dropout(nz, cv, (0.25, 0.35))), ("resize", lambda: N.resize(nz, (0.4, 0.6))),
+           ("quant", lambda: N.quantization(nz)), ("identity", lambda: nz)]
+    for i, (k, f) in enumerate(fns):
+        np.random.seed(100 + i)
+        r = f().numpy().astype(np.float32)
+        assert r.shape == g["noise_" + k].shape and _maxrel(r, g["noise_" + k]) < 1e-6, k
+
+
+def test_modelA_state_dict_is_reference_compatible():
+    from image_in_speech_watermarking_b200.model import ModelA
+    m = ModelA()
+    o = C.ModelAOracle()
+    assert list(m.state_dict().keys()) == list(o.state_dict().keys())
+    m.load_state_dict(o.state_dict(), strict=True)
+
+
+@pytest.mark.gpu
+def test_modelA_matches_reference_golden(golden):
+    from image_in_speech_watermarking_b200.model import ModelA
+    g = golden("cnn.npz")
+    m = ModelA()
+    m.load_state_dict(C.randomize_(C.ModelAOracle(), 11).state_dict())
+    m = m.cuda().eval()
+    x, wm = torch.from_numpy(g["x"]).cuda(), torch.from_numpy(g["wm"]).cuda()
+    enc, ext = m(x, wm)
+    assert enc.shape == (2, 2, 128, 128) and ext.shape == (2, 1, 32, 32)
+    assert _maxrel(enc.cpu().numpy(), g["modelA_encoded"]) < 1e-4          # fp32 path: 1e-3 bound
+    assert _maxrel(ext.cpu().numpy(), g["modelA_extracted"]) < 1e-4
+    assert _maxrel(m.decode(x).cpu().numpy(), g["modelA_decode_x"]) < 1e-4
+    m.train()
+    with pytest.raises(NotImplementedError):
+        m(x, wm)
+
+
+@pytest.mark.gpu
+def test_hidden_decoder_matches_reference_golden(golden):
+    from image_in_speech_watermarking_b200.hidden.model.decoder import Decoder
+    from image_in_speech_watermarking_b200.hidden.options import HiDDenConfiguration
+    g = golden("cnn.npz")
+    cfg = HiDDenConfiguration(H=128, W=128, message_length=30, encoder_blocks=4, encoder_channels=64, decoder_blocks=7,
+                              decoder_channels=64, use_discriminator=True, use_vgg=False, discriminator_blocks=3,
+                              discriminator_channels=64, decoder_loss=1, encoder_loss=0.7, adversarial_loss=1e-3)
+    d = Decoder(cfg)
+    d.load_state_dict(C.randomize_(C.HiddenDecoderOracle(), 12).state_dict())
+    d = d.cuda().eval()
+    out = d(torch.from_numpy(g["dec_x"]).cuda())
+    assert out.shape == (2, 1, 32, 32)
+    assert _maxrel(out.cpu().numpy(), g["dec_out"]) < 1e-4
+    # batch 128 x (1,128,128) (BASELINE config 3 shape): consistent with the batch-2 result
+    big = torch.from_numpy(g["dec_x"]).cuda().repeat(8, 1, 1, 1)
+    assert torch.equal(d(big)[:2], out)
+
+
+@pytest.mark.gpu
+def test_noise_layers_match_reference_golden(golden):
+    from image_in_speech_watermarking_b200.hidden import noise_layers as NL
+    g = golden("cnn.npz")
+    nz, cv = torch.from_numpy(g["noised"]).cuda(), torch.from_numpy(g["cover"]).cuda()
+    layers = [("crop", NL.Crop(*HR["crop"])), ("cropout", NL.Cropout(*HR["cropout"])), ("dropout", NL.Dropout((0.25, 0.35))),
+              ("resize", NL.Resize((0.4, 0.6))), ("quant", NL.Quantization()), ("identity", NL.Identity())]
+    for i, (k, layer) in enumerate(layers):
+        np.random.seed(100 + i)
+        r = layer([nz.clone(), cv.clone()])
+        assert isinstance(r, list) and len(r) == 2
+        got = r[0].cpu().numpy()
+        tol = 2e-5 if k == "quant" else 0.0
+        assert got.shape == g["noise_" + k].shape, k
+        assert _maxrel(got, g["noise_" + k]) <= tol, k
+    np.random.seed(5)
+    noiser = NL.Noiser([NL.Cropout(*HR["cropout"]), 'QuantizationPlaceholder'], torch.device("cuda"))
+    out = noiser([nz.clone(), cv.clone()])
+    assert out[0].shape[:2] == nz.shape[:2]
+    with pytest.raises(ValueError):
+        NL.Noiser(['bogus'], None)
+    with pytest.raises(NotImplementedError):
+        NL.Noiser(['JpegPlaceholder'], None)
