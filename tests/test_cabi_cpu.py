@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _declared():
     txt = open(os.path.join(ROOT, "include", "wmk.h")).read()
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
-    return sorted(set(re.findall(r"\b(wmk_[a-z0-9_]+)\s*\(", txt)))
+    return sorted(set(re.findall(r"\b(wmk_[A-Za-z0-9_]+)\s*\(", txt)))
 
 
 def test_library_exports_every_declared_symbol():
