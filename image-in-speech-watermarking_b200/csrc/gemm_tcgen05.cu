@@ -13,109 +13,17 @@
 // epilogue overlaps another's main loop.  Replaces every nn.Linear of the LeWin blocks
 // (uformerWM/model.py:455-456,518,686,690) and, through im2col / pixel-shuffle, the 4x4-s2 and
 // transposed 2x2-s2 convolutions (model.py:763,789).
-#include <cuda.h>
 #include <mutex>
 
-#include "wmk_common.cuh"
+#include "tc_ptx.cuh"
 
 namespace wmk {
 
 namespace {
 
-constexpr int BM = 128;       // rows per tile = TMEM lanes
-constexpr int BK = 64;        // bf16 elements per k-block = one 128-byte swizzle row
-constexpr int UMMA_K = 16;
+using namespace tc;
 constexpr int kThreads = 192;
 
-// ------------------------------------------------------------------------------------- PTX
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  uint32_t spins = 0;
-  do {
-    if (++spins > (1u << 26)) __trap();       // a lost arrival becomes a CUDA error, not a hang
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-  } while (!done);
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1,
-                                            uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%2, %3}], [%4];"
-      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
-      : "memory");
-}
-__device__ __forceinline__ void tcgen05_fence_after() {
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void tcgen05_fence_before() {
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ void tcgen05_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
-                                                 uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
-        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
-        "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
-        "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
-        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
-
-// UMMA shared-memory descriptor of a K-major, 128B-swizzled tile whose rows are 128 bytes
-// (64 bf16): 8-row swizzle atoms of 1024 B stacked along M/N (SBO = 1024 B); LBO unused.
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);   // start address  [0,14)
-  d |= (uint64_t)1 << 16;                     // leading byte offset (ignored for swizzled K-major)
-  d |= (uint64_t)(1024u >> 4) << 32;          // stride byte offset [32,46)
-  d |= (uint64_t)1 << 46;                     // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;                     // layout type: SWIZZLE_128B
-  return d;
-}
-
-// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=BN.
-__host__ __device__ constexpr uint32_t umma_idesc(int bn) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-}
-
-__host__ __device__ constexpr int tmem_cols(int bn) { return bn <= 32 ? 32 : bn <= 64 ? 64 : bn <= 128 ? 128 : 256; }
 
 template <int BN>
 __global__ void __launch_bounds__(kThreads)
@@ -274,18 +182,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // ---------------------------------------------------------------------------------------------
 constexpr int kEpiWarps = 16;
 constexpr int kPThreads = 64 + 32 * kEpiWarps;
-
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-               ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
-  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-}
-__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
 
 // columns of the accumulator each epilogue warp owns, and the TMA-store box width
 __host__ __device__ constexpr int epi_cpw(int bn) { return bn >= 128 ? bn / 4 : 32; }
@@ -527,12 +423,16 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __
 }
 
 // ------------------------------------------------------------------------------------- host
+}  // namespace
+
+namespace tc {
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-EncodeTiledFn get_encode_fn() {
+static EncodeTiledFn get_encode_fn() {
   static EncodeTiledFn fn = nullptr;
   static std::once_flag once;
   std::call_once(once, [] {
@@ -545,30 +445,29 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// 2-D row-major [rows][cols] tensor of bf16 (or fp32), box = box_cols x box_rows, zero OOB fill.
-int make_map_ex(CUtensorMap* map, const void* ptr, int rows, int cols, int box_rows, int box_cols, bool f32) {
+int make_tensor_map(CUtensorMap* map, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box, bool f32, int swizzle_bytes) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
     return WMK_ERR_CUDA;
   }
-  const int es_bytes = f32 ? 4 : 2;
-  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)cols * es_bytes};
-  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
-  cuuint32_t es[2] = {1, 1};
-  const CUtensorMapSwizzle swz = box_cols * es_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
-  CUresult r = fn(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
-                  const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+  cuuint64_t d[5], st[5];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) st[i] = strides_bytes[i];
+  const CUtensorMapSwizzle swz = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                 : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                 : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = fn(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank,
+                  const_cast<void*>(ptr), d, st, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled failed (%d) for [%d][%d] box %dx%d", (int)r, rows, cols, box_rows, box_cols);
+    set_error("cuTensorMapEncodeTiled failed (%d), rank %d, dims %llu x %llu, box %u x %u", (int)r, rank,
+              (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
     return WMK_ERR_CUDA;
   }
   return 0;
-}
-int make_map(CUtensorMap* map, const void* ptr, int rows, int K, int box_rows) {
-  return make_map_ex(map, ptr, rows, K, box_rows, BK, false);
 }
 
 int num_sms() {
@@ -579,6 +478,21 @@ int num_sms() {
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
   }
   return n;
+}
+
+}  // namespace tc
+
+namespace {
+
+// 2-D row-major [rows][cols] tensor of bf16 (or fp32), box = box_cols x box_rows
+int make_map_ex(CUtensorMap* map, const void* ptr, int rows, int cols, int box_rows, int box_cols, bool f32) {
+  const uint64_t dims[2] = {(uint64_t)cols, (uint64_t)rows};
+  const uint64_t strides[1] = {(uint64_t)cols * (f32 ? 4 : 2)};
+  const uint32_t box[2] = {(uint32_t)box_cols, (uint32_t)box_rows};
+  return make_tensor_map(map, ptr, 2, dims, strides, box, f32, box_cols * (f32 ? 4 : 2) == 128 ? 128 : 64);
+}
+int make_map(CUtensorMap* map, const void* ptr, int rows, int K, int box_rows) {
+  return make_map_ex(map, ptr, rows, K, box_rows, BK, false);
 }
 
 template <int BN, int EPI, bool OUT_BF16>
