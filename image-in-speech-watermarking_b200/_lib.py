@@ -19,7 +19,7 @@ SIGNATURES = {
     "wmk_profile_enable": (_i, [_i]),
     "wmk_profile_num_families": (_i, []),
     "wmk_profile_family_name": (ctypes.c_char_p, [_i]),
-    "wmk_profile_collect": (_i, [_dp, _dp, ctypes.POINTER(ctypes.c_uint64)]),
+    "wmk_profile_collect": (_i, [_dp, _dp, _dp, ctypes.POINTER(ctypes.c_uint64)]),
     "wmk_stft_num_frames": (_i, [_i]),
     "wmk_stft_clips_f32": (_i, [_vp, _i, _i, _vp, _i, _vp]),
     "wmk_istft_clips_f32": (_i, [_vp, _i, _i, _i, _vp, _i, _vp]),
@@ -108,7 +108,8 @@ def profile_collect():
     n = lib.wmk_profile_num_families()
     ms = (ctypes.c_double * n)()
     work = (ctypes.c_double * n)()
+    work2 = (ctypes.c_double * n)()
     cnt = (ctypes.c_uint64 * n)()
-    check(lib.wmk_profile_collect(ms, work, cnt))
-    return {lib.wmk_profile_family_name(i).decode(): {"ms": ms[i], "work": work[i], "launches": int(cnt[i])}
+    check(lib.wmk_profile_collect(ms, work, work2, cnt))
+    return {lib.wmk_profile_family_name(i).decode(): {"ms": ms[i], "work": work[i], "work2": work2[i], "launches": int(cnt[i])}
             for i in range(n)}

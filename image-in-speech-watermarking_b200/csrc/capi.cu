@@ -23,8 +23,8 @@ void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_r
 
 // ------------------------------------------------------------------------------------ profiling
 static const char* kFamilyNames[FAM_COUNT] = {"gemm", "window_attention", "layernorm", "dwconv_gelu", "layout",
-                                              "small", "stft", "istft", "attack", "stats"};
-struct ProfRec { cudaEvent_t a, b; int family; double work; };
+                                              "small", "stft", "istft", "attack", "stats", "gemm_hbm"};
+struct ProfRec { cudaEvent_t a, b; int family; double work, work2; };
 static bool g_prof_on = false;
 static std::mutex g_prof_mu;
 static std::vector<ProfRec> g_prof;
@@ -37,10 +37,10 @@ static cudaEvent_t prof_event() {
   return e;
 }
 
-ProfScope::ProfScope(int family, double work, cudaStream_t s) : slot(-1), st(s) {
+ProfScope::ProfScope(int family, double work, cudaStream_t s, double work2) : slot(-1), st(s) {
   if (!g_prof_on) return;
   std::lock_guard<std::mutex> lk(g_prof_mu);
-  ProfRec r{prof_event(), prof_event(), family, work};
+  ProfRec r{prof_event(), prof_event(), family, work, work2};
   cudaEventRecord(r.a, st);
   g_prof.push_back(r);
   slot = (int)g_prof.size() - 1;
@@ -60,15 +60,16 @@ extern "C" int wmk_profile_enable(int on) {
 }
 extern "C" int wmk_profile_num_families(void) { return wmk::FAM_COUNT; }
 extern "C" const char* wmk_profile_family_name(int f) { return f >= 0 && f < wmk::FAM_COUNT ? wmk::kFamilyNames[f] : ""; }
-extern "C" int wmk_profile_collect(double* ms, double* work, uint64_t* launches) {
+extern "C" int wmk_profile_collect(double* ms, double* work, double* work2, uint64_t* launches) {
   using namespace wmk;
   std::lock_guard<std::mutex> lk(g_prof_mu);
-  for (int f = 0; f < FAM_COUNT; ++f) { ms[f] = 0; work[f] = 0; launches[f] = 0; }
+  for (int f = 0; f < FAM_COUNT; ++f) { ms[f] = 0; work[f] = 0; launches[f] = 0; if (work2) work2[f] = 0; }
   for (ProfRec& r : g_prof) {
     if (cudaEventSynchronize(r.b) != cudaSuccess) { set_error("profile: event sync failed"); return WMK_ERR_CUDA; }
     float t = 0.f;
     cudaEventElapsedTime(&t, r.a, r.b);
     ms[r.family] += t; work[r.family] += r.work; launches[r.family] += 1;
+    if (work2) work2[r.family] += r.work2;
     g_prof_pool.push_back(r.a); g_prof_pool.push_back(r.b);
   }
   g_prof.clear();

@@ -71,7 +71,8 @@ int gemm_fp32_simt(const GemmArgs& g, cudaStream_t st) {
   WMK_REQUIRE(g.K % 4 == 0, "gemm_fp32: K=%d must be a multiple of 4", g.K);
   WMK_REQUIRE(((uintptr_t)g.A & 15) == 0 && ((uintptr_t)g.W & 15) == 0, "gemm_fp32: operands must be 16-byte aligned");
   EpiParams p{g.bias, g.resid, g.C, g.M, g.N, g.ldc, g.epi, g.out_bf16, g.up_h, g.up_w, g.up_cout};
-  ProfScope prof(FAM_GEMM, 2.0 * g.M * g.N * g.K, st);
+  const GemmWork gw = gemm_work(g, 4);
+  ProfScope prof(gw.family, gw.work, st, gw.work2);
   const int n_tiles = cdiv(g.N, TN);
   const long long grid = (long long)cdiv(g.M, TM) * n_tiles;
   gemm_fp32_kernel<<<(unsigned)grid, 256, 0, st>>>(reinterpret_cast<const float*>(g.A),

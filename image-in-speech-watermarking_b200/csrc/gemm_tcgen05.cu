@@ -577,7 +577,8 @@ int gemm_bf16_tcgen05(const GemmArgs& g, cudaStream_t st) {
   if (g.epi == EPI_UPSAMPLE)
     WMK_REQUIRE(g.up_cout % 32 == 0 && g.N == 4 * g.up_cout && g.M % (g.up_h * g.up_w) == 0,
                 "gemm_bf16: bad upsample geometry");
-  ProfScope prof(FAM_GEMM, 2.0 * g.M * g.N * g.K, st);
+  const GemmWork gw = gemm_work(g, 2);
+  ProfScope prof(gw.family, gw.work, st, gw.work2);
   if (g.epi != EPI_UPSAMPLE && g.ldc == g.N) {
     const bool wide_ok = g.epi != EPI_BIAS_RESID || g.K >= 1024;   // fp32 residual tiles: one 32-column piece per warp
     if (g.N % 256 == 0 && g.N >= 256 && wide_ok) return launch_persistent<256>(g, st);

@@ -54,10 +54,10 @@ void count_launch(int n = 1);
 // ---------------------------------------------------------------------------------------------
 enum Family {
   FAM_GEMM = 0, FAM_ATTENTION, FAM_LAYERNORM, FAM_DWCONV, FAM_LAYOUT, FAM_SMALL, FAM_STFT, FAM_ISTFT,
-  FAM_ATTACK, FAM_STATS, FAM_COUNT
+  FAM_ATTACK, FAM_STATS, FAM_GEMM_HBM, FAM_COUNT
 };
 struct ProfScope {
-  ProfScope(int family, double work, cudaStream_t st);
+  ProfScope(int family, double work, cudaStream_t st, double work2 = 0.0);
   ~ProfScope();
   int slot;
   cudaStream_t st;
@@ -91,6 +91,18 @@ struct GemmArgs {
   // co < up_cout; element goes to token (b, 2h+i, 2w+j), channel co of a [.., ldc] buffer.
   int up_h = 0, up_w = 0, up_cout = 0;
 };
+
+// Roofline class of a dense-layer launch: algorithmic bytes (A + W + C, + the fp32 residual) against
+// 2 M N K FLOPs; below the ridge point of the B200 (1401.6 TFLOP/s / 6548.8 GB/s = 214 FLOP/B) the
+// launch is HBM bound.  `es` = operand element size (2 = bf16, 4 = fp32).
+struct GemmWork { int family; double work, work2; };
+static inline GemmWork gemm_work(const GemmArgs& g, int es) {
+  const double flops = 2.0 * g.M * g.N * g.K;
+  const double bytes = (double)g.M * g.K * es + (double)g.N * g.K * es + (double)g.M * g.N * (g.out_bf16 ? 2 : 4) +
+                       (g.epi == EPI_BIAS_RESID ? (double)g.M * g.N * 4 : 0.0);
+  if (flops / bytes >= 214.0) return {FAM_GEMM, flops, bytes};
+  return {FAM_GEMM_HBM, bytes, flops};
+}
 
 int gemm_fp32_simt(const GemmArgs& g, cudaStream_t st);
 int gemm_bf16_tcgen05(const GemmArgs& g, cudaStream_t st);

@@ -54,11 +54,14 @@ uint64_t wmk_launch_count(void);
 /* Per-kernel-family device timing (CUDA events on the launching stream around every launch of the
  * family).  collect() synchronises, fills ms / work / launches [wmk_profile_num_families()] with
  * the totals since the last collect and resets them.  work = algorithmic FLOPs (gemm,
- * window_attention) or algorithmic bytes (all other families). */
+ * window_attention) or algorithmic bytes (all other families).  Dense-layer launches are split by
+ * their arithmetic intensity against the B200 ridge point (214 FLOP/B): "gemm" holds the
+ * tensor-bound launches (work = FLOPs, work2 = bytes), "gemm_hbm" the HBM-bound ones (work =
+ * algorithmic bytes A + W + C (+ residual), work2 = FLOPs).  work2 may be NULL. */
 int wmk_profile_enable(int on);
 int wmk_profile_num_families(void);
 const char* wmk_profile_family_name(int family);
-int wmk_profile_collect(double* ms, double* work, uint64_t* launches);
+int wmk_profile_collect(double* ms, double* work, double* work2, uint64_t* launches);
 
 /* ------------------------------------------------------------------------------------------
  * STFT / ISTFT front end.
