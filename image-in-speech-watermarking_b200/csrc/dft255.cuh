@@ -12,7 +12,7 @@
 //
 // The phase functions below are written per (role, lane): in the kernels `f` (the frame inside a
 // 32-frame tile) is always the lane, so every shared-memory access is conflict free and every
-// role index (n2, k1, part, bin) is warp uniform.  They also compile as plain C++ (g++) so that the
+// role index (n2, k1, bin) is warp uniform.  They also compile as plain C++ (g++) so that the
 // index maps can be unit-tested on the host (tests/test_dft255_host.py).
 #pragma once
 
@@ -31,8 +31,7 @@ namespace dft255 {
 
 constexpr int NFFT = 255, HOP = 63, PAD = 127, BINS = 128;
 constexpr int FT = 32;                        // frames per tile = lanes of a warp
-constexpr int SA_FLOAT2 = 8 * 17 * FT;        // stage-A output  [k1][n2][f]
-constexpr int R_FLOAT2 = 2 * 8 * 9 * FT;      // half-DFT-17 sums [part][k1][k][f]
+constexpr int SA_FLOAT2 = 8 * 17 * FT;        // stage-A output / inverse stage-B output  [k1][n2][f]
 
 WMK_HD constexpr float cos15(int m) {
   constexpr float t[15] = {1.000000000e+00f, 9.135454297e-01f, 6.691306233e-01f, 3.090170026e-01f, -1.045284644e-01f,
@@ -62,11 +61,15 @@ WMK_HD constexpr float sin17(int m) {
 }
 
 // Bin tables (built once on the host, read warp-uniformly from __constant__ memory).
-//   fwd[bin]      : which half-sums make one-sided bin `bin`:  k1 | kk<<3 | minus<<7 | conj<<8
-//   inv[k1*17+k2] : which one-sided bin feeds Y[k1][k2]:       bin | conj<<7
+//   fwd[k1*17+k2] : the one-sided bin that output (k1,k2) of the forward transform is and the sign of
+//                   its imaginary part (bin < 0 for the mirrored half of the real k1 = 0 transform,
+//                   which is not stored)
+//   inv[k1*17+k2] : the one-sided bin that feeds Y[k1][k2] of the inverse and the sign of its
+//                   imaginary part (-1: conjugate, 0: the ignored imaginary part of DC)
+struct InvEntry { int bin; float im_sign; };
 struct Tables {
-  unsigned short fwd[128];
-  unsigned char inv[8 * 17];
+  InvEntry fwd[8 * 17];
+  InvEntry inv[8 * 17];
 };
 
 static inline void build_tables(Tables* t) {
@@ -75,59 +78,75 @@ static inline void build_tables(Tables* t) {
       const int k = (136 * k1 + 120 * k2) % 255;
       const int bin = k <= 127 ? k : 255 - k;
       const int conj = k > 127;
-      t->inv[k1 * 17 + k2] = (unsigned char)(bin | (conj << 7));
-      if (k1 == 0 && k2 > 8) continue;          // the mirrored half of the real k1 = 0 transform
-      const int kk = k2 <= 8 ? k2 : 17 - k2;
-      const int minus = k2 > 8;
-      t->fwd[bin] = (unsigned short)(k1 | (kk << 3) | (minus << 7) | (conj << 8));
+      t->inv[k1 * 17 + k2].bin = bin;
+      t->inv[k1 * 17 + k2].im_sign = bin == 0 ? 0.f : (conj ? -1.f : 1.f);
+      t->fwd[k1 * 17 + k2].bin = (k1 == 0 && k2 > 8) ? -1 : bin;
+      t->fwd[k1 * 17 + k2].im_sign = conj ? -1.f : 1.f;
     }
 }
 
-// One half of a 17-point complex DFT by the even/odd split.
-//   PART 0: acc[0] = y0 + sum_n y[n];  acc[k] = y0 + sum_{n=1..8} (y[n]+y[17-n]) cos(2 pi k n/17)
-//   PART 1: acc[0] = 0;                acc[k] =      sum_{n=1..8} (y[n]-y[17-n]) sin(2 pi k n/17)
-// forward  (e^-):  Y[k] = A - iB = (A.x + B.y, A.y - B.x),  Y[17-k] = A + iB = (A.x - B.y, A.y + B.x)
-// inverse  (e^+):  roles of k and 17-k swap.
-template <int PART>
-WMK_HD void dft17_half(const float2 (&y)[17], float2 (&acc)[9]) {
-  float2 d[9];
+// 17-point complex DFT by the even/odd split; emit(k, Y[k]) is called once for every k = 0..16.
+//   A_k = y0 + sum_{n=1..8} (y[n]+y[17-n]) cos(2 pi k n/17),   B_k = sum_{n=1..8} (y[n]-y[17-n]) sin(2 pi k n/17)
+//   forward (e^-):  Y[k] = A - iB,  Y[17-k] = A + iB;     inverse (e^+): the two swap.
+template <bool INVERSE, class Emit>
+WMK_HD void dft17(const float2 (&y)[17], Emit&& emit) {
+  float2 e[9], o[9];
 #pragma unroll
   for (int n = 1; n <= 8; ++n) {
-    if (PART == 0) d[n] = make_float2(y[n].x + y[17 - n].x, y[n].y + y[17 - n].y);
-    else d[n] = make_float2(y[n].x - y[17 - n].x, y[n].y - y[17 - n].y);
+    e[n] = make_float2(y[n].x + y[17 - n].x, y[n].y + y[17 - n].y);
+    o[n] = make_float2(y[n].x - y[17 - n].x, y[n].y - y[17 - n].y);
   }
-  if (PART == 0) {
-    float2 s = y[0];
+  float2 s = y[0];
 #pragma unroll
-    for (int n = 1; n <= 8; ++n) { s.x += d[n].x; s.y += d[n].y; }
-    acc[0] = s;
-  } else {
-    acc[0] = make_float2(0.f, 0.f);
-  }
+  for (int n = 1; n <= 8; ++n) { s.x += e[n].x; s.y += e[n].y; }
+  emit(0, s);
 #pragma unroll
   for (int k = 1; k <= 8; ++k) {
-    float2 a = PART == 0 ? y[0] : make_float2(0.f, 0.f);
+    float2 a = y[0], b = make_float2(0.f, 0.f);
 #pragma unroll
     for (int n = 1; n <= 8; ++n) {
-      const float c = PART == 0 ? cos17((k * n) % 17) : sin17((k * n) % 17);
-      a.x = fmaf(d[n].x, c, a.x);
-      a.y = fmaf(d[n].y, c, a.y);
+      const float c = cos17((k * n) % 17), sn = sin17((k * n) % 17);
+      a.x = fmaf(e[n].x, c, a.x);
+      a.y = fmaf(e[n].y, c, a.y);
+      b.x = fmaf(o[n].x, sn, b.x);
+      b.y = fmaf(o[n].y, sn, b.y);
     }
-    acc[k] = a;
+    const float2 m = make_float2(a.x + b.y, a.y - b.x);     // A - iB
+    const float2 q = make_float2(a.x - b.y, a.y + b.x);     // A + iB
+    emit(INVERSE ? 17 - k : k, m);
+    emit(INVERSE ? k : 17 - k, q);
   }
 }
+
+// Good-Thomas input map n = (17 n1 + 15 n2) mod 255 for the 15 samples of residue n2.  n2 is warp
+// uniform; the switch turns the 15 offsets into immediates (one uniform branch instead of a
+// compare/select chain per sample).
+template <int N2>
+WMK_HD void gather15(const float* base, float (&v)[15]) {
+#pragma unroll
+  for (int n1 = 0; n1 < 15; ++n1) v[n1] = base[(17 * n1 + 15 * N2) % NFFT];
+}
+template <int N2>
+WMK_HD void scatter15(float* base, const float (&v)[15]) {
+#pragma unroll
+  for (int n1 = 0; n1 < 15; ++n1) base[(17 * n1 + 15 * N2) % NFFT] = v[n1];
+}
+#define WMK_DFT255_SWITCH17(n2, CALL)                                                                     \
+  switch (n2) {                                                                                           \
+    case 0: CALL(0); break;   case 1: CALL(1); break;   case 2: CALL(2); break;   case 3: CALL(3); break;   \
+    case 4: CALL(4); break;   case 5: CALL(5); break;   case 6: CALL(6); break;   case 7: CALL(7); break;   \
+    case 8: CALL(8); break;   case 9: CALL(9); break;   case 10: CALL(10); break; case 11: CALL(11); break; \
+    case 12: CALL(12); break; case 13: CALL(13); break; case 14: CALL(14); break; case 15: CALL(15); break; \
+    default: CALL(16); break;                                                                             \
+  }
 
 // ---- forward stage A: 15-point real DFT over n1 for one (frame f, residue n2) -> k1 = 0..7
 // samp: the tile's padded samples (frame f starts at samp[63 f]); SA[k1][n2][f].
 WMK_HD void fwd_stage_a(const float* samp, float2* SA, int n2, int f) {
   float v[15];
-  int off = 15 * n2;
-#pragma unroll
-  for (int n1 = 0; n1 < 15; ++n1) {
-    v[n1] = samp[HOP * f + off];
-    off += 17;
-    if (off >= NFFT) off -= NFFT;
-  }
+#define WMK_CALL(N) gather15<N>(samp + HOP * f, v)
+  WMK_DFT255_SWITCH17(n2, WMK_CALL)
+#undef WMK_CALL
   float e[8], o[8];
 #pragma unroll
   for (int n = 1; n <= 7; ++n) { e[n] = v[n] + v[15 - n]; o[n] = v[n] - v[15 - n]; }
@@ -147,61 +166,41 @@ WMK_HD void fwd_stage_a(const float* samp, float2* SA, int n2, int f) {
   }
 }
 
-// ---- forward stage B: one half of the 17-point DFT over n2 for (part, k1, frame f)
-template <int PART>
-WMK_HD void fwd_stage_b(const float2* SA, float2* R, int k1, int f) {
-  float2 y[17], acc[9];
+// ---- forward stage B: the 17-point DFT over n2 for (k1, frame f); store(bin, re, im) receives each
+// one-sided bin exactly once over k1 = 0..7.
+template <class Store>
+WMK_HD void fwd_stage_b(const float2* SA, const InvEntry* fwd_tab, int k1, int f, Store&& store) {
+  float2 y[17];
 #pragma unroll
   for (int n2 = 0; n2 < 17; ++n2) y[n2] = SA[(k1 * 17 + n2) * FT + f];
-  dft17_half<PART>(y, acc);
-#pragma unroll
-  for (int k = 0; k <= 8; ++k) R[((PART * 8 + k1) * 9 + k) * FT + f] = acc[k];
+  dft17<false>(y, [&](int k2, float2 X) {
+    const InvEntry e = fwd_tab[k1 * 17 + k2];
+    if (e.bin >= 0) store(e.bin, X.x, X.y * e.im_sign);
+  });
 }
 
-// ---- forward stage C: combine the two halves into one-sided bin `bin` of frame f
-WMK_HD float2 fwd_stage_c(const float2* R, unsigned short entry, int f) {
-  const int k1 = entry & 7, kk = (entry >> 3) & 15;
-  const float2 a = R[((0 * 8 + k1) * 9 + kk) * FT + f];
-  const float2 b = R[((1 * 8 + k1) * 9 + kk) * FT + f];
-  const float sg = (entry & 0x80) ? -1.f : 1.f;
-  float2 X = make_float2(fmaf(sg, b.y, a.x), fmaf(-sg, b.x, a.y));
-  if (entry & 0x100) X.y = -X.y;
-  return X;
-}
-
-// ---- inverse stage B': half of the inverse 17-point DFT over k2 for (part, k1, frame f).
+// ---- inverse stage B': the inverse 17-point DFT over k2 for (k1, frame f) -> ZS[k1][n2][f].
 // XS[row][f], row = reim*128 + bin: the one-sided spectrum tile; the imaginary part of DC is ignored
 // as in a C2R transform.
-template <int PART>
-WMK_HD void inv_stage_b(const float* XS, const unsigned char* inv_tab, float2* R, int k1, int f) {
-  float2 y[17], acc[9];
+WMK_HD void inv_stage_b(const float* XS, const InvEntry* inv_tab, float2* ZS, int k1, int f) {
+  float2 y[17];
 #pragma unroll
   for (int k2 = 0; k2 < 17; ++k2) {
-    const int e = inv_tab[k1 * 17 + k2];
-    const int bin = e & 127;
-    const float re = XS[bin * FT + f];
-    float im = XS[(BINS + bin) * FT + f];
-    if (e & 128) im = -im;
-    if (bin == 0) im = 0.f;
-    y[k2] = make_float2(re, im);
+    const InvEntry e = inv_tab[k1 * 17 + k2];
+    y[k2] = make_float2(XS[e.bin * FT + f], XS[(BINS + e.bin) * FT + f] * e.im_sign);
   }
-  dft17_half<PART>(y, acc);
-#pragma unroll
-  for (int k = 0; k <= 8; ++k) R[((PART * 8 + k1) * 9 + k) * FT + f] = acc[k];
+  dft17<true>(y, [&](int n2, float2 Z) { ZS[(k1 * 17 + n2) * FT + f] = Z; });
 }
 
 // ---- inverse stage A': complex-to-real inverse 15-point DFT over k1 for (n2, frame f); writes the
 // 15 time samples n = (17 n1 + 15 n2) mod 255 of frame f (already divided by 255) to FR[f][n].
-WMK_HD void inv_stage_a(const float2* R, float* FR, int n2, int f) {
-  const int n = n2 <= 8 ? n2 : 17 - n2;
-  const float sg = n2 <= 8 ? 1.f : -1.f;
+WMK_HD void inv_stage_a(const float2* ZS, float* FR, int n2, int f) {
   float zr[8], zi[8];
 #pragma unroll
   for (int k1 = 0; k1 < 8; ++k1) {
-    const float2 a = R[((0 * 8 + k1) * 9 + n) * FT + f];
-    const float2 b = R[((1 * 8 + k1) * 9 + n) * FT + f];
-    zr[k1] = fmaf(-sg, b.y, a.x);
-    zi[k1] = fmaf(sg, b.x, a.y);
+    const float2 z = ZS[(k1 * 17 + n2) * FT + f];
+    zr[k1] = z.x;
+    zi[k1] = z.y;
   }
   constexpr float s1 = 1.0f / 255.0f, s2 = 2.0f / 255.0f;
   float v[15];
@@ -220,13 +219,9 @@ WMK_HD void inv_stage_a(const float2* R, float* FR, int n2, int f) {
     v[n1] = P - Q;
     v[15 - n1] = P + Q;
   }
-  int off = 15 * n2;
-#pragma unroll
-  for (int n1 = 0; n1 < 15; ++n1) {
-    FR[f * NFFT + off] = v[n1];
-    off += 17;
-    if (off >= NFFT) off -= NFFT;
-  }
+#define WMK_CALL(N) scatter15<N>(FR + f * NFFT, v)
+  WMK_DFT255_SWITCH17(n2, WMK_CALL)
+#undef WMK_CALL
 }
 
 }  // namespace dft255

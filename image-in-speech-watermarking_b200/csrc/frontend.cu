@@ -5,8 +5,8 @@
 //
 // v2 formulation (HBM bound by design): one CTA = one tile of 32 consecutive frames, lane = frame.
 // The 255-point transform is the twiddle-free 15 x 17 prime-factor FFT of dft255.cuh with
-// shared-memory staged butterflies: stage A (17 warps, one per residue n2) -> stage B (16 warps,
-// one per (half, k1)) -> stage C (bins, warp uniform).  Every waveform sample is read from HBM
+// shared-memory staged butterflies: stage A (17 warps, one per residue n2) -> stage B (8 warps,
+// one per k1, storing straight to global memory).  Every waveform sample is read from HBM
 // once per CTA (the 75% frame overlap is served from shared memory, 9% halo re-read hits L2) and
 // every spectrogram value is written / read once, directly in the (2,128,128) clip layout the
 // model consumes, as 128-byte row segments.  Algorithmic traffic: 1276 B per frame.
@@ -23,7 +23,8 @@ namespace {
 constexpr int NFFT = 255, HOP = 63, PAD = 127, BINS = 128;
 using dft255::FT;
 constexpr int kFrontThreads = 17 * 32;
-constexpr int kSampFloats = HOP * (FT - 1) + NFFT + 1;   // 2209 (kept even for float2 alignment after it)
+constexpr int kTileSamples = HOP * (FT - 1) + NFFT;      // 2208 samples feed the 32 frames of a tile
+constexpr int kSampFloats = kTileSamples + 8;            // + up to 3 floats of alignment slack, 16-byte multiple
 
 __constant__ dft255::Tables c_tab;
 
@@ -42,80 +43,212 @@ int ensure_tables() {
   return 0;
 }
 
-// grid (frame tiles of 32 = 4 * n_clips, B); 544 threads = 17 warps.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// grid (ceil(4 n_clips / G), B); 544 threads = 17 warps; a CTA walks G consecutive 32-frame tiles of
+// one utterance and prefetches the next tile's samples with cp.async while it transforms the
+// current one.
+//   load : 2208 samples -> smem (16-byte cp.async on interior tiles; reflect padding on edge tiles)
+//   A    : warp = residue n2 (17 warps): 15-point real DFTs                -> SA[k1][n2][f]
+//   B    : warp = k1 (8 warps): 17-point complex DFTs, results stored straight to the clip rows
+//          (lane = frame, so every store instruction writes one 128-byte row segment)
+struct StftTile {
+  const float* wv; int L, q0, mis, n4; bool fast;
+  __device__ StftTile(const float* wv_, int L_, int f0) : wv(wv_), L(L_) {
+    q0 = HOP * f0 - PAD;                            // first sample of the tile (centre=True: 127 of padding)
+    mis = (int)(((uintptr_t)(wv + q0) >> 2) & 3);   // floats past a 16-byte boundary
+    n4 = (kTileSamples + mis + 3) >> 2;
+    fast = q0 - mis >= 0 && q0 - mis + 4 * n4 <= L;
+  }
+  __device__ void prefetch(float* buf, int tid) const {
+    const float4* src = reinterpret_cast<const float4*>(wv + q0 - mis);
+    for (int i = tid; i < n4; i += kFrontThreads) cp_async16(reinterpret_cast<float4*>(buf) + i, src + i);
+  }
+  __device__ void load_edge(float* buf, int tid) const {
+    float r[5];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      const int i = tid + j * kFrontThreads;
+      int q = q0 + i;
+      if (q < 0) q = -q;                            // reflect padding
+      if (q >= L) q = 2 * (L - 1) - q;
+      r[j] = (i < kTileSamples && q >= 0 && q < L) ? wv[q] : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      const int i = tid + j * kFrontThreads;
+      if (i < kTileSamples) buf[i] = r[j];
+    }
+  }
+};
+
+template <bool ALL_LIVE>
+__device__ __forceinline__ void stft_stage_b(const float2* SA, int k1, int lane, float* orow, float live) {
+  dft255::fwd_stage_b(SA, c_tab.fwd, k1, lane, [&](int bin, float re, float im) {
+    float* o = orow + bin * 128;
+    o[0] = ALL_LIVE ? re : re * live;
+    o[BINS * 128] = ALL_LIVE ? im : im * live;
+  });
+}
+
 __global__ void __launch_bounds__(kFrontThreads, 2)
-stft_clips_kernel(const float* __restrict__ wave, int L, int T, float* __restrict__ clips, int n_clips) {
+stft_clips_kernel(const float* __restrict__ wave, int L, int T, float* __restrict__ clips, int n_clips, int G) {
   extern __shared__ __align__(16) float smem[];
-  float* samp = smem;                                                   // [2210]
-  float2* SA = reinterpret_cast<float2*>(smem + kSampFloats + 1);        // [8][17][32]
-  float2* R = SA + dft255::SA_FLOAT2;                                    // [2][8][9][32]
-  const int b = blockIdx.y, f0 = blockIdx.x * FT;
+  float2* SA = reinterpret_cast<float2*>(smem + 2 * kSampFloats);        // [8][17][32]
+  const int b = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  float* orow = clips + ((size_t)b * n_clips + (f0 >> 7)) * 2 * BINS * 128 + (f0 & 127) + lane;
-  if (f0 >= T) {                                    // padding frames of the last clip (audio_test.py:319-320)
-    for (int r = warp; r < 2 * BINS; r += 17) orow[(size_t)r * 128] = 0.f;
-    return;
-  }
   const float* wv = wave + (size_t)b * L;
-  for (int i = tid; i < HOP * (FT - 1) + NFFT; i += kFrontThreads) {
-    int q = HOP * f0 + i - PAD;
-    if (q < 0) q = -q;                              // centre=True reflect padding
-    if (q >= L) q = 2 * (L - 1) - q;
-    samp[i] = (q >= 0 && q < L) ? wv[q] : 0.f;
+  const int tile0 = blockIdx.x * G;
+  const int n_tiles = min(G, 4 * n_clips - tile0);
+  bool prefetched = false;
+  if (tile0 * FT < T) {
+    StftTile t0(wv, L, tile0 * FT);
+    if (t0.fast) { t0.prefetch(smem, tid); prefetched = true; }
   }
-  __syncthreads();
-  dft255::fwd_stage_a(samp, SA, warp, lane);
-  __syncthreads();
-  if (warp < 8) dft255::fwd_stage_b<0>(SA, R, warp, lane);
-  else if (warp < 16) dft255::fwd_stage_b<1>(SA, R, warp - 8, lane);
-  __syncthreads();
-  const bool live = f0 + lane < T;
-  for (int bin = warp; bin < BINS; bin += 17) {
-    const float2 X = dft255::fwd_stage_c(R, c_tab.fwd[bin], lane);
-    orow[(size_t)bin * 128] = live ? X.x : 0.f;
-    orow[(size_t)(BINS + bin) * 128] = live ? X.y : 0.f;
+  for (int it = 0; it < n_tiles; ++it) {
+    const int f0 = (tile0 + it) * FT;
+    float* orow = clips + ((size_t)b * n_clips + (f0 >> 7)) * 2 * BINS * 128 + (f0 & 127) + lane;
+    if (f0 >= T) {                                  // padding frames of the last clip (audio_test.py:319-320)
+      for (int r = warp; r < 2 * BINS; r += 17) orow[(size_t)r * 128] = 0.f;
+      continue;
+    }
+    float* buf = smem + (it & 1) * kSampFloats;
+    const StftTile cur(wv, L, f0);
+    if (prefetched) cp_async_wait_all();
+    else cur.load_edge(buf, tid);
+    __syncthreads();                                // samples visible; everyone is done with SA of the last tile
+    prefetched = false;
+    if (it + 1 < n_tiles && f0 + FT < T) {
+      const StftTile nxt(wv, L, f0 + FT);
+      if (nxt.fast) { nxt.prefetch(smem + ((it + 1) & 1) * kSampFloats, tid); prefetched = true; }
+    }
+    dft255::fwd_stage_a(buf + (cur.fast ? cur.mis : 0), SA, warp, lane);
+    __syncthreads();
+    if (warp < 8) {
+      if (f0 + FT <= T) stft_stage_b<true>(SA, warp, lane, orow, 1.f);
+      else stft_stage_b<false>(SA, warp, lane, orow, f0 + lane < T ? 1.f : 0.f);
+    }
   }
 }
 
-// One CTA reconstructs 28 hops (1764 samples) of the padded overlap-add buffer from 32 frames
-// (4 halo frames recomputed instead of atomics), divides by the overlap count and trims.
+// One CTA step reconstructs 28 hops (1764 samples) of the padded overlap-add buffer from 32 frames
+// (4 halo frames recomputed instead of atomics), divides by the overlap count and trims; a CTA walks
+// G consecutive steps and prefetches the next spectrum tile with cp.async.
+//   load : the 256 x 32 spectrum tile -> XS (lane = frame)
+//   B'   : warp = k1 (8 warps): inverse 17-point DFTs        -> ZS[k1][n2][f]
+//   A'   : warp = n2 (17 warps): complex-to-real 15-point inverse DFTs -> FR[f][n] (over XS)
+//   OLA  : each output sample sums the 4-5 frames that cover it
 constexpr int IFT = FT - 4;
+constexpr int kXsFloats = 2 * BINS * FT;
+
+__device__ __forceinline__ void istft_prefetch(const float* __restrict__ clips_b, int fbase, float* XS, int tid) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = tid + j * kFrontThreads;          // 16-byte chunk: row c>>3, frames fbase + 4 (c&7) ..
+    if (c < 2 * BINS * 8) {
+      const int row = c >> 3, t = fbase + 4 * (c & 7);
+      cp_async16(XS + row * FT + 4 * (c & 7), clips_b + ((size_t)(t >> 7) * 2 * BINS + row) * 128 + (t & 127));
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kFrontThreads, 2)
-istft_clips_kernel(const float* __restrict__ clips, int n_clips, int T, float* __restrict__ wave, int length) {
+istft_clips_kernel(const float* __restrict__ clips, int n_clips, int T, float* __restrict__ wave, int length, int G,
+                   int n_steps) {
   extern __shared__ __align__(16) float smem[];
-  float* XS = smem;                                                     // [256][32], later FR [32][255]
-  float2* R = reinterpret_cast<float2*>(smem + 2 * BINS * FT);          // [2][8][9][32]
+  float2* ZS = reinterpret_cast<float2*>(smem + 2 * kXsFloats);         // [8][17][32]
   const int b = blockIdx.y;
-  const int fbase = blockIdx.x * IFT - 4;           // first (halo) frame of this CTA
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  {
-    const int t = fbase + lane;
-    const bool tv = t >= 0 && t < T;
-    const float* src = clips + ((size_t)b * n_clips + (tv ? (t >> 7) : 0)) * 2 * BINS * 128 + (t & 127);
-    for (int r = warp; r < 2 * BINS; r += 17) XS[r * FT + lane] = tv ? src[(size_t)r * 128] : 0.f;
-  }
-  __syncthreads();
-  if (warp < 8) dft255::inv_stage_b<0>(XS, c_tab.inv, R, warp, lane);
-  else if (warp < 16) dft255::inv_stage_b<1>(XS, c_tab.inv, R, warp - 8, lane);
-  __syncthreads();
-  float* FR = XS;
-  dft255::inv_stage_a(R, FR, warp, lane);
-  __syncthreads();
-  const int p0 = HOP * (fbase + 4);
+  const float* clips_b = clips + (size_t)b * n_clips * 2 * BINS * 128;
   float* wv = wave + (size_t)b * length;
-  for (int i = tid; i < HOP * IFT; i += kFrontThreads) {
-    const int p = p0 + i;
-    const int jn = p - PAD;
-    if (jn < 0 || jn >= length) continue;
-    int t_hi = p / HOP;
-    if (t_hi > T - 1) t_hi = T - 1;
-    int t_lo = (p - (NFFT - 1) + HOP - 1) / HOP;
-    if (p - (NFFT - 1) < 0) t_lo = 0;
-    float s = 0.f;
-    for (int t = t_lo; t <= t_hi; ++t) s += FR[(t - fbase) * NFFT + (p - HOP * t)];
-    const int cnt = t_hi - t_lo + 1;
-    wv[jn] = cnt > 0 ? s / (float)cnt : 0.f;
+  const int step0 = blockIdx.x * G;
+  const int n_it = min(G, n_steps - step0);
+  auto is_interior = [&](int fb) { return fb >= 0 && fb + FT - 1 <= T - 1; };
+  bool prefetched = false;
+  if (is_interior(step0 * IFT - 4)) { istft_prefetch(clips_b, step0 * IFT - 4, smem, tid); prefetched = true; }
+  for (int it = 0; it < n_it; ++it) {
+    const int fbase = (step0 + it) * IFT - 4;       // first (halo) frame of this step
+    float* XS = smem + (it & 1) * kXsFloats;        // [256][32], later FR [32][255]
+    if (prefetched) {
+      cp_async_wait_all();
+    } else {
+      const int t = fbase + lane;
+      const bool tv = t >= 0 && t < T;
+      const int tc = tv ? t : 0;                    // out-of-range frames read a valid address and are zeroed
+      const float* src = clips_b + (size_t)(tc >> 7) * 2 * BINS * 128 + (tc & 127) + warp * 128;
+      float r[16];
+#pragma unroll
+      for (int j = 0; j < 15; ++j) r[j] = __ldg(src + j * 17 * 128);     // rows warp + 17 j <= 254
+      r[15] = warp == 0 ? __ldg(src + 255 * 128) : 0.f;                   // row 255
+      float* dst = XS + warp * FT + lane;
+#pragma unroll
+      for (int j = 0; j < 15; ++j) dst[j * 17 * FT] = tv ? r[j] : 0.f;
+      if (warp == 0) dst[255 * FT] = tv ? r[15] : 0.f;
+    }
+    __syncthreads();                                // tile visible; the other buffer (FR of the last step) is free
+    prefetched = false;
+    if (it + 1 < n_it && is_interior(fbase + IFT)) {
+      istft_prefetch(clips_b, fbase + IFT, smem + ((it + 1) & 1) * kXsFloats, tid);
+      prefetched = true;
+    }
+    if (warp < 8) dft255::inv_stage_b(XS, c_tab.inv, ZS, warp, lane);
+    __syncthreads();
+    float* FR = XS;
+    dft255::inv_stage_a(ZS, FR, warp, lane);
+    __syncthreads();
+    if (is_interior(fbase) && PAD + length >= HOP * (fbase + FT)) {
+      // 8 groups of 63 threads: thread (g, r) owns offset r of hops g, g+8, g+16, (g+24).  Sample p = 63 h' + r
+      // is covered by frames h', h'-1, .., h'-3 (and h'-4 when r <= 2) at offsets r, r+63, ..: rows 192 apart.
+      if (tid < 8 * HOP) {
+        const int g = tid / HOP, r = tid - g * HOP;
+        const bool five = r <= 2;
+        const float inv = five ? 0.2f : 0.25f;
+        const float* fr = FR + (g + 4) * NFFT + r;
+        float* o = wv + HOP * (fbase + 4 + g) + r - PAD;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (g + 8 * j < IFT) {
+            const float* q = fr + j * 8 * NFFT;
+            float s = (q[0] + q[-192]) + (q[-384] + q[-576]);
+            if (five) s += q[-768];
+            o[j * 8 * HOP] = s * inv;
+          }
+        }
+      }
+    } else {
+      for (int i = tid; i < HOP * IFT; i += kFrontThreads) {
+        const int p = HOP * (fbase + 4) + i;
+        const int jn = p - PAD;
+        if (jn < 0 || jn >= length) continue;
+        int t_hi = p / HOP;
+        if (t_hi > T - 1) t_hi = T - 1;
+        int t_lo = (p - (NFFT - 1) + HOP - 1) / HOP;
+        if (p - (NFFT - 1) < 0) t_lo = 0;
+        float s = 0.f;
+        for (int t = t_lo; t <= t_hi; ++t) s += FR[(t - fbase) * NFFT + (p - HOP * t)];
+        const int cnt = t_hi - t_lo + 1;
+        wv[jn] = cnt > 0 ? s / (float)cnt : 0.f;
+      }
+    }
   }
+}
+
+// tiles (steps) per CTA: 1 until the grid is several waves deep, then up to 4 (prefetch pays once
+// there are enough CTAs to keep 2 x 148 resident ones busy)
+int tiles_per_cta(long long tiles_total) {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  const long long per = tiles_total / (2LL * sms * 4);
+  return per >= 4 ? 4 : per >= 2 ? 2 : 1;
 }
 
 }  // namespace
@@ -125,15 +258,17 @@ int stft_clips(const float* wave, int B, int L, float* clips, int n_clips, cudaS
   const int T = 1 + (L - 1) / HOP;
   WMK_REQUIRE(n_clips * 128 >= T, "stft: n_clips=%d cannot hold %d frames", n_clips, T);
   WMK_TRY(ensure_tables());
-  const size_t smem = (kSampFloats + 1) * sizeof(float) + (dft255::SA_FLOAT2 + dft255::R_FLOAT2) * sizeof(float2);
+  const size_t smem = 2 * kSampFloats * sizeof(float) + dft255::SA_FLOAT2 * sizeof(float2);
   static bool attr = false;
   if (!attr) {
     WMK_CHECK_CUDA(cudaFuncSetAttribute(stft_clips_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
   ProfScope prof(FAM_STFT, 1276.0 * T * B, st);
-  dim3 grid(n_clips * (128 / FT), B);
-  stft_clips_kernel<<<grid, kFrontThreads, smem, st>>>(wave, L, T, clips, n_clips);
+  const int tiles = n_clips * (128 / FT);
+  const int G = tiles_per_cta((long long)tiles * B);
+  dim3 grid(cdiv(tiles, G), B);
+  stft_clips_kernel<<<grid, kFrontThreads, smem, st>>>(wave, L, T, clips, n_clips, G);
   WMK_CHECK_LAUNCH("stft_clips_kernel");
   return 0;
 }
@@ -145,15 +280,17 @@ int istft_clips(const float* clips, int B, int n_clips, int T, float* wave, int 
   const int total = NFFT + HOP * (T - 1);
   int need = PAD + length;
   if (need < total) need = total;
-  const size_t smem = 2 * BINS * FT * sizeof(float) + dft255::R_FLOAT2 * sizeof(float2);
+  const size_t smem = 2 * kXsFloats * sizeof(float) + dft255::SA_FLOAT2 * sizeof(float2);
   static bool attr = false;
   if (!attr) {
     WMK_CHECK_CUDA(cudaFuncSetAttribute(istft_clips_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
   ProfScope prof(FAM_ISTFT, 1276.0 * T * B, st);
-  dim3 grid(cdiv(need, HOP * IFT), B);
-  istft_clips_kernel<<<grid, kFrontThreads, smem, st>>>(clips, n_clips, T, wave, length);
+  const int steps = cdiv(need, HOP * IFT);
+  const int G = tiles_per_cta((long long)steps * B);
+  dim3 grid(cdiv(steps, G), B);
+  istft_clips_kernel<<<grid, kFrontThreads, smem, st>>>(clips, n_clips, T, wave, length, G, steps);
   WMK_CHECK_LAUNCH("istft_clips_kernel");
   return 0;
 }

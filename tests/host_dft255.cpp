@@ -9,31 +9,25 @@ using namespace wmk::dft255;
 extern "C" void host_stft_tile(const float* samp, float* out /* [256][32] */) {
   Tables tb;
   build_tables(&tb);
-  std::vector<float2> SA(SA_FLOAT2), R(R_FLOAT2);
+  std::vector<float2> SA(SA_FLOAT2);
   for (int n2 = 0; n2 < 17; ++n2)
     for (int f = 0; f < FT; ++f) fwd_stage_a(samp, SA.data(), n2, f);
+  for (int i = 0; i < 256 * FT; ++i) out[i] = -12345.f;        // every bin must be stored exactly once
   for (int k1 = 0; k1 < 8; ++k1)
-    for (int f = 0; f < FT; ++f) {
-      fwd_stage_b<0>(SA.data(), R.data(), k1, f);
-      fwd_stage_b<1>(SA.data(), R.data(), k1, f);
-    }
-  for (int bin = 0; bin < BINS; ++bin)
-    for (int f = 0; f < FT; ++f) {
-      const float2 X = fwd_stage_c(R.data(), tb.fwd[bin], f);
-      out[bin * FT + f] = X.x;
-      out[(BINS + bin) * FT + f] = X.y;
-    }
+    for (int f = 0; f < FT; ++f)
+      fwd_stage_b(SA.data(), tb.fwd, k1, f, [&](int bin, float re, float im) {
+        if (out[bin * FT + f] != -12345.f) out[bin * FT + f] = 1e30f;    // duplicate store -> test fails
+        else out[bin * FT + f] = re;
+        out[(BINS + bin) * FT + f] = im;
+      });
 }
 
 extern "C" void host_istft_tile(const float* XS /* [256][32] */, float* FR /* [32][255] */) {
   Tables tb;
   build_tables(&tb);
-  std::vector<float2> R(R_FLOAT2);
+  std::vector<float2> ZS(SA_FLOAT2);
   for (int k1 = 0; k1 < 8; ++k1)
-    for (int f = 0; f < FT; ++f) {
-      inv_stage_b<0>(XS, tb.inv, R.data(), k1, f);
-      inv_stage_b<1>(XS, tb.inv, R.data(), k1, f);
-    }
+    for (int f = 0; f < FT; ++f) inv_stage_b(XS, tb.inv, ZS.data(), k1, f);
   for (int n2 = 0; n2 < 17; ++n2)
-    for (int f = 0; f < FT; ++f) inv_stage_a(R.data(), FR, n2, f);
+    for (int f = 0; f < FT; ++f) inv_stage_a(ZS.data(), FR, n2, f);
 }
