@@ -140,6 +140,82 @@ WMK_HD void scatter15(float* base, const float (&v)[15]) {
     default: CALL(16); break;                                                                             \
   }
 
+// 15-point transforms by a second Good-Thomas split, 15 = 3 x 5: n1 = (5a + 3b) mod 15,
+// k1 = (10 ka + 6 kb) mod 15, again twiddle free: five 3-point DFTs, then one real and one complex
+// 5-point DFT (the ka = 2 column is the conjugate mirror of ka = 1).  ~75 flops instead of 119.
+constexpr float kC5_1 = 3.090169944e-01f, kC5_2 = -8.090169944e-01f;     // cos(2 pi/5), cos(4 pi/5)
+constexpr float kS5_1 = 9.510565163e-01f, kS5_2 = 5.877852523e-01f;      // sin(2 pi/5), sin(4 pi/5)
+constexpr float kS3 = 8.660254038e-01f;                                  // sin(2 pi/3)
+
+// real v[n1] -> X[k1], k1 = 0..7 (forward, e^-)
+WMK_HD void dft15_real(const float (&v)[15], float2 (&X)[8]) {
+  float u0[5];
+  float2 u1[5];
+#pragma unroll
+  for (int b = 0; b < 5; ++b) {
+    const float x0 = v[(3 * b) % 15], x1 = v[(5 + 3 * b) % 15], x2 = v[(10 + 3 * b) % 15];
+    const float t = x1 + x2;
+    u0[b] = x0 + t;
+    u1[b] = make_float2(fmaf(-0.5f, t, x0), kS3 * (x2 - x1));
+  }
+  {  // ka = 0: real 5-point DFT, kb = 0..2 -> k1 = 0, 6, 12 (= conj of 3)
+    const float e1 = u0[1] + u0[4], e2 = u0[2] + u0[3], o1 = u0[1] - u0[4], o2 = u0[2] - u0[3];
+    X[0] = make_float2(u0[0] + e1 + e2, 0.f);
+    X[6] = make_float2(fmaf(kC5_2, e2, fmaf(kC5_1, e1, u0[0])), -fmaf(kS5_2, o2, kS5_1 * o1));
+    X[3] = make_float2(fmaf(kC5_1, e2, fmaf(kC5_2, e1, u0[0])), fmaf(-kS5_1, o2, kS5_2 * o1));      // conj(U0[2])
+  }
+  {  // ka = 1: complex 5-point DFT, kb = 0..4 -> k1 = 10 (conj of 5), 1, 7, 13 (conj of 2), 4
+    const float2 e1 = make_float2(u1[1].x + u1[4].x, u1[1].y + u1[4].y), e2 = make_float2(u1[2].x + u1[3].x, u1[2].y + u1[3].y);
+    const float2 o1 = make_float2(u1[1].x - u1[4].x, u1[1].y - u1[4].y), o2 = make_float2(u1[2].x - u1[3].x, u1[2].y - u1[3].y);
+    X[5] = make_float2(u1[0].x + e1.x + e2.x, -(u1[0].y + e1.y + e2.y));                            // conj(U1[0])
+    const float2 a1 = make_float2(fmaf(kC5_2, e2.x, fmaf(kC5_1, e1.x, u1[0].x)), fmaf(kC5_2, e2.y, fmaf(kC5_1, e1.y, u1[0].y)));
+    const float2 a2 = make_float2(fmaf(kC5_1, e2.x, fmaf(kC5_2, e1.x, u1[0].x)), fmaf(kC5_1, e2.y, fmaf(kC5_2, e1.y, u1[0].y)));
+    const float2 b1 = make_float2(fmaf(kS5_2, o2.x, kS5_1 * o1.x), fmaf(kS5_2, o2.y, kS5_1 * o1.y));
+    const float2 b2 = make_float2(fmaf(-kS5_1, o2.x, kS5_2 * o1.x), fmaf(-kS5_1, o2.y, kS5_2 * o1.y));
+    X[1] = make_float2(a1.x + b1.y, a1.y - b1.x);                     // U1[1] = A1 - iB1
+    X[4] = make_float2(a1.x - b1.y, a1.y + b1.x);                     // U1[4] = A1 + iB1
+    X[7] = make_float2(a2.x + b2.y, a2.y - b2.x);                     // U1[2] = A2 - iB2
+    X[2] = make_float2(a2.x - b2.y, -(a2.y + b2.x));                  // conj(U1[3]) = conj(A2 + iB2)
+  }
+}
+
+// Hermitian z[k1] (k1 = 0..7, z[15-k] = conj z[k], Im z[0] ignored) -> real v[n1] = sum_k z[k] e^{+2 pi i n1 k/15} * scale
+WMK_HD void dft15_c2r(const float2 (&z)[8], float scale, float (&v)[15]) {
+  float u0[5];
+  float2 u1[5];
+  {  // ka = 0 column: U0[0] = z0, U0[1] = z6, U0[2] = conj z3  -> real 5-point inverse
+    const float x1 = z[6].x, y1 = z[6].y, x2 = z[3].x, y2 = -z[3].y;
+    u0[0] = fmaf(2.f, x1 + x2, z[0].x);
+    const float p1 = fmaf(2.f * kC5_2, x2, fmaf(2.f * kC5_1, x1, z[0].x)), q1 = fmaf(2.f * kS5_2, y2, 2.f * kS5_1 * y1);
+    const float p2 = fmaf(2.f * kC5_1, x2, fmaf(2.f * kC5_2, x1, z[0].x)), q2 = fmaf(-2.f * kS5_1, y2, 2.f * kS5_2 * y1);
+    u0[1] = p1 - q1; u0[4] = p1 + q1;
+    u0[2] = p2 - q2; u0[3] = p2 + q2;
+  }
+  {  // ka = 1 column: U1[0] = conj z5, U1[1] = z1, U1[2] = z7, U1[3] = conj z2, U1[4] = z4 -> complex 5-point inverse
+    const float2 w0 = make_float2(z[5].x, -z[5].y), w1 = z[1], w2 = z[7], w3 = make_float2(z[2].x, -z[2].y), w4 = z[4];
+    const float2 e1 = make_float2(w1.x + w4.x, w1.y + w4.y), e2 = make_float2(w2.x + w3.x, w2.y + w3.y);
+    const float2 o1 = make_float2(w1.x - w4.x, w1.y - w4.y), o2 = make_float2(w2.x - w3.x, w2.y - w3.y);
+    u1[0] = make_float2(w0.x + e1.x + e2.x, w0.y + e1.y + e2.y);
+    const float2 a1 = make_float2(fmaf(kC5_2, e2.x, fmaf(kC5_1, e1.x, w0.x)), fmaf(kC5_2, e2.y, fmaf(kC5_1, e1.y, w0.y)));
+    const float2 a2 = make_float2(fmaf(kC5_1, e2.x, fmaf(kC5_2, e1.x, w0.x)), fmaf(kC5_1, e2.y, fmaf(kC5_2, e1.y, w0.y)));
+    const float2 b1 = make_float2(fmaf(kS5_2, o2.x, kS5_1 * o1.x), fmaf(kS5_2, o2.y, kS5_1 * o1.y));
+    const float2 b2 = make_float2(fmaf(-kS5_1, o2.x, kS5_2 * o1.x), fmaf(-kS5_1, o2.y, kS5_2 * o1.y));
+    u1[1] = make_float2(a1.x - b1.y, a1.y + b1.x);                    // A1 + iB1
+    u1[4] = make_float2(a1.x + b1.y, a1.y - b1.x);                    // A1 - iB1
+    u1[2] = make_float2(a2.x - b2.y, a2.y + b2.x);
+    u1[3] = make_float2(a2.x + b2.y, a2.y - b2.x);
+  }
+  const float r3 = 2.f * kS3 * scale;
+#pragma unroll
+  for (int b = 0; b < 5; ++b) {       // 3-point inverse over ka: u0 + 2 Re(u1 e^{+2 pi i a/3})
+    const float base = u0[b] * scale;
+    const float t = fmaf(-scale, u1[b].x, base);
+    v[(3 * b) % 15] = fmaf(2.f * scale, u1[b].x, base);
+    v[(5 + 3 * b) % 15] = fmaf(-r3, u1[b].y, t);
+    v[(10 + 3 * b) % 15] = fmaf(r3, u1[b].y, t);
+  }
+}
+
 // ---- forward stage A: 15-point real DFT over n1 for one (frame f, residue n2) -> k1 = 0..7
 // samp: the tile's padded samples (frame f starts at samp[63 f]); SA[k1][n2][f].
 WMK_HD void fwd_stage_a(const float* samp, float2* SA, int n2, int f) {
@@ -147,23 +223,10 @@ WMK_HD void fwd_stage_a(const float* samp, float2* SA, int n2, int f) {
 #define WMK_CALL(N) gather15<N>(samp + HOP * f, v)
   WMK_DFT255_SWITCH17(n2, WMK_CALL)
 #undef WMK_CALL
-  float e[8], o[8];
+  float2 X[8];
+  dft15_real(v, X);
 #pragma unroll
-  for (int n = 1; n <= 7; ++n) { e[n] = v[n] + v[15 - n]; o[n] = v[n] - v[15 - n]; }
-  float s0 = v[0];
-#pragma unroll
-  for (int n = 1; n <= 7; ++n) s0 += e[n];
-  SA[(0 * 17 + n2) * FT + f] = make_float2(s0, 0.f);
-#pragma unroll
-  for (int k1 = 1; k1 <= 7; ++k1) {
-    float re = v[0], im = 0.f;
-#pragma unroll
-    for (int n = 1; n <= 7; ++n) {
-      re = fmaf(e[n], cos15((k1 * n) % 15), re);
-      im = fmaf(o[n], -sin15((k1 * n) % 15), im);
-    }
-    SA[(k1 * 17 + n2) * FT + f] = make_float2(re, im);
-  }
+  for (int k1 = 0; k1 < 8; ++k1) SA[(k1 * 17 + n2) * FT + f] = X[k1];
 }
 
 // ---- forward stage B: the 17-point DFT over n2 for (k1, frame f); store(bin, re, im) receives each
@@ -195,30 +258,11 @@ WMK_HD void inv_stage_b(const float* XS, const InvEntry* inv_tab, float2* ZS, in
 // ---- inverse stage A': complex-to-real inverse 15-point DFT over k1 for (n2, frame f); writes the
 // 15 time samples n = (17 n1 + 15 n2) mod 255 of frame f (already divided by 255) to FR[f][n].
 WMK_HD void inv_stage_a(const float2* ZS, float* FR, int n2, int f) {
-  float zr[8], zi[8];
+  float2 z[8];
 #pragma unroll
-  for (int k1 = 0; k1 < 8; ++k1) {
-    const float2 z = ZS[(k1 * 17 + n2) * FT + f];
-    zr[k1] = z.x;
-    zi[k1] = z.y;
-  }
-  constexpr float s1 = 1.0f / 255.0f, s2 = 2.0f / 255.0f;
+  for (int k1 = 0; k1 < 8; ++k1) z[k1] = ZS[(k1 * 17 + n2) * FT + f];
   float v[15];
-  float p0 = zr[0] * s1;
-#pragma unroll
-  for (int k = 1; k <= 7; ++k) p0 = fmaf(zr[k], s2, p0);
-  v[0] = p0;
-#pragma unroll
-  for (int n1 = 1; n1 <= 7; ++n1) {
-    float P = zr[0] * s1, Q = 0.f;
-#pragma unroll
-    for (int k = 1; k <= 7; ++k) {
-      P = fmaf(zr[k], s2 * cos15((k * n1) % 15), P);
-      Q = fmaf(zi[k], s2 * sin15((k * n1) % 15), Q);
-    }
-    v[n1] = P - Q;
-    v[15 - n1] = P + Q;
-  }
+  dft15_c2r(z, 1.0f / 255.0f, v);
 #define WMK_CALL(N) scatter15<N>(FR + f * NFFT, v)
   WMK_DFT255_SWITCH17(n2, WMK_CALL)
 #undef WMK_CALL
