@@ -1,0 +1,155 @@
+// LeFF depthwise 3x3 convolution (pad 1) + GELU on the bf16 hidden tensor [B][H][W][Ch]
+// (uformerWM/model.py:688-689,706), HBM-bound formulation for sm_100a:
+//   * persistent CTAs (4 per SM) walk (channel slab of 64, spatial tile of TH x 8 pixels) items;
+//   * the (TH+2) x 10 x 64-channel input patch of the NEXT item is fetched by one TMA
+//     cp.async.bulk.tensor.4d while the current one is convolved (2-stage mbarrier pipeline); the
+//     conv's zero padding is the tensor map's out-of-bounds fill, so there is no border code;
+//   * a thread owns 4 channels of one tile column and slides a 3x3 register window down the
+//     rows: 3 conflict-free 8-byte shared loads, 18 packed FFMA2 and 2 packed GELUs per 4 outputs.
+// Algorithmic traffic: 4 B per element (bf16 in + out); the 1.4x patch halo is served by L2.
+#include "tc_ptx.cuh"
+
+namespace wmk {
+
+namespace {
+
+using namespace tc;
+
+constexpr int DW_TW = 8, DW_PW = DW_TW + 2;
+constexpr int kDwThreads = 128;
+
+__device__ __forceinline__ float2 bf2f(uint32_t u) {
+  return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+}
+
+struct DwGeom {
+  int H, Ch, ncs, tiles_w, tiles_h, n_items;
+};
+
+template <int TH>
+__global__ void __launch_bounds__(kDwThreads, 4)
+dwconv3x3_gelu_tma_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict__ out,
+                          const float* __restrict__ wt, const float* __restrict__ bias, DwGeom g) {
+  constexpr int PH = TH + 2;
+  constexpr uint32_t kPatchBytes = PH * DW_PW * 128;
+  __shared__ __align__(128) uint8_t patch[2][kPatchBytes];
+  __shared__ __align__(8) uint64_t bar[2];
+  const int tid = threadIdx.x;
+  const int cg = tid & 15, col = tid >> 4;
+
+  auto decode = [&](int item, int& slab, int& b, int& h0, int& w0) {
+    slab = item % g.ncs;
+    const int sp = item / g.ncs;
+    const int per = g.tiles_w * g.tiles_h;
+    b = sp / per;
+    const int rem = sp - b * per;
+    const int th = rem / g.tiles_w;
+    h0 = th * TH;
+    w0 = (rem - th * g.tiles_w) * DW_TW;
+  };
+  auto issue = [&](int item, int stage) {
+    int slab, b, h0, w0;
+    decode(item, slab, b, h0, w0);
+    mbar_arrive_expect_tx(smem_u32(&bar[stage]), kPatchBytes);
+    tma_load_4d(smem_u32(patch[stage]), &tm, slab * 64, w0 - 1, h0 - 1, b, smem_u32(&bar[stage]));
+  };
+
+  if (tid == 0) {
+    mbar_init(smem_u32(&bar[0]), 1);
+    mbar_init(smem_u32(&bar[1]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  int item = blockIdx.x;
+  if (item >= g.n_items) return;
+  if (tid == 0) issue(item, 0);
+
+  for (int it = 0; item < g.n_items; item += gridDim.x, ++it) {
+    const int stage = it & 1;
+    const int next = item + gridDim.x;
+    if (tid == 0 && next < g.n_items) issue(next, stage ^ 1);   // that buffer was drained before the last barrier
+
+    int slab, b, h0, w0;
+    decode(item, slab, b, h0, w0);
+    const int c = slab * 64 + cg * 4;
+    float2 wreg[9][2], bz[2];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(wt + (size_t)t * g.Ch + c));
+      wreg[t][0] = make_float2(a.x, a.y);
+      wreg[t][1] = make_float2(a.z, a.w);
+    }
+    {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(bias + c));
+      bz[0] = make_float2(a.x, a.y);
+      bz[1] = make_float2(a.z, a.w);
+    }
+    mbar_wait(smem_u32(&bar[stage]), (it >> 1) & 1);
+
+    // patch[r][x][64 ch] bf16; this thread reads columns col..col+2, channels 4 cg..4 cg+3
+    const uint8_t* pb = patch[stage] + col * 128 + cg * 8;
+    float2 win[3][3][2];
+    auto load_row = [&](int r, float2 (&dst)[3][2]) {
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const uint2 u = *reinterpret_cast<const uint2*>(pb + (r * DW_PW + dx) * 128);
+        dst[dx][0] = bf2f(u.x);
+        dst[dx][1] = bf2f(u.y);
+      }
+    };
+    load_row(0, win[0]);
+    load_row(1, win[1]);
+    __nv_bfloat16* op = out + (((size_t)b * g.H + h0) * g.H + w0 + col) * g.Ch + c;
+#pragma unroll
+    for (int r = 0; r < TH; ++r) {
+      load_row(r + 2, win[(r + 2) % 3]);
+      float2 a0 = bz[0], a1 = bz[1];
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          a0 = __ffma2_rn(win[(r + dy) % 3][dx][0], wreg[dy * 3 + dx][0], a0);
+          a1 = __ffma2_rn(win[(r + dy) % 3][dx][1], wreg[dy * 3 + dx][1], a1);
+        }
+      a0 = gelu_tanh2(a0);
+      a1 = gelu_tanh2(a1);
+      uint2 o;
+      o.x = pack_bf16x2(a0.x, a0.y);
+      o.y = pack_bf16x2(a1.x, a1.y);
+      *reinterpret_cast<uint2*>(op + (size_t)r * g.H * g.Ch) = o;
+    }
+    __syncthreads();                                // everyone has drained this stage's patch
+  }
+}
+
+template <int TH>
+int launch_dw(const __nv_bfloat16* in, __nv_bfloat16* out, const float* wt, const float* bias, int B, int H, int Ch,
+              cudaStream_t st) {
+  CUtensorMap tm;
+  const uint64_t dims[4] = {(uint64_t)Ch, (uint64_t)H, (uint64_t)H, (uint64_t)B};
+  const uint64_t strides[3] = {(uint64_t)Ch * 2, (uint64_t)H * Ch * 2, (uint64_t)H * H * Ch * 2};
+  const uint32_t box[4] = {64, DW_PW, TH + 2, 1};
+  WMK_TRY(make_tensor_map(&tm, in, 4, dims, strides, box, false, 0));
+  DwGeom g;
+  g.H = H; g.Ch = Ch; g.ncs = Ch / 64; g.tiles_w = H / DW_TW; g.tiles_h = H / TH;
+  const long long items = (long long)B * g.tiles_w * g.tiles_h * g.ncs;
+  WMK_REQUIRE(items < (1LL << 31), "dwconv: too many tiles (%lld)", items);
+  g.n_items = (int)items;
+  const int grid = (int)(items < 4LL * num_sms() ? items : 4LL * num_sms());
+  dwconv3x3_gelu_tma_kernel<TH><<<grid, kDwThreads, 0, st>>>(tm, out, wt, bias, g);
+  WMK_CHECK_LAUNCH("dwconv3x3_gelu_tma_kernel");
+  return 0;
+}
+
+}  // namespace
+
+// in / out: [B][H][H][Ch] bf16 (token layout), wt: [9][Ch] fp32 tap-major, bias: [Ch] fp32.
+int dwconv3x3_gelu_bf16(const __nv_bfloat16* in, __nv_bfloat16* out, const float* wt, const float* bias, int B, int H,
+                        int Ch, cudaStream_t st) {
+  WMK_REQUIRE(H % 8 == 0 && Ch % 64 == 0, "dwconv: H=%d must be a multiple of 8 and Ch=%d of 64", H, Ch);
+  WMK_REQUIRE(((uintptr_t)in & 15) == 0 && ((uintptr_t)out & 15) == 0, "dwconv: buffers must be 16-byte aligned");
+  if (H % 16 == 0) return launch_dw<16>(in, out, wt, bias, B, H, Ch, st);
+  return launch_dw<8>(in, out, wt, bias, B, H, Ch, st);
+}
+
+}  // namespace wmk

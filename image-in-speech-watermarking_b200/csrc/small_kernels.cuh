@@ -7,15 +7,13 @@
 namespace wmk {
 
 // InputProj (uformerWM/model.py:813-816,824-826): Conv2d(2,32,3,p=1) + LeakyReLU(0.01),
-// NCHW [B][2][128][128] in -> token layout [B*16384][32] out.  One thread per pixel.
+// NCHW [B][2][128][128] in -> token layout [B*16384][32] out.  One thread per pixel; the 576 weights
+// travel as a kernel parameter, i.e. in the constant bank, so every FMA takes its weight as an
+// immediate-like c[][] operand (no shared-memory traffic).
+struct InProjW { float w[32 * 18]; float b[32]; };
+
 __global__ void __launch_bounds__(128)
-input_proj_kernel(const float* __restrict__ x, float* __restrict__ out, const float* __restrict__ w,
-                  const float* __restrict__ bias, int B) {
-  __shared__ float ws[32 * 18];
-  __shared__ float bs[32];
-  for (int i = threadIdx.x; i < 576; i += blockDim.x) ws[i] = w[i];
-  if (threadIdx.x < 32) bs[threadIdx.x] = bias[threadIdx.x];
-  __syncthreads();
+input_proj_kernel(const float* __restrict__ x, float* __restrict__ out, const __grid_constant__ InProjW W, int B) {
   const size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (pix >= (size_t)B * 16384) return;
   const int wq = (int)(pix & 127), h = (int)((pix >> 7) & 127);
@@ -38,9 +36,9 @@ input_proj_kernel(const float* __restrict__ x, float* __restrict__ out, const fl
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int co = g * 4 + j;
-      float a = bs[co];
+      float a = W.b[co];
 #pragma unroll
-      for (int t = 0; t < 18; ++t) a = fmaf(in[t], ws[co * 18 + t], a);
+      for (int t = 0; t < 18; ++t) a = fmaf(in[t], W.w[co * 18 + t], a);
       r[j] = a > 0.f ? a : 0.01f * a;
     }
     o[g] = make_float4(r[0], r[1], r[2], r[3]);
@@ -48,43 +46,78 @@ input_proj_kernel(const float* __restrict__ x, float* __restrict__ out, const fl
 }
 
 // OutputProj (uformerWM/model.py:845-847,857-862) Conv2d(64,2,3,p=1) on the token-layout decoder
-// output + the residual y = x + noise (model.py:2419-2421).  One warp per pixel.
-__global__ void __launch_bounds__(256)
+// output + the residual y = x + noise (model.py:2419-2421).
+// One CTA = an 8 x 32 pixel tile.  Phase 1: one thread per pixel of the 10 x 34 halo tile turns its 64
+// channels into the 18 per-tap partial sums P[pixel][(dy,dx),o] = sum_c W[o][c][dy][dx] in[pixel][c] (each
+// token row is read once per tile, 1.33x halo served by L2).  Phase 2: every output pixel gathers
+// its 9 taps from shared memory; NCHW stores are coalesced along w.
+constexpr int OP_TH = 8, OP_TW = 32, OP_PH = OP_TH + 2, OP_PW = OP_TW + 2, OP_NPIX = OP_PH * OP_PW;
+constexpr int OP_THREADS = 352;      // >= OP_NPIX (340)
+__global__ void __launch_bounds__(OP_THREADS)
 output_proj_kernel(const float* __restrict__ tokens, const float* __restrict__ x, float* __restrict__ noise,
                    float* __restrict__ y, const float* __restrict__ w, const float* __restrict__ bias, int B) {
-  __shared__ float ws[9 * 2 * 64];          // [tap][o][c]
-  for (int i = threadIdx.x; i < 1152; i += blockDim.x) {
-    const int tap = i / 128, o = (i / 64) & 1, c = i & 63;
-    ws[i] = w[(o * 64 + c) * 9 + tap];
+  __shared__ __align__(16) float ws[64 * 20];       // [c][(tap,o) padded to 20]
+  __shared__ float Ps[OP_NPIX * 19];                // [pixel][18 padded to 19]
+  for (int i = threadIdx.x; i < 64 * 20; i += blockDim.x) {
+    const int c = i / 20, k = i - c * 20;
+    ws[i] = k < 18 ? w[((k & 1) * 64 + c) * 9 + (k >> 1)] : 0.f;      // k = tap*2 + o
+  }
+  const int tiles_w = 128 / OP_TW, tiles_h = 128 / OP_TH;
+  const int tile = blockIdx.x;
+  const int b = tile / (tiles_w * tiles_h);
+  const int trem = tile - b * tiles_w * tiles_h;
+  const int h0 = (trem / tiles_w) * OP_TH, w0 = (trem % tiles_w) * OP_TW;
+  __syncthreads();
+  if (threadIdx.x < OP_NPIX) {
+    const int pr = threadIdx.x / OP_PW, pc = threadIdx.x - pr * OP_PW;
+    const int hh = h0 + pr - 1, wwp = w0 + pc - 1;
+    float acc[18];
+#pragma unroll
+    for (int k = 0; k < 18; ++k) acc[k] = 0.f;
+    if (hh >= 0 && hh < 128 && wwp >= 0 && wwp < 128) {
+      const float4* src = reinterpret_cast<const float4*>(tokens + (((size_t)b * 128 + hh) * 128 + wwp) * 64);
+      float4 v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = src[j];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float vv[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float4* wr = reinterpret_cast<const float4*>(ws + (j * 4 + e) * 20);
+#pragma unroll
+          for (int q = 0; q < 5; ++q) {
+            const float4 w4 = wr[q];
+            acc[q * 4] = fmaf(vv[e], w4.x, acc[q * 4]);
+            acc[q * 4 + 1] = fmaf(vv[e], w4.y, acc[q * 4 + 1]);
+            if (q < 4) {
+              acc[q * 4 + 2] = fmaf(vv[e], w4.z, acc[q * 4 + 2]);
+              acc[q * 4 + 3] = fmaf(vv[e], w4.w, acc[q * 4 + 3]);
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 18; ++k) Ps[threadIdx.x * 19 + k] = acc[k];
   }
   __syncthreads();
-  const size_t pix = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (pix >= (size_t)B * 16384) return;
-  const int wq = (int)(pix & 127), h = (int)((pix >> 7) & 127);
-  const size_t b = pix >> 14;
-  float a0 = 0.f, a1 = 0.f;
+  if (threadIdx.x < OP_TH * OP_TW) {
+    const int r = threadIdx.x / OP_TW, c = threadIdx.x - r * OP_TW;
+    float a0 = bias[0], a1 = bias[1];
 #pragma unroll
-  for (int dy = 0; dy < 3; ++dy) {
-    const int hh = h + dy - 1;
-    if (hh < 0 || hh >= 128) continue;
+    for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
-    for (int dx = 0; dx < 3; ++dx) {
-      const int wwp = wq + dx - 1;
-      if (wwp < 0 || wwp >= 128) continue;
-      const float2 v = *reinterpret_cast<const float2*>(tokens + ((b * 128 + hh) * 128 + wwp) * 64 + 2 * lane);
-      const float* wt = ws + (dy * 3 + dx) * 128 + 2 * lane;
-      a0 = fmaf(v.x, wt[0], fmaf(v.y, wt[1], a0));
-      a1 = fmaf(v.x, wt[64], fmaf(v.y, wt[65], a1));
-    }
-  }
-  a0 = warp_sum(a0);
-  a1 = warp_sum(a1);
-  if (lane < 2) {
-    const float n = (lane == 0 ? a0 : a1) + bias[lane];
-    const size_t o = ((b * 2 + lane) * 128 + h) * 128 + wq;
-    if (noise) noise[o] = n;
-    y[o] = x[o] + n;
+      for (int dx = 0; dx < 3; ++dx) {
+        const float* pp = Ps + ((r + dy) * OP_PW + c + dx) * 19 + (dy * 3 + dx) * 2;
+        a0 += pp[0];
+        a1 += pp[1];
+      }
+    const size_t o0 = (((size_t)b * 2 + 0) * 128 + h0 + r) * 128 + w0 + c;
+    const size_t o1 = o0 + 16384;
+    if (noise) { noise[o0] = a0; noise[o1] = a1; }
+    y[o0] = x[o0] + a0;
+    y[o1] = x[o1] + a1;
   }
 }
 

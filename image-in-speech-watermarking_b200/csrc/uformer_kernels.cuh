@@ -245,17 +245,15 @@ constexpr int ATT_LD = 40;     // bf16 elements per smem row (80 B): conflict-fr
 constexpr int ATT_TILE = 64 * ATT_LD;   // one 64 x 32 operand tile
 
 struct AttGeom {
-  int C, H, shift, heads, nws;
+  int C, H, shift, lg_heads, lg_nws;      // heads = C/32 and windows per side = H/8 are powers of two
 };
 // token index and shift-mask region of row r (0..63) of window `win`
 __device__ __forceinline__ void att_row(const AttGeom& g, int win, int r, int& token, int& region) {
-  const int b = win / (g.nws * g.nws);
-  const int wrem = win - b * g.nws * g.nws;
-  const int wh = wrem / g.nws, ww = wrem - wh * g.nws;
+  const int b = win >> (2 * g.lg_nws);
+  const int wrem = win & ((1 << (2 * g.lg_nws)) - 1);
+  const int wh = wrem >> g.lg_nws, ww = wrem & ((1 << g.lg_nws) - 1);
   const int hs = wh * 8 + (r >> 3), ws = ww * 8 + (r & 7);
-  int h = hs + g.shift, w = ws + g.shift;
-  if (h >= g.H) h -= g.H;
-  if (w >= g.H) w -= g.H;
+  const int h = (hs + g.shift) & (g.H - 1), w = (ws + g.shift) & (g.H - 1);
   token = (b * g.H + h) * g.H + w;
   const int rh = hs < g.H - 8 ? 0 : (hs < g.H - g.shift ? 1 : 2);
   const int rw = ws < g.H - 8 ? 0 : (ws < g.H - g.shift ? 1 : 2);
@@ -264,16 +262,25 @@ __device__ __forceinline__ void att_row(const AttGeom& g, int win, int r, int& t
 
 // Persistent: each CTA loops over (window, head) items (heads fastest) and prefetches the next
 // item's q/k/v tiles with cp.async while the tensor cores work on the current one.
+// Scores arrive in the log2 domain: the packed q rows and the bias table carry a factor log2(e)
+// (uformer_plan.cu pack_block), so softmax is exp2(s - max) with one FADD + one MUFU.EX2 per score.
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+constexpr float kLog2e = 1.4426950408889634f;
 static __global__ void __launch_bounds__(128)
 window_attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
                             const float* __restrict__ bias, int C, int H, int shift, int n_items) {
   __shared__ __align__(16) __nv_bfloat16 sbuf[2][3 * ATT_TILE];
   __shared__ int s_tok[2][64], s_rid[2][64];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  AttGeom g{C, H, shift, C >> 5, H >> 3};
+  AttGeom g{C, H, shift, 31 - __clz(C >> 5), 31 - __clz(H >> 3)};
+  const int head_mask = (C >> 5) - 1;
 
   auto prefetch = [&](int item, int buf) {
-    const int head = item % g.heads, win = item / g.heads;
+    const int head = item & head_mask, win = item >> g.lg_heads;
     if (tid < 64) {
       int t, r;
       att_row(g, win, tid, t, r);
@@ -309,7 +316,7 @@ window_attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16
       asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
-    const int head = item % g.heads;
+    const int head = item & head_mask;
     __nv_bfloat16* Qs = &sbuf[buf][0];
     const int* tok = s_tok[buf];
     const int* rid = s_rid[buf];
@@ -345,10 +352,10 @@ window_attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16
       sacc[n][0] += b0.x; sacc[n][1] += b0.y; sacc[n][2] += b1.x; sacc[n][3] += b1.y;
       if (shift > 0) {
         const int c0 = rid[col], c1 = rid[col + 1];
-        if (c0 != rid0) sacc[n][0] -= 100.0f;
-        if (c1 != rid0) sacc[n][1] -= 100.0f;
-        if (c0 != rid1) sacc[n][2] -= 100.0f;
-        if (c1 != rid1) sacc[n][3] -= 100.0f;
+        if (c0 != rid0) sacc[n][0] -= 100.0f * kLog2e;
+        if (c1 != rid0) sacc[n][1] -= 100.0f * kLog2e;
+        if (c0 != rid1) sacc[n][2] -= 100.0f * kLog2e;
+        if (c1 != rid1) sacc[n][3] -= 100.0f * kLog2e;
       }
       m0 = fmaxf(m0, fmaxf(sacc[n][0], sacc[n][1]));
       m1 = fmaxf(m1, fmaxf(sacc[n][2], sacc[n][3]));
@@ -358,8 +365,8 @@ window_attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16
     float s0 = 0.f, s1 = 0.f;
 #pragma unroll
     for (int n = 0; n < 8; ++n) {
-      sacc[n][0] = __expf(sacc[n][0] - m0); sacc[n][1] = __expf(sacc[n][1] - m0);
-      sacc[n][2] = __expf(sacc[n][2] - m1); sacc[n][3] = __expf(sacc[n][3] - m1);
+      sacc[n][0] = ex2_approx(sacc[n][0] - m0); sacc[n][1] = ex2_approx(sacc[n][1] - m0);
+      sacc[n][2] = ex2_approx(sacc[n][2] - m1); sacc[n][3] = ex2_approx(sacc[n][3] - m1);
       s0 += sacc[n][0] + sacc[n][1];
       s1 += sacc[n][2] + sacc[n][3];
     }

@@ -18,6 +18,8 @@ namespace wmk {
 
 int stft_clips(const float* wave, int B, int L, float* clips, int n_clips, cudaStream_t st);
 int istft_clips(const float* clips, int B, int n_clips, int T, float* wave, int length, cudaStream_t st);
+int dwconv3x3_gelu_bf16(const __nv_bfloat16* in, __nv_bfloat16* out, const float* wt, const float* bias, int B, int H,
+                        int Ch, cudaStream_t st);
 
 namespace {
 
@@ -38,7 +40,7 @@ struct BlockW {
 };
 
 struct EncW {
-  float *in_w = nullptr, *in_b = nullptr;
+  InProjW in_proj;                // travels as a kernel parameter (constant bank)
   std::vector<BlockW> stage[5];
   void* down_w[4] = {};
   float* down_b[4] = {};
@@ -134,19 +136,22 @@ int pack_block(wmk_plan* P, const std::string& p, int C, int heads, int H, int s
   if (mod) WMK_TRY(get_f32(P, p + "modulator.weight", 64 * (size_t)C, &w->mod));
   const HostTensor *tab, *wq, *bq, *wkv, *bkv, *dw;
   WMK_TRY(get(P, p + "attn.relative_position_bias_table", 225 * (size_t)heads, &tab));
+  // bf16 mode: the tensor-core attention kernel works in the log2 domain (softmax by exp2), so
+  // log2(e) is folded into the bias table and the q rows; fp32 mode keeps natural-log scores.
+  const float lg = P->precision == WMK_PREC_BF16 ? 1.4426950408889634f : 1.0f;
   std::vector<float> bias((size_t)heads * 4096);
   for (int h = 0; h < heads; ++h)
     for (int i = 0; i < 64; ++i)
       for (int j = 0; j < 64; ++j) {
         const int idx = ((i >> 3) - (j >> 3) + 7) * 15 + ((i & 7) - (j & 7) + 7);      // model.py:496-505
-        bias[((size_t)h * 64 + i) * 64 + j] = tab->data[(size_t)idx * heads + h];
+        bias[((size_t)h * 64 + i) * 64 + j] = tab->data[(size_t)idx * heads + h] * lg;
       }
   WMK_TRY(upload_f32(P, bias, &w->attn_bias));
   WMK_TRY(get(P, p + "attn.qkv.to_q.weight", (size_t)C * C, &wq));
   WMK_TRY(get(P, p + "attn.qkv.to_q.bias", C, &bq));
   WMK_TRY(get(P, p + "attn.qkv.to_kv.weight", 2 * (size_t)C * C, &wkv));
   WMK_TRY(get(P, p + "attn.qkv.to_kv.bias", 2 * (size_t)C, &bkv));
-  const float scale = 1.0f / sqrtf((float)(C / heads));              // model.py:489,526
+  const float scale = lg / sqrtf((float)(C / heads));                // model.py:489,526
   std::vector<float> wqkv(3 * (size_t)C * C), bqkv(3 * (size_t)C);
   for (size_t i = 0; i < (size_t)C * C; ++i) wqkv[i] = wq->data[i] * scale;
   for (size_t i = 0; i < 2 * (size_t)C * C; ++i) wqkv[(size_t)C * C + i] = wkv->data[i];
@@ -174,8 +179,13 @@ int pack_block(wmk_plan* P, const std::string& p, int C, int heads, int H, int s
 }
 
 int pack_encoder(wmk_plan* P, const std::string& p, const std::string& inproj, EncW* e) {
-  WMK_TRY(get_f32(P, inproj + "proj.0.weight", 32 * 2 * 9, &e->in_w));
-  WMK_TRY(get_f32(P, inproj + "proj.0.bias", 32, &e->in_b));
+  {
+    const HostTensor *tw, *tb;
+    WMK_TRY(get(P, inproj + "proj.0.weight", 32 * 2 * 9, &tw));
+    WMK_TRY(get(P, inproj + "proj.0.bias", 32, &tb));
+    for (int i = 0; i < 576; ++i) e->in_proj.w[i] = tw->data[i];
+    for (int i = 0; i < 32; ++i) e->in_proj.b[i] = tb->data[i];
+  }
   for (int s = 0; s < 5; ++s) {
     const int C = 32 << s, H = 128 >> s;
     e->stage[s].resize(kDepths[s]);
@@ -296,11 +306,12 @@ int run_block(wmk_plan* P, const BlockW& w, float* x, int n, cudaStream_t st) {
     const size_t total = (size_t)M * C;     // (4C / 4) channel groups per pixel
     ProfScope prof(FAM_DWCONV, 8.0 * M * C * sizeof(OpT), st);
     (void)total;
-    if constexpr (sizeof(OpT) == 2)
-      dwconv3x3_gelu_bf16_kernel<<<n * (H / 8) * (H / 8) * ((4 * C) / 64), 128, 0, st>>>(H1, H2, w.dw_w, w.dw_b, n, H, 4 * C);
-    else
+    if constexpr (sizeof(OpT) == 2) {
+      WMK_TRY(dwconv3x3_gelu_bf16(H1, H2, w.dw_w, w.dw_b, n, H, 4 * C, st));
+    } else {
       dwconv3x3_gelu_kernel<OpT><<<n * (H / 8) * (H / 8) * ((4 * C) / 64), 128, 0, st>>>(H1, H2, w.dw_w, w.dw_b, n, H, 4 * C);
-    WMK_CHECK_LAUNCH("dwconv3x3_gelu_kernel");
+      WMK_CHECK_LAUNCH("dwconv3x3_gelu_kernel");
+    }
   }
   g = GemmArgs();
   g.A = H2; g.W = w.w_l2; g.bias = w.b_l2; g.resid = x; g.C = x; g.M = M; g.N = C; g.K = 4 * C; g.ldc = C;
@@ -314,7 +325,7 @@ template <typename OpT>
 int run_encoder(wmk_plan* P, const EncW& e, const float* x_nchw, int n, const char* tag, cudaStream_t st) {
   {
     ProfScope prof(FAM_SMALL, (double)n * 16384 * (8 + 128), st);
-    input_proj_kernel<<<cdiv((size_t)n * 16384, 128), 128, 0, st>>>(x_nchw, P->E[0], e.in_w, e.in_b, n);
+    input_proj_kernel<<<cdiv((size_t)n * 16384, 128), 128, 0, st>>>(x_nchw, P->E[0], e.in_proj, n);
     WMK_CHECK_LAUNCH("input_proj_kernel");
   }
   const std::string t(tag);
@@ -395,7 +406,7 @@ int run_forward(wmk_plan* P, const float* x, const float* msg, int msg_stride, i
   float* y = y_out ? y_out : P->ybuf;
   {
     ProfScope prof(FAM_SMALL, (double)n * 16384 * (256 + 24), st);
-    output_proj_kernel<<<cdiv((size_t)n * 16384 * 32, 256), 256, 0, st>>>(P->D[3], x, noise, y, P->out_w, P->out_b, n);
+    output_proj_kernel<<<n * (128 / OP_TH) * (128 / OP_TW), OP_THREADS, 0, st>>>(P->D[3], x, noise, y, P->out_w, P->out_b, n);
     WMK_CHECK_LAUNCH("output_proj_kernel");
   }
   if (stft_new) {
