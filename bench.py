@@ -176,7 +176,7 @@ def run_ours(args):
     import torch.distributed as dist
     from image_in_speech_watermarking_b200 import _lib, synthetic as SY
     from image_in_speech_watermarking_b200.model import UformerAudio
-    from image_in_speech_watermarking_b200 import audio_test as PT
+    from image_in_speech_watermarking_b200 import audio_test as PT, sharding as SH
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -200,13 +200,8 @@ def run_ours(args):
 
     def step(w, m):
         r = PT.embed_attack_extract(w, m, model, ATTACK, seed=1, want_outputs=False)
-        s = r["stats"]
-        vec = torch.stack([s[:, 4].sum(), torch.tensor(1024.0 * B, device=dev, dtype=torch.float64), s[:, 5].sum(),
-                           s[:, 6].sum(), s[:, 0].sum(), s[:, 1].sum(), s[:, 3].sum(),
-                           torch.tensor(float(B), device=dev, dtype=torch.float64)])
-        if world > 1:
-            dist.all_reduce(vec)           # the path's only collective: BER / SNR statistics (NCCL)
-        return vec
+        # the path's only collective: one all-reduce of the BER / SNR statistics vector (NCCL)
+        return SH.allreduce_stats(SH.stats_vector(r["stats"]))
 
     def sync():
         torch.cuda.synchronize()

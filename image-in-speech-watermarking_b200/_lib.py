@@ -39,6 +39,9 @@ SIGNATURES = {
     "wmk_noise_crop_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "wmk_noise_resize_nearest_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _f, _vp]),
     "wmk_noise_quantize_f32": (_i, [_vp, _vp, _sz, _vp]),
+    "wmk_noise_jpeg_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "wmk_magphase_split_f32": (_i, [_vp, _vp, _vp, _sz, _sz, _vp]),
+    "wmk_magphase_merge_f32": (_i, [_vp, _vp, _vp, _sz, _sz, _vp]),
     "wmk_uformer_plan_create": (_i, [_i, ctypes.POINTER(_vp)]),
     "wmk_plan_destroy": (_i, [_vp]),
     "wmk_plan_set_tensor": (_i, [_vp, ctypes.c_char_p, _vp, ctypes.POINTER(ctypes.c_int64), _i]),

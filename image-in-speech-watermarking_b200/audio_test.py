@@ -25,8 +25,40 @@ def prepare_data(soundwave, audio_scale='0'):
     return [(soundwave, 16000), [clips[:, j] for j in range(clips.shape[1])], T % 128]
 
 
+def tile_image(images, tile=32):
+    """(B,1,H,W) with H, W multiples of 32 -> (B, K, 1, 32, 32) row-major 32x32 tiles (K = 4 for 64x64).
+    The reference hard-codes 32x32 messages (`uformerWM/model.py:2388-2404`); BASELINE config 4's 64x64
+    greyscale image is carried as four tiles, tile t in every clip whose index is t (mod 4)."""
+    B, _, H, W = images.shape
+    if H % tile or W % tile:
+        raise ValueError("image size %dx%d is not a multiple of %d" % (H, W, tile))
+    t = images.reshape(B, 1, H // tile, tile, W // tile, tile).permute(0, 2, 4, 1, 3, 5)
+    return t.reshape(B, (H // tile) * (W // tile), 1, tile, tile).contiguous()
+
+
+def untile_image(tiles, H, W, tile=32):
+    """Inverse of `tile_image`: (B, K, 1, 32, 32) -> (B, 1, H, W)."""
+    B = tiles.shape[0]
+    t = tiles.reshape(B, H // tile, W // tile, 1, tile, tile).permute(0, 3, 1, 4, 2, 5)
+    return t.reshape(B, 1, H, W).contiguous()
+
+
+def recover_tiled(wm_clips, K):
+    """(B, n_clips, 1, 32, 32) per-clip sigmoid outputs -> (B, K, 1, 32, 32): the mean over the clips
+    that carried each tile (clip j carries tile j mod K); needs n_clips >= K."""
+    B, n = wm_clips.shape[:2]
+    if n < K:
+        raise ValueError("%d clips cannot carry %d tiles" % (n, K))
+    idx = torch.arange(n, device=wm_clips.device) % K
+    out = torch.zeros((B, K, 1, 32, 32), device=wm_clips.device, dtype=wm_clips.dtype)
+    out.index_add_(1, idx, wm_clips)
+    cnt = torch.bincount(idx, minlength=K).to(wm_clips.dtype)
+    return out / cnt.view(1, K, 1, 1, 1)
+
+
 def embed_attack_extract(waves, messages, model, attack="closed_loop", draws=None, seed=0, want_outputs=True):
-    """Batched hot path.  waves (B, L) CUDA fp32; messages (B or 1, 1, 32, 32) CUDA.
+    """Batched hot path.  waves (B, L) CUDA fp32; messages (B or 1, 1, 32, 32) CUDA, or
+    (B, K, 1, 32, 32) tiles (see `tile_image`): clip j of an utterance then carries tile j mod K.
     Returns a dict of device tensors:
       recon (B,L) watermarked audio, att (B,L) attacked audio, wm (B,nc,1,32,32) clean extraction,
       wm_att (B,nc_att,1,32,32), logits / logits_att, stats: per-utterance float64 columns
@@ -37,10 +69,24 @@ def embed_attack_extract(waves, messages, model, attack="closed_loop", draws=Non
     T = FE.num_frames(L)
     nc = T // 128 + 1                                          # quirk B-6
     clips = FE.stft_clips(waves, nc)                           # (B,nc,2,128,128)
-    msg = messages.float().reshape(-1, 1, 32, 32)
-    msg_b = msg if msg.shape[0] == B else msg.expand(B, 1, 32, 32)
-    msg_clips = msg_b[:, None].expand(B, nc, 1, 32, 32).reshape(B * nc, 1, 32, 32).contiguous()
-    o = model.run(clips.reshape(B * nc, 2, 128, 128), msg_clips if msg.shape[0] == B else msg,
+    tiled = messages.dim() == 5
+    if tiled:
+        tiles = messages.float()
+        K = tiles.shape[1]
+
+        def msg_for(n):                                        # (B, n, 1, 32, 32): tile j mod K in clip j
+            return tiles[:, torch.arange(n, device=tiles.device) % K]
+        msg = None
+        msg_b = msg_for(nc)[:, -1]                             # what the last clip carries (quirk B-8)
+        msg_clips = msg_for(nc).reshape(B * nc, 1, 32, 32).contiguous()
+    else:
+        msg = messages.float().reshape(-1, 1, 32, 32)
+        msg_b = msg if msg.shape[0] == B else msg.expand(B, 1, 32, 32)
+
+        def msg_for(n):
+            return msg_b[:, None].expand(B, n, 1, 32, 32)
+        msg_clips = msg_for(nc).reshape(B * nc, 1, 32, 32).contiguous()
+    o = model.run(clips.reshape(B * nc, 2, 128, 128), msg_clips if (tiled or msg.shape[0] == B) else msg,
                   want=("stft_new", "wm", "wm_logits"))
     recon = FE.istft_clips(o["stft_new"].reshape(B, nc, 2, 128, 128), T, L)          # audio_test.py:595-600
     att = AT.apply_attack(recon, attack, draws, seed)                                 # :631-660
@@ -52,13 +98,20 @@ def embed_attack_extract(waves, messages, model, attack="closed_loop", draws=Non
     st_att = EV.wave_stats(waves, att)
     st_rec = EV.wave_stats(waves, recon)
     ws_clean = EV.wm_stats(wm[:, -1], msg_b)                                          # quirk B-8
-    msg_att = msg_b[:, None].expand(B, nc_att, 1, 32, 32).reshape(B * nc_att, 1, 32, 32)
+    msg_att = msg_for(nc_att).reshape(B * nc_att, 1, 32, 32)
     ws_att = EV.wm_stats(wm_att.reshape(B * nc_att, 1, 32, 32), msg_att).reshape(B, nc_att, 2)
     stats = torch.stack([
         EV.snr_from_stats(st_att), st_rec[:, 1] / st_rec[:, 5], ws_clean[:, 1] / 1024.0,
         ws_att[:, :, 1].sum(1) / (1024.0 * nc_att), ws_clean[:, 0], ws_att[:, :, 0].sum(1),
         torch.full((B,), 1024.0 * nc_att, device=waves.device, dtype=torch.float64)], dim=1)
     out = {"stats": stats, "n_clips": nc, "n_clips_att": nc_att}
+    if tiled:
+        # image-level recovery: average the sigmoids of the clips that carried each tile, then threshold
+        rec = recover_tiled(wm_att, K)
+        ws_img = EV.wm_stats(rec.reshape(B * K, 1, 32, 32), tiles.reshape(B * K, 1, 32, 32)).reshape(B, K, 2)
+        out["image_att"] = rec                                                        # (B,K,1,32,32)
+        out["image_stats"] = torch.stack([ws_img[:, :, 0].sum(1), ws_img[:, :, 1].sum(1) / (1024.0 * K),
+                                          torch.full((B,), 1024.0 * K, device=waves.device, dtype=torch.float64)], dim=1)
     if want_outputs:
         out.update({"recon": recon, "att": att, "wm": wm, "wm_att": wm_att,
                     "logits": o["wm_logits"].reshape(B, nc, 1, 32, 32),

@@ -215,6 +215,94 @@ rescale_kernel(const float* __restrict__ t, float* __restrict__ out, size_t n, c
   out[i] = v * (mm_x[1] - mm_x[0]) + mm_x[0];
 }
 
+
+// JpegCompression (hidden/noise_layers/jpeg_compression.py:128-160), 3-channel input as in the
+// reference (:53-55): RGB->YUV, 8x8 DCT-II (the reference's 64-filter stride-8 conv, :40-41,93-101),
+// keep the first 25 / 9 / 9 zig-zag coefficients of Y / U / V (:28-38), inverse (:44-46), YUV->RGB,
+// zero padding of H, W to multiples of 8 and un-padding.  One CTA = one 8x8 block of one image:
+// 192 threads = (channel, y, x); the three planes go through shared memory so the colour
+// transforms are fused with the DCT and nothing but the output reaches HBM.
+__constant__ unsigned long long c_jpeg_keep[3];          // bit (u*8+v) set = coefficient (u,v) kept
+
+__global__ void __launch_bounds__(192)
+jpeg_kernel(const float* __restrict__ in, float* __restrict__ out, int H, int W) {
+  __shared__ float pl[3][8][9], tmp[3][8][9];
+  const int tid = threadIdx.x, c = tid >> 6, yy = (tid >> 3) & 7, xx = tid & 7;
+  const int bx = blockIdx.x, by = blockIdx.y, b = blockIdx.z;
+  const int h = by * 8 + yy, w = bx * 8 + xx;
+  const bool inside = h < H && w < W;
+  const size_t plane = (size_t)H * W;
+  const float* src = in + (size_t)b * 3 * plane + (size_t)h * W + w;
+  const float r = inside ? src[0] : 0.f, g = inside ? src[plane] : 0.f, bl = inside ? src[2 * plane] : 0.f;
+  float v;
+  if (c == 0) v = 0.299f * r + 0.587f * g + 0.114f * bl;
+  else if (c == 1) v = -0.14713f * r + -0.28886f * g + 0.436f * bl;
+  else v = 0.615f * r + -0.51499f * g + -0.10001f * bl;
+  pl[c][yy][xx] = v;
+  __syncthreads();
+  // forward: D[u][v] = sum_{y,x} cos(pi/8 (y+1/2) u) cos(pi/8 (x+1/2) v) P[y][x]; rows first (u = yy role)
+  {
+    float a = 0.f;
+#pragma unroll
+    for (int n = 0; n < 8; ++n) a = fmaf(cospif((n + 0.5f) * xx * 0.125f), pl[c][yy][n], a);   // along x: v = xx
+    tmp[c][yy][xx] = a;
+  }
+  __syncthreads();
+  {
+    float a = 0.f;
+#pragma unroll
+    for (int n = 0; n < 8; ++n) a = fmaf(cospif((n + 0.5f) * yy * 0.125f), tmp[c][n][xx], a);  // along y: u = yy
+    const bool keep = (c_jpeg_keep[c] >> (yy * 8 + xx)) & 1ull;
+    pl[c][yy][xx] = keep ? a : 0.f;
+  }
+  __syncthreads();
+  // inverse: P[y][x] = sum_{u,v} i(u,y) i(v,x) D[u][v],  i(n,k) = ((n==0 ? -1/2 : 0) + cos(pi/8 (k+1/2) n)) / 4
+  {
+    float a = 0.f;
+#pragma unroll
+    for (int n = 0; n < 8; ++n) a = fmaf(((n == 0 ? -0.5f : 0.f) + cospif((xx + 0.5f) * n * 0.125f)) * 0.25f, pl[c][yy][n], a);
+    tmp[c][yy][xx] = a;
+  }
+  __syncthreads();
+  {
+    float a = 0.f;
+#pragma unroll
+    for (int n = 0; n < 8; ++n) a = fmaf(((n == 0 ? -0.5f : 0.f) + cospif((yy + 0.5f) * n * 0.125f)) * 0.25f, tmp[c][n][xx], a);
+    pl[c][yy][xx] = a;
+  }
+  __syncthreads();
+  if (!inside) return;
+  const float Y = pl[0][yy][xx], U = pl[1][yy][xx], V = pl[2][yy][xx];
+  float o;
+  if (c == 0) o = Y + 1.13983f * V;
+  else if (c == 1) o = Y + -0.39465f * U + -0.58060f * V;
+  else o = Y + 2.03211f * U;
+  out[((size_t)b * 3 + c) * plane + (size_t)h * W + w] = o;
+}
+
+// Magnitude / phase view of a spectrogram clip (the 1-channel "STFT magnitudes" input of the HiDDeN
+// flavour, BASELINE config 3; the reference keeps re/im and has no such op - SURVEY 8a note).
+// spec [n][2][plane] (re, im) <-> mag [n][plane], phase [n][plane]
+__global__ void __launch_bounds__(256)
+magphase_split_kernel(const float* __restrict__ spec, float* __restrict__ mag, float* __restrict__ phase, size_t n, size_t plane) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * plane) return;
+  const size_t b = i / plane, r = i - b * plane;
+  const float re = spec[(2 * b) * plane + r], im = spec[(2 * b + 1) * plane + r];
+  mag[i] = hypotf(re, im);
+  if (phase) phase[i] = atan2f(im, re);
+}
+__global__ void __launch_bounds__(256)
+magphase_merge_kernel(const float* __restrict__ mag, const float* __restrict__ phase, float* __restrict__ spec, size_t n, size_t plane) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * plane) return;
+  const size_t b = i / plane, r = i - b * plane;
+  float sn, cs;
+  sincosf(phase[i], &sn, &cs);
+  spec[(2 * b) * plane + r] = mag[i] * cs;
+  spec[(2 * b + 1) * plane + r] = mag[i] * sn;
+}
+
 }  // namespace
 }  // namespace wmk
 
@@ -310,5 +398,50 @@ extern "C" int wmk_noise_quantize_f32(const float* in, float* out, size_t n, voi
   WMK_CHECK_LAUNCH("rescale_kernel");
   WMK_CHECK_CUDA(cudaFreeAsync(mm, st));
   WMK_CHECK_CUDA(cudaFreeAsync(tmp, st));
+  return 0;
+}
+
+extern "C" int wmk_noise_jpeg_f32(const float* in, float* out, int B, int H, int W, int keep_y, int keep_u, int keep_v,
+                                  void* stream) {
+  WMK_REQUIRE(in && out && B > 0 && B <= 65535 && H > 0 && W > 0 && keep_y >= 0 && keep_y <= 64 && keep_u >= 0 &&
+                  keep_u <= 64 && keep_v >= 0 && keep_v <= 64, "noise_jpeg: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  // zig-zag order of jpeg_compression.py:31-32: sort (x, y) by (x + y, -y if (x + y) odd else y)
+  int order[64][2], n = 0;
+  for (int sum = 0; sum < 15; ++sum)
+    for (int k = 0; k < 8; ++k) {
+      const int y = (sum & 1) ? 7 - k : k;          // odd sums: descending y; even sums: ascending y
+      const int x = sum - y;
+      if (x < 0 || x > 7) continue;
+      order[n][0] = x; order[n][1] = y; ++n;
+    }
+  unsigned long long keep[3] = {0, 0, 0};
+  const int cnt[3] = {keep_y, keep_u, keep_v};
+  for (int c = 0; c < 3; ++c)
+    for (int i = 0; i < cnt[c]; ++i) keep[c] |= 1ull << (order[i][0] * 8 + order[i][1]);
+  WMK_CHECK_CUDA(cudaMemcpyToSymbolAsync(c_jpeg_keep, keep, sizeof(keep), 0, cudaMemcpyHostToDevice, st));
+  WMK_CHECK_CUDA(cudaStreamSynchronize(st));          // `keep` lives on this stack frame
+  ProfScope prof(FAM_ATTACK, 24.0 * B * H * W, st);
+  dim3 grid(cdiv(W, 8), cdiv(H, 8), B);
+  jpeg_kernel<<<grid, 192, 0, st>>>(in, out, H, W);
+  WMK_CHECK_LAUNCH("jpeg_kernel");
+  return 0;
+}
+
+extern "C" int wmk_magphase_split_f32(const float* spec, float* mag, float* phase, size_t n, size_t plane, void* stream) {
+  WMK_REQUIRE(spec && mag && n > 0 && plane > 0, "magphase_split: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  ProfScope prof(FAM_ATTACK, (phase ? 16.0 : 12.0) * n * plane, st);
+  magphase_split_kernel<<<cdiv(n * plane, 256), 256, 0, st>>>(spec, mag, phase, n, plane);
+  WMK_CHECK_LAUNCH("magphase_split_kernel");
+  return 0;
+}
+
+extern "C" int wmk_magphase_merge_f32(const float* mag, const float* phase, float* spec, size_t n, size_t plane, void* stream) {
+  WMK_REQUIRE(spec && mag && phase && n > 0 && plane > 0, "magphase_merge: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  ProfScope prof(FAM_ATTACK, 16.0 * n * plane, st);
+  magphase_merge_kernel<<<cdiv(n * plane, 256), 256, 0, st>>>(mag, phase, spec, n, plane);
+  WMK_CHECK_LAUNCH("magphase_merge_kernel");
   return 0;
 }

@@ -4,6 +4,7 @@ import numpy as np
 import torch.nn as nn
 
 from .identity import Identity
+from .jpeg_compression import JpegCompression
 from .quantization import Quantization
 
 
@@ -14,8 +15,7 @@ class Noiser(nn.Module):
         for layer in noise_layers:
             if type(layer) is str:
                 if layer == 'JpegPlaceholder':
-                    raise NotImplementedError("JpegCompression is hard-wired to 3-channel images in the reference "
-                                              "(jpeg_compression.py:53-55) and cannot run on 1/2-channel spectrograms")
+                    self.noise_layers.append(JpegCompression(device))
                 elif layer == 'QuantizationPlaceholder':
                     self.noise_layers.append(Quantization(device))
                 else:

@@ -162,6 +162,19 @@ int wmk_noise_resize_nearest_f32(const float* in, float* out, int planes, int H,
 /* Quantization (quantization.py:32-45): min-max to [0,255], Fourier soft rounding (10 terms),
  * min-max back to the input's range, over all n elements */
 int wmk_noise_quantize_f32(const float* in, float* out, size_t n, void* stream);
+/* JpegCompression (jpeg_compression.py:128-160): in / out [B][3][H][W] (the reference is hard-wired
+ * to 3 channels, :53-55); RGB->YUV, 8x8 DCT, keep the first keep_y / keep_u / keep_v zig-zag
+ * coefficients (reference default 25, 9, 9), inverse DCT, YUV->RGB; H, W are zero-padded to
+ * multiples of 8 internally and un-padded. */
+int wmk_noise_jpeg_f32(const float* in, float* out, int B, int H, int W, int keep_y, int keep_u,
+                       int keep_v, void* stream);
+/* Magnitude / phase view of re/im spectrogram clips: spec [n][2][plane] <-> mag, phase [n][plane]
+ * (hypot / atan2 and mag*cos / mag*sin).  Feeds "STFT magnitudes" to the 1-channel HiDDeN decoder
+ * (hidden/model/decoder.py:12-40); phase may be NULL in split. */
+int wmk_magphase_split_f32(const float* spec, float* mag, float* phase, size_t n, size_t plane,
+                           void* stream);
+int wmk_magphase_merge_f32(const float* mag, const float* phase, float* spec, size_t n, size_t plane,
+                           void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * UformerAudio embedder / extractor (uformerWM/model.py:2225-2511, configuration

@@ -134,6 +134,11 @@ def cnn_fixture():
         with torch.no_grad():
             r = layer([noised.clone(), cover.clone()])
         out["noise_" + name] = r[0].numpy().astype(np.float32)
+    # JpegCompression is hard-wired to 3 channels (jpeg_compression.py:53-55): (2,3,36,44) exercises the padding
+    rgb = torch.rand(2, 3, 36, 44, generator=g)
+    with torch.no_grad():
+        jr = hid["jpeg_compression"].JpegCompression(torch.device("cpu"))([rgb.clone(), rgb.clone()])
+    out.update(jpeg_in=rgb.numpy(), noise_jpeg=jr[0].numpy().astype(np.float32))
     np.savez_compressed(os.path.join(OUT, "cnn.npz"), **out)
     print("cnn.npz", {k: v.shape for k, v in out.items() if k.startswith("noise_")})
 

@@ -27,16 +27,25 @@ def prepare_data(wave_1L):
     return [(wave_1L, 16000), clips, stft.shape[2] % 128]
 
 
-def reconstruct_audio(audio_data, watermark, sd, n_fft=255, attack="closed_loop", draws=None):
+def reconstruct_audio(audio_data, watermark, sd, n_fft=255, attack="closed_loop", draws=None, tiles=None):
     """`uformerWM/audio_test.py:528-785`.  Returns the reference's 10-tuple plus a dict of
-    extras (logits) used by the parity tests."""
+    extras (logits) used by the parity tests.
+
+    `tiles` (K,1,32,32) is the 64x64 extension of BASELINE config 4 (the reference hard-codes 32x32
+    messages, `uformerWM/model.py:2388-2404`): clip j embeds / is scored against tile j mod K instead
+    of `watermark`; everything else is the reference's loop unchanged."""
     clips = audio_data[1]
+    if tiles is not None:
+        K = tiles.shape[0]
+        wm_of = lambda j: tiles[j % K][None]
+    else:
+        wm_of = lambda j: watermark
     len_last_clip = audio_data[2]
     preds, wm_losses, wm_losses_att, wms_decode = [], [], [], []
     logits_clean = []
     with torch.no_grad():
         for i, clip in enumerate(clips):
-            audio_clip, _, _, wm_decode, lg = U.forward(sd, clip, watermark, return_logits=True)   # `:553`
+            audio_clip, _, _, wm_decode, lg = U.forward(sd, clip, wm_of(i), return_logits=True)    # `:553`
             wms_decode.append(wm_decode.numpy())
             logits_clean.append(lg.numpy())
             if i != len(clips) - 1:
@@ -47,7 +56,7 @@ def reconstruct_audio(audio_data, watermark, sd, n_fft=255, attack="closed_loop"
         recon_audio = torch.istft(torch.view_as_complex(spec.contiguous()), n_fft=n_fft,
                                   length=audio_data[0][0].shape[-1], return_complex=False)        # `:598-600`
         mse_loss = torch.nn.MSELoss()(audio_data[0][0].squeeze(), recon_audio).item()             # `:618`
-        wm_losses.append(torch.nn.MSELoss()(watermark, wm_decode).item())                         # `:625` (last clip only)
+        wm_losses.append(torch.nn.MSELoss()(wm_of(len(clips) - 1), wm_decode).item())             # `:625` (last clip only)
         audio_att = S.apply_attack(recon_audio.numpy(), attack, draws)                            # `:631-660`
         feat = torch.view_as_real(torch.stft(torch.from_numpy(np.ascontiguousarray(audio_att)), n_fft=255,
                                              return_complex=True))                                # `:677`
@@ -60,12 +69,15 @@ def reconstruct_audio(audio_data, watermark, sd, n_fft=255, attack="closed_loop"
             wm_att, lg = U.wm_decode(sd, data_clip, return_logits=True)                           # `:706`
             wms_att_decode.append(wm_att.numpy())
             logits_att.append(lg.numpy())
-            wm_losses_att.append(torch.nn.MSELoss()(watermark, wm_att).item())                    # `:712`
+            wm_losses_att.append(torch.nn.MSELoss()(wm_of(j), wm_att).item())                     # `:712`
     snr_ori = S.signaltonoise(audio_data[0][0].squeeze().numpy())
     snr_recon = S.signaltonoise(recon_audio.numpy())
-    out = (audio_att, recon_audio, watermark.numpy(), wms_decode, wms_att_decode, mse_loss,
+    out = (audio_att, recon_audio, (watermark if tiles is None else tiles).numpy(), wms_decode, wms_att_decode, mse_loss,
            np.mean(wm_losses), np.mean(wm_losses_att), snr_ori, snr_recon)
     extras = {"logits_clean": logits_clean, "logits_att": logits_att}
+    if tiles is not None:          # image-level recovery: mean of the sigmoids of the clips that carried each tile
+        rec = np.stack([np.mean([w[0] for j, w in enumerate(wms_att_decode) if j % K == t], axis=0) for t in range(K)])
+        extras["image_att"] = rec                                                                 # (K,1,32,32)
     return out, extras
 
 

@@ -211,7 +211,7 @@ def reference_hidden_modules():
     importlib.invalidate_caches()
     try:
         out = {"decoder": importlib.import_module("model.decoder"), "options": importlib.import_module("options")}
-        for n in ("identity", "crop", "cropout", "dropout", "resize", "quantization"):
+        for n in ("identity", "crop", "cropout", "dropout", "resize", "quantization", "jpeg_compression"):
             out[n] = importlib.import_module("noise_layers." + n)
     finally:
         sys.path.remove(hp)

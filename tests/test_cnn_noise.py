@@ -106,5 +106,77 @@ def test_noise_layers_match_reference_golden(golden):
     assert out[0].shape[:2] == nz.shape[:2]
     with pytest.raises(ValueError):
         NL.Noiser(['bogus'], None)
-    with pytest.raises(NotImplementedError):
-        NL.Noiser(['JpegPlaceholder'], None)
+
+
+def test_jpeg_and_magphase_oracles(golden):
+    g = golden("cnn.npz")
+    r = N.jpeg_compression(torch.from_numpy(g["jpeg_in"])).numpy()
+    assert r.shape == g["noise_jpeg"].shape and _maxrel(r, g["noise_jpeg"]) < 2e-6     # vs the unmodified reference
+    spec = torch.from_numpy(g["x"])
+    mag, ph = N.magphase_split(spec)
+    assert _maxrel(N.magphase_merge(mag, ph).numpy(), g["x"]) < 1e-6
+
+
+def test_noise_argparser_grammar():
+    from image_in_speech_watermarking_b200.hidden import noise_argparser as NA, noise_layers as NL
+    layers = NA.parse_noise("crop((0.4,0.55),(0.4,0.55))+cropout((0.25,0.35),(0.25,0.35))+dropout(0.25,0.35)"
+                            "+resize(0.4,0.6)+jpeg()+quant()+identity()")           # hidden/runfiles/combined-noise.sh
+    assert [type(l).__name__ if not isinstance(l, str) else l for l in layers] == [
+        "Crop", "Cropout", "Dropout", "Resize", "JpegPlaceholder", "QuantizationPlaceholder"]
+    assert layers[0].height_ratio_range == (0.4, 0.55) and layers[2].keep_min == 0.25 and layers[3].resize_ratio_min == 0.4
+    with pytest.raises(ValueError):
+        NA.parse_noise("blur(3)")
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--noise", nargs="*", action=NA.NoiseArgParser)
+    ns = ap.parse_args(["--noise", "dropout(0.55,0.6)"])
+    assert isinstance(ns.noise[0], NL.Dropout)
+
+
+@pytest.mark.gpu
+def test_jpeg_layer_and_magphase_match_reference_golden(golden):
+    from image_in_speech_watermarking_b200.hidden import noise_layers as NL, audio_test as HT
+    g = golden("cnn.npz")
+    rgb = torch.from_numpy(g["jpeg_in"]).cuda()
+    out = NL.JpegCompression(torch.device("cuda"))([rgb.clone(), rgb.clone()])[0]
+    assert out.shape == rgb.shape and _maxrel(out.cpu().numpy(), g["noise_jpeg"]) < 1e-5
+    with pytest.raises(ValueError):
+        NL.JpegCompression()([rgb[:, :2].contiguous(), rgb])
+    noiser = NL.Noiser(['JpegPlaceholder'], torch.device("cuda"))
+    assert len(noiser.noise_layers) == 2
+    spec = torch.from_numpy(g["x"]).cuda()
+    mag, ph = HT.magphase_split(spec)
+    mo, po = N.magphase_split(torch.from_numpy(g["x"]))
+    assert _maxrel(mag.cpu().numpy(), mo.numpy()) < 1e-6 and np.abs(ph.cpu().numpy() - po.numpy()).max() < 1e-5
+    assert _maxrel(HT.magphase_merge(mag, ph).cpu().numpy(), g["x"]) < 1e-5
+
+
+@pytest.mark.gpu
+def test_hidden_magnitude_pipeline_config3_shape():
+    """BASELINE config 3 shape: 128 x 2 s utterances -> 512 clips -> magnitudes -> noise layer -> decoder."""
+    from image_in_speech_watermarking_b200.hidden import noise_layers as NL, audio_test as HT, noise_argparser as NA
+    from image_in_speech_watermarking_b200.hidden.model.decoder import Decoder
+    from image_in_speech_watermarking_b200.hidden.options import HiDDenConfiguration
+    from image_in_speech_watermarking_b200 import synthetic as SY
+    cfg = HiDDenConfiguration(H=128, W=128, message_length=30, encoder_blocks=4, encoder_channels=64, decoder_blocks=7,
+                              decoder_channels=64, use_discriminator=True, use_vgg=False, discriminator_blocks=3,
+                              discriminator_channels=64, decoder_loss=1, encoder_loss=0.7, adversarial_loss=1e-3)
+    oracle_dec = C.randomize_(C.HiddenDecoderOracle(), 12)
+    d = Decoder(cfg)
+    d.load_state_dict(oracle_dec.state_dict())
+    d = d.cuda().eval()
+    B = 128
+    waves = SY.synth_speech_batch(0, 4, 2.0).repeat(B // 4, 1).cuda()
+    msgs = torch.stack([SY.synth_image_binary(i) for i in range(B)]).cuda()
+    np.random.seed(3)
+    noiser = NL.Noiser(NA.parse_noise("cropout((0.25,0.35),(0.25,0.35))+dropout(0.25,0.35)+quant()"), torch.device("cuda"))
+    dec, stats = HT.attack_and_decode(waves, msgs, d, noiser)
+    assert dec.shape == (512, 1, 32, 32) and stats.shape == (512, 2)
+    # clean path (no noise layer) against the CPU oracle on the first utterance's clips
+    dec0, _ = HT.attack_and_decode(waves[:1], msgs[:1], d, None)
+    from oracle import pipeline as P
+    clips = torch.cat(P.prepare_data(waves[:1].cpu())[1][:4])
+    mag = N.magphase_split(clips)[0] * HT.AUDIO_SCALE
+    with torch.no_grad():
+        ref = oracle_dec(mag)
+    assert _maxrel(dec0.cpu().numpy(), ref.numpy()) < 1e-3

@@ -279,3 +279,28 @@ def test_batched_pipeline_equals_per_utterance_and_oracle(models, weights):
     bits_got = (r["logits_att"][1].cpu().numpy() > 0)[safe]
     assert np.array_equal(bits_ref, bits_got)
     assert abs(s[5] / s[6] - ev["ber_att"]) <= (~safe).sum() / lg.size + 1e-12
+
+
+def test_tiled_64x64_image_pipeline_matches_oracle(models, weights):
+    """BASELINE config 4 shape (64x64 greyscale image carried as four 32x32 tiles, tile j mod 4 in clip j):
+    per-clip extraction, the averaged image and its error statistics == the oracle's loop."""
+    from image_in_speech_watermarking_b200 import audio_test as PT
+    m = models("fp32", "stress")
+    wave = SY.synth_speech(21, 2.2)[None]                       # T = 559 frames -> 5 clips
+    img = SY.synth_image_grey(21)[None]                         # (1,1,64,64)
+    tiles = PT.tile_image(img)                                  # (1,4,1,32,32)
+    r = PT.embed_attack_extract(wave.cuda(), tiles.cuda(), m, "amplitude_scaling-0.8")
+    ref, ex = P.reconstruct_audio(P.prepare_data(wave), None, weights("stress"), attack="amplitude_scaling-0.8",
+                                  tiles=tiles[0])
+    assert r["n_clips"] == 5 and r["n_clips_att"] == 5
+    for j in range(5):
+        assert maxrel(r["wm"][0, j].cpu().numpy(), ref[3][j][0]) < TOL["fp32"]
+        assert maxrel(r["wm_att"][0, j].cpu().numpy(), ref[4][j][0]) < TOL["fp32"]
+    assert l2rel(r["recon"][0].cpu().numpy(), ref[1].numpy()) < TOL["fp32"]
+    assert maxrel(r["image_att"][0].cpu().numpy(), ex["image_att"]) < TOL["fp32"]
+    s = r["stats"][0].cpu().numpy()
+    assert abs(s[2] - ref[6]) < 1e-4 and abs(s[3] - ref[7]) < 1e-4
+    mse_img = float(np.mean((ex["image_att"] - tiles[0].numpy()) ** 2))
+    assert abs(float(r["image_stats"][0, 1]) - mse_img) < 1e-4
+    back = PT.untile_image(r["image_att"], 64, 64)
+    assert back.shape == (1, 1, 64, 64)

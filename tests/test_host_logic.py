@@ -1,0 +1,40 @@
+"""CPU tests of host-side logic that needs no GPU: 64x64 image tiling (BASELINE config 4),
+statistics vector layout, attack-string grammar."""
+import numpy as np
+import pytest
+import torch
+
+from image_in_speech_watermarking_b200 import audio_test as PT, sharding as SH
+
+
+def test_tile_untile_roundtrip_and_order():
+    g = torch.Generator().manual_seed(0)
+    img = torch.rand(3, 1, 64, 64, generator=g)
+    t = PT.tile_image(img)
+    assert t.shape == (3, 4, 1, 32, 32)
+    assert torch.equal(t[:, 0, 0], img[:, 0, :32, :32]) and torch.equal(t[:, 1, 0], img[:, 0, :32, 32:])
+    assert torch.equal(t[:, 2, 0], img[:, 0, 32:, :32]) and torch.equal(t[:, 3, 0], img[:, 0, 32:, 32:])
+    assert torch.equal(PT.untile_image(t, 64, 64), img)
+    with pytest.raises(ValueError):
+        PT.tile_image(torch.zeros(1, 1, 48, 64))
+
+
+def test_recover_tiled_averages_clips_of_the_same_tile():
+    g = torch.Generator().manual_seed(1)
+    wm = torch.rand(2, 6, 1, 32, 32, generator=g)                 # 6 clips, 4 tiles: tiles 0,1 seen twice
+    rec = PT.recover_tiled(wm, 4)
+    assert torch.allclose(rec[:, 0], (wm[:, 0] + wm[:, 4]) / 2) and torch.allclose(rec[:, 1], (wm[:, 1] + wm[:, 5]) / 2)
+    assert torch.allclose(rec[:, 2], wm[:, 2]) and torch.allclose(rec[:, 3], wm[:, 3])
+    with pytest.raises(ValueError):
+        PT.recover_tiled(wm[:, :3], 4)
+
+
+def test_stats_vector_and_summary():
+    st = torch.tensor([[10.0, 1e-4, 0.2, 0.3, 500.0, 3000.0, 6144.0],
+                       [12.0, 3e-4, 0.1, 0.2, 520.0, 3100.0, 6144.0]], dtype=torch.float64)
+    v = SH.stats_vector(st)
+    assert v.shape == (8,) and len(SH.STAT_KEYS) == 8
+    s = SH.summarize(SH.allreduce_stats(v))
+    assert abs(s["ber_clean"] - 1020.0 / 2048.0) < 1e-12 and abs(s["ber_attacked"] - 6100.0 / 12288.0) < 1e-12
+    assert abs(s["mean_snr_db"] - 11.0) < 1e-12 and s["utterances"] == 2
+    assert list(SH.shard_range(10, 1, 4)) == [3, 4, 5] and list(SH.shard_range(10, 3, 4)) == [9]

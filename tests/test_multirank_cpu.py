@@ -16,21 +16,22 @@ def _free_port():
     return p
 
 
+from image_in_speech_watermarking_b200 import sharding as SH
+
+
 def _shard(n_utt, rank, world):
-    per = (n_utt + world - 1) // world
-    return list(range(rank * per, min(n_utt, (rank + 1) * per)))
+    return list(SH.shard_range(n_utt, rank, world))
 
 
 def _worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     g = torch.Generator().manual_seed(0)
-    per_utt = torch.rand(10, 8, generator=g, dtype=torch.float64)          # same table on every rank
+    per_utt = torch.rand(10, 7, generator=g, dtype=torch.float64)          # same table on every rank
     mine = _shard(10, rank, world)
-    vec = per_utt[mine].sum(0)
-    dist.all_reduce(vec)
+    vec = SH.allreduce_stats(SH.stats_vector(per_utt[mine]))
     if rank == 0:
-        out.put((vec, per_utt.sum(0)))
+        out.put((vec, SH.stats_vector(per_utt)))
     dist.destroy_process_group()
 
 
