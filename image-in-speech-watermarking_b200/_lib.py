@@ -35,6 +35,15 @@ SIGNATURES = {
     "wmk_conv3x3_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp]),
     "wmk_convT2x2_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp]),
     "wmk_maxpool2x2_f32": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "wmk_bn_train_fwd_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _f, _i, _f, _vp]),
+    "wmk_bn_train_bwd_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
+    "wmk_maxpool2x2_bwd_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
+    "wmk_mask_scale_f32": (_i, [_vp, _vp, _vp, _sz, _f, _vp]),
+    "wmk_conv3x3_wgrad_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "wmk_convT2x2_dgrad_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "wmk_convT2x2_wgrad_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "wmk_mse_f32": (_i, [_vp, _vp, _vp, _sz, _f, _vp, _vp]),
+    "wmk_adam_step_f32": (_i, [_vp, _vp, _vp, _vp, _sz, _f, _f, _f, _f, _f, _i, _f, _i, _vp]),
     "wmk_noise_mix_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "wmk_noise_crop_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "wmk_noise_resize_nearest_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _f, _vp]),

@@ -1,0 +1,463 @@
+// Training-mode kernels of ModelA (uformerWM/model.py:3000-3066; step uformerWM/train_modelA.py:402-500):
+// BatchNorm with batch statistics (+ fused activation) forward / backward, max-pool backward,
+// weight / bias gradients of the 3x3 convolution and of the 2x2 stride-2 transposed convolution,
+// its data gradient, the mean-squared-error loss with its gradient, and a fused Adam step.
+// (The data gradient of the 3x3 convolution is the forward kernel of conv_noise.cu run with the
+// flipped, transposed weights.)  NCHW float32; all of these are memory bound: every tensor is read
+// once per kernel, per-channel reductions go through warp shuffles and fp64 atomics.
+#include "uformer_kernels.cuh"
+
+namespace wmk {
+namespace {
+
+enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY = 2, ACT_SIGMOID = 3 };
+
+__device__ __forceinline__ float act_fwd(float v, int act, float slope) {
+  if (act == ACT_RELU) return fmaxf(v, 0.f);
+  if (act == ACT_LEAKY) return v > 0.f ? v : slope * v;
+  if (act == ACT_SIGMOID) return 1.0f / (1.0f + expf(-v));
+  return v;
+}
+// derivative of the activation expressed through its OUTPUT y (sign(y) = sign(z) for (leaky) ReLU)
+__device__ __forceinline__ float act_grad_from_out(float y, int act, float slope) {
+  if (act == ACT_RELU) return y > 0.f ? 1.f : 0.f;
+  if (act == ACT_LEAKY) return y > 0.f ? 1.f : slope;
+  if (act == ACT_SIGMOID) return y * (1.f - y);
+  return 1.f;
+}
+
+// ---- BatchNorm2d (training): per-channel sums over (B, H, W)
+// grid (chunks, C): stats[c] = {sum x, sum x^2}  (fp64 atomics)
+__global__ void __launch_bounds__(256)
+bn_stats_kernel(const float* __restrict__ x, int B, int C, int HW, double* __restrict__ stats) {
+  const int c = blockIdx.y;
+  const size_t n = (size_t)B * HW;
+  float s1 = 0.f, s2 = 0.f;      // per-thread partials stay short (<= a few thousand terms); fp64 beyond
+  double d1 = 0.0, d2 = 0.0;
+  int cnt = 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t b = i / HW, r = i - b * HW;
+    const float v = x[(b * C + c) * HW + r];
+    s1 += v;
+    s2 = fmaf(v, v, s2);
+    if (++cnt == 1024) { d1 += s1; d2 += s2; s1 = s2 = 0.f; cnt = 0; }
+  }
+  d1 += s1; d2 += s2;
+  d1 = warp_sum(d1); d2 = warp_sum(d2);
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(stats + 2 * c, d1);
+    atomicAdd(stats + 2 * c + 1, d2);
+  }
+}
+
+// mean / rstd from the sums; running statistics updated as nn.BatchNorm2d does (momentum, unbiased var)
+__global__ void bn_finalize_kernel(const double* __restrict__ stats, int C, double n, float eps, float momentum,
+                                   float* __restrict__ mean_rstd, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double mean = stats[2 * c] / n;
+  double var = stats[2 * c + 1] / n - mean * mean;
+  if (var < 0.0) var = 0.0;
+  mean_rstd[2 * c] = (float)mean;
+  mean_rstd[2 * c + 1] = (float)(1.0 / sqrt(var + (double)eps));
+  if (running_mean) {
+    const double unbiased = n > 1.0 ? var * n / (n - 1.0) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+  }
+}
+
+// y = act(gamma * (x - mean) * rstd + beta)
+__global__ void __launch_bounds__(256)
+bn_act_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ mean_rstd,
+                  const float* __restrict__ gamma, const float* __restrict__ beta, size_t total, int C, int HW, int act,
+                  float slope) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)((i / HW) % C);
+  const float xh = (x[i] - mean_rstd[2 * c]) * mean_rstd[2 * c + 1];
+  y[i] = act_fwd(fmaf(gamma[c], xh, beta[c]), act, slope);
+}
+
+// backward pass 1: dz = dy * act'(y); sums[c] = {sum dz, sum dz * xhat}
+__global__ void __launch_bounds__(256)
+bn_act_bwd_reduce_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ dy,
+                         const float* __restrict__ mean_rstd, int B, int C, int HW, int act, float slope,
+                         double* __restrict__ sums) {
+  const int c = blockIdx.y;
+  const size_t n = (size_t)B * HW;
+  const float mean = mean_rstd[2 * c], rstd = mean_rstd[2 * c + 1];
+  float s1 = 0.f, s2 = 0.f;
+  double d1 = 0.0, d2 = 0.0;
+  int cnt = 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t b = i / HW, r = i - b * HW;
+    const size_t o = (b * C + c) * HW + r;
+    const float dz = dy[o] * act_grad_from_out(y[o], act, slope);
+    s1 += dz;
+    s2 = fmaf(dz, (x[o] - mean) * rstd, s2);
+    if (++cnt == 1024) { d1 += s1; d2 += s2; s1 = s2 = 0.f; cnt = 0; }
+  }
+  d1 += s1; d2 += s2;
+  d1 = warp_sum(d1); d2 = warp_sum(d2);
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(sums + 2 * c, d1);
+    atomicAdd(sums + 2 * c + 1, d2);
+  }
+}
+
+// backward pass 2: dx = gamma * rstd * (dz - mean(dz) - xhat * mean(dz * xhat)); thread 0 of channel rows writes dgamma / dbeta
+__global__ void __launch_bounds__(256)
+bn_act_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ dy,
+                        float* __restrict__ dx, const float* __restrict__ mean_rstd, const float* __restrict__ gamma,
+                        const double* __restrict__ sums, size_t total, int C, int HW, double n, int act, float slope,
+                        float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < (size_t)C) {
+    dgamma[i] = (float)sums[2 * i + 1];
+    dbeta[i] = (float)sums[2 * i];
+  }
+  if (i >= total) return;
+  const int c = (int)((i / HW) % C);
+  const float rstd = mean_rstd[2 * c + 1];
+  const float xh = (x[i] - mean_rstd[2 * c]) * rstd;
+  const float dz = dy[i] * act_grad_from_out(y[i], act, slope);
+  const float m1 = (float)(sums[2 * c] / n), m2 = (float)(sums[2 * c + 1] / n);
+  dx[i] = gamma[c] * rstd * (dz - m1 - xh * m2);
+}
+
+// MaxPool2d(2,2) backward: the gradient goes to the first maximum of each window (PyTorch's scan order)
+__global__ void __launch_bounds__(256)
+maxpool2x2_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, size_t planes,
+                      int H, int W) {
+  const int Ho = H >> 1, Wo = W >> 1;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= planes * Ho * Wo) return;
+  const int wq = (int)(idx % Wo), h = (int)((idx / Wo) % Ho);
+  const size_t p = idx / ((size_t)Ho * Wo);
+  const size_t o = (p * H + 2 * h) * W + 2 * wq;
+  const float v[4] = {x[o], x[o + 1], x[o + W], x[o + W + 1]};
+  int k = 0;
+  if (v[1] > v[k]) k = 1;
+  if (v[2] > v[k]) k = 2;
+  if (v[3] > v[k]) k = 3;
+  const float g = dy[idx];
+  dx[o] = k == 0 ? g : 0.f;
+  dx[o + 1] = k == 1 ? g : 0.f;
+  dx[o + W] = k == 2 ? g : 0.f;
+  dx[o + W + 1] = k == 3 ? g : 0.f;
+}
+
+// out = in * mask * scale   (Dropout forward and backward with the same mask)
+__global__ void __launch_bounds__(256)
+mask_scale_kernel(const float* __restrict__ in, const float* __restrict__ mask, float* __restrict__ out, size_t n, float scale) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[i] * mask[i] * scale;
+}
+
+// ---- weight gradient of Conv2d(Cin, Cout, 3, padding=1):
+//   dw[co][ci][ky][kx] = sum_{b,h,w} x[b][ci][h+ky-1][w+kx-1] dy[b][co][h][w],   db[co] = sum dy[b][co][h][w]
+// One CTA = a 16x16 pixel tile of one image: x tile (+halo) and dy tile in shared memory; a thread owns
+// (pixel subset s, ci, block of CB output channels) = CB x 9 accumulators, loops over its pixels and adds
+// its partial sums to the global gradient with atomics.
+constexpr int WG_T = 16;
+template <int CB>
+__global__ void __launch_bounds__(256)
+conv3x3_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw,
+                     float* __restrict__ db, int Cin, int Cout, int H, int W) {
+  extern __shared__ float sm[];
+  float* xs = sm;                                        // [Cin][18][18]
+  float* ds = sm + Cin * (WG_T + 2) * (WG_T + 2);        // [Cout][16][16]
+  const int tiles_w = W / WG_T;
+  const int th = blockIdx.x / tiles_w, tw = blockIdx.x % tiles_w;
+  const int b = blockIdx.y;
+  for (int e = threadIdx.x; e < Cin * (WG_T + 2) * (WG_T + 2); e += 256) {
+    const int ci = e / ((WG_T + 2) * (WG_T + 2)), r = (e / (WG_T + 2)) % (WG_T + 2), c = e % (WG_T + 2);
+    const int hh = th * WG_T + r - 1, ww = tw * WG_T + c - 1;
+    xs[e] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? x[(((size_t)b * Cin + ci) * H + hh) * W + ww] : 0.f;
+  }
+  for (int e = threadIdx.x; e < Cout * WG_T * WG_T; e += 256) {
+    const int co = e / (WG_T * WG_T), r = (e / WG_T) % WG_T, c = e % WG_T;
+    ds[e] = dy[(((size_t)b * Cout + co) * H + th * WG_T + r) * W + tw * WG_T + c];
+  }
+  __syncthreads();
+  const int n_cb = (Cout + CB - 1) / CB;
+  const int pairs = n_cb * Cin;
+  const int S = 256 / pairs > 0 ? 256 / pairs : 1;       // pixel subsets
+  const int pair = threadIdx.x % pairs, s = threadIdx.x / pairs;
+  if (s >= S || threadIdx.x >= pairs * S) return;
+  const int ci = pair % Cin, cb = pair / Cin;
+  float acc[CB][9], bsum[CB];
+#pragma unroll
+  for (int j = 0; j < CB; ++j) {
+    bsum[j] = 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) acc[j][t] = 0.f;
+  }
+  for (int p = s; p < WG_T * WG_T; p += S) {
+    const int r = p / WG_T, c = p % WG_T;
+    float xv[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) xv[t] = xs[(ci * (WG_T + 2) + r + t / 3) * (WG_T + 2) + c + t % 3];
+#pragma unroll
+    for (int j = 0; j < CB; ++j) {
+      const int co = cb * CB + j;
+      const float d = co < Cout ? ds[co * WG_T * WG_T + p] : 0.f;
+      bsum[j] += d;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) acc[j][t] = fmaf(xv[t], d, acc[j][t]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < CB; ++j) {
+    const int co = cb * CB + j;
+    if (co >= Cout) break;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) atomicAdd(dw + ((size_t)co * Cin + ci) * 9 + t, acc[j][t]);
+    if (ci == 0 && db) atomicAdd(db + co, bsum[j]);
+  }
+}
+
+// ---- ConvTranspose2d(Cin, Cout, 2, stride=2): data gradient
+//   dx[b][ci][h][w] = sum_{co,i,j} w[ci][co][i][j] dy[b][co][2h+i][2w+j]
+__global__ void __launch_bounds__(256)
+convT2x2_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dx, int B, int Cin,
+                      int Cout, int H, int W) {
+  extern __shared__ float wsm[];             // [Cin][Cout][4]
+  for (int e = threadIdx.x; e < Cin * Cout * 4; e += blockDim.x) wsm[e] = w[e];
+  __syncthreads();
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)B * H * W) return;
+  const int wq = (int)(idx % W), h = (int)((idx / W) % H);
+  const size_t b = idx / ((size_t)H * W);
+  for (int ci = 0; ci < Cin; ++ci) {
+    float a = 0.f;
+    for (int co = 0; co < Cout; ++co) {
+      const float* d = dy + ((b * Cout + co) * (size_t)(2 * H) + 2 * h) * (2 * W) + 2 * wq;
+      const float2 d0 = *reinterpret_cast<const float2*>(d), d1 = *reinterpret_cast<const float2*>(d + 2 * W);
+      const float* wp = wsm + ((size_t)ci * Cout + co) * 4;
+      a = fmaf(wp[0], d0.x, fmaf(wp[1], d0.y, fmaf(wp[2], d1.x, fmaf(wp[3], d1.y, a))));
+    }
+    dx[((b * Cin + ci) * H + h) * W + wq] = a;
+  }
+}
+
+// weight gradient: dw[ci][co][i][j] = sum_{b,h,w} x[b][ci][h][w] dy[b][co][2h+i][2w+j];  db[co] = sum dy
+// One CTA = a 16x16 input tile of one image; a thread owns (pixel subset, ci, co) = 4 accumulators.
+__global__ void __launch_bounds__(256)
+convT2x2_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw,
+                      float* __restrict__ db, int Cin, int Cout, int H, int W) {
+  extern __shared__ float sm[];
+  float* xs = sm;                              // [Cin][256]
+  float* ds = sm + Cin * 256;                  // [Cout][32][32]
+  const int tiles_w = W / 16;
+  const int th = blockIdx.x / tiles_w, tw = blockIdx.x % tiles_w;
+  const int b = blockIdx.y;
+  for (int e = threadIdx.x; e < Cin * 256; e += 256) {
+    const int ci = e >> 8, r = (e >> 4) & 15, c = e & 15;
+    xs[e] = x[(((size_t)b * Cin + ci) * H + th * 16 + r) * W + tw * 16 + c];
+  }
+  for (int e = threadIdx.x; e < Cout * 1024; e += 256) {
+    const int co = e >> 10, r = (e >> 5) & 31, c = e & 31;
+    ds[e] = dy[(((size_t)b * Cout + co) * (2 * H) + th * 32 + r) * (size_t)(2 * W) + tw * 32 + c];
+  }
+  __syncthreads();
+  const int pairs = Cin * Cout;
+  for (int pair = threadIdx.x; pair < pairs; pair += 256) {
+    const int ci = pair / Cout, co = pair % Cout;
+    float a[4] = {0.f, 0.f, 0.f, 0.f}, bs = 0.f;
+    for (int p = 0; p < 256; ++p) {
+      const int r = p >> 4, c = p & 15;
+      const float xv = xs[ci * 256 + p];
+      const float* d = ds + co * 1024 + (2 * r) * 32 + 2 * c;
+      a[0] = fmaf(xv, d[0], a[0]); a[1] = fmaf(xv, d[1], a[1]); a[2] = fmaf(xv, d[32], a[2]); a[3] = fmaf(xv, d[33], a[3]);
+      bs += (d[0] + d[1]) + (d[32] + d[33]);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) atomicAdd(dw + ((size_t)ci * Cout + co) * 4 + k, a[k]);
+    if (ci == 0 && db) atomicAdd(db + co, bs);
+  }
+}
+
+// ---- mean squared error (nn.MSELoss, train_modelA.py:435-445): loss += mean((a-b)^2) (fp64 accumulator),
+// grad_a = grad_scale * 2 (a - b) / n
+__global__ void __launch_bounds__(256)
+mse_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ grad_a, size_t n, float grad_scale,
+           double* __restrict__ loss) {
+  double acc = 0.0;
+  float part = 0.f;
+  int cnt = 0;
+  const float gs = grad_scale * 2.0f / (float)n;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float d = a[i] - b[i];
+    part = fmaf(d, d, part);
+    if (grad_a) grad_a[i] = gs * d;
+    if (++cnt == 1024) { acc += part; part = 0.f; cnt = 0; }
+  }
+  acc += part;
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) atomicAdd(loss, acc / (double)n);
+}
+
+// ---- Adam / AdamW over a flat parameter buffer (torch.optim.Adam semantics, train_modelA.py:234-236)
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, size_t n,
+            float lr, float beta1, float beta2, float eps, float weight_decay, float bc1, float bc2, float grad_scale,
+            int decoupled) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float grad = g[i] * grad_scale, w = p[i];
+  if (decoupled) w *= 1.f - lr * weight_decay;        // AdamW
+  else grad = fmaf(weight_decay, w, grad);            // Adam with L2 penalty
+  const float mi = beta1 * m[i] + (1.f - beta1) * grad;
+  const float vi = beta2 * v[i] + (1.f - beta2) * grad * grad;
+  m[i] = mi;
+  v[i] = vi;
+  const float denom = sqrtf(vi) / sqrtf(bc2) + eps;
+  p[i] = w - (lr / bc1) * (mi / denom);
+}
+
+int grid_for(size_t n) { return (int)((n + 255) / 256); }
+
+}  // namespace
+}  // namespace wmk
+
+using namespace wmk;
+
+extern "C" int wmk_bn_train_fwd_f32(const float* x, float* y, const float* gamma, const float* beta, float* running_mean,
+                                    float* running_var, float* mean_rstd, double* scratch, int B, int C, int HW, float eps,
+                                    float momentum, int act, float slope, void* stream) {
+  WMK_REQUIRE(x && y && gamma && beta && mean_rstd && scratch && B > 0 && C > 0 && HW > 0 && act >= 0 && act <= 3,
+              "bn_train_fwd: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t total = (size_t)B * C * HW;
+  ProfScope prof(FAM_SMALL, 12.0 * total, st);
+  WMK_CHECK_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * C, st));
+  const size_t per_c = (size_t)B * HW;
+  int chunks = (int)((per_c + 256 * 16 - 1) / (256 * 16));
+  if (chunks > 2048) chunks = 2048;
+  bn_stats_kernel<<<dim3(chunks, C), 256, 0, st>>>(x, B, C, HW, scratch);
+  WMK_CHECK_LAUNCH("bn_stats_kernel");
+  bn_finalize_kernel<<<cdiv(C, 64), 64, 0, st>>>(scratch, C, (double)per_c, eps, momentum, mean_rstd, running_mean, running_var);
+  WMK_CHECK_LAUNCH("bn_finalize_kernel");
+  bn_act_fwd_kernel<<<grid_for(total), 256, 0, st>>>(x, y, mean_rstd, gamma, beta, total, C, HW, act, slope);
+  WMK_CHECK_LAUNCH("bn_act_fwd_kernel");
+  return 0;
+}
+
+extern "C" int wmk_bn_train_bwd_f32(const float* x, const float* y, const float* dy, float* dx, const float* gamma,
+                                    const float* mean_rstd, float* dgamma, float* dbeta, double* scratch, int B, int C,
+                                    int HW, int act, float slope, void* stream) {
+  WMK_REQUIRE(x && y && dy && dx && gamma && mean_rstd && dgamma && dbeta && scratch && B > 0 && C > 0 && HW > 0,
+              "bn_train_bwd: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t total = (size_t)B * C * HW;
+  ProfScope prof(FAM_SMALL, 28.0 * total, st);
+  WMK_CHECK_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * C, st));
+  const size_t per_c = (size_t)B * HW;
+  int chunks = (int)((per_c + 256 * 16 - 1) / (256 * 16));
+  if (chunks > 2048) chunks = 2048;
+  bn_act_bwd_reduce_kernel<<<dim3(chunks, C), 256, 0, st>>>(x, y, dy, mean_rstd, B, C, HW, act, slope, scratch);
+  WMK_CHECK_LAUNCH("bn_act_bwd_reduce_kernel");
+  bn_act_bwd_apply_kernel<<<grid_for(total), 256, 0, st>>>(x, y, dy, dx, mean_rstd, gamma, scratch, total, C, HW,
+                                                           (double)per_c, act, slope, dgamma, dbeta);
+  WMK_CHECK_LAUNCH("bn_act_bwd_apply_kernel");
+  return 0;
+}
+
+extern "C" int wmk_maxpool2x2_bwd_f32(const float* x, const float* dy, float* dx, int planes, int H, int W, void* stream) {
+  WMK_REQUIRE(x && dy && dx && planes > 0 && H >= 2 && W >= 2 && H % 2 == 0 && W % 2 == 0, "maxpool2x2_bwd: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  ProfScope prof(FAM_SMALL, 9.0 * planes * H * W, st);
+  maxpool2x2_bwd_kernel<<<grid_for((size_t)planes * (H / 2) * (W / 2)), 256, 0, st>>>(x, dy, dx, (size_t)planes, H, W);
+  WMK_CHECK_LAUNCH("maxpool2x2_bwd_kernel");
+  return 0;
+}
+
+extern "C" int wmk_mask_scale_f32(const float* in, const float* mask, float* out, size_t n, float scale, void* stream) {
+  WMK_REQUIRE(in && mask && out && n > 0, "mask_scale: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  ProfScope prof(FAM_SMALL, 12.0 * n, st);
+  mask_scale_kernel<<<grid_for(n), 256, 0, st>>>(in, mask, out, n, scale);
+  WMK_CHECK_LAUNCH("mask_scale_kernel");
+  return 0;
+}
+
+extern "C" int wmk_conv3x3_wgrad_f32(const float* x, const float* dy, float* dw, float* db, int B, int Cin, int Cout, int H,
+                                     int W, void* stream) {
+  WMK_REQUIRE(x && dy && dw && B > 0 && B <= 65535 && Cin > 0 && Cout > 0 && H % 16 == 0 && W % 16 == 0,
+              "conv3x3_wgrad: bad arguments (H, W must be multiples of 16)");
+  cudaStream_t st = (cudaStream_t)stream;
+  ProfScope prof(FAM_SMALL, 4.0 * B * H * W * (Cin + Cout), st);
+  WMK_CHECK_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)Cout * Cin * 9, st));
+  if (db) WMK_CHECK_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * Cout, st));
+  const size_t smem = ((size_t)Cin * 18 * 18 + (size_t)Cout * 256) * sizeof(float);
+  WMK_REQUIRE(smem <= 200 * 1024, "conv3x3_wgrad: Cin=%d Cout=%d needs %zu bytes of shared memory", Cin, Cout, smem);
+  const dim3 grid((H / 16) * (W / 16), B);
+  // CB output channels per thread: keep (Cout/CB)*Cin <= 256 thread slots
+  if ((size_t)((Cout + 3) / 4) * Cin <= 256) {
+    if (smem > 48 * 1024) WMK_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv3x3_wgrad_kernel<4><<<grid, 256, smem, st>>>(x, dy, dw, db, Cin, Cout, H, W);
+  } else {
+    WMK_REQUIRE((size_t)((Cout + 15) / 16) * Cin <= 256, "conv3x3_wgrad: Cin=%d x Cout=%d too large", Cin, Cout);
+    if (smem > 48 * 1024) WMK_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv3x3_wgrad_kernel<16><<<grid, 256, smem, st>>>(x, dy, dw, db, Cin, Cout, H, W);
+  }
+  WMK_CHECK_LAUNCH("conv3x3_wgrad_kernel");
+  return 0;
+}
+
+extern "C" int wmk_convT2x2_dgrad_f32(const float* dy, const float* w, float* dx, int B, int Cin, int Cout, int H, int W,
+                                      void* stream) {
+  WMK_REQUIRE(dy && w && dx && B > 0 && Cin > 0 && Cout > 0 && H > 0 && W > 0 && (size_t)Cin * Cout * 16 <= 96 * 1024,
+              "convT2x2_dgrad: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  ProfScope prof(FAM_SMALL, 4.0 * B * H * W * (Cin + 4 * Cout), st);
+  const size_t smem = (size_t)Cin * Cout * 16;
+  if (smem > 48 * 1024) WMK_CHECK_CUDA(cudaFuncSetAttribute(convT2x2_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  convT2x2_dgrad_kernel<<<grid_for((size_t)B * H * W), 256, smem, st>>>(dy, w, dx, B, Cin, Cout, H, W);
+  WMK_CHECK_LAUNCH("convT2x2_dgrad_kernel");
+  return 0;
+}
+
+extern "C" int wmk_convT2x2_wgrad_f32(const float* x, const float* dy, float* dw, float* db, int B, int Cin, int Cout, int H,
+                                      int W, void* stream) {
+  WMK_REQUIRE(x && dy && dw && B > 0 && B <= 65535 && Cin > 0 && Cout > 0 && H % 16 == 0 && W % 16 == 0,
+              "convT2x2_wgrad: bad arguments (H, W must be multiples of 16)");
+  cudaStream_t st = (cudaStream_t)stream;
+  ProfScope prof(FAM_SMALL, 4.0 * B * H * W * (Cin + 4 * Cout), st);
+  WMK_CHECK_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)Cout * Cin * 4, st));
+  if (db) WMK_CHECK_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * Cout, st));
+  const size_t smem = ((size_t)Cin * 256 + (size_t)Cout * 1024) * sizeof(float);
+  WMK_REQUIRE(smem <= 200 * 1024, "convT2x2_wgrad: Cin=%d Cout=%d needs %zu bytes of shared memory", Cin, Cout, smem);
+  if (smem > 48 * 1024) WMK_CHECK_CUDA(cudaFuncSetAttribute(convT2x2_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  convT2x2_wgrad_kernel<<<dim3((H / 16) * (W / 16), B), 256, smem, st>>>(x, dy, dw, db, Cin, Cout, H, W);
+  WMK_CHECK_LAUNCH("convT2x2_wgrad_kernel");
+  return 0;
+}
+
+extern "C" int wmk_mse_f32(const float* a, const float* b, float* grad_a, size_t n, float grad_scale, double* loss_accum,
+                           void* stream) {
+  WMK_REQUIRE(a && b && loss_accum && n > 0, "mse: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  ProfScope prof(FAM_STATS, (grad_a ? 12.0 : 8.0) * n, st);
+  int blocks = grid_for(n);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  mse_kernel<<<blocks, 256, 0, st>>>(a, b, grad_a, n, grad_scale, loss_accum);
+  WMK_CHECK_LAUNCH("mse_kernel");
+  return 0;
+}
+
+extern "C" int wmk_adam_step_f32(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, size_t n, float lr,
+                                 float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
+                                 int decoupled, void* stream) {
+  WMK_REQUIRE(params && grads && exp_avg && exp_avg_sq && n > 0 && step >= 1, "adam_step: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  ProfScope prof(FAM_SMALL, 28.0 * n, st);
+  const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
+  adam_kernel<<<grid_for(n), 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2,
+                                           grad_scale, decoupled);
+  WMK_CHECK_LAUNCH("adam_kernel");
+  return 0;
+}

@@ -232,8 +232,13 @@ class UformerAudio(nn.Module):
 
 class ModelA(nn.Module):
     """Drop-in for the reference CNN baseline `ModelA` (`uformerWM/model.py:3000-3066`): same layer
-    structure and state_dict keys; `forward` / `encode` / `decode` run on libwmk's conv kernels
-    (eval mode: BatchNorm uses running statistics, Dropout is the identity)."""
+    structure and state_dict keys; `forward` / `encode` / `decode` run on libwmk's conv kernels.
+    eval(): BatchNorm uses running statistics, Dropout is the identity, no autograd.
+    train(): BatchNorm uses batch statistics (and updates the running ones), Dropout(0.5) is active and
+    the outputs carry a backward through libwmk's gradient kernels (`cnn_train.py`), so the reference
+    loop of `train_modelA.py:423-500` (`loss.backward()`) runs unchanged.  `dropout_masks` / `attack`
+    are test / benchmark hooks: an injected keep mask, and a differentiable attack between encode and
+    decode (BASELINE config 5 'embed+attack+extract')."""
 
     def __init__(self, in_chans=1):
         super().__init__()
@@ -247,19 +252,26 @@ class ModelA(nn.Module):
             nn.Conv2d(2, 16, 3, padding=1), nn.BatchNorm2d(16), nn.LeakyReLU(0.2), nn.MaxPool2d(2, 2),
             nn.Conv2d(16, 64, 3, padding=1), nn.BatchNorm2d(64), nn.LeakyReLU(0.2), nn.MaxPool2d(2, 2),
             nn.Conv2d(64, 1, 3, padding=1), nn.ReLU())
-        for p in self.parameters():
-            p.requires_grad_(False)
+        self.dropout_masks = None      # optional list of keep masks for the Dropout layer (parity tests)
+        self.attack = None             # optional callable(encoded) -> attacked, applied before decode
 
     def decode(self, x):
-        from . import cnn
+        from . import cnn, cnn_train
+        if self.training:
+            return cnn_train.run_sequential_train(self.detector, x)
         return cnn.run_sequential(self.detector, x)
 
     def encode(self, stft, watermark):
-        from . import cnn
+        from . import cnn, cnn_train
+        if self.training:
+            x = cnn_train.run_sequential_train(self.embedder_encoder, stft)
+            x = torch.cat([x, watermark.to(x.device, torch.float32)], 1)    # model.py:3057
+            return cnn_train.run_sequential_train(self.embedder_decoder, x, self.dropout_masks)
         x = cnn.run_sequential(self.embedder_encoder, stft)
         x = torch.cat([x, watermark.to(x.device, torch.float32)], 1)        # model.py:3057
         return cnn.run_sequential(self.embedder_decoder, x)
 
     def forward(self, stft, watermark):
         encoded_stft = self.encode(stft, watermark)
-        return encoded_stft, self.decode(encoded_stft)
+        attacked = self.attack(encoded_stft) if self.attack is not None else encoded_stft
+        return encoded_stft, self.decode(attacked)

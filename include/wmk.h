@@ -147,6 +147,49 @@ int wmk_convT2x2_f32(const float* x, float* y, const float* w, const float* bias
 int wmk_maxpool2x2_f32(const float* x, float* y, int planes, int H, int W, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Training-mode kernels of ModelA (step: uformerWM/train_modelA.py:402-500, BASELINE config 5).
+ * The data gradient of Conv2d(3x3) is wmk_conv3x3_f32 with the flipped / transposed weights.
+ * ------------------------------------------------------------------------------------------ */
+/* nn.BatchNorm2d in training mode + activation: batch statistics over (B,H,W) per channel,
+ * y = act(gamma * xhat + beta); running_mean / running_var (may be NULL) are updated with
+ * `momentum` and the unbiased variance; mean_rstd [C][2] is saved for the backward pass;
+ * scratch: 2*C doubles. */
+int wmk_bn_train_fwd_f32(const float* x, float* y, const float* gamma, const float* beta,
+                         float* running_mean, float* running_var, float* mean_rstd, double* scratch,
+                         int B, int C, int HW, float eps, float momentum, int act, float slope,
+                         void* stream);
+/* backward of the above through the activation (from its output y) and the normalisation:
+ * dx, dgamma [C], dbeta [C] */
+int wmk_bn_train_bwd_f32(const float* x, const float* y, const float* dy, float* dx, const float* gamma,
+                         const float* mean_rstd, float* dgamma, float* dbeta, double* scratch, int B,
+                         int C, int HW, int act, float slope, void* stream);
+/* MaxPool2d(2,2) backward: x [planes][H][W] is the pooled layer's input, dy [planes][H/2][W/2] */
+int wmk_maxpool2x2_bwd_f32(const float* x, const float* dy, float* dx, int planes, int H, int W,
+                           void* stream);
+/* out = in * mask * scale (nn.Dropout forward / backward with a given keep mask) */
+int wmk_mask_scale_f32(const float* in, const float* mask, float* out, size_t n, float scale,
+                       void* stream);
+/* weight / bias gradients of Conv2d(Cin, Cout, 3, padding=1): dw [Cout][Cin][3][3], db [Cout] or NULL */
+int wmk_conv3x3_wgrad_f32(const float* x, const float* dy, float* dw, float* db, int B, int Cin,
+                          int Cout, int H, int W, void* stream);
+/* ConvTranspose2d(Cin, Cout, 2, stride=2): data gradient dx [B][Cin][H][W] from dy [B][Cout][2H][2W],
+ * and weight / bias gradients dw [Cin][Cout][2][2], db [Cout] or NULL (x is [B][Cin][H][W]) */
+int wmk_convT2x2_dgrad_f32(const float* dy, const float* w, float* dx, int B, int Cin, int Cout, int H,
+                           int W, void* stream);
+int wmk_convT2x2_wgrad_f32(const float* x, const float* dy, float* dw, float* db, int B, int Cin,
+                           int Cout, int H, int W, void* stream);
+/* nn.MSELoss: *loss_accum += mean((a-b)^2) (device double, caller zeroes it); grad_a (may be NULL) =
+ * grad_scale * 2 (a-b) / n */
+int wmk_mse_f32(const float* a, const float* b, float* grad_a, size_t n, float grad_scale,
+                double* loss_accum, void* stream);
+/* torch.optim.Adam (decoupled = 0, weight decay as L2 penalty) / AdamW (decoupled = 1) over a flat
+ * buffer; grads are multiplied by grad_scale first (1 / world size after a sum all-reduce);
+ * step counts from 1 */
+int wmk_adam_step_f32(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, size_t n,
+                      float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                      float grad_scale, int decoupled, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * HiDDeN noise layers (hidden/noise_layers/), `planes` = B*C images of H x W, float32.
  * ------------------------------------------------------------------------------------------ */
 /* Cropout (cropout.py:16-28) with mask_hw == NULL: out = noised inside [h0,h1)x[w0,w1), cover

@@ -36,6 +36,29 @@ class ModelAOracle(nn.Module):
         return e, self.decode(e)
 
 
+def modelA_train_step(model, x, wm, keep_mask, attack_noise=None):
+    """One training forward/backward of `uformerWM/train_modelA.py:423-445` on the CPU with torch autograd:
+    model in train() mode (BatchNorm batch statistics, running-stat update), Dropout(0.5) with the GIVEN
+    keep mask (so that the CUDA path can replay it), optional additive `attack_noise` on the encoded
+    spectrogram before the detector (BASELINE config 5), loss = MSE(target, encoded) + MSE(extracted, wm).
+    Returns dict(encoded, extracted, loss1, loss2, grads{name: tensor})."""
+    model.train()
+    for p in model.parameters():
+        p.grad = None
+    h = model.embedder_encoder(x)
+    h = torch.cat([h, wm], 1)
+    dec = model.embedder_decoder
+    h = dec[2](dec[1](dec[0](h)))                      # ConvT + BN + ReLU
+    h = h * keep_mask * 2.0                            # nn.Dropout(0.5) with an explicit mask
+    enc = dec[6](dec[5](dec[4](h)))                    # ConvT + BN + Sigmoid
+    ext = model.detector(enc if attack_noise is None else enc + attack_noise)
+    loss1 = torch.nn.functional.mse_loss(x, enc)
+    loss2 = torch.nn.functional.mse_loss(ext, wm)
+    (loss1 + loss2).backward()
+    return {"encoded": enc.detach(), "extracted": ext.detach(), "loss1": float(loss1), "loss2": float(loss2),
+            "grads": {n: p.grad.detach().clone() for n, p in model.named_parameters()}}
+
+
 def _cbr(ci, co):
     return nn.Sequential()  # placeholder replaced below (keeps the 'layers.N.layers.M' key structure)
 

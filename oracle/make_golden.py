@@ -143,11 +143,46 @@ def cnn_fixture():
     print("cnn.npz", {k: v.shape for k, v in out.items() if k.startswith("noise_")})
 
 
+def modelA_train_fixture():
+    """One training step of the UNMODIFIED reference ModelA (train mode, nn.Dropout drawn from a seeded torch
+    RNG; the keep mask is recovered from the Dropout module's input/output with a hook - where the input is 0
+    the mask is irrelevant and recorded as 1).  Saves inputs, mask, outputs, losses, all gradients (flat, in
+    named_parameters order) and the updated BatchNorm running statistics."""
+    from oracle import cnn as C
+    ref = shims.import_reference_model()
+    m = C.randomize_(ref.ModelA(), 11)
+    m.train()
+    g = torch.Generator().manual_seed(31)
+    x = torch.rand(4, 2, 128, 128, generator=g)            # the sigmoid output regresses onto [0,1] spectrograms
+    wm = (torch.rand(4, 1, 32, 32, generator=g) > 0.5).float()
+    rec = {}
+
+    def hook(mod, inp, out):
+        rec["mask"] = ((out != 0) | (inp[0] == 0)).float()
+    m.embedder_decoder[3].register_forward_hook(hook)
+    torch.manual_seed(5)
+    enc, ext = m(x, wm)
+    loss1 = torch.nn.MSELoss()(x, enc)                     # train_modelA.py:435
+    loss2 = torch.nn.MSELoss()(ext, wm)                    # :445
+    (loss1 + loss2).backward()
+    names = [n for n, _ in m.named_parameters()]
+    flat = torch.cat([p.grad.reshape(-1) for _, p in m.named_parameters()])
+    out = dict(x=x.numpy(), wm=wm.numpy(), keep_mask=rec["mask"].numpy().astype(np.uint8), encoded=enc.detach().numpy(),
+               extracted=ext.detach().numpy(), loss1=np.float64(loss1.item()), loss2=np.float64(loss2.item()),
+               grads_flat=flat.numpy(), names=np.array(names))
+    for k, v in m.state_dict().items():
+        if "running" in k:
+            out["bn." + k] = v.numpy()
+    np.savez_compressed(os.path.join(OUT, "modelA_train.npz"), **out)
+    print("modelA_train.npz", float(loss1), float(loss2), flat.shape)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
     signal_fixture()
     cnn_fixture()
+    modelA_train_fixture()
     model_fixture("stress", 0)
     model_fixture("reference", 0)
     pipeline_fixture("stress", 0, "awgn-20")
