@@ -158,35 +158,24 @@ mask_scale_kernel(const float* __restrict__ in, const float* __restrict__ mask, 
 
 // ---- weight gradient of Conv2d(Cin, Cout, 3, padding=1):
 //   dw[co][ci][ky][kx] = sum_{b,h,w} x[b][ci][h+ky-1][w+kx-1] dy[b][co][h][w],   db[co] = sum dy[b][co][h][w]
-// One CTA = a 16x16 pixel tile of one image: x tile (+halo) and dy tile in shared memory; a thread owns
-// (pixel subset s, ci, block of CB output channels) = CB x 9 accumulators, loops over its pixels and adds
-// its partial sums to the global gradient with atomics.
+// Persistent CTAs walk 16x16 pixel tiles (all images): x tile (+halo) and dy tile in shared memory; a thread
+// owns (pixel subset s, ci, block of CB output channels) = CB x 9 accumulators that stay in registers
+// across ALL of the CTA's tiles, so the global gradient sees one atomic per accumulator per CTA
+// (a few hundred CTAs) instead of one per tile (tens of thousands: measured 13.5 ms of atomic contention).
 constexpr int WG_T = 16;
 template <int CB>
 __global__ void __launch_bounds__(256)
 conv3x3_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw,
-                     float* __restrict__ db, int Cin, int Cout, int H, int W) {
+                     float* __restrict__ db, int Cin, int Cout, int H, int W, int n_tiles) {
   extern __shared__ float sm[];
   float* xs = sm;                                        // [Cin][18][18]
   float* ds = sm + Cin * (WG_T + 2) * (WG_T + 2);        // [Cout][16][16]
-  const int tiles_w = W / WG_T;
-  const int th = blockIdx.x / tiles_w, tw = blockIdx.x % tiles_w;
-  const int b = blockIdx.y;
-  for (int e = threadIdx.x; e < Cin * (WG_T + 2) * (WG_T + 2); e += 256) {
-    const int ci = e / ((WG_T + 2) * (WG_T + 2)), r = (e / (WG_T + 2)) % (WG_T + 2), c = e % (WG_T + 2);
-    const int hh = th * WG_T + r - 1, ww = tw * WG_T + c - 1;
-    xs[e] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? x[(((size_t)b * Cin + ci) * H + hh) * W + ww] : 0.f;
-  }
-  for (int e = threadIdx.x; e < Cout * WG_T * WG_T; e += 256) {
-    const int co = e / (WG_T * WG_T), r = (e / WG_T) % WG_T, c = e % WG_T;
-    ds[e] = dy[(((size_t)b * Cout + co) * H + th * WG_T + r) * W + tw * WG_T + c];
-  }
-  __syncthreads();
+  const int tiles_w = W / WG_T, tiles_img = tiles_w * (H / WG_T);
   const int n_cb = (Cout + CB - 1) / CB;
   const int pairs = n_cb * Cin;
   const int S = 256 / pairs > 0 ? 256 / pairs : 1;       // pixel subsets
   const int pair = threadIdx.x % pairs, s = threadIdx.x / pairs;
-  if (s >= S || threadIdx.x >= pairs * S) return;
+  const bool worker = s < S && threadIdx.x < pairs * S;
   const int ci = pair % Cin, cb = pair / Cin;
   float acc[CB][9], bsum[CB];
 #pragma unroll
@@ -195,20 +184,37 @@ conv3x3_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, 
 #pragma unroll
     for (int t = 0; t < 9; ++t) acc[j][t] = 0.f;
   }
-  for (int p = s; p < WG_T * WG_T; p += S) {
-    const int r = p / WG_T, c = p % WG_T;
-    float xv[9];
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int b = tile / tiles_img, trem = tile - b * tiles_img;
+    const int th = trem / tiles_w, tw = trem - th * tiles_w;
+    __syncthreads();                                     // the previous tile has been consumed
+    for (int e = threadIdx.x; e < Cin * (WG_T + 2) * (WG_T + 2); e += 256) {
+      const int cc = e / ((WG_T + 2) * (WG_T + 2)), r = (e / (WG_T + 2)) % (WG_T + 2), c = e % (WG_T + 2);
+      const int hh = th * WG_T + r - 1, ww = tw * WG_T + c - 1;
+      xs[e] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? x[(((size_t)b * Cin + cc) * H + hh) * W + ww] : 0.f;
+    }
+    for (int e = threadIdx.x; e < Cout * WG_T * WG_T; e += 256) {
+      const int co = e / (WG_T * WG_T), r = (e / WG_T) % WG_T, c = e % WG_T;
+      ds[e] = dy[(((size_t)b * Cout + co) * H + th * WG_T + r) * W + tw * WG_T + c];
+    }
+    __syncthreads();
+    if (!worker) continue;
+    for (int p = s; p < WG_T * WG_T; p += S) {
+      const int r = p / WG_T, c = p % WG_T;
+      float xv[9];
 #pragma unroll
-    for (int t = 0; t < 9; ++t) xv[t] = xs[(ci * (WG_T + 2) + r + t / 3) * (WG_T + 2) + c + t % 3];
+      for (int t = 0; t < 9; ++t) xv[t] = xs[(ci * (WG_T + 2) + r + t / 3) * (WG_T + 2) + c + t % 3];
 #pragma unroll
-    for (int j = 0; j < CB; ++j) {
-      const int co = cb * CB + j;
-      const float d = co < Cout ? ds[co * WG_T * WG_T + p] : 0.f;
-      bsum[j] += d;
+      for (int j = 0; j < CB; ++j) {
+        const int co = cb * CB + j;
+        const float d = co < Cout ? ds[co * WG_T * WG_T + p] : 0.f;
+        bsum[j] += d;
 #pragma unroll
-      for (int t = 0; t < 9; ++t) acc[j][t] = fmaf(xv[t], d, acc[j][t]);
+        for (int t = 0; t < 9; ++t) acc[j][t] = fmaf(xv[t], d, acc[j][t]);
+      }
     }
   }
+  if (!worker) return;
 #pragma unroll
   for (int j = 0; j < CB; ++j) {
     const int co = cb * CB + j;
@@ -244,39 +250,56 @@ convT2x2_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w,
 }
 
 // weight gradient: dw[ci][co][i][j] = sum_{b,h,w} x[b][ci][h][w] dy[b][co][2h+i][2w+j];  db[co] = sum dy
-// One CTA = a 16x16 input tile of one image; a thread owns (pixel subset, ci, co) = 4 accumulators.
+// Persistent CTAs walk 16x16 input tiles; a thread owns up to 3 (ci, co) pairs = 4 accumulators each, kept in
+// registers across all of the CTA's tiles (one atomic per accumulator per CTA).
+constexpr int TW_PAIRS = 3;        // pairs per thread: Cin * Cout <= 768
 __global__ void __launch_bounds__(256)
 convT2x2_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw,
-                      float* __restrict__ db, int Cin, int Cout, int H, int W) {
+                      float* __restrict__ db, int Cin, int Cout, int H, int W, int n_tiles) {
   extern __shared__ float sm[];
   float* xs = sm;                              // [Cin][256]
   float* ds = sm + Cin * 256;                  // [Cout][32][32]
-  const int tiles_w = W / 16;
-  const int th = blockIdx.x / tiles_w, tw = blockIdx.x % tiles_w;
-  const int b = blockIdx.y;
-  for (int e = threadIdx.x; e < Cin * 256; e += 256) {
-    const int ci = e >> 8, r = (e >> 4) & 15, c = e & 15;
-    xs[e] = x[(((size_t)b * Cin + ci) * H + th * 16 + r) * W + tw * 16 + c];
-  }
-  for (int e = threadIdx.x; e < Cout * 1024; e += 256) {
-    const int co = e >> 10, r = (e >> 5) & 31, c = e & 31;
-    ds[e] = dy[(((size_t)b * Cout + co) * (2 * H) + th * 32 + r) * (size_t)(2 * W) + tw * 32 + c];
-  }
-  __syncthreads();
+  const int tiles_w = W / 16, tiles_img = tiles_w * (H / 16);
   const int pairs = Cin * Cout;
-  for (int pair = threadIdx.x; pair < pairs; pair += 256) {
-    const int ci = pair / Cout, co = pair % Cout;
-    float a[4] = {0.f, 0.f, 0.f, 0.f}, bs = 0.f;
-    for (int p = 0; p < 256; ++p) {
-      const int r = p >> 4, c = p & 15;
-      const float xv = xs[ci * 256 + p];
-      const float* d = ds + co * 1024 + (2 * r) * 32 + 2 * c;
-      a[0] = fmaf(xv, d[0], a[0]); a[1] = fmaf(xv, d[1], a[1]); a[2] = fmaf(xv, d[32], a[2]); a[3] = fmaf(xv, d[33], a[3]);
-      bs += (d[0] + d[1]) + (d[32] + d[33]);
-    }
+  float a[TW_PAIRS][4], bs[TW_PAIRS];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) atomicAdd(dw + ((size_t)ci * Cout + co) * 4 + k, a[k]);
-    if (ci == 0 && db) atomicAdd(db + co, bs);
+  for (int q = 0; q < TW_PAIRS; ++q) { a[q][0] = a[q][1] = a[q][2] = a[q][3] = 0.f; bs[q] = 0.f; }
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int b = tile / tiles_img, trem = tile - b * tiles_img;
+    const int th = trem / tiles_w, tw = trem - th * tiles_w;
+    __syncthreads();
+    for (int e = threadIdx.x; e < Cin * 256; e += 256) {
+      const int ci = e >> 8, r = (e >> 4) & 15, c = e & 15;
+      xs[e] = x[(((size_t)b * Cin + ci) * H + th * 16 + r) * W + tw * 16 + c];
+    }
+    for (int e = threadIdx.x; e < Cout * 1024; e += 256) {
+      const int co = e >> 10, r = (e >> 5) & 31, c = e & 31;
+      ds[e] = dy[(((size_t)b * Cout + co) * (2 * H) + th * 32 + r) * (size_t)(2 * W) + tw * 32 + c];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < TW_PAIRS; ++q) {
+      const int pair = threadIdx.x + q * 256;
+      if (pair >= pairs) break;
+      const int ci = pair / Cout, co = pair % Cout;
+      for (int p = 0; p < 256; ++p) {
+        const int r = p >> 4, c = p & 15;
+        const float xv = xs[ci * 256 + p];
+        const float* d = ds + co * 1024 + (2 * r) * 32 + 2 * c;
+        a[q][0] = fmaf(xv, d[0], a[q][0]); a[q][1] = fmaf(xv, d[1], a[q][1]);
+        a[q][2] = fmaf(xv, d[32], a[q][2]); a[q][3] = fmaf(xv, d[33], a[q][3]);
+        bs[q] += (d[0] + d[1]) + (d[32] + d[33]);
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < TW_PAIRS; ++q) {
+    const int pair = threadIdx.x + q * 256;
+    if (pair >= pairs) break;
+    const int ci = pair / Cout, co = pair % Cout;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) atomicAdd(dw + ((size_t)ci * Cout + co) * 4 + k, a[q][k]);
+    if (ci == 0 && db) atomicAdd(db + co, bs[q]);
   }
 }
 
@@ -386,7 +409,7 @@ extern "C" int wmk_mask_scale_f32(const float* in, const float* mask, float* out
 
 extern "C" int wmk_conv3x3_wgrad_f32(const float* x, const float* dy, float* dw, float* db, int B, int Cin, int Cout, int H,
                                      int W, void* stream) {
-  WMK_REQUIRE(x && dy && dw && B > 0 && B <= 65535 && Cin > 0 && Cout > 0 && H % 16 == 0 && W % 16 == 0,
+  WMK_REQUIRE(x && dy && dw && B > 0 && Cin > 0 && Cout > 0 && H % 16 == 0 && W % 16 == 0,
               "conv3x3_wgrad: bad arguments (H, W must be multiples of 16)");
   cudaStream_t st = (cudaStream_t)stream;
   ProfScope prof(FAM_SMALL, 4.0 * B * H * W * (Cin + Cout), st);
@@ -394,15 +417,18 @@ extern "C" int wmk_conv3x3_wgrad_f32(const float* x, const float* dy, float* dw,
   if (db) WMK_CHECK_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * Cout, st));
   const size_t smem = ((size_t)Cin * 18 * 18 + (size_t)Cout * 256) * sizeof(float);
   WMK_REQUIRE(smem <= 200 * 1024, "conv3x3_wgrad: Cin=%d Cout=%d needs %zu bytes of shared memory", Cin, Cout, smem);
-  const dim3 grid((H / 16) * (W / 16), B);
+  const int n_tiles = (H / 16) * (W / 16) * B;
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  const int grid = n_tiles < 2 * sms ? n_tiles : 2 * sms;
   // CB output channels per thread: keep (Cout/CB)*Cin <= 256 thread slots
   if ((size_t)((Cout + 3) / 4) * Cin <= 256) {
     if (smem > 48 * 1024) WMK_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conv3x3_wgrad_kernel<4><<<grid, 256, smem, st>>>(x, dy, dw, db, Cin, Cout, H, W);
+    conv3x3_wgrad_kernel<4><<<grid, 256, smem, st>>>(x, dy, dw, db, Cin, Cout, H, W, n_tiles);
   } else {
     WMK_REQUIRE((size_t)((Cout + 15) / 16) * Cin <= 256, "conv3x3_wgrad: Cin=%d x Cout=%d too large", Cin, Cout);
     if (smem > 48 * 1024) WMK_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conv3x3_wgrad_kernel<16><<<grid, 256, smem, st>>>(x, dy, dw, db, Cin, Cout, H, W);
+    conv3x3_wgrad_kernel<16><<<grid, 256, smem, st>>>(x, dy, dw, db, Cin, Cout, H, W, n_tiles);
   }
   WMK_CHECK_LAUNCH("conv3x3_wgrad_kernel");
   return 0;
@@ -431,8 +457,13 @@ extern "C" int wmk_convT2x2_wgrad_f32(const float* x, const float* dy, float* dw
   if (db) WMK_CHECK_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * Cout, st));
   const size_t smem = ((size_t)Cin * 256 + (size_t)Cout * 1024) * sizeof(float);
   WMK_REQUIRE(smem <= 200 * 1024, "convT2x2_wgrad: Cin=%d Cout=%d needs %zu bytes of shared memory", Cin, Cout, smem);
+  WMK_REQUIRE(Cin * Cout <= 256 * TW_PAIRS, "convT2x2_wgrad: Cin*Cout=%d exceeds %d", Cin * Cout, 256 * TW_PAIRS);
+  const int n_tiles = (H / 16) * (W / 16) * B;
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  const int grid = n_tiles < 2 * sms ? n_tiles : 2 * sms;
   if (smem > 48 * 1024) WMK_CHECK_CUDA(cudaFuncSetAttribute(convT2x2_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  convT2x2_wgrad_kernel<<<dim3((H / 16) * (W / 16), B), 256, smem, st>>>(x, dy, dw, db, Cin, Cout, H, W);
+  convT2x2_wgrad_kernel<<<grid, 256, smem, st>>>(x, dy, dw, db, Cin, Cout, H, W, n_tiles);
   WMK_CHECK_LAUNCH("convT2x2_wgrad_kernel");
   return 0;
 }

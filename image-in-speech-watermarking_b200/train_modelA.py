@@ -22,6 +22,17 @@ def gaussian_attack(std, generator=None):
     return attack
 
 
+def sync_gradients(flat_grad):
+    """Sum the flat gradient buffer over the ranks (one collective); returns the world size (the mean
+    is taken by the Adam kernel's grad_scale)."""
+    world = 1
+    if dist.is_available() and dist.is_initialized():
+        world = dist.get_world_size()
+        if world > 1:
+            dist.all_reduce(flat_grad)
+    return world
+
+
 def train_step(model, optimizer, input_, message, loss_scale=1.0):
     """One optimisation step on this rank's batch; returns (loss, loss1, loss2) as python floats' device tensors.
     `optimizer` is a `cnn_train.FlatAdam`.  `loss_scale` plays NativeScaler's static role (the scaled
@@ -34,11 +45,6 @@ def train_step(model, optimizer, input_, message, loss_scale=1.0):
     loss2 = cnn_train.mse_loss(wm_decode, message)
     loss = loss1 + loss2
     (loss * loss_scale).backward()
-    grad = optimizer.gather_grads()
-    world = 1
-    if dist.is_available() and dist.is_initialized():
-        world = dist.get_world_size()
-        if world > 1:
-            dist.all_reduce(grad)                      # sum of the ranks' gradients (mean taken in the Adam kernel)
+    world = sync_gradients(optimizer.gather_grads())
     optimizer.step(grad_scale=1.0 / (loss_scale * world))
     return loss.detach(), loss1.detach(), loss2.detach()

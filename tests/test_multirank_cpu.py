@@ -26,6 +26,10 @@ def _shard(n_utt, rank, world):
 def _worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
+    # data-parallel training step: ONE all-reduce of the flat gradient buffer (train_modelA.sync_gradients)
+    from image_in_speech_watermarking_b200 import train_modelA as TM
+    flat = torch.full((17655,), float(rank + 1))
+    assert TM.sync_gradients(flat) == world and torch.all(flat == sum(range(1, world + 1)))
     g = torch.Generator().manual_seed(0)
     per_utt = torch.rand(10, 7, generator=g, dtype=torch.float64)          # same table on every rank
     mine = _shard(10, rank, world)
