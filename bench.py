@@ -294,8 +294,16 @@ def run_ours(args):
     both = [r for r in (r_hbm, r_tc) if r]
     both.sort(key=lambda r: -r["share_of_step"])
     roofline = dict(both[0]) if both else {"bound": "tensor", "achieved": 0.0, "peak": peak_tf, "unit": "TFLOP/s", "frac": 0.0}
-    roofline.update({"kernel": kname, "peak_source": src, "traffic": None, "family_ms_per_step": step_ms_families,
-                     "profiled_step_ms": ms_profiled})
+    traffic, traffic_src = None, None
+    try:                # dram__bytes_read + dram__bytes_write per launch of the dense-layer kernel, from the committed ncu pass
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        traffic = tj["families"]["gemm"]["dram_bytes_per_launch"]
+        traffic_src = "profiles/r01_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean over the %d dense-layer " \
+                      "launches of one 64 x 3 s step, both roofline classes)" % tj["families"]["gemm"]["launches"]
+    except Exception:
+        pass
+    roofline.update({"kernel": kname, "peak_source": src, "traffic": traffic, "traffic_source": traffic_src,
+                     "family_ms_per_step": step_ms_families, "profiled_step_ms": ms_profiled})
     if len(both) > 1:
         roofline["roofline_other"] = both[1]
     gm = fam["gemm"]["ms"] + fam["gemm_hbm"]["ms"]
