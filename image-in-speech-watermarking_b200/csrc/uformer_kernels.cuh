@@ -260,27 +260,36 @@ __device__ __forceinline__ void att_row(const AttGeom& g, int win, int r, int& t
   region = rh * 3 + rw;
 }
 
-// Persistent: each CTA loops over (window, head) items (heads fastest) and prefetches the next
-// item's q/k/v tiles with cp.async while the tensor cores work on the current one.
-// Scores arrive in the log2 domain: the packed q rows and the bias table carry a factor log2(e)
-// (uformer_plan.cu pack_block), so softmax is exp2(s - max) with one FADD + one MUFU.EX2 per score.
+// Persistent: a CTA owns ONE head (blockIdx.x % heads) and loops over windows, prefetching the next
+// window's q/k/v tiles with cp.async while the tensor cores work on the current one.
+//  * The head's 64x64 relative-position bias sits in shared memory as bf16 (loaded once per CTA) and is
+//    added by the tensor cores: S = I * Bias + Q K^T (one extra k-step with an identity A fragment)
+//    instead of 16 global loads + 32 FADDs per thread per window (the kernel was L1/TEX bound on them).
+//  * Scores arrive in the log2 domain: the packed q rows and the bias table carry a factor log2(e)
+//    (uformer_plan.cu pack_block), so softmax is exp2(s - max) with one FADD + one MUFU.EX2 per score.
+//  * The shift mask only exists in windows of the last window row / column: all others skip it.
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 constexpr float kLog2e = 1.4426950408889634f;
+constexpr int ATT_BLD = 72;    // bf16 elements per bias row in smem (144 B: conflict-free ldmatrix)
+
 static __global__ void __launch_bounds__(128)
 window_attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
-                            const float* __restrict__ bias, int C, int H, int shift, int n_items) {
+                            const float* __restrict__ bias, int C, int H, int shift, int n_windows) {
   __shared__ __align__(16) __nv_bfloat16 sbuf[2][3 * ATT_TILE];
+  __shared__ __align__(16) __nv_bfloat16 sbias[64 * ATT_BLD];
   __shared__ int s_tok[2][64], s_rid[2][64];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   AttGeom g{C, H, shift, 31 - __clz(C >> 5), 31 - __clz(H >> 3)};
-  const int head_mask = (C >> 5) - 1;
+  const int heads = C >> 5;
+  const int head = blockIdx.x & (heads - 1);
+  const int wstep = gridDim.x >> g.lg_heads;
+  const int nws_mask = (1 << g.lg_nws) - 1;
 
-  auto prefetch = [&](int item, int buf) {
-    const int head = item & head_mask, win = item >> g.lg_heads;
+  auto prefetch = [&](int win, int buf) {
     if (tid < 64) {
       int t, r;
       att_row(g, win, tid, t, r);
@@ -303,29 +312,48 @@ window_attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
 
-  int item = blockIdx.x;
-  if (item >= n_items) return;
-  prefetch(item, 0);
-  for (int it = 0; item < n_items; item += gridDim.x, ++it) {
+  int win = blockIdx.x >> g.lg_heads;
+  if (win >= n_windows) return;
+  prefetch(win, 0);
+  {
+    const float* bh = bias + (size_t)head * 4096;
+    for (int e = tid; e < 2048; e += 128) {
+      const float2 v = __ldg(reinterpret_cast<const float2*>(bh) + e);
+      *reinterpret_cast<uint32_t*>(&sbias[(e >> 5) * ATT_BLD + (e & 31) * 2]) = pack_bf16(v.x, v.y);
+    }
+  }
+  const int gq = lane >> 2, t = lane & 3;
+  // identity A fragment (16x16): thread (gq, t) holds A[gq][2t..2t+1] and A[gq+8][2t+8..2t+9]
+  const uint32_t ident = pack_bf16(gq == 2 * t ? 1.f : 0.f, gq == 2 * t + 1 ? 1.f : 0.f);
+  const uint32_t aI[4] = {ident, 0u, 0u, ident};
+  const uint32_t bs_addr = (uint32_t)__cvta_generic_to_shared(sbias);
+  for (int it = 0; win < n_windows; win += wstep, ++it) {
     const int buf = it & 1;
-    const int next = item + gridDim.x;
-    if (next < n_items) {
+    const int next = win + wstep;
+    if (next < n_windows) {
       prefetch(next, buf ^ 1);
       asm volatile("cp.async.wait_group 1;" ::: "memory");
     } else {
       asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
-    const int head = item & head_mask;
     __nv_bfloat16* Qs = &sbuf[buf][0];
     const int* tok = s_tok[buf];
     const int* rid = s_rid[buf];
     const uint32_t qs = (uint32_t)__cvta_generic_to_shared(Qs), ks = qs + 2u * ATT_TILE, vs = qs + 4u * ATT_TILE;
     const int r0 = warp * 16;
-    // ---- S = Q K^T
+    // ---- S = I * Bias  (rows r0..r0+15 of the bias as the B operand)
     float sacc[8][4];
 #pragma unroll
     for (int n = 0; n < 8; ++n) { sacc[n][0] = sacc[n][1] = sacc[n][2] = sacc[n][3] = 0.f; }
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {
+      uint32_t bb[4];
+      ldmatrix_x4_trans(bb, bs_addr + 2u * ((r0 + (lane & 7) + ((lane >> 3) & 1) * 8) * ATT_BLD + np * 16 + (lane >> 4) * 8));
+      mma_bf16_16816(sacc[2 * np], aI, bb[0], bb[1]);
+      mma_bf16_16816(sacc[2 * np + 1], aI, bb[2], bb[3]);
+    }
+    // ---- S += Q K^T
 #pragma unroll
     for (int kk = 0; kk < 2; ++kk) {
       uint32_t a[4];
@@ -338,25 +366,25 @@ window_attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16
         mma_bf16_16816(sacc[2 * np + 1], a, bq[2], bq[3]);
       }
     }
-    // ---- + relative-position bias (+ shift mask), softmax over the 64 keys of each row
-    const int gq = lane >> 2, t = lane & 3;
+    // ---- shift mask (only windows of the last window row / column hold more than one region), softmax
     const int row0 = r0 + gq, row1 = row0 + 8;
-    const float* bh = bias + (size_t)head * 4096;
-    const int rid0 = rid[row0], rid1 = rid[row1];
+    const int wrem = win & ((1 << (2 * g.lg_nws)) - 1);
+    const bool edge = shift > 0 && (((wrem >> g.lg_nws) == nws_mask) || ((wrem & nws_mask) == nws_mask));
     float m0 = -INFINITY, m1 = -INFINITY;
+    if (edge) {
+      const int rid0 = rid[row0], rid1 = rid[row1];
 #pragma unroll
-    for (int n = 0; n < 8; ++n) {
-      const int col = n * 8 + 2 * t;
-      const float2 b0 = __ldg(reinterpret_cast<const float2*>(bh + row0 * 64 + col));
-      const float2 b1 = __ldg(reinterpret_cast<const float2*>(bh + row1 * 64 + col));
-      sacc[n][0] += b0.x; sacc[n][1] += b0.y; sacc[n][2] += b1.x; sacc[n][3] += b1.y;
-      if (shift > 0) {
+      for (int n = 0; n < 8; ++n) {
+        const int col = n * 8 + 2 * t;
         const int c0 = rid[col], c1 = rid[col + 1];
         if (c0 != rid0) sacc[n][0] -= 100.0f * kLog2e;
         if (c1 != rid0) sacc[n][1] -= 100.0f * kLog2e;
         if (c0 != rid1) sacc[n][2] -= 100.0f * kLog2e;
         if (c1 != rid1) sacc[n][3] -= 100.0f * kLog2e;
       }
+    }
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
       m0 = fmaxf(m0, fmaxf(sacc[n][0], sacc[n][1]));
       m1 = fmaxf(m1, fmaxf(sacc[n][2], sacc[n][3]));
     }

@@ -281,9 +281,11 @@ int run_block(wmk_plan* P, const BlockW& w, float* x, int n, cudaStream_t st) {
     ProfScope prof(FAM_ATTENTION, 256.0 * C * M, st);
     if constexpr (sizeof(OpT) == 2)
     {
-      const int items = n * (H / 8) * (H / 8) * w.heads;
-      const int grid = items < 148 * 6 ? items : 148 * 6;
-      window_attention_mma_kernel<<<grid, 128, 0, st>>>(QKV, O, w.attn_bias, C, H, w.shift, items);
+      const int n_windows = n * (H / 8) * (H / 8);
+      int per_head = (148 * 5) / w.heads;                 // CTAs per head (5 resident CTAs per SM)
+      if (per_head > n_windows) per_head = n_windows;
+      if (per_head < 1) per_head = 1;
+      window_attention_mma_kernel<<<per_head * w.heads, 128, 0, st>>>(QKV, O, w.attn_bias, C, H, w.shift, n_windows);
     }
     else
       window_attention_kernel<OpT><<<dim3(n * (H / 8) * (H / 8), w.heads), 128, 0, st>>>(QKV, O, w.attn_bias, C, H, w.shift);
