@@ -583,6 +583,9 @@ int gemm_bf16_tcgen05(const GemmArgs& g, cudaStream_t st) {
     const bool wide_ok = g.epi != EPI_BIAS_RESID || g.K >= 1024;   // fp32 residual tiles: one 32-column piece per warp
     if (g.N % 256 == 0 && g.N >= 256 && wide_ok) return launch_persistent<256>(g, st);
     if (g.N % 128 == 0) return launch_persistent<128>(g, st);
+    // N = 96 / 192 (the fused q|k|v projection of the C = 32 / 64 stages): one / two 96-wide tiles instead of three
+    // 32- / 64-wide ones (A is fetched once, 12 of the 16 epilogue warps work instead of 4 / 8)
+    if (g.N % 96 == 0 && g.epi == EPI_BIAS) return launch_persistent<96>(g, st);
     if (g.N % 64 == 0) return launch_persistent<64>(g, st);
     return launch_persistent<32>(g, st);
   }
