@@ -189,11 +189,17 @@ __host__ __device__ constexpr int epi_box_cols(int bn, bool out_bf16) {
   return out_bf16 ? (epi_cpw(bn) >= 64 ? 64 : 32) : 32;
 }
 
-template <int BN, int EPI, bool OUT_BF16>
+// LN = true (EPI_BIAS_RESID, BN <= 128, n_tiles == 1): the epilogue also LayerNorms the finished row and writes
+// it as bf16 through tmD - the operand of the next dense layer.  The SLABS warps that share a lane quarter
+// exchange their partial (sum, sum of squares) through shared memory and a named barrier.
+constexpr uint32_t STG2_BYTES = 2048;                       // bf16 staging box of the fused LayerNorm: 32 rows x 64 B
+constexpr uint32_t LN_EXCH_BYTES = 2 * kEpiWarps * 32 * 8;  // [tile parity][slab][quarter][lane] float2
+
+template <int BN, int EPI, bool OUT_BF16, bool LN = false>
 __global__ void __launch_bounds__(kPThreads, 1)
 gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-                               const __grid_constant__ CUtensorMap tmC, EpiParams p, int K, int m_tiles,
-                               int n_tiles, int n_stages, int w_stationary) {
+                               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmD,
+                               EpiParams p, int K, int m_tiles, int n_tiles, int n_stages, int w_stationary) {
   // w_stationary: the CTA keeps its whole BN x K weight tile resident in shared memory and walks
   // down the M tiles of one N tile, so only A streams from L2 (for K <= 256 the weight tile would
   // otherwise be re-fetched for every output tile and the L2 -> SM path becomes the bound).
@@ -208,7 +214,9 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __
   const uint32_t stages = base + (w_stationary ? (uint32_t)kblocks * W_BYTES : 0u);
   constexpr uint32_t STG_BYTES = 4096;                      // one staging box: 32 rows x <=128 B
   const uint32_t staging = stages + (uint32_t)n_stages * STAGE;          // [16 warps][4096]
-  const uint32_t bars = staging + kEpiWarps * STG_BYTES;
+  const uint32_t staging2 = staging + kEpiWarps * STG_BYTES;             // LN: [16 warps][2048] + exchange
+  const uint32_t ln_exch = staging2 + kEpiWarps * STG2_BYTES;
+  const uint32_t bars = LN ? ln_exch + LN_EXCH_BYTES : staging + kEpiWarps * STG_BYTES;
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (n_stages + s); };
   const uint32_t tfull_bar = bars + 16u * n_stages;         // [2]
@@ -244,6 +252,7 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
+    if (LN) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmD) : "memory");
     mbar_init(wfull_bar, 1);
     for (int s = 0; s < n_stages; ++s) {
       mbar_init(full_bar(s), 1);
@@ -403,6 +412,56 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) tma_store_2d(&tmC, buf, n, m0 + q * 32);
+            if constexpr (LN) {
+              // ---- fused LayerNorm of the finished rows (this warp holds 32 of the BN columns of row `row`)
+              float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) { s1 += f[j]; s2 = fmaf(f[j], f[j], s2); }
+              if constexpr (SLABS > 1) {
+                float2* ex = reinterpret_cast<float2*>(smem_raw + (ln_exch - raw));
+                const int par = lt & 1;
+                ex[((par * 4 + slab) * 4 + q) * 32 + lane] = make_float2(s1, s2);
+                asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "r"(SLABS * 32) : "memory");
+                s1 = 0.f; s2 = 0.f;
+#pragma unroll
+                for (int sb = 0; sb < SLABS; ++sb) {
+                  const float2 e2 = ex[((par * 4 + sb) * 4 + q) * 32 + lane];
+                  s1 += e2.x; s2 += e2.y;
+                }
+              }
+              const float mean = s1 * (1.0f / BN);
+              const float rstd = rsqrtf(fmaxf(s2 * (1.0f / BN) - mean * mean, 0.f) + 1e-5f);
+              const float* modrow = nullptr;
+              if (p.ln_mod) {
+                const int Hm = p.ln_H - 1, lgH = 31 - __clz(p.ln_H);
+                const int hw = row & (p.ln_H * p.ln_H - 1);
+                const int hs = ((hw >> lgH) - p.ln_shift) & Hm, ws = ((hw & Hm) - p.ln_shift) & Hm;
+                modrow = p.ln_mod + (size_t)(((hs & 7) << 3) | (ws & 7)) * BN + n;
+              }
+              const float4* g4 = reinterpret_cast<const float4*>(p.ln_gamma + n);
+              const float4* be4 = reinterpret_cast<const float4*>(p.ln_beta + n);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 gg = __ldg(g4 + j), bb = __ldg(be4 + j);
+                f[4 * j] = fmaf((f[4 * j] - mean) * rstd, gg.x, bb.x);
+                f[4 * j + 1] = fmaf((f[4 * j + 1] - mean) * rstd, gg.y, bb.y);
+                f[4 * j + 2] = fmaf((f[4 * j + 2] - mean) * rstd, gg.z, bb.z);
+                f[4 * j + 3] = fmaf((f[4 * j + 3] - mean) * rstd, gg.w, bb.w);
+                if (modrow) {
+                  const float4 mm = __ldg(reinterpret_cast<const float4*>(modrow) + j);
+                  f[4 * j] += mm.x; f[4 * j + 1] += mm.y; f[4 * j + 2] += mm.z; f[4 * j + 3] += mm.w;
+                }
+              }
+              const uint32_t buf2 = staging2 + (uint32_t)ew * STG2_BYTES;     // free: every earlier store was waited for above
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                st_shared_v4(buf2 + (uint32_t)lane * 64u + ((((uint32_t)j) ^ ((uint32_t)(lane >> 1) & 3u)) << 4),
+                             pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                             pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+              asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+              __syncwarp();
+              if (lane == 0) tma_store_2d(&tmD, buf2, n, m0 + q * 32);
+            }
           }
         }
         // all tcgen05.ld of this accumulator have completed (tmem_ld32 waits): hand it back
@@ -495,14 +554,16 @@ int make_map(CUtensorMap* map, const void* ptr, int rows, int K, int box_rows) {
   return make_map_ex(map, ptr, rows, K, box_rows, BK, false);
 }
 
-template <int BN, int EPI, bool OUT_BF16>
+template <int BN, int EPI, bool OUT_BF16, bool LN = false>
 int launch_persistent_t(const GemmArgs& g, cudaStream_t st) {
-  CUtensorMap tmA, tmW, tmC;
+  CUtensorMap tmA, tmW, tmC, tmD;
   WMK_TRY(make_map(&tmA, g.A, g.M, g.K, BM));
   WMK_TRY(make_map(&tmW, g.W, g.N, g.K, BN));
   WMK_TRY(make_map_ex(&tmC, g.C, g.M, g.ldc, 32, epi_box_cols(BN, OUT_BF16), !OUT_BF16));
+  if (LN) WMK_TRY(make_map_ex(&tmD, g.ln_out, g.M, g.N, 32, 32, false));
+  else tmD = tmC;
   const int kblocks = cdiv(g.K, BK);
-  constexpr int fixed = kEpiWarps * 4096 + 1024 + 256;
+  constexpr int fixed = kEpiWarps * 4096 + 1024 + 256 + (LN ? (int)(kEpiWarps * STG2_BYTES + LN_EXCH_BYTES) : 0);
   constexpr int budget = 226 * 1024;
   const int n_tiles = g.N / BN, m_tiles = cdiv(g.M, BM);
   const int w_bytes = kblocks * BN * BK * 2;
@@ -516,15 +577,16 @@ int launch_persistent_t(const GemmArgs& g, cudaStream_t st) {
   const size_t smem = (size_t)n_stages * stage + (ws ? w_bytes : 0) + fixed;
   static bool attr_set = false;
   if (!attr_set) {
-    WMK_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_persistent_kernel<BN, EPI, OUT_BF16>,
+    WMK_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_persistent_kernel<BN, EPI, OUT_BF16, LN>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   EpiParams p{g.bias, g.resid, g.C, g.M, g.N, g.ldc, g.epi, g.out_bf16, g.up_h, g.up_w, g.up_cout};
+  p.ln_gamma = g.ln_gamma; p.ln_beta = g.ln_beta; p.ln_mod = g.ln_mod; p.ln_H = g.ln_H; p.ln_shift = g.ln_shift;
   const long long total = (long long)m_tiles * n_tiles;
   const int grid = ws ? (num_sms() / n_tiles) * n_tiles : (int)(total < num_sms() ? total : num_sms());
-  gemm_tcgen05_persistent_kernel<BN, EPI, OUT_BF16><<<grid, kPThreads, smem, st>>>(tmA, tmW, tmC, p, g.K, m_tiles,
-                                                                                   n_tiles, n_stages, ws);
+  gemm_tcgen05_persistent_kernel<BN, EPI, OUT_BF16, LN><<<grid, kPThreads, smem, st>>>(tmA, tmW, tmC, tmD, p, g.K, m_tiles,
+                                                                                       n_tiles, n_stages, ws);
   WMK_CHECK_LAUNCH("gemm_tcgen05_persistent_kernel");
   return 0;
 }
@@ -536,7 +598,18 @@ int launch_persistent(const GemmArgs& g, cudaStream_t st) {
     set_error("gemm_bf16: the GELU epilogue writes bf16 only");
     return WMK_ERR_UNSUPPORTED;
   }
-  if (g.epi == EPI_BIAS_RESID) return launch_persistent_t<BN, EPI_BIAS_RESID, false>(g, st);
+  if (g.epi == EPI_BIAS_RESID) {
+    if constexpr (BN <= 128) {
+      if (g.ln_out) {
+        if (g.N != BN || !g.ln_gamma || !g.ln_beta || (g.ln_mod && (g.ln_H & (g.ln_H - 1)))) {
+          set_error("gemm_bf16: fused LayerNorm needs N == tile width (%d), gamma/beta and a power-of-two H", BN);
+          return WMK_ERR_ARG;
+        }
+        return launch_persistent_t<BN, EPI_BIAS_RESID, false, true>(g, st);
+      }
+    }
+    return launch_persistent_t<BN, EPI_BIAS_RESID, false>(g, st);
+  }
   if (g.out_bf16) return launch_persistent_t<BN, EPI_BIAS, true>(g, st);
   return launch_persistent_t<BN, EPI_BIAS, false>(g, st);
 }

@@ -8,6 +8,7 @@
 // Weights are packed once: every nn.Linear / conv-as-GEMM weight as a K-major [N][K] matrix in
 // OpT, q/k/v fused into one [3C][C] matrix with the attention scale folded into the q rows, the
 // relative-position bias gathered to [heads][64][64], depthwise weights tap-major.
+#include <stdlib.h>
 #include <map>
 #include <string>
 #include <vector>
@@ -258,17 +259,25 @@ int gemm(wmk_plan* P, const GemmArgs& g, cudaStream_t st) {
   return P->precision == WMK_PREC_BF16 ? gemm_bf16_tcgen05(g, st) : gemm_fp32_simt(g, st);
 }
 
+// One LeWin block (uformerWM/model.py:937-1019) on the residual stream x.  bf16 mode, C <= 128: the two
+// LayerNorms are fused into the epilogues of the dense layers that produce their input - norm2 into the
+// attention projection, and the NEXT block's norm1 (+ modulator) into this block's linear2 - so the fp32
+// stream is not re-read; `ln1_ready` says the previous block already left LN1(x) in bufA, `next` is the
+// following block of the same stage (nullptr for the last one).
 template <typename OpT>
-int run_block(wmk_plan* P, const BlockW& w, float* x, int n, cudaStream_t st) {
+int run_block(wmk_plan* P, const BlockW& w, float* x, int n, cudaStream_t st, bool ln1_ready = false,
+              const BlockW* next = nullptr) {
   const int C = w.C, H = w.H;
   const int M = n * H * H;
   const int ob = sizeof(OpT) == 2;
+  static const int fuse_min_c = getenv("WMK_FUSE_LN_MINC") ? atoi(getenv("WMK_FUSE_LN_MINC")) : 32;
+  const bool fuse_ln = sizeof(OpT) == 2 && C <= 128 && C >= fuse_min_c;
   OpT* A = reinterpret_cast<OpT*>(P->bufA);
   OpT* QKV = reinterpret_cast<OpT*>(P->bufQKV);
   OpT* O = reinterpret_cast<OpT*>(P->bufO);
   OpT* H1 = reinterpret_cast<OpT*>(P->bufH1);
   OpT* H2 = reinterpret_cast<OpT*>(P->bufH2);
-  {
+  if (!(ln1_ready && fuse_ln)) {
     ProfScope prof(FAM_LAYERNORM, (double)M * C * (4 + sizeof(OpT)), st);
     launch_layernorm<OpT>(x, A, w.ln1_w, w.ln1_b, w.mod, M, C, H, w.shift, st);
     WMK_CHECK_LAUNCH("layernorm_kernel");
@@ -294,8 +303,9 @@ int run_block(wmk_plan* P, const BlockW& w, float* x, int n, cudaStream_t st) {
   g = GemmArgs();
   g.A = O; g.W = w.w_proj; g.bias = w.b_proj; g.resid = x; g.C = x; g.M = M; g.N = C; g.K = C; g.ldc = C;
   g.epi = EPI_BIAS_RESID; g.out_bf16 = 0;
+  if (fuse_ln) { g.ln_out = A; g.ln_gamma = w.ln2_w; g.ln_beta = w.ln2_b; }        // norm2 (model.py:1017)
   WMK_TRY(gemm(P, g, st));
-  {
+  if (!fuse_ln) {
     ProfScope prof(FAM_LAYERNORM, (double)M * C * (4 + sizeof(OpT)), st);
     launch_layernorm<OpT>(x, A, w.ln2_w, w.ln2_b, nullptr, M, C, H, 0, st);
     WMK_CHECK_LAUNCH("layernorm_kernel");
@@ -318,7 +328,18 @@ int run_block(wmk_plan* P, const BlockW& w, float* x, int n, cudaStream_t st) {
   g = GemmArgs();
   g.A = H2; g.W = w.w_l2; g.bias = w.b_l2; g.resid = x; g.C = x; g.M = M; g.N = C; g.K = 4 * C; g.ldc = C;
   g.epi = EPI_BIAS_RESID; g.out_bf16 = 0;
+  if (fuse_ln && next) {                                                           // the next block's norm1 + modulator
+    g.ln_out = A; g.ln_gamma = next->ln1_w; g.ln_beta = next->ln1_b; g.ln_mod = next->mod; g.ln_H = H; g.ln_shift = next->shift;
+  }
   WMK_TRY(gemm(P, g, st));
+  return 0;
+}
+
+// all blocks of one stage
+template <typename OpT>
+int run_stage(wmk_plan* P, const std::vector<BlockW>& blocks, float* x, int n, cudaStream_t st) {
+  for (size_t i = 0; i < blocks.size(); ++i)
+    WMK_TRY(run_block<OpT>(P, blocks[i], x, n, st, i > 0, i + 1 < blocks.size() ? &blocks[i + 1] : nullptr));
   return 0;
 }
 
@@ -334,15 +355,17 @@ int run_encoder(wmk_plan* P, const EncW& e, const float* x_nchw, int n, const ch
   if (t == "enc") WMK_TRY(tap(P, "emb.inproj", P->E[0], (size_t)n * 16384 * 32, st));
   for (int s = 0; s < 5; ++s) {
     const int C = 32 << s, H = 128 >> s;
-    for (const BlockW& b : e.stage[s]) WMK_TRY(run_block<OpT>(P, b, P->E[s], n, st));
+    WMK_TRY(run_stage<OpT>(P, e.stage[s], P->E[s], n, st));
     WMK_TRY(tap(P, t + ".conv" + std::to_string(s), P->E[s], (size_t)n * H * H * C, st));
     if (s == 4) break;
     const int Ho = H / 2;
     OpT* col = reinterpret_cast<OpT*>(P->bufH1);
     const size_t total = (size_t)n * Ho * Ho * 4 * (C / 8);
-    ProfScope prof_l(FAM_LAYOUT, (double)n * H * H * C * 4 + (double)n * Ho * Ho * 16 * C * sizeof(OpT), st);
-    im2col_4x4s2_kernel<OpT><<<cdiv(total, 256), 256, 0, st>>>(P->E[s], col, n, H, C);
-    WMK_CHECK_LAUNCH("im2col_4x4s2_kernel");
+    {
+      ProfScope prof_l(FAM_LAYOUT, (double)n * H * H * C * 4 + (double)n * Ho * Ho * 16 * C * sizeof(OpT), st);
+      im2col_4x4s2_kernel<OpT><<<cdiv(total, 256), 256, 0, st>>>(P->E[s], col, n, H, C);
+      WMK_CHECK_LAUNCH("im2col_4x4s2_kernel");
+    }
     GemmArgs g;
     g.A = col; g.W = e.down_w[s]; g.bias = e.down_b[s]; g.C = P->E[s + 1]; g.M = n * Ho * Ho; g.N = 2 * C;
     g.K = 16 * C; g.ldc = 2 * C; g.epi = EPI_BIAS; g.out_bf16 = 0;
@@ -401,7 +424,7 @@ int run_forward(wmk_plan* P, const float* x, const float* msg, int msg_stride, i
       copy_cols_kernel<float><<<cdiv(rows * (Cout / 4), 256), 256, 0, st>>>(P->E[3 - s], P->D[s], rows, Cout, Cd, Cout);
       WMK_CHECK_LAUNCH("copy_cols_kernel");
     }
-    for (const BlockW& b : P->dec[s]) WMK_TRY(run_block<OpT>(P, b, P->D[s], n, st));
+    WMK_TRY(run_stage<OpT>(P, P->dec[s], P->D[s], n, st));
     WMK_TRY(tap(P, "dec.deconv" + std::to_string(s), P->D[s], (size_t)n * Hout * Hout * Cd, st));
   }
   (void)ob;

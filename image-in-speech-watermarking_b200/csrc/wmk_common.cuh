@@ -90,6 +90,14 @@ struct GemmArgs {
   // EPI_UPSAMPLE: A rows are (b, h, w) over an up_h x up_w grid; columns are (i, j, co) with
   // co < up_cout; element goes to token (b, 2h+i, 2w+j), channel co of a [.., ldc] buffer.
   int up_h = 0, up_w = 0, up_cout = 0;
+  // Fused LayerNorm of the output row (EPI_BIAS_RESID, bf16 kernel, N in {32, 64, 128} = one tile per row):
+  // ln_out[m][:] = bf16( LN(C[m][:]) * gamma + beta (+ modulator[window position of token m]) ), i.e. the
+  // operand of the NEXT dense layer (uformerWM/model.py:982,996-999,1017) without re-reading C.
+  void* ln_out = nullptr;          // [M][N] bf16
+  const float* ln_gamma = nullptr;
+  const float* ln_beta = nullptr;
+  const float* ln_mod = nullptr;   // [64][N] or nullptr
+  int ln_H = 0, ln_shift = 0;      // image side (power of two) and cyclic shift of the block that consumes ln_out
 };
 
 // Roofline class of a dense-layer launch: algorithmic bytes (A + W + C, + the fp32 residual) against
@@ -169,6 +177,10 @@ struct EpiParams {
   void* C;
   int M, N, ldc, epi, out_bf16;
   int up_h, up_w, up_cout;
+  const float* ln_gamma = nullptr;
+  const float* ln_beta = nullptr;
+  const float* ln_mod = nullptr;
+  int ln_H = 0, ln_shift = 0;
 };
 
 __device__ __forceinline__ size_t epi_row_offset(const EpiParams& p, int m, int n_first) {
