@@ -219,17 +219,22 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __
   const uint32_t bars = LN ? ln_exch + LN_EXCH_BYTES : staging + kEpiWarps * STG_BYTES;
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (n_stages + s); };
-  const uint32_t tfull_bar = bars + 16u * n_stages;         // [2]
-  const uint32_t tempty_bar = tfull_bar + 16u;              // [2]
-  const uint32_t wfull_bar = tempty_bar + 16u;
+  const uint32_t tfull_bar = bars + 16u * n_stages;         // [NACC <= 8]
+  const uint32_t tempty_bar = tfull_bar + 64u;              // [NACC <= 8]
+  const uint32_t wfull_bar = tempty_bar + 64u;
   const uint32_t tmem_slot = wfull_bar + 8u;
   volatile uint32_t* tmem_slot_ptr = (volatile uint32_t*)(smem_raw + (tmem_slot - raw));
 
   constexpr int CPW = epi_cpw(BN);
-  constexpr int SLABS = BN / CPW;                           // epilogue warps per lane quarter with work
-  constexpr int ACTIVE_EPI = SLABS * 4;
+  constexpr int SLABS = BN / CPW;                           // epilogue warps per lane quarter that share one tile
+  constexpr int ACTIVE_EPI = SLABS * 4;                     // warps of one epilogue team
+  // Narrow tiles (BN <= 64) finish their main loop faster than one epilogue pass (TMEM load -> residual ->
+  // store [-> LayerNorm exchange -> store]) can run, so the 16 epilogue warps form 4 / 2 independent TEAMS
+  // that take alternate tiles, with 2 TMEM accumulators per team: up to 8 tiles in flight.
+  constexpr int TEAMS = BN <= 32 ? 4 : BN <= 64 ? 2 : 1;
+  constexpr int NACC = 2 * TEAMS;
   constexpr int BOXC = epi_box_cols(BN, OUT_BF16);
-  constexpr int TCOLS = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
+  constexpr int TCOLS = NACC * BN <= 32 ? 32 : NACC * BN <= 64 ? 64 : NACC * BN <= 128 ? 128 : NACC * BN <= 256 ? 256 : 512;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total = m_tiles * n_tiles;
@@ -258,7 +263,7 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < NACC; ++a) {
       mbar_init(tfull_bar + 8u * a, 1);
       mbar_init(tempty_bar + 8u * a, ACTIVE_EPI);
     }
@@ -298,8 +303,8 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __
       int it = 0, m0, n0;
       if (w_stationary && tile_at(0, m0, n0)) mbar_wait(wfull_bar, 0);
       for (int lt = 0; tile_at(lt, m0, n0); ++lt) {
-        const int acc = lt & 1;
-        mbar_wait(tempty_bar + 8u * acc, ((uint32_t)(lt >> 1) & 1u) ^ 1u);      // epilogue drained this accumulator
+        const int acc = lt % NACC;
+        mbar_wait(tempty_bar + 8u * acc, ((uint32_t)(lt / NACC) & 1u) ^ 1u);    // epilogue drained this accumulator
         tcgen05_fence_after();
         const uint32_t tacc = tmem_base + (uint32_t)(acc * BN);
         for (int kb = 0; kb < kblocks; ++kb, ++it) {
@@ -322,12 +327,13 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __
   } else {
     const int ew = warp - 2;
     const int q = warp & 3;                       // TMEM lane quarter this warp may read
-    const int slab = ew >> 2;                     // which CPW-wide column slab
-    if (slab < SLABS) {
+    const int team = (ew >> 2) / SLABS;           // which epilogue team
+    const int slab = (ew >> 2) % SLABS;           // which CPW-wide column slab of the team's tile
+    if (team < TEAMS) {
       const uint32_t buf = staging + (uint32_t)ew * STG_BYTES;
       int m0, n0;
-      for (int lt = 0; tile_at(lt, m0, n0); ++lt) {
-        const int acc = lt & 1;
+      for (int lt = team; tile_at(lt, m0, n0); lt += TEAMS) {
+        const int acc = lt % NACC;
         const int row = m0 + q * 32 + lane;
         // residual rows do not depend on the accumulator: fetch the first 32-column piece while the MMAs run
         float4 rpre[8];
@@ -341,7 +347,7 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __
             for (int j = 0; j < 8; ++j) rpre[j] = make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
-        mbar_wait(tfull_bar + 8u * acc, (uint32_t)(lt >> 1) & 1u);
+        mbar_wait(tfull_bar + 8u * acc, (uint32_t)(lt / NACC) & 1u);
         tcgen05_fence_after();
         const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + slab * CPW);
 #pragma unroll 1
@@ -419,13 +425,13 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __
               for (int j = 0; j < 32; ++j) { s1 += f[j]; s2 = fmaf(f[j], f[j], s2); }
               if constexpr (SLABS > 1) {
                 float2* ex = reinterpret_cast<float2*>(smem_raw + (ln_exch - raw));
-                const int par = lt & 1;
-                ex[((par * 4 + slab) * 4 + q) * 32 + lane] = make_float2(s1, s2);
-                asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "r"(SLABS * 32) : "memory");
+                const int par = (lt / TEAMS) & 1;
+                ex[((par * 4 + team * SLABS + slab) * 4 + q) * 32 + lane] = make_float2(s1, s2);
+                asm volatile("bar.sync %0, %1;" ::"r"(1 + q + 4 * team), "r"(SLABS * 32) : "memory");
                 s1 = 0.f; s2 = 0.f;
 #pragma unroll
                 for (int sb = 0; sb < SLABS; ++sb) {
-                  const float2 e2 = ex[((par * 4 + sb) * 4 + q) * 32 + lane];
+                  const float2 e2 = ex[((par * 4 + team * SLABS + sb) * 4 + q) * 32 + lane];
                   s1 += e2.x; s2 += e2.y;
                 }
               }
