@@ -121,8 +121,11 @@ static inline void build_tables(Tables* t) {
 // 17-point complex DFT by the even/odd split; emit(k, Y[k]) is called once for every k = 0..16.
 //   A_k = y0 + sum_{n=1..8} (y[n]+y[17-n]) cos(2 pi k n/17),   B_k = sum_{n=1..8} (y[n]-y[17-n]) sin(2 pi k n/17)
 //   forward (e^-):  Y[k] = A - iB,  Y[17-k] = A + iB;     inverse (e^+): the two swap.
-template <bool INVERSE, class Emit>
+// HALF: -1 = all outputs; 0 = k in {0, 1..4, 13..16}; 1 = k in {5..12}: lets two warps share one transform
+// (each recomputes the 16 butterflies, the 256 multiply-adds are split).
+template <bool INVERSE, int HALF, class Emit>
 WMK_HD void dft17(const float2 (&y)[17], Emit&& emit) {
+  constexpr int KLO = HALF == 1 ? 5 : 1, KHI = HALF == 0 ? 4 : 8;
   // The inverse kernel runs this with packed float2 instructions (FADD2 / FFMA2: measured +5 %), the forward
   // kernel with scalar ones (packed measured -7 % there: its stage B is FMA-pipe bound, not issue bound).
   float2 e[9], o[9];
@@ -142,9 +145,9 @@ WMK_HD void dft17(const float2 (&y)[17], Emit&& emit) {
     if (INVERSE) s = add2(s, e[n]);
     else { s.x += e[n].x; s.y += e[n].y; }
   }
-  emit(0, s);
+  if (HALF != 1) emit(0, s);
 #pragma unroll
-  for (int k = 1; k <= 8; ++k) {
+  for (int k = KLO; k <= KHI; ++k) {
     float2 a = y[0], b = make_float2(0.f, 0.f);
 #pragma unroll
     for (int n = 1; n <= 8; ++n) {
@@ -283,12 +286,12 @@ WMK_HD void fwd_stage_a(const float* samp, float2* SA, int n2, int f) {
 
 // ---- forward stage B: the 17-point DFT over n2 for (k1, frame f); store(bin, re, im) receives each
 // one-sided bin exactly once over k1 = 0..7.
-template <class Store>
+template <int HALF, class Store>
 WMK_HD void fwd_stage_b(const float2* SA, const InvEntry* fwd_tab, int k1, int f, Store&& store) {
   float2 y[17];
 #pragma unroll
   for (int n2 = 0; n2 < 17; ++n2) y[n2] = SA[(k1 * 17 + n2) * FT + f];
-  dft17<false>(y, [&](int k2, float2 X) {
+  dft17<false, HALF>(y, [&](int k2, float2 X) {
     const InvEntry e = fwd_tab[k1 * 17 + k2];
     if (e.bin >= 0) store(e.bin, X.x, X.y * e.im_sign);
   });
@@ -297,6 +300,7 @@ WMK_HD void fwd_stage_b(const float2* SA, const InvEntry* fwd_tab, int k1, int f
 // ---- inverse stage B': the inverse 17-point DFT over k2 for (k1, frame f) -> ZS[k1][n2][f].
 // XS[row][f], row = reim*128 + bin: the one-sided spectrum tile; the imaginary part of DC is ignored
 // as in a C2R transform.
+template <int HALF>
 WMK_HD void inv_stage_b(const float* XS, const InvEntry* inv_tab, float2* ZS, int k1, int f) {
   float2 y[17];
 #pragma unroll
@@ -304,7 +308,7 @@ WMK_HD void inv_stage_b(const float* XS, const InvEntry* inv_tab, float2* ZS, in
     const InvEntry e = inv_tab[k1 * 17 + k2];
     y[k2] = make_float2(XS[e.bin * FT + f], XS[(BINS + e.bin) * FT + f] * e.im_sign);
   }
-  dft17<true>(y, [&](int n2, float2 Z) { ZS[(k1 * 17 + n2) * FT + f] = Z; });
+  dft17<true, HALF>(y, [&](int n2, float2 Z) { ZS[(k1 * 17 + n2) * FT + f] = Z; });
 }
 
 // ---- inverse stage A': complex-to-real inverse 15-point DFT over k1 for (n2, frame f); writes the

@@ -26,6 +26,15 @@ constexpr int kFrontThreads = 17 * 32;
 constexpr int kTileSamples = HOP * (FT - 1) + NFFT;      // 2208 samples feed the 32 frames of a tile
 constexpr int kSampFloats = kTileSamples + 8;            // + up to 3 floats of alignment slack, 16-byte multiple
 
+// 1 = two warps per 17-point transform (k1, half): balances the 17-warp CTA across its phases but re-does the
+// butterflies; measured slower (both kernels are instruction-issue bound: STFT 3.94 -> 3.64 TB/s), so off.
+#ifndef STFT_SPLIT
+#define STFT_SPLIT 0
+#endif
+#ifndef ISTFT_SPLIT
+#define ISTFT_SPLIT 0
+#endif
+
 __constant__ dft255::Tables c_tab;
 
 int ensure_tables() {
@@ -86,9 +95,9 @@ struct StftTile {
   }
 };
 
-template <bool ALL_LIVE>
+template <bool ALL_LIVE, int HALF>
 __device__ __forceinline__ void stft_stage_b(const float2* SA, int k1, int lane, float* orow, float live) {
-  dft255::fwd_stage_b(SA, c_tab.fwd, k1, lane, [&](int bin, float re, float im) {
+  dft255::fwd_stage_b<HALF>(SA, c_tab.fwd, k1, lane, [&](int bin, float re, float im) {
     float* o = orow + bin * 128;
     o[0] = ALL_LIVE ? re : re * live;
     o[BINS * 128] = ALL_LIVE ? im : im * live;
@@ -129,8 +138,11 @@ stft_clips_kernel(const float* __restrict__ wave, int L, int T, float* __restric
     dft255::fwd_stage_a(buf + (cur.fast ? cur.mis : 0), SA, warp, lane);
     __syncthreads();
     if (warp < 8) {
-      if (f0 + FT <= T) stft_stage_b<true>(SA, warp, lane, orow, 1.f);
-      else stft_stage_b<false>(SA, warp, lane, orow, f0 + lane < T ? 1.f : 0.f);
+      if (f0 + FT <= T) stft_stage_b<true, STFT_SPLIT ? 0 : -1>(SA, warp, lane, orow, 1.f);
+      else stft_stage_b<false, STFT_SPLIT ? 0 : -1>(SA, warp, lane, orow, f0 + lane < T ? 1.f : 0.f);
+    } else if (STFT_SPLIT && warp < 16) {
+      if (f0 + FT <= T) stft_stage_b<true, 1>(SA, warp - 8, lane, orow, 1.f);
+      else stft_stage_b<false, 1>(SA, warp - 8, lane, orow, f0 + lane < T ? 1.f : 0.f);
     }
   }
 }
@@ -195,7 +207,8 @@ istft_clips_kernel(const float* __restrict__ clips, int n_clips, int T, float* _
       istft_prefetch(clips_b, fbase + IFT, smem + ((it + 1) & 1) * kXsFloats, tid);
       prefetched = true;
     }
-    if (warp < 8) dft255::inv_stage_b(XS, c_tab.inv, ZS, warp, lane);
+    if (warp < 8) dft255::inv_stage_b<ISTFT_SPLIT ? 0 : -1>(XS, c_tab.inv, ZS, warp, lane);
+    else if (ISTFT_SPLIT && warp < 16) dft255::inv_stage_b<1>(XS, c_tab.inv, ZS, warp - 8, lane);
     __syncthreads();
     float* FR = XS;
     dft255::inv_stage_a(ZS, FR, warp, lane);
