@@ -19,6 +19,8 @@ namespace wmk {
 
 int stft_clips(const float* wave, int B, int L, float* clips, int n_clips, cudaStream_t st);
 int istft_clips(const float* clips, int B, int n_clips, int T, float* wave, int length, cudaStream_t st);
+int leff_dwconv_linear2_bf16(const __nv_bfloat16* H1, const float* dw_w, const float* dw_b, const __nv_bfloat16* W2,
+                             const float* b2, float* x, int n, int H, int C, cudaStream_t st);
 int dwconv3x3_gelu_bf16(const __nv_bfloat16* in, __nv_bfloat16* out, const float* wt, const float* bias, int B, int H,
                         int Ch, cudaStream_t st);
 
@@ -79,6 +81,10 @@ struct wmk_plan {
         *rt2 = nullptr;
   bool ws_ready = false;
 
+  // WMK_FUSED_LEFF=1 (read when the plan is created): run the LeFF tail as the fused dwconv -> linear2 tcgen05
+  // kernel of leff_fused.cu for the C <= 256 stages.  Off by default: it removes 16C bytes/token of HBM traffic
+  // but the tail is bound by the convolution's fp32 work, so it measures the same as the two separate kernels.
+  int fused_leff = 0, fused_maxh = 128, fused_minh = 8;
   bool taps_on = false;
   std::map<std::string, std::pair<float*, size_t>> taps;
 
@@ -314,6 +320,18 @@ int run_block(wmk_plan* P, const BlockW& w, float* x, int n, cudaStream_t st, bo
   g.A = A; g.W = w.w_l1; g.bias = w.b_l1; g.C = H1; g.M = M; g.N = 4 * C; g.K = C; g.ldc = 4 * C;
   g.epi = EPI_BIAS_GELU; g.out_bf16 = ob;
   WMK_TRY(gemm(P, g, st));
+  if constexpr (sizeof(OpT) == 2) {
+    if (P->fused_leff && C <= 256 && H <= P->fused_maxh && H >= P->fused_minh) {
+      // depthwise conv + GELU as the producer of linear2's A operand: H2 never reaches HBM (leff_fused.cu)
+      WMK_TRY(leff_dwconv_linear2_bf16(H1, w.dw_w, w.dw_b, reinterpret_cast<const __nv_bfloat16*>(w.w_l2), w.b_l2, x, n, H, C, st));
+      if (fuse_ln && next) {
+        ProfScope prof(FAM_LAYERNORM, (double)M * C * (4 + sizeof(OpT)), st);
+        launch_layernorm<OpT>(x, A, next->ln1_w, next->ln1_b, next->mod, M, C, H, next->shift, st);
+        WMK_CHECK_LAUNCH("layernorm_kernel");
+      }
+      return 0;
+    }
+  }
   {
     const size_t total = (size_t)M * C;     // (4C / 4) channel groups per pixel
     ProfScope prof(FAM_DWCONV, 8.0 * M * C * sizeof(OpT), st);
@@ -475,6 +493,9 @@ extern "C" int wmk_uformer_plan_create(int precision, wmk_plan** out) {
     return WMK_ERR_UNSUPPORTED;
   }
   wmk_plan* P = new wmk_plan();
+  if (getenv("WMK_FUSED_LEFF")) P->fused_leff = atoi(getenv("WMK_FUSED_LEFF"));
+  if (getenv("WMK_FUSED_LEFF_MAXH")) P->fused_maxh = atoi(getenv("WMK_FUSED_LEFF_MAXH"));
+  if (getenv("WMK_FUSED_LEFF_MINH")) P->fused_minh = atoi(getenv("WMK_FUSED_LEFF_MINH"));
   P->precision = precision;
   P->device = dev;
   *out = P;

@@ -304,3 +304,25 @@ def test_tiled_64x64_image_pipeline_matches_oracle(models, weights):
     assert abs(float(r["image_stats"][0, 1]) - mse_img) < 1e-4
     back = PT.untile_image(r["image_att"], 64, 64)
     assert back.shape == (1, 1, 64, 64)
+
+
+def test_fused_leff_kernel_matches_reference_golden(golden, weights, monkeypatch):
+    """Optional fused LeFF tail (depthwise conv + GELU as the producer of linear2's tcgen05 A operand,
+    csrc/leff_fused.cu, WMK_FUSED_LEFF=1 at plan creation): same bounds as the default bf16 path."""
+    from image_in_speech_watermarking_b200.model import UformerAudio
+    monkeypatch.setenv("WMK_FUSED_LEFF", "1")
+    g = golden("model_stress.npz")
+    m = UformerAudio(precision="bf16")
+    m.load_state_dict(weights("stress"))
+    m = m.cuda().eval()
+    o = m.run(torch.from_numpy(g["x"]).cuda(), torch.from_numpy(g["msg"]).cuda(), want=("stft_new", "noise", "wm_pred", "wm", "wm_logits"))
+    for k in ("stft_new", "noise", "wm_pred", "wm"):
+        assert l2rel(o[k].cpu().numpy(), g[k]) < TOL["bf16"], k
+        assert maxrel(o[k].cpu().numpy(), g[k]) < TOL["bf16"], k
+    with torch.no_grad():
+        ref_logits = O.forward(weights("stress"), torch.from_numpy(g["x"]), torch.from_numpy(g["msg"]), return_logits=True)[4].numpy()
+    lg = o["wm_logits"].cpu().numpy()
+    flips = (lg > 0) != (ref_logits > 0)
+    assert (np.abs(ref_logits[flips]) < LOGIT_MARGIN["bf16"]).all()
+    wa = m.wm_decode(torch.from_numpy(g["x_att"]).cuda()).cpu().numpy()
+    assert maxrel(wa, g["wm_att"]) < TOL["bf16"]
