@@ -42,6 +42,7 @@ SIGNATURES = {
     "wmk_conv3x3_wgrad_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "wmk_convT2x2_dgrad_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "wmk_convT2x2_wgrad_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "wmk_affine_f32": (_i, [_vp, _vp, _sz, _f, _f, _vp]),
     "wmk_mse_f32": (_i, [_vp, _vp, _vp, _sz, _f, _vp, _vp]),
     "wmk_adam_step_f32": (_i, [_vp, _vp, _vp, _vp, _sz, _f, _f, _f, _f, _f, _i, _f, _i, _vp]),
     "wmk_noise_mix_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),

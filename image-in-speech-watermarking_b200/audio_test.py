@@ -14,14 +14,37 @@ from . import audio_attack as AT
 from . import evaluate as EV
 
 
-def prepare_data(soundwave, audio_scale='0'):
+def scale_params(audio_scale='0', data_min=None, data_max=None):
+    """`audio_scale` of the reference (`audio_test.py:33-55,329-341`) as an affine map x -> x * scale + shift:
+    '0' (or any 1-char string) = identity, 'k' = multiply by float(k), 'a-b' = min-max from the dataset range
+    [data_min, data_max] to [a, b].  The inverse (`:559-571`) is (y - shift) / scale."""
+    a = str(audio_scale)
+    if '-' not in a:
+        return (float(a), 0.0) if len(a) > 1 else (1.0, 0.0)
+    lo, hi = (float(v) for v in a.split('-'))
+    if data_min is None or data_max is None:
+        raise ValueError("audio_scale '%s' needs data_min / data_max" % a)
+    scale = (hi - lo) / (float(data_max) - float(data_min))
+    return scale, lo - float(data_min) * scale
+
+
+def affine(x, scale, shift, out=None):
+    """x * scale + shift on the GPU (`wmk_affine_f32`)."""
+    if scale == 1.0 and shift == 0.0:
+        return x
+    x = x.contiguous().float()
+    out = torch.empty_like(x) if out is None else out
+    _lib.check(_lib.load().wmk_affine_f32(_lib.ptr(x), _lib.ptr(out), x.numel(), float(scale), float(shift), _lib.stream_ptr()))
+    return out
+
+
+def prepare_data(soundwave, audio_scale='0', data_min=None, data_max=None):
     """`SpeechDataTest.prepare_data` (`audio_test.py:314-347`) for one utterance on the GPU.
     soundwave (1, L) -> [ (wave, sr), [clip (1,2,128,128) ...], len_last_clip ]."""
-    if len(str(audio_scale)) > 1:
-        raise NotImplementedError("audio_scale normalisation is a 'next' row (SURVEY 8f-1)")
     w = soundwave.reshape(1, -1).cuda().float()
     T = FE.num_frames(w.shape[1])
     clips = FE.stft_clips(w)                                   # (1, T//128+1, 2,128,128)
+    clips = affine(clips, *scale_params(audio_scale, data_min, data_max))       # `audio_test.py:329-341`
     return [(soundwave, 16000), [clips[:, j] for j in range(clips.shape[1])], T % 128]
 
 
@@ -56,7 +79,20 @@ def recover_tiled(wm_clips, K):
     return out / cnt.view(1, K, 1, 1, 1)
 
 
-def embed_attack_extract(waves, messages, model, attack="closed_loop", draws=None, seed=0, want_outputs=True):
+def _model_embed(model, x, msg_clips, model_name):
+    """-> (audio clips, clean wm, clean logits or None) for the two model kinds of `audio_test.py:552-556`."""
+    if model_name == 'uformer':
+        o = model.run(x, msg_clips, want=("stft_new", "wm", "wm_logits"))
+        return o["stft_new"], o["wm"], o["wm_logits"]
+    if model_name == 'modelA':
+        m = msg_clips if msg_clips.shape[0] == x.shape[0] else msg_clips.expand(x.shape[0], 1, 32, 32)
+        audio, wm = model(x, m)
+        return audio, wm, None
+    raise ValueError("model_name must be 'uformer' or 'modelA', got %r" % (model_name,))
+
+
+def embed_attack_extract(waves, messages, model, attack="closed_loop", draws=None, seed=0, want_outputs=True,
+                         audio_scale='0', data_min=None, data_max=None, model_name='uformer'):
     """Batched hot path.  waves (B, L) CUDA fp32; messages (B or 1, 1, 32, 32) CUDA, or
     (B, K, 1, 32, 32) tiles (see `tile_image`): clip j of an utterance then carries tile j mod K.
     Returns a dict of device tensors:
@@ -68,7 +104,8 @@ def embed_attack_extract(waves, messages, model, attack="closed_loop", draws=Non
     B, L = waves.shape
     T = FE.num_frames(L)
     nc = T // 128 + 1                                          # quirk B-6
-    clips = FE.stft_clips(waves, nc)                           # (B,nc,2,128,128)
+    sc, sh = scale_params(audio_scale, data_min, data_max)
+    clips = affine(FE.stft_clips(waves, nc), sc, sh)           # (B,nc,2,128,128), `audio_test.py:329-341`
     tiled = messages.dim() == 5
     if tiled:
         tiles = messages.float()
@@ -86,14 +123,19 @@ def embed_attack_extract(waves, messages, model, attack="closed_loop", draws=Non
         def msg_for(n):
             return msg_b[:, None].expand(B, n, 1, 32, 32)
         msg_clips = msg_for(nc).reshape(B * nc, 1, 32, 32).contiguous()
-    o = model.run(clips.reshape(B * nc, 2, 128, 128), msg_clips if (tiled or msg.shape[0] == B) else msg,
-                  want=("stft_new", "wm", "wm_logits"))
-    recon = FE.istft_clips(o["stft_new"].reshape(B, nc, 2, 128, 128), T, L)          # audio_test.py:595-600
+    audio_clips, wm_clean, lg_clean = _model_embed(model, clips.reshape(B * nc, 2, 128, 128),
+                                                   msg_clips if (tiled or msg.shape[0] == B) else msg, model_name)
+    audio_clips = affine(audio_clips, 1.0 / sc, -sh / sc)                             # back to the audio range, :559-571
+    recon = FE.istft_clips(audio_clips.reshape(B, nc, 2, 128, 128), T, L)             # audio_test.py:595-600
     att = AT.apply_attack(recon, attack, draws, seed)                                 # :631-660
     nc_att = (T + 126) // 128                                                         # quirk B-7
     clips_att = FE.stft_clips(att, max(nc_att, (T + 127) // 128))[:, :nc_att].contiguous()
-    wm_att, lg_att = model.wm_decode(clips_att.reshape(B * nc_att, 2, 128, 128), return_logits=True)
-    wm = o["wm"].reshape(B, nc, 1, 32, 32)
+    clips_att = affine(clips_att, sc, sh)                                             # :691-702
+    if model_name == 'uformer':
+        wm_att, lg_att = model.wm_decode(clips_att.reshape(B * nc_att, 2, 128, 128), return_logits=True)
+    else:
+        wm_att, lg_att = model.decode(clips_att.reshape(B * nc_att, 2, 128, 128)), None
+    wm = wm_clean.reshape(B, nc, 1, 32, 32)
     wm_att = wm_att.reshape(B, nc_att, 1, 32, 32)
     st_att = EV.wave_stats(waves, att)
     st_rec = EV.wave_stats(waves, recon)
@@ -114,9 +156,9 @@ def embed_attack_extract(waves, messages, model, attack="closed_loop", draws=Non
                                           torch.full((B,), 1024.0 * K, device=waves.device, dtype=torch.float64)], dim=1)
     if want_outputs:
         out.update({"recon": recon, "att": att, "wm": wm, "wm_att": wm_att,
-                    "logits": o["wm_logits"].reshape(B, nc, 1, 32, 32),
-                    "logits_att": lg_att.reshape(B, nc_att, 1, 32, 32), "stft_new": o["stft_new"],
-                    "stats_recon": st_rec})
+                    "logits": lg_clean.reshape(B, nc, 1, 32, 32) if lg_clean is not None else None,
+                    "logits_att": lg_att.reshape(B, nc_att, 1, 32, 32) if lg_att is not None else None,
+                    "stft_new": audio_clips, "stats_recon": st_rec})
     return out
 
 
@@ -128,10 +170,11 @@ def reconstruct_audio(audio_data, watermark, model, n_fft=255, attack=None, data
                       data_min=None, data_max=None, model_name='uformer', draws=None):
     """Reference signature and 10-tuple (`audio_test.py:528,784-785`) for data_mode='stft',
     model_name='uformer'."""
-    if data_mode != 'stft' or model_name != 'uformer' or len(str(audio_scale)) > 1:
-        raise NotImplementedError("hot path covers data_mode='stft', model_name='uformer', audio_scale='0'")
+    if data_mode != 'stft':
+        raise NotImplementedError("hot path covers data_mode='stft' (the DWT mode needs pywt, SURVEY 8f-4)")
     wave = audio_data[0][0].reshape(1, -1).cuda().float()
-    r = embed_attack_extract(wave, watermark.cuda(), model, attack or "closed_loop", draws)
+    r = embed_attack_extract(wave, watermark.cuda(), model, attack or "closed_loop", draws, audio_scale=audio_scale,
+                             data_min=data_min, data_max=data_max, model_name=model_name)
     s = r["stats"][0].cpu().numpy()
     audio_att = r["att"][0].double().cpu().numpy()
     recon_audio = r["recon"][0].cpu()

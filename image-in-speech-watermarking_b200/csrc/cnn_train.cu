@@ -341,6 +341,20 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
   p[i] = w - (lr / bc1) * (mi / denom);
 }
 
+// out = in * scale + shift (the audio_scale normalisation of the clips, uformerWM/audio_test.py:329-341,559-571,691-702)
+__global__ void __launch_bounds__(256)
+affine_kernel(const float* __restrict__ in, float* __restrict__ out, size_t n4, size_t n, float scale, float shift) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n4) {
+    float4 v = reinterpret_cast<const float4*>(in)[i];
+    v.x = fmaf(v.x, scale, shift); v.y = fmaf(v.y, scale, shift); v.z = fmaf(v.z, scale, shift); v.w = fmaf(v.w, scale, shift);
+    reinterpret_cast<float4*>(out)[i] = v;
+  } else if (i < n4 + (n & 3)) {
+    const size_t j = n4 * 4 + (i - n4);
+    out[j] = fmaf(in[j], scale, shift);
+  }
+}
+
 int grid_for(size_t n) { return (int)((n + 255) / 256); }
 
 }  // namespace
@@ -490,5 +504,15 @@ extern "C" int wmk_adam_step_f32(float* params, const float* grads, float* exp_a
   adam_kernel<<<grid_for(n), 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2,
                                            grad_scale, decoupled);
   WMK_CHECK_LAUNCH("adam_kernel");
+  return 0;
+}
+
+extern "C" int wmk_affine_f32(const float* in, float* out, size_t n, float scale, float shift, void* stream) {
+  WMK_REQUIRE(in && out && n > 0 && ((uintptr_t)in & 15) == 0 && ((uintptr_t)out & 15) == 0, "affine: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  ProfScope prof(FAM_ATTACK, 8.0 * n, st);
+  const size_t n4 = n / 4;
+  affine_kernel<<<grid_for(n4 + 3), 256, 0, st>>>(in, out, n4, n, scale, shift);
+  WMK_CHECK_LAUNCH("affine_kernel");
   return 0;
 }

@@ -178,6 +178,9 @@ int wmk_convT2x2_dgrad_f32(const float* dy, const float* w, float* dx, int B, in
                            int W, void* stream);
 int wmk_convT2x2_wgrad_f32(const float* x, const float* dy, float* dw, float* db, int B, int Cin,
                            int Cout, int H, int W, void* stream);
+/* out = in * scale + shift: the audio_scale normalisation of spectrogram clips and its inverse
+ * (uformerWM/audio_test.py:33-55,329-341,559-571,691-702); in may equal out */
+int wmk_affine_f32(const float* in, float* out, size_t n, float scale, float shift, void* stream);
 /* nn.MSELoss: *loss_accum += mean((a-b)^2) (device double, caller zeroes it); grad_a (may be NULL) =
  * grad_scale * 2 (a-b) / n */
 int wmk_mse_f32(const float* a, const float* b, float* grad_a, size_t n, float grad_scale,

@@ -14,7 +14,21 @@ from . import uformer as U
 from . import signal as S
 
 
-def prepare_data(wave_1L):
+def _scale_clip(data_clip, audio_scale, data_min, data_max):
+    """`uformerWM/audio_test.py:329-341` (and `:691-702`), verbatim arithmetic."""
+    if '-' not in audio_scale:
+        if len(audio_scale) > 1:
+            data_clip = data_clip * float(audio_scale)
+    else:
+        min_range, max_range = audio_scale.split('-')
+        min_range = float(min_range)
+        max_range = float(max_range)
+        data_clip = (data_clip - data_min) / (data_max - data_min)
+        data_clip = data_clip * (max_range - min_range) + min_range
+    return data_clip
+
+
+def prepare_data(wave_1L, audio_scale='0', data_min=None, data_max=None):
     """`uformerWM/audio_test.py:314-347` for one utterance.  wave (1,L) fp32 torch.
     Returns [ (wave, sr), [clip (1,2,128,128)...], len_last_clip ]."""
     stft = torch.view_as_real(torch.stft(wave_1L, n_fft=255, return_complex=True))   # (1,128,T,2)
@@ -22,12 +36,13 @@ def prepare_data(wave_1L):
     stft_2 = F.pad(stft, (0, 0, 0, len_pad), mode="constant", value=0)
     clips = []
     for j in range(stft_2.shape[2] // 128):
-        c = stft_2[:, :, 128 * j:128 * (j + 1), :]
+        c = _scale_clip(stft_2[:, :, 128 * j:128 * (j + 1), :], audio_scale, data_min, data_max)
         clips.append(c.permute(0, 3, 1, 2).squeeze(0).unsqueeze(0))   # DataLoader(bs=1) adds the batch dim
     return [(wave_1L, 16000), clips, stft.shape[2] % 128]
 
 
-def reconstruct_audio(audio_data, watermark, sd, n_fft=255, attack="closed_loop", draws=None, tiles=None):
+def reconstruct_audio(audio_data, watermark, sd, n_fft=255, attack="closed_loop", draws=None, tiles=None,
+                      audio_scale='0', data_min=None, data_max=None, model_name='uformer'):
     """`uformerWM/audio_test.py:528-785`.  Returns the reference's 10-tuple plus a dict of
     extras (logits) used by the parity tests.
 
@@ -45,7 +60,18 @@ def reconstruct_audio(audio_data, watermark, sd, n_fft=255, attack="closed_loop"
     logits_clean = []
     with torch.no_grad():
         for i, clip in enumerate(clips):
-            audio_clip, _, _, wm_decode, lg = U.forward(sd, clip, wm_of(i), return_logits=True)    # `:553`
+            if model_name == 'uformer':
+                audio_clip, _, _, wm_decode, lg = U.forward(sd, clip, wm_of(i), return_logits=True)    # `:553`
+            else:                                       # `:555`: sd is then a ModelA-like module (oracle/cnn.py)
+                audio_clip, wm_decode = sd(clip, wm_of(i))
+                lg = wm_decode
+            if len(audio_scale) > 1:                    # rescale to the audio value range, `:559-571`
+                if '-' not in audio_scale:
+                    audio_clip = audio_clip * (1 / float(audio_scale))
+                else:
+                    min_range, max_range = (float(v) for v in audio_scale.split('-'))
+                    audio_clip = (audio_clip - min_range) / (max_range - min_range)
+                    audio_clip = audio_clip * (data_max - data_min) + data_min
             wms_decode.append(wm_decode.numpy())
             logits_clean.append(lg.numpy())
             if i != len(clips) - 1:
@@ -66,7 +92,13 @@ def reconstruct_audio(audio_data, watermark, sd, n_fft=255, attack="closed_loop"
         wms_att_decode, logits_att = [], []
         for j in range(feat.shape[3] // 128):
             data_clip = feat[:, :, :, 128 * j:128 * (j + 1)].float()
-            wm_att, lg = U.wm_decode(sd, data_clip, return_logits=True)                           # `:706`
+            if len(audio_scale) > 1:                                                              # `:691-702`
+                data_clip = _scale_clip(data_clip, audio_scale, data_min, data_max)
+            if model_name == 'uformer':
+                wm_att, lg = U.wm_decode(sd, data_clip, return_logits=True)                       # `:706`
+            else:
+                wm_att = sd.decode(data_clip)                                                     # `:708`
+                lg = wm_att
             wms_att_decode.append(wm_att.numpy())
             logits_att.append(lg.numpy())
             wm_losses_att.append(torch.nn.MSELoss()(wm_of(j), wm_att).item())                     # `:712`

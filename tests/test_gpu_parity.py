@@ -326,3 +326,52 @@ def test_fused_leff_kernel_matches_reference_golden(golden, weights, monkeypatch
     assert (np.abs(ref_logits[flips]) < LOGIT_MARGIN["bf16"]).all()
     wa = m.wm_decode(torch.from_numpy(g["x_att"]).cuda()).cpu().numpy()
     assert maxrel(wa, g["wm_att"]) < TOL["bf16"]
+
+
+@pytest.mark.parametrize("audio_scale", ["0.5", "0.01-0.1"])
+def test_audio_scale_normalisation_matches_oracle(audio_scale, models, weights):
+    """`audio_scale` of the reference front end / driver (`audio_test.py:33-55,329-341,559-571,691-702`): scaled clips
+    into the model, watermarked clips back to the audio range, attacked clips scaled again."""
+    from image_in_speech_watermarking_b200 import audio_test as PT
+    m = models("fp32", "stress")
+    wave = SY.synth_speech(31, 1.0)[None]
+    msg = SY.synth_image_binary(31)[None]
+    dmin, dmax = -3.0, 4.0
+    data = PT.prepare_data(wave, audio_scale, dmin, dmax)
+    ref_data = P.prepare_data(wave, audio_scale, dmin, dmax)
+    for c, rc in zip(data[1], ref_data[1]):
+        assert maxrel(c.cpu().numpy(), rc.numpy()) < 1e-5
+    out = PT.reconstruct_audio(data, msg, m, attack="amplitude_scaling-0.9", audio_scale=audio_scale, data_min=dmin, data_max=dmax)
+    ref, _ = P.reconstruct_audio(ref_data, msg, weights("stress"), attack="amplitude_scaling-0.9", audio_scale=audio_scale,
+                                 data_min=dmin, data_max=dmax)
+    assert l2rel(out[1].numpy(), ref[1].numpy()) < TOL["fp32"]
+    assert l2rel(out[0], ref[0]) < TOL["fp32"]
+    for a, b in zip(out[4], ref[4]):
+        assert maxrel(a, b) < TOL["fp32"]
+    assert abs(out[7] - ref[7]) < 1e-4 and abs(out[5] - ref[5]) < 1e-3 * max(ref[5], 1e-9) + 1e-9
+    assert PT.scale_params("0") == (1.0, 0.0) and PT.scale_params("40") == (40.0, 0.0)
+    with pytest.raises(ValueError):
+        PT.scale_params("0.01-0.1")
+
+
+def test_driver_with_modelA_matches_oracle():
+    """`reconstruct_audio(..., model_name='modelA')` (`audio_test.py:554-556,707-708`): ModelA.forward per clip, ISTFT,
+    attack, STFT, ModelA.decode per clip."""
+    from image_in_speech_watermarking_b200 import audio_test as PT
+    from image_in_speech_watermarking_b200.model import ModelA
+    from oracle import cnn as C
+    oracle = C.randomize_(C.ModelAOracle(), 11)
+    m = ModelA()
+    m.load_state_dict(oracle.state_dict())
+    m = m.cuda().eval()
+    wave = SY.synth_speech(32, 1.0)[None]
+    msg = SY.synth_image_binary(32)[None]
+    out = PT.reconstruct_audio(PT.prepare_data(wave), msg, m, attack="low_pass", model_name='modelA')
+    with torch.no_grad():
+        ref, _ = P.reconstruct_audio(P.prepare_data(wave), msg, oracle, attack="low_pass", model_name='modelA')
+    assert l2rel(out[1].numpy(), ref[1].numpy()) < TOL["fp32"]
+    assert l2rel(out[0], ref[0]) < TOL["fp32"]
+    assert len(out[4]) == len(ref[4])
+    for a, b in zip(out[4], ref[4]):
+        assert np.abs(a - b).max() < 1e-3 * max(1.0, np.abs(b).max())
+    assert abs(out[6] - ref[6]) < 1e-3 * max(1.0, abs(ref[6])) and abs(out[7] - ref[7]) < 1e-3 * max(1.0, abs(ref[7]))
