@@ -79,3 +79,26 @@ def format_result(data_cat, attack, clips_total, mse, wm_loss, wm_loss_att, snr,
     """The `sample_result.txt` line of `uformerWM/evaluate.py:289-291` (parsed by result_extract.py:14).
     PESQ needs the third-party pypesq and is reported as N/A."""
     return RESULT_LINE.format(data_cat, attack, clips_total, mse, wm_loss, wm_loss_att, snr, pesq)
+
+
+def test(model, messages, waves, data_cat='train', result_path=None, attack=None, audio_scale='0', data_max=None,
+         data_min=None, model_name='uformer', draws=None, seed=0):
+    """Batched counterpart of `test()` (`uformerWM/evaluate.py:174-292`): the reference loops over utterances with
+    batch 1, appends python floats to lists and averages them; here all utterances (waves (B,L) CUDA, messages
+    (B or 1,1,32,32)) go through `audio_test.embed_attack_extract` in one pass and only the per-utterance
+    statistics vector leaves the GPU.  Appends the reference's line to `<result_path>/sample_result.txt` (if given)
+    and returns (line, dict of the averaged numbers)."""
+    from . import audio_test as PT
+    r = PT.embed_attack_extract(waves, messages, model, attack or "closed_loop", draws, seed, want_outputs=False,
+                                audio_scale=audio_scale, data_min=data_min, data_max=data_max, model_name=model_name)
+    s = r["stats"].mean(0).cpu().numpy()
+    clips_total = int(r["n_clips"]) * int(waves.shape[0])
+    out = {"clips": clips_total, "mse": float(s[1]), "wm_loss": float(s[2]), "wm_loss_att": float(s[3]), "snr": float(s[0]),
+           "ber_clean": float(r["stats"][:, 4].sum() / (1024.0 * waves.shape[0])),
+           "ber_att": float(r["stats"][:, 5].sum() / r["stats"][:, 6].sum())}
+    line = format_result(data_cat, attack, clips_total, out["mse"], out["wm_loss"], out["wm_loss_att"], out["snr"])
+    if result_path:
+        with open('{}/sample_result.txt'.format(result_path), 'a') as f:
+            f.write('\n')
+            f.write(line)
+    return line, out

@@ -375,3 +375,21 @@ def test_driver_with_modelA_matches_oracle():
     for a, b in zip(out[4], ref[4]):
         assert np.abs(a - b).max() < 1e-3 * max(1.0, np.abs(b).max())
     assert abs(out[6] - ref[6]) < 1e-3 * max(1.0, abs(ref[6])) and abs(out[7] - ref[7]) < 1e-3 * max(1.0, abs(ref[7]))
+
+
+def test_batched_evaluate_writes_the_reference_result_line(models, weights, tmp_path):
+    """`evaluate.test` (batched `uformerWM/evaluate.py:174-292`): averages == mean of the oracle's per-utterance
+    numbers; the line parses with result_extract."""
+    from image_in_speech_watermarking_b200 import evaluate as EV, result_extract as RX
+    m = models("fp32", "stress")
+    B = 2
+    waves = SY.synth_speech_batch(40, B, 1.0).cuda()
+    msgs = torch.stack([SY.synth_image_binary(40 + i) for i in range(B)]).cuda()
+    line, out = EV.test(m, msgs, waves, data_cat='test', result_path=str(tmp_path), attack='echo_addition')
+    evs = [P.evaluate_utterance(waves[i:i + 1].cpu(), msgs[i:i + 1].cpu(), weights("stress"), 'echo_addition') for i in range(B)]
+    assert out["clips"] == sum(e["clips"] for e in evs)
+    assert abs(out["snr"] - np.mean([e["snr"] for e in evs])) < 1e-3
+    assert abs(out["wm_loss_att"] - np.mean([e["wm_loss_att"] for e in evs])) < 1e-4
+    assert abs(out["mse"] - np.mean([e["mse"] for e in evs])) < 1e-3 * np.mean([e["mse"] for e in evs])
+    rows = RX.parse_results(open(tmp_path / "sample_result.txt").read())
+    assert len(rows) == 1 and rows[0]["Set"] == "test" and rows[0]["Attack"] == "echo_addition" and rows[0]["Total Clips"] == out["clips"]

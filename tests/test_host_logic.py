@@ -38,3 +38,14 @@ def test_stats_vector_and_summary():
     assert abs(s["ber_clean"] - 1020.0 / 2048.0) < 1e-12 and abs(s["ber_attacked"] - 6100.0 / 12288.0) < 1e-12
     assert abs(s["mean_snr_db"] - 11.0) < 1e-12 and s["utterances"] == 2
     assert list(SH.shard_range(10, 1, 4)) == [3, 4, 5] and list(SH.shard_range(10, 3, 4)) == [9]
+
+
+def test_result_line_roundtrips_through_result_extract(tmp_path):
+    from image_in_speech_watermarking_b200 import evaluate as EV, result_extract as RX
+    text = "\n" + EV.format_result("train", "awgn-20", 30, 1.5e-5, 0.21, 0.24, 19.7) + \
+           "\n" + EV.format_result("test", "low_pass", 12, 2.5e-5, 0.20, 0.26, 21.3, pesq=3.1)
+    rows = RX.process_data_to_csv(text, str(tmp_path / "results.csv"))
+    assert [r["Attack"] for r in rows] == ["awgn-20", "low_pass"] and rows[0]["Total Clips"] == 30
+    assert rows[0]["PESQ Score"] == "" and rows[1]["PESQ Score"] == 3.1 and abs(rows[1]["SNR Score"] - 21.3) < 1e-12
+    head = open(tmp_path / "results.csv").read().splitlines()[0]
+    assert head == "Set,Attack,Total Clips,MSE Loss,WM Loss,WM Loss After Attack,SNR Score,PESQ Score"
