@@ -44,7 +44,7 @@ SIGNATURES = {
     "wmk_convT2x2_wgrad_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "wmk_affine_f32": (_i, [_vp, _vp, _sz, _f, _f, _vp]),
     "wmk_mse_f32": (_i, [_vp, _vp, _vp, _sz, _f, _vp, _vp]),
-    "wmk_adam_step_f32": (_i, [_vp, _vp, _vp, _vp, _sz, _f, _f, _f, _f, _f, _i, _f, _i, _vp]),
+    "wmk_adam_step_f32": (_i, [_vp, _vp, _vp, _vp, _sz, _f, _f, _f, _f, _f, _i, _f, _i, _vp, _vp]),
     "wmk_noise_mix_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "wmk_noise_crop_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "wmk_noise_resize_nearest_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _f, _vp]),

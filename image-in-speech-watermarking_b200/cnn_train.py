@@ -264,10 +264,14 @@ class FlatAdam:
         self.m = torch.zeros_like(self.grad)
         self.v = torch.zeros_like(self.grad)
         self.t = 0
+        self.step_dev = torch.zeros(1, device=dev, dtype=torch.int32)       # completed steps (graph-replayable counter)
 
-    def zero_grad(self):
+    def zero_grad(self, set_to_none=True):
         for p in self.params:
-            p.grad = None
+            if set_to_none:
+                p.grad = None
+            elif p.grad is not None:
+                p.grad.zero_()
 
     def gather_grads(self):
         o = 0
@@ -286,7 +290,7 @@ class FlatAdam:
         self.t += 1
         _lib.check(lib.wmk_adam_step_f32(_lib.ptr(self.flat), _lib.ptr(self.grad), _lib.ptr(self.m), _lib.ptr(self.v),
                                          self.flat.numel(), self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
-                                         self.t, grad_scale, int(self.decoupled), _lib.stream_ptr()))
+                                         self.t, grad_scale, int(self.decoupled), _lib.ptr(self.step_dev), _lib.stream_ptr()))
         o = 0
         with torch.no_grad():
             for p in self.params:

@@ -324,12 +324,22 @@ mse_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __re
 }
 
 // ---- Adam / AdamW over a flat parameter buffer (torch.optim.Adam semantics, train_modelA.py:234-236)
+// step_dev (optional): device-resident step counter, so that the launch can be replayed from a CUDA graph: the
+// kernel reads the count of COMPLETED steps, uses count + 1 for the bias corrections, and thread 0 of the LAST block
+// to finish nothing - the increment is a separate 1-thread kernel launched after this one (adam_tick_kernel).
+__global__ void adam_tick_kernel(int* step_dev) { *step_dev += 1; }
+
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, size_t n,
             float lr, float beta1, float beta2, float eps, float weight_decay, float bc1, float bc2, float grad_scale,
-            int decoupled) {
+            int decoupled, const int* __restrict__ step_dev) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (step_dev) {
+    const float t = (float)(*step_dev + 1);
+    bc1 = 1.f - powf(beta1, t);
+    bc2 = 1.f - powf(beta2, t);
+  }
   float grad = g[i] * grad_scale, w = p[i];
   if (decoupled) w *= 1.f - lr * weight_decay;        // AdamW
   else grad = fmaf(weight_decay, w, grad);            // Adam with L2 penalty
@@ -496,14 +506,18 @@ extern "C" int wmk_mse_f32(const float* a, const float* b, float* grad_a, size_t
 
 extern "C" int wmk_adam_step_f32(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, size_t n, float lr,
                                  float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
-                                 int decoupled, void* stream) {
-  WMK_REQUIRE(params && grads && exp_avg && exp_avg_sq && n > 0 && step >= 1, "adam_step: bad arguments");
+                                 int decoupled, int* step_dev, void* stream) {
+  WMK_REQUIRE(params && grads && exp_avg && exp_avg_sq && n > 0 && (step >= 1 || step_dev), "adam_step: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
   ProfScope prof(FAM_SMALL, 28.0 * n, st);
-  const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
+  const float bc1 = 1.f - powf(beta1, (float)(step >= 1 ? step : 1)), bc2 = 1.f - powf(beta2, (float)(step >= 1 ? step : 1));
   adam_kernel<<<grid_for(n), 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2,
-                                           grad_scale, decoupled);
+                                           grad_scale, decoupled, step_dev);
   WMK_CHECK_LAUNCH("adam_kernel");
+  if (step_dev) {
+    adam_tick_kernel<<<1, 1, 0, st>>>(step_dev);
+    WMK_CHECK_LAUNCH("adam_tick_kernel");
+  }
   return 0;
 }
 

@@ -48,3 +48,4 @@ def train_step(model, optimizer, input_, message, loss_scale=1.0):
     world = sync_gradients(optimizer.gather_grads())
     optimizer.step(grad_scale=1.0 / (loss_scale * world))
     return loss.detach(), loss1.detach(), loss2.detach()
+

@@ -187,10 +187,12 @@ int wmk_mse_f32(const float* a, const float* b, float* grad_a, size_t n, float g
                 double* loss_accum, void* stream);
 /* torch.optim.Adam (decoupled = 0, weight decay as L2 penalty) / AdamW (decoupled = 1) over a flat
  * buffer; grads are multiplied by grad_scale first (1 / world size after a sum all-reduce);
- * step counts from 1 */
+ * step counts from 1.  step_dev (may be NULL): device int holding the number of completed steps - when given
+ * it overrides `step` (bias corrections from *step_dev + 1) and is incremented after the update, which makes the
+ * launch replayable from a CUDA graph */
 int wmk_adam_step_f32(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, size_t n,
                       float lr, float beta1, float beta2, float eps, float weight_decay, int step,
-                      float grad_scale, int decoupled, void* stream);
+                      float grad_scale, int decoupled, int* step_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * HiDDeN noise layers (hidden/noise_layers/), `planes` = B*C images of H x W, float32.

@@ -270,3 +270,4 @@ def test_modelA_attack_in_the_loop_and_adam_match_torch(golden):
     before = opt.flat.clone()
     loss, l1, l2 = TM.train_step(m2, opt, x.cuda(), wm.cuda())
     assert torch.isfinite(loss) and float((opt.flat - before).abs().max()) > 0
+

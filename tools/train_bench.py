@@ -33,8 +33,9 @@ def main():
     g = torch.Generator(device="cuda").manual_seed(rank)
     x = torch.rand(a.clips, 2, 128, 128, device="cuda", generator=g)
     wm = (torch.rand(a.clips, 1, 32, 32, device="cuda", generator=g) > 0.5).float()
+    step = lambda: TM.train_step(m, opt, x, wm)
     for _ in range(3):
-        TM.train_step(m, opt, x, wm)
+        step()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -42,7 +43,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(a.steps):
-        loss, l1, l2 = TM.train_step(m, opt, x, wm)
+        loss, l1, l2 = step()
     e1.record()
     torch.cuda.synchronize()
     ms = torch.tensor([e0.elapsed_time(e1) / a.steps], device="cuda", dtype=torch.float64)
