@@ -27,20 +27,21 @@ __device__ __forceinline__ float act_grad_from_out(float y, int act, float slope
 }
 
 // ---- BatchNorm2d (training): per-channel sums over (B, H, W)
-// grid (chunks, C): stats[c] = {sum x, sum x^2}  (fp64 atomics)
+// grid (chunks, C): stats[c] = {sum x, sum x^2}  (fp64 atomics); 16-byte loads (HW is a multiple of 4)
 __global__ void __launch_bounds__(256)
 bn_stats_kernel(const float* __restrict__ x, int B, int C, int HW, double* __restrict__ stats) {
   const int c = blockIdx.y;
-  const size_t n = (size_t)B * HW;
-  float s1 = 0.f, s2 = 0.f;      // per-thread partials stay short (<= a few thousand terms); fp64 beyond
+  const int hw4 = HW >> 2;
+  const size_t n4 = (size_t)B * hw4;
+  float s1 = 0.f, s2 = 0.f;      // per-thread partials stay short; fp64 beyond
   double d1 = 0.0, d2 = 0.0;
   int cnt = 0;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const size_t b = i / HW, r = i - b * HW;
-    const float v = x[(b * C + c) * HW + r];
-    s1 += v;
-    s2 = fmaf(v, v, s2);
-    if (++cnt == 1024) { d1 += s1; d2 += s2; s1 = s2 = 0.f; cnt = 0; }
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t b = i / hw4, r = i - b * hw4;
+    const float4 v = reinterpret_cast<const float4*>(x + (b * C + c) * HW)[r];
+    s1 += (v.x + v.y) + (v.z + v.w);
+    s2 = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, s2))));
+    if (++cnt == 256) { d1 += s1; d2 += s2; s1 = s2 = 0.f; cnt = 0; }
   }
   d1 += s1; d2 += s2;
   d1 = warp_sum(d1); d2 = warp_sum(d2);
@@ -68,16 +69,21 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, int C, doub
   }
 }
 
-// y = act(gamma * (x - mean) * rstd + beta)
+// y = act(gamma * (x - mean) * rstd + beta); one thread = 4 consecutive elements of one plane
 __global__ void __launch_bounds__(256)
 bn_act_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ mean_rstd,
-                  const float* __restrict__ gamma, const float* __restrict__ beta, size_t total, int C, int HW, int act,
+                  const float* __restrict__ gamma, const float* __restrict__ beta, size_t total4, int C, int HW, int act,
                   float slope) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int c = (int)((i / HW) % C);
-  const float xh = (x[i] - mean_rstd[2 * c]) * mean_rstd[2 * c + 1];
-  y[i] = act_fwd(fmaf(gamma[c], xh, beta[c]), act, slope);
+  if (i >= total4) return;
+  const int c = (int)((i / (HW >> 2)) % C);
+  const float mean = mean_rstd[2 * c], rstd = mean_rstd[2 * c + 1], g = gamma[c], be = beta[c];
+  float4 v = reinterpret_cast<const float4*>(x)[i];
+  v.x = act_fwd(fmaf(g, (v.x - mean) * rstd, be), act, slope);
+  v.y = act_fwd(fmaf(g, (v.y - mean) * rstd, be), act, slope);
+  v.z = act_fwd(fmaf(g, (v.z - mean) * rstd, be), act, slope);
+  v.w = act_fwd(fmaf(g, (v.w - mean) * rstd, be), act, slope);
+  reinterpret_cast<float4*>(y)[i] = v;
 }
 
 // backward pass 1: dz = dy * act'(y); sums[c] = {sum dz, sum dz * xhat}
@@ -86,18 +92,22 @@ bn_act_bwd_reduce_kernel(const float* __restrict__ x, const float* __restrict__ 
                          const float* __restrict__ mean_rstd, int B, int C, int HW, int act, float slope,
                          double* __restrict__ sums) {
   const int c = blockIdx.y;
-  const size_t n = (size_t)B * HW;
+  const int hw4 = HW >> 2;
+  const size_t n4 = (size_t)B * hw4;
   const float mean = mean_rstd[2 * c], rstd = mean_rstd[2 * c + 1];
   float s1 = 0.f, s2 = 0.f;
   double d1 = 0.0, d2 = 0.0;
   int cnt = 0;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const size_t b = i / HW, r = i - b * HW;
-    const size_t o = (b * C + c) * HW + r;
-    const float dz = dy[o] * act_grad_from_out(y[o], act, slope);
-    s1 += dz;
-    s2 = fmaf(dz, (x[o] - mean) * rstd, s2);
-    if (++cnt == 1024) { d1 += s1; d2 += s2; s1 = s2 = 0.f; cnt = 0; }
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t b = i / hw4, r = i - b * hw4;
+    const size_t o = ((b * C + c) * HW >> 2) + r;
+    const float4 xv = reinterpret_cast<const float4*>(x)[o], yv = reinterpret_cast<const float4*>(y)[o],
+                 gv = reinterpret_cast<const float4*>(dy)[o];
+    const float z0 = gv.x * act_grad_from_out(yv.x, act, slope), z1 = gv.y * act_grad_from_out(yv.y, act, slope);
+    const float z2 = gv.z * act_grad_from_out(yv.z, act, slope), z3 = gv.w * act_grad_from_out(yv.w, act, slope);
+    s1 += (z0 + z1) + (z2 + z3);
+    s2 = fmaf(z0, (xv.x - mean) * rstd, fmaf(z1, (xv.y - mean) * rstd, fmaf(z2, (xv.z - mean) * rstd, fmaf(z3, (xv.w - mean) * rstd, s2))));
+    if (++cnt == 256) { d1 += s1; d2 += s2; s1 = s2 = 0.f; cnt = 0; }
   }
   d1 += s1; d2 += s2;
   d1 = warp_sum(d1); d2 = warp_sum(d2);
@@ -107,24 +117,29 @@ bn_act_bwd_reduce_kernel(const float* __restrict__ x, const float* __restrict__ 
   }
 }
 
-// backward pass 2: dx = gamma * rstd * (dz - mean(dz) - xhat * mean(dz * xhat)); thread 0 of channel rows writes dgamma / dbeta
+// backward pass 2: dx = gamma * rstd * (dz - mean(dz) - xhat * mean(dz * xhat)); the first C threads also write dgamma / dbeta
 __global__ void __launch_bounds__(256)
 bn_act_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ dy,
                         float* __restrict__ dx, const float* __restrict__ mean_rstd, const float* __restrict__ gamma,
-                        const double* __restrict__ sums, size_t total, int C, int HW, double n, int act, float slope,
+                        const double* __restrict__ sums, size_t total4, int C, int HW, double n, int act, float slope,
                         float* __restrict__ dgamma, float* __restrict__ dbeta) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < (size_t)C) {
     dgamma[i] = (float)sums[2 * i + 1];
     dbeta[i] = (float)sums[2 * i];
   }
-  if (i >= total) return;
-  const int c = (int)((i / HW) % C);
-  const float rstd = mean_rstd[2 * c + 1];
-  const float xh = (x[i] - mean_rstd[2 * c]) * rstd;
-  const float dz = dy[i] * act_grad_from_out(y[i], act, slope);
-  const float m1 = (float)(sums[2 * c] / n), m2 = (float)(sums[2 * c + 1] / n);
-  dx[i] = gamma[c] * rstd * (dz - m1 - xh * m2);
+  if (i >= total4) return;
+  const int c = (int)((i / (HW >> 2)) % C);
+  const float mean = mean_rstd[2 * c], rstd = mean_rstd[2 * c + 1];
+  const float m1 = (float)(sums[2 * c] / n), m2 = (float)(sums[2 * c + 1] / n), gr = gamma[c] * rstd;
+  const float4 xv = reinterpret_cast<const float4*>(x)[i], yv = reinterpret_cast<const float4*>(y)[i],
+               gv = reinterpret_cast<const float4*>(dy)[i];
+  float4 o;
+  o.x = gr * (gv.x * act_grad_from_out(yv.x, act, slope) - m1 - (xv.x - mean) * rstd * m2);
+  o.y = gr * (gv.y * act_grad_from_out(yv.y, act, slope) - m1 - (xv.y - mean) * rstd * m2);
+  o.z = gr * (gv.z * act_grad_from_out(yv.z, act, slope) - m1 - (xv.z - mean) * rstd * m2);
+  o.w = gr * (gv.w * act_grad_from_out(yv.w, act, slope) - m1 - (xv.w - mean) * rstd * m2);
+  reinterpret_cast<float4*>(dx)[i] = o;
 }
 
 // MaxPool2d(2,2) backward: the gradient goes to the first maximum of each window (PyTorch's scan order)
@@ -375,20 +390,21 @@ using namespace wmk;
 extern "C" int wmk_bn_train_fwd_f32(const float* x, float* y, const float* gamma, const float* beta, float* running_mean,
                                     float* running_var, float* mean_rstd, double* scratch, int B, int C, int HW, float eps,
                                     float momentum, int act, float slope, void* stream) {
-  WMK_REQUIRE(x && y && gamma && beta && mean_rstd && scratch && B > 0 && C > 0 && HW > 0 && act >= 0 && act <= 3,
-              "bn_train_fwd: bad arguments");
+  WMK_REQUIRE(x && y && gamma && beta && mean_rstd && scratch && B > 0 && C > 0 && HW > 0 && HW % 4 == 0 && act >= 0 &&
+                  act <= 3 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0,
+              "bn_train_fwd: bad arguments (H*W must be a multiple of 4, buffers 16-byte aligned)");
   cudaStream_t st = (cudaStream_t)stream;
   const size_t total = (size_t)B * C * HW;
   ProfScope prof(FAM_SMALL, 12.0 * total, st);
   WMK_CHECK_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * C, st));
   const size_t per_c = (size_t)B * HW;
-  int chunks = (int)((per_c + 256 * 16 - 1) / (256 * 16));
-  if (chunks > 2048) chunks = 2048;
+  int chunks = (int)((per_c / 4 + 256 * 8 - 1) / (256 * 8));
+  if (chunks > 1184) chunks = 1184;
   bn_stats_kernel<<<dim3(chunks, C), 256, 0, st>>>(x, B, C, HW, scratch);
   WMK_CHECK_LAUNCH("bn_stats_kernel");
   bn_finalize_kernel<<<cdiv(C, 64), 64, 0, st>>>(scratch, C, (double)per_c, eps, momentum, mean_rstd, running_mean, running_var);
   WMK_CHECK_LAUNCH("bn_finalize_kernel");
-  bn_act_fwd_kernel<<<grid_for(total), 256, 0, st>>>(x, y, mean_rstd, gamma, beta, total, C, HW, act, slope);
+  bn_act_fwd_kernel<<<grid_for(total / 4), 256, 0, st>>>(x, y, mean_rstd, gamma, beta, total / 4, C, HW, act, slope);
   WMK_CHECK_LAUNCH("bn_act_fwd_kernel");
   return 0;
 }
@@ -396,18 +412,19 @@ extern "C" int wmk_bn_train_fwd_f32(const float* x, float* y, const float* gamma
 extern "C" int wmk_bn_train_bwd_f32(const float* x, const float* y, const float* dy, float* dx, const float* gamma,
                                     const float* mean_rstd, float* dgamma, float* dbeta, double* scratch, int B, int C,
                                     int HW, int act, float slope, void* stream) {
-  WMK_REQUIRE(x && y && dy && dx && gamma && mean_rstd && dgamma && dbeta && scratch && B > 0 && C > 0 && HW > 0,
-              "bn_train_bwd: bad arguments");
+  WMK_REQUIRE(x && y && dy && dx && gamma && mean_rstd && dgamma && dbeta && scratch && B > 0 && C > 0 && HW > 0 && HW % 4 == 0 &&
+                  (size_t)C <= (size_t)B * C * HW / 4,
+              "bn_train_bwd: bad arguments (H*W must be a multiple of 4)");
   cudaStream_t st = (cudaStream_t)stream;
   const size_t total = (size_t)B * C * HW;
   ProfScope prof(FAM_SMALL, 28.0 * total, st);
   WMK_CHECK_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * C, st));
   const size_t per_c = (size_t)B * HW;
-  int chunks = (int)((per_c + 256 * 16 - 1) / (256 * 16));
-  if (chunks > 2048) chunks = 2048;
+  int chunks = (int)((per_c / 4 + 256 * 8 - 1) / (256 * 8));
+  if (chunks > 1184) chunks = 1184;
   bn_act_bwd_reduce_kernel<<<dim3(chunks, C), 256, 0, st>>>(x, y, dy, mean_rstd, B, C, HW, act, slope, scratch);
   WMK_CHECK_LAUNCH("bn_act_bwd_reduce_kernel");
-  bn_act_bwd_apply_kernel<<<grid_for(total), 256, 0, st>>>(x, y, dy, dx, mean_rstd, gamma, scratch, total, C, HW,
+  bn_act_bwd_apply_kernel<<<grid_for(total / 4), 256, 0, st>>>(x, y, dy, dx, mean_rstd, gamma, scratch, total / 4, C, HW,
                                                            (double)per_c, act, slope, dgamma, dbeta);
   WMK_CHECK_LAUNCH("bn_act_bwd_apply_kernel");
   return 0;

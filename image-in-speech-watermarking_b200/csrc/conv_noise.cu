@@ -31,7 +31,7 @@ conv3x3_kernel(const float* __restrict__ x, float* __restrict__ y, const float* 
                const float* __restrict__ bias, const float* __restrict__ scale, const float* __restrict__ shift,
                int Cin, int Cout, int H, int W, int co_off, int Ctot, int act, float slope) {
   __shared__ float tile[CIB][CT + 2][CT + 2];
-  __shared__ float ws[CIB][9][COB];
+  __shared__ __align__(16) float ws[CIB][9][COB];
   const int tiles_w = (W + CT - 1) / CT;
   const int th = blockIdx.x / tiles_w, tw = blockIdx.x % tiles_w;
   const int co0 = blockIdx.y * COB;
@@ -63,8 +63,15 @@ conv3x3_kernel(const float* __restrict__ x, float* __restrict__ y, const float* 
 #pragma unroll
       for (int t = 0; t < 9; ++t) {
         const float v = tile[ci][ty + t / 3][tx + t % 3];
+        const float4* w4 = reinterpret_cast<const float4*>(&ws[ci][t][0]);      // 4 weights per shared-memory load
 #pragma unroll
-        for (int j = 0; j < COB; ++j) acc[j] = fmaf(v, ws[ci][t][j], acc[j]);
+        for (int j4 = 0; j4 < COB / 4; ++j4) {
+          const float4 wv = w4[j4];
+          acc[4 * j4] = fmaf(v, wv.x, acc[4 * j4]);
+          acc[4 * j4 + 1] = fmaf(v, wv.y, acc[4 * j4 + 1]);
+          acc[4 * j4 + 2] = fmaf(v, wv.z, acc[4 * j4 + 2]);
+          acc[4 * j4 + 3] = fmaf(v, wv.w, acc[4 * j4 + 3]);
+        }
       }
   }
   if (h >= H || wq >= W) return;

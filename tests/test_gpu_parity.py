@@ -392,4 +392,4 @@ def test_batched_evaluate_writes_the_reference_result_line(models, weights, tmp_
     assert abs(out["wm_loss_att"] - np.mean([e["wm_loss_att"] for e in evs])) < 1e-4
     assert abs(out["mse"] - np.mean([e["mse"] for e in evs])) < 1e-3 * np.mean([e["mse"] for e in evs])
     rows = RX.parse_results(open(tmp_path / "sample_result.txt").read())
-    assert len(rows) == 1 and rows[0]["Set"] == "test" and rows[0]["Attack"] == "echo_addition" and rows[0]["Total Clips"] == out["clips"]
+    assert len(rows) == 1 and rows[0]["Set"] == "test set" and rows[0]["Attack"] == "echo_addition" and rows[0]["Total Clips"] == out["clips"]
