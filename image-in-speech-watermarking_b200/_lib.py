@@ -35,6 +35,10 @@ SIGNATURES = {
     "wmk_conv3x3_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp]),
     "wmk_convT2x2_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp]),
     "wmk_maxpool2x2_f32": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "wmk_conv3x3_c1_nhwc_bf16": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "wmk_conv3x3_nhwc_bf16_tc": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "wmk_maxpool2x2_nhwc_bf16": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "wmk_conv3x3_nhwc_to1_f32": (_i, [_vp, _vp, _vp, _f, _f, _f, _i, _i, _i, _i, _vp]),
     "wmk_bn_train_fwd_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _f, _i, _f, _vp]),
     "wmk_bn_train_bwd_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
     "wmk_maxpool2x2_bwd_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),

@@ -310,6 +310,112 @@ magphase_merge_kernel(const float* __restrict__ mag, const float* __restrict__ p
   spec[(2 * b + 1) * plane + r] = mag[i] * sn;
 }
 
+// ---------------------------------------------------------------------------- tensor-core path of the HiDDeN decoder
+// (hidden/model/decoder.py:12-40): activations NHWC bf16, the 64 -> 64 / 64 -> message_length ConvBNRelu layers run as
+// implicit GEMMs on tcgen05 (gemm_tcgen05.cu, conv_H mode); these are the layout-changing layers around them.
+// first layer: Conv2d(1, 64, 3, p=1) + BN + ReLU, NCHW fp32 [B][1][H][W] -> NHWC bf16 [B][H][W][64]; thread = pixel x 8 channels
+__global__ void __launch_bounds__(256)
+conv3x3_c1_nhwc_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, const float* __restrict__ w,
+                       const float* __restrict__ bias, const float* __restrict__ scale, const float* __restrict__ shift,
+                       size_t npix, int H, int W) {
+  __shared__ float ws[64 * 9], sc[64], sh[64];
+  for (int i = threadIdx.x; i < 576; i += 256) ws[i] = w[i];
+  if (threadIdx.x < 64) {
+    const float s = scale ? scale[threadIdx.x] : 1.f;
+    sc[threadIdx.x] = s;
+    sh[threadIdx.x] = (bias ? bias[threadIdx.x] : 0.f) * s + (shift ? shift[threadIdx.x] : 0.f);
+  }
+  __syncthreads();
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= npix * 8) return;
+  const int g8 = (int)(idx & 7);
+  const size_t pix = idx >> 3;
+  const int wq = (int)(pix % W), h = (int)((pix / W) % H);
+  const size_t b = pix / ((size_t)H * W);
+  float v[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const int hh = h + t / 3 - 1, ww = wq + t % 3 - 1;
+    v[t] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? x[(b * H + hh) * W + ww] : 0.f;
+  }
+  uint32_t o[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float r[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int co = g8 * 8 + 2 * j + e;
+      float a = 0.f;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) a = fmaf(v[t], ws[co * 9 + t], a);
+      r[e] = fmaxf(fmaf(a, sc[co], sh[co]), 0.f);
+    }
+    o[j] = pack_bf16(r[0], r[1]);
+  }
+  *reinterpret_cast<uint4*>(y + pix * 64 + g8 * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+// MaxPool2d(2,2) on NHWC bf16 [B][H][W][C] (C multiple of 8); thread = output pixel x 8 channels
+__global__ void __launch_bounds__(256)
+maxpool2x2_nhwc_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, size_t total, int H, int W, int C) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int cg = C >> 3, Ho = H >> 1, Wo = W >> 1;
+  const int g8 = (int)(idx % cg);
+  size_t r = idx / cg;
+  const int wo = (int)(r % Wo), ho = (int)((r / Wo) % Ho);
+  const size_t b = r / ((size_t)Wo * Ho);
+  const __nv_bfloat16* s = x + (((b * H + 2 * ho) * W + 2 * wo) * C + g8 * 8);
+  const uint4 a = *reinterpret_cast<const uint4*>(s), bq = *reinterpret_cast<const uint4*>(s + C);
+  const uint4 c = *reinterpret_cast<const uint4*>(s + (size_t)W * C), d = *reinterpret_cast<const uint4*>(s + (size_t)W * C + C);
+  const uint32_t av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {bq.x, bq.y, bq.z, bq.w}, cv[4] = {c.x, c.y, c.z, c.w}, dv[4] = {d.x, d.y, d.z, d.w};
+  uint32_t o[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const __nv_bfloat162 m = __hmax2(__hmax2(*reinterpret_cast<const __nv_bfloat162*>(&av[j]), *reinterpret_cast<const __nv_bfloat162*>(&bv[j])),
+                                     __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&cv[j]), *reinterpret_cast<const __nv_bfloat162*>(&dv[j])));
+    o[j] = *reinterpret_cast<const uint32_t*>(&m);
+  }
+  *reinterpret_cast<uint4*>(y + (((b * Ho + ho) * Wo + wo) * C + g8 * 8)) = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+// last layer: Conv2d(Cin, 1, 3, p=1) + BN + ReLU from NHWC bf16 [B][H][W][Cp] (Cp = Cin padded to a multiple of 8, padding
+// channels ignored) to NCHW fp32 [B][1][H][W]; wt: [9][Cp] fp32 (tap-major, zero in the padding channels); a warp-quarter
+// (8 lanes) shares one pixel, each lane owning 8-channel groups
+__global__ void __launch_bounds__(256)
+conv3x3_nhwc_to1_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, const float* __restrict__ wt, float bias,
+                        float scale, float shift, size_t npix, int H, int W, int Cp) {
+  extern __shared__ float wsm[];                  // [9][Cp]
+  for (int i = threadIdx.x; i < 9 * Cp; i += 256) wsm[i] = wt[i];
+  __syncthreads();
+  const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t pix = gid >> 2;
+  const int part = (int)(gid & 3);                // 4 lanes per pixel
+  float a = 0.f;
+  if (pix < npix) {
+    const int wq = (int)(pix % W), h = (int)((pix / W) % H);
+    const size_t b = pix / ((size_t)H * W);
+    for (int t = 0; t < 9; ++t) {
+      const int hh = h + t / 3 - 1, ww = wq + t % 3 - 1;
+      if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
+      const __nv_bfloat16* s = x + ((b * H + hh) * W + ww) * Cp;
+      for (int c8 = part * 8; c8 < Cp; c8 += 32) {
+        const uint4 u = *reinterpret_cast<const uint4*>(s + c8);
+        const uint32_t uv[4] = {u.x, u.y, u.z, u.w};
+        const float* wp = wsm + t * Cp + c8;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          a = fmaf(__uint_as_float(uv[j] << 16), wp[2 * j], a);
+          a = fmaf(__uint_as_float(uv[j] & 0xffff0000u), wp[2 * j + 1], a);
+        }
+      }
+    }
+  }
+  a += __shfl_xor_sync(0xffffffffu, a, 1);
+  a += __shfl_xor_sync(0xffffffffu, a, 2);
+  if (part == 0 && pix < npix) y[pix] = fmaxf(fmaf(a + bias, scale, shift), 0.f);
+}
+
 }  // namespace
 }  // namespace wmk
 
@@ -450,5 +556,49 @@ extern "C" int wmk_magphase_merge_f32(const float* mag, const float* phase, floa
   ProfScope prof(FAM_ATTACK, 16.0 * n * plane, st);
   magphase_merge_kernel<<<cdiv(n * plane, 256), 256, 0, st>>>(mag, phase, spec, n, plane);
   WMK_CHECK_LAUNCH("magphase_merge_kernel");
+  return 0;
+}
+
+extern "C" int wmk_conv3x3_c1_nhwc_bf16(const float* x, void* y, const float* w, const float* bias, const float* scale,
+                                        const float* shift, int B, int H, int W, void* stream) {
+  WMK_REQUIRE(x && y && w && B > 0 && H > 0 && W > 0 && ((uintptr_t)y & 15) == 0, "conv3x3_c1_nhwc: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t npix = (size_t)B * H * W;
+  ProfScope prof(FAM_SMALL, npix * (4.0 + 128.0), st);
+  conv3x3_c1_nhwc_kernel<<<cdiv(npix * 8, 256), 256, 0, st>>>(x, reinterpret_cast<__nv_bfloat16*>(y), w, bias, scale, shift, npix, H, W);
+  WMK_CHECK_LAUNCH("conv3x3_c1_nhwc_kernel");
+  return 0;
+}
+
+extern "C" int wmk_conv3x3_nhwc_bf16_tc(const void* x, void* y, const void* w_packed, const float* bias, int B, int H, int W,
+                                        int Cout, void* stream) {
+  WMK_REQUIRE(x && y && w_packed && bias && B > 0 && H > 0 && W == 128 && (Cout == 32 || Cout == 64),
+              "conv3x3_nhwc_bf16_tc: needs W = 128, 64 input channels and Cout in {32, 64}");
+  GemmArgs g;
+  g.A = x; g.W = w_packed; g.bias = bias; g.C = y; g.M = B * H * 128; g.N = Cout; g.K = 576; g.ldc = Cout;
+  g.epi = EPI_BIAS_RELU; g.out_bf16 = 1; g.conv_H = H; g.conv_B = B;
+  return gemm_bf16_tcgen05(g, (cudaStream_t)stream);
+}
+
+extern "C" int wmk_maxpool2x2_nhwc_bf16(const void* x, void* y, int B, int H, int W, int C, void* stream) {
+  WMK_REQUIRE(x && y && B > 0 && H >= 2 && W >= 2 && H % 2 == 0 && W % 2 == 0 && C % 8 == 0, "maxpool2x2_nhwc: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t total = (size_t)B * (H / 2) * (W / 2) * (C / 8);
+  ProfScope prof(FAM_SMALL, 2.5 * B * H * W * C, st);
+  maxpool2x2_nhwc_kernel<<<cdiv(total, 256), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(y),
+                                                           total, H, W, C);
+  WMK_CHECK_LAUNCH("maxpool2x2_nhwc_kernel");
+  return 0;
+}
+
+extern "C" int wmk_conv3x3_nhwc_to1_f32(const void* x, float* y, const float* wt, float bias, float scale, float shift, int B,
+                                        int H, int W, int Cp, void* stream) {
+  WMK_REQUIRE(x && y && wt && B > 0 && H > 0 && W > 0 && Cp % 8 == 0 && Cp <= 256, "conv3x3_nhwc_to1: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t npix = (size_t)B * H * W;
+  ProfScope prof(FAM_SMALL, npix * (2.0 * Cp + 4.0), st);
+  conv3x3_nhwc_to1_kernel<<<cdiv(npix * 4, 256), 256, 9 * Cp * sizeof(float), st>>>(reinterpret_cast<const __nv_bfloat16*>(x), y, wt, bias,
+                                                                                   scale, shift, npix, H, W, Cp);
+  WMK_CHECK_LAUNCH("conv3x3_nhwc_to1_kernel");
   return 0;
 }

@@ -292,7 +292,12 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __
           mbar_wait(empty_bar(s), ph ^ 1u);
           mbar_arrive_expect_tx(full_bar(s), STAGE);
           const uint32_t sa = stages + (uint32_t)s * STAGE;
-          tma_load_2d(sa, &tmA, kb * BK, m0, full_bar(s));
+          if (p.conv_H > 0) {          // implicit GEMM: tap kb of the 3x3 window = the image row shifted by (dy-1, dx-1)
+            const int rowi = m0 >> 7, img = rowi / p.conv_H, h = rowi - img * p.conv_H;
+            tma_load_4d(sa, &tmA, 0, kb % 3 - 1, h + kb / 3 - 1, img, full_bar(s));
+          } else {
+            tma_load_2d(sa, &tmA, kb * BK, m0, full_bar(s));
+          }
           if (!w_stationary) tma_load_2d(sa + A_BYTES, &tmW, kb * BK, n0, full_bar(s));
         }
       }
@@ -372,6 +377,9 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __
               const float2 gq = gelu_tanh2(make_float2(f[2 * j], f[2 * j + 1]));
               f[2 * j] = gq.x; f[2 * j + 1] = gq.y;
             }
+          } else if constexpr (EPI == EPI_BIAS_RELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
           } else if constexpr (EPI == EPI_BIAS_RESID) {
             if (cc == 0) {
 #pragma unroll
@@ -563,7 +571,14 @@ int make_map(CUtensorMap* map, const void* ptr, int rows, int K, int box_rows) {
 template <int BN, int EPI, bool OUT_BF16, bool LN = false>
 int launch_persistent_t(const GemmArgs& g, cudaStream_t st) {
   CUtensorMap tmA, tmW, tmC, tmD;
-  WMK_TRY(make_map(&tmA, g.A, g.M, g.K, BM));
+  if (g.conv_H > 0) {
+    const uint64_t dims[4] = {64, 128, (uint64_t)g.conv_H, (uint64_t)g.conv_B};
+    const uint64_t strides[3] = {128, 128ull * 128, 128ull * 128 * (uint64_t)g.conv_H};
+    const uint32_t box[4] = {64, 128, 1, 1};
+    WMK_TRY(make_tensor_map(&tmA, g.A, 4, dims, strides, box, false, 128));
+  } else {
+    WMK_TRY(make_map(&tmA, g.A, g.M, g.K, BM));
+  }
   WMK_TRY(make_map(&tmW, g.W, g.N, g.K, BN));
   WMK_TRY(make_map_ex(&tmC, g.C, g.M, g.ldc, 32, epi_box_cols(BN, OUT_BF16), !OUT_BF16));
   if (LN) WMK_TRY(make_map_ex(&tmD, g.ln_out, g.M, g.N, 32, 32, false));
@@ -574,7 +589,7 @@ int launch_persistent_t(const GemmArgs& g, cudaStream_t st) {
   const int n_tiles = g.N / BN, m_tiles = cdiv(g.M, BM);
   const int w_bytes = kblocks * BN * BK * 2;
   // weight-stationary when the whole BN x K tile + >= 2 A stages fit and every N tile gets >= 1 CTA
-  const int ws = (kblocks <= 4 && w_bytes + 2 * BM * BK * 2 + fixed <= budget && n_tiles <= num_sms() &&
+  const int ws = (g.conv_H == 0 && kblocks <= 4 && w_bytes + 2 * BM * BK * 2 + fixed <= budget && n_tiles <= num_sms() &&
                   m_tiles >= 2 * (num_sms() / n_tiles)) ? 1 : 0;
   const int stage = ws ? BM * BK * 2 : (BM + BN) * BK * 2;
   const int avail = budget - fixed - (ws ? w_bytes : 0);
@@ -589,6 +604,7 @@ int launch_persistent_t(const GemmArgs& g, cudaStream_t st) {
   }
   EpiParams p{g.bias, g.resid, g.C, g.M, g.N, g.ldc, g.epi, g.out_bf16, g.up_h, g.up_w, g.up_cout};
   p.ln_gamma = g.ln_gamma; p.ln_beta = g.ln_beta; p.ln_mod = g.ln_mod; p.ln_H = g.ln_H; p.ln_shift = g.ln_shift;
+  p.conv_H = g.conv_H;
   const long long total = (long long)m_tiles * n_tiles;
   const int grid = ws ? (num_sms() / n_tiles) * n_tiles : (int)(total < num_sms() ? total : num_sms());
   gemm_tcgen05_persistent_kernel<BN, EPI, OUT_BF16, LN><<<grid, kPThreads, smem, st>>>(tmA, tmW, tmC, tmD, p, g.K, m_tiles,
@@ -602,6 +618,13 @@ int launch_persistent(const GemmArgs& g, cudaStream_t st) {
   if (g.epi == EPI_BIAS_GELU) {
     if (g.out_bf16) return launch_persistent_t<BN, EPI_BIAS_GELU, true>(g, st);
     set_error("gemm_bf16: the GELU epilogue writes bf16 only");
+    return WMK_ERR_UNSUPPORTED;
+  }
+  if (g.epi == EPI_BIAS_RELU) {
+    if constexpr (BN <= 64) {
+      if (g.out_bf16) return launch_persistent_t<BN, EPI_BIAS_RELU, true>(g, st);
+    }
+    set_error("gemm_bf16: the ReLU epilogue covers N = 32 / 64 with bf16 output");
     return WMK_ERR_UNSUPPORTED;
   }
   if (g.epi == EPI_BIAS_RESID) {
@@ -653,6 +676,9 @@ int gemm_bf16_tcgen05(const GemmArgs& g, cudaStream_t st) {
   WMK_REQUIRE(((uintptr_t)g.A & 15) == 0 && ((uintptr_t)g.W & 15) == 0 && ((uintptr_t)g.C & 15) == 0,
               "gemm_bf16: operands must be 16-byte aligned");
   WMK_REQUIRE(g.ldc % 8 == 0, "gemm_bf16: ldc=%d must be a multiple of 8", g.ldc);
+  if (g.conv_H > 0)
+    WMK_REQUIRE(g.K == 576 && g.M == g.conv_B * g.conv_H * 128 && g.ldc == g.N && g.epi != EPI_UPSAMPLE,
+                "gemm_bf16: implicit-GEMM conv needs K = 576 and M = B*H*128 (W = 128)");
   if (g.epi == EPI_UPSAMPLE)
     WMK_REQUIRE(g.up_cout % 32 == 0 && g.N == 4 * g.up_cout && g.M % (g.up_h * g.up_w) == 0,
                 "gemm_bf16: bad upsample geometry");

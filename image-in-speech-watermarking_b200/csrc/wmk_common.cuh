@@ -74,7 +74,8 @@ enum Epilogue {
   EPI_BIAS = 0,       // C = acc + bias
   EPI_BIAS_GELU = 1,  // C = gelu(acc + bias)                      (LeFF linear1, model.py:686-687)
   EPI_BIAS_RESID = 2, // C = resid + acc + bias  (fp32 out; resid may alias C)  (model.py:1016-1017)
-  EPI_UPSAMPLE = 3    // ConvTranspose2d(k=2,s=2) pixel shuffle into the concat buffer (model.py:794-800,1225)
+  EPI_UPSAMPLE = 3,   // ConvTranspose2d(k=2,s=2) pixel shuffle into the concat buffer (model.py:794-800,1225)
+  EPI_BIAS_RELU = 4   // C = max(acc + bias, 0), bf16 out  (ConvBNRelu with the BatchNorm affine folded, hidden/model/conv_bn_relu.py:7-18)
 };
 
 struct GemmArgs {
@@ -98,6 +99,10 @@ struct GemmArgs {
   const float* ln_beta = nullptr;
   const float* ln_mod = nullptr;   // [64][N] or nullptr
   int ln_H = 0, ln_shift = 0;      // image side (power of two) and cyclic shift of the block that consumes ln_out
+  // Implicit-GEMM 3x3 convolution (pad 1) over an NHWC bf16 image batch [conv_B][conv_H][128][64]: A is that tensor, a row
+  // tile = the 128 pixels of one image row, k-block kb = tap (dy, dx) fetched as the TMA box shifted by (dy-1, dx-1)
+  // with out-of-bounds zero fill as the padding; W is [N][9*64] with k = tap*64 + ci.  M = conv_B*conv_H*128, K = 576.
+  int conv_H = 0, conv_B = 0;
 };
 
 // Roofline class of a dense-layer launch: algorithmic bytes (A + W + C, + the fp32 residual) against
@@ -181,6 +186,7 @@ struct EpiParams {
   const float* ln_beta = nullptr;
   const float* ln_mod = nullptr;
   int ln_H = 0, ln_shift = 0;
+  int conv_H = 0;      // > 0: implicit-GEMM 3x3 convolution (see GemmArgs)
 };
 
 __device__ __forceinline__ size_t epi_row_offset(const EpiParams& p, int m, int n_first) {

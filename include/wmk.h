@@ -146,6 +146,18 @@ int wmk_convT2x2_f32(const float* x, float* y, const float* w, const float* bias
 /* MaxPool2d(2, 2) over `planes` = B*C images of H x W */
 int wmk_maxpool2x2_f32(const float* x, float* y, int planes, int H, int W, void* stream);
 
+/* Tensor-core path of the HiDDeN Decoder (hidden/model/decoder.py:12-40): activations NHWC bf16.
+ * c1: first ConvBNRelu(1 -> 64), NCHW fp32 in.  tc: ConvBNRelu(64 -> Cout in {32, 64}) as an implicit GEMM on tcgen05
+ * (W = 128; w_packed [Cout][9*64] bf16 with k = (ky*3+kx)*64 + ci and the BatchNorm scale folded in, bias = folded
+ * bias/shift; ReLU fused).  to1: last ConvBNRelu(Cin -> 1) from NHWC bf16 with Cp padded channels to NCHW fp32. */
+int wmk_conv3x3_c1_nhwc_bf16(const float* x, void* y, const float* w, const float* bias, const float* scale,
+                             const float* shift, int B, int H, int W, void* stream);
+int wmk_conv3x3_nhwc_bf16_tc(const void* x, void* y, const void* w_packed, const float* bias, int B, int H,
+                             int W, int Cout, void* stream);
+int wmk_maxpool2x2_nhwc_bf16(const void* x, void* y, int B, int H, int W, int C, void* stream);
+int wmk_conv3x3_nhwc_to1_f32(const void* x, float* y, const float* wt, float bias, float scale, float shift,
+                             int B, int H, int W, int Cp, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Training-mode kernels of ModelA (step: uformerWM/train_modelA.py:402-500, BASELINE config 5).
  * The data gradient of Conv2d(3x3) is wmk_conv3x3_f32 with the flipped / transposed weights.

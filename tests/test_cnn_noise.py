@@ -274,3 +274,26 @@ def test_modelA_attack_in_the_loop_and_adam_match_torch(golden):
     loss, l1, l2 = TM.train_step(m2, opt, x.cuda(), wm.cuda())
     assert torch.isfinite(loss) and float((opt.flat - before).abs().max()) > 0
 
+
+
+@pytest.mark.gpu
+def test_hidden_decoder_tensor_core_path_matches_reference_golden(golden):
+    """Decoder(precision='bf16'): NHWC bf16 activations, 64 -> 64 / 64 -> 30 ConvBNRelu layers as implicit GEMMs on tcgen05.
+    2e-2 relative (bf16 tensor-core tolerance of the north star) against the unmodified reference's output."""
+    from image_in_speech_watermarking_b200.hidden.model.decoder import Decoder
+    from image_in_speech_watermarking_b200.hidden.options import HiDDenConfiguration
+    g = golden("cnn.npz")
+    cfg = HiDDenConfiguration(H=128, W=128, message_length=30, encoder_blocks=4, encoder_channels=64, decoder_blocks=7,
+                              decoder_channels=64, use_discriminator=True, use_vgg=False, discriminator_blocks=3,
+                              discriminator_channels=64, decoder_loss=1, encoder_loss=0.7, adversarial_loss=1e-3)
+    d = Decoder(cfg, precision='bf16')
+    d.load_state_dict(C.randomize_(C.HiddenDecoderOracle(), 12).state_dict())
+    d = d.cuda().eval()
+    x = torch.from_numpy(g["dec_x"]).cuda()
+    out = d(x)
+    assert out.shape == (2, 1, 32, 32)
+    ref = g["dec_out"]
+    assert np.linalg.norm(out.cpu().numpy() - ref) / np.linalg.norm(ref) < 2e-2
+    assert _maxrel(out.cpu().numpy(), ref) < 5e-2
+    big = x.repeat(40, 1, 1, 1)                                  # 80 clips: several waves of persistent tiles
+    assert torch.equal(d(big)[:2], out)
