@@ -9,39 +9,52 @@ namespace wmk {
 // InputProj (uformerWM/model.py:813-816,824-826): Conv2d(2,32,3,p=1) + LeakyReLU(0.01),
 // NCHW [B][2][128][128] in -> token layout [B*16384][32] out.  One thread per pixel; the 576 weights
 // travel as a kernel parameter, i.e. in the constant bank, so every FMA takes its weight as an
-// immediate-like c[][] operand (no shared-memory traffic).
+// immediate-like c[][] operand (no shared-memory traffic).  The 128-byte token rows are transposed
+// through swizzled shared memory so that every store instruction of a warp writes 512 contiguous bytes
+// (a thread storing its own row touches 32 half-filled sectors per instruction).
 struct InProjW { float w[32 * 18]; float b[32]; };
 
 __global__ void __launch_bounds__(128)
 input_proj_kernel(const float* __restrict__ x, float* __restrict__ out, const __grid_constant__ InProjW W, int B) {
-  const size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (pix >= (size_t)B * 16384) return;
-  const int wq = (int)(pix & 127), h = (int)((pix >> 7) & 127);
-  const size_t b = pix >> 14;
-  float in[18];
+  __shared__ __align__(16) float4 stage[128 * 8];            // [pixel][8 float4], chunk index XOR (pixel & 7)
+  const size_t pix0 = (size_t)blockIdx.x * blockDim.x;
+  const size_t pix = pix0 + threadIdx.x;
+  const size_t npix = (size_t)B * 16384;
+  if (pix < npix) {
+    const int wq = (int)(pix & 127), h = (int)((pix >> 7) & 127);
+    const size_t b = pix >> 14;
+    float in[18];
 #pragma unroll
-  for (int c = 0; c < 2; ++c)
+    for (int c = 0; c < 2; ++c)
 #pragma unroll
-    for (int dy = 0; dy < 3; ++dy)
+      for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
-      for (int dx = 0; dx < 3; ++dx) {
-        const int hh = h + dy - 1, wwp = wq + dx - 1;
-        in[c * 9 + dy * 3 + dx] =
-            (hh >= 0 && hh < 128 && wwp >= 0 && wwp < 128) ? x[((b * 2 + c) * 128 + hh) * 128 + wwp] : 0.f;
+        for (int dx = 0; dx < 3; ++dx) {
+          const int hh = h + dy - 1, wwp = wq + dx - 1;
+          in[c * 9 + dy * 3 + dx] =
+              (hh >= 0 && hh < 128 && wwp >= 0 && wwp < 128) ? x[((b * 2 + c) * 128 + hh) * 128 + wwp] : 0.f;
+        }
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      float r[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int co = g * 4 + j;
+        float a = W.b[co];
+#pragma unroll
+        for (int t = 0; t < 18; ++t) a = fmaf(in[t], W.w[co * 18 + t], a);
+        r[j] = a > 0.f ? a : 0.01f * a;
       }
-  float4* o = reinterpret_cast<float4*>(out + pix * 32);
-#pragma unroll
-  for (int g = 0; g < 8; ++g) {
-    float r[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int co = g * 4 + j;
-      float a = W.b[co];
-#pragma unroll
-      for (int t = 0; t < 18; ++t) a = fmaf(in[t], W.w[co * 18 + t], a);
-      r[j] = a > 0.f ? a : 0.01f * a;
+      stage[threadIdx.x * 8 + (g ^ (threadIdx.x & 7))] = make_float4(r[0], r[1], r[2], r[3]);
     }
-    o[g] = make_float4(r[0], r[1], r[2], r[3]);
+  }
+  __syncthreads();
+  float4* o = reinterpret_cast<float4*>(out + pix0 * 32);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int e = k * 128 + threadIdx.x;                       // float4 index inside the CTA's 16 KB of output
+    const int p = e >> 3, g = e & 7;
+    if (pix0 + p < npix) o[e] = stage[p * 8 + (g ^ (p & 7))];
   }
 }
 
@@ -53,21 +66,16 @@ input_proj_kernel(const float* __restrict__ x, float* __restrict__ out, const __
 // its 9 taps from shared memory; NCHW stores are coalesced along w.
 constexpr int OP_TH = 8, OP_TW = 32, OP_PH = OP_TH + 2, OP_PW = OP_TW + 2, OP_NPIX = OP_PH * OP_PW;
 constexpr int OP_THREADS = 352;      // >= OP_NPIX (340)
+struct OutProjW { float w[64 * 18]; float b[2]; };     // [c][tap*2 + o]: constant-bank FMA operands
 __global__ void __launch_bounds__(OP_THREADS)
 output_proj_kernel(const float* __restrict__ tokens, const float* __restrict__ x, float* __restrict__ noise,
-                   float* __restrict__ y, const float* __restrict__ w, const float* __restrict__ bias, int B) {
-  __shared__ __align__(16) float ws[64 * 20];       // [c][(tap,o) padded to 20]
+                   float* __restrict__ y, const __grid_constant__ OutProjW W, int B) {
   __shared__ float Ps[OP_NPIX * 19];                // [pixel][18 padded to 19]
-  for (int i = threadIdx.x; i < 64 * 20; i += blockDim.x) {
-    const int c = i / 20, k = i - c * 20;
-    ws[i] = k < 18 ? w[((k & 1) * 64 + c) * 9 + (k >> 1)] : 0.f;      // k = tap*2 + o
-  }
   const int tiles_w = 128 / OP_TW, tiles_h = 128 / OP_TH;
   const int tile = blockIdx.x;
   const int b = tile / (tiles_w * tiles_h);
   const int trem = tile - b * tiles_w * tiles_h;
   const int h0 = (trem / tiles_w) * OP_TH, w0 = (trem % tiles_w) * OP_TW;
-  __syncthreads();
   if (threadIdx.x < OP_NPIX) {
     const int pr = threadIdx.x / OP_PW, pc = threadIdx.x - pr * OP_PW;
     const int hh = h0 + pr - 1, wwp = w0 + pc - 1;
@@ -76,24 +84,19 @@ output_proj_kernel(const float* __restrict__ tokens, const float* __restrict__ x
     for (int k = 0; k < 18; ++k) acc[k] = 0.f;
     if (hh >= 0 && hh < 128 && wwp >= 0 && wwp < 128) {
       const float4* src = reinterpret_cast<const float4*>(tokens + (((size_t)b * 128 + hh) * 128 + wwp) * 64);
-      float4 v[16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = src[j];
+      for (int half = 0; half < 2; ++half) {
+        float4 v[8];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float vv[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+        for (int j = 0; j < 8; ++j) v[j] = src[half * 8 + j];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float4* wr = reinterpret_cast<const float4*>(ws + (j * 4 + e) * 20);
+        for (int j = 0; j < 8; ++j) {
+          const float vv[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
 #pragma unroll
-          for (int q = 0; q < 5; ++q) {
-            const float4 w4 = wr[q];
-            acc[q * 4] = fmaf(vv[e], w4.x, acc[q * 4]);
-            acc[q * 4 + 1] = fmaf(vv[e], w4.y, acc[q * 4 + 1]);
-            if (q < 4) {
-              acc[q * 4 + 2] = fmaf(vv[e], w4.z, acc[q * 4 + 2]);
-              acc[q * 4 + 3] = fmaf(vv[e], w4.w, acc[q * 4 + 3]);
-            }
+          for (int e = 0; e < 4; ++e) {
+            const int c = (half * 8 + j) * 4 + e;
+#pragma unroll
+            for (int k = 0; k < 18; ++k) acc[k] = fmaf(vv[e], W.w[c * 18 + k], acc[k]);
           }
         }
       }
@@ -104,7 +107,7 @@ output_proj_kernel(const float* __restrict__ tokens, const float* __restrict__ x
   __syncthreads();
   if (threadIdx.x < OP_TH * OP_TW) {
     const int r = threadIdx.x / OP_TW, c = threadIdx.x - r * OP_TW;
-    float a0 = bias[0], a1 = bias[1];
+    float a0 = W.b[0], a1 = W.b[1];
 #pragma unroll
     for (int dy = 0; dy < 3; ++dy)
 #pragma unroll

@@ -68,7 +68,7 @@ struct wmk_plan {
   std::vector<BlockW> dec[4];
   void* up_w[4] = {};
   float* up_b[4] = {};
-  float *out_w = nullptr, *out_b = nullptr;
+  OutProjW out_proj;              // kernel parameter (constant bank)
   float *codec_c1w = nullptr, *codec_c1b = nullptr, *codec_c2w = nullptr, *codec_c2b = nullptr;
   float *codec_t1w = nullptr, *codec_t1b = nullptr, *codec_t2w = nullptr, *codec_t2b = nullptr;
   float *head_w = nullptr, *head_b = nullptr;
@@ -449,7 +449,7 @@ int run_forward(wmk_plan* P, const float* x, const float* msg, int msg_stride, i
   float* y = y_out ? y_out : P->ybuf;
   {
     ProfScope prof(FAM_SMALL, (double)n * 16384 * (256 + 24), st);
-    output_proj_kernel<<<n * (128 / OP_TH) * (128 / OP_TW), OP_THREADS, 0, st>>>(P->D[3], x, noise, y, P->out_w, P->out_b, n);
+    output_proj_kernel<<<n * (128 / OP_TH) * (128 / OP_TW), OP_THREADS, 0, st>>>(P->D[3], x, noise, y, P->out_proj, n);
     WMK_CHECK_LAUNCH("output_proj_kernel");
   }
   if (stft_new) {
@@ -557,8 +557,16 @@ extern "C" int wmk_plan_finalize(wmk_plan* P) {
       WMK_TRY(pack_block(P, bp, Cd, kHeads[5 + s], H, (i % 2) ? 4 : 0, true, &P->dec[s][i]));
     }
   }
-  WMK_TRY(get_f32(P, "output_proj.proj.0.weight", 2 * 64 * 9, &P->out_w));
-  WMK_TRY(get_f32(P, "output_proj.proj.0.bias", 2, &P->out_b));
+  {
+    const HostTensor *tw, *tb;
+    WMK_TRY(get(P, "output_proj.proj.0.weight", 2 * 64 * 9, &tw));   // [o][c][tap] -> [c][tap*2 + o]
+    WMK_TRY(get(P, "output_proj.proj.0.bias", 2, &tb));
+    for (int o = 0; o < 2; ++o)
+      for (int c = 0; c < 64; ++c)
+        for (int t = 0; t < 9; ++t) P->out_proj.w[c * 18 + t * 2 + o] = tw->data[(o * 64 + c) * 9 + t];
+    P->out_proj.b[0] = tb->data[0];
+    P->out_proj.b[1] = tb->data[1];
+  }
   WMK_TRY(get_f32(P, "encoder_wm.conv1.weight", 144, &P->codec_c1w));
   WMK_TRY(get_f32(P, "encoder_wm.conv1.bias", 16, &P->codec_c1b));
   WMK_TRY(get_f32(P, "encoder_wm.conv2.weight", 576, &P->codec_c2w));
