@@ -1,12 +1,17 @@
 // LeFF depthwise 3x3 convolution (pad 1) + GELU on the bf16 hidden tensor [B][H][W][Ch]
-// (uformerWM/model.py:688-689,706), HBM-bound formulation for sm_100a:
-//   * persistent CTAs (4 per SM) walk (channel slab of 64, spatial tile of TH x 8 pixels) items;
-//   * the (TH+2) x 10 x 64-channel input patch of the NEXT item is fetched by one TMA
+// (uformerWM/model.py:688-689,706) for sm_100a:
+//   * persistent CTAs (4 per SM) walk (channel slab of 64, spatial tile of 8 x 16 pixels) items;
+//   * the 10 x 18 x 64-channel input patch of the NEXT item is fetched by one TMA
 //     cp.async.bulk.tensor.4d while the current one is convolved (2-stage mbarrier pipeline); the
 //     conv's zero padding is the tensor map's out-of-bounds fill, so there is no border code;
-//   * a thread owns 4 channels of one tile column and slides a 3x3 register window down the
-//     rows: 3 conflict-free 8-byte shared loads, 18 packed FFMA2 and 2 packed GELUs per 4 outputs.
+//   * a thread owns 4 channels of TWO adjacent tile columns and walks down the patch rows in scatter form:
+//     each input row (4 columns, loaded and unpacked once) is accumulated into the three output rows it
+//     touches, a finished row goes through the GELU and out.  Per 4 outputs: 2 conflict-free 8-byte shared
+//     loads, 8 unpack ops, 18 packed FFMA2, 2 packed GELUs (the kernel is instruction-issue / FMA-pipe
+//     bound, not HBM bound: measured 57 % issue-active at 64 % of the HBM peak with one column per thread);
+//   * the 0.5 of the GELU is folded into the (pre-halved) weights and bias: gelu_tanh2_half_arg.
 // Algorithmic traffic: 4 B per element (bf16 in + out); the 1.4x patch halo is served by L2.
+// H = 8 (the bottleneck stage) keeps the one-column kernel with 8 x 8 tiles.
 #include "tc_ptx.cuh"
 
 namespace wmk {
@@ -111,8 +116,8 @@ dwconv3x3_gelu_tma_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16*
           a0 = __ffma2_rn(win[(r + dy) % 3][dx][0], wreg[dy * 3 + dx][0], a0);
           a1 = __ffma2_rn(win[(r + dy) % 3][dx][1], wreg[dy * 3 + dx][1], a1);
         }
-      a0 = gelu_tanh2(a0);
-      a1 = gelu_tanh2(a1);
+      a0 = gelu_tanh2_half_arg(a0);
+      a1 = gelu_tanh2_half_arg(a1);
       uint2 o;
       o.x = pack_bf16x2(a0.x, a0.y);
       o.y = pack_bf16x2(a1.x, a1.y);
@@ -141,13 +146,147 @@ int launch_dw(const __nv_bfloat16* in, __nv_bfloat16* out, const float* wt, cons
   return 0;
 }
 
+// ---------------------------------------------------------------------------------- two columns per thread
+constexpr int DW2_TW = 16, DW2_PW = DW2_TW + 2, DW2_TH = 8, DW2_PH = DW2_TH + 2;
+
+struct DwGeom2 {
+  int H, Ch, lg_ncs, lg_tw, lg_th, n_items;      // channel slabs, tiles per row / column: powers of two
+};
+
+__global__ void __launch_bounds__(kDwThreads, 4)
+dwconv3x3_gelu_tma2_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict__ out,
+                           const float* __restrict__ wt, const float* __restrict__ bias, DwGeom2 g) {
+  constexpr uint32_t kPatchBytes = DW2_PH * DW2_PW * 128;
+  __shared__ __align__(128) uint8_t patch[2][kPatchBytes];
+  __shared__ __align__(8) uint64_t bar[2];
+  const int tid = threadIdx.x;
+  const int cg = tid & 15, cp = tid >> 4;          // 4 channels x columns 2 cp, 2 cp + 1
+
+  auto decode = [&](int item, int& slab, int& b, int& h0, int& w0) {
+    slab = item & ((1 << g.lg_ncs) - 1);
+    const int sp = item >> g.lg_ncs;
+    w0 = (sp & ((1 << g.lg_tw) - 1)) * DW2_TW;
+    h0 = ((sp >> g.lg_tw) & ((1 << g.lg_th) - 1)) * DW2_TH;
+    b = sp >> (g.lg_tw + g.lg_th);
+  };
+  auto issue = [&](int item, int stage) {
+    int slab, b, h0, w0;
+    decode(item, slab, b, h0, w0);
+    mbar_arrive_expect_tx(smem_u32(&bar[stage]), kPatchBytes);
+    tma_load_4d(smem_u32(patch[stage]), &tm, slab * 64, w0 - 1, h0 - 1, b, smem_u32(&bar[stage]));
+  };
+
+  if (tid == 0) {
+    mbar_init(smem_u32(&bar[0]), 1);
+    mbar_init(smem_u32(&bar[1]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  int item = blockIdx.x;
+  if (item >= g.n_items) return;
+  if (tid == 0) issue(item, 0);
+
+  for (int it = 0; item < g.n_items; item += gridDim.x, ++it) {
+    const int stage = it & 1;
+    const int next = item + gridDim.x;
+    if (tid == 0 && next < g.n_items) issue(next, stage ^ 1);   // that buffer was drained before the last barrier
+
+    int slab, b, h0, w0;
+    decode(item, slab, b, h0, w0);
+    const int c = slab * 64 + cg * 4;
+    float2 wreg[9][2], bz[2];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(wt + (size_t)t * g.Ch + c));
+      wreg[t][0] = make_float2(a.x, a.y);
+      wreg[t][1] = make_float2(a.z, a.w);
+    }
+    {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(bias + c));
+      bz[0] = make_float2(a.x, a.y);
+      bz[1] = make_float2(a.z, a.w);
+    }
+    float2 acc[3][2][2];                           // [output row mod 3][column][channel pair]
+#pragma unroll
+    for (int s = 0; s < 3; ++s)
+#pragma unroll
+      for (int q = 0; q < 2; ++q) { acc[s][q][0] = bz[0]; acc[s][q][1] = bz[1]; }
+    __nv_bfloat16* op = out + (((size_t)b * g.H + h0) * g.H + w0 + 2 * cp) * g.Ch + c;
+    mbar_wait(smem_u32(&bar[stage]), (it >> 1) & 1);
+
+    // patch[r][x][64 ch] bf16; this thread reads columns 2 cp .. 2 cp + 3, channels 4 cg .. 4 cg + 3
+    const uint8_t* pb = patch[stage] + cp * 256 + cg * 8;
+#pragma unroll
+    for (int i = 0; i < DW2_PH; ++i) {
+      float2 in[4][2];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint2 u = *reinterpret_cast<const uint2*>(pb + (i * DW2_PW + j) * 128);
+        in[j][0] = bf2f(u.x);
+        in[j][1] = bf2f(u.y);
+      }
+      // input row i is tap row dy of output row i - dy (same tap order per output as the gather form)
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy) {
+        const int o = i - dy;
+        if (o < 0 || o >= DW2_TH) continue;
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx)
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            acc[o % 3][q][0] = __ffma2_rn(in[q + dx][0], wreg[dy * 3 + dx][0], acc[o % 3][q][0]);
+            acc[o % 3][q][1] = __ffma2_rn(in[q + dx][1], wreg[dy * 3 + dx][1], acc[o % 3][q][1]);
+          }
+      }
+      if (i >= 2) {                                 // output row i - 2 is complete
+        const int o = i - 2;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const float2 g0 = gelu_tanh2_half_arg(acc[o % 3][q][0]);
+          const float2 g1 = gelu_tanh2_half_arg(acc[o % 3][q][1]);
+          uint2 v;
+          v.x = pack_bf16x2(g0.x, g0.y);
+          v.y = pack_bf16x2(g1.x, g1.y);
+          *reinterpret_cast<uint2*>(op + ((size_t)o * g.H + q) * g.Ch) = v;
+          acc[o % 3][q][0] = bz[0];
+          acc[o % 3][q][1] = bz[1];
+        }
+      }
+    }
+    __syncthreads();                                // everyone has drained this stage's patch
+  }
+}
+
+int launch_dw2(const __nv_bfloat16* in, __nv_bfloat16* out, const float* wt, const float* bias, int B, int H, int Ch,
+               cudaStream_t st) {
+  CUtensorMap tm;
+  const uint64_t dims[4] = {(uint64_t)Ch, (uint64_t)H, (uint64_t)H, (uint64_t)B};
+  const uint64_t strides[3] = {(uint64_t)Ch * 2, (uint64_t)H * Ch * 2, (uint64_t)H * H * Ch * 2};
+  const uint32_t box[4] = {64, DW2_PW, DW2_PH, 1};
+  WMK_TRY(make_tensor_map(&tm, in, 4, dims, strides, box, false, 0));
+  auto lg = [](int v) { int l = 0; while ((1 << l) < v) ++l; return l; };
+  DwGeom2 g;
+  g.H = H; g.Ch = Ch; g.lg_ncs = lg(Ch / 64); g.lg_tw = lg(H / DW2_TW); g.lg_th = lg(H / DW2_TH);
+  const long long items = (long long)B * (H / DW2_TW) * (H / DW2_TH) * (Ch / 64);
+  WMK_REQUIRE(items < (1LL << 31), "dwconv: too many tiles (%lld)", items);
+  g.n_items = (int)items;
+  const int grid = (int)(items < 4LL * num_sms() ? items : 4LL * num_sms());
+  dwconv3x3_gelu_tma2_kernel<<<grid, kDwThreads, 0, st>>>(tm, out, wt, bias, g);
+  WMK_CHECK_LAUNCH("dwconv3x3_gelu_tma2_kernel");
+  return 0;
+}
+
 }  // namespace
 
-// in / out: [B][H][H][Ch] bf16 (token layout), wt: [9][Ch] fp32 tap-major, bias: [Ch] fp32.
+// in / out: [B][H][H][Ch] bf16 (token layout), wt_half: [9][Ch] fp32 tap-major, bias_half: [Ch] fp32 -
+// BOTH PRE-MULTIPLIED BY 0.5 (uformer_plan.cu pack_block), see gelu_tanh2_half_arg.
 int dwconv3x3_gelu_bf16(const __nv_bfloat16* in, __nv_bfloat16* out, const float* wt, const float* bias, int B, int H,
                         int Ch, cudaStream_t st) {
-  WMK_REQUIRE(H % 8 == 0 && Ch % 64 == 0, "dwconv: H=%d must be a multiple of 8 and Ch=%d of 64", H, Ch);
+  WMK_REQUIRE(H >= 8 && (H & (H - 1)) == 0 && Ch >= 64 && (Ch & (Ch - 1)) == 0,
+              "dwconv: H=%d must be a power of two >= 8 and Ch=%d a power of two >= 64", H, Ch);
   WMK_REQUIRE(((uintptr_t)in & 15) == 0 && ((uintptr_t)out & 15) == 0, "dwconv: buffers must be 16-byte aligned");
+  static const int one_col = getenv("WMK_DW_ONECOL") ? atoi(getenv("WMK_DW_ONECOL")) : 0;
+  if (H % 16 == 0 && !one_col) return launch_dw2(in, out, wt, bias, B, H, Ch, st);
   if (H % 16 == 0) return launch_dw<16>(in, out, wt, bias, B, H, Ch, st);
   return launch_dw<8>(in, out, wt, bias, B, H, Ch, st);
 }

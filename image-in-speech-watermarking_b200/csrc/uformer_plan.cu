@@ -40,6 +40,7 @@ struct BlockW {
   float* attn_bias = nullptr;
   void *w_qkv = nullptr, *w_proj = nullptr, *w_l1 = nullptr, *w_l2 = nullptr;
   float *b_qkv = nullptr, *b_proj = nullptr, *b_l1 = nullptr, *b_l2 = nullptr, *dw_w = nullptr, *dw_b = nullptr;
+  float *dw_wh = nullptr, *dw_bh = nullptr;      // 0.5 x the depthwise weights / bias (dwconv_tma.cu folds the GELU's 0.5)
 };
 
 struct EncW {
@@ -182,6 +183,15 @@ int pack_block(wmk_plan* P, const std::string& p, int C, int heads, int H, int s
     for (int tap = 0; tap < 9; ++tap) dwt[(size_t)tap * 4 * C + c] = dw->data[(size_t)c * 9 + tap];
   WMK_TRY(upload_f32(P, dwt, &w->dw_w));
   WMK_TRY(get_f32(P, p + "mlp.dwconv.0.bias", 4 * (size_t)C, &w->dw_b));
+  if (P->precision == WMK_PREC_BF16) {
+    const HostTensor* db;
+    WMK_TRY(get(P, p + "mlp.dwconv.0.bias", 4 * (size_t)C, &db));
+    std::vector<float> bh(4 * (size_t)C);
+    for (size_t i = 0; i < dwt.size(); ++i) dwt[i] *= 0.5f;
+    for (size_t i = 0; i < bh.size(); ++i) bh[i] = db->data[i] * 0.5f;
+    WMK_TRY(upload_f32(P, dwt, &w->dw_wh));
+    WMK_TRY(upload_f32(P, bh, &w->dw_bh));
+  }
   return 0;
 }
 
@@ -337,7 +347,7 @@ int run_block(wmk_plan* P, const BlockW& w, float* x, int n, cudaStream_t st, bo
     ProfScope prof(FAM_DWCONV, 8.0 * M * C * sizeof(OpT), st);
     (void)total;
     if constexpr (sizeof(OpT) == 2) {
-      WMK_TRY(dwconv3x3_gelu_bf16(H1, H2, w.dw_w, w.dw_b, n, H, 4 * C, st));
+      WMK_TRY(dwconv3x3_gelu_bf16(H1, H2, w.dw_wh, w.dw_bh, n, H, 4 * C, st));
     } else {
       dwconv3x3_gelu_kernel<OpT><<<n * (H / 8) * (H / 8) * ((4 * C) / 64), 128, 0, st>>>(H1, H2, w.dw_w, w.dw_b, n, H, 4 * C);
       WMK_CHECK_LAUNCH("dwconv3x3_gelu_kernel");

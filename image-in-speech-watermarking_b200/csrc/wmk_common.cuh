@@ -175,6 +175,22 @@ __device__ __forceinline__ float2 gelu_tanh2(float2 x) {
   return __ffma2_rn(h, t, h);
 }
 
+// The same GELU for an argument that arrives HALVED (h = x / 2): the producer folds the 0.5 of
+// x * 0.5 * (1 + tanh(u)) into its weights and bias (an exact power-of-two scaling), the polynomial takes
+// the matching power-of-two multiples of its coefficients, and one packed multiply per pair disappears.
+// Bit-identical to gelu_tanh2(2 h) outside the denormal range.
+__device__ __forceinline__ float2 gelu_tanh2_half_arg(float2 h) {
+  const float2 h2 = __fmul2_rn(h, h);
+  float2 p = __ffma2_rn(h2, make_float2(32.f * -3.81889112e-04f, 32.f * -3.81889112e-04f),
+                        make_float2(8.f * 3.72153111e-02f, 8.f * 3.72153111e-02f));
+  p = __ffma2_rn(p, h2, make_float2(2.f * 7.97237410e-01f, 2.f * 7.97237410e-01f));
+  const float2 u = __fmul2_rn(p, h);
+  float2 t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t.x) : "f"(u.x));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t.y) : "f"(u.y));
+  return __ffma2_rn(h, t, h);
+}
+
 // Where element (m, n) of a GEMM result is stored.
 struct EpiParams {
   const float* bias;
