@@ -13,6 +13,7 @@
 // epilogue overlaps another's main loop.  Replaces every nn.Linear of the LeWin blocks
 // (uformerWM/model.py:455-456,518,686,690) and, through im2col / pixel-shuffle, the 4x4-s2 and
 // transposed 2x2-s2 convolutions (model.py:763,789).
+#include <cstdlib>
 #include <mutex>
 
 #include "tc_ptx.cuh"
@@ -212,8 +213,11 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __
   const uint32_t STAGE = w_stationary ? A_BYTES : A_BYTES + W_BYTES;
   const uint32_t wres = base;                                // resident weights: kblocks x W_BYTES
   const uint32_t stages = base + (w_stationary ? (uint32_t)kblocks * W_BYTES : 0u);
-  constexpr uint32_t STG_BYTES = 4096;                      // one staging box: 32 rows x <=128 B
-  const uint32_t staging = stages + (uint32_t)n_stages * STAGE;          // [16 warps][4096]
+  // one staging box per epilogue warp: 32 rows x <= 128 B (bf16 output may use 64-byte rows, p.boxc = 32, when
+  // a resident weight tile leaves too little shared memory for the A ring)
+  const int BOXC = OUT_BF16 ? p.boxc : 32;
+  const uint32_t STG_BYTES = OUT_BF16 ? 64u * (uint32_t)BOXC : 4096u;
+  const uint32_t staging = stages + (uint32_t)n_stages * STAGE;          // [16 warps][STG_BYTES]
   const uint32_t staging2 = staging + kEpiWarps * STG_BYTES;             // LN: [16 warps][2048] + exchange
   const uint32_t ln_exch = staging2 + kEpiWarps * STG2_BYTES;
   const uint32_t bars = LN ? ln_exch + LN_EXCH_BYTES : staging + kEpiWarps * STG_BYTES;
@@ -233,7 +237,6 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __
   // that take alternate tiles, with 2 TMEM accumulators per team: up to 8 tiles in flight.
   constexpr int TEAMS = BN <= 32 ? 4 : BN <= 64 ? 2 : 1;
   constexpr int NACC = 2 * TEAMS;
-  constexpr int BOXC = epi_box_cols(BN, OUT_BF16);
   constexpr int TCOLS = NACC * BN <= 32 ? 32 : NACC * BN <= 64 ? 64 : NACC * BN <= 128 ? 128 : NACC * BN <= 256 ? 256 : 512;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -568,6 +571,11 @@ int make_map(CUtensorMap* map, const void* ptr, int rows, int K, int box_rows) {
   return make_map_ex(map, ptr, rows, K, box_rows, BK, false);
 }
 
+static bool narrow_staging() {
+  static const int v = getenv("WMK_GEMM_NARROW_STAGING") ? atoi(getenv("WMK_GEMM_NARROW_STAGING")) : 1;
+  return v != 0;
+}
+
 template <int BN, int EPI, bool OUT_BF16, bool LN = false>
 int launch_persistent_t(const GemmArgs& g, cudaStream_t st) {
   CUtensorMap tmA, tmW, tmC, tmD;
@@ -580,22 +588,31 @@ int launch_persistent_t(const GemmArgs& g, cudaStream_t st) {
     WMK_TRY(make_map(&tmA, g.A, g.M, g.K, BM));
   }
   WMK_TRY(make_map(&tmW, g.W, g.N, g.K, BN));
-  WMK_TRY(make_map_ex(&tmC, g.C, g.M, g.ldc, 32, epi_box_cols(BN, OUT_BF16), !OUT_BF16));
-  if (LN) WMK_TRY(make_map_ex(&tmD, g.ln_out, g.M, g.N, 32, 32, false));
-  else tmD = tmC;
   const int kblocks = cdiv(g.K, BK);
-  constexpr int fixed = kEpiWarps * 4096 + 1024 + 256 + (LN ? (int)(kEpiWarps * STG2_BYTES + LN_EXCH_BYTES) : 0);
   constexpr int budget = 226 * 1024;
   const int n_tiles = g.N / BN, m_tiles = cdiv(g.M, BM);
   const int w_bytes = kblocks * BN * BK * 2;
-  // weight-stationary when the whole BN x K tile + >= 2 A stages fit and every N tile gets >= 1 CTA
-  const int ws = (g.conv_H == 0 && kblocks <= 4 && w_bytes + 2 * BM * BK * 2 + fixed <= budget && n_tiles <= num_sms() &&
-                  m_tiles >= 2 * (num_sms() / n_tiles)) ? 1 : 0;
-  const int stage = ws ? BM * BK * 2 : (BM + BN) * BK * 2;
-  const int avail = budget - fixed - (ws ? w_bytes : 0);
-  int n_stages = ws ? 6 : (kblocks < 6 ? (kblocks < 2 ? 2 : kblocks) : 6);
-  while (n_stages > 2 && n_stages * stage > avail) --n_stages;
-  const size_t smem = (size_t)n_stages * stage + (ws ? w_bytes : 0) + fixed;
+  int boxc = epi_box_cols(BN, OUT_BF16), ws = 0, n_stages = 0;
+  size_t smem = 0;
+  for (;;) {
+    const int stg = OUT_BF16 ? 64 * boxc : 4096;
+    const int fixed = kEpiWarps * stg + 1024 + 256 + (LN ? (int)(kEpiWarps * STG2_BYTES + LN_EXCH_BYTES) : 0);
+    // weight-stationary when the whole BN x K tile + >= 2 A stages fit and every N tile gets >= 1 CTA
+    ws = (g.conv_H == 0 && kblocks <= 4 && w_bytes + 2 * BM * BK * 2 + fixed <= budget && n_tiles <= num_sms() &&
+          m_tiles >= 2 * (num_sms() / n_tiles)) ? 1 : 0;
+    const int stage = ws ? BM * BK * 2 : (BM + BN) * BK * 2;
+    const int avail = budget - fixed - (ws ? w_bytes : 0);
+    n_stages = ws ? 6 : (kblocks < 6 ? (kblocks < 2 ? 2 : kblocks) : 6);
+    while (n_stages > 2 && n_stages * stage > avail) --n_stages;
+    smem = (size_t)n_stages * stage + (ws ? w_bytes : 0) + fixed;
+    // a resident 128 KB weight tile leaves two 16 KB A stages = 32 KB in flight per SM, which bounds the kernel
+    // by load latency (3.1 TB/s measured): halve the bf16 staging boxes to make room for a 4-deep ring
+    if (ws && n_stages < 4 && OUT_BF16 && boxc == 64 && narrow_staging()) { boxc = 32; continue; }
+    break;
+  }
+  WMK_TRY(make_map_ex(&tmC, g.C, g.M, g.ldc, 32, boxc, !OUT_BF16));
+  if (LN) WMK_TRY(make_map_ex(&tmD, g.ln_out, g.M, g.N, 32, 32, false));
+  else tmD = tmC;
   static bool attr_set = false;
   if (!attr_set) {
     WMK_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_persistent_kernel<BN, EPI, OUT_BF16, LN>,
@@ -605,6 +622,7 @@ int launch_persistent_t(const GemmArgs& g, cudaStream_t st) {
   EpiParams p{g.bias, g.resid, g.C, g.M, g.N, g.ldc, g.epi, g.out_bf16, g.up_h, g.up_w, g.up_cout};
   p.ln_gamma = g.ln_gamma; p.ln_beta = g.ln_beta; p.ln_mod = g.ln_mod; p.ln_H = g.ln_H; p.ln_shift = g.ln_shift;
   p.conv_H = g.conv_H;
+  p.boxc = boxc;
   const long long total = (long long)m_tiles * n_tiles;
   const int grid = ws ? (num_sms() / n_tiles) * n_tiles : (int)(total < num_sms() ? total : num_sms());
   gemm_tcgen05_persistent_kernel<BN, EPI, OUT_BF16, LN><<<grid, kPThreads, smem, st>>>(tmA, tmW, tmC, tmD, p, g.K, m_tiles,

@@ -203,6 +203,7 @@ struct EpiParams {
   const float* ln_mod = nullptr;
   int ln_H = 0, ln_shift = 0;
   int conv_H = 0;      // > 0: implicit-GEMM 3x3 convolution (see GemmArgs)
+  int boxc = 64;       // persistent kernel, bf16 output: columns per TMA store box (64 or 32)
 };
 
 __device__ __forceinline__ size_t epi_row_offset(const EpiParams& p, int m, int n_first) {

@@ -1,13 +1,13 @@
 python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -3 > gpurun_out/exp_tests.log
 cat gpurun_out/exp_tests.log
-python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/e3_new.json 2> gpurun_out/e3_new.err
-WMK_DW_ONECOL=1 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/e3_old.json 2> gpurun_out/e3_old.err
+python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/e4_new.json 2> gpurun_out/e4_new.err
+WMK_GEMM_NARROW_STAGING=0 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/e4_old.json 2> gpurun_out/e4_old.err
 python - <<'PY'
 import json
 for n in ('new','old'):
     try:
-        d=json.loads(open('gpurun_out/e3_%s.json'%n).read().strip().splitlines()[-1])
+        d=json.loads(open('gpurun_out/e4_%s.json'%n).read().strip().splitlines()[-1])
         f=d['roofline']['family_ms_per_step']
-        print(n, round(d['ms_per_step'],2), d['clocks']['sm_mhz'], {k:f[k] for k in ('gemm','gemm_hbm','layernorm','dwconv_gelu','window_attention','small','layout')}, d['stats'])
+        print(n, round(d['ms_per_step'],2), d['clocks']['sm_mhz'], {k:f[k] for k in ('gemm','gemm_hbm','layernorm','dwconv_gelu','window_attention','small','layout')}, d['roofline']['frac'], d['roofline']['roofline_other']['frac'])
     except Exception as e: print(n,'ERR',e)
 PY
