@@ -185,9 +185,15 @@ constexpr int kEpiWarps = 16;
 constexpr int kPThreads = 64 + 32 * kEpiWarps;
 
 // columns of the accumulator each epilogue warp owns, and the TMA-store box width
-__host__ __device__ constexpr int epi_cpw(int bn) { return bn >= 128 ? bn / 4 : 32; }
-__host__ __device__ constexpr int epi_box_cols(int bn, bool out_bf16) {
-  return out_bf16 ? (epi_cpw(bn) >= 64 ? 64 : 32) : 32;
+// (128-wide tiles without the fused LayerNorm: 64 columns per warp, i.e. two teams of 8 warps)
+#ifndef WMK_BN128_TEAMS
+#define WMK_BN128_TEAMS 2
+#endif
+__host__ __device__ constexpr int epi_cpw(int bn, bool ln) {
+  return bn >= 256 ? bn / 4 : (bn == 128 && !ln && WMK_BN128_TEAMS == 2) ? 64 : 32;
+}
+__host__ __device__ constexpr int epi_box_cols(int bn, bool out_bf16, bool ln) {
+  return out_bf16 ? (epi_cpw(bn, ln) >= 64 ? 64 : 32) : 32;
 }
 
 // LN = true (EPI_BIAS_RESID, BN <= 128, n_tiles == 1): the epilogue also LayerNorms the finished row and writes
@@ -229,13 +235,15 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __
   const uint32_t tmem_slot = wfull_bar + 8u;
   volatile uint32_t* tmem_slot_ptr = (volatile uint32_t*)(smem_raw + (tmem_slot - raw));
 
-  constexpr int CPW = epi_cpw(BN);
+  constexpr int CPW = epi_cpw(BN, LN);
   constexpr int SLABS = BN / CPW;                           // epilogue warps per lane quarter that share one tile
   constexpr int ACTIVE_EPI = SLABS * 4;                     // warps of one epilogue team
   // Narrow tiles (BN <= 64) finish their main loop faster than one epilogue pass (TMEM load -> residual ->
   // store [-> LayerNorm exchange -> store]) can run, so the 16 epilogue warps form 4 / 2 independent TEAMS
   // that take alternate tiles, with 2 TMEM accumulators per team: up to 8 tiles in flight.
-  constexpr int TEAMS = BN <= 32 ? 4 : BN <= 64 ? 2 : 1;
+  // 128-wide tiles whose epilogue is a latency chain (residual load -> TMEM load -> store) also run two teams
+  // of 8 warps (two 32-column pieces per warp); the LayerNorm epilogue needs one piece per warp and keeps one team.
+  constexpr int TEAMS = BN <= 32 ? 4 : BN <= 64 ? 2 : (BN == 128 && CPW == 64) ? 2 : 1;
   constexpr int NACC = 2 * TEAMS;
   constexpr int TCOLS = NACC * BN <= 32 ? 32 : NACC * BN <= 64 ? 64 : NACC * BN <= 128 ? 128 : NACC * BN <= 256 ? 256 : 512;
 
@@ -353,6 +361,19 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __
           } else {
 #pragma unroll
             for (int j = 0; j < 8; ++j) rpre[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+        if constexpr (EPI == EPI_BIAS_RESID) {
+          // the residual rows of this team's NEXT tile: pull them from HBM into L2 now, so the loads at the top of
+          // the next iteration see L2 latency (the epilogue chain of a tile is latency bound, not bandwidth bound)
+          int m1, n1;
+          if (p.resid_prefetch && tile_at(lt + TEAMS, m1, n1)) {
+            const int row1 = m1 + q * 32 + lane;
+            if (row1 < p.M) {
+              const float* r1 = p.resid + (size_t)row1 * p.ldc + n1 + slab * CPW;
+#pragma unroll
+              for (int cc = 0; cc < CPW; cc += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(r1 + cc));
+            }
           }
         }
         mbar_wait(tfull_bar + 8u * acc, (uint32_t)(lt / NACC) & 1u);
@@ -592,7 +613,7 @@ int launch_persistent_t(const GemmArgs& g, cudaStream_t st) {
   constexpr int budget = 226 * 1024;
   const int n_tiles = g.N / BN, m_tiles = cdiv(g.M, BM);
   const int w_bytes = kblocks * BN * BK * 2;
-  int boxc = epi_box_cols(BN, OUT_BF16), ws = 0, n_stages = 0;
+  int boxc = epi_box_cols(BN, OUT_BF16, LN), ws = 0, n_stages = 0;
   size_t smem = 0;
   for (;;) {
     const int stg = OUT_BF16 ? 64 * boxc : 4096;
@@ -623,6 +644,8 @@ int launch_persistent_t(const GemmArgs& g, cudaStream_t st) {
   p.ln_gamma = g.ln_gamma; p.ln_beta = g.ln_beta; p.ln_mod = g.ln_mod; p.ln_H = g.ln_H; p.ln_shift = g.ln_shift;
   p.conv_H = g.conv_H;
   p.boxc = boxc;
+  static const int resid_pf = getenv("WMK_GEMM_RESID_PREFETCH") ? atoi(getenv("WMK_GEMM_RESID_PREFETCH")) : 1;
+  p.resid_prefetch = resid_pf;
   const long long total = (long long)m_tiles * n_tiles;
   const int grid = ws ? (num_sms() / n_tiles) * n_tiles : (int)(total < num_sms() ? total : num_sms());
   gemm_tcgen05_persistent_kernel<BN, EPI, OUT_BF16, LN><<<grid, kPThreads, smem, st>>>(tmA, tmW, tmC, tmD, p, g.K, m_tiles,

@@ -204,6 +204,7 @@ struct EpiParams {
   int ln_H = 0, ln_shift = 0;
   int conv_H = 0;      // > 0: implicit-GEMM 3x3 convolution (see GemmArgs)
   int boxc = 64;       // persistent kernel, bf16 output: columns per TMA store box (64 or 32)
+  int resid_prefetch = 0;   // persistent kernel: L2-prefetch the next tile's residual rows
 };
 
 __device__ __forceinline__ size_t epi_row_offset(const EpiParams& p, int m, int n_first) {
