@@ -396,10 +396,18 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __
             }
           }
           if constexpr (EPI == EPI_BIAS_GELU) {
+            if (p.gelu_half) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float2 gq = gelu_tanh2(make_float2(f[2 * j], f[2 * j + 1]));
-              f[2 * j] = gq.x; f[2 * j + 1] = gq.y;
+              for (int j = 0; j < 16; ++j) {
+                const float2 gq = gelu_tanh2_half_arg(make_float2(f[2 * j], f[2 * j + 1]));
+                f[2 * j] = gq.x; f[2 * j + 1] = gq.y;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float2 gq = gelu_tanh2(make_float2(f[2 * j], f[2 * j + 1]));
+                f[2 * j] = gq.x; f[2 * j + 1] = gq.y;
+              }
             }
           } else if constexpr (EPI == EPI_BIAS_RELU) {
 #pragma unroll
@@ -646,6 +654,7 @@ int launch_persistent_t(const GemmArgs& g, cudaStream_t st) {
   p.boxc = boxc;
   static const int resid_pf = getenv("WMK_GEMM_RESID_PREFETCH") ? atoi(getenv("WMK_GEMM_RESID_PREFETCH")) : 1;
   p.resid_prefetch = resid_pf;
+  p.gelu_half = g.gelu_half;
   const long long total = (long long)m_tiles * n_tiles;
   const int grid = ws ? (num_sms() / n_tiles) * n_tiles : (int)(total < num_sms() ? total : num_sms());
   gemm_tcgen05_persistent_kernel<BN, EPI, OUT_BF16, LN><<<grid, kPThreads, smem, st>>>(tmA, tmW, tmC, tmD, p, g.K, m_tiles,

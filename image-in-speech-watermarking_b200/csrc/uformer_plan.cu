@@ -172,8 +172,19 @@ int pack_block(wmk_plan* P, const std::string& p, int C, int heads, int H, int s
   WMK_TRY(upload_op(P, t->data, &w->w_proj));
   WMK_TRY(get_f32(P, p + "attn.proj.bias", C, &w->b_proj));
   WMK_TRY(get(P, p + "mlp.linear1.0.weight", 4 * (size_t)C * C, &t));
-  WMK_TRY(upload_op(P, t->data, &w->w_l1));
-  WMK_TRY(get_f32(P, p + "mlp.linear1.0.bias", 4 * (size_t)C, &w->b_l1));
+  if (P->precision == WMK_PREC_BF16) {
+    // the GELU epilogue of linear1 takes x / 2 (gelu_tanh2_half_arg): halve W1 and b1, exact in bf16 / fp32
+    const HostTensor* tb;
+    WMK_TRY(get(P, p + "mlp.linear1.0.bias", 4 * (size_t)C, &tb));
+    std::vector<float> wh(t->data), bh(tb->data);
+    for (auto& v : wh) v *= 0.5f;
+    for (auto& v : bh) v *= 0.5f;
+    WMK_TRY(upload_op(P, wh, &w->w_l1));
+    WMK_TRY(upload_f32(P, bh, &w->b_l1));
+  } else {
+    WMK_TRY(upload_op(P, t->data, &w->w_l1));
+    WMK_TRY(get_f32(P, p + "mlp.linear1.0.bias", 4 * (size_t)C, &w->b_l1));
+  }
   WMK_TRY(get(P, p + "mlp.linear2.0.weight", 4 * (size_t)C * C, &t));
   WMK_TRY(upload_op(P, t->data, &w->w_l2));
   WMK_TRY(get_f32(P, p + "mlp.linear2.0.bias", C, &w->b_l2));
@@ -328,7 +339,7 @@ int run_block(wmk_plan* P, const BlockW& w, float* x, int n, cudaStream_t st, bo
   }
   g = GemmArgs();
   g.A = A; g.W = w.w_l1; g.bias = w.b_l1; g.C = H1; g.M = M; g.N = 4 * C; g.K = C; g.ldc = 4 * C;
-  g.epi = EPI_BIAS_GELU; g.out_bf16 = ob;
+  g.epi = EPI_BIAS_GELU; g.out_bf16 = ob; g.gelu_half = ob;      // bf16 plans carry W1 / 2, b1 / 2 (pack_block)
   WMK_TRY(gemm(P, g, st));
   if constexpr (sizeof(OpT) == 2) {
     if (P->fused_leff && C <= 256 && H <= P->fused_maxh && H >= P->fused_minh) {

@@ -88,6 +88,7 @@ struct GemmArgs {
   int ldc = 0;                  // row stride of C / resid in elements
   int epi = EPI_BIAS;
   int out_bf16 = 0;
+  int gelu_half = 0;            // EPI_BIAS_GELU: W and bias were pre-multiplied by 0.5 (gelu_tanh2_half_arg)
   // EPI_UPSAMPLE: A rows are (b, h, w) over an up_h x up_w grid; columns are (i, j, co) with
   // co < up_cout; element goes to token (b, 2h+i, 2w+j), channel co of a [.., ldc] buffer.
   int up_h = 0, up_w = 0, up_cout = 0;
@@ -205,6 +206,7 @@ struct EpiParams {
   int conv_H = 0;      // > 0: implicit-GEMM 3x3 convolution (see GemmArgs)
   int boxc = 64;       // persistent kernel, bf16 output: columns per TMA store box (64 or 32)
   int resid_prefetch = 0;   // persistent kernel: L2-prefetch the next tile's residual rows
+  int gelu_half = 0;        // GELU epilogue: the accumulator holds x / 2 (weights and bias pre-halved)
 };
 
 __device__ __forceinline__ size_t epi_row_offset(const EpiParams& p, int m, int n_first) {
