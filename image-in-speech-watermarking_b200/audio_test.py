@@ -48,6 +48,43 @@ def prepare_data(soundwave, audio_scale='0', data_min=None, data_max=None):
     return [(soundwave, 16000), [clips[:, j] for j in range(clips.shape[1])], T % 128]
 
 
+def normalize_batch(data, audio_scale):
+    """`normalize_batch` of the reference (`audio_test.py:33-55`) on the GPU: data -> (rescaled, min, max) with
+    the GLOBAL min / max of the tensor; '0' = identity, 'k' = multiply by float(k), 'a-b' = min-max to [a, b]."""
+    mm = FE.minmax(data)
+    a = str(audio_scale)
+    if '-' not in a:
+        return (affine(data, float(a), 0.0) if len(a) > 1 else data), mm[0], mm[1]
+    lo, hi = mm.tolist()
+    return affine(data, *scale_params(a, lo, hi)), mm[0], mm[1]
+
+
+def prepare_data_train(soundwaves, audio_scale='0'):
+    """`SpeechDataTrain.prepare_data` (`audio_test.py:439-502`) on the GPU: every utterance -> training-time STFT
+    (n_fft 256, hop 128, Nyquist row dropped) -> 128-frame clips, all utterances of equal length in ONE launch.
+    soundwaves: (N, L) tensor or a list of (1, L) / (L,) tensors.  Returns (data, min, max): data is
+    (n_clips_total, 2, 128, 128) - the (re/im, bin, frame) layout `UformerAudio` / `ModelA` consume (the reference
+    keeps (1, 128, 128, 2) items and permutes later) - and min = max = 0 when `len(audio_scale) <= 1`
+    (`audio_test.py:489-499`)."""
+    if torch.is_tensor(soundwaves):
+        groups = [soundwaves.reshape(-1, soundwaves.shape[-1])]
+    else:
+        groups, cur = [], []
+        for w in soundwaves:                      # batch consecutive utterances of equal length
+            w = w.reshape(1, -1)
+            if cur and cur[-1].shape[1] != w.shape[1]:
+                groups.append(torch.cat(cur))
+                cur = []
+            cur.append(w)
+        if cur:
+            groups.append(torch.cat(cur))
+    clips = [FE.stft256_clips(g.cuda().float()).flatten(0, 1) for g in groups]
+    data = clips[0] if len(clips) == 1 else torch.cat(clips)
+    if len(str(audio_scale)) > 1:
+        return normalize_batch(data, audio_scale)
+    return data, 0, 0
+
+
 def tile_image(images, tile=32):
     """(B,1,H,W) with H, W multiples of 32 -> (B, K, 1, 32, 32) row-major 32x32 tiles (K = 4 for 64x64).
     The reference hard-codes 32x32 messages (`uformerWM/model.py:2388-2404`); BASELINE config 4's 64x64

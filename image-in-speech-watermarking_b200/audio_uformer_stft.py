@@ -74,3 +74,42 @@ def istft(spec, n_fft=N_FFT, length=None, return_complex=False):
     clips = s.reshape(B, F, nc, CLIP, 2).permute(0, 2, 4, 1, 3).contiguous()
     w = istft_clips(clips, T, length)
     return w[0] if squeeze else w
+
+
+# ---------------------------------------------------------------------------------------------
+# training-time analysis (`SpeechDataTrain.prepare_data`, `uformerWM/audio_test.py:465-491`)
+N_FFT_TRAIN, HOP_TRAIN = 256, 128
+
+
+def num_frames_train(L):
+    """frames of `torch.stft(x, n_fft=256, hop_length=128, win_length=256)`: 1 + L // 128."""
+    return 1 + L // HOP_TRAIN
+
+
+def stft256_clips(wave, n_clips=None):
+    """wave (B, L) float32 CUDA -> clips (B, n_clips, 2, 128, 128) of the training-time STFT: n_fft 256,
+    hop 128, rectangular window, centre reflect padding, Nyquist row dropped (`audio_test.py:465-469`),
+    frames zero-padded and cut into 128-frame clips (`:475-487`).  Default n_clips is the reference's
+    `T // 128 + 1` (its `len_pad = 128 - T % 128` appends a whole empty clip when T % 128 == 0)."""
+    lib = _lib.load()
+    if wave.dim() == 1:
+        wave = wave[None]
+    wave = wave.contiguous().float()
+    B, L = wave.shape
+    T = num_frames_train(L)
+    if n_clips is None:
+        n_clips = T // CLIP + 1
+    out = torch.empty((B, n_clips, 2, BINS, CLIP), device=wave.device, dtype=torch.float32)
+    _lib.check(lib.wmk_stft256_clips_f32(_lib.ptr(wave), B, L, _lib.ptr(out), n_clips, _lib.stream_ptr()))
+    return out
+
+
+def minmax(x):
+    """(min, max) of a CUDA float32 tensor as a 2-element device tensor (`normalize_batch`, `audio_test.py:35-37`)."""
+    lib = _lib.load()
+    x = x.contiguous().float()
+    out = torch.empty(2, device=x.device, dtype=torch.float32)
+    scratch = torch.empty(2, device=x.device, dtype=torch.int32)
+    _lib.check(lib.wmk_minmax_f32(_lib.ptr(x), x.numel(), _lib.ptr(out), _lib.ptr(scratch), _lib.stream_ptr()))
+    return out
+

@@ -83,6 +83,18 @@ int wmk_stft_clips_f32(const float* wave, int B, int L, float* clips, int n_clip
 int wmk_istft_clips_f32(const float* clips, int B, int n_clips, int T, float* wave, int length,
                         void* stream);
 
+/* Training-time analysis of the dataset front end (uformerWM/audio_test.py:465-491,
+ * SpeechDataTrain.prepare_data): torch.stft(x, n_fft=256, hop_length=128, win_length=256) - rectangular
+ * window, centre reflect padding 128 - with the Nyquist row dropped (128 bins) and the 128-frame clip split.
+ * frames of an L-sample waveform: 1 + L / 128. */
+int wmk_stft256_num_frames(int L);
+/* wave [B][L] (L > 128) -> clips [B][n_clips][2][128][128]; frames t >= T are zero.  The reference pads by
+ * 128 - T % 128 frames, i.e. n_clips = T / 128 + 1. */
+int wmk_stft256_clips_f32(const float* wave, int B, int L, float* clips, int n_clips, void* stream);
+/* global min / max of n floats (normalize_batch, uformerWM/audio_test.py:33-37): out2 = {min, max} (device),
+ * scratch8 = 8 bytes of device scratch.  x must be 16-byte aligned. */
+int wmk_minmax_f32(const float* x, size_t n, float* out2, void* scratch8, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Waveform attacks (uformerWM/audio_attack.py), batched over B utterances of L samples, fp32 in
  * HBM, fp64 arithmetic where the reference's numpy code promotes.  In-place (dst == src) allowed

@@ -177,10 +177,34 @@ def modelA_train_fixture():
     print("modelA_train.npz", float(loss1), float(loss2), flat.shape)
 
 
+def train_frontend_fixture():
+    """`SpeechDataTrain.prepare_data` (unmodified reference, `uformerWM/audio_test.py:439-502`) on three seeded
+    utterances: 16 000 samples (T = 126: one clip), 16 300 (T = 128: the reference appends an empty clip),
+    24 000 (T = 188); audio_scale '0' (list of clips), '10' (x 10 + global min / max) and, on the single-clip
+    utterance alone, '0-1' (the reference's min-max branch only runs when the dataset holds ONE clip:
+    `min_values.view(c, 1, 1, 1, 1)` of a scalar, `audio_test.py:49-50`)."""
+    run = shims.reference_prepare_data_train()
+    lens = [16000, 16300, 24000]
+    waves = [SY.synth_speech(20 + i, 1.5)[:L].reshape(1, L).clone() for i, L in enumerate(lens)]
+    d0, _, _ = run(waves, "0")
+    d0 = torch.stack(d0)                                     # (5, 1, 128, 128, 2)
+    d10, mn10, mx10 = run(waves, "10")
+    d01, mn01, mx01 = run(waves[:1], "0-1")
+    np.savez_compressed(os.path.join(OUT, "train_frontend.npz"), lens=np.array(lens),
+                        wave0=waves[0].numpy(), wave1=waves[1].numpy(), wave2=waves[2].numpy(),
+                        data0=d0.numpy(), data10_s8=d10.numpy()[:, :, ::8, ::8], min10=float(mn10), max10=float(mx10),
+                        data01=d01.numpy(), min01=float(mn01.reshape(-1)[0]), max01=float(mx01.reshape(-1)[0]))
+    print("train_frontend.npz", tuple(d0.shape), tuple(d10.shape), tuple(d01.shape), float(mn10), float(mx10))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
+    if len(sys.argv) > 1 and sys.argv[1] == "train_frontend":
+        train_frontend_fixture()
+        return
     signal_fixture()
+    train_frontend_fixture()
     cnn_fixture()
     modelA_train_fixture()
     model_fixture("stress", 0)

@@ -194,6 +194,40 @@ def reference_reconstruct_audio():
     return run
 
 
+def extract_method(rel_path, cls, name, namespace):
+    """Compile method ``cls.name`` of ``<reference>/<rel_path>`` as a plain function into ``namespace``."""
+    import ast
+    path = os.path.join(REFERENCE_ROOT, rel_path)
+    with open(path, "r") as f:
+        tree = ast.parse(f.read(), filename=path)
+    for node in tree.body:
+        if isinstance(node, ast.ClassDef) and node.name == cls:
+            for item in node.body:
+                if isinstance(item, ast.FunctionDef) and item.name == name:
+                    exec(compile(ast.Module(body=[item], type_ignores=[]), path, "exec"), namespace)
+                    return namespace[name]
+    raise RuntimeError("%s.%s not found in %s" % (cls, name, path))
+
+
+def reference_prepare_data_train():
+    """`SpeechDataTrain.prepare_data` + `normalize_batch` of `uformerWM/audio_test.py:33-55,439-502`, executed
+    unmodified on the CPU.  Returns run(waves, audio_scale) -> (data, min, max) where `waves` is a list of
+    (1, L) tensors standing in for the LibriSpeech items (`self.data_raw[i][0]`)."""
+    import types
+    import numpy as _np
+    import torch.nn.functional as _F
+    ns = {"torch": _CpuTorchProxy(), "np": _np, "F": _F}
+    extract_functions("uformerWM/audio_test.py", ["normalize_batch"], ns)
+    fn = extract_method("uformerWM/audio_test.py", "SpeechDataTrain", "prepare_data", ns)
+
+    def run(waves, audio_scale):
+        me = types.SimpleNamespace(data_raw=[(w, 16000) for w in waves], size=len(waves), data_type="train",
+                                   frequency=128, len_clip=128, audio_scale=audio_scale)
+        with legacy_torch_spectral():
+            return fn(me)
+    return run
+
+
 def reference_hidden_modules():
     """The unmodified `hidden/model/decoder.py`, `hidden/options.py` and `hidden/noise_layers/*`.
     `hidden/` uses top-level module names (`model`, `options`, `noise_layers`) that collide with

@@ -55,6 +55,42 @@ def istft(spec, n_fft=N_FFT, length=None):
     return y
 
 
+def stft_train(x):
+    """Training-time analysis `torch.stft(x, n_fft=256, hop_length=128, win_length=256)` with the Nyquist row
+    dropped (`uformerWM/audio_test.py:465-469`): rectangular window, centre reflect pad 128, T = 1 + L // 128.
+    x: (L,) -> (128, T, 2) float64."""
+    x = np.asarray(x, dtype=np.float64).reshape(-1)
+    xp = np.pad(x, (128, 128), mode="reflect")
+    T = 1 + x.shape[0] // 128
+    idx = 128 * np.arange(T)[:, None] + np.arange(256)[None, :]
+    X = np.fft.rfft(xp[idx], n=256, axis=-1)[:, :128].T          # (128, T)
+    return np.stack([X.real, X.imag], axis=-1)
+
+
+def prepare_data_train(waves, audio_scale="0"):
+    """`SpeechDataTrain.prepare_data` + `normalize_batch` (`uformerWM/audio_test.py:33-55,439-502`): per utterance
+    stft_train, zero-pad by `128 - T % 128` frames (a whole empty clip when T % 128 == 0), cut 128-frame clips;
+    then the dataset-wide scaling.  Returns (data (N, 2, 128, 128) float64 in the (re/im, bin, frame) layout the
+    models consume, min, max) - min = max = 0 when len(audio_scale) <= 1 (`:489-499`).  The 'a-b' branch uses
+    the GLOBAL min / max (the reference's `view(c,1,1,1,1)` of those scalars only runs for a one-clip dataset)."""
+    clips = []
+    for w in waves:
+        s = stft_train(w)
+        T = s.shape[1]
+        s = np.pad(s, ((0, 0), (0, 128 - T % 128), (0, 0)))
+        for j in range(s.shape[1] // 128):
+            clips.append(np.transpose(s[:, 128 * j:128 * (j + 1), :], (2, 0, 1)))
+    data = np.stack(clips)
+    a = str(audio_scale)
+    if len(a) <= 1:
+        return data, 0, 0
+    mn, mx = data.min(), data.max()
+    if "-" not in a:
+        return data * float(a), mn, mx
+    lo, hi = (float(v) for v in a.split("-"))
+    return (data - mn) / (mx - mn) * (hi - lo) + lo, mn, mx
+
+
 def clip_spectrogram(spec):
     """`SpeechDataTest.prepare_data` `uformerWM/audio_test.py:319-347`.
     spec (1,bins,T,2) -> list of (2,128,128) clips, len_last_clip.  Keeps quirk B-6:

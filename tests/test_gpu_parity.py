@@ -101,6 +101,52 @@ def test_stft_istft_match_oracle(L):
     assert maxrel(back.numpy(), w.numpy()) < 1e-5
 
 
+@pytest.mark.parametrize("L", [16000, 16300, 48000, 129, 4096, 128 * 255 + 127, 160000])
+def test_train_stft_matches_oracle(L):
+    """training-time STFT (n_fft 256 / hop 128 / Nyquist row dropped, `audio_test.py:465-487`) vs the oracle,
+    incl. the shortest legal input, T % 128 == 0 (empty extra clip) and a 10 s utterance."""
+    from image_in_speech_watermarking_b200 import audio_uformer_stft as FE
+    w = torch.stack([SY.synth_speech(30 + i, L / 16000.0 + 0.01)[:L] for i in range(3)])
+    clips = FE.stft256_clips(w.cuda()).cpu().numpy()
+    T = 1 + L // 128
+    assert clips.shape == (3, T // 128 + 1, 2, 128, 128)
+    ref, _, _ = S.prepare_data_train([w[i].numpy() for i in range(3)], "0")
+    ref = ref.reshape(clips.shape)
+    assert maxrel(clips, ref) < 1e-5
+    full = np.concatenate([clips[:, j] for j in range(clips.shape[1])], axis=-1)     # (3, 2, 128, n_clips*128)
+    assert float(np.abs(full[..., T:]).max()) == 0.0                                 # zero padding is exact zeros
+    # Parseval over the one-sided bins is not available (Nyquist dropped): check linearity instead
+    a, b = w[:1].cuda(), w[1:2].cuda()
+    lin = FE.stft256_clips(2.0 * a - 3.0 * b) - (2.0 * FE.stft256_clips(a) - 3.0 * FE.stft256_clips(b))
+    assert float(lin.abs().max()) < 1e-4 * float(np.abs(ref).max())
+
+
+def test_train_frontend_matches_reference_golden(golden):
+    """`prepare_data_train` (GPU) vs the unmodified `SpeechDataTrain.prepare_data` golden."""
+    from image_in_speech_watermarking_b200 import audio_test as AT
+    g = golden("train_frontend.npz")
+    waves = [torch.from_numpy(g["wave%d" % i]) for i in range(3)]
+    ref0 = np.transpose(g["data0"][:, 0], (0, 3, 1, 2))
+    d0, mn, mx = AT.prepare_data_train(waves, "0")
+    assert tuple(d0.shape) == ref0.shape and mn == 0 and mx == 0
+    assert maxrel(d0.cpu().numpy(), ref0) < 1e-5
+    d10, mn10, mx10 = AT.prepare_data_train(waves, "10")
+    scale = np.abs(ref0).max()
+    assert abs(float(mn10) - float(g["min10"])) < 1e-5 * scale and abs(float(mx10) - float(g["max10"])) < 1e-5 * scale
+    ref10 = np.transpose(g["data10_s8"][:, 0], (0, 3, 1, 2))
+    assert maxrel(d10.cpu().numpy()[:, :, ::8, ::8], ref10) < 1e-5
+    d01, mn01, mx01 = AT.prepare_data_train(waves[:1], "0-1")
+    ref01 = np.transpose(g["data01"][:, 0], (0, 3, 1, 2))
+    assert float(np.abs(d01.cpu().numpy() - ref01).max()) < 1e-5
+    assert float(d01.min()) >= -1e-6 and float(d01.max()) <= 1 + 1e-6
+    # min / max kernel on its own: odd length, negative-only and mixed-sign data
+    from image_in_speech_watermarking_b200 import audio_uformer_stft as FE
+    for n, off in ((7, 0.0), (1001, -5.0), (4096 * 3 + 1, 2.0)):
+        x = torch.randn(n, generator=torch.Generator().manual_seed(n)) + off
+        mm = FE.minmax(x.cuda()).cpu()
+        assert float(mm[0]) == float(x.min()) and float(mm[1]) == float(x.max())
+
+
 def test_stft_is_linear_and_projection_is_idempotent():
     from image_in_speech_watermarking_b200 import audio_uformer_stft as FE
     g = torch.Generator().manual_seed(0)

@@ -47,6 +47,30 @@ def test_numpy_stft_istft_match_torch():
     np.testing.assert_allclose(S.istft(ref), torch.istft(z, 255).numpy(), atol=1e-13)
 
 
+def test_train_frontend_matches_reference(golden):
+    """oracle `prepare_data_train` vs the unmodified `SpeechDataTrain.prepare_data` (`audio_test.py:439-502`)."""
+    g = golden("train_frontend.npz")
+    waves = [g["wave%d" % i].reshape(-1) for i in range(3)]
+    ref0 = np.transpose(g["data0"][:, 0], (0, 3, 1, 2))              # (N,1,128,128,2) -> (N,2,128,128)
+    d0, mn, mx = S.prepare_data_train(waves, "0")
+    assert d0.shape == ref0.shape == (5, 2, 128, 128) and mn == 0 and mx == 0
+    scale = np.abs(ref0).max()
+    assert np.abs(d0 - ref0).max() < 2e-6 * scale                     # reference is fp32 (torch.stft)
+    assert np.abs(d0[2]).max() == 0.0                                 # T = 128: the appended clip is empty
+    d10, mn10, mx10 = S.prepare_data_train(waves, "10")
+    assert abs(mn10 - float(g["min10"])) < 2e-6 * scale and abs(mx10 - float(g["max10"])) < 2e-6 * scale
+    ref10 = np.transpose(g["data10_s8"][:, 0], (0, 3, 1, 2))
+    assert np.abs(d10[:, :, ::8, ::8] - ref10).max() < 2e-5 * scale
+    d01, mn01, mx01 = S.prepare_data_train(waves[:1], "0-1")
+    ref01 = np.transpose(g["data01"][:, 0], (0, 3, 1, 2))
+    assert np.abs(d01 - ref01).max() < 2e-6
+    assert abs(mn01 - float(g["min01"])) < 2e-6 * scale and abs(mx01 - float(g["max01"])) < 2e-6 * scale
+    # the numpy restatement against torch.stft itself (float64)
+    x = SY.synth_speech(9, 0.7)
+    ref = torch.view_as_real(torch.stft(x.double(), 256, hop_length=128, win_length=256, return_complex=True))[:-1]
+    np.testing.assert_allclose(S.stft_train(x.numpy()), ref.numpy(), rtol=0, atol=1e-11)
+
+
 def test_pipeline_matches_reference_driver(golden, weights):
     for name in ("pipeline_cfg1_awgn_20.npz", "pipeline_cfg1_low_pass.npz"):
         g = golden(name)

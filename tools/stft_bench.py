@@ -33,6 +33,20 @@ def measure(utterances=2048, seconds=3.0, iters=20):
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / iters
         out[name] = {"ms": ms, "gbs": 1276.0 * T * utterances / (ms * 1e-3) / 1e9, "frames": T * utterances}
+    # training-time analysis (n_fft 256 / hop 128): 1536 B per frame (128 samples read + 128 complex bins written)
+    T2 = FE.num_frames_train(L)
+    fn = lambda: FE.stft256_clips(wave)
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    out["stft256"] = {"ms": ms, "gbs": 1536.0 * T2 * utterances / (ms * 1e-3) / 1e9, "frames": T2 * utterances}
     return out
 
 
