@@ -1,8 +1,8 @@
 // 256-point DFT of the training-time STFT (torch.stft(x, n_fft=256, hop_length=128, win_length=256),
 // uformerWM/audio_test.py:465-469) as 16 x 16 Cooley-Tukey: with n = 16 n1 + n2, k = k1 + 16 k2
 //     X[k1 + 16 k2] = sum_n2 W16^(n2 k2) * W256^(n2 k1) * ( sum_n1 x[16 n1 + n2] W16^(n1 k1) )
-// pass A = the inner 16-point DFTs (one per n2) times the W256 twiddle, pass B = the outer 16-point DFTs
-// (one per k1); every 16-point DFT is two radix-4 stages in registers with immediate coefficients.
+// pass A = the inner 16-point DFTs (one per n2; real input, so only k1 = 0..8 are kept), pass B = the W256
+// twiddle and the outer 16-point DFTs (one per k1); every 16-point DFT is two radix-4 stages in registers with immediate coefficients.
 // Compiles as plain C++ too, so tests/test_dft256_host.py checks the math against numpy without a GPU.
 #pragma once
 
@@ -56,19 +56,29 @@ WMK256_HD void dft16(c32 (&v)[16]) {
     for (int d = c + 1; d < 4; ++d) { const c32 t = v[4 * c + d]; v[4 * c + d] = v[4 * d + c]; v[4 * d + c] = t; }
 }
 
-// pass A for one (n2, frame): x[n1] = sample 16 n1 + n2 of the frame; out[k1] = DFT16(x)[k1] * W256^(n2 k1).
-// tw = e^{-2 pi i m / 256} table (cos, sin pairs).
-template <typename TW>
-WMK256_HD void pass_a(const float (&x)[16], int n2, const TW* tw, c32 (&out)[16]) {
+// pass A for one (n2, frame): x[n1] = sample 16 n1 + n2 of the frame; out[k1] = DFT16(x)[k1].  The input is
+// real, so out[16 - k1] = conj(out[k1]): callers keep k1 = 0..8 only.
+WMK256_HD void pass_a(const float (&x)[16], c32 (&out)[16]) {
 #pragma unroll
   for (int n1 = 0; n1 < 16; ++n1) { out[n1].re = x[n1]; out[n1].im = 0.f; }
   dft16(out);
-#pragma unroll
-  for (int k1 = 0; k1 < 16; ++k1) out[k1] = cmul(out[k1], tw[(n2 * k1) & 255].x, tw[(n2 * k1) & 255].y);
 }
 
-// pass B for one (k1, frame): v[n2] = pass-A value (n2, k1); afterwards v[k2] = X[k1 + 16 k2].
-WMK256_HD void pass_b(c32 (&v)[16]) { dft16(v); }
+// where pass B finds A[n2][k1] among the stored k1 = 0..8, and whether it is the conjugate
+WMK256_HD int pass_b_src(int k1) { return k1 <= 8 ? k1 : 16 - k1; }
+
+// pass B for one (k1, frame): v[n2] = A[n2][pass_b_src(k1)] as stored; afterwards v[k2] = X[k1 + 16 k2].
+// tw = e^{-2 pi i m / 256} table (cos, sin pairs).
+template <typename TW>
+WMK256_HD void pass_b(c32 (&v)[16], int k1, const TW* tw) {
+  const float sgn = k1 <= 8 ? 1.f : -1.f;
+#pragma unroll
+  for (int n2 = 0; n2 < 16; ++n2) {
+    v[n2].im *= sgn;
+    v[n2] = cmul(v[n2], tw[(n2 * k1) & 255].x, tw[(n2 * k1) & 255].y);
+  }
+  dft16(v);
+}
 
 }  // namespace dft256
 }  // namespace wmk

@@ -8,8 +8,8 @@
 // HBM-bound (1536 B per frame: 128 new samples in, 128 complex bins out).  One CTA = 32 consecutive frames
 // of one utterance, lane = frame, so every shared-memory access is conflict free and every global store
 // is a 128-byte row segment of the clip.  256 = 16 x 16 Cooley-Tukey: pass A (per n2: 16-point DFT over
-// the stride-16 samples, times W256^(n2 k1)) -> shared memory -> pass B (per k1: 16-point DFT over n2)
-// -> registers -> global; each 16-point DFT is two radix-4 stages in registers.  The frame overlap
+// the stride-16 samples; real input: only k1 = 0..8 go to shared memory, 54 KB per CTA, 4 CTAs per SM) ->
+// pass B (per k1: W256^(n2 k1) twiddle, 16-point DFT over n2) -> registers -> global; each 16-point DFT is two radix-4 stages in registers.  The frame overlap
 // (hop 128 = 0 mod 32 banks) is broken by skewing the staged waveform by one word per hop.
 #include <math.h>
 
@@ -33,8 +33,8 @@ __global__ void __launch_bounds__(F256_THREADS)
 stft256_clips_kernel(const float* __restrict__ wave, float* __restrict__ clips, int L, int T, int n_clips) {
   extern __shared__ float smem256[];
   float* span = smem256;                                 // skewed waveform span
-  float* wre = smem256 + F256_SPAN_WORDS;                // [256][32]
-  float* wim = wre + 256 * F256_TILE;
+  float* wre = smem256 + F256_SPAN_WORDS;                // [16 n2][9 k1][32]: Hermitian half of pass A
+  float* wim = wre + 144 * F256_TILE;
   const int tiles_per_utt = n_clips * (128 / F256_TILE);
   const int b = blockIdx.x / tiles_per_utt;
   const int tile = blockIdx.x - b * tiles_per_utt;
@@ -44,11 +44,22 @@ stft256_clips_kernel(const float* __restrict__ wave, float* __restrict__ clips, 
 
   // stage samples 128 t0 - 128 .. 128 (t0 + 32) + 127 with torch's reflect padding (centre = True)
   const int g0 = 128 * t0 - 128;
-  for (int i = tid; i < F256_SPAN; i += F256_THREADS) {
-    int g = g0 + i;
-    if (g < 0) g = -g;
-    if (g >= L) g = 2 * (L - 1) - g;
-    span[i + (i >> 7)] = (g >= 0 && g < L) ? x[g] : 0.f;
+  {
+    constexpr int NLD = (F256_SPAN + F256_THREADS - 1) / F256_THREADS;     // 17 independent loads in flight
+    float r[NLD];
+#pragma unroll
+    for (int u = 0; u < NLD; ++u) {
+      const int i = tid + u * F256_THREADS;
+      int g = g0 + i;
+      if (g < 0) g = -g;
+      if (g >= L) g = 2 * (L - 1) - g;
+      r[u] = (i < F256_SPAN && g >= 0 && g < L) ? __ldg(x + g) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < NLD; ++u) {
+      const int i = tid + u * F256_THREADS;
+      if (i < F256_SPAN) span[i + (i >> 7)] = r[u];
+    }
   }
   __syncthreads();
 
@@ -63,11 +74,11 @@ stft256_clips_kernel(const float* __restrict__ wave, float* __restrict__ clips, 
       xs[n1] = span[129 * lane + n + (n >> 7)];
     }
     c32 v[16];
-    pass_a(xs, n2, c_tw256, v);
+    pass_a(xs, v);
 #pragma unroll
-    for (int k1 = 0; k1 < 16; ++k1) {
-      wre[(16 * n2 + k1) * F256_TILE + lane] = v[k1].re;
-      wim[(16 * n2 + k1) * F256_TILE + lane] = v[k1].im;
+    for (int k1 = 0; k1 <= 8; ++k1) {
+      wre[(9 * n2 + k1) * F256_TILE + lane] = v[k1].re;
+      wim[(9 * n2 + k1) * F256_TILE + lane] = v[k1].im;
     }
   }
   __syncthreads();
@@ -81,13 +92,14 @@ stft256_clips_kernel(const float* __restrict__ wave, float* __restrict__ clips, 
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     const int k1 = 2 * warp + h;
+    const int ks = pass_b_src(k1);
     c32 v[16];
 #pragma unroll
     for (int n2 = 0; n2 < 16; ++n2) {
-      v[n2].re = wre[(16 * n2 + k1) * F256_TILE + lane];
-      v[n2].im = wim[(16 * n2 + k1) * F256_TILE + lane];
+      v[n2].re = wre[(9 * n2 + ks) * F256_TILE + lane];
+      v[n2].im = wim[(9 * n2 + ks) * F256_TILE + lane];
     }
-    pass_b(v);
+    pass_b(v, k1, c_tw256);
 #pragma unroll
     for (int k2 = 0; k2 < 8; ++k2) {
       const int k = k1 + 16 * k2;
@@ -156,7 +168,7 @@ int stft256_clips(const float* wave, int B, int L, float* clips, int n_clips, cu
   WMK_REQUIRE(n_clips * 128 >= T, "stft256: %d clips cannot hold %d frames", n_clips, T);
   WMK_REQUIRE((long long)B * n_clips * 4 < (1LL << 31), "stft256: too many tiles");
   WMK_TRY(init_tw256());
-  const size_t smem = (size_t)(F256_SPAN_WORDS + 2 * 256 * F256_TILE) * sizeof(float);
+  const size_t smem = (size_t)(F256_SPAN_WORDS + 2 * 144 * F256_TILE) * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
     WMK_CHECK_CUDA(cudaFuncSetAttribute(stft256_clips_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -14,18 +14,18 @@ extern "C" void host_fft256_frame(const float* frame /* [256] */, float* out /* 
     tw[m].x = (float)cos(a);
     tw[m].y = (float)sin(a);
   }
-  static c32 work[256];
+  static c32 work[16 * 9];                 // Hermitian half of pass A, as the kernel stores it
   for (int n2 = 0; n2 < 16; ++n2) {
     float xs[16];
     for (int n1 = 0; n1 < 16; ++n1) xs[n1] = frame[16 * n1 + n2];
     c32 v[16];
-    pass_a(xs, n2, tw, v);
-    for (int k1 = 0; k1 < 16; ++k1) work[16 * n2 + k1] = v[k1];
+    pass_a(xs, v);
+    for (int k1 = 0; k1 <= 8; ++k1) work[9 * n2 + k1] = v[k1];
   }
   for (int k1 = 0; k1 < 16; ++k1) {
     c32 v[16];
-    for (int n2 = 0; n2 < 16; ++n2) v[n2] = work[16 * n2 + k1];
-    pass_b(v);
+    for (int n2 = 0; n2 < 16; ++n2) v[n2] = work[9 * n2 + pass_b_src(k1)];
+    pass_b(v, k1, tw);
     for (int k2 = 0; k2 < 8; ++k2) {
       out[k1 + 16 * k2] = v[k2].re;
       out[128 + k1 + 16 * k2] = v[k2].im;
