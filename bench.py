@@ -220,7 +220,9 @@ def run_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
+        torch.cuda.nvtx.range_push("wmk_timed_step")     # ncu --nvtx --nvtx-include "wmk_timed_step/" (tools/profile_round.sh)
         vec = step(waves, msgs)
+        torch.cuda.nvtx.range_pop()
     e1.record()
     sync()
     launches = (lib.wmk_launch_count() - l0) // args.steps
@@ -296,7 +298,7 @@ def run_ours(args):
     roofline = dict(both[0]) if both else {"bound": "tensor", "achieved": 0.0, "peak": peak_tf, "unit": "TFLOP/s", "frac": 0.0}
     traffic, traffic_src = None, None
     try:                # dram__bytes_read + dram__bytes_write per launch of the dense-layer kernel, from the committed ncu pass
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))      # regenerated by tools/make_profiles.py
         traffic = tj["families"]["gemm"]["dram_bytes_per_launch"]
         traffic_src = "profiles/r01_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean over the %d dense-layer " \
                       "launches of one 64 x 3 s step, both roofline classes)" % tj["families"]["gemm"]["launches"]

@@ -327,6 +327,34 @@ def test_batched_pipeline_equals_per_utterance_and_oracle(models, weights):
     assert abs(s[5] / s[6] - ev["ber_att"]) <= (~safe).sum() / lg.size + 1e-12
 
 
+def test_full_size_config2_batch_is_split_invariant(models):
+    """BASELINE configs[1] at FULL size (64 x 3 s, 384 clips per pass, bf16 product path, awgn-20+low_pass):
+    size-independent properties - every utterance's statistics and extracted bits are identical whether it is
+    processed in the 64-utterance batch or in a 16-utterance shard (utterances are independent: SURVEY 8e), the
+    closed-loop attack leaves the watermarked audio untouched, and the watermarked audio survives an
+    ISTFT -> STFT round trip (it lies in the range of the STFT)."""
+    from image_in_speech_watermarking_b200 import audio_test as PT
+    from image_in_speech_watermarking_b200 import audio_uformer_stft as FE
+    m = models("bf16", "stress")
+    B = 64
+    waves = SY.synth_speech_batch(100, B, 3.0).cuda()
+    msgs = torch.stack([SY.synth_image_binary(100 + i) for i in range(B)]).cuda()
+    unit = torch.randn(B, 48000, generator=torch.Generator().manual_seed(5))
+    full = PT.embed_attack_extract(waves, msgs, m, "awgn-20+low_pass", {"awgn": unit})
+    assert full["wm"].shape == (B, 6, 1, 32, 32) and full["stats"].shape[0] == B
+    assert bool(torch.isfinite(full["stats"]).all())
+    lo, hi = 32, 48
+    part = PT.embed_attack_extract(waves[lo:hi], msgs[lo:hi], m, "awgn-20+low_pass", {"awgn": unit[lo:hi]})
+    assert torch.equal(full["logits_att"][lo:hi] > 0, part["logits_att"] > 0)
+    assert torch.allclose(full["stats"][lo:hi], part["stats"], rtol=1e-9, atol=1e-12)
+    assert torch.equal(full["recon"][lo:hi], part["recon"])
+    cl = PT.embed_attack_extract(waves[:8], msgs[:8], m, "closed_loop")
+    assert torch.equal(cl["att"], cl["recon"])
+    T = FE.num_frames(48000)
+    again = FE.istft_clips(FE.stft_clips(cl["recon"]), T, 48000)
+    assert maxrel(again.cpu().numpy(), cl["recon"].cpu().numpy()) < 1e-5
+
+
 def test_tiled_64x64_image_pipeline_matches_oracle(models, weights):
     """BASELINE config 4 shape (64x64 greyscale image carried as four 32x32 tiles, tile j mod 4 in clip j):
     per-clip extraction, the averaged image and its error statistics == the oracle's loop."""
