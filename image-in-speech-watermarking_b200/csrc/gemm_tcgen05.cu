@@ -354,7 +354,7 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __
         // residual rows do not depend on the accumulator: fetch the first 32-column piece while the MMAs run
         float4 rpre[8];
         if constexpr (EPI == EPI_BIAS_RESID) {
-          if (row < p.M) {
+          if (row < p.M && p.resid) {                     // resid == nullptr: plain bias epilogue (+ fused LayerNorm)
             const float4* r4 = reinterpret_cast<const float4*>(p.resid + (size_t)row * p.ldc + n0 + slab * CPW);
 #pragma unroll
             for (int j = 0; j < 8; ++j) rpre[j] = r4[j];
@@ -367,7 +367,7 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __
           // the residual rows of this team's NEXT tile: pull them from HBM into L2 now, so the loads at the top of
           // the next iteration see L2 latency (the epilogue chain of a tile is latency bound, not bandwidth bound)
           int m1, n1;
-          if (p.resid_prefetch && tile_at(lt + TEAMS, m1, n1)) {
+          if (p.resid_prefetch && p.resid && tile_at(lt + TEAMS, m1, n1)) {
             const int row1 = m1 + q * 32 + lane;
             if (row1 < p.M) {
               const float* r1 = p.resid + (size_t)row1 * p.ldc + n1 + slab * CPW;
@@ -418,7 +418,7 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __
               for (int j = 0; j < 8; ++j) {
                 f[4 * j] += rpre[j].x; f[4 * j + 1] += rpre[j].y; f[4 * j + 2] += rpre[j].z; f[4 * j + 3] += rpre[j].w;
               }
-            } else if (row < p.M) {
+            } else if (row < p.M && p.resid) {
               const float4* r4 = reinterpret_cast<const float4*>(p.resid + (size_t)row * p.ldc + n);
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
@@ -734,6 +734,17 @@ int gemm_bf16_tcgen05(const GemmArgs& g, cudaStream_t st) {
                 "gemm_bf16: bad upsample geometry");
   const GemmWork gw = gemm_work(g, 2);
   ProfScope prof(gw.family, gw.work, st, gw.work2);
+  if (g.epi == EPI_BIAS && g.ln_out && !g.out_bf16) {
+    // bias-only layer whose finished row is also LayerNormed (the downsample conv feeding the next stage's norm1):
+    // the residual epilogue with no residual
+    GemmArgs h = g;
+    h.epi = EPI_BIAS_RESID;
+    h.resid = nullptr;
+    WMK_REQUIRE(h.ldc == h.N && (h.N == 32 || h.N == 64 || h.N == 128), "gemm_bf16: fused LayerNorm needs N in {32, 64, 128}");
+    if (h.N == 128) return launch_persistent<128>(h, st);
+    if (h.N == 64) return launch_persistent<64>(h, st);
+    return launch_persistent<32>(h, st);
+  }
   if (g.epi != EPI_UPSAMPLE && g.ldc == g.N) {
     const bool wide_ok = g.epi != EPI_BIAS_RESID || g.K >= 1024;   // fp32 residual tiles: one 32-column piece per warp
     if (g.N % 256 == 0 && g.N >= 256 && wide_ok) return launch_persistent<256>(g, st);

@@ -12,10 +12,14 @@ namespace wmk {
 // immediate-like c[][] operand (no shared-memory traffic).  The 128-byte token rows are transposed
 // through swizzled shared memory so that every store instruction of a warp writes 512 contiguous bytes
 // (a thread storing its own row touches 32 half-filled sectors per instruction).
-struct InProjW { float w[32 * 18]; float b[32]; };
+// ln_out != nullptr: the kernel also LayerNorms each finished token (norm1 of the stage-0 block that follows,
+// uformerWM/model.py:982; gamma / beta ride in the same parameter block) and stores it as the bf16 operand of the
+// QKV projection, so the separate LayerNorm pass over the largest activation of the model disappears.
+struct InProjW { float w[32 * 18]; float b[32]; float ln_g[32]; float ln_b[32]; };
 
 __global__ void __launch_bounds__(128)
-input_proj_kernel(const float* __restrict__ x, float* __restrict__ out, const __grid_constant__ InProjW W, int B) {
+input_proj_kernel(const float* __restrict__ x, float* __restrict__ out, const __grid_constant__ InProjW W, int B,
+                  __nv_bfloat16* __restrict__ ln_out) {
   __shared__ __align__(16) float4 stage[128 * 8];            // [pixel][8 float4], chunk index XOR (pixel & 7)
   const size_t pix0 = (size_t)blockIdx.x * blockDim.x;
   const size_t pix = pix0 + threadIdx.x;
@@ -34,18 +38,41 @@ input_proj_kernel(const float* __restrict__ x, float* __restrict__ out, const __
           in[c * 9 + dy * 3 + dx] =
               (hh >= 0 && hh < 128 && wwp >= 0 && wwp < 128) ? x[((b * 2 + c) * 128 + hh) * 128 + wwp] : 0.f;
         }
+    float v[32];
 #pragma unroll
     for (int g = 0; g < 8; ++g) {
-      float r[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int co = g * 4 + j;
         float a = W.b[co];
 #pragma unroll
         for (int t = 0; t < 18; ++t) a = fmaf(in[t], W.w[co * 18 + t], a);
-        r[j] = a > 0.f ? a : 0.01f * a;
+        v[co] = a > 0.f ? a : 0.01f * a;
       }
-      stage[threadIdx.x * 8 + (g ^ (threadIdx.x & 7))] = make_float4(r[0], r[1], r[2], r[3]);
+      stage[threadIdx.x * 8 + (g ^ (threadIdx.x & 7))] = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+    }
+    if (ln_out) {
+      float mean = 0.f, var = 0.f;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) mean += v[c];
+      mean *= (1.0f / 32);
+#pragma unroll
+      for (int c = 0; c < 32; ++c) { const float d = v[c] - mean; var = fmaf(d, d, var); }
+      const float rstd = rsqrtf(var * (1.0f / 32) + 1e-5f);
+      uint4* o4 = reinterpret_cast<uint4*>(ln_out + pix * 32);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int c = q * 8 + 2 * e;
+          const float a0 = fmaf((v[c] - mean) * rstd, W.ln_g[c], W.ln_b[c]);
+          const float a1 = fmaf((v[c + 1] - mean) * rstd, W.ln_g[c + 1], W.ln_b[c + 1]);
+          const __nv_bfloat162 h = __floats2bfloat162_rn(a0, a1);
+          pk[e] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+        o4[q] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
     }
   }
   __syncthreads();

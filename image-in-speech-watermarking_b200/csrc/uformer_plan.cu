@@ -45,6 +45,7 @@ struct BlockW {
 
 struct EncW {
   InProjW in_proj;                // travels as a kernel parameter (constant bank)
+  bool in_proj_has_ln = false;    // in_proj.ln_g / ln_b hold norm1 of the stage-0 block
   std::vector<BlockW> stage[5];
   void* down_w[4] = {};
   float* down_b[4] = {};
@@ -213,6 +214,11 @@ int pack_encoder(wmk_plan* P, const std::string& p, const std::string& inproj, E
     WMK_TRY(get(P, inproj + "proj.0.bias", 32, &tb));
     for (int i = 0; i < 576; ++i) e->in_proj.w[i] = tw->data[i];
     for (int i = 0; i < 32; ++i) e->in_proj.b[i] = tb->data[i];
+    const HostTensor *lg, *lb;                       // norm1 of the stage-0 block (no modulator, no shift in encoders)
+    WMK_TRY(get(P, p + "encoderlayer_0.blocks.0.norm1.weight", 32, &lg));
+    WMK_TRY(get(P, p + "encoderlayer_0.blocks.0.norm1.bias", 32, &lb));
+    for (int i = 0; i < 32; ++i) { e->in_proj.ln_g[i] = lg->data[i]; e->in_proj.ln_b[i] = lb->data[i]; }
+    e->in_proj_has_ln = true;
   }
   for (int s = 0; s < 5; ++s) {
     const int C = 32 << s, H = 128 >> s;
@@ -376,25 +382,33 @@ int run_block(wmk_plan* P, const BlockW& w, float* x, int n, cudaStream_t st, bo
 
 // all blocks of one stage
 template <typename OpT>
-int run_stage(wmk_plan* P, const std::vector<BlockW>& blocks, float* x, int n, cudaStream_t st) {
+int run_stage(wmk_plan* P, const std::vector<BlockW>& blocks, float* x, int n, cudaStream_t st, bool first_ln_ready = false) {
   for (size_t i = 0; i < blocks.size(); ++i)
-    WMK_TRY(run_block<OpT>(P, blocks[i], x, n, st, i > 0, i + 1 < blocks.size() ? &blocks[i + 1] : nullptr));
+    WMK_TRY(run_block<OpT>(P, blocks[i], x, n, st, i > 0 || first_ln_ready,
+                           i + 1 < blocks.size() ? &blocks[i + 1] : nullptr));
   return 0;
 }
 
 // Encoder / EncoderTransformerWM stages (model.py:1381-1394, 1569-1579): x NCHW -> E[0..4].
 template <typename OpT>
 int run_encoder(wmk_plan* P, const EncW& e, const float* x_nchw, int n, const char* tag, cudaStream_t st) {
+  bool stage0_ln_ready = false;
   {
     ProfScope prof(FAM_SMALL, (double)n * 16384 * (8 + 128), st);
-    input_proj_kernel<<<cdiv((size_t)n * 16384, 128), 128, 0, st>>>(x_nchw, P->E[0], e.in_proj, n);
+    static const int fuse_ln0 = getenv("WMK_FUSE_FIRST_LN") ? atoi(getenv("WMK_FUSE_FIRST_LN")) : 1;
+    const bool ln0 = sizeof(OpT) == 2 && fuse_ln0 && e.in_proj_has_ln;       // norm1 of stage 0's block in the same pass
+    input_proj_kernel<<<cdiv((size_t)n * 16384, 128), 128, 0, st>>>(x_nchw, P->E[0], e.in_proj, n,
+                                                                   ln0 ? reinterpret_cast<__nv_bfloat16*>(P->bufA) : nullptr);
     WMK_CHECK_LAUNCH("input_proj_kernel");
+    stage0_ln_ready = ln0;
   }
   const std::string t(tag);
   if (t == "enc") WMK_TRY(tap(P, "emb.inproj", P->E[0], (size_t)n * 16384 * 32, st));
+  bool ln_ready = stage0_ln_ready;          // norm1 of the stage's first block already left in bufA by the producer of E[s]
   for (int s = 0; s < 5; ++s) {
     const int C = 32 << s, H = 128 >> s;
-    WMK_TRY(run_stage<OpT>(P, e.stage[s], P->E[s], n, st));
+    WMK_TRY(run_stage<OpT>(P, e.stage[s], P->E[s], n, st, ln_ready));
+    ln_ready = false;
     WMK_TRY(tap(P, t + ".conv" + std::to_string(s), P->E[s], (size_t)n * H * H * C, st));
     if (s == 4) break;
     const int Ho = H / 2;
@@ -408,6 +422,13 @@ int run_encoder(wmk_plan* P, const EncW& e, const float* x_nchw, int n, const ch
     GemmArgs g;
     g.A = col; g.W = e.down_w[s]; g.bias = e.down_b[s]; g.C = P->E[s + 1]; g.M = n * Ho * Ho; g.N = 2 * C;
     g.K = 16 * C; g.ldc = 2 * C; g.epi = EPI_BIAS; g.out_bf16 = 0;
+    static const int fuse_first_ln = getenv("WMK_FUSE_FIRST_LN") ? atoi(getenv("WMK_FUSE_FIRST_LN")) : 1;
+    if (sizeof(OpT) == 2 && fuse_first_ln && 2 * C <= 128) {
+      // the next stage's first norm1 rides on the downsample conv's epilogue (encoder blocks carry no modulator)
+      const BlockW& nb = e.stage[s + 1][0];
+      g.ln_out = P->bufA; g.ln_gamma = nb.ln1_w; g.ln_beta = nb.ln1_b; g.ln_mod = nb.mod; g.ln_H = Ho; g.ln_shift = nb.shift;
+      ln_ready = true;
+    }
     WMK_TRY(gemm(P, g, st));
     WMK_TRY(tap(P, t + ".pool" + std::to_string(s), P->E[s + 1], (size_t)n * Ho * Ho * 2 * C, st));
   }
