@@ -327,6 +327,16 @@ def run_ours(args):
             "stats": {"ber_clean": float(vec[0] / vec[1]), "ber_attacked": float(vec[2] / vec[3]),
                       "mean_snr_db": float(vec[4] / vec[7])}}
     if world == 1 and not args.no_cpu_baseline:
+        # BASELINE metric "STFT GB/s vs HBM peak": the front-end kernels on their own at a size that fills the GPU
+        # (2048 x 3 s; the launches inside the step above cover 64 utterances in ~20 us and are latency dominated)
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import stft_bench
+            sb = stft_bench.measure(2048, SECONDS, 10)
+            line["stft_standalone"] = {k: {"gbs": v["gbs"], "frac_of_hbm": v["gbs"] / peak_bw, "ms": v["ms"]} for k, v in sb.items()}
+            line["stft_standalone"]["workload"] = "2048 x 3 s; algorithmic bytes 1276 B/frame (n_fft 255, hop 63), 1536 B/frame (stft256)"
+        except Exception as e:                       # never lose the bench line over the side measurement
+            line["stft_standalone"] = {"error": str(e)}
         line["cpu_baseline"] = cpu_baseline()
     else:
         line["cpu_baseline"] = None
