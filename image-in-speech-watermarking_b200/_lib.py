@@ -31,6 +31,7 @@ SIGNATURES = {
     "wmk_attack_echo_f32": (_i, [_vp, _vp, _i, _i, _i, _f, _vp]),
     "wmk_attack_lowpass_f32": (_i, [_vp, _vp, _i, _i, _i, _dp, _dp, _dp, _vp]),
     "wmk_attack_jitter_zero_f32": (_i, [_vp, _i, _i, _vp, _i, _vp]),
+    "wmk_attack_jitter_delete_f32": (_i, [_vp, _vp, _i, _i, _vp, _i, _vp, _vp]),
     "wmk_attack_requant8_f32": (_i, [_vp, _vp, _i, _i, _vp]),
     "wmk_attack_resample2_f32": (_i, [_vp, _vp, _i, _i, _dp, _i, _vp]),
     "wmk_wave_stats_f64": (_i, [_vp, _vp, _i, _i, _vp, _vp]),

@@ -8,7 +8,7 @@ Two call surfaces:
   to chain attacks on the same waveform (BASELINE config 2: 'awgn-20+low_pass').
 
 Attacks that need third-party codecs / phase vocoders (aac, mp3compress, time_scaling,
-pitch_scaling, jittering with sample deletion) are outside the hot-path scope and raise."""
+pitch_scaling) are outside the hot-path scope and raise."""
 import ctypes
 
 import numpy as np
@@ -90,6 +90,26 @@ def jittering_2_(wave, jit_ratio=1000, indices=None, seed=0):
     return w
 
 
+def jittering_(wave, jit_ratio=1000, indices=None, seed=0):
+    """`jittering` (`audio_attack.py:156-173`): np.delete of `jit_ratio` random (not necessarily distinct) samples.
+    Returns (out (B, L) zero-padded, lengths: list of B ints).  Like numpy, an index >= L raises IndexError (the
+    reference draws `random.randint(0, len)` inclusive, so it fails itself about 2 % of the time at 3 s)."""
+    w = _wave2d(wave)
+    B, L = w.shape
+    if indices is None:
+        g = torch.Generator(device="cpu").manual_seed(int(seed))
+        indices = torch.randint(0, L, (B, jit_ratio), generator=g, dtype=torch.int32)
+    idx = torch.as_tensor(indices, dtype=torch.int32).reshape(B, -1)
+    if int(idx.max()) >= L or int(idx.min()) < -L:
+        raise IndexError("index %d is out of bounds for axis 0 with size %d" % (int(idx.max()), L))
+    idx = torch.where(idx < 0, idx + L, idx).to(w.device).contiguous()
+    out = torch.empty_like(w)
+    lens = torch.empty(B, dtype=torch.int32, device=w.device)
+    _lib.check(_lib.load().wmk_attack_jitter_delete_f32(_lib.ptr(w), _lib.ptr(out), B, L, _lib.ptr(idx), idx.shape[1],
+                                                        _lib.ptr(lens), _lib.stream_ptr()))
+    return out, lens.tolist()
+
+
 def requantization_(wave):
     w = _wave2d(wave)
     out = torch.empty_like(w)
@@ -130,6 +150,13 @@ def apply_attack(wave, attack, draws=None, seed=0):
             w = requantization_(w)
         elif p[0] == "jittering_2":
             w = jittering_2_(w, int(p[1]), draws.get("jitter"), seed)
+        elif p[0] == "jittering":
+            # sample deletion shortens every utterance by its own number of distinct indices: one utterance at a
+            # time (the reference driver's batch size), so that the result stays a dense (1, L') waveform
+            if w.shape[0] != 1:
+                raise ValueError("attack 'jittering' (sample deletion) yields ragged lengths: run it one utterance at a time")
+            w, lens = jittering_(w, 1000, draws.get("jitter_delete"), seed)
+            w = w[:, :lens[0]].contiguous()
         else:
             raise ValueError("attack %r is outside the hot-path scope (needs third-party codecs)" % one)
     return w
@@ -168,6 +195,14 @@ def requantization(S_watermarked, quantization_bits=8):
 def awgn(signal, snr=15):
     unit = torch.from_numpy(np.random.normal(0, 1.0, np.shape(signal)))     # reference RNG stream
     return _np_call(awgn_, signal, snr, unit)
+
+
+def jittering(S_watermarked, jit_ratio=1000):
+    import random
+    idx = [random.randint(0, len(S_watermarked)) for _ in range(jit_ratio)]      # the reference's inclusive bound
+    t = torch.as_tensor(np.ascontiguousarray(S_watermarked), dtype=torch.float32).cuda()
+    out, lens = jittering_(t, jit_ratio, np.asarray(idx)[None])
+    return out[0, :lens[0]].double().cpu().numpy()
 
 
 def jittering_2(S_watermarked, jit_ratio=1000):

@@ -165,8 +165,9 @@ def embed_attack_extract(waves, messages, model, attack="closed_loop", draws=Non
     audio_clips = affine(audio_clips, 1.0 / sc, -sh / sc)                             # back to the audio range, :559-571
     recon = FE.istft_clips(audio_clips.reshape(B, nc, 2, 128, 128), T, L)             # audio_test.py:595-600
     att = AT.apply_attack(recon, attack, draws, seed)                                 # :631-660
-    nc_att = (T + 126) // 128                                                         # quirk B-7
-    clips_att = FE.stft_clips(att, max(nc_att, (T + 127) // 128))[:, :nc_att].contiguous()
+    Ta = FE.num_frames(att.shape[1])                                                  # == T unless the attack deletes samples
+    nc_att = (Ta + 126) // 128                                                        # quirk B-7
+    clips_att = FE.stft_clips(att, max(nc_att, (Ta + 127) // 128))[:, :nc_att].contiguous()
     clips_att = affine(clips_att, sc, sh)                                             # :691-702
     if model_name == 'uformer':
         wm_att, lg_att = model.wm_decode(clips_att.reshape(B * nc_att, 2, 128, 128), return_logits=True)

@@ -104,6 +104,58 @@ __global__ void jitter_zero_kernel(float* __restrict__ wave, int L, const int32_
   if (k >= 0 && k < L) wave[(size_t)blockIdx.y * L + k] = 0.f;                    // audio_attack.py:187
 }
 
+// jittering (audio_attack.py:156-173): np.delete(x, indices) - the unique listed samples disappear and the
+// rest close up.  Two launches per batch: the indices are marked in `dst` (as 1.0f flags over a zeroed row), then
+// one CTA per utterance compacts: thread t owns a contiguous chunk of <= 256 samples, turns its flags into a
+// bitmask, the block scans the keep counts, and - after a barrier, because the compacted samples land on top of the
+// flags - every thread copies its kept samples to their final positions; the tail is zero-filled.
+__global__ void jitter_mark_kernel(float* __restrict__ flags, int L, const int32_t* __restrict__ idx, int n_idx) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_idx) return;
+  const int k = idx[(size_t)blockIdx.y * n_idx + i];
+  if (k >= 0 && k < L) flags[(size_t)blockIdx.y * L + k] = 1.0f;
+}
+
+constexpr int JD_THREADS = 1024, JD_MAXCHUNK = 256;
+__global__ void __launch_bounds__(JD_THREADS)
+jitter_delete_kernel(const float* __restrict__ src, float* __restrict__ dst, int L, int32_t* __restrict__ out_len) {
+  __shared__ int warp_tot[JD_THREADS / 32];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* x = src + (size_t)b * L;
+  float* y = dst + (size_t)b * L;
+  const int chunk = (L + JD_THREADS - 1) / JD_THREADS;
+  const int i0 = tid * chunk, i1 = min(i0 + chunk, L);
+  uint32_t del[JD_MAXCHUNK / 32];
+#pragma unroll
+  for (int w = 0; w < JD_MAXCHUNK / 32; ++w) del[w] = 0u;
+  int keep = 0;
+  for (int i = i0; i < i1; ++i) {
+    const bool d = y[i] != 0.f;
+    if (d) del[(i - i0) >> 5] |= 1u << ((i - i0) & 31);
+    keep += d ? 0 : 1;
+  }
+  // exclusive scan of `keep` over the block
+  int incl = keep;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) warp_tot[warp] = incl;
+  __syncthreads();                                   // also: every flag has been read before any sample is written
+  int base = 0, total = 0;
+  for (int w = 0; w < JD_THREADS / 32; ++w) {
+    if (w < warp) base += warp_tot[w];
+    total += warp_tot[w];
+  }
+  int pos = base + incl - keep;
+  for (int i = i0; i < i1; ++i)
+    if (!((del[(i - i0) >> 5] >> ((i - i0) & 31)) & 1u)) y[pos++] = x[i];
+  __syncthreads();
+  for (int i = total + tid; i < L; i += JD_THREADS) y[i] = 0.f;
+  if (tid == 0) out_len[b] = total;
+}
+
 // ---------------------------------------------------------------------------- zero-phase IIR
 // scipy.signal.filtfilt(b, a, x) (audio_attack.py:29): odd extension by padlen samples, forward
 // lfilter (transposed direct form II, state zi * first sample), the same on the reversed signal.
@@ -300,6 +352,21 @@ extern "C" int wmk_attack_jitter_zero_f32(float* wave, int B, int L, const int32
   ProfScope prof(FAM_ATTACK, 8.0 * B * n_idx, (cudaStream_t)stream);
   jitter_zero_kernel<<<dim3(cdiv(n_idx, 256), B), 256, 0, (cudaStream_t)stream>>>(wave, L, idx, n_idx);
   WMK_CHECK_LAUNCH("jitter_zero_kernel");
+  return 0;
+}
+
+extern "C" int wmk_attack_jitter_delete_f32(const float* src, float* dst, int B, int L, const int32_t* idx, int n_idx,
+                                            int32_t* out_len, void* stream) {
+  WMK_REQUIRE(src && dst && src != dst && idx && out_len && B > 0 && L > 0 && n_idx > 0,
+              "jitter_delete: bad arguments (in-place not allowed)");
+  WMK_REQUIRE(L <= JD_THREADS * JD_MAXCHUNK, "jitter_delete: at most %d samples per utterance, got %d", JD_THREADS * JD_MAXCHUNK, L);
+  cudaStream_t st = (cudaStream_t)stream;
+  ProfScope prof(FAM_ATTACK, 12.0 * B * L, st);
+  WMK_CHECK_CUDA(cudaMemsetAsync(dst, 0, (size_t)B * L * sizeof(float), st));
+  jitter_mark_kernel<<<dim3(cdiv(n_idx, 256), B), 256, 0, st>>>(dst, L, idx, n_idx);
+  WMK_CHECK_LAUNCH("jitter_mark_kernel");
+  jitter_delete_kernel<<<B, JD_THREADS, 0, st>>>(src, dst, L, out_len);
+  WMK_CHECK_LAUNCH("jitter_delete_kernel");
   return 0;
 }
 

@@ -118,6 +118,11 @@ int wmk_attack_lowpass_f32(const float* src, float* dst, int B, int L, int order
 /* jittering_2 (audio_attack.py:176-193): zero the samples idx[b][0..n_idx) of utterance b */
 int wmk_attack_jitter_zero_f32(float* wave, int B, int L, const int32_t* idx, int n_idx,
                                void* stream);
+/* jittering (audio_attack.py:156-173): np.delete(x, idx) - the unique samples idx[b][0..n_idx) of utterance b are
+ * removed, the rest close up; dst [B][L] holds the shortened waveforms zero-padded, out_len[b] (device int32) their
+ * lengths.  Indices outside [0, L) are ignored (numpy raises for them); L <= 262144; dst != src. */
+int wmk_attack_jitter_delete_f32(const float* src, float* dst, int B, int L, const int32_t* idx,
+                                 int n_idx, int32_t* out_len, void* stream);
 /* requantization (audio_attack.py:85-96), 8-bit unsigned PCM round trip (parity unpinned) */
 int wmk_attack_requant8_f32(const float* src, float* dst, int B, int L, void* stream);
 /* resampling (audio_attack.py:71-83): 2:1 down then 1:2 up with an n_taps polyphase FIR

@@ -177,6 +177,24 @@ def modelA_train_fixture():
     print("modelA_train.npz", float(loss1), float(loss2), flat.shape)
 
 
+def jitter_delete_fixture():
+    """`jittering` (sample deletion, `uformerWM/audio_attack.py:156-173`) executed unmodified; the python RNG is
+    re-seeded until the reference's inclusive `randint(0, len)` stays in bounds (np.delete raises otherwise)."""
+    att = shims.reference_attack_functions()
+    x = SY.synth_speech(3, 1.0).numpy()
+    seed = 11
+    while True:
+        random.seed(seed)
+        idx = np.array([random.randint(0, len(x)) for _ in range(1000)])
+        if idx.max() < len(x):
+            break
+        seed += 1
+    random.seed(seed)
+    y = att["jittering"](x.copy())
+    np.savez_compressed(os.path.join(OUT, "jitter_delete.npz"), seed=seed, idx=idx, out=y)
+    print("jitter_delete.npz", seed, len(x), len(y), len(np.unique(idx)))
+
+
 def train_frontend_fixture():
     """`SpeechDataTrain.prepare_data` (unmodified reference, `uformerWM/audio_test.py:439-502`) on three seeded
     utterances: 16 000 samples (T = 126: one clip), 16 300 (T = 128: the reference appends an empty clip),
@@ -203,7 +221,11 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "train_frontend":
         train_frontend_fixture()
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "jitter_delete":
+        jitter_delete_fixture()
+        return
     signal_fixture()
+    jitter_delete_fixture()
     train_frontend_fixture()
     cnn_fixture()
     modelA_train_fixture()

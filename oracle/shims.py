@@ -167,7 +167,7 @@ def reference_attack_functions():
     from scipy import signal as _signal
     ns = {"np": _np, "signal": _signal, "random": _random, "math": _math}
     names = ["low_pass_filter", "echo_addition", "amplitude_scaling", "closed_loop", "awgn",
-             "jittering_2"]
+             "jittering_2", "jittering"]
     return extract_functions("uformerWM/audio_attack.py", names, ns)
 
 

@@ -162,6 +162,16 @@ def jittering_2(x, jit_ratio=1000, indices=None, rng=None):
     return y
 
 
+def jittering(x, jit_ratio=1000, indices=None, rng=None):
+    """`uformerWM/audio_attack.py:156-173`: np.delete of `jit_ratio` random samples (inclusive upper bound
+    `len(x)` as in the reference, so an out-of-bounds draw raises IndexError exactly like the reference)."""
+    import random
+    if indices is None:
+        r = rng or random
+        indices = [r.randint(0, len(x)) for _ in range(jit_ratio)]
+    return np.delete(np.asarray(x), np.asarray(indices, dtype=np.int64))
+
+
 def requantization(x):
     """`uformerWM/audio_attack.py:85-96`: libsndfile PCM_U8 write + read.
     PARITY UNPINNED (libsndfile is not in the reference tree nor installed): restated from
@@ -204,6 +214,8 @@ def apply_attack(x, attack, draws=None):
         return requantization(x)
     if p[0] == "jittering_2":
         return jittering_2(x, int(p[1]), indices=draws.get("jitter"))
+    if p[0] == "jittering":
+        return jittering(x, indices=draws.get("jitter_delete"))
     raise ValueError("attack %r is outside the hot-path scope (needs third-party codecs)" % attack)
 
 

@@ -180,6 +180,47 @@ def test_attacks_match_reference_golden(golden):
         AT.apply_attack(x, "mp3compress-64k")
 
 
+def test_jitter_delete_matches_reference_golden(golden, models, weights):
+    """sample-deletion attack: exact vs the unmodified reference; ragged batch; edge cases; and the single-utterance
+    driver with the shortened attacked waveform (clip count from the attacked length, quirk B-7) vs the oracle."""
+    from image_in_speech_watermarking_b200 import audio_attack as AT
+    from image_in_speech_watermarking_b200 import audio_test as PT
+    g = golden("jitter_delete.npz")
+    x = golden("signal.npz")["x"]
+    out, lens = AT.jittering_(torch.from_numpy(x).cuda()[None], 1000, g["idx"][None])
+    assert lens == [len(g["out"])]
+    assert np.array_equal(out[0, :lens[0]].cpu().numpy(), g["out"].astype(np.float32))
+    assert float(out[0, lens[0]:].abs().max()) == 0.0
+    # ragged batch: every utterance loses its own number of distinct samples
+    rng = np.random.default_rng(3)
+    w = torch.from_numpy(rng.standard_normal((5, 48000)).astype(np.float32)) + 2.0      # no zeros in the signal
+    idx = rng.integers(0, 48000, size=(5, 3000))
+    idx[0] = 7                                                      # all duplicates: one sample removed
+    idx[1, :] = np.arange(3000)                                     # a leading run
+    idx[2, :] = 48000 - 1 - np.arange(3000)                         # a trailing run
+    out, lens = AT.jittering_(w.cuda(), 3000, idx)
+    for b in range(5):
+        ref = np.delete(w[b].numpy(), idx[b])
+        assert lens[b] == len(ref) and np.array_equal(out[b, :lens[b]].cpu().numpy(), ref)
+    with pytest.raises(IndexError):
+        AT.jittering_(w[:1].cuda(), 1, np.array([[48000]]))
+    with pytest.raises(ValueError):
+        AT.apply_attack(w.cuda(), "jittering")                      # ragged lengths: one utterance at a time
+    # driver: B = 1, attacked audio shorter than the watermarked one
+    m = models("fp32", "stress")
+    wave = SY.synth_speech(12, 1.0)[None].cuda()
+    msg = SY.synth_image_binary(12)[None].cuda()
+    di = rng.integers(0, 16000, size=(1, 1000))
+    r = PT.embed_attack_extract(wave, msg, m, "jittering", {"jitter_delete": di})
+    ev = P.evaluate_utterance(wave.cpu(), msg.cpu(), weights("stress"), "jittering", {"jitter_delete": di[0]})
+    assert r["att"].shape[1] == 16000 - len(np.unique(di))
+    s = r["stats"][0].cpu().numpy()
+    assert abs(s[0] - ev["snr"]) < 1e-3 and abs(s[3] - ev["wm_loss_att"]) < 1e-4
+    lg = np.concatenate(ev["extras"]["logits_att"])
+    safe = np.abs(lg) > 1e-4
+    assert np.array_equal((lg > 0)[safe], (r["logits_att"][0].cpu().numpy() > 0)[safe])
+
+
 def test_lowpass_long_batch_matches_scipy():
     """full-size property: 64 x 3 s batch, every utterance equals scipy filtfilt (chunked IIR is exact)."""
     from image_in_speech_watermarking_b200 import audio_attack as AT

@@ -36,6 +36,17 @@ def test_signal_functions_match_reference(golden):
     assert abs(S.SNR_singlech(x.astype(np.float64), g["low_pass"]) - float(g["snr_singlech"])) < 1e-9
 
 
+def test_jitter_delete_matches_reference(golden):
+    """oracle `jittering` (sample deletion) vs the unmodified reference run (`audio_attack.py:156-173`)."""
+    g = golden("jitter_delete.npz")
+    x = golden("signal.npz")["x"]
+    y = S.jittering(x, indices=g["idx"])
+    assert y.shape == g["out"].shape == (len(x) - len(np.unique(g["idx"])),)
+    np.testing.assert_array_equal(y, g["out"])
+    with np.testing.assert_raises(IndexError):
+        S.jittering(x, indices=[len(x)])                 # the reference's inclusive randint bound
+
+
 def test_numpy_stft_istft_match_torch():
     x = SY.synth_speech(5, 1.0)
     ref = torch.view_as_real(torch.stft(x.double()[None], 255, return_complex=True)).numpy()
