@@ -59,6 +59,24 @@ def cal_snr(audio_ori, audio_recon):
     return float(snr_from_stats(st)[0])
 
 
+def SNR_singlech(S, SN):
+    """`uformerWM/evaluate.py:83-90` (numpy in, python float out): S is centred and peak-normalised, then
+    10 log10( sum (S - mean S)^2 / sum (S - SN)^2 ).  Mean, peak and both sums are GPU reductions
+    (`wmk_wave_stats_f64`, `wmk_minmax_f32`), the normalisation is `wmk_affine_f32`."""
+    from . import audio_uformer_stft as FE
+    s, sn = _cuda1d(S), _cuda1d(SN)
+    st = wave_stats(s, s)
+    n = float(st[0, 5])
+    mean = float(st[0, 4]) / n
+    mn, mx = FE.minmax(s).tolist()
+    peak = max(mx - mean, mean - mn)
+    s2 = torch.empty_like(s)
+    _lib.check(_lib.load().wmk_affine_f32(_lib.ptr(s), _lib.ptr(s2), s.numel(), 1.0 / peak, -mean / peak, _lib.stream_ptr()))
+    st2 = wave_stats(s2, sn)
+    ps = float(st2[0, 0]) - float(st2[0, 4]) ** 2 / n
+    return 10 * math.log(ps / float(st2[0, 1]), 10)
+
+
 def signaltonoise(a, axis=0, ddof=0):
     """`uformerWM/evaluate.py:133-137` for 1-D input."""
     x = _cuda1d(np.asanyarray(a).reshape(-1))

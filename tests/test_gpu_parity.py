@@ -245,6 +245,7 @@ def test_metrics_match_reference_golden(golden):
     g = golden("signal.npz")
     assert abs(EV.cal_snr(g["x"], g["low_pass"]) - float(g["cal_snr"])) < 1e-5
     assert abs(EV.signaltonoise(g["x"]) - float(g["signaltonoise"])) < 1e-3
+    assert abs(EV.SNR_singlech(g["x"].astype(np.float64), g["low_pass"]) - float(g["snr_singlech"])) < 1e-4
     gen = torch.Generator().manual_seed(1)
     wm = torch.rand(5, 1, 32, 32, generator=gen)
     wm[0, 0, 0, :4] = torch.tensor([0.5, 1.5, 0.49999, 0.50001])        # half-to-even / clip cases
