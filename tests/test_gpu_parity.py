@@ -501,7 +501,14 @@ def test_batched_evaluate_writes_the_reference_result_line(models, weights, tmp_
     B = 2
     waves = SY.synth_speech_batch(40, B, 1.0).cuda()
     msgs = torch.stack([SY.synth_image_binary(40 + i) for i in range(B)]).cuda()
-    line, out = EV.test(m, msgs, waves, data_cat='test', result_path=str(tmp_path), attack='echo_addition')
+    line, out = EV.test(m, msgs, waves, data_cat='test', result_path=str(tmp_path), attack='echo_addition', save_audio=True)
+    from image_in_speech_watermarking_b200 import wavio
+    for i in range(B):                                    # the reference's three dumps per utterance (`evaluate.py:240-247`)
+        ori, sr = wavio.read_wav(str(tmp_path / "audio_gen_sample" / "test" / "ori" / ("%d.wav" % i)))
+        assert sr == 16000 and np.array_equal(ori[0], waves[i].cpu().numpy())
+        rec, _ = wavio.read_wav(str(tmp_path / "audio_gen_sample" / "test" / "recon" / ("%d.wav" % i)))
+        att, _ = wavio.read_wav(str(tmp_path / "audio_gen_sample" / "test" / "echo_addition" / ("%d.wav" % i)))
+        assert rec.shape == att.shape == (1, 16000) and maxrel(att[0], S.echo_addition(rec[0].astype(np.float64))) < 1e-6
     evs = [P.evaluate_utterance(waves[i:i + 1].cpu(), msgs[i:i + 1].cpu(), weights("stress"), 'echo_addition') for i in range(B)]
     assert out["clips"] == sum(e["clips"] for e in evs)
     assert abs(out["snr"] - np.mean([e["snr"] for e in evs])) < 1e-3

@@ -49,3 +49,29 @@ def test_result_line_roundtrips_through_result_extract(tmp_path):
     assert rows[0]["PESQ Score"] == "" and rows[1]["PESQ Score"] == 3.1 and abs(rows[1]["SNR Score"] - 21.3) < 1e-12
     head = open(tmp_path / "results.csv").read().splitlines()[0]
     assert head == "Set,Attack,Total Clips,MSE Loss,WM Loss,WM Loss After Attack,SNR Score,PESQ Score"
+
+
+def test_wav_roundtrip(tmp_path):
+    """float32 WAV dumps of the evaluator (`evaluate.py:240-247`): write -> read is exact; PCM16 / PCM8 files decode
+    with libsndfile's scaling."""
+    import struct
+    import numpy as np
+    from image_in_speech_watermarking_b200 import wavio
+    rng = np.random.default_rng(0)
+    x = (rng.standard_normal(16001) * 0.1).astype(np.float32)
+    p = str(tmp_path / "a.wav")
+    wavio.write_wav(p, x, 16000)
+    y, sr = wavio.read_wav(p)
+    assert sr == 16000 and y.shape == (1, 16001) and np.array_equal(y[0], x)
+    st = np.stack([x[:100], -x[:100]])
+    wavio.write_wav(p, st, 8000)
+    y, sr = wavio.read_wav(p)
+    assert sr == 8000 and np.array_equal(y, st)
+    pcm = (np.arange(-5, 5) * 1000).astype("<i2")
+    body = b"WAVEfmt " + struct.pack("<IHHIIHH", 16, 1, 1, 16000, 32000, 2, 16) + b"data" + struct.pack("<I", pcm.nbytes) + pcm.tobytes()
+    q = str(tmp_path / "b.wav")
+    with open(q, "wb") as f:
+        f.write(b"RIFF" + struct.pack("<I", len(body)) + body)
+    y, sr = wavio.read_wav(q)
+    assert np.allclose(y[0], pcm.astype(np.float32) / 32768.0)
+
