@@ -600,9 +600,9 @@ int make_map(CUtensorMap* map, const void* ptr, int rows, int K, int box_rows) {
   return make_map_ex(map, ptr, rows, K, box_rows, BK, false);
 }
 
-static bool narrow_staging() {
-  static const int v = getenv("WMK_GEMM_NARROW_STAGING") ? atoi(getenv("WMK_GEMM_NARROW_STAGING")) : 1;
-  return v != 0;
+static int narrow_staging() {      // 0 off, 1 weight-stationary launches, 2 also streamed-weight launches with < 4 stages
+  static const int v = getenv("WMK_GEMM_NARROW_STAGING") ? atoi(getenv("WMK_GEMM_NARROW_STAGING")) : 2;
+  return v;
 }
 
 template <int BN, int EPI, bool OUT_BF16, bool LN = false>
@@ -636,7 +636,7 @@ int launch_persistent_t(const GemmArgs& g, cudaStream_t st) {
     smem = (size_t)n_stages * stage + (ws ? w_bytes : 0) + fixed;
     // a resident 128 KB weight tile leaves two 16 KB A stages = 32 KB in flight per SM, which bounds the kernel
     // by load latency (3.1 TB/s measured): halve the bf16 staging boxes to make room for a 4-deep ring
-    if (ws && n_stages < 4 && OUT_BF16 && boxc == 64 && narrow_staging()) { boxc = 32; continue; }
+    if ((ws ? narrow_staging() >= 1 : narrow_staging() >= 2) && n_stages < 4 && OUT_BF16 && boxc == 64) { boxc = 32; continue; }
     break;
   }
   WMK_TRY(make_map_ex(&tmC, g.C, g.M, g.ldc, 32, boxc, !OUT_BF16));
