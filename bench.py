@@ -332,7 +332,9 @@ def run_ours(args):
         try:
             sys.path.insert(0, os.path.join(ROOT, "tools"))
             import stft_bench
-            sb = stft_bench.measure(2048, SECONDS, 10)
+            torch.cuda.synchronize()
+            time.sleep(2.0)        # a kernel timed alone: let the board leave the power-capped state of the step loop
+            sb = stft_bench.measure(2048, SECONDS, 20)
             line["stft_standalone"] = {k: {"gbs": v["gbs"], "frac_of_hbm": v["gbs"] / peak_bw, "ms": v["ms"]} for k, v in sb.items()}
             line["stft_standalone"]["workload"] = "2048 x 3 s; algorithmic bytes 1276 B/frame (n_fft 255, hop 63), 1536 B/frame (stft256)"
         except Exception as e:                       # never lose the bench line over the side measurement
