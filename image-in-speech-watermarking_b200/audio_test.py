@@ -85,6 +85,60 @@ def prepare_data_train(soundwaves, audio_scale='0'):
     return data, 0, 0
 
 
+class SpeechDataTest:
+    """`SpeechDataTest` of the reference (`audio_test.py:265-362`) over an in-memory / caller-supplied corpus: `data_raw`
+    is anything indexable whose items start with the (1, L) waveform and the sample rate - a
+    `torchaudio.datasets.LIBRISPEECH` instance (what the reference opens at a hard-coded path) or a plain list.
+    `prepare_data(audio_scale)` returns the reference's `[item, [clip (2,128,128) ...], len_last_clip]` entries with
+    the STFT, padding, clip split and scaling done on the GPU; utterances `300 .. 300+size` unless data_cat == 'train'."""
+
+    def __init__(self, data_raw, size=300, len_clip=128, frequency=128, data_cat='test'):
+        if len_clip != 128 or frequency != 128:
+            raise NotImplementedError("the CUDA front end is built for 128-frame clips of the n_fft = 255 STFT")
+        self.data_raw, self.len_clip, self.frequency, self.data_cat = data_raw, len_clip, frequency, data_cat
+        self.data_min = self.data_max = None
+        self.size = len(data_raw) if size == -1 else size
+        self.data = []
+
+    def prepare_data(self, audio_scale='0'):
+        first = 0 if self.data_cat == 'train' else 300
+        data = []
+        for i in range(first, min(first + self.size, len(self.data_raw))):
+            item = self.data_raw[i]
+            entry = prepare_data(item[0], str(audio_scale), self.data_min, self.data_max)
+            data.append([item, [c[0] for c in entry[1]], entry[2]])
+        self.data = data
+        return data
+
+    def __len__(self):
+        return len(self.data)
+
+    def __getitem__(self, idx):
+        return self.data[idx]
+
+
+class SpeechDataTrain:
+    """`SpeechDataTrain` (`audio_test.py:395-521`): all clips of utterances `0 .. size` (`size .. 2 size` for any other
+    `data_type`) of `data_raw` through the training-time STFT (n_fft 256 / hop 128, Nyquist row dropped) on the GPU;
+    items are the (2, 128, 128) tensors the reference's `__getitem__` yields after its permute / squeeze."""
+
+    def __init__(self, data_raw, size=300, len_clip=128, frequency=128, transform=None, audio_scale='0', data_type='train'):
+        if len_clip != 128 or frequency != 128:
+            raise NotImplementedError("the CUDA front end is built for 128-frame clips of the n_fft = 256 / hop 128 STFT")
+        self.data_raw, self.size, self.transform, self.data_type = data_raw, size, transform, data_type
+        self.len_clip, self.frequency = len_clip, frequency
+        self.audio_scale = str(audio_scale) if audio_scale else '0'
+        first = 0 if data_type == 'train' else size
+        waves = [data_raw[i][0] for i in range(first, min(first + size, len(data_raw)))]
+        self.data, self.data_min, self.data_max = prepare_data_train(waves, self.audio_scale)
+
+    def __len__(self):
+        return len(self.data)
+
+    def __getitem__(self, idx):
+        return self.data[idx]
+
+
 def tile_image(images, tile=32):
     """(B,1,H,W) with H, W multiples of 32 -> (B, K, 1, 32, 32) row-major 32x32 tiles (K = 4 for 64x64).
     The reference hard-codes 32x32 messages (`uformerWM/model.py:2388-2404`); BASELINE config 4's 64x64

@@ -147,6 +147,28 @@ def test_train_frontend_matches_reference_golden(golden):
         assert float(mm[0]) == float(x.min()) and float(mm[1]) == float(x.max())
 
 
+def test_dataset_classes_match_reference_structures(golden):
+    """`SpeechDataTest` / `SpeechDataTrain` over an in-memory corpus: the reference's item structures
+    (`audio_test.py:299-347,439-521`) with GPU-side analysis; values vs the oracle / the reference golden."""
+    from image_in_speech_watermarking_b200 import audio_test as AT
+    g = golden("train_frontend.npz")
+    corpus = [(torch.from_numpy(g["wave%d" % i]), 16000, "transcript", i) for i in range(3)]
+    tr = AT.SpeechDataTrain(corpus, size=3, audio_scale='0')
+    ref0 = np.transpose(g["data0"][:, 0], (0, 3, 1, 2))
+    assert len(tr) == 5 and tuple(tr[0].shape) == (2, 128, 128)
+    assert maxrel(torch.stack([tr[i] for i in range(5)]).cpu().numpy(), ref0) < 1e-5
+    va = AT.SpeechDataTrain(corpus, size=1, audio_scale='0', data_type='valid')         # utterances size .. 2 size
+    assert len(va) == 2 and maxrel(va[0].cpu().numpy(), ref0[1]) < 1e-5
+    te = AT.SpeechDataTest(corpus, size=2, data_cat='train')
+    data = te.prepare_data('0.5')
+    assert len(te) == 2 and data[1][0] is corpus[1] and len(data[1][1]) == 259 // 128 + 1 and data[1][2] == 259 % 128
+    w1 = g["wave1"].reshape(-1)
+    ref = S.stft(w1[None])[0]                                             # (128, T, 2)
+    got = torch.cat([c for c in data[1][1]], dim=-1).cpu().numpy()        # (2, 128, n_clips * 128)
+    T = ref.shape[1]
+    assert maxrel(got[:, :, :T], 0.5 * np.transpose(ref, (2, 0, 1))) < 1e-5 and float(np.abs(got[:, :, T:]).max()) == 0.0
+
+
 def test_stft_is_linear_and_projection_is_idempotent():
     from image_in_speech_watermarking_b200 import audio_uformer_stft as FE
     g = torch.Generator().manual_seed(0)
