@@ -206,6 +206,7 @@ template <int BN, int EPI, bool OUT_BF16, bool LN = false>
 __global__ void __launch_bounds__(kPThreads, 1)
 gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmD,
+                               const __grid_constant__ CUtensorMap tmR,
                                EpiParams p, int K, int m_tiles, int n_tiles, int n_stages, int w_stationary) {
   // w_stationary: the CTA keeps its whole BN x K weight tile resident in shared memory and walks
   // down the M tiles of one N tile, so only A streams from L2 (for K <= 256 the weight tile would
@@ -233,6 +234,7 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __
   const uint32_t tempty_bar = tfull_bar + 64u;              // [NACC <= 8]
   const uint32_t wfull_bar = tempty_bar + 64u;
   const uint32_t tmem_slot = wfull_bar + 8u;
+  const uint32_t rbar0 = tmem_slot + 8u;                    // [16 epilogue warps]: residual tile landed in the staging buffer
   volatile uint32_t* tmem_slot_ptr = (volatile uint32_t*)(smem_raw + (tmem_slot - raw));
 
   constexpr int CPW = epi_cpw(BN, LN);
@@ -269,6 +271,7 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
     if (LN) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmD) : "memory");
+    if (EPI == EPI_BIAS_RESID) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmR) : "memory");
     mbar_init(wfull_bar, 1);
     for (int s = 0; s < n_stages; ++s) {
       mbar_init(full_bar(s), 1);
@@ -278,6 +281,7 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __
       mbar_init(tfull_bar + 8u * a, 1);
       mbar_init(tempty_bar + 8u * a, ACTIVE_EPI);
     }
+    for (int e = 0; e < kEpiWarps; ++e) mbar_init(rbar0 + 8u * e, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -348,13 +352,24 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __
     if (team < TEAMS) {
       const uint32_t buf = staging + (uint32_t)ew * STG_BYTES;
       int m0, n0;
+      // resid_tma: the residual rows of a tile are fetched by one TMA box into this warp's staging buffer (the buffer
+      // alternates residual-in / result-out), issued as soon as the previous tile's store has been read - instead of
+      // eight 16-byte global loads per lane, on which the epilogue warps were stalled (long_scoreboard)
+      constexpr bool RT = EPI == EPI_BIAS_RESID && CPW == 32 && !OUT_BF16;      // one fp32 32-column piece per warp
+      const bool rtma = RT && p.resid != nullptr;
+      const uint32_t rbar = rbar0 + 8u * (uint32_t)ew;
+      uint32_t rphase = 0;
+      if (rtma && tile_at(team, m0, n0) && lane == 0) {
+        mbar_arrive_expect_tx(rbar, 4096u);
+        tma_load_2d(buf, &tmR, n0 + slab * CPW, m0 + q * 32, rbar);
+      }
       for (int lt = team; tile_at(lt, m0, n0); lt += TEAMS) {
         const int acc = lt % NACC;
         const int row = m0 + q * 32 + lane;
         // residual rows do not depend on the accumulator: fetch the first 32-column piece while the MMAs run
-        float4 rpre[8];
-        if constexpr (EPI == EPI_BIAS_RESID) {
-          if (row < p.M && p.resid) {                     // resid == nullptr: plain bias epilogue (+ fused LayerNorm)
+        float4 rpre[RT ? 1 : 8];
+        if constexpr (EPI == EPI_BIAS_RESID && !RT) {
+          if (row < p.M && p.resid) {                     // resid == nullptr: plain bias epilogue
             const float4* r4 = reinterpret_cast<const float4*>(p.resid + (size_t)row * p.ldc + n0 + slab * CPW);
 #pragma unroll
             for (int j = 0; j < 8; ++j) rpre[j] = r4[j];
@@ -363,7 +378,7 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __
             for (int j = 0; j < 8; ++j) rpre[j] = make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
-        if constexpr (EPI == EPI_BIAS_RESID) {
+        if constexpr (EPI == EPI_BIAS_RESID && !RT) {
           // the residual rows of this team's NEXT tile: pull them from HBM into L2 now, so the loads at the top of
           // the next iteration see L2 latency (the epilogue chain of a tile is latency bound, not bandwidth bound)
           int m1, n1;
@@ -413,7 +428,17 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
           } else if constexpr (EPI == EPI_BIAS_RESID) {
-            if (cc == 0) {
+            if constexpr (RT) {
+              if (rtma) {                                  // resid == nullptr: plain bias epilogue (+ fused LayerNorm)
+                mbar_wait(rbar, rphase);
+                rphase ^= 1u;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float4 r = ld_shared_f4(buf + (uint32_t)lane * 128u + (((uint32_t)j ^ (uint32_t)(lane & 7)) << 4));
+                  f[4 * j] += r.x; f[4 * j + 1] += r.y; f[4 * j + 2] += r.z; f[4 * j + 3] += r.w;
+                }
+              }
+            } else if (cc == 0) {
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
                 f[4 * j] += rpre[j].x; f[4 * j + 1] += rpre[j].y; f[4 * j + 2] += rpre[j].z; f[4 * j + 3] += rpre[j].w;
@@ -429,7 +454,7 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __
           }
           // stage this 32-column piece (one warp-private buffer; the previous store must have been read)
           const bool first_piece = OUT_BF16 ? (cc % BOXC) == 0 : true;
-          if (first_piece) {
+          if (first_piece && !rtma) {                   // rtma: the buffer was drained before the residual load was issued
             if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             __syncwarp();
           }
@@ -514,6 +539,14 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar + 8u * acc);
+        if (rtma) {
+          int m1, n1;
+          if (tile_at(lt + TEAMS, m1, n1) && lane == 0) {
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // the stores have read buf (and buf2)
+            mbar_arrive_expect_tx(rbar, 4096u);
+            tma_load_2d(buf, &tmR, n1 + slab * CPW, m1 + q * 32, rbar);
+          }
+        }
       }
       if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
@@ -625,7 +658,7 @@ int launch_persistent_t(const GemmArgs& g, cudaStream_t st) {
   size_t smem = 0;
   for (;;) {
     const int stg = OUT_BF16 ? 64 * boxc : 4096;
-    const int fixed = kEpiWarps * stg + 1024 + 256 + (LN ? (int)(kEpiWarps * STG2_BYTES + LN_EXCH_BYTES) : 0);
+    const int fixed = kEpiWarps * stg + 1024 + 512 + (LN ? (int)(kEpiWarps * STG2_BYTES + LN_EXCH_BYTES) : 0);
     // weight-stationary when the whole BN x K tile + >= 2 A stages fit and every N tile gets >= 1 CTA
     ws = (g.conv_H == 0 && kblocks <= 4 && w_bytes + 2 * BM * BK * 2 + fixed <= budget && n_tiles <= num_sms() &&
           m_tiles >= 2 * (num_sms() / n_tiles)) ? 1 : 0;
@@ -642,6 +675,9 @@ int launch_persistent_t(const GemmArgs& g, cudaStream_t st) {
   WMK_TRY(make_map_ex(&tmC, g.C, g.M, g.ldc, 32, boxc, !OUT_BF16));
   if (LN) WMK_TRY(make_map_ex(&tmD, g.ln_out, g.M, g.N, 32, 32, false));
   else tmD = tmC;
+  CUtensorMap tmR = tmC;                                   // residual tiles (fp32, same geometry as C; usually C itself)
+  if (EPI == EPI_BIAS_RESID && g.resid && (const void*)g.resid != (const void*)g.C)
+    WMK_TRY(make_map_ex(&tmR, g.resid, g.M, g.ldc, 32, 32, true));
   static bool attr_set = false;
   if (!attr_set) {
     WMK_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_persistent_kernel<BN, EPI, OUT_BF16, LN>,
@@ -655,9 +691,10 @@ int launch_persistent_t(const GemmArgs& g, cudaStream_t st) {
   static const int resid_pf = getenv("WMK_GEMM_RESID_PREFETCH") ? atoi(getenv("WMK_GEMM_RESID_PREFETCH")) : 1;
   p.resid_prefetch = resid_pf;
   p.gelu_half = g.gelu_half;
+
   const long long total = (long long)m_tiles * n_tiles;
   const int grid = ws ? (num_sms() / n_tiles) * n_tiles : (int)(total < num_sms() ? total : num_sms());
-  gemm_tcgen05_persistent_kernel<BN, EPI, OUT_BF16, LN><<<grid, kPThreads, smem, st>>>(tmA, tmW, tmC, tmD, p, g.K, m_tiles,
+  gemm_tcgen05_persistent_kernel<BN, EPI, OUT_BF16, LN><<<grid, kPThreads, smem, st>>>(tmA, tmW, tmC, tmD, tmR, p, g.K, m_tiles,
                                                                                        n_tiles, n_stages, ws);
   WMK_CHECK_LAUNCH("gemm_tcgen05_persistent_kernel");
   return 0;
