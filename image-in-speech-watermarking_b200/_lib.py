@@ -68,12 +68,14 @@ SIGNATURES = {
     "wmk_plan_workspace_bytes": (_sz, [_vp]),
     "wmk_uformer_forward": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "wmk_uformer_extract": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
+    "wmk_uformer_autoencode": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "wmk_plan_enable_taps": (_i, [_vp, _i]),
     "wmk_plan_get_tap": (_i, [_vp, ctypes.c_char_p, _vp, _sz, ctypes.POINTER(_sz)]),
     "wmk_linear_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
 }
 
-PREC_FP32, PREC_BF16 = 0, 1
+PREC_FP32, PREC_BF16, PREC_MIXED = 0, 1, 2
+PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "mixed": PREC_MIXED}
 _lib = None
 
 

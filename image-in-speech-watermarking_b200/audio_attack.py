@@ -10,6 +10,7 @@ Two call surfaces:
 Attacks that need third-party codecs / phase vocoders (aac, mp3compress, time_scaling,
 pitch_scaling) are outside the hot-path scope and raise."""
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -17,6 +18,19 @@ import torch
 from . import _lib
 
 _BUTTER_CACHE = {}
+_CALLS = [0]
+_M64 = 0xFFFFFFFFFFFFFFFF
+
+
+def fresh_seed():
+    """A new 64-bit key for the device RNG (Philox AWGN, jitter index draws), one per attack call - the reference
+    draws new `np.random` / `random` values on every call (`audio_attack.py:112-123,161-163,181-183`), so no two
+    utterances, calls or ranks may share a noise realisation.  Taken from numpy's global stream (the reference's
+    own source: `np.random.seed()` still makes a run reproducible) and mixed with the rank and a call counter."""
+    _CALLS[0] += 1
+    base = int(np.random.randint(0, 1 << 31)) | (int(np.random.randint(0, 1 << 31)) << 31)
+    rank = int(os.environ.get("RANK", "0"))
+    return (base ^ ((rank + 1) * 0x9E3779B97F4A7C15) ^ (_CALLS[0] * 0xD1B54A32D192ED03)) & _M64
 
 
 def _butter(order=8, wn=0.5):
@@ -44,7 +58,9 @@ def _wave2d(w):
 
 
 # ------------------------------------------------------------------ batched device API
-def awgn_(wave, snr=15.0, noise_unit=None, seed=0):
+def awgn_(wave, snr=15.0, noise_unit=None, seed=None):
+    """seed=None: a fresh key per call (`fresh_seed`); an explicit seed is for tests / reproducible benchmarks."""
+    seed = fresh_seed() if seed is None else int(seed) & _M64
     w = _wave2d(wave)
     out = torch.empty_like(w)
     nu = None if noise_unit is None else noise_unit.to(w.device, torch.float32).contiguous().reshape(w.shape)
@@ -79,25 +95,25 @@ def low_pass_filter_(wave, Fs=16000, low_pass_parameter=8000):
     return out
 
 
-def jittering_2_(wave, jit_ratio=1000, indices=None, seed=0):
+def jittering_2_(wave, jit_ratio=1000, indices=None, seed=None):
     w = _wave2d(wave).clone()
     B, L = w.shape
     if indices is None:
-        g = torch.Generator(device="cpu").manual_seed(int(seed))
+        g = torch.Generator(device="cpu").manual_seed(fresh_seed() if seed is None else int(seed) & _M64)
         indices = torch.randint(0, L, (B, jit_ratio), generator=g, dtype=torch.int32)
     idx = torch.as_tensor(indices, dtype=torch.int32).reshape(B, -1).to(w.device).contiguous()
     _lib.check(_lib.load().wmk_attack_jitter_zero_f32(_lib.ptr(w), B, L, _lib.ptr(idx), idx.shape[1], _lib.stream_ptr()))
     return w
 
 
-def jittering_(wave, jit_ratio=1000, indices=None, seed=0):
+def jittering_(wave, jit_ratio=1000, indices=None, seed=None):
     """`jittering` (`audio_attack.py:156-173`): np.delete of `jit_ratio` random (not necessarily distinct) samples.
     Returns (out (B, L) zero-padded, lengths: list of B ints).  Like numpy, an index >= L raises IndexError (the
     reference draws `random.randint(0, len)` inclusive, so it fails itself about 2 % of the time at 3 s)."""
     w = _wave2d(wave)
     B, L = w.shape
     if indices is None:
-        g = torch.Generator(device="cpu").manual_seed(int(seed))
+        g = torch.Generator(device="cpu").manual_seed(fresh_seed() if seed is None else int(seed) & _M64)
         indices = torch.randint(0, L, (B, jit_ratio), generator=g, dtype=torch.int32)
     idx = torch.as_tensor(indices, dtype=torch.int32).reshape(B, -1)
     if int(idx.max()) >= L or int(idx.min()) < -L:
@@ -127,12 +143,15 @@ def resampling_(wave):
     return out
 
 
-def apply_attack(wave, attack, draws=None, seed=0):
+def apply_attack(wave, attack, draws=None, seed=None):
     """Device-resident attack dispatch; `attack` follows `uformerWM/audio_test.py:631-660`,
-    '+' chains several attacks."""
+    '+' chains several attacks.  Random attacks draw a fresh key per call (`fresh_seed`) unless `seed` is given
+    (tests, reproducible benchmark steps); stage i of a chain uses seed + i."""
     draws = draws or {}
     w = _wave2d(wave)
-    for one in attack.split("+"):
+    base_seed = seed
+    for stage, one in enumerate(attack.split("+")):
+        seed = None if base_seed is None else (int(base_seed) + stage) & _M64
         p = one.split("-")
         if p[0] == "echo_addition":
             w = echo_addition_(w)

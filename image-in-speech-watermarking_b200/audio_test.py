@@ -182,11 +182,13 @@ def _model_embed(model, x, msg_clips, model_name):
     raise ValueError("model_name must be 'uformer' or 'modelA', got %r" % (model_name,))
 
 
-def embed_attack_extract(waves, messages, model, attack="closed_loop", draws=None, seed=0, want_outputs=True,
+def embed_attack_extract(waves, messages, model, attack="closed_loop", draws=None, seed=None, want_outputs=True,
                          audio_scale='0', data_min=None, data_max=None, model_name='uformer'):
     """Batched hot path.  waves (B, L) CUDA fp32; messages (B or 1, 1, 32, 32) CUDA, or
     (B, K, 1, 32, 32) tiles (see `tile_image`): clip j of an utterance then carries tile j mod K.
     Returns a dict of device tensors:
+      (seed=None: random attacks draw a fresh device-RNG key on every call, as the reference draws new numpy
+      randoms; pass a seed only for tests / reproducible timing)
       recon (B,L) watermarked audio, att (B,L) attacked audio, wm (B,nc,1,32,32) clean extraction,
       wm_att (B,nc_att,1,32,32), logits / logits_att, stats: per-utterance float64 columns
       [snr_db(orig,att), audio_mse(orig,recon), wm_mse_clean(last clip), wm_mse_att(mean over clips),

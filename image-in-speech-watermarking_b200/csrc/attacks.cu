@@ -92,7 +92,18 @@ elementwise_kernel(const float* __restrict__ src, float* __restrict__ dst, int L
     float r;
     if (OP == EW_SCALE) r = v * p0;                                               // audio_attack.py:55-58
     else if (OP == EW_ECHO) r = v + (i >= p1 ? p0 * src[base + i - p1] : 0.f);    // audio_attack.py:47-51
-    else r = rintf(fminf(fmaxf(v, -1.f), 1.f) * 127.0f) * (1.0f / 128.0f);         // PCM_U8 round trip
+    else {
+      // PCM_U8 file round trip (audio_attack.py:85-96) as python-soundfile + libsndfile do it: soundfile opens every
+      // file with SFC_SET_CLIPPING = TRUE, so the write goes through pcm.c f2uc_clip_array / d2uc_clip_array:
+      // u = (lrint(x * 2^31) >> 24) + 128, saturating to 255 / 0; the read is (u - 128) / 128.  I.e. floor(x * 128) / 128
+      // clipped to [-1, 127/128] (a -1/256 DC bias and twice the noise of round-to-nearest).
+      const double sv = (double)v * 2147483648.0;
+      int u;
+      if (sv >= 2147483647.0) u = 255;
+      else if (sv <= -2147483648.0) u = 0;
+      else u = (int)(__double2ll_rn(sv) >> 24) + 128;
+      r = (float)(u - 128) * (1.0f / 128.0f);
+    }
     dst[base + i] = r;
   }
 }
@@ -105,35 +116,30 @@ __global__ void jitter_zero_kernel(float* __restrict__ wave, int L, const int32_
 }
 
 // jittering (audio_attack.py:156-173): np.delete(x, indices) - the unique listed samples disappear and the
-// rest close up.  Two launches per batch: the indices are marked in `dst` (as 1.0f flags over a zeroed row), then
-// one CTA per utterance compacts: thread t owns a contiguous chunk of <= 256 samples, turns its flags into a
-// bitmask, the block scans the keep counts, and - after a barrier, because the compacted samples land on top of the
-// flags - every thread copies its kept samples to their final positions; the tail is zero-filled.
-__global__ void jitter_mark_kernel(float* __restrict__ flags, int L, const int32_t* __restrict__ idx, int n_idx) {
+// rest close up.  Two launches per batch: the indices are marked in a byte-flag scratch row, then one CTA per
+// utterance compacts: thread t owns a contiguous chunk of ceil(L / 1024) samples (any L: LibriSpeech utterances
+// run to ~35 s), counts its kept samples, the block scans the counts, every thread copies its kept samples to
+// their final positions; the tail is zero-filled.
+__global__ void jitter_mark_kernel(uint8_t* __restrict__ flags, int L, const int32_t* __restrict__ idx, int n_idx) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_idx) return;
   const int k = idx[(size_t)blockIdx.y * n_idx + i];
-  if (k >= 0 && k < L) flags[(size_t)blockIdx.y * L + k] = 1.0f;
+  if (k >= 0 && k < L) flags[(size_t)blockIdx.y * L + k] = 1;
 }
 
-constexpr int JD_THREADS = 1024, JD_MAXCHUNK = 256;
+constexpr int JD_THREADS = 1024;
 __global__ void __launch_bounds__(JD_THREADS)
-jitter_delete_kernel(const float* __restrict__ src, float* __restrict__ dst, int L, int32_t* __restrict__ out_len) {
+jitter_delete_kernel(const float* __restrict__ src, float* __restrict__ dst, const uint8_t* __restrict__ flags, int L,
+                     int32_t* __restrict__ out_len) {
   __shared__ int warp_tot[JD_THREADS / 32];
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* x = src + (size_t)b * L;
+  const uint8_t* f = flags + (size_t)b * L;
   float* y = dst + (size_t)b * L;
   const int chunk = (L + JD_THREADS - 1) / JD_THREADS;
-  const int i0 = tid * chunk, i1 = min(i0 + chunk, L);
-  uint32_t del[JD_MAXCHUNK / 32];
-#pragma unroll
-  for (int w = 0; w < JD_MAXCHUNK / 32; ++w) del[w] = 0u;
+  const int i0 = min(tid * chunk, L), i1 = min(i0 + chunk, L);
   int keep = 0;
-  for (int i = i0; i < i1; ++i) {
-    const bool d = y[i] != 0.f;
-    if (d) del[(i - i0) >> 5] |= 1u << ((i - i0) & 31);
-    keep += d ? 0 : 1;
-  }
+  for (int i = i0; i < i1; ++i) keep += f[i] ? 0 : 1;
   // exclusive scan of `keep` over the block
   int incl = keep;
 #pragma unroll
@@ -142,7 +148,7 @@ jitter_delete_kernel(const float* __restrict__ src, float* __restrict__ dst, int
     if (lane >= o) incl += v;
   }
   if (lane == 31) warp_tot[warp] = incl;
-  __syncthreads();                                   // also: every flag has been read before any sample is written
+  __syncthreads();
   int base = 0, total = 0;
   for (int w = 0; w < JD_THREADS / 32; ++w) {
     if (w < warp) base += warp_tot[w];
@@ -150,9 +156,8 @@ jitter_delete_kernel(const float* __restrict__ src, float* __restrict__ dst, int
   }
   int pos = base + incl - keep;
   for (int i = i0; i < i1; ++i)
-    if (!((del[(i - i0) >> 5] >> ((i - i0) & 31)) & 1u)) y[pos++] = x[i];
-  __syncthreads();
-  for (int i = total + tid; i < L; i += JD_THREADS) y[i] = 0.f;
+    if (!f[i]) y[pos++] = x[i];
+  for (int i = total + tid; i < L; i += JD_THREADS) y[i] = 0.f;      // disjoint from the compacted range [0, total)
   if (tid == 0) out_len[b] = total;
 }
 
@@ -219,8 +224,13 @@ iir_pass_kernel(const float* __restrict__ x, double* __restrict__ tmp, float* __
 }
 
 // ---------------------------------------------------------------------------- 2:1 / 1:2 resample
+// the FIR taps travel as a kernel parameter (constant bank): no device buffer, no host synchronisation
+constexpr int RS_MAX_TAPS = 255;
+struct ResampleTaps { float h[RS_MAX_TAPS]; int nt; };
 __global__ void __launch_bounds__(256)
-resample_down_kernel(const float* __restrict__ x, float* __restrict__ d, int L, int Ld, const float* __restrict__ h, int nt) {
+resample_down_kernel(const float* __restrict__ x, float* __restrict__ d, int L, int Ld, const __grid_constant__ ResampleTaps T) {
+  const float* h = T.h;
+  const int nt = T.nt;
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= Ld) return;
   const float* xr = x + (size_t)blockIdx.y * L;
@@ -233,7 +243,9 @@ resample_down_kernel(const float* __restrict__ x, float* __restrict__ d, int L, 
   d[(size_t)blockIdx.y * Ld + m] = (float)a;
 }
 __global__ void __launch_bounds__(256)
-resample_up_kernel(const float* __restrict__ d, float* __restrict__ y, int L, int Ld, const float* __restrict__ h, int nt) {
+resample_up_kernel(const float* __restrict__ d, float* __restrict__ y, int L, int Ld, const __grid_constant__ ResampleTaps T) {
+  const float* h = T.h;
+  const int nt = T.nt;
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= L) return;
   const float* dr = d + (size_t)blockIdx.y * Ld;
@@ -359,13 +371,15 @@ extern "C" int wmk_attack_jitter_delete_f32(const float* src, float* dst, int B,
                                             int32_t* out_len, void* stream) {
   WMK_REQUIRE(src && dst && src != dst && idx && out_len && B > 0 && L > 0 && n_idx > 0,
               "jitter_delete: bad arguments (in-place not allowed)");
-  WMK_REQUIRE(L <= JD_THREADS * JD_MAXCHUNK, "jitter_delete: at most %d samples per utterance, got %d", JD_THREADS * JD_MAXCHUNK, L);
   cudaStream_t st = (cudaStream_t)stream;
   ProfScope prof(FAM_ATTACK, 12.0 * B * L, st);
-  WMK_CHECK_CUDA(cudaMemsetAsync(dst, 0, (size_t)B * L * sizeof(float), st));
-  jitter_mark_kernel<<<dim3(cdiv(n_idx, 256), B), 256, 0, st>>>(dst, L, idx, n_idx);
+  uint8_t* flags = nullptr;                                   // stream-ordered scratch: one byte per sample
+  WMK_CHECK_CUDA(cudaMallocAsync(&flags, (size_t)B * L, st));
+  WMK_CHECK_CUDA(cudaMemsetAsync(flags, 0, (size_t)B * L, st));
+  jitter_mark_kernel<<<dim3(cdiv(n_idx, 256), B), 256, 0, st>>>(flags, L, idx, n_idx);
   WMK_CHECK_LAUNCH("jitter_mark_kernel");
-  jitter_delete_kernel<<<B, JD_THREADS, 0, st>>>(src, dst, L, out_len);
+  jitter_delete_kernel<<<B, JD_THREADS, 0, st>>>(src, dst, flags, L, out_len);
+  cudaFreeAsync(flags, st);
   WMK_CHECK_LAUNCH("jitter_delete_kernel");
   return 0;
 }
@@ -411,24 +425,21 @@ extern "C" int wmk_attack_lowpass_f32(const float* src, float* dst, int B, int L
 
 extern "C" int wmk_attack_resample2_f32(const float* src, float* dst, int B, int L, const double* taps_host, int n_taps,
                                         void* stream) {
-  WMK_REQUIRE(src && dst && src != dst && B > 0 && L > 0 && taps_host && n_taps > 0 && n_taps <= 1024 && (n_taps & 1),
-              "resample2: bad arguments (odd n_taps <= 1024, in-place not allowed)");
+  WMK_REQUIRE(src && dst && src != dst && B > 0 && L > 0 && taps_host && n_taps > 0 && n_taps <= RS_MAX_TAPS && (n_taps & 1),
+              "resample2: bad arguments (odd n_taps <= 255, in-place not allowed)");
   ProfScope prof(FAM_ATTACK, 8.0 * B * L, (cudaStream_t)stream);
   cudaStream_t st = (cudaStream_t)stream;
-  std::vector<float> hf(n_taps);
-  for (int i = 0; i < n_taps; ++i) hf[i] = (float)taps_host[i];
+  ResampleTaps T;
+  T.nt = n_taps;
+  for (int i = 0; i < RS_MAX_TAPS; ++i) T.h[i] = i < n_taps ? (float)taps_host[i] : 0.f;
   const int Ld = (L + 1) / 2;
   keep_pool_memory();
-  float *h = nullptr, *d = nullptr;
-  WMK_CHECK_CUDA(cudaMallocAsync(&h, sizeof(float) * n_taps, st));
+  float* d = nullptr;
   WMK_CHECK_CUDA(cudaMallocAsync(&d, sizeof(float) * (size_t)B * Ld, st));
-  WMK_CHECK_CUDA(cudaMemcpyAsync(h, hf.data(), sizeof(float) * n_taps, cudaMemcpyHostToDevice, st));
-  WMK_CHECK_CUDA(cudaStreamSynchronize(st));   // hf is a stack-owned host buffer
-  resample_down_kernel<<<dim3(cdiv(Ld, 256), B), 256, 0, st>>>(src, d, L, Ld, h, n_taps);
+  resample_down_kernel<<<dim3(cdiv(Ld, 256), B), 256, 0, st>>>(src, d, L, Ld, T);
   WMK_CHECK_LAUNCH("resample_down_kernel");
-  resample_up_kernel<<<dim3(cdiv(L, 256), B), 256, 0, st>>>(d, dst, L, Ld, h, n_taps);
+  resample_up_kernel<<<dim3(cdiv(L, 256), B), 256, 0, st>>>(d, dst, L, Ld, T);
   WMK_CHECK_LAUNCH("resample_up_kernel");
-  WMK_CHECK_CUDA(cudaFreeAsync(h, st));
   WMK_CHECK_CUDA(cudaFreeAsync(d, st));
   return 0;
 }

@@ -229,10 +229,10 @@ rescale_kernel(const float* __restrict__ t, float* __restrict__ out, size_t n, c
 // zero padding of H, W to multiples of 8 and un-padding.  One CTA = one 8x8 block of one image:
 // 192 threads = (channel, y, x); the three planes go through shared memory so the colour
 // transforms are fused with the DCT and nothing but the output reaches HBM.
-__constant__ unsigned long long c_jpeg_keep[3];          // bit (u*8+v) set = coefficient (u,v) kept
+struct JpegKeep { unsigned long long m[3]; };             // bit (u*8+v) set = coefficient (u,v) kept; a kernel parameter
 
 __global__ void __launch_bounds__(192)
-jpeg_kernel(const float* __restrict__ in, float* __restrict__ out, int H, int W) {
+jpeg_kernel(const float* __restrict__ in, float* __restrict__ out, int H, int W, const JpegKeep K) {
   __shared__ float pl[3][8][9], tmp[3][8][9];
   const int tid = threadIdx.x, c = tid >> 6, yy = (tid >> 3) & 7, xx = tid & 7;
   const int bx = blockIdx.x, by = blockIdx.y, b = blockIdx.z;
@@ -259,7 +259,7 @@ jpeg_kernel(const float* __restrict__ in, float* __restrict__ out, int H, int W)
     float a = 0.f;
 #pragma unroll
     for (int n = 0; n < 8; ++n) a = fmaf(cospif((n + 0.5f) * yy * 0.125f), tmp[c][n][xx], a);  // along y: u = yy
-    const bool keep = (c_jpeg_keep[c] >> (yy * 8 + xx)) & 1ull;
+    const bool keep = (K.m[c] >> (yy * 8 + xx)) & 1ull;
     pl[c][yy][xx] = keep ? a : 0.f;
   }
   __syncthreads();
@@ -490,6 +490,10 @@ extern "C" int wmk_noise_resize_nearest_f32(const float* in, float* out, int pla
   return 0;
 }
 
+static __global__ void minmax_init_kernel(float* mm) {
+  if (threadIdx.x < 4) mm[threadIdx.x] = (threadIdx.x & 1) ? -INFINITY : INFINITY;
+}
+
 extern "C" int wmk_noise_quantize_f32(const float* in, float* out, size_t n, void* stream) {
   WMK_REQUIRE(in && out && n > 0, "noise_quantize: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
@@ -497,9 +501,8 @@ extern "C" int wmk_noise_quantize_f32(const float* in, float* out, size_t n, voi
   float *mm = nullptr, *tmp = nullptr;
   WMK_CHECK_CUDA(cudaMallocAsync(&mm, 4 * sizeof(float), st));
   WMK_CHECK_CUDA(cudaMallocAsync(&tmp, n * sizeof(float), st));
-  const float init[4] = {INFINITY, -INFINITY, INFINITY, -INFINITY};
-  WMK_CHECK_CUDA(cudaMemcpyAsync(mm, init, sizeof(init), cudaMemcpyHostToDevice, st));
-  WMK_CHECK_CUDA(cudaStreamSynchronize(st));          // `init` lives on this stack frame
+  minmax_init_kernel<<<1, 32, 0, st>>>(mm);             // {+inf, -inf, +inf, -inf}: no host buffer, no synchronisation
+  WMK_CHECK_LAUNCH("minmax_init_kernel");
   const int rb = (int)(cdiv(n, 256) < 1184 ? cdiv(n, 256) : 1184);
   minmax_kernel<<<rb, 256, 0, st>>>(in, n, mm);
   WMK_CHECK_LAUNCH("minmax_kernel");
@@ -528,15 +531,13 @@ extern "C" int wmk_noise_jpeg_f32(const float* in, float* out, int B, int H, int
       if (x < 0 || x > 7) continue;
       order[n][0] = x; order[n][1] = y; ++n;
     }
-  unsigned long long keep[3] = {0, 0, 0};
+  JpegKeep keep = {{0, 0, 0}};
   const int cnt[3] = {keep_y, keep_u, keep_v};
   for (int c = 0; c < 3; ++c)
-    for (int i = 0; i < cnt[c]; ++i) keep[c] |= 1ull << (order[i][0] * 8 + order[i][1]);
-  WMK_CHECK_CUDA(cudaMemcpyToSymbolAsync(c_jpeg_keep, keep, sizeof(keep), 0, cudaMemcpyHostToDevice, st));
-  WMK_CHECK_CUDA(cudaStreamSynchronize(st));          // `keep` lives on this stack frame
+    for (int i = 0; i < cnt[c]; ++i) keep.m[c] |= 1ull << (order[i][0] * 8 + order[i][1]);
   ProfScope prof(FAM_ATTACK, 24.0 * B * H * W, st);
   dim3 grid(cdiv(W, 8), cdiv(H, 8), B);
-  jpeg_kernel<<<grid, 192, 0, st>>>(in, out, H, W);
+  jpeg_kernel<<<grid, 192, 0, st>>>(in, out, H, W, keep);
   WMK_CHECK_LAUNCH("jpeg_kernel");
   return 0;
 }

@@ -216,10 +216,25 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __
   const uint32_t base = (raw + 1023u) & ~1023u;
   constexpr uint32_t A_BYTES = BM * BK * 2;
   constexpr uint32_t W_BYTES = BN * BK * 2;
-  const int kblocks = (K + BK - 1) / BK;
+  // k-block schedule.  Plain: k-block kb = columns kb*64 of A and W.  Split-bf16 (p.split = 1, K % 64 == 0): every
+  // logical k-block kk runs as three (A tile, W tile) pairs - (hi, hi), (lo, hi), (hi, lo) - where A rows are
+  // [hi(K) | lo(K)] and W rows [hi(K) | lo(K)]; p.split = 2 (K == 32): A rows [hi | lo] are ONE 64-wide tile, used
+  // against W tile 0 = [hi | hi] and W tile 1 = [lo | 0] (two k-steps).
+  const int KB = (K + BK - 1) / BK;
+  const int split = p.split;
+  const int kblocks = split == 1 ? 3 * KB : split == 2 ? 2 : KB;     // (A, W) tile pairs per output tile
+  const int wblocks = split == 1 ? 2 * KB : split == 2 ? 2 : KB;     // distinct W tiles
+  auto a_col = [&](int kb) -> int {
+    if (split == 1) { const int kk = kb / 3, seg = kb - 3 * kk; return (seg == 1 ? K : 0) + kk * BK; }
+    return split == 2 ? 0 : kb * BK;
+  };
+  auto w_idx = [&](int kb) -> int {
+    if (split == 1) { const int kk = kb / 3, seg = kb - 3 * kk; return (seg == 2 ? KB : 0) + kk; }
+    return kb;
+  };
   const uint32_t STAGE = w_stationary ? A_BYTES : A_BYTES + W_BYTES;
-  const uint32_t wres = base;                                // resident weights: kblocks x W_BYTES
-  const uint32_t stages = base + (w_stationary ? (uint32_t)kblocks * W_BYTES : 0u);
+  const uint32_t wres = base;                                // resident weights: wblocks x W_BYTES
+  const uint32_t stages = base + (w_stationary ? (uint32_t)wblocks * W_BYTES : 0u);
   // one staging box per epilogue warp: 32 rows x <= 128 B (bf16 output may use 64-byte rows, p.boxc = 32, when
   // a resident weight tile leaves too little shared memory for the A ring)
   const int BOXC = OUT_BF16 ? p.boxc : 32;
@@ -297,8 +312,8 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __
     if (lane == 0) {
       int it = 0, m0, n0;
       if (w_stationary && tile_at(0, m0, n0)) {
-        mbar_arrive_expect_tx(wfull_bar, (uint32_t)kblocks * W_BYTES);
-        for (int kb = 0; kb < kblocks; ++kb) tma_load_2d(wres + (uint32_t)kb * W_BYTES, &tmW, kb * BK, n0, wfull_bar);
+        mbar_arrive_expect_tx(wfull_bar, (uint32_t)wblocks * W_BYTES);
+        for (int wb = 0; wb < wblocks; ++wb) tma_load_2d(wres + (uint32_t)wb * W_BYTES, &tmW, wb * BK, n0, wfull_bar);
       }
       for (int i = 0; tile_at(i, m0, n0); ++i) {
         for (int kb = 0; kb < kblocks; ++kb, ++it) {
@@ -311,9 +326,9 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __
             const int rowi = m0 >> 7, img = rowi / p.conv_H, h = rowi - img * p.conv_H;
             tma_load_4d(sa, &tmA, 0, kb % 3 - 1, h + kb / 3 - 1, img, full_bar(s));
           } else {
-            tma_load_2d(sa, &tmA, kb * BK, m0, full_bar(s));
+            tma_load_2d(sa, &tmA, a_col(kb), m0, full_bar(s));
           }
-          if (!w_stationary) tma_load_2d(sa + A_BYTES, &tmW, kb * BK, n0, full_bar(s));
+          if (!w_stationary) tma_load_2d(sa + A_BYTES, &tmW, w_idx(kb) * BK, n0, full_bar(s));
         }
       }
     }
@@ -334,8 +349,8 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __
           tcgen05_fence_after();
           const uint32_t sa = stages + (uint32_t)s * STAGE;
           const uint64_t adesc = umma_desc_sw128(sa);
-          const uint64_t bdesc = umma_desc_sw128(w_stationary ? wres + (uint32_t)kb * W_BYTES : sa + A_BYTES);
-          const int krem = K - kb * BK;
+          const uint64_t bdesc = umma_desc_sw128(w_stationary ? wres + (uint32_t)w_idx(kb) * W_BYTES : sa + A_BYTES);
+          const int krem = split == 1 ? BK : split == 2 ? (kb == 0 ? 64 : 32) : K - kb * BK;
           const int ksteps = krem >= BK ? BK / UMMA_K : (krem + UMMA_K - 1) / UMMA_K;   // skip zero-filled K
           for (int k = 0; k < ksteps; ++k)
             tcgen05_mma_bf16(tacc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
@@ -411,7 +426,10 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __
             }
           }
           if constexpr (EPI == EPI_BIAS_GELU) {
-            if (p.gelu_half) {
+            if (p.gelu_exact) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = gelu_fast(f[j]);
+            } else if (p.gelu_half) {
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
                 const float2 gq = gelu_tanh2_half_arg(make_float2(f[2 * j], f[2 * j + 1]));
@@ -647,20 +665,23 @@ int launch_persistent_t(const GemmArgs& g, cudaStream_t st) {
     const uint32_t box[4] = {64, 128, 1, 1};
     WMK_TRY(make_tensor_map(&tmA, g.A, 4, dims, strides, box, false, 128));
   } else {
-    WMK_TRY(make_map(&tmA, g.A, g.M, g.K, BM));
+    WMK_TRY(make_map(&tmA, g.A, g.M, g.split ? 2 * g.K : g.K, BM));
   }
-  WMK_TRY(make_map(&tmW, g.W, g.N, g.K, BN));
-  const int kblocks = cdiv(g.K, BK);
+  const int split_mode = !g.split ? 0 : (g.K == 32 ? 2 : 1);
+  WMK_TRY(make_map(&tmW, g.W, g.N, split_mode == 2 ? 128 : split_mode == 1 ? 2 * g.K : g.K, BN));
+  const int KBl = cdiv(g.K, BK);
+  const int kblocks = split_mode == 1 ? 3 * KBl : split_mode == 2 ? 2 : KBl;       // (A, W) tile pairs per output tile
+  const int wblocks = split_mode == 1 ? 2 * KBl : split_mode == 2 ? 2 : KBl;       // distinct W tiles
   constexpr int budget = 226 * 1024;
   const int n_tiles = g.N / BN, m_tiles = cdiv(g.M, BM);
-  const int w_bytes = kblocks * BN * BK * 2;
+  const int w_bytes = wblocks * BN * BK * 2;
   int boxc = epi_box_cols(BN, OUT_BF16, LN), ws = 0, n_stages = 0;
   size_t smem = 0;
   for (;;) {
     const int stg = OUT_BF16 ? 64 * boxc : 4096;
     const int fixed = kEpiWarps * stg + 1024 + 512 + (LN ? (int)(kEpiWarps * STG2_BYTES + LN_EXCH_BYTES) : 0);
     // weight-stationary when the whole BN x K tile + >= 2 A stages fit and every N tile gets >= 1 CTA
-    ws = (g.conv_H == 0 && kblocks <= 4 && w_bytes + 2 * BM * BK * 2 + fixed <= budget && n_tiles <= num_sms() &&
+    ws = (g.conv_H == 0 && wblocks <= (split_mode ? 8 : 4) && w_bytes + 2 * BM * BK * 2 + fixed <= budget && n_tiles <= num_sms() &&
           m_tiles >= 2 * (num_sms() / n_tiles)) ? 1 : 0;
     const int stage = ws ? BM * BK * 2 : (BM + BN) * BK * 2;
     const int avail = budget - fixed - (ws ? w_bytes : 0);
@@ -691,6 +712,8 @@ int launch_persistent_t(const GemmArgs& g, cudaStream_t st) {
   static const int resid_pf = getenv("WMK_GEMM_RESID_PREFETCH") ? atoi(getenv("WMK_GEMM_RESID_PREFETCH")) : 1;
   p.resid_prefetch = resid_pf;
   p.gelu_half = g.gelu_half;
+  p.gelu_exact = g.gelu_exact;
+  p.split = split_mode;
 
   const long long total = (long long)m_tiles * n_tiles;
   const int grid = ws ? (num_sms() / n_tiles) * n_tiles : (int)(total < num_sms() ? total : num_sms());
@@ -704,8 +727,7 @@ template <int BN>
 int launch_persistent(const GemmArgs& g, cudaStream_t st) {
   if (g.epi == EPI_BIAS_GELU) {
     if (g.out_bf16) return launch_persistent_t<BN, EPI_BIAS_GELU, true>(g, st);
-    set_error("gemm_bf16: the GELU epilogue writes bf16 only");
-    return WMK_ERR_UNSUPPORTED;
+    return launch_persistent_t<BN, EPI_BIAS_GELU, false>(g, st);      // split-bf16 plans keep the hidden tensor in fp32
   }
   if (g.epi == EPI_BIAS_RELU) {
     if constexpr (BN <= 64) {
@@ -766,6 +788,9 @@ int gemm_bf16_tcgen05(const GemmArgs& g, cudaStream_t st) {
   if (g.conv_H > 0)
     WMK_REQUIRE(g.K == 576 && g.M == g.conv_B * g.conv_H * 128 && g.ldc == g.N && g.epi != EPI_UPSAMPLE,
                 "gemm_bf16: implicit-GEMM conv needs K = 576 and M = B*H*128 (W = 128)");
+  if (g.split)
+    WMK_REQUIRE((g.K == 32 || g.K % 64 == 0) && !g.out_bf16 && g.conv_H == 0 && g.epi != EPI_UPSAMPLE && g.ldc == g.N && !g.ln_out,
+                "gemm_bf16: split-bf16 operands need K = 32 or K %% 64 == 0 (K = %d), fp32 output, a plain row-major C", g.K);
   if (g.epi == EPI_UPSAMPLE)
     WMK_REQUIRE(g.up_cout % 32 == 0 && g.N == 4 * g.up_cout && g.M % (g.up_h * g.up_w) == 0,
                 "gemm_bf16: bad upsample geometry");

@@ -17,12 +17,15 @@
 
 namespace wmk {
 
+namespace tc { int num_sms(); }
 int stft_clips(const float* wave, int B, int L, float* clips, int n_clips, cudaStream_t st);
 int istft_clips(const float* clips, int B, int n_clips, int T, float* wave, int length, cudaStream_t st);
 int leff_dwconv_linear2_bf16(const __nv_bfloat16* H1, const float* dw_w, const float* dw_b, const __nv_bfloat16* W2,
                              const float* b2, float* x, int n, int H, int C, cudaStream_t st);
 int dwconv3x3_gelu_bf16(const __nv_bfloat16* in, __nv_bfloat16* out, const float* wt, const float* bias, int B, int H,
                         int Ch, cudaStream_t st);
+int dwconv3x3_gelu_split(const float* in, __nv_bfloat16* out, const float* wt, const float* bias, int B, int H, int Ch,
+                         cudaStream_t st);
 
 namespace {
 
@@ -90,7 +93,10 @@ struct wmk_plan {
   bool taps_on = false;
   std::map<std::string, std::pair<float*, size_t>> taps;
 
-  size_t op_size() const { return precision == WMK_PREC_BF16 ? 2 : 4; }
+  // operand mode of the two networks: 0 fp32 (SIMT), 1 bf16 (tcgen05), 2 split-bf16 (tcgen05, three MMAs per product)
+  int embed_mode() const { return precision == WMK_PREC_FP32 ? 0 : 1; }
+  int extract_mode() const { return precision == WMK_PREC_FP32 ? 0 : precision == WMK_PREC_BF16 ? 1 : 2; }
+  size_t op_size() const { return precision == WMK_PREC_BF16 ? 2 : 4; }      // bytes per operand element (split: hi + lo)
 };
 
 namespace wmk {
@@ -106,10 +112,27 @@ int upload_f32(wmk_plan* P, const std::vector<float>& v, float** out) {
   return 0;
 }
 
-int upload_op(wmk_plan* P, const std::vector<float>& v, void** out) {
-  if (P->precision == WMK_PREC_FP32) return upload_f32(P, v, reinterpret_cast<float**>(out));
-  std::vector<__nv_bfloat16> h(v.size());
-  for (size_t i = 0; i < v.size(); ++i) h[i] = __float2bfloat16(v[i]);
+// Dense-layer weight [N][K] (K-major) in the operand format of `mode`.  Split-bf16 (mode 2): rows [hi(K) | lo(K)]
+// with hi = bf16(w), lo = bf16(w - hi); K == 32: rows of 128 = [hi | hi | lo | 0] (gemm_tcgen05.cu, p.split = 2).
+int upload_op(wmk_plan* P, const std::vector<float>& v, void** out, int mode, int K) {
+  if (mode == 0) return upload_f32(P, v, reinterpret_cast<float**>(out));
+  std::vector<__nv_bfloat16> h;
+  if (mode == 2) {
+    const size_t N = v.size() / (size_t)K;
+    const size_t ld = K == 32 ? 128 : 2 * (size_t)K;
+    h.assign(N * ld, __float2bfloat16(0.f));
+    for (size_t n = 0; n < N; ++n)
+      for (int k = 0; k < K; ++k) {
+        const float w = v[n * K + k];
+        const __nv_bfloat16 hi = __float2bfloat16(w);
+        const __nv_bfloat16 lo = __float2bfloat16(w - __bfloat162float(hi));
+        if (K == 32) { h[n * ld + k] = hi; h[n * ld + 32 + k] = hi; h[n * ld + 64 + k] = lo; }
+        else { h[n * ld + k] = hi; h[n * ld + K + k] = lo; }
+      }
+  } else {
+    h.resize(v.size());
+    for (size_t i = 0; i < v.size(); ++i) h[i] = __float2bfloat16(v[i]);
+  }
   void* d = nullptr;
   if (cudaMalloc(&d, h.size() * 2) != cudaSuccess) { set_error("cudaMalloc of %zu bytes failed", h.size() * 2); return WMK_ERR_ALLOC; }
   P->allocs.push_back(d);
@@ -135,7 +158,7 @@ int get_f32(wmk_plan* P, const std::string& name, size_t numel, float** dev) {
   return upload_f32(P, t->data, dev);
 }
 
-int pack_block(wmk_plan* P, const std::string& p, int C, int heads, int H, int shift, bool mod, BlockW* w) {
+int pack_block(wmk_plan* P, const std::string& p, int C, int heads, int H, int shift, bool mod, BlockW* w, int mode) {
   w->C = C; w->heads = heads; w->H = H;
   w->shift = (H <= 8) ? 0 : shift;                                    // model.py:892-894
   WMK_TRY(get_f32(P, p + "norm1.weight", C, &w->ln1_w));
@@ -147,7 +170,7 @@ int pack_block(wmk_plan* P, const std::string& p, int C, int heads, int H, int s
   WMK_TRY(get(P, p + "attn.relative_position_bias_table", 225 * (size_t)heads, &tab));
   // bf16 mode: the tensor-core attention kernel works in the log2 domain (softmax by exp2), so
   // log2(e) is folded into the bias table and the q rows; fp32 mode keeps natural-log scores.
-  const float lg = P->precision == WMK_PREC_BF16 ? 1.4426950408889634f : 1.0f;
+  const float lg = mode != 0 ? 1.4426950408889634f : 1.0f;
   std::vector<float> bias((size_t)heads * 4096);
   for (int h = 0; h < heads; ++h)
     for (int i = 0; i < 64; ++i)
@@ -166,28 +189,28 @@ int pack_block(wmk_plan* P, const std::string& p, int C, int heads, int H, int s
   for (size_t i = 0; i < 2 * (size_t)C * C; ++i) wqkv[(size_t)C * C + i] = wkv->data[i];
   for (int i = 0; i < C; ++i) bqkv[i] = bq->data[i] * scale;
   for (int i = 0; i < 2 * C; ++i) bqkv[C + i] = bkv->data[i];
-  WMK_TRY(upload_op(P, wqkv, &w->w_qkv));
+  WMK_TRY(upload_op(P, wqkv, &w->w_qkv, mode, C));
   WMK_TRY(upload_f32(P, bqkv, &w->b_qkv));
   const HostTensor* t;
   WMK_TRY(get(P, p + "attn.proj.weight", (size_t)C * C, &t));
-  WMK_TRY(upload_op(P, t->data, &w->w_proj));
+  WMK_TRY(upload_op(P, t->data, &w->w_proj, mode, C));
   WMK_TRY(get_f32(P, p + "attn.proj.bias", C, &w->b_proj));
   WMK_TRY(get(P, p + "mlp.linear1.0.weight", 4 * (size_t)C * C, &t));
-  if (P->precision == WMK_PREC_BF16) {
+  if (mode == 1) {
     // the GELU epilogue of linear1 takes x / 2 (gelu_tanh2_half_arg): halve W1 and b1, exact in bf16 / fp32
     const HostTensor* tb;
     WMK_TRY(get(P, p + "mlp.linear1.0.bias", 4 * (size_t)C, &tb));
     std::vector<float> wh(t->data), bh(tb->data);
     for (auto& v : wh) v *= 0.5f;
     for (auto& v : bh) v *= 0.5f;
-    WMK_TRY(upload_op(P, wh, &w->w_l1));
+    WMK_TRY(upload_op(P, wh, &w->w_l1, mode, C));
     WMK_TRY(upload_f32(P, bh, &w->b_l1));
   } else {
-    WMK_TRY(upload_op(P, t->data, &w->w_l1));
+    WMK_TRY(upload_op(P, t->data, &w->w_l1, mode, C));
     WMK_TRY(get_f32(P, p + "mlp.linear1.0.bias", 4 * (size_t)C, &w->b_l1));
   }
   WMK_TRY(get(P, p + "mlp.linear2.0.weight", 4 * (size_t)C * C, &t));
-  WMK_TRY(upload_op(P, t->data, &w->w_l2));
+  WMK_TRY(upload_op(P, t->data, &w->w_l2, mode, 4 * C));
   WMK_TRY(get_f32(P, p + "mlp.linear2.0.bias", C, &w->b_l2));
   WMK_TRY(get(P, p + "mlp.dwconv.0.weight", 36 * (size_t)C, &dw));
   std::vector<float> dwt(36 * (size_t)C);
@@ -195,7 +218,7 @@ int pack_block(wmk_plan* P, const std::string& p, int C, int heads, int H, int s
     for (int tap = 0; tap < 9; ++tap) dwt[(size_t)tap * 4 * C + c] = dw->data[(size_t)c * 9 + tap];
   WMK_TRY(upload_f32(P, dwt, &w->dw_w));
   WMK_TRY(get_f32(P, p + "mlp.dwconv.0.bias", 4 * (size_t)C, &w->dw_b));
-  if (P->precision == WMK_PREC_BF16) {
+  if (mode == 1) {
     const HostTensor* db;
     WMK_TRY(get(P, p + "mlp.dwconv.0.bias", 4 * (size_t)C, &db));
     std::vector<float> bh(4 * (size_t)C);
@@ -207,7 +230,7 @@ int pack_block(wmk_plan* P, const std::string& p, int C, int heads, int H, int s
   return 0;
 }
 
-int pack_encoder(wmk_plan* P, const std::string& p, const std::string& inproj, EncW* e) {
+int pack_encoder(wmk_plan* P, const std::string& p, const std::string& inproj, EncW* e, int mode) {
   {
     const HostTensor *tw, *tb;
     WMK_TRY(get(P, inproj + "proj.0.weight", 32 * 2 * 9, &tw));
@@ -226,7 +249,7 @@ int pack_encoder(wmk_plan* P, const std::string& p, const std::string& inproj, E
     for (int i = 0; i < kDepths[s]; ++i) {
       const std::string bp = p + (s < 4 ? "encoderlayer_" + std::to_string(s) : std::string("conv")) + ".blocks." +
                              std::to_string(i) + ".";
-      WMK_TRY(pack_block(P, bp, C, kHeads[s], H, (i % 2) ? 4 : 0, false, &e->stage[s][i]));
+      WMK_TRY(pack_block(P, bp, C, kHeads[s], H, (i % 2) ? 4 : 0, false, &e->stage[s][i], mode));
     }
     if (s < 4) {
       const HostTensor* t;
@@ -237,7 +260,7 @@ int pack_encoder(wmk_plan* P, const std::string& p, const std::string& inproj, E
         for (int ci = 0; ci < C; ++ci)
           for (int tap = 0; tap < 16; ++tap)
             g[((size_t)co * 16 + tap) * C + ci] = t->data[((size_t)co * C + ci) * 16 + tap];
-      WMK_TRY(upload_op(P, g, &e->down_w[s]));
+      WMK_TRY(upload_op(P, g, &e->down_w[s], mode, 16 * C));
       WMK_TRY(get_f32(P, dp + "bias", 2 * (size_t)C, &e->down_b[s]));
     }
   }
@@ -288,8 +311,8 @@ int tap(wmk_plan* P, const std::string& name, const float* src, size_t n, cudaSt
 }
 
 // ------------------------------------------------------------------------------------ execution
-int gemm(wmk_plan* P, const GemmArgs& g, cudaStream_t st) {
-  return P->precision == WMK_PREC_BF16 ? gemm_bf16_tcgen05(g, st) : gemm_fp32_simt(g, st);
+int gemm(int mode, const GemmArgs& g, cudaStream_t st) {
+  return mode != 0 ? gemm_bf16_tcgen05(g, st) : gemm_fp32_simt(g, st);
 }
 
 // One LeWin block (uformerWM/model.py:937-1019) on the residual stream x.  bf16 mode, C <= 128: the two
@@ -297,60 +320,76 @@ int gemm(wmk_plan* P, const GemmArgs& g, cudaStream_t st) {
 // attention projection, and the NEXT block's norm1 (+ modulator) into this block's linear2 - so the fp32
 // stream is not re-read; `ln1_ready` says the previous block already left LN1(x) in bufA, `next` is the
 // following block of the same stage (nullptr for the last one).
+// Split-bf16 mode (OpT = SplitBf16, the WMK_PREC_MIXED extractor): the A operands of the four dense layers
+// (bufA, bufO, bufH2) are split rows [hi | lo] written by their producers (LayerNorm, attention, depthwise
+// conv), the dense layers' outputs (bufQKV, bufH1) stay fp32, every GELU is the erf form.
 template <typename OpT>
 int run_block(wmk_plan* P, const BlockW& w, float* x, int n, cudaStream_t st, bool ln1_ready = false,
               const BlockW* next = nullptr) {
+  constexpr int MODE = OpMode<OpT>::v;
   const int C = w.C, H = w.H;
   const int M = n * H * H;
-  const int ob = sizeof(OpT) == 2;
+  const int ob = MODE == 1;
   static const int fuse_min_c = getenv("WMK_FUSE_LN_MINC") ? atoi(getenv("WMK_FUSE_LN_MINC")) : 32;
-  const bool fuse_ln = sizeof(OpT) == 2 && C <= 128 && C >= fuse_min_c;
+  const bool fuse_ln = MODE == 1 && C <= 128 && C >= fuse_min_c;
   OpT* A = reinterpret_cast<OpT*>(P->bufA);
-  OpT* QKV = reinterpret_cast<OpT*>(P->bufQKV);
-  OpT* O = reinterpret_cast<OpT*>(P->bufO);
-  OpT* H1 = reinterpret_cast<OpT*>(P->bufH1);
-  OpT* H2 = reinterpret_cast<OpT*>(P->bufH2);
   if (!(ln1_ready && fuse_ln)) {
     ProfScope prof(FAM_LAYERNORM, (double)M * C * (4 + sizeof(OpT)), st);
     launch_layernorm<OpT>(x, A, w.ln1_w, w.ln1_b, w.mod, M, C, H, w.shift, st);
     WMK_CHECK_LAUNCH("layernorm_kernel");
   }
   GemmArgs g;
-  g.A = A; g.W = w.w_qkv; g.bias = w.b_qkv; g.C = QKV; g.M = M; g.N = 3 * C; g.K = C; g.ldc = 3 * C;
-  g.epi = EPI_BIAS; g.out_bf16 = ob;
-  WMK_TRY(gemm(P, g, st));
+  g.A = A; g.W = w.w_qkv; g.bias = w.b_qkv; g.C = P->bufQKV; g.M = M; g.N = 3 * C; g.K = C; g.ldc = 3 * C;
+  g.epi = EPI_BIAS; g.out_bf16 = ob; g.split = MODE == 2;
+  WMK_TRY(gemm(MODE, g, st));
   {
     ProfScope prof(FAM_ATTENTION, 256.0 * C * M, st);
-    if constexpr (sizeof(OpT) == 2)
-    {
-      const int n_windows = n * (H / 8) * (H / 8);
+    const int n_windows = n * (H / 8) * (H / 8);
+    if constexpr (MODE == 1) {
       int per_head = (148 * 5) / w.heads;                 // CTAs per head (5 resident CTAs per SM)
       if (per_head > n_windows) per_head = n_windows;
       if (per_head < 1) per_head = 1;
-      window_attention_mma_kernel<<<per_head * w.heads, 128, 0, st>>>(QKV, O, w.attn_bias, C, H, w.shift, n_windows);
+      window_attention_mma_kernel<<<per_head * w.heads, 128, 0, st>>>(
+          reinterpret_cast<const __nv_bfloat16*>(P->bufQKV), reinterpret_cast<__nv_bfloat16*>(P->bufO), w.attn_bias, C, H,
+          w.shift, n_windows);
+    } else if constexpr (MODE == 2) {
+      static bool attr_set = false;
+      if (!attr_set) {
+        WMK_CHECK_CUDA(cudaFuncSetAttribute(window_attention_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTS_SMEM));
+        attr_set = true;
+      }
+      int per_head = (tc::num_sms() * 2) / w.heads;       // two resident CTAs per SM (97 KB of shared memory each)
+      if (per_head > n_windows) per_head = n_windows;
+      if (per_head < 1) per_head = 1;
+      window_attention_split_kernel<<<per_head * w.heads, 128, ATTS_SMEM, st>>>(
+          reinterpret_cast<const float*>(P->bufQKV), reinterpret_cast<__nv_bfloat16*>(P->bufO), w.attn_bias, C, H, w.shift,
+          n_windows);
+    } else {
+      window_attention_kernel<float><<<dim3(n_windows, w.heads), 128, 0, st>>>(
+          reinterpret_cast<const float*>(P->bufQKV), reinterpret_cast<float*>(P->bufO), w.attn_bias, C, H, w.shift);
     }
-    else
-      window_attention_kernel<OpT><<<dim3(n * (H / 8) * (H / 8), w.heads), 128, 0, st>>>(QKV, O, w.attn_bias, C, H, w.shift);
     WMK_CHECK_LAUNCH("window_attention_kernel");
   }
   g = GemmArgs();
-  g.A = O; g.W = w.w_proj; g.bias = w.b_proj; g.resid = x; g.C = x; g.M = M; g.N = C; g.K = C; g.ldc = C;
-  g.epi = EPI_BIAS_RESID; g.out_bf16 = 0;
+  g.A = P->bufO; g.W = w.w_proj; g.bias = w.b_proj; g.resid = x; g.C = x; g.M = M; g.N = C; g.K = C; g.ldc = C;
+  g.epi = EPI_BIAS_RESID; g.out_bf16 = 0; g.split = MODE == 2;
   if (fuse_ln) { g.ln_out = A; g.ln_gamma = w.ln2_w; g.ln_beta = w.ln2_b; }        // norm2 (model.py:1017)
-  WMK_TRY(gemm(P, g, st));
+  WMK_TRY(gemm(MODE, g, st));
   if (!fuse_ln) {
     ProfScope prof(FAM_LAYERNORM, (double)M * C * (4 + sizeof(OpT)), st);
     launch_layernorm<OpT>(x, A, w.ln2_w, w.ln2_b, nullptr, M, C, H, 0, st);
     WMK_CHECK_LAUNCH("layernorm_kernel");
   }
   g = GemmArgs();
-  g.A = A; g.W = w.w_l1; g.bias = w.b_l1; g.C = H1; g.M = M; g.N = 4 * C; g.K = C; g.ldc = 4 * C;
+  g.A = A; g.W = w.w_l1; g.bias = w.b_l1; g.C = P->bufH1; g.M = M; g.N = 4 * C; g.K = C; g.ldc = 4 * C;
   g.epi = EPI_BIAS_GELU; g.out_bf16 = ob; g.gelu_half = ob;      // bf16 plans carry W1 / 2, b1 / 2 (pack_block)
-  WMK_TRY(gemm(P, g, st));
-  if constexpr (sizeof(OpT) == 2) {
+  g.split = MODE == 2; g.gelu_exact = MODE == 2;
+  WMK_TRY(gemm(MODE, g, st));
+  if constexpr (MODE == 1) {
     if (P->fused_leff && C <= 256 && H <= P->fused_maxh && H >= P->fused_minh) {
       // depthwise conv + GELU as the producer of linear2's A operand: H2 never reaches HBM (leff_fused.cu)
-      WMK_TRY(leff_dwconv_linear2_bf16(H1, w.dw_w, w.dw_b, reinterpret_cast<const __nv_bfloat16*>(w.w_l2), w.b_l2, x, n, H, C, st));
+      WMK_TRY(leff_dwconv_linear2_bf16(reinterpret_cast<const __nv_bfloat16*>(P->bufH1), w.dw_w, w.dw_b,
+                                       reinterpret_cast<const __nv_bfloat16*>(w.w_l2), w.b_l2, x, n, H, C, st));
       if (fuse_ln && next) {
         ProfScope prof(FAM_LAYERNORM, (double)M * C * (4 + sizeof(OpT)), st);
         launch_layernorm<OpT>(x, A, next->ln1_w, next->ln1_b, next->mod, M, C, H, next->shift, st);
@@ -360,23 +399,26 @@ int run_block(wmk_plan* P, const BlockW& w, float* x, int n, cudaStream_t st, bo
     }
   }
   {
-    const size_t total = (size_t)M * C;     // (4C / 4) channel groups per pixel
     ProfScope prof(FAM_DWCONV, 8.0 * M * C * sizeof(OpT), st);
-    (void)total;
-    if constexpr (sizeof(OpT) == 2) {
-      WMK_TRY(dwconv3x3_gelu_bf16(H1, H2, w.dw_wh, w.dw_bh, n, H, 4 * C, st));
+    if constexpr (MODE == 1) {
+      WMK_TRY(dwconv3x3_gelu_bf16(reinterpret_cast<const __nv_bfloat16*>(P->bufH1), reinterpret_cast<__nv_bfloat16*>(P->bufH2),
+                                  w.dw_wh, w.dw_bh, n, H, 4 * C, st));
+    } else if constexpr (MODE == 2) {
+      WMK_TRY(dwconv3x3_gelu_split(reinterpret_cast<const float*>(P->bufH1), reinterpret_cast<__nv_bfloat16*>(P->bufH2),
+                                   w.dw_w, w.dw_b, n, H, 4 * C, st));
     } else {
-      dwconv3x3_gelu_kernel<OpT><<<n * (H / 8) * (H / 8) * ((4 * C) / 64), 128, 0, st>>>(H1, H2, w.dw_w, w.dw_b, n, H, 4 * C);
+      dwconv3x3_gelu_kernel<float><<<n * (H / 8) * (H / 8) * ((4 * C) / 64), 128, 0, st>>>(
+          reinterpret_cast<const float*>(P->bufH1), reinterpret_cast<float*>(P->bufH2), w.dw_w, w.dw_b, n, H, 4 * C);
       WMK_CHECK_LAUNCH("dwconv3x3_gelu_kernel");
     }
   }
   g = GemmArgs();
-  g.A = H2; g.W = w.w_l2; g.bias = w.b_l2; g.resid = x; g.C = x; g.M = M; g.N = C; g.K = 4 * C; g.ldc = C;
-  g.epi = EPI_BIAS_RESID; g.out_bf16 = 0;
+  g.A = P->bufH2; g.W = w.w_l2; g.bias = w.b_l2; g.resid = x; g.C = x; g.M = M; g.N = C; g.K = 4 * C; g.ldc = C;
+  g.epi = EPI_BIAS_RESID; g.out_bf16 = 0; g.split = MODE == 2;
   if (fuse_ln && next) {                                                           // the next block's norm1 + modulator
     g.ln_out = A; g.ln_gamma = next->ln1_w; g.ln_beta = next->ln1_b; g.ln_mod = next->mod; g.ln_H = H; g.ln_shift = next->shift;
   }
-  WMK_TRY(gemm(P, g, st));
+  WMK_TRY(gemm(MODE, g, st));
   return 0;
 }
 
@@ -396,7 +438,7 @@ int run_encoder(wmk_plan* P, const EncW& e, const float* x_nchw, int n, const ch
   {
     ProfScope prof(FAM_SMALL, (double)n * 16384 * (8 + 128), st);
     static const int fuse_ln0 = getenv("WMK_FUSE_FIRST_LN") ? atoi(getenv("WMK_FUSE_FIRST_LN")) : 1;
-    const bool ln0 = sizeof(OpT) == 2 && fuse_ln0 && e.in_proj_has_ln;       // norm1 of stage 0's block in the same pass
+    const bool ln0 = OpMode<OpT>::v == 1 && fuse_ln0 && e.in_proj_has_ln;       // norm1 of stage 0's block in the same pass
     input_proj_kernel<<<cdiv((size_t)n * 16384, 128), 128, 0, st>>>(x_nchw, P->E[0], e.in_proj, n,
                                                                    ln0 ? reinterpret_cast<__nv_bfloat16*>(P->bufA) : nullptr);
     WMK_CHECK_LAUNCH("input_proj_kernel");
@@ -421,15 +463,15 @@ int run_encoder(wmk_plan* P, const EncW& e, const float* x_nchw, int n, const ch
     }
     GemmArgs g;
     g.A = col; g.W = e.down_w[s]; g.bias = e.down_b[s]; g.C = P->E[s + 1]; g.M = n * Ho * Ho; g.N = 2 * C;
-    g.K = 16 * C; g.ldc = 2 * C; g.epi = EPI_BIAS; g.out_bf16 = 0;
+    g.K = 16 * C; g.ldc = 2 * C; g.epi = EPI_BIAS; g.out_bf16 = 0; g.split = OpMode<OpT>::v == 2;
     static const int fuse_first_ln = getenv("WMK_FUSE_FIRST_LN") ? atoi(getenv("WMK_FUSE_FIRST_LN")) : 1;
-    if (sizeof(OpT) == 2 && fuse_first_ln && 2 * C <= 128) {
+    if (OpMode<OpT>::v == 1 && fuse_first_ln && 2 * C <= 128) {
       // the next stage's first norm1 rides on the downsample conv's epilogue (encoder blocks carry no modulator)
       const BlockW& nb = e.stage[s + 1][0];
       g.ln_out = P->bufA; g.ln_gamma = nb.ln1_w; g.ln_beta = nb.ln1_b; g.ln_mod = nb.mod; g.ln_H = Ho; g.ln_shift = nb.shift;
       ln_ready = true;
     }
-    WMK_TRY(gemm(P, g, st));
+    WMK_TRY(gemm(OpMode<OpT>::v, g, st));
     WMK_TRY(tap(P, t + ".pool" + std::to_string(s), P->E[s + 1], (size_t)n * Ho * Ho * 2 * C, st));
   }
   return 0;
@@ -447,10 +489,18 @@ int run_extract(wmk_plan* P, const float* y, int n, float* wm, float* logits, cu
   return 0;
 }
 
+// the extractor in the plan's extractor mode (WMK_PREC_MIXED: split-bf16 whatever the embedder runs in)
+int run_extract_any(wmk_plan* P, const float* y, int n, float* wm, float* logits, cudaStream_t st) {
+  switch (P->extract_mode()) {
+    case 0: return run_extract<float>(P, y, n, wm, logits, st);
+    case 1: return run_extract<__nv_bfloat16>(P, y, n, wm, logits, st);
+    default: return run_extract<SplitBf16>(P, y, n, wm, logits, st);
+  }
+}
+
 template <typename OpT>
 int run_forward(wmk_plan* P, const float* x, const float* msg, int msg_stride, int n, float* stft_new, float* noise,
                 float* y_out, float* wm_pred, float* wm, float* wm_logits, cudaStream_t st) {
-  const int ob = sizeof(OpT) == 2;
   wm_encode_kernel<<<n, 256, 0, st>>>(msg, msg_stride, P->feat, P->codec_c1w, P->codec_c1b, P->codec_c2w, P->codec_c2b);
   WMK_CHECK_LAUNCH("wm_encode_kernel");
   WMK_TRY(run_encoder<OpT>(P, P->enc, x, n, "enc", st));
@@ -477,7 +527,7 @@ int run_forward(wmk_plan* P, const float* x, const float* msg, int msg_stride, i
     GemmArgs g;
     g.A = A; g.W = P->up_w[s]; g.bias = P->up_b[s]; g.C = P->D[s]; g.M = n * Hin * Hin; g.N = 4 * Cout; g.K = Cin;
     g.ldc = Cd; g.epi = EPI_UPSAMPLE; g.out_bf16 = 0; g.up_h = Hin; g.up_w = Hin; g.up_cout = Cout;
-    WMK_TRY(gemm(P, g, st));
+    WMK_TRY(gemm(OpMode<OpT>::v, g, st));
     {
       const size_t rows = (size_t)n * Hout * Hout;
       ProfScope prof_cp(FAM_LAYOUT, (double)rows * Cout * 8, st);
@@ -487,7 +537,6 @@ int run_forward(wmk_plan* P, const float* x, const float* msg, int msg_stride, i
     WMK_TRY(run_stage<OpT>(P, P->dec[s], P->D[s], n, st));
     WMK_TRY(tap(P, "dec.deconv" + std::to_string(s), P->D[s], (size_t)n * Hout * Hout * Cd, st));
   }
-  (void)ob;
   float* y = y_out ? y_out : P->ybuf;
   {
     ProfScope prof(FAM_SMALL, (double)n * 16384 * (256 + 24), st);
@@ -508,7 +557,7 @@ int run_forward(wmk_plan* P, const float* x, const float* msg, int msg_stride, i
       WMK_CHECK_LAUNCH("conv3x3_nchw_kernel<4,2>");
     }
   }
-  if (wm || wm_logits) WMK_TRY(run_extract<OpT>(P, y, n, wm, wm_logits, st));   // model.py:2508-2509 reads y
+  if (wm || wm_logits) WMK_TRY(run_extract_any(P, y, n, wm, wm_logits, st));    // model.py:2508-2509 reads y
   return 0;
 }
 
@@ -525,13 +574,14 @@ int check_ready(wmk_plan* P) {
 // ------------------------------------------------------------------------------------ C ABI
 extern "C" int wmk_uformer_plan_create(int precision, wmk_plan** out) {
   WMK_REQUIRE(out, "plan_create: null out");
-  WMK_REQUIRE(precision == WMK_PREC_FP32 || precision == WMK_PREC_BF16, "plan_create: unknown precision %d", precision);
+  WMK_REQUIRE(precision == WMK_PREC_FP32 || precision == WMK_PREC_BF16 || precision == WMK_PREC_MIXED,
+              "plan_create: unknown precision %d", precision);
   int dev = 0;
   WMK_CHECK_CUDA(cudaGetDevice(&dev));
   cudaDeviceProp prop;
   WMK_CHECK_CUDA(cudaGetDeviceProperties(&prop, dev));
-  if (precision == WMK_PREC_BF16 && prop.major != 10) {
-    set_error("bf16 precision needs an sm_100 device (tcgen05); found sm_%d%d", prop.major, prop.minor);
+  if (precision != WMK_PREC_FP32 && prop.major != 10) {
+    set_error("bf16 / mixed precision needs an sm_100 device (tcgen05); found sm_%d%d", prop.major, prop.minor);
     return WMK_ERR_UNSUPPORTED;
   }
   wmk_plan* P = new wmk_plan();
@@ -577,8 +627,8 @@ extern "C" int wmk_plan_finalize(wmk_plan* P) {
   WMK_REQUIRE(P, "finalize: null plan");
   if (P->finalized) return 0;
   WMK_CHECK_CUDA(cudaSetDevice(P->device));
-  WMK_TRY(pack_encoder(P, "encoder.", "input_proj.", &P->enc));
-  WMK_TRY(pack_encoder(P, "decoder_wm.", "decoder_wm.input_proj.", &P->ext));
+  WMK_TRY(pack_encoder(P, "encoder.", "input_proj.", &P->enc, P->embed_mode()));
+  WMK_TRY(pack_encoder(P, "decoder_wm.", "decoder_wm.input_proj.", &P->ext, P->extract_mode()));
   for (int s = 0; s < 4; ++s) {
     const int Cin = (s == 0) ? 1024 : (1024 >> s), Cout = 256 >> s, Cd = 2 * Cout, H = 16 << s;
     const std::string up = "decoder.upsample_" + std::to_string(s) + ".deconv.0.";
@@ -591,12 +641,12 @@ extern "C" int wmk_plan_finalize(wmk_plan* P) {
         for (int ij = 0; ij < 4; ++ij) g[((size_t)ij * Cout + co) * Cin + ci] = t->data[((size_t)ci * Cout + co) * 4 + ij];
     for (int ij = 0; ij < 4; ++ij)
       for (int co = 0; co < Cout; ++co) b4[(size_t)ij * Cout + co] = tb->data[co];
-    WMK_TRY(upload_op(P, g, &P->up_w[s]));
+    WMK_TRY(upload_op(P, g, &P->up_w[s], P->embed_mode(), Cin));
     WMK_TRY(upload_f32(P, b4, &P->up_b[s]));
     P->dec[s].resize(kDepths[5 + s]);
     for (int i = 0; i < kDepths[5 + s]; ++i) {
       const std::string bp = "decoder.decoderlayer_" + std::to_string(s) + ".blocks." + std::to_string(i) + ".";
-      WMK_TRY(pack_block(P, bp, Cd, kHeads[5 + s], H, (i % 2) ? 4 : 0, true, &P->dec[s][i]));
+      WMK_TRY(pack_block(P, bp, Cd, kHeads[5 + s], H, (i % 2) ? 4 : 0, true, &P->dec[s][i], P->embed_mode()));
     }
   }
   {
@@ -638,7 +688,7 @@ extern "C" int wmk_uformer_forward(wmk_plan* P, const float* x, const float* msg
     const size_t o = (size_t)b0;
     auto off = [&](float* p, size_t per) { return p ? p + o * per : nullptr; };
     int s;
-    if (P->precision == WMK_PREC_BF16)
+    if (P->embed_mode() == 1)
       s = run_forward<__nv_bfloat16>(P, x + o * 32768, msg + o * msg_stride, msg_stride, n, off(stft_new, 32768),
                                      off(noise, 32768), off(y, 32768), off(wm_pred, 1024), off(wm, 1024),
                                      off(wm_logits, 1024), st);
@@ -657,14 +707,25 @@ extern "C" int wmk_uformer_extract(wmk_plan* P, const float* y, int B, float* wm
   for (int b0 = 0; b0 < B; b0 += P->chunk) {
     const int n = B - b0 < P->chunk ? B - b0 : P->chunk;
     const size_t o = (size_t)b0;
-    int s;
-    if (P->precision == WMK_PREC_BF16)
-      s = run_extract<__nv_bfloat16>(P, y + o * 32768, n, wm ? wm + o * 1024 : nullptr,
-                                     wm_logits ? wm_logits + o * 1024 : nullptr, st);
-    else
-      s = run_extract<float>(P, y + o * 32768, n, wm ? wm + o * 1024 : nullptr,
-                             wm_logits ? wm_logits + o * 1024 : nullptr, st);
+    const int s = run_extract_any(P, y + o * 32768, n, wm ? wm + o * 1024 : nullptr,
+                                  wm_logits ? wm_logits + o * 1024 : nullptr, st);
     if (s) return s;
+  }
+  return 0;
+}
+
+extern "C" int wmk_uformer_autoencode(wmk_plan* P, const float* msg, int msg_stride, int B, float* wm_pred, void* stream) {
+  WMK_TRY(check_ready(P));
+  WMK_REQUIRE(msg && wm_pred && B > 0 && (msg_stride == 0 || msg_stride == 1024), "autoencode: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int b0 = 0; b0 < B; b0 += P->chunk) {
+    const int n = B - b0 < P->chunk ? B - b0 : P->chunk;
+    wm_encode_kernel<<<n, 256, 0, st>>>(msg + (size_t)b0 * msg_stride, msg_stride, P->feat, P->codec_c1w, P->codec_c1b,
+                                        P->codec_c2w, P->codec_c2b);
+    WMK_CHECK_LAUNCH("wm_encode_kernel");
+    wm_decode_kernel<<<n, 256, 0, st>>>(P->feat, nullptr, wm_pred + (size_t)b0 * 1024, nullptr, P->codec_t1w, P->codec_t1b,
+                                        P->codec_t2w, P->codec_t2b);
+    WMK_CHECK_LAUNCH("wm_decode_kernel");
   }
   return 0;
 }
@@ -692,6 +753,24 @@ static __global__ void widen_kernel(const __nv_bfloat16* in, float* out, size_t 
   if (i < n) out[i] = __bfloat162float(in[i]);
 }
 
+// fp32 [rows][K] -> split-bf16 rows.  form 0: [hi(K) | lo(K)]; form 1 (K = 32 weight rows): [hi | hi | lo | 0].
+static __global__ void split_rows_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t rows, int K, int form) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * (size_t)K) return;
+  const size_t r = i / K;
+  const int k = (int)(i - r * K);
+  const float v = src[i];
+  const __nv_bfloat16 hi = __float2bfloat16(v);
+  const __nv_bfloat16 lo = __float2bfloat16(v - __bfloat162float(hi));
+  if (form == 1) {
+    __nv_bfloat16* d = dst + r * 128;
+    d[k] = hi; d[32 + k] = hi; d[64 + k] = lo; d[96 + k] = __float2bfloat16(0.f);
+  } else {
+    __nv_bfloat16* d = dst + r * 2 * (size_t)K;
+    d[k] = hi; d[K + k] = lo;
+  }
+}
+
 extern "C" int wmk_linear_f32(const float* A, const float* W, const float* bias, float* C, int M, int N, int K,
                               int precision, int gelu, void* stream) {
   WMK_REQUIRE(A && W && C && M > 0 && N > 0 && K > 0, "linear: bad arguments");
@@ -701,6 +780,22 @@ extern "C" int wmk_linear_f32(const float* A, const float* W, const float* bias,
   if (precision == WMK_PREC_FP32) {
     g.A = A; g.W = W;
     return gemm_fp32_simt(g, st);
+  }
+  if (precision == WMK_PREC_MIXED) {       // split-bf16 operands: three tcgen05 MMAs per product, fp32 output
+    WMK_REQUIRE(K == 32 || K % 64 == 0, "linear(split): K must be 32 or a multiple of 64, got %d", K);
+    const int ldw = K == 32 ? 128 : 2 * K;
+    __nv_bfloat16 *as = nullptr, *wsp = nullptr;
+    WMK_CHECK_CUDA(cudaMallocAsync(&as, (size_t)M * 2 * K * 2, st));
+    WMK_CHECK_CUDA(cudaMallocAsync(&wsp, (size_t)N * ldw * 2, st));
+    split_rows_kernel<<<cdiv((size_t)M * K, 256), 256, 0, st>>>(A, as, (size_t)M, K, 0);
+    WMK_CHECK_LAUNCH("split_rows_kernel");
+    split_rows_kernel<<<cdiv((size_t)N * K, 256), 256, 0, st>>>(W, wsp, (size_t)N, K, K == 32 ? 1 : 0);
+    WMK_CHECK_LAUNCH("split_rows_kernel");
+    g.A = as; g.W = wsp; g.split = 1; g.gelu_exact = 1;
+    const int s = gemm_bf16_tcgen05(g, st);
+    cudaFreeAsync(as, st);
+    cudaFreeAsync(wsp, st);
+    return s;
   }
   WMK_REQUIRE(precision == WMK_PREC_BF16, "linear: unknown precision %d", precision);
   __nv_bfloat16 *a16 = nullptr, *w16 = nullptr;

@@ -104,6 +104,12 @@ struct GemmArgs {
   // tile = the 128 pixels of one image row, k-block kb = tap (dy, dx) fetched as the TMA box shifted by (dy-1, dx-1)
   // with out-of-bounds zero fill as the padding; W is [N][9*64] with k = tap*64 + ci.  M = conv_B*conv_H*128, K = 576.
   int conv_H = 0, conv_B = 0;
+  // Split-bf16 ("bf16x3") operands: A is [M][2K] bf16, row = [hi(K) | lo(K)] with hi = bf16(v), lo = bf16(v - hi);
+  // W is the packed split weight of pack_split_weight() ([N][2K] = [hi | lo]; K == 32: [N][128] = [hi | hi | lo | 0]).
+  // The product is hi*hi + lo*hi + hi*lo, accumulated by three tcgen05 MMAs per k-step into the same fp32 TMEM
+  // accumulator.  Outputs are fp32 (out_bf16 = 0).  gelu_exact: GELU by the 1.5e-7 erf form (gelu_fast).
+  int split = 0;
+  int gelu_exact = 0;
 };
 
 // Roofline class of a dense-layer launch: algorithmic bytes (A + W + C, + the fp32 residual) against
@@ -111,6 +117,7 @@ struct GemmArgs {
 // launch is HBM bound.  `es` = operand element size (2 = bf16, 4 = fp32).
 struct GemmWork { int family; double work, work2; };
 static inline GemmWork gemm_work(const GemmArgs& g, int es) {
+  if (g.split) es = 4;                   // hi + lo
   const double flops = 2.0 * g.M * g.N * g.K;
   const double bytes = (double)g.M * g.K * es + (double)g.N * g.K * es + (double)g.M * g.N * (g.out_bf16 ? 2 : 4) +
                        (g.epi == EPI_BIAS_RESID ? (double)g.M * g.N * 4 : 0.0);
@@ -192,6 +199,31 @@ __device__ __forceinline__ float2 gelu_tanh2_half_arg(float2 h) {
   return __ffma2_rn(h, t, h);
 }
 
+// Split-bf16 ("bf16x3") operand format of the WMK_PREC_MIXED extractor: a value v travels as hi = bf16(v),
+// lo = bf16(v - hi) (16 mantissa bits); a row of K values is stored as [hi(K) | lo(K)], i.e. 2K bf16 = 4K bytes.
+// Tag type: sizeof 4 like the storage per element.
+struct SplitBf16 { __nv_bfloat16 h, l; };
+template <typename T> struct OpMode { static constexpr int v = 0; };                // 0 fp32, 1 bf16, 2 split-bf16
+template <> struct OpMode<__nv_bfloat16> { static constexpr int v = 1; };
+template <> struct OpMode<SplitBf16> { static constexpr int v = 2; };
+
+// (hi, lo) words of two consecutive values
+__device__ __forceinline__ void split_pack2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  const float ra = a - __uint_as_float(hi << 16), rb = b - __uint_as_float(hi & 0xffff0000u);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(ra, rb);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+// store 4 consecutive values of a split row: `row` points at the row's hi part, the lo part starts K elements later
+__device__ __forceinline__ void split_store4(__nv_bfloat16* row, int c, int K, float a, float b, float c2, float d) {
+  uint2 h, l;
+  split_pack2(a, b, h.x, l.x);
+  split_pack2(c2, d, h.y, l.y);
+  *reinterpret_cast<uint2*>(row + c) = h;
+  *reinterpret_cast<uint2*>(row + K + c) = l;
+}
+
 // Where element (m, n) of a GEMM result is stored.
 struct EpiParams {
   const float* bias;
@@ -207,6 +239,8 @@ struct EpiParams {
   int boxc = 64;       // persistent kernel, bf16 output: columns per TMA store box (64 or 32)
   int resid_prefetch = 0;   // persistent kernel: L2-prefetch the next tile's residual rows
   int gelu_half = 0;        // GELU epilogue: the accumulator holds x / 2 (weights and bias pre-halved)
+  int gelu_exact = 0;       // GELU epilogue: erf form (gelu_fast, |error| 1.5e-7) instead of the tanh form
+  int split = 0;            // 0: plain; 1: split-bf16 operands, K % 64 == 0; 2: split-bf16 operands, K == 32
 };
 
 __device__ __forceinline__ size_t epi_row_offset(const EpiParams& p, int m, int n_first) {

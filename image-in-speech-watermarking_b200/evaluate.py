@@ -100,7 +100,7 @@ def format_result(data_cat, attack, clips_total, mse, wm_loss, wm_loss_att, snr,
 
 
 def test(model, messages, waves, data_cat='train', result_path=None, attack=None, audio_scale='0', data_max=None,
-         data_min=None, model_name='uformer', draws=None, seed=0, save_audio=False):
+         data_min=None, model_name='uformer', draws=None, seed=None, save_audio=False):
     """Batched counterpart of `test()` (`uformerWM/evaluate.py:174-292`): the reference loops over utterances with
     batch 1, appends python floats to lists and averages them; here all utterances (waves (B,L) CUDA, messages
     (B or 1,1,32,32)) go through `audio_test.embed_attack_extract` in one pass and only the per-utterance

@@ -10,7 +10,7 @@ def get_arch(opt):
         return UformerAudio(img_size=opt.train_ps, embed_dim=32, win_size=8, token_projection='linear',
                             token_mlp='leff', depths=[1, 2, 8, 8, 2, 8, 8, 2, 1], modulator=True, dd_in=2,
                             in_chans=2, audio_scale=getattr(opt, 'audio_scale', '0'),
-                            precision=getattr(opt, 'precision', 'bf16'))
+                            precision=getattr(opt, 'precision', 'mixed'))
     raise Exception("Arch error!")
 
 

@@ -41,8 +41,13 @@ typedef enum wmk_status {
 /* arithmetic of the dense contractions of the Uformer blocks */
 typedef enum wmk_precision {
   WMK_PREC_FP32 = 0,     /* fp32 SIMT GEMMs: the 1e-3 parity mode */
-  WMK_PREC_BF16 = 1      /* bf16 operands on tcgen05 tensor cores, fp32 accumulate in TMEM,
+  WMK_PREC_BF16 = 1,     /* bf16 operands on tcgen05 tensor cores, fp32 accumulate in TMEM,
                             fp32 residual stream / LayerNorm / softmax */
+  WMK_PREC_MIXED = 2     /* embedder as WMK_PREC_BF16; the EXTRACTOR (decoder_wm + head, the path whose thresholded
+                            bits must equal the reference's outside |logit| < 1e-4) in split-bf16 ("bf16x3"): every
+                            operand carried as hi = bf16(v), lo = bf16(v - hi) and every product as the three
+                            tcgen05 MMAs hi*hi + lo*hi + hi*lo into one fp32 TMEM accumulator (16 mantissa bits per
+                            operand); intermediates fp32, GELU by the 1.5e-7 erf form.  The benchmarked mode. */
 } wmk_precision;
 
 int wmk_version(void);
@@ -286,6 +291,11 @@ int wmk_uformer_forward(wmk_plan* plan, const float* x, const float* msg, int ms
 /* UformerAudio.wm_decode (model.py:2379-2382). */
 int wmk_uformer_extract(wmk_plan* plan, const float* y, int B, float* wm, float* wm_logits,
                         void* stream);
+/* ConvAutoencoder.forward on the message alone (model.py:1733-1748): wm_pred = sigmoid(decode(encode(msg))),
+ * the second output of UformerAudio.feature_extract (model.py:2345-2346,2377) - no bottleneck term, unlike the
+ * wm_pred of forward (model.py:2398-2404).  msg [B or 1][1][32][32] (msg_stride 0 or 1024), wm_pred [B][1024]. */
+int wmk_uformer_autoencode(wmk_plan* plan, const float* msg, int msg_stride, int B, float* wm_pred,
+                           void* stream);
 /* Debug taps: copy a named intermediate of the LAST pass (e.g. "enc.conv0", "dec.deconv3",
  * "ext.conv4", see oracle/uformer.py) to out (float32, token layout).  Only valid when B <=
  * clips_per_pass.  Returns the element count through n_out. */

@@ -55,6 +55,20 @@ def model_fixture(kind, seed):
     print("model_%s: wm range %.4f..%.4f" % (kind, wm.min(), wm.max()))
 
 
+def feature_extract_fixture(kind="stress", seed=0):
+    """`UformerAudio.feature_extract` (`uformerWM/model.py:2345-2377`) of the unmodified reference on the inputs of
+    `model_<kind>.npz`: wm_pred (the image codec's own reconstruction) and a subsample of y = x + noise."""
+    m, sd = reference_module(kind, seed)
+    wave = SY.synth_speech(0, 1.0)[None]
+    x = torch.cat(P.prepare_data(wave)[1], 0)
+    msg = torch.stack([SY.synth_image_binary(0), SY.synth_image_binary(1)])
+    with torch.no_grad(), shims.legacy_torch_spectral():
+        y, wm_pred = m.feature_extract(x, msg)
+    np.savez_compressed(os.path.join(OUT, "feature_extract.npz"), kind=kind, seed=seed, wm_pred=wm_pred.numpy(),
+                        y_s8=y.numpy()[:, :, ::8, ::8])
+    print("feature_extract.npz", tuple(y.shape), tuple(wm_pred.shape))
+
+
 def pipeline_fixture(kind, seed, attack):
     m, sd = reference_module(kind, seed)
     run = shims.reference_reconstruct_audio()
@@ -221,6 +235,9 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "train_frontend":
         train_frontend_fixture()
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "feature_extract":
+        feature_extract_fixture()
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "jitter_delete":
         jitter_delete_fixture()
         return
@@ -231,6 +248,7 @@ def main():
     modelA_train_fixture()
     model_fixture("stress", 0)
     model_fixture("reference", 0)
+    feature_extract_fixture()
     pipeline_fixture("stress", 0, "awgn-20")
     pipeline_fixture("stress", 0, "low_pass")
 

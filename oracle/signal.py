@@ -173,12 +173,16 @@ def jittering(x, jit_ratio=1000, indices=None, rng=None):
 
 
 def requantization(x):
-    """`uformerWM/audio_attack.py:85-96`: libsndfile PCM_U8 write + read.
-    PARITY UNPINNED (libsndfile is not in the reference tree nor installed): restated from
-    libsndfile's published float->u8 / u8->float conversion with clipping enabled:
-    v = lrint(clip(x,-1,1)*127) + 128 ; x' = (v - 128) / 128."""
-    v = np.rint(np.clip(x, -1.0, 1.0) * 127.0) + 128.0
-    return (v - 128.0) / 128.0
+    """`uformerWM/audio_attack.py:85-96`: `sf.write(..., subtype='PCM_U8')` + `sf.read`.
+    PARITY UNPINNED (neither python-soundfile nor libsndfile is in the reference tree or installed here):
+    restated from their sources - soundfile opens every file with SFC_SET_CLIPPING = TRUE, so libsndfile's
+    pcm.c converts with `f2uc_clip_array` / `d2uc_clip_array`: u = (lrint(x * 2^31) >> 24) + 128, saturating to
+    255 for x * 2^31 >= 2^31 - 1 and to 0 for x <= -1; the read (`uc2f_array`) is (u - 128) / 128.
+    Net effect: floor(x * 128) / 128 clipped to [-1, 127/128]."""
+    sv = np.asarray(x, np.float64) * 2147483648.0
+    q = np.floor_divide(np.rint(np.clip(sv, -2147483648.0, 2147483647.0)).astype(np.int64), 1 << 24) + 128
+    u = np.where(sv >= 2147483647.0, 255, np.where(sv <= -2147483648.0, 0, q))
+    return (u.astype(np.float64) - 128.0) / 128.0
 
 
 def resampling(x):

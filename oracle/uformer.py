@@ -256,6 +256,13 @@ def embed(sd, x, message, taps=None):
     return y, noise, torch.sigmoid(wm_pred_logits), wm_pred_logits
 
 
+def feature_extract(sd, x, message):
+    """`UformerAudio.feature_extract` `uformerWM/model.py:2345-2377`: (y, wm_pred) with wm_pred the image codec's own
+    reconstruction `ConvAutoencoder.forward` `:1733-1748` (no bottleneck term, unlike `forward`)."""
+    y, _, _, _ = embed(sd, x, message)
+    return y, torch.sigmoid(wm_decode_logits(sd, wm_encode(sd, message)))
+
+
 def forward(sd, x, message, taps=None, return_logits=False):
     """`UformerAudio.forward` `uformerWM/model.py:2384-2511` -> (stft_new, noise, wm_pred, wm)."""
     y, noise, wm_pred, _ = embed(sd, x, message, taps)

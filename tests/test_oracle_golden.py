@@ -23,6 +23,19 @@ def test_model_forward_matches_reference(golden, weights):
             np.testing.assert_allclose(got.numpy(), g[ref], rtol=0, atol=2e-5, err_msg=kind + ":" + ref)
 
 
+def test_feature_extract_matches_reference(golden, weights):
+    """oracle `feature_extract` vs the unmodified reference (`uformerWM/model.py:2345-2377`): wm_pred is the image
+    codec's own reconstruction, not forward()'s bottleneck-added one."""
+    g = golden("feature_extract.npz")
+    m = golden("model_%s.npz" % str(g["kind"]))
+    sd = weights(str(g["kind"]), int(g["seed"]))
+    with torch.no_grad():
+        y, wp = O.feature_extract(sd, _t(m["x"]), _t(m["msg"]))
+    np.testing.assert_allclose(wp.numpy(), g["wm_pred"], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(y.numpy()[:, :, ::8, ::8], g["y_s8"], rtol=0, atol=2e-5)
+    assert np.abs(g["wm_pred"] - m["wm_pred"]).max() > 1e-3        # the two wm_pred definitions really differ
+
+
 def test_signal_functions_match_reference(golden):
     g = golden("signal.npz")
     x = g["x"]
@@ -34,6 +47,17 @@ def test_signal_functions_match_reference(golden):
     assert abs(S.cal_snr(x, g["low_pass"]) - float(g["cal_snr"])) < 1e-9
     assert abs(S.signaltonoise(x) - float(g["signaltonoise"])) < 1e-9
     assert abs(S.SNR_singlech(x.astype(np.float64), g["low_pass"]) - float(g["snr_singlech"])) < 1e-9
+
+
+def test_requantization_restates_the_soundfile_clipping_path():
+    """PCM_U8 round trip as python-soundfile + libsndfile do it (SFC_SET_CLIPPING on: `f2uc_clip_array`):
+    floor(x * 128) / 128 saturating to [-1, 127/128].  PARITY UNPINNED: no soundfile here to generate a golden."""
+    x = np.array([0.0, 0.5, -0.5, 1.0, -1.0, 1.5, -1.5, 0.003, -0.003, 127.0 / 128, 0.999999, -0.999999, 1.0 / 256])
+    want = np.array([0.0, 0.5, -0.5, 127.0 / 128, -1.0, 127.0 / 128, -1.0, 0.0, -1.0 / 128, 127.0 / 128, 127.0 / 128,
+                     -1.0, 0.0])
+    np.testing.assert_array_equal(S.requantization(x), want)
+    r = np.random.default_rng(0).uniform(-0.9, 0.9, 10000)
+    np.testing.assert_array_equal(S.requantization(r), np.floor(r * 128.0) / 128.0)
 
 
 def test_jitter_delete_matches_reference(golden):
