@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Benchmark of the embed -> attack -> extract hot path (BASELINE.json metric: audio-seconds/s).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision bf16|fp32]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision mixed|bf16|fp32]
+                    [--config 2|3|4|5]
 
 One "step" = one pass of the hot path over one batch of synthetic utterances:
 STFT -> UformerAudio.forward (embed + in-model ISTFT/STFT projection + clean extract) -> ISTFT ->
@@ -41,6 +42,11 @@ def parse():
     ap.add_argument("--utterances", type=int, default=B_UTT)
     ap.add_argument("--chunk", type=int, default=0, help="clips per internal pass (0 = the whole batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5],
+                    help="BASELINE.json configs, 1-based: 2 = the headline workload (default; its line also carries short runs of "
+                         "the others under `other_configs`), 3 = HiDDeN magnitudes pipeline, 4 = 64x64 image in 10 s utterances, "
+                         "fixed batch sharded over the GPUs (strong scaling), 5 = ModelA training step")
+    ap.add_argument("--no-other-configs", action="store_true")
     return ap.parse_args()
 
 
@@ -174,24 +180,232 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- our arm
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
+class Ctx:
+    """ranks, device, barrier + max-over-ranks timing shared by every workload."""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+
+    def sync(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, *vals):
+        t = self.torch.tensor(list(vals), device=self.dev, dtype=self.torch.float64)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(v) for v in t]
+
+    def timed(self, fn, steps, warmup, nvtx=None):
+        """warm-up, barrier + synchronize, K steps between CUDA events on the launching stream, barrier +
+        synchronize; returns (ms per step as the max over ranks, launches per step, last result)."""
+        from image_in_speech_watermarking_b200 import _lib
+        torch = self.torch
+        lib = _lib.load()
+        out = None
+        for _ in range(max(warmup, 3)):
+            out = fn()
+        self.sync()
+        l0 = lib.wmk_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            if nvtx:
+                torch.cuda.nvtx.range_push(nvtx)
+            out = fn()
+            if nvtx:
+                torch.cuda.nvtx.range_pop()
+        e1.record()
+        self.sync()
+        launches = (lib.wmk_launch_count() - l0) // steps
+        return self.max_over_ranks(e0.elapsed_time(e1) / steps)[0], int(launches), out
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def peaks():
+    pk = {}
+    try:
+        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    src = "MEASURED_PEAKS.json (sustained figures: kernels timed inside a long step)" if pk \
+        else "fallback 1.4 PFLOP/s / 6.55 TB/s (B200_PROFILING.md)"
+    return pk.get("bf16_tflops_sustained", 1400.0), pk.get("hbm_gbs", 6550.0), src
+
+
+def base_line(ctx, metric, unit, value, ms, steps, warmup, scaling, dtype, cfg, launches):
+    return {"metric": metric, "value": value, "unit": unit, "n_gpus": ctx.world, "steps": steps, "warmup": max(warmup, 3),
+            "ms_per_step": ms, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": dtype,
+            "data": "synthetic", "config": cfg, "gpu_launches": launches}
+
+
+# ---- BASELINE configs[2]: HiDDeN decoder + noise layers on STFT magnitudes, 128 x 2 s per GPU (weak scaling)
+def bench_config3(ctx, steps, warmup, utterances=128):
+    import numpy as np
+    torch = ctx.torch
+    from image_in_speech_watermarking_b200 import synthetic as SY, sharding as SH
+    from image_in_speech_watermarking_b200.hidden import noise_layers as NL, audio_test as HT, noise_argparser as NA
+    from image_in_speech_watermarking_b200.hidden.model.decoder import Decoder
+    from image_in_speech_watermarking_b200.hidden.options import HiDDenConfiguration
+    cfg = HiDDenConfiguration(H=128, W=128, message_length=30, encoder_blocks=4, encoder_channels=64, decoder_blocks=7,
+                              decoder_channels=64, use_discriminator=True, use_vgg=False, discriminator_blocks=3,
+                              discriminator_channels=64, decoder_loss=1, encoder_loss=0.7, adversarial_loss=1e-3)
+    torch.manual_seed(0)
+    d = Decoder(cfg, precision="bf16").cuda().eval()
+    B = utterances
+    host_w = SY.synth_speech_batch(ctx.rank * 4, 4, 2.0).repeat((B + 3) // 4, 1)[:B].contiguous().pin_memory()
+    host_m = torch.stack([SY.synth_image_binary(ctx.rank * B + i) for i in range(B)]).pin_memory()
+    waves, msgs = host_w.to(ctx.dev), host_m.to(ctx.dev)
+    np.random.seed(ctx.rank)
+    noise = "cropout((0.25,0.35),(0.25,0.35))+dropout(0.25,0.35)+quant()"       # geometry-preserving layers of hidden/runfiles/combined-noise.sh
+    noiser = NL.Noiser(NA.parse_noise(noise), ctx.dev)
+
+    def step(w=waves, m=msgs):
+        dec, st = HT.attack_and_decode(w, m, d, noiser)
+        vec = torch.stack([st[:, 0].sum(), st[:, 1].sum(), torch.tensor(float(st.shape[0] * 1024), device=ctx.dev, dtype=torch.float64)])
+        return SH.allreduce_stats(vec), dec
+
+    ms, launches, (vec, dec) = ctx.timed(step, steps, warmup)
+    host_dec = torch.empty(dec.shape, dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        vec, dec = step(host_w.to(ctx.dev, non_blocking=True), host_m.to(ctx.dev, non_blocking=True))
+        host_dec.copy_(dec, non_blocking=True)
+        return vec.cpu()
+
+    ms_e2e, _, _ = ctx.timed(e2e_step, steps, warmup)
+    clips = dec.shape[0] * ctx.world
+    total_audio = B * 2.0 * ctx.world
+    peak_tf, _, src = peaks()
+    line = base_line(ctx, "HiDDeN noise-layer + decode audio-seconds per second", "audio-s/s", total_audio / (ms * 1e-3), ms,
+                     steps, warmup, "weak", "bf16 (decoder 64->64 convs on tcgen05), fp32 elsewhere",
+                     {"workload": "BASELINE configs[2]: HiDDeN decoder (hidden/model) + one random noise layer per batch (%s) on STFT "
+                                  "magnitudes, %d x 2 s utterances per GPU = %d clips" % (noise, B, dec.shape[0]),
+                      "utterances_per_gpu": B, "seconds_per_utterance": 2.0}, launches)
+    line["e2e"] = {"value": total_audio / (ms_e2e * 1e-3), "unit": "audio-s/s", "ms_per_step": ms_e2e,
+                   "h2d_bytes_per_step": host_w.numel() * 4 + host_m.numel() * 4, "d2h_bytes_per_step": host_dec.numel() * 4 + 24}
+    tf = 7.84e9 * clips / (ms * 1e-3) / 1e12
+    line["roofline"] = {"bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf,
+                        "kernel": "gemm_tcgen05_persistent_kernel (implicit-GEMM conv)", "peak_source": src, "traffic": None,
+                        "definition": "7.84 GFLOP/clip decoder (BASELINE.md 3) x clips / whole-step time"}
+    line["stats"] = {"ber": float(vec[0] / vec[2])}
+    return line
+
+
+# ---- BASELINE configs[3]: 64x64 greyscale image in 10 s utterances, a FIXED batch of 64 sharded over the ranks
+def bench_config4(ctx, model, steps, warmup, utterances=64, seconds=10.0):
+    torch = ctx.torch
+    from image_in_speech_watermarking_b200 import synthetic as SY, audio_test as PT, sharding as SH
+    mine = SH.shard_range(utterances, ctx.rank, ctx.world)
+    B = len(mine)
+    host_w = torch.stack([SY.synth_speech(i, seconds) for i in mine]).pin_memory()
+    host_t = PT.tile_image(torch.stack([SY.synth_image_grey(i) for i in mine])).pin_memory()     # (B,4,1,32,32)
+    waves, tiles = host_w.to(ctx.dev), host_t.to(ctx.dev)
+    cnt = [0]
+
+    def step(w=waves, t=tiles, outputs=False):
+        cnt[0] += 1
+        r = PT.embed_attack_extract(w, t, model, ATTACK, seed=cnt[0], want_outputs=outputs)
+        vec = torch.cat([r["vec"], r["image_stats"].sum(0)])                             # + image bit errors, sum MSE, image bits
+        return SH.allreduce_stats(vec), r
+
+    ms, launches, (vec, r) = ctx.timed(step, steps, warmup)
+    host_att = torch.empty((B, host_w.shape[1]), dtype=torch.float32).pin_memory()
+    host_img = torch.empty((B, 4, 1, 32, 32), dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        vec, r = step(host_w.to(ctx.dev, non_blocking=True), host_t.to(ctx.dev, non_blocking=True), True)
+        host_att.copy_(r["att"], non_blocking=True)
+        host_img.copy_(r["image_att"], non_blocking=True)
+        return vec.cpu()
+
+    ms_e2e, _, _ = ctx.timed(e2e_step, steps, warmup)
+    total_audio = utterances * seconds
+    peak_tf, _, src = peaks()
+    n_clips = utterances * r["n_clips"]
+    tf = n_clips * (GFLOP_PER_CLIP_FWD + GFLOP_PER_CLIP_EXT) * 1e9 / (ms * 1e-3) / 1e12
+    line = base_line(ctx, "embed+attack+extract audio-seconds per second", "audio-s/s", total_audio / (ms * 1e-3), ms, steps, warmup,
+                     "strong", DTYPE[model.precision],
+                     {"workload": "BASELINE configs[3]: uformerWM, 64x64 greyscale image (four 32x32 tiles, tile j mod 4 in clip j) in "
+                                  "%d x %.0f s utterances (%d clips), attacks %s, the FIXED batch sharded by utterance over %d GPU(s), "
+                                  "NCCL all-reduce of the BER / SNR / image statistics" % (utterances, seconds, n_clips, ATTACK, ctx.world),
+                      "utterances_total": utterances, "utterances_per_gpu": B, "seconds_per_utterance": seconds,
+                      "clips_per_utterance": r["n_clips"], "precision": model.precision,
+                      "limiter": "per-GPU work shrinks as 1/N while the ~700 launches per pass stay: launch latency bounds the step "
+                                 "once a GPU holds < ~100 clips"}, launches)
+    line["e2e"] = {"value": total_audio / (ms_e2e * 1e-3), "unit": "audio-s/s", "ms_per_step": ms_e2e,
+                   "h2d_bytes_per_step": (host_w.numel() + host_t.numel()) * 4, "d2h_bytes_per_step": (host_att.numel() + host_img.numel()) * 4 + 88}
+    line["roofline"] = {"bound": "tensor", "achieved": tf, "peak": peak_tf * ctx.world, "unit": "TFLOP/s", "frac": tf / (peak_tf * ctx.world),
+                        "kernel": "gemm_tcgen05_persistent_kernel", "peak_source": src, "traffic": None,
+                        "definition": "64.19 GFLOP/clip (BASELINE.md 3) x clips / whole-step time, against N x the sustained bf16 peak"}
+    line["stats"] = {"ber_attacked_clips": float(vec[2] / vec[3]), "ber_image_64x64": float(vec[8] / vec[10]), "mean_snr_db": float(vec[4] / vec[7])}
+    return line
+
+
+# ---- BASELINE configs[4]: ModelA training step (embed + Gaussian attack + extract, fwd/bwd, Adam), 192 clips per GPU
+def bench_config5(ctx, steps, warmup, clips=192):
+    torch = ctx.torch
+    from image_in_speech_watermarking_b200.model import ModelA
+    from image_in_speech_watermarking_b200 import cnn_train as CT, train_modelA as TM
+    torch.manual_seed(0)
+    m = ModelA().cuda().train()
+    m.attack = TM.gaussian_attack(0.05)
+    opt = CT.FlatAdam(m.parameters(), lr=2e-4, weight_decay=0.02)
+    g = torch.Generator().manual_seed(ctx.rank)
+    host_x = torch.rand(clips, 2, 128, 128, generator=g).pin_memory()
+    host_wm = (torch.rand(clips, 1, 32, 32, generator=g) > 0.5).float().pin_memory()
+    x, wm = host_x.to(ctx.dev), host_wm.to(ctx.dev)
+    ms, launches, out = ctx.timed(lambda: TM.train_step(m, opt, x, wm), steps, warmup)
+
+    def e2e_step():
+        loss, _, _ = TM.train_step(m, opt, host_x.to(ctx.dev, non_blocking=True), host_wm.to(ctx.dev, non_blocking=True))
+        return loss.cpu()
+
+    ms_e2e, _, _ = ctx.timed(e2e_step, steps, warmup)
+    total = clips * ctx.world
+    _, peak_bw, src = peaks()
+    # algorithmic bytes of the step: ~13 MB of fp32 activations per clip forward (BASELINE.md 3), written once and read once in
+    # the forward, read again + gradient of the same size written and read in the backward: ~5 x 13 MB per clip
+    gbs = total * 5 * 13e6 / (ms * 1e-3) / 1e9
+    line = base_line(ctx, "ModelA training-step audio-seconds per second", "audio-s/s", total * 0.5 / (ms * 1e-3), ms, steps, warmup,
+                     "weak", "f32",
+                     {"workload": "BASELINE configs[4]: uformerWM train_modelA training step (embed + Gaussian attack + extract, "
+                                  "forward/backward, MSE losses, fused Adam), %d clips (= %d x 3 s utterances) per GPU, data parallel: "
+                                  "ONE NCCL all-reduce of the flat 17 655-float gradient per step; 8 GPUs = the named 256 x 3 s batch"
+                                  % (clips, clips // 6), "clips_per_gpu": clips, "global_batch_clips": total}, launches)
+    line["e2e"] = {"value": total * 0.5 / (ms_e2e * 1e-3), "unit": "audio-s/s", "ms_per_step": ms_e2e,
+                   "h2d_bytes_per_step": (host_x.numel() + host_wm.numel()) * 4, "d2h_bytes_per_step": 4}
+    line["roofline"] = {"bound": "hbm", "achieved": gbs, "peak": peak_bw * ctx.world, "unit": "GB/s", "frac": gbs / (peak_bw * ctx.world),
+                        "kernel": "conv3x3_kernel / conv3x3_wgrad_kernel / bn_train_*", "peak_source": src, "traffic": None,
+                        "definition": "5 x 13 MB of fp32 activation traffic per clip (forward write + read, backward read + gradient "
+                                      "write + read) / whole-step time"}
+    line["stats"] = {"loss": float(out[0]), "clips_per_s": total / (ms * 1e-3)}
+    return line
+
+
+# ---- BASELINE configs[1]: the headline workload
+def bench_config2(ctx, args):
+    torch = ctx.torch
     from image_in_speech_watermarking_b200 import _lib, synthetic as SY
     from image_in_speech_watermarking_b200.model import UformerAudio
     from image_in_speech_watermarking_b200 import audio_test as PT, sharding as SH
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    lib = _lib.load()
-
+    world, rank, dev = ctx.world, ctx.rank, ctx.dev
     B = args.utterances
     # all clips of the rank's batch in one pass (12 GEMM-sized passes of 32 clips would be launch bound)
     chunk = args.chunk or 6 * B
@@ -199,81 +413,53 @@ def run_ours(args):
     host_w = SY.synth_speech_batch(rank * B, B, SECONDS).pin_memory()
     host_m = torch.stack([SY.synth_image_binary(rank * B + i) for i in range(B)]).pin_memory()
     waves, msgs = host_w.to(dev), host_m.to(dev)
-    stats_sum = torch.zeros(8, device=dev, dtype=torch.float64)
+    cnt = [0]
 
-    def step(w, m):
-        r = PT.embed_attack_extract(w, m, model, ATTACK, seed=1, want_outputs=False)
+    def step(w=waves, m=msgs, outputs=False):
+        cnt[0] += 1                                   # a new device-RNG key per step (explicit: reproducible runs)
+        r = PT.embed_attack_extract(w, m, model, ATTACK, seed=cnt[0], want_outputs=outputs)
         # the path's only collective: one all-reduce of the BER / SNR statistics vector (NCCL)
-        return SH.allreduce_stats(SH.stats_vector(r["stats"]))
+        return SH.allreduce_stats(r["vec"]), r
 
-    def sync():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    sampler = ClockSampler(local)
-    for _ in range(max(args.warmup, 3)):
-        step(waves, msgs)
-    sync()
+    sampler = ClockSampler(ctx.local)
+    step()                                            # builds the plan, allocates the workspace
+    ctx.sync()
     if rank == 0:
-        sampler.start()
-    # ---- device-resident timing (value): K steps, CUDA events on the launching stream
-    l0 = lib.wmk_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        torch.cuda.nvtx.range_push("wmk_timed_step")     # ncu --nvtx --nvtx-include "wmk_timed_step/" (tools/profile_round.sh)
-        vec = step(waves, msgs)
-        torch.cuda.nvtx.range_pop()
-    e1.record()
-    sync()
-    launches = (lib.wmk_launch_count() - l0) // args.steps
-    ms = e0.elapsed_time(e1) / args.steps
+        sampler.start()                               # SM clock / throttle reasons sampled under load (warm-up + timed steps)
+    # ---- device-resident timing (value): W warm-up steps, then K steps between CUDA events on the launching stream
+    ms, launches, (vec, _) = ctx.timed(step, args.steps, args.warmup, nvtx="wmk_timed_step")   # ncu --nvtx-include "wmk_timed_step/"
     clocks = sampler.stop() if rank == 0 else None
     # ---- per-kernel-family durations: the same steps again with a CUDA-event pair around every
-    # launch (kept out of the timed region above: ~8k extra event records per step cost host time)
+    # launch (kept out of the timed region above: ~1.4k extra event records per step cost host time)
     _lib.profile_enable(True)
-    step(waves, msgs)
+    step()
     _lib.profile_collect()                       # first profiled step only fills the event pool
     p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     p0.record()
     for _ in range(args.steps):
-        step(waves, msgs)
+        step()
     p1.record()
-    sync()
+    ctx.sync()
     ms_profiled = p0.elapsed_time(p1) / args.steps
     fam = _lib.profile_collect()
     _lib.profile_enable(False)
-    # ---- end to end through the public API with host buffers
-    sync()
-    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
-    t0.record()
-    for _ in range(args.steps):
-        w = host_w.to(dev, non_blocking=True)
-        m = host_m.to(dev, non_blocking=True)
-        out = step(w, m).cpu()
-    t1.record()
-    sync()
-    ms_e2e = t0.elapsed_time(t1) / args.steps
-    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e = float(t[0]), float(t[1])
+    # ---- end to end through the public API with host buffers: waveforms + images in from pinned memory, the
+    # attacked audio, the recovered images and the statistics vector back to pinned memory, every step
+    nc_att = 6
+    host_att = torch.empty((B, host_w.shape[1]), dtype=torch.float32).pin_memory()
+    host_wm = torch.empty((B, nc_att, 1, 32, 32), dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        vec, r = step(host_w.to(dev, non_blocking=True), host_m.to(dev, non_blocking=True), True)
+        host_att.copy_(r["att"], non_blocking=True)            # the attacked audio (product output)
+        host_wm.copy_(r["wm_att"], non_blocking=True)          # the recovered images (product output)
+        return vec.cpu()                                       # BER / SNR statistics; synchronises the step
+
+    ms_e2e, _, _ = ctx.timed(e2e_step, args.steps, 3)
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        return None, model
     total_audio = B * SECONDS * world
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
-    peak_bw = peaks.get("hbm_gbs", 6550.0)
-    src = "MEASURED_PEAKS.json (sustained figures: kernels timed inside a long step)" if peaks \
-        else "fallback 1.4 PFLOP/s / 6.55 TB/s (B200_PROFILING.md)"
+    peak_tf, peak_bw, src = peaks()
     step_ms_families = {k: round(v["ms"] / args.steps, 3) for k, v in fam.items()}
     kname = "gemm_tcgen05_persistent_kernel" if args.precision != "fp32" else "gemm_fp32_kernel"
 
@@ -291,63 +477,102 @@ def run_ours(args):
                 "launches_per_step": f["launches"] // args.steps, "avg_launch_ms": f["ms"] / n,
                 "algorithmic_work_per_launch": f["work"] / n, "share_of_step": f["ms"] / args.steps / ms_profiled}
 
-    # The dense layers are ONE kernel template launched on ~45 shapes: launches whose arithmetic intensity is
-    # below the B200 ridge (214 FLOP/B: the C<=128 stages, K = 32..128) are HBM bound, the rest tensor bound
-    # (classified per launch in csrc/wmk_common.cuh gemm_work()).  `roofline` is the class with the larger
-    # share of the step; the other class is `roofline_other`.
-    r_hbm, r_tc = fam_roof("gemm_hbm", "hbm"), fam_roof("gemm", "tensor")
-    both = [r for r in (r_hbm, r_tc) if r]
-    both.sort(key=lambda r: -r["share_of_step"])
-    roofline = dict(both[0]) if both else {"bound": "tensor", "achieved": 0.0, "peak": peak_tf, "unit": "TFLOP/s", "frac": 0.0}
+    # `roofline` = the dense-layer kernel against the TENSOR roofline, as SURVEY 8(d) defines it: algorithmic FLOPs
+    # (2 M N K of every Linear / conv-as-GEMM launch; a split-bf16 product counts ONCE although it executes three
+    # MMAs) / the summed durations of its launches (CUDA events around every launch) vs the sustained bf16 peak.
+    # The per-launch intensity classes (below / above the 214 FLOP/B ridge) stay as diagnostics.
+    gm_ms = fam["gemm"]["ms"] + fam["gemm_hbm"]["ms"]
+    dense_flops = fam["gemm"]["work"] + fam["gemm_hbm"]["work2"]
+    n_dense = max(1, fam["gemm"]["launches"] + fam["gemm_hbm"]["launches"])
+    dense_tf = dense_flops / (gm_ms * 1e-3) / 1e12 if gm_ms > 0 else 0.0
+    step_flops = world * B * 6 * (GFLOP_PER_CLIP_FWD + GFLOP_PER_CLIP_EXT) * 1e9
     traffic, traffic_src = None, None
-    try:                # dram__bytes_read + dram__bytes_write per launch of the dense-layer kernel, from the committed ncu pass
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))      # regenerated by tools/make_profiles.py
-        traffic = tj["families"]["gemm"]["dram_bytes_per_launch"]
-        traffic_src = "profiles/r01_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean over the %d dense-layer " \
-                      "launches of one 64 x 3 s step, both roofline classes)" % tj["families"]["gemm"]["launches"]
-    except Exception:
-        pass
-    roofline.update({"kernel": kname, "peak_source": src, "traffic": traffic, "traffic_source": traffic_src,
-                     "family_ms_per_step": step_ms_families, "profiled_step_ms": ms_profiled})
-    if len(both) > 1:
-        roofline["roofline_other"] = both[1]
-    gm = fam["gemm"]["ms"] + fam["gemm_hbm"]["ms"]
-    if gm > 0:
-        roofline["all_dense_tflops"] = (fam["gemm"]["work"] + fam["gemm_hbm"]["work2"]) / (gm * 1e-3) / 1e12
-    for nm, key in (("stft", "stft"), ("istft", "istft")):
+    for name in ("r02_traffic.json", "r01_traffic.json"):   # dram__bytes_read + dram__bytes_write per dense-layer launch (ncu --set full)
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", name)))      # regenerated by tools/make_profiles.py
+            traffic = tj["families"]["gemm"]["dram_bytes_per_launch"]
+            traffic_src = "profiles/%s (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean over the %d dense-layer " \
+                          "launches of one 64 x 3 s step)" % (name, tj["families"]["gemm"]["launches"])
+            break
+        except Exception:
+            pass
+    roofline = {"bound": "tensor", "kernel": kname, "achieved": dense_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": dense_tf / peak_tf, "tensor_frac_dense": dense_tf / peak_tf,
+                "tensor_frac_step": step_flops / world / (ms * 1e-3) / 1e12 / peak_tf,
+                "definition": "frac = algorithmic dense FLOPs / summed dense-kernel launch time / sustained bf16 peak (SURVEY 8d); "
+                              "tensor_frac_step = 64.19 GFLOP/clip x clips / whole-step time / peak",
+                "launches_per_step": n_dense // args.steps, "avg_launch_ms": gm_ms / n_dense,
+                "algorithmic_work_per_launch": dense_flops / n_dense, "share_of_step": gm_ms / args.steps / ms_profiled,
+                "peak_source": src, "traffic": traffic, "traffic_source": traffic_src,
+                "family_ms_per_step": step_ms_families, "profiled_step_ms": ms_profiled,
+                "hbm_class": fam_roof("gemm_hbm", "hbm"), "tensor_class": fam_roof("gemm", "tensor")}
+    for nm in ("stft", "istft"):
         st = fam[nm]
         if st["ms"] > 0:
-            roofline[key + "_gbs"] = st["work"] / (st["ms"] * 1e-3) / 1e9
-            roofline[key + "_frac_of_hbm"] = roofline[key + "_gbs"] / peak_bw
-    line = {"metric": "embed+attack+extract audio-seconds per second", "value": total_audio / (ms * 1e-3),
-            "unit": "audio-s/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": DTYPE[args.precision], "data": "synthetic", "config": config(args),
-            "e2e": {"value": total_audio / (ms_e2e * 1e-3), "unit": "audio-s/s",
-                    "h2d_bytes_per_step": host_w.numel() * 4 + host_m.numel() * 4, "d2h_bytes_per_step": 8 * 8,
-                    "ms_per_step": ms_e2e},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
-            "stats": {"ber_clean": float(vec[0] / vec[1]), "ber_attacked": float(vec[2] / vec[3]),
-                      "mean_snr_db": float(vec[4] / vec[7])}}
-    if world == 1 and not args.no_cpu_baseline:
-        # BASELINE metric "STFT GB/s vs HBM peak": the front-end kernels on their own at a size that fills the GPU
-        # (2048 x 3 s; the launches inside the step above cover 64 utterances in ~20 us and are latency dominated)
-        try:
-            sys.path.insert(0, os.path.join(ROOT, "tools"))
-            import stft_bench
-            torch.cuda.synchronize()
-            time.sleep(2.0)        # a kernel timed alone: let the board leave the power-capped state of the step loop
-            sb = stft_bench.measure(2048, SECONDS, 20)
-            line["stft_standalone"] = {k: {"gbs": v["gbs"], "frac_of_hbm": v["gbs"] / peak_bw, "ms": v["ms"]} for k, v in sb.items()}
-            line["stft_standalone"]["workload"] = "2048 x 3 s; algorithmic bytes 1276 B/frame (n_fft 255, hop 63), 1536 B/frame (stft256)"
-        except Exception as e:                       # never lose the bench line over the side measurement
-            line["stft_standalone"] = {"error": str(e)}
-        line["cpu_baseline"] = cpu_baseline()
+            roofline[nm + "_gbs"] = st["work"] / (st["ms"] * 1e-3) / 1e9
+            roofline[nm + "_frac_of_hbm"] = roofline[nm + "_gbs"] / peak_bw
+    line = base_line(ctx, "embed+attack+extract audio-seconds per second", "audio-s/s", total_audio / (ms * 1e-3), ms, args.steps,
+                     args.warmup, "weak", DTYPE[args.precision], config(args), launches)
+    line["e2e"] = {"value": total_audio / (ms_e2e * 1e-3), "unit": "audio-s/s",
+                   "h2d_bytes_per_step": host_w.numel() * 4 + host_m.numel() * 4,
+                   "d2h_bytes_per_step": host_att.numel() * 4 + host_wm.numel() * 4 + 8 * 8, "ms_per_step": ms_e2e,
+                   "d2h": "attacked audio (B x L fp32) + recovered images (B x 6 x 32 x 32 fp32) + the 8-double statistics vector"}
+    line.update({"clocks": clocks, "roofline": roofline,
+                 "stats": {"ber_clean": float(vec[0] / vec[1]), "ber_attacked": float(vec[2] / vec[3]),
+                           "mean_snr_db": float(vec[4] / vec[7])}})
+    return line, model
+
+
+def run_ours(args):
+    ctx = Ctx()
+    torch = ctx.torch
+    if args.config == 3:
+        line = bench_config3(ctx, args.steps, args.warmup, args.utterances if args.utterances != B_UTT else 128)
+    elif args.config == 5:
+        line = bench_config5(ctx, args.steps, args.warmup)
+    elif args.config == 4:
+        from image_in_speech_watermarking_b200.model import UformerAudio
+        model = UformerAudio(precision=args.precision, clips_per_pass=args.chunk or 384).cuda().eval()
+        line = bench_config4(ctx, model, args.steps, args.warmup)
     else:
-        line["cpu_baseline"] = None
-    print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+        line, model = bench_config2(ctx, args)
+        if not args.no_other_configs:
+            # the other BASELINE configs, short runs in the same process (every rank takes part: configs 4 / 5 hold collectives)
+            others = {}
+            for name, fn in (("configs[3] 64x64 image, 10 s, fixed batch sharded (strong scaling)", lambda: bench_config4(ctx, model, 3, 3)),
+                             ("configs[2] HiDDeN magnitudes pipeline", lambda: bench_config3(ctx, 5, 3)),
+                             ("configs[4] ModelA training step", lambda: bench_config5(ctx, 5, 3))):
+                try:
+                    o = fn()
+                    others[name] = {k: o[k] for k in ("metric", "value", "unit", "ms_per_step", "scaling", "dtype", "config", "e2e",
+                                                      "roofline", "gpu_launches", "stats", "steps", "warmup")}
+                except Exception as e:                   # never lose the headline line over a side measurement
+                    others[name] = {"error": "%s: %s" % (type(e).__name__, e)}
+                if name.startswith("configs[3]"):
+                    del model                        # frees the 25 GB activation workspace before the other workloads
+                    torch.cuda.empty_cache()
+            if line is not None:
+                line["other_configs"] = others
+    if ctx.rank == 0:
+        if args.config == 2 and ctx.world == 1 and not args.no_cpu_baseline:
+            _, peak_bw, _ = peaks()
+            # BASELINE metric "STFT GB/s vs HBM peak": the front-end kernels on their own at a size that fills the GPU
+            # (2048 x 3 s; the launches inside the step above cover 64 utterances in ~20 us and are latency dominated)
+            try:
+                sys.path.insert(0, os.path.join(ROOT, "tools"))
+                import stft_bench
+                torch.cuda.synchronize()
+                time.sleep(2.0)        # a kernel timed alone: let the board leave the power-capped state of the step loop
+                sb = stft_bench.measure(2048, SECONDS, 20)
+                line["stft_standalone"] = {k: {"gbs": v["gbs"], "frac_of_hbm": v["gbs"] / peak_bw, "ms": v["ms"]} for k, v in sb.items()}
+                line["stft_standalone"]["workload"] = "2048 x 3 s; algorithmic bytes 1276 B/frame (n_fft 255, hop 63), 1536 B/frame (stft256)"
+            except Exception as e:                       # never lose the bench line over the side measurement
+                line["stft_standalone"] = {"error": str(e)}
+            line["cpu_baseline"] = cpu_baseline()
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line))
+    ctx.close()
 
 
 if __name__ == "__main__":

@@ -36,6 +36,8 @@ SIGNATURES = {
     "wmk_attack_resample2_f32": (_i, [_vp, _vp, _i, _i, _dp, _i, _vp]),
     "wmk_wave_stats_f64": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "wmk_wm_stats_f64": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
+    "wmk_wm_stats_mapped_f64": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _vp, _vp]),
+    "wmk_stats_finalize_f64": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "wmk_conv3x3_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp]),
     "wmk_convT2x2_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp]),
     "wmk_maxpool2x2_f32": (_i, [_vp, _vp, _i, _i, _i, _vp]),
@@ -67,6 +69,7 @@ SIGNATURES = {
     "wmk_plan_set_chunk": (_i, [_vp, _i]),
     "wmk_plan_workspace_bytes": (_sz, [_vp]),
     "wmk_uformer_forward": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "wmk_uformer_forward_mapped": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "wmk_uformer_extract": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
     "wmk_uformer_autoencode": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "wmk_plan_enable_taps": (_i, [_vp, _i]),

@@ -192,7 +192,8 @@ def embed_attack_extract(waves, messages, model, attack="closed_loop", draws=Non
       recon (B,L) watermarked audio, att (B,L) attacked audio, wm (B,nc,1,32,32) clean extraction,
       wm_att (B,nc_att,1,32,32), logits / logits_att, stats: per-utterance float64 columns
       [snr_db(orig,att), audio_mse(orig,recon), wm_mse_clean(last clip), wm_mse_att(mean over clips),
-       bit_err_clean(last clip), bit_err_att(sum), n_bits_att]."""
+       bit_err_clean(last clip), bit_err_att(sum), n_bits_att];
+      vec: the additive float64 8-vector of `sharding.STAT_KEYS` for this batch (what the ranks all-reduce)."""
     waves = waves.float().contiguous()
     B, L = waves.shape
     T = FE.num_frames(L)
@@ -203,21 +204,26 @@ def embed_attack_extract(waves, messages, model, attack="closed_loop", draws=Non
     if tiled:
         tiles = messages.float()
         K = tiles.shape[1]
-
-        def msg_for(n):                                        # (B, n, 1, 32, 32): tile j mod K in clip j
-            return tiles[:, torch.arange(n, device=tiles.device) % K]
-        msg = None
-        msg_b = msg_for(nc)[:, -1]                             # what the last clip carries (quirk B-8)
-        msg_clips = msg_for(nc).reshape(B * nc, 1, 32, 32).contiguous()
+        msgs = tiles.reshape(B * K, 1, 32, 32).contiguous()
     else:
-        msg = messages.float().reshape(-1, 1, 32, 32)
-        msg_b = msg if msg.shape[0] == B else msg.expand(B, 1, 32, 32)
+        K = 1
+        msgs = messages.float().reshape(-1, 1, 32, 32).contiguous()
+    # clip -> image rule of the reference driver (`audio_test.py:546-553`, every clip of an utterance carries the
+    # utterance's image; tiles: clip j carries tile j mod K) as index arithmetic inside the kernels:
+    # image of clip c = (c // clips_per_utt) * K + (c % clips_per_utt) % K; one image for the whole batch: cpu = "infinity"
+    one_for_all = msgs.shape[0] == K and B > 1
+    big = 0x7fffffff
 
-        def msg_for(n):
-            return msg_b[:, None].expand(B, n, 1, 32, 32)
-        msg_clips = msg_for(nc).reshape(B * nc, 1, 32, 32).contiguous()
-    audio_clips, wm_clean, lg_clean = _model_embed(model, clips.reshape(B * nc, 2, 128, 128),
-                                                   msg_clips if (tiled or msg.shape[0] == B) else msg, model_name)
+    def cpu_of(n):
+        return big if one_for_all else n
+    x = clips.reshape(B * nc, 2, 128, 128)
+    if model_name == 'uformer':
+        o = model.run(x, msgs, want=("stft_new", "wm", "wm_logits"), msg_map=(cpu_of(nc), K))
+        audio_clips, wm_clean, lg_clean = o["stft_new"], o["wm"], o["wm_logits"]
+    else:
+        idx = (torch.arange(B * nc, device=msgs.device) // nc) * K + (torch.arange(B * nc, device=msgs.device) % nc) % K
+        audio_clips, wm_clean, lg_clean = _model_embed(model, x, msgs[idx % msgs.shape[0]] if not one_for_all else msgs[:1],
+                                                       model_name)
     audio_clips = affine(audio_clips, 1.0 / sc, -sh / sc)                             # back to the audio range, :559-571
     recon = FE.istft_clips(audio_clips.reshape(B, nc, 2, 128, 128), T, L)             # audio_test.py:595-600
     att = AT.apply_attack(recon, attack, draws, seed)                                 # :631-660
@@ -229,18 +235,14 @@ def embed_attack_extract(waves, messages, model, attack="closed_loop", draws=Non
         wm_att, lg_att = model.wm_decode(clips_att.reshape(B * nc_att, 2, 128, 128), return_logits=True)
     else:
         wm_att, lg_att = model.decode(clips_att.reshape(B * nc_att, 2, 128, 128)), None
-    wm = wm_clean.reshape(B, nc, 1, 32, 32)
-    wm_att = wm_att.reshape(B, nc_att, 1, 32, 32)
     st_att = EV.wave_stats(waves, att)
     st_rec = EV.wave_stats(waves, recon)
-    ws_clean = EV.wm_stats(wm[:, -1], msg_b)                                          # quirk B-8
-    msg_att = msg_for(nc_att).reshape(B * nc_att, 1, 32, 32)
-    ws_att = EV.wm_stats(wm_att.reshape(B * nc_att, 1, 32, 32), msg_att).reshape(B, nc_att, 2)
-    stats = torch.stack([
-        EV.snr_from_stats(st_att), st_rec[:, 1] / st_rec[:, 5], ws_clean[:, 1] / 1024.0,
-        ws_att[:, :, 1].sum(1) / (1024.0 * nc_att), ws_clean[:, 0], ws_att[:, :, 0].sum(1),
-        torch.full((B,), 1024.0 * nc_att, device=waves.device, dtype=torch.float64)], dim=1)
-    out = {"stats": stats, "n_clips": nc, "n_clips_att": nc_att}
+    ws_clean = EV.wm_stats_mapped(wm_clean, nc - 1, nc, msgs, cpu_of(nc), K, B)       # last clean clip only: quirk B-8
+    ws_att = EV.wm_stats_mapped(wm_att, 0, 1, msgs, cpu_of(nc_att), K, B * nc_att)
+    stats, vec = EV.stats_finalize(st_att, st_rec, ws_clean, ws_att, nc_att)          # one launch; vec = sharding.STAT_KEYS
+    wm = wm_clean.reshape(B, nc, 1, 32, 32)
+    wm_att = wm_att.reshape(B, nc_att, 1, 32, 32)
+    out = {"stats": stats, "vec": vec, "n_clips": nc, "n_clips_att": nc_att}
     if tiled:
         # image-level recovery: average the sigmoids of the clips that carried each tile, then threshold
         rec = recover_tiled(wm_att, K)

@@ -295,6 +295,59 @@ wm_stats_kernel(const float* __restrict__ wm, const float* __restrict__ msg, int
   block_atomic_add(se, stats + r * 2 + 1);
 }
 
+// image i of the launch is clip c = first + i * step of the batch: its sigmoid output is wm[c], its message
+// msg[msg_index(mm, c)] - no expanded / gathered message copies (audio_test.py:625,712)
+__global__ void __launch_bounds__(256)
+wm_stats_mapped_kernel(const float* __restrict__ wm, int first, int step, const float* __restrict__ msg, MsgMap mm,
+                       double* __restrict__ stats) {
+  const size_t r = blockIdx.x;
+  const int c = first + (int)r * step;
+  const float* w = wm + (size_t)c * 1024;
+  const float* m = msg + msg_index(mm, c) * 1024;
+  double err = 0, se = 0;
+  for (int i = threadIdx.x; i < 1024; i += 256) {
+    const float v = w[i], mv = m[i];
+    const float bit = fminf(fmaxf(rintf(v), 0.f), 1.f);
+    err += fabsf(bit - mv);
+    const double d = (double)v - (double)mv;
+    se += d * d;
+  }
+  block_atomic_add(err, stats + r * 2);
+  block_atomic_add(se, stats + r * 2 + 1);
+}
+
+// Per-utterance result columns + the additive 8-vector of one batch in ONE launch (what the driver assembled with a
+// dozen elementwise / reduction launches): evaluate.py:139-144 cal_snr, audio_test.py:618 audio MSE, :625 clean
+// watermark MSE of the LAST clip (quirk B-8), :712 mean attacked watermark MSE, hidden/test_model.py:60-64 bit errors.
+//   stats[b] = { snr_db(orig, att), mse(orig, recon), wm_mse_clean, wm_mse_att, bit_err_clean, bit_err_att, bits_att }
+//   vec      = { sum bit_err_clean, 1024 B, sum bit_err_att, sum bits_att, sum snr_db, sum mse, sum wm_mse_att, B }
+__global__ void __launch_bounds__(256)
+stats_finalize_kernel(const double* __restrict__ st_att, const double* __restrict__ st_rec, const double* __restrict__ ws_clean,
+                      const double* __restrict__ ws_att, int B, int nca, double* __restrict__ stats, double* __restrict__ vec) {
+  __shared__ double red[8][256];
+  double acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.0;
+  for (int b = threadIdx.x; b < B; b += 256) {
+    const double snr = 10.0 * log10(st_att[b * 6] / st_att[b * 6 + 1]);
+    const double mse = st_rec[b * 6 + 1] / st_rec[b * 6 + 5];
+    double be = 0.0, se = 0.0;
+    for (int j = 0; j < nca; ++j) { be += ws_att[((size_t)b * nca + j) * 2]; se += ws_att[((size_t)b * nca + j) * 2 + 1]; }
+    const double wmc = ws_clean[b * 2 + 1] / 1024.0, wma = se / (1024.0 * nca), bits = 1024.0 * nca;
+    double* s = stats + (size_t)b * 7;
+    s[0] = snr; s[1] = mse; s[2] = wmc; s[3] = wma; s[4] = ws_clean[b * 2]; s[5] = be; s[6] = bits;
+    acc[0] += ws_clean[b * 2]; acc[1] += 1024.0; acc[2] += be; acc[3] += bits; acc[4] += snr; acc[5] += mse; acc[6] += wma; acc[7] += 1.0;
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) red[k][threadIdx.x] = acc[k];
+  __syncthreads();
+  if (threadIdx.x < 8) {                       // fixed-order sum: the vector is bit-reproducible run to run
+    double t = 0.0;
+    for (int i = 0; i < 256; ++i) t += red[threadIdx.x][i];
+    vec[threadIdx.x] = t;
+  }
+}
+
 dim3 wave_grid(int L, int B, int per_thread = 4) { return dim3(cdiv(L, 256 * per_thread), B); }
 
 // Scratch buffers come from the stream-ordered pool; keep its memory across synchronisation points
@@ -451,6 +504,27 @@ extern "C" int wmk_wave_stats_f64(const float* orig, const float* test, int B, i
   WMK_CHECK_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 6 * B, st));
   wave_stats_kernel<<<wave_grid(L, B, 8), 256, 0, st>>>(orig, test, L, stats);
   WMK_CHECK_LAUNCH("wave_stats_kernel");
+  return 0;
+}
+
+extern "C" int wmk_wm_stats_mapped_f64(const float* wm, int first, int step, const float* msg, int clips_per_utt,
+                                       int msgs_per_utt, int n, double* stats, void* stream) {
+  WMK_REQUIRE(wm && msg && stats && n > 0 && first >= 0 && step > 0 && clips_per_utt > 0 && msgs_per_utt > 0,
+              "wm_stats_mapped: bad arguments");
+  ProfScope prof(FAM_STATS, 8.0 * 1024 * n, (cudaStream_t)stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  WMK_CHECK_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * n, st));
+  wm_stats_mapped_kernel<<<n, 256, 0, st>>>(wm, first, step, msg, MsgMap{clips_per_utt, msgs_per_utt}, stats);
+  WMK_CHECK_LAUNCH("wm_stats_mapped_kernel");
+  return 0;
+}
+
+extern "C" int wmk_stats_finalize_f64(const double* st_att, const double* st_rec, const double* ws_clean, const double* ws_att,
+                                      int B, int n_clips_att, double* stats, double* vec, void* stream) {
+  WMK_REQUIRE(st_att && st_rec && ws_clean && ws_att && stats && vec && B > 0 && n_clips_att > 0, "stats_finalize: bad arguments");
+  ProfScope prof(FAM_STATS, 8.0 * B * (12 + 2 + 2 * n_clips_att + 7), (cudaStream_t)stream);
+  stats_finalize_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(st_att, st_rec, ws_clean, ws_att, B, n_clips_att, stats, vec);
+  WMK_CHECK_LAUNCH("stats_finalize_kernel");
   return 0;
 }
 

@@ -187,15 +187,15 @@ conv3x3_nchw_kernel(const float* __restrict__ in, float* __restrict__ out, const
 }
 
 // ConvAutoencoder.encode (uformerWM/model.py:1720-1726): [1][32][32] -> [4][8][8]; one CTA per image.
-// msg_stride = 0 broadcasts one image to every clip.
+// The image of clip `clip0 + blockIdx.x` is msg[msg_index(mm, clip)] (wmk_common.cuh MsgMap).
 __global__ void __launch_bounds__(256)
-wm_encode_kernel(const float* __restrict__ msg, int msg_stride, float* __restrict__ feat,
+wm_encode_kernel(const float* __restrict__ msg, MsgMap mm, int clip0, float* __restrict__ feat,
                  const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
                  const float* __restrict__ b2) {
   __shared__ float img[34][34];
   __shared__ float hid[16][18][18];        // pooled conv1 output with a zero border
   __shared__ float sw1[16 * 9], sb1[16], sw2[4 * 16 * 9], sb2[4];
-  const float* m = msg + (size_t)blockIdx.x * msg_stride;
+  const float* m = msg + msg_index(mm, clip0 + (int)blockIdx.x) * 1024;
   const int tid = threadIdx.x;
   for (int i = tid; i < 34 * 34; i += 256) {
     const int r = i / 34 - 1, c = i % 34 - 1;

@@ -499,9 +499,9 @@ int run_extract_any(wmk_plan* P, const float* y, int n, float* wm, float* logits
 }
 
 template <typename OpT>
-int run_forward(wmk_plan* P, const float* x, const float* msg, int msg_stride, int n, float* stft_new, float* noise,
+int run_forward(wmk_plan* P, const float* x, const float* msg, MsgMap mm, int clip0, int n, float* stft_new, float* noise,
                 float* y_out, float* wm_pred, float* wm, float* wm_logits, cudaStream_t st) {
-  wm_encode_kernel<<<n, 256, 0, st>>>(msg, msg_stride, P->feat, P->codec_c1w, P->codec_c1b, P->codec_c2w, P->codec_c2b);
+  wm_encode_kernel<<<n, 256, 0, st>>>(msg, mm, clip0, P->feat, P->codec_c1w, P->codec_c1b, P->codec_c2w, P->codec_c2b);
   WMK_CHECK_LAUNCH("wm_encode_kernel");
   WMK_TRY(run_encoder<OpT>(P, P->enc, x, n, "enc", st));
   if (wm_pred) {
@@ -678,10 +678,9 @@ extern "C" int wmk_plan_finalize(wmk_plan* P) {
   return 0;
 }
 
-extern "C" int wmk_uformer_forward(wmk_plan* P, const float* x, const float* msg, int msg_stride, int B, float* stft_new,
-                                   float* noise, float* y, float* wm_pred, float* wm, float* wm_logits, void* stream) {
+static int forward_mapped(wmk_plan* P, const float* x, const float* msg, MsgMap mm, int B, float* stft_new, float* noise,
+                          float* y, float* wm_pred, float* wm, float* wm_logits, void* stream) {
   WMK_TRY(check_ready(P));
-  WMK_REQUIRE(x && msg && B > 0 && (msg_stride == 0 || msg_stride == 1024), "forward: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
   for (int b0 = 0; b0 < B; b0 += P->chunk) {
     const int n = B - b0 < P->chunk ? B - b0 : P->chunk;
@@ -689,15 +688,28 @@ extern "C" int wmk_uformer_forward(wmk_plan* P, const float* x, const float* msg
     auto off = [&](float* p, size_t per) { return p ? p + o * per : nullptr; };
     int s;
     if (P->embed_mode() == 1)
-      s = run_forward<__nv_bfloat16>(P, x + o * 32768, msg + o * msg_stride, msg_stride, n, off(stft_new, 32768),
-                                     off(noise, 32768), off(y, 32768), off(wm_pred, 1024), off(wm, 1024),
-                                     off(wm_logits, 1024), st);
+      s = run_forward<__nv_bfloat16>(P, x + o * 32768, msg, mm, b0, n, off(stft_new, 32768), off(noise, 32768), off(y, 32768),
+                                     off(wm_pred, 1024), off(wm, 1024), off(wm_logits, 1024), st);
     else
-      s = run_forward<float>(P, x + o * 32768, msg + o * msg_stride, msg_stride, n, off(stft_new, 32768),
-                             off(noise, 32768), off(y, 32768), off(wm_pred, 1024), off(wm, 1024), off(wm_logits, 1024), st);
+      s = run_forward<float>(P, x + o * 32768, msg, mm, b0, n, off(stft_new, 32768), off(noise, 32768), off(y, 32768),
+                             off(wm_pred, 1024), off(wm, 1024), off(wm_logits, 1024), st);
     if (s) return s;
   }
   return 0;
+}
+
+extern "C" int wmk_uformer_forward(wmk_plan* P, const float* x, const float* msg, int msg_stride, int B, float* stft_new,
+                                   float* noise, float* y, float* wm_pred, float* wm, float* wm_logits, void* stream) {
+  WMK_REQUIRE(x && msg && B > 0 && (msg_stride == 0 || msg_stride == 1024), "forward: bad arguments");
+  const MsgMap mm = msg_stride == 0 ? MsgMap{0x7fffffff, 1} : MsgMap{1, 1};
+  return forward_mapped(P, x, msg, mm, B, stft_new, noise, y, wm_pred, wm, wm_logits, stream);
+}
+
+extern "C" int wmk_uformer_forward_mapped(wmk_plan* P, const float* x, const float* msg, int clips_per_utt, int msgs_per_utt,
+                                          int B, float* stft_new, float* noise, float* y, float* wm_pred, float* wm,
+                                          float* wm_logits, void* stream) {
+  WMK_REQUIRE(x && msg && B > 0 && clips_per_utt > 0 && msgs_per_utt > 0, "forward_mapped: bad arguments");
+  return forward_mapped(P, x, msg, MsgMap{clips_per_utt, msgs_per_utt}, B, stft_new, noise, y, wm_pred, wm, wm_logits, stream);
 }
 
 extern "C" int wmk_uformer_extract(wmk_plan* P, const float* y, int B, float* wm, float* wm_logits, void* stream) {
@@ -720,8 +732,8 @@ extern "C" int wmk_uformer_autoencode(wmk_plan* P, const float* msg, int msg_str
   cudaStream_t st = (cudaStream_t)stream;
   for (int b0 = 0; b0 < B; b0 += P->chunk) {
     const int n = B - b0 < P->chunk ? B - b0 : P->chunk;
-    wm_encode_kernel<<<n, 256, 0, st>>>(msg + (size_t)b0 * msg_stride, msg_stride, P->feat, P->codec_c1w, P->codec_c1b,
-                                        P->codec_c2w, P->codec_c2b);
+    wm_encode_kernel<<<n, 256, 0, st>>>(msg, msg_stride == 0 ? MsgMap{0x7fffffff, 1} : MsgMap{1, 1}, b0, P->feat, P->codec_c1w,
+                                        P->codec_c1b, P->codec_c2w, P->codec_c2b);
     WMK_CHECK_LAUNCH("wm_encode_kernel");
     wm_decode_kernel<<<n, 256, 0, st>>>(P->feat, nullptr, wm_pred + (size_t)b0 * 1024, nullptr, P->codec_t1w, P->codec_t1b,
                                         P->codec_t2w, P->codec_t2b);

@@ -224,6 +224,15 @@ __device__ __forceinline__ void split_store4(__nv_bfloat16* row, int c, int K, f
   *reinterpret_cast<uint2*>(row + K + c) = l;
 }
 
+// Which message image a clip carries: clip c of the batch belongs to utterance c / cpu and carries that utterance's
+// image (c % cpu) % mpu.  mpu = 1: one 32x32 image per utterance; mpu = 4: a 64x64 image as four tiles, tile j mod 4
+// in clip j; cpu = 1: one image per clip; cpu >= the batch: one image for every clip.
+struct MsgMap { int cpu, mpu; };
+__host__ __device__ __forceinline__ size_t msg_index(MsgMap m, int clip) {
+  const int u = clip / m.cpu;
+  return (size_t)u * m.mpu + (clip - u * m.cpu) % m.mpu;
+}
+
 // Where element (m, n) of a GEMM result is stored.
 struct EpiParams {
   const float* bias;

@@ -35,6 +35,31 @@ def wm_stats(wm, msg):
     return st
 
 
+def wm_stats_mapped(wm, first, step, msg, clips_per_utt, msgs_per_utt, n):
+    """wm (N,1,32,32) sigmoid outputs of a batch of clips, msg (U * msgs_per_utt,1,32,32) the utterances' images:
+    row i = clip c = first + i * step against image (c // clips_per_utt) * msgs_per_utt + (c % clips_per_utt) %
+    msgs_per_utt -> (n, 2) float64 {bit errors, sum sq err}; no expanded message tensor."""
+    w = wm.float().contiguous().reshape(-1, 1024)
+    m = msg.float().contiguous().reshape(-1, 1024)
+    if first + (n - 1) * step >= w.shape[0]:
+        raise ValueError("clip selection runs past the %d clips" % w.shape[0])
+    st = torch.empty((n, 2), device=w.device, dtype=torch.float64)
+    _lib.check(_lib.load().wmk_wm_stats_mapped_f64(_lib.ptr(w), int(first), int(step), _lib.ptr(m), int(clips_per_utt),
+                                                   int(msgs_per_utt), int(n), _lib.ptr(st), _lib.stream_ptr()))
+    return st
+
+
+def stats_finalize(st_att, st_rec, ws_clean, ws_att, n_clips_att):
+    """One launch: per-utterance columns (B, 7) {snr_db, audio_mse, wm_mse_clean, wm_mse_att, bit_err_clean, bit_err_att,
+    bits_att} and the additive vector (8,) of `sharding.STAT_KEYS` (what the ranks all-reduce)."""
+    B = st_att.shape[0]
+    stats = torch.empty((B, 7), device=st_att.device, dtype=torch.float64)
+    vec = torch.empty(8, device=st_att.device, dtype=torch.float64)
+    _lib.check(_lib.load().wmk_stats_finalize_f64(_lib.ptr(st_att), _lib.ptr(st_rec), _lib.ptr(ws_clean), _lib.ptr(ws_att), B,
+                                                  int(n_clips_att), _lib.ptr(stats), _lib.ptr(vec), _lib.stream_ptr()))
+    return stats, vec
+
+
 def snr_from_stats(st):
     """`cal_snr` (`uformerWM/evaluate.py:139-144`) per utterance from wave_stats."""
     return 10.0 * torch.log10(st[:, 0] / st[:, 1])

@@ -181,8 +181,11 @@ class UformerAudio(nn.Module):
             raise _lib.WmkError("UformerAudio has no CPU path: inputs must be CUDA tensors")
         return x.detach().contiguous().float()
 
-    def run(self, x, message, want=("stft_new", "noise", "wm_pred", "wm")):
-        """One fused pass; returns a dict with the requested outputs (+ 'y', 'wm_logits')."""
+    def run(self, x, message, want=("stft_new", "noise", "wm_pred", "wm"), msg_map=None):
+        """One fused pass; returns a dict with the requested outputs (+ 'y', 'wm_logits').
+        msg_map = (clips_per_utt, msgs_per_utt): `message` holds the utterances' images ((U * msgs_per_utt, 1, 32, 32))
+        and clip c carries image (c // clips_per_utt) * msgs_per_utt + (c % clips_per_utt) % msgs_per_utt - the
+        reference driver's rule (`audio_test.py:546-553`) without materialising a per-clip message tensor."""
         lib = _lib.load()
         x = self._prep(x)
         message = self._prep(message)
@@ -190,7 +193,11 @@ class UformerAudio(nn.Module):
         if x.shape[1:] != (2, 128, 128):
             raise ValueError("x must be (B,2,128,128), got %s" % (tuple(x.shape),))
         m = message.reshape(-1, 1024)
-        if m.shape[0] not in (1, B):
+        if msg_map is not None:
+            cpu, mpu = int(msg_map[0]), int(msg_map[1])
+            if cpu < 1 or mpu < 1 or m.shape[0] < ((B - 1) // cpu + 1) * mpu:
+                raise ValueError("msg_map %r needs %d images, got %d" % (msg_map, ((B - 1) // max(cpu, 1) + 1) * mpu, m.shape[0]))
+        elif m.shape[0] not in (1, B):
             raise ValueError("message batch %d does not match %d clips" % (m.shape[0], B))
         stride = 0 if m.shape[0] == 1 and B > 1 else 1024
         o = {}
@@ -200,10 +207,12 @@ class UformerAudio(nn.Module):
         if o["y"] is None:
             o["y"] = torch.empty((B, 2, 128, 128), device=x.device, dtype=torch.float32)
         with torch.cuda.device(x.device):
-            _lib.check(lib.wmk_uformer_forward(self.plan(), _lib.ptr(x), _lib.ptr(m), stride, B,
-                                               _lib.ptr(o["stft_new"]), _lib.ptr(o["noise"]), _lib.ptr(o["y"]),
-                                               _lib.ptr(o["wm_pred"]), _lib.ptr(o["wm"]), _lib.ptr(o["wm_logits"]),
-                                               _lib.stream_ptr()))
+            outs = (_lib.ptr(o["stft_new"]), _lib.ptr(o["noise"]), _lib.ptr(o["y"]), _lib.ptr(o["wm_pred"]), _lib.ptr(o["wm"]),
+                    _lib.ptr(o["wm_logits"]), _lib.stream_ptr())
+            if msg_map is not None:
+                _lib.check(lib.wmk_uformer_forward_mapped(self.plan(), _lib.ptr(x), _lib.ptr(m), cpu, mpu, B, *outs))
+            else:
+                _lib.check(lib.wmk_uformer_forward(self.plan(), _lib.ptr(x), _lib.ptr(m), stride, B, *outs))
         return o
 
     def forward(self, x, message, mask=None):

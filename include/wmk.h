@@ -147,6 +147,22 @@ int wmk_wave_stats_f64(const float* orig, const float* test, int B, int L, doubl
 /* wm [n][1024] sigmoid outputs, msg [n or 1][1024] -> stats [n][2] (float64) =
  * { bit errors = sum |clip(rint(wm),0,1) - msg| , sum (wm - msg)^2 }.  msg_stride = 0 broadcasts
  * one image, 1024 gives one image per row. */
+/* The same over a strided selection of clips with the clip -> message rule of wmk_uformer_forward_mapped: row i is
+ * clip c = first + i * step of the batch (wm[c], msg[(c / clips_per_utt) * msgs_per_utt + (c % clips_per_utt) %
+ * msgs_per_utt]); first = clips_per_utt - 1, step = clips_per_utt selects every utterance's LAST clip
+ * (audio_test.py:625). */
+int wmk_wm_stats_mapped_f64(const float* wm, int first, int step, const float* msg, int clips_per_utt,
+                            int msgs_per_utt, int n, double* stats, void* stream);
+/* The per-utterance result columns and the additive statistics vector of one batch in one launch
+ * (evaluate.py:139-144,285-291; audio_test.py:618,625,712; hidden/test_model.py:60-64):
+ *   st_att / st_rec [B][6]: wmk_wave_stats_f64(orig, attacked) / (orig, watermarked); ws_clean [B][2]: every
+ *   utterance's last clean clip; ws_att [B * n_clips_att][2];
+ *   stats [B][7] = { snr_db, audio_mse, wm_mse_clean, wm_mse_att, bit_err_clean, bit_err_att, bits_att };
+ *   vec [8] = { sum bit_err_clean, 1024 B, sum bit_err_att, sum bits_att, sum snr_db, sum audio_mse, sum wm_mse_att, B }
+ * - the vector the ranks all-reduce (NCCL) at the end of an evaluation. */
+int wmk_stats_finalize_f64(const double* st_att, const double* st_rec, const double* ws_clean,
+                           const double* ws_att, int B, int n_clips_att, double* stats, double* vec,
+                           void* stream);
 int wmk_wm_stats_f64(const float* wm, const float* msg, int n, int msg_stride, double* stats,
                      void* stream);
 
@@ -288,6 +304,13 @@ size_t wmk_plan_workspace_bytes(const wmk_plan* plan);
 int wmk_uformer_forward(wmk_plan* plan, const float* x, const float* msg, int msg_stride, int B,
                         float* stft_new, float* noise, float* y, float* wm_pred, float* wm,
                         float* wm_logits, void* stream);
+/* The same with the reference driver's clip -> message rule folded in (audio_test.py:546-553: every clip of an
+ * utterance carries the utterance's image): clip c of the batch reads msg[(c / clips_per_utt) * msgs_per_utt +
+ * (c % clips_per_utt) % msgs_per_utt][1024].  msgs_per_utt = 1: one 32x32 image per utterance; 4: a 64x64 image as
+ * four tiles, tile j mod 4 in clip j (BASELINE config 4).  No expanded message tensor is materialised. */
+int wmk_uformer_forward_mapped(wmk_plan* plan, const float* x, const float* msg, int clips_per_utt,
+                               int msgs_per_utt, int B, float* stft_new, float* noise, float* y, float* wm_pred,
+                               float* wm, float* wm_logits, void* stream);
 /* UformerAudio.wm_decode (model.py:2379-2382). */
 int wmk_uformer_extract(wmk_plan* plan, const float* y, int B, float* wm, float* wm_logits,
                         void* stream);

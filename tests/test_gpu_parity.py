@@ -419,6 +419,17 @@ def test_batched_pipeline_equals_per_utterance_and_oracle(models, weights):
     unit = torch.from_numpy(rng.standard_normal((B, 48000))).float()
     r = PT.embed_attack_extract(waves, msgs, m, "awgn-20+low_pass", {"awgn": unit})
     assert r["n_clips"] == 6 and r["n_clips_att"] == 6 and r["wm"].shape == (B, 6, 1, 32, 32)
+    from image_in_speech_watermarking_b200 import sharding as SH, evaluate as EV
+    assert torch.allclose(r["vec"], SH.stats_vector(r["stats"]), rtol=1e-12, atol=0)      # wmk_stats_finalize_f64's vector
+    # the mapped statistics kernels == the element-wise composition over expanded messages
+    ws = EV.wm_stats(r["wm_att"].reshape(B * 6, 1, 32, 32), msgs[:, None].expand(B, 6, 1, 32, 32).reshape(B * 6, 1, 32, 32))
+    assert torch.allclose(r["stats"][:, 5], ws[:, 0].reshape(B, 6).sum(1)) and \
+        torch.allclose(r["stats"][:, 3], ws[:, 1].reshape(B, 6).sum(1) / (1024.0 * 6), rtol=1e-12)
+    wc = EV.wm_stats(r["wm"][:, -1], msgs)
+    assert torch.allclose(r["stats"][:, 4], wc[:, 0]) and torch.allclose(r["stats"][:, 2], wc[:, 1] / 1024.0, rtol=1e-12)
+    one_msg = PT.embed_attack_extract(waves, msgs[:1], m, "awgn-20+low_pass", {"awgn": unit})       # one image for the whole batch
+    rep_msg = PT.embed_attack_extract(waves, msgs[:1].expand(B, 1, 32, 32).contiguous(), m, "awgn-20+low_pass", {"awgn": unit})
+    assert torch.equal(one_msg["stats"], rep_msg["stats"]) and torch.equal(one_msg["wm"], rep_msg["wm"])
     one = PT.embed_attack_extract(waves[1:2], msgs[1:2], m, "awgn-20+low_pass", {"awgn": unit[1:2]})
     assert torch.allclose(r["stats"][1], one["stats"][0], rtol=1e-9, atol=1e-12)
     ev = P.evaluate_utterance(waves[1:2].cpu(), msgs[1:2].cpu(), weights("stress"), "awgn-20+low_pass",
