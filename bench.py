@@ -27,8 +27,9 @@ sys.path.insert(0, ROOT)
 B_UTT, SECONDS, SR = 64, 3.0, 16000
 ATTACK = "awgn-20+low_pass"
 GFLOP_PER_CLIP_FWD, GFLOP_PER_CLIP_EXT = 53.76, 10.43
-DTYPE = {"mixed": "bf16 operands / fp32 accumulate (embedder); split-bf16 'bf16x3' = hi*hi+lo*hi+hi*lo / fp32 accumulate "
+DTYPE = {"mixed": "fp16 operands / fp32 accumulate (embedder); split-bf16 'bf16x3' = hi*hi+lo*hi+hi*lo / fp32 accumulate "
                   "(extractor: bit parity at |logit| >= 1e-4)",
+         "fp16": "fp16",
          "bf16": "bf16", "fp32": "f32"}
 
 
@@ -38,7 +39,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="mixed", choices=["mixed", "bf16", "fp32"])
+    ap.add_argument("--precision", default="mixed", choices=["mixed", "fp16", "bf16", "fp32"])
     ap.add_argument("--utterances", type=int, default=B_UTT)
     ap.add_argument("--chunk", type=int, default=0, help="clips per internal pass (0 = the whole batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -77,8 +77,8 @@ SIGNATURES = {
     "wmk_linear_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
 }
 
-PREC_FP32, PREC_BF16, PREC_MIXED = 0, 1, 2
-PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "mixed": PREC_MIXED}
+PREC_FP32, PREC_BF16, PREC_MIXED, PREC_F16 = 0, 1, 2, 3
+PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "mixed": PREC_MIXED, "fp16": PREC_F16}
 _lib = None
 
 

@@ -23,17 +23,13 @@ using namespace tc;
 constexpr int DW_TW = 8, DW_PW = DW_TW + 2;
 constexpr int kDwThreads = 128;
 
-__device__ __forceinline__ float2 bf2f(uint32_t u) {
-  return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
-}
-
 struct DwGeom {
   int H, Ch, ncs, tiles_w, tiles_h, n_items;
 };
 
-template <int TH>
+template <int TH, bool F16>
 __global__ void __launch_bounds__(kDwThreads, 4)
-dwconv3x3_gelu_tma_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict__ out,
+dwconv3x3_gelu_tma_kernel(const __grid_constant__ CUtensorMap tm, uint16_t* __restrict__ out,
                           const float* __restrict__ wt, const float* __restrict__ bias, DwGeom g) {
   constexpr int PH = TH + 2;
   constexpr uint32_t kPatchBytes = PH * DW_PW * 128;
@@ -98,13 +94,13 @@ dwconv3x3_gelu_tma_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16*
 #pragma unroll
       for (int dx = 0; dx < 3; ++dx) {
         const uint2 u = *reinterpret_cast<const uint2*>(pb + (r * DW_PW + dx) * 128);
-        dst[dx][0] = bf2f(u.x);
-        dst[dx][1] = bf2f(u.y);
+        dst[dx][0] = unpack2_16<F16>(u.x);
+        dst[dx][1] = unpack2_16<F16>(u.y);
       }
     };
     load_row(0, win[0]);
     load_row(1, win[1]);
-    __nv_bfloat16* op = out + (((size_t)b * g.H + h0) * g.H + w0 + col) * g.Ch + c;
+    uint16_t* op = out + (((size_t)b * g.H + h0) * g.H + w0 + col) * g.Ch + c;
 #pragma unroll
     for (int r = 0; r < TH; ++r) {
       load_row(r + 2, win[(r + 2) % 3]);
@@ -119,17 +115,16 @@ dwconv3x3_gelu_tma_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16*
       a0 = gelu_tanh2_half_arg(a0);
       a1 = gelu_tanh2_half_arg(a1);
       uint2 o;
-      o.x = pack_bf16x2(a0.x, a0.y);
-      o.y = pack_bf16x2(a1.x, a1.y);
+      o.x = pack2_16<F16>(a0.x, a0.y);
+      o.y = pack2_16<F16>(a1.x, a1.y);
       *reinterpret_cast<uint2*>(op + (size_t)r * g.H * g.Ch) = o;
     }
     __syncthreads();                                // everyone has drained this stage's patch
   }
 }
 
-template <int TH>
-int launch_dw(const __nv_bfloat16* in, __nv_bfloat16* out, const float* wt, const float* bias, int B, int H, int Ch,
-              cudaStream_t st) {
+template <int TH, bool F16>
+int launch_dw(const void* in, void* out, const float* wt, const float* bias, int B, int H, int Ch, cudaStream_t st) {
   CUtensorMap tm;
   const uint64_t dims[4] = {(uint64_t)Ch, (uint64_t)H, (uint64_t)H, (uint64_t)B};
   const uint64_t strides[3] = {(uint64_t)Ch * 2, (uint64_t)H * Ch * 2, (uint64_t)H * H * Ch * 2};
@@ -141,7 +136,7 @@ int launch_dw(const __nv_bfloat16* in, __nv_bfloat16* out, const float* wt, cons
   WMK_REQUIRE(items < (1LL << 31), "dwconv: too many tiles (%lld)", items);
   g.n_items = (int)items;
   const int grid = (int)(items < 4LL * num_sms() ? items : 4LL * num_sms());
-  dwconv3x3_gelu_tma_kernel<TH><<<grid, kDwThreads, 0, st>>>(tm, out, wt, bias, g);
+  dwconv3x3_gelu_tma_kernel<TH, F16><<<grid, kDwThreads, 0, st>>>(tm, reinterpret_cast<uint16_t*>(out), wt, bias, g);
   WMK_CHECK_LAUNCH("dwconv3x3_gelu_tma_kernel");
   return 0;
 }
@@ -153,8 +148,9 @@ struct DwGeom2 {
   int H, Ch, lg_ncs, lg_tw, lg_th, n_items;      // channel slabs, tiles per row / column: powers of two
 };
 
+template <bool F16>
 __global__ void __launch_bounds__(kDwThreads, 4)
-dwconv3x3_gelu_tma2_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict__ out,
+dwconv3x3_gelu_tma2_kernel(const __grid_constant__ CUtensorMap tm, uint16_t* __restrict__ out,
                            const float* __restrict__ wt, const float* __restrict__ bias, DwGeom2 g) {
   constexpr uint32_t kPatchBytes = DW2_PH * DW2_PW * 128;
   __shared__ __align__(128) uint8_t patch[2][kPatchBytes];
@@ -211,10 +207,10 @@ dwconv3x3_gelu_tma2_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16
     for (int s = 0; s < 3; ++s)
 #pragma unroll
       for (int q = 0; q < 2; ++q) { acc[s][q][0] = bz[0]; acc[s][q][1] = bz[1]; }
-    __nv_bfloat16* op = out + (((size_t)b * g.H + h0) * g.H + w0 + 2 * cp) * g.Ch + c;
+    uint16_t* op = out + (((size_t)b * g.H + h0) * g.H + w0 + 2 * cp) * g.Ch + c;
     mbar_wait(smem_u32(&bar[stage]), (it >> 1) & 1);
 
-    // patch[r][x][64 ch] bf16; this thread reads columns 2 cp .. 2 cp + 3, channels 4 cg .. 4 cg + 3
+    // patch[r][x][64 ch] 16-bit; this thread reads columns 2 cp .. 2 cp + 3, channels 4 cg .. 4 cg + 3
     const uint8_t* pb = patch[stage] + cp * 256 + cg * 8;
 #pragma unroll
     for (int i = 0; i < DW2_PH; ++i) {
@@ -222,8 +218,8 @@ dwconv3x3_gelu_tma2_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const uint2 u = *reinterpret_cast<const uint2*>(pb + (i * DW2_PW + j) * 128);
-        in[j][0] = bf2f(u.x);
-        in[j][1] = bf2f(u.y);
+        in[j][0] = unpack2_16<F16>(u.x);
+        in[j][1] = unpack2_16<F16>(u.y);
       }
       // input row i is tap row dy of output row i - dy (same tap order per output as the gather form)
 #pragma unroll
@@ -245,8 +241,8 @@ dwconv3x3_gelu_tma2_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16
           const float2 g0 = gelu_tanh2_half_arg(acc[o % 3][q][0]);
           const float2 g1 = gelu_tanh2_half_arg(acc[o % 3][q][1]);
           uint2 v;
-          v.x = pack_bf16x2(g0.x, g0.y);
-          v.y = pack_bf16x2(g1.x, g1.y);
+          v.x = pack2_16<F16>(g0.x, g0.y);
+          v.y = pack2_16<F16>(g1.x, g1.y);
           *reinterpret_cast<uint2*>(op + ((size_t)o * g.H + q) * g.Ch) = v;
           acc[o % 3][q][0] = bz[0];
           acc[o % 3][q][1] = bz[1];
@@ -257,8 +253,8 @@ dwconv3x3_gelu_tma2_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16
   }
 }
 
-int launch_dw2(const __nv_bfloat16* in, __nv_bfloat16* out, const float* wt, const float* bias, int B, int H, int Ch,
-               cudaStream_t st) {
+template <bool F16>
+int launch_dw2(const void* in, void* out, const float* wt, const float* bias, int B, int H, int Ch, cudaStream_t st) {
   CUtensorMap tm;
   const uint64_t dims[4] = {(uint64_t)Ch, (uint64_t)H, (uint64_t)H, (uint64_t)B};
   const uint64_t strides[3] = {(uint64_t)Ch * 2, (uint64_t)H * Ch * 2, (uint64_t)H * H * Ch * 2};
@@ -271,7 +267,7 @@ int launch_dw2(const __nv_bfloat16* in, __nv_bfloat16* out, const float* wt, con
   WMK_REQUIRE(items < (1LL << 31), "dwconv: too many tiles (%lld)", items);
   g.n_items = (int)items;
   const int grid = (int)(items < 4LL * num_sms() ? items : 4LL * num_sms());
-  dwconv3x3_gelu_tma2_kernel<<<grid, kDwThreads, 0, st>>>(tm, out, wt, bias, g);
+  dwconv3x3_gelu_tma2_kernel<F16><<<grid, kDwThreads, 0, st>>>(tm, reinterpret_cast<uint16_t*>(out), wt, bias, g);
   WMK_CHECK_LAUNCH("dwconv3x3_gelu_tma2_kernel");
   return 0;
 }
@@ -427,17 +423,22 @@ int dwconv3x3_gelu_split(const float* in, __nv_bfloat16* out, const float* wt, c
   return 0;
 }
 
-// in / out: [B][H][H][Ch] bf16 (token layout), wt_half: [9][Ch] fp32 tap-major, bias_half: [Ch] fp32 -
-// BOTH PRE-MULTIPLIED BY 0.5 (uformer_plan.cu pack_block), see gelu_tanh2_half_arg.
-int dwconv3x3_gelu_bf16(const __nv_bfloat16* in, __nv_bfloat16* out, const float* wt, const float* bias, int B, int H,
-                        int Ch, cudaStream_t st) {
+// in / out: [B][H][H][Ch] 16-bit (token layout; bf16, or fp16 when f16 != 0), wt_half: [9][Ch] fp32 tap-major,
+// bias_half: [Ch] fp32 - BOTH PRE-MULTIPLIED BY 0.5 (uformer_plan.cu pack_block), see gelu_tanh2_half_arg.
+int dwconv3x3_gelu_op16(const void* in, void* out, const float* wt, const float* bias, int B, int H, int Ch, int f16,
+                        cudaStream_t st) {
   WMK_REQUIRE(H >= 8 && (H & (H - 1)) == 0 && Ch >= 64 && (Ch & (Ch - 1)) == 0,
               "dwconv: H=%d must be a power of two >= 8 and Ch=%d a power of two >= 64", H, Ch);
   WMK_REQUIRE(((uintptr_t)in & 15) == 0 && ((uintptr_t)out & 15) == 0, "dwconv: buffers must be 16-byte aligned");
   static const int one_col = getenv("WMK_DW_ONECOL") ? atoi(getenv("WMK_DW_ONECOL")) : 0;
-  if (H % 16 == 0 && !one_col) return launch_dw2(in, out, wt, bias, B, H, Ch, st);
-  if (H % 16 == 0) return launch_dw<16>(in, out, wt, bias, B, H, Ch, st);
-  return launch_dw<8>(in, out, wt, bias, B, H, Ch, st);
+  if (f16) {
+    if (H % 16 == 0 && !one_col) return launch_dw2<true>(in, out, wt, bias, B, H, Ch, st);
+    if (H % 16 == 0) return launch_dw<16, true>(in, out, wt, bias, B, H, Ch, st);
+    return launch_dw<8, true>(in, out, wt, bias, B, H, Ch, st);
+  }
+  if (H % 16 == 0 && !one_col) return launch_dw2<false>(in, out, wt, bias, B, H, Ch, st);
+  if (H % 16 == 0) return launch_dw<16, false>(in, out, wt, bias, B, H, Ch, st);
+  return launch_dw<8, false>(in, out, wt, bias, B, H, Ch, st);
 }
 
 }  // namespace wmk

@@ -84,7 +84,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc(BN);
+      const uint32_t idesc = umma_idesc(BN, p.f16 != 0);
       for (int kb = 0; kb < kblocks; ++kb) {
         const int s = kb % n_stages;
         const uint32_t ph = (uint32_t)(kb / n_stages) & 1u;
@@ -140,18 +140,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
       }
       if (p.out_bf16) {
-        uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C) + off);
+        uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.C) + off);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          __nv_bfloat162 h0 = __floats2bfloat162_rn(f[8 * j], f[8 * j + 1]);
-          __nv_bfloat162 h1 = __floats2bfloat162_rn(f[8 * j + 2], f[8 * j + 3]);
-          __nv_bfloat162 h2 = __floats2bfloat162_rn(f[8 * j + 4], f[8 * j + 5]);
-          __nv_bfloat162 h3 = __floats2bfloat162_rn(f[8 * j + 6], f[8 * j + 7]);
           uint4 u;
-          u.x = *reinterpret_cast<uint32_t*>(&h0);
-          u.y = *reinterpret_cast<uint32_t*>(&h1);
-          u.z = *reinterpret_cast<uint32_t*>(&h2);
-          u.w = *reinterpret_cast<uint32_t*>(&h3);
+          pack8_16(f + 8 * j, p.f16 != 0, u.x, u.y, u.z, u.w);
           o[j] = u;
         }
       } else {
@@ -334,7 +327,7 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc(BN);
+      const uint32_t idesc = umma_idesc(BN, p.f16 != 0 && split == 0);      // split operands are bf16 by construction
       int it = 0, m0, n0;
       if (w_stationary && tile_at(0, m0, n0)) mbar_wait(wfull_bar, 0);
       for (int lt = 0; tile_at(lt, m0, n0); ++lt) {
@@ -484,8 +477,9 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __
               uint32_t off;
               if (BOXC == 64) off = (uint32_t)lane * 128u + ((c16 ^ (uint32_t)(lane & 7)) << 4);       // SWIZZLE_128B
               else off = (uint32_t)lane * 64u + ((c16 ^ ((uint32_t)(lane >> 1) & 3u)) << 4);          // SWIZZLE_64B
-              st_shared_v4(buf + off, pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
-                           pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+              uint32_t w0, w1, w2, w3;
+              pack8_16(f + 8 * j, p.f16 != 0, w0, w1, w2, w3);
+              st_shared_v4(buf + off, w0, w1, w2, w3);
             }
             if ((cc % BOXC) + 32 == BOXC) {
               asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -543,10 +537,11 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __
               }
               const uint32_t buf2 = staging2 + (uint32_t)ew * STG2_BYTES;     // free: every earlier store was waited for above
 #pragma unroll
-              for (int j = 0; j < 4; ++j)
-                st_shared_v4(buf2 + (uint32_t)lane * 64u + ((((uint32_t)j) ^ ((uint32_t)(lane >> 1) & 3u)) << 4),
-                             pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
-                             pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+              for (int j = 0; j < 4; ++j) {
+                uint32_t w0, w1, w2, w3;
+                pack8_16(f + 8 * j, p.f16 != 0, w0, w1, w2, w3);
+                st_shared_v4(buf2 + (uint32_t)lane * 64u + ((((uint32_t)j) ^ ((uint32_t)(lane >> 1) & 3u)) << 4), w0, w1, w2, w3);
+              }
               asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
               __syncwarp();
               if (lane == 0) tma_store_2d(&tmD, buf2, n, m0 + q * 32);
@@ -714,6 +709,7 @@ int launch_persistent_t(const GemmArgs& g, cudaStream_t st) {
   p.gelu_half = g.gelu_half;
   p.gelu_exact = g.gelu_exact;
   p.split = split_mode;
+  p.f16 = g.f16;
 
   const long long total = (long long)m_tiles * n_tiles;
   const int grid = ws ? (num_sms() / n_tiles) * n_tiles : (int)(total < num_sms() ? total : num_sms());
@@ -769,6 +765,7 @@ int launch(const GemmArgs& g, cudaStream_t st) {
     attr_set = true;
   }
   EpiParams p{g.bias, g.resid, g.C, g.M, g.N, g.ldc, g.epi, g.out_bf16, g.up_h, g.up_w, g.up_cout};
+  p.f16 = g.f16;
   const int n_tiles = g.N / BN;
   const long long grid = (long long)cdiv(g.M, BM) * n_tiles;
   gemm_tcgen05_kernel<BN><<<(unsigned)grid, kThreads, smem, st>>>(tmA, tmW, p, g.K, n_tiles, n_stages);

@@ -19,7 +19,7 @@ struct InProjW { float w[32 * 18]; float b[32]; float ln_g[32]; float ln_b[32]; 
 
 __global__ void __launch_bounds__(128)
 input_proj_kernel(const float* __restrict__ x, float* __restrict__ out, const __grid_constant__ InProjW W, int B,
-                  __nv_bfloat16* __restrict__ ln_out) {
+                  uint16_t* __restrict__ ln_out, int ln_f16) {
   __shared__ __align__(16) float4 stage[128 * 8];            // [pixel][8 float4], chunk index XOR (pixel & 7)
   const size_t pix0 = (size_t)blockIdx.x * blockDim.x;
   const size_t pix = pix0 + threadIdx.x;
@@ -68,8 +68,7 @@ input_proj_kernel(const float* __restrict__ x, float* __restrict__ out, const __
           const int c = q * 8 + 2 * e;
           const float a0 = fmaf((v[c] - mean) * rstd, W.ln_g[c], W.ln_b[c]);
           const float a1 = fmaf((v[c + 1] - mean) * rstd, W.ln_g[c + 1], W.ln_b[c + 1]);
-          const __nv_bfloat162 h = __floats2bfloat162_rn(a0, a1);
-          pk[e] = *reinterpret_cast<const uint32_t*>(&h);
+          pk[e] = ln_f16 ? pack2_f16(a0, a1) : pack2_bf16(a0, a1);
         }
         o4[q] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }

@@ -102,9 +102,9 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
   return d;
 }
 
-// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=BN.
-__host__ __device__ constexpr uint32_t umma_idesc(int bn) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// kind::f16 instruction descriptor: D=f32, A=B=bf16 (format 1) or fp16 (format 0), both K-major, M=128, N=BN.
+__host__ __device__ constexpr uint32_t umma_idesc(int bn, bool f16 = false) {
+  return (1u << 4) | (f16 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
 __host__ __device__ constexpr int tmem_cols(int bn) { return bn <= 32 ? 32 : bn <= 64 ? 64 : bn <= 128 ? 128 : 256; }

@@ -11,9 +11,13 @@ namespace wmk {
 template <typename T> __device__ __forceinline__ float to_f(T v);
 template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
 template <> __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <> __device__ __forceinline__ float to_f<__half>(__half v) { return __half2float(v); }
 template <typename T> __device__ __forceinline__ T from_f(float v);
 template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
 template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16(v); }
+template <> __device__ __forceinline__ __half from_f<__half>(float v) {
+  return __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));      // saturate instead of overflowing to inf
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -117,6 +121,14 @@ layernorm_kernel(const float* __restrict__ x, OpT* __restrict__ out, const float
         store4<OpT>(out + (size_t)token * C + c, y0, y1, y2, y3);
     }
   }
+}
+
+template <>
+__device__ __forceinline__ void store4<__half>(__half* p, float a, float b, float c, float d) {
+  uint2 u;
+  u.x = pack2_f16(a, b);
+  u.y = pack2_f16(c, d);
+  *reinterpret_cast<uint2*>(p) = u;
 }
 
 template <typename OpT>
@@ -233,6 +245,11 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t add
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
 }
+__device__ __forceinline__ void mma_f16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
 __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
@@ -278,11 +295,17 @@ __device__ __forceinline__ float ex2_approx(float x) {
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr int ATT_BLD = 72;    // bf16 elements per bias row in smem (144 B: conflict-free ldmatrix)
 
+// F16: q / k / v / out (and the in-kernel bias and probability fragments) are IEEE fp16 instead of bf16.
+template <bool F16>
 static __global__ void __launch_bounds__(128)
-window_attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
+window_attention_mma_kernel(const uint16_t* __restrict__ qkv, uint16_t* __restrict__ out,
                             const float* __restrict__ bias, int C, int H, int shift, int n_windows) {
-  __shared__ __align__(16) __nv_bfloat16 sbuf[2][3 * ATT_TILE];
-  __shared__ __align__(16) __nv_bfloat16 sbias[64 * ATT_BLD];
+  __shared__ __align__(16) uint16_t sbuf[2][3 * ATT_TILE];
+  __shared__ __align__(16) uint16_t sbias[64 * ATT_BLD];
+  auto mma = [](float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    if constexpr (F16) mma_f16_16816(d, a, b0, b1);
+    else mma_bf16_16816(d, a, b0, b1);
+  };
   __shared__ int s_tok[2][64], s_rid[2][64];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   AttGeom g{C, H, shift, 31 - __clz(C >> 5), 31 - __clz(H >> 3)};
@@ -302,8 +325,8 @@ window_attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16
     int ta, tb, rr;
     att_row(g, win, tid >> 2, ta, rr);
     att_row(g, win, 32 + (tid >> 2), tb, rr);
-    const __nv_bfloat16* pa = qkv + (size_t)ta * (3 * C) + head * 32 + (tid & 3) * 8;
-    const __nv_bfloat16* pb = qkv + (size_t)tb * (3 * C) + head * 32 + (tid & 3) * 8;
+    const uint16_t* pa = qkv + (size_t)ta * (3 * C) + head * 32 + (tid & 3) * 8;
+    const uint16_t* pb = qkv + (size_t)tb * (3 * C) + head * 32 + (tid & 3) * 8;
     const uint32_t da = (uint32_t)__cvta_generic_to_shared(&sbuf[buf][(tid >> 2) * ATT_LD + (tid & 3) * 8]);
     const uint32_t db = da + 2u * 32 * ATT_LD;
 #pragma unroll
@@ -321,12 +344,12 @@ window_attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16
     const float* bh = bias + (size_t)head * 4096;
     for (int e = tid; e < 2048; e += 128) {
       const float2 v = __ldg(reinterpret_cast<const float2*>(bh) + e);
-      *reinterpret_cast<uint32_t*>(&sbias[(e >> 5) * ATT_BLD + (e & 31) * 2]) = pack_bf16(v.x, v.y);
+      *reinterpret_cast<uint32_t*>(&sbias[(e >> 5) * ATT_BLD + (e & 31) * 2]) = pack2_16<F16>(v.x, v.y);
     }
   }
   const int gq = lane >> 2, t = lane & 3;
   // identity A fragment (16x16): thread (gq, t) holds A[gq][2t..2t+1] and A[gq+8][2t+8..2t+9]
-  const uint32_t ident = pack_bf16(gq == 2 * t ? 1.f : 0.f, gq == 2 * t + 1 ? 1.f : 0.f);
+  const uint32_t ident = pack2_16<F16>(gq == 2 * t ? 1.f : 0.f, gq == 2 * t + 1 ? 1.f : 0.f);
   const uint32_t aI[4] = {ident, 0u, 0u, ident};
   const uint32_t bs_addr = (uint32_t)__cvta_generic_to_shared(sbias);
   for (int it = 0; win < n_windows; win += wstep, ++it) {
@@ -339,7 +362,7 @@ window_attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16
       asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
-    __nv_bfloat16* Qs = &sbuf[buf][0];
+    uint16_t* Qs = &sbuf[buf][0];
     const int* tok = s_tok[buf];
     const int* rid = s_rid[buf];
     const uint32_t qs = (uint32_t)__cvta_generic_to_shared(Qs), ks = qs + 2u * ATT_TILE, vs = qs + 4u * ATT_TILE;
@@ -352,8 +375,8 @@ window_attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16
     for (int np = 0; np < 4; ++np) {
       uint32_t bb[4];
       ldmatrix_x4_trans(bb, bs_addr + 2u * ((r0 + (lane & 7) + ((lane >> 3) & 1) * 8) * ATT_BLD + np * 16 + (lane >> 4) * 8));
-      mma_bf16_16816(sacc[2 * np], aI, bb[0], bb[1]);
-      mma_bf16_16816(sacc[2 * np + 1], aI, bb[2], bb[3]);
+      mma(sacc[2 * np], aI, bb[0], bb[1]);
+      mma(sacc[2 * np + 1], aI, bb[2], bb[3]);
     }
     // ---- S += Q K^T
 #pragma unroll
@@ -364,8 +387,8 @@ window_attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16
       for (int np = 0; np < 4; ++np) {           // two n-tiles (16 keys) per ldmatrix.x4
         uint32_t bq[4];
         ldmatrix_x4(bq, ks + 2u * ((np * 16 + (lane & 7) + (lane >> 4) * 8) * ATT_LD + kk * 16 + ((lane >> 3) & 1) * 8));
-        mma_bf16_16816(sacc[2 * np], a, bq[0], bq[1]);
-        mma_bf16_16816(sacc[2 * np + 1], a, bq[2], bq[3]);
+        mma(sacc[2 * np], a, bq[0], bq[1]);
+        mma(sacc[2 * np + 1], a, bq[2], bq[3]);
       }
     }
     // ---- shift mask (only windows of the last window row / column hold more than one region), softmax
@@ -410,24 +433,24 @@ window_attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {             // 16 keys per step
       uint32_t a[4];
-      a[0] = pack_bf16(sacc[2 * kk][0], sacc[2 * kk][1]);
-      a[1] = pack_bf16(sacc[2 * kk][2], sacc[2 * kk][3]);
-      a[2] = pack_bf16(sacc[2 * kk + 1][0], sacc[2 * kk + 1][1]);
-      a[3] = pack_bf16(sacc[2 * kk + 1][2], sacc[2 * kk + 1][3]);
+      a[0] = pack2_16<F16>(sacc[2 * kk][0], sacc[2 * kk][1]);
+      a[1] = pack2_16<F16>(sacc[2 * kk][2], sacc[2 * kk][3]);
+      a[2] = pack2_16<F16>(sacc[2 * kk + 1][0], sacc[2 * kk + 1][1]);
+      a[3] = pack2_16<F16>(sacc[2 * kk + 1][2], sacc[2 * kk + 1][3]);
 #pragma unroll
       for (int np = 0; np < 2; ++np) {           // two n-tiles (16 dims) per ldmatrix.x4.trans
         uint32_t bv[4];
         ldmatrix_x4_trans(bv, vs + 2u * ((kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * ATT_LD + np * 16 + (lane >> 4) * 8));
-        mma_bf16_16816(oacc[2 * np], a, bv[0], bv[1]);
-        mma_bf16_16816(oacc[2 * np + 1], a, bv[2], bv[3]);
+        mma(oacc[2 * np], a, bv[0], bv[1]);
+        mma(oacc[2 * np + 1], a, bv[2], bv[3]);
       }
     }
     // ---- stage O (this warp's 16 rows) in the Q tile, then 16-byte stores to the token rows
     __syncwarp();
 #pragma unroll
     for (int n = 0; n < 4; ++n) {
-      *reinterpret_cast<uint32_t*>(Qs + row0 * ATT_LD + n * 8 + 2 * t) = pack_bf16(oacc[n][0] * inv0, oacc[n][1] * inv0);
-      *reinterpret_cast<uint32_t*>(Qs + row1 * ATT_LD + n * 8 + 2 * t) = pack_bf16(oacc[n][2] * inv1, oacc[n][3] * inv1);
+      *reinterpret_cast<uint32_t*>(Qs + row0 * ATT_LD + n * 8 + 2 * t) = pack2_16<F16>(oacc[n][0] * inv0, oacc[n][1] * inv0);
+      *reinterpret_cast<uint32_t*>(Qs + row1 * ATT_LD + n * 8 + 2 * t) = pack2_16<F16>(oacc[n][2] * inv1, oacc[n][3] * inv1);
     }
     __syncwarp();
 #pragma unroll
@@ -845,10 +868,11 @@ im2col_4x4s2_kernel(const float* __restrict__ x, OpT* __restrict__ A, int B, int
   OpT* dst = A + ((b * Ho + oh) * Ho + ow) * (size_t)(16 * C) + (kh * 4) * C + c;
 #pragma unroll
   for (int kw = 0; kw < 4; ++kw) {
-    if constexpr (OpMode<OpT>::v == 1) {
+    if constexpr (OpPlain16<OpT>::v) {
+      constexpr bool F16 = OpMode<OpT>::v == 3;
       uint4 u;
-      u.x = pack_bf16(v[kw][0].x, v[kw][0].y); u.y = pack_bf16(v[kw][0].z, v[kw][0].w);
-      u.z = pack_bf16(v[kw][1].x, v[kw][1].y); u.w = pack_bf16(v[kw][1].z, v[kw][1].w);
+      u.x = pack2_16<F16>(v[kw][0].x, v[kw][0].y); u.y = pack2_16<F16>(v[kw][0].z, v[kw][0].w);
+      u.z = pack2_16<F16>(v[kw][1].x, v[kw][1].y); u.w = pack2_16<F16>(v[kw][1].z, v[kw][1].w);
       *reinterpret_cast<uint4*>(dst + kw * C) = u;
     } else {
       *reinterpret_cast<float4*>(dst + kw * C) = v[kw][0];

@@ -22,8 +22,8 @@ int stft_clips(const float* wave, int B, int L, float* clips, int n_clips, cudaS
 int istft_clips(const float* clips, int B, int n_clips, int T, float* wave, int length, cudaStream_t st);
 int leff_dwconv_linear2_bf16(const __nv_bfloat16* H1, const float* dw_w, const float* dw_b, const __nv_bfloat16* W2,
                              const float* b2, float* x, int n, int H, int C, cudaStream_t st);
-int dwconv3x3_gelu_bf16(const __nv_bfloat16* in, __nv_bfloat16* out, const float* wt, const float* bias, int B, int H,
-                        int Ch, cudaStream_t st);
+int dwconv3x3_gelu_op16(const void* in, void* out, const float* wt, const float* bias, int B, int H, int Ch, int f16,
+                        cudaStream_t st);
 int dwconv3x3_gelu_split(const float* in, __nv_bfloat16* out, const float* wt, const float* bias, int B, int H, int Ch,
                          cudaStream_t st);
 
@@ -93,10 +93,13 @@ struct wmk_plan {
   bool taps_on = false;
   std::map<std::string, std::pair<float*, size_t>> taps;
 
-  // operand mode of the two networks: 0 fp32 (SIMT), 1 bf16 (tcgen05), 2 split-bf16 (tcgen05, three MMAs per product)
-  int embed_mode() const { return precision == WMK_PREC_FP32 ? 0 : 1; }
-  int extract_mode() const { return precision == WMK_PREC_FP32 ? 0 : precision == WMK_PREC_BF16 ? 1 : 2; }
-  size_t op_size() const { return precision == WMK_PREC_BF16 ? 2 : 4; }      // bytes per operand element (split: hi + lo)
+  // operand mode of the two networks: 0 fp32 (SIMT), 1 bf16 (tcgen05), 2 split-bf16 (tcgen05, three MMAs per product),
+  // 3 fp16 (tcgen05)
+  int embed_mode() const { return precision == WMK_PREC_FP32 ? 0 : precision == WMK_PREC_BF16 ? 1 : 3; }
+  int extract_mode() const {
+    return precision == WMK_PREC_FP32 ? 0 : precision == WMK_PREC_BF16 ? 1 : precision == WMK_PREC_F16 ? 3 : 2;
+  }
+  size_t op_size() const { return (precision == WMK_PREC_BF16 || precision == WMK_PREC_F16) ? 2 : 4; }   // bytes per operand element (split: hi + lo)
 };
 
 namespace wmk {
@@ -129,6 +132,13 @@ int upload_op(wmk_plan* P, const std::vector<float>& v, void** out, int mode, in
         if (K == 32) { h[n * ld + k] = hi; h[n * ld + 32 + k] = hi; h[n * ld + 64 + k] = lo; }
         else { h[n * ld + k] = hi; h[n * ld + K + k] = lo; }
       }
+  } else if (mode == 3) {          // IEEE fp16, saturating
+    h.resize(v.size());
+    for (size_t i = 0; i < v.size(); ++i) {
+      const float c = v[i] > 65504.f ? 65504.f : (v[i] < -65504.f ? -65504.f : v[i]);
+      const __half hv = __float2half_rn(c);
+      h[i] = *reinterpret_cast<const __nv_bfloat16*>(&hv);      // 16-bit container
+    }
   } else {
     h.resize(v.size());
     for (size_t i = 0; i < v.size(); ++i) h[i] = __float2bfloat16(v[i]);
@@ -196,7 +206,7 @@ int pack_block(wmk_plan* P, const std::string& p, int C, int heads, int H, int s
   WMK_TRY(upload_op(P, t->data, &w->w_proj, mode, C));
   WMK_TRY(get_f32(P, p + "attn.proj.bias", C, &w->b_proj));
   WMK_TRY(get(P, p + "mlp.linear1.0.weight", 4 * (size_t)C * C, &t));
-  if (mode == 1) {
+  if (mode == 1 || mode == 3) {
     // the GELU epilogue of linear1 takes x / 2 (gelu_tanh2_half_arg): halve W1 and b1, exact in bf16 / fp32
     const HostTensor* tb;
     WMK_TRY(get(P, p + "mlp.linear1.0.bias", 4 * (size_t)C, &tb));
@@ -218,7 +228,7 @@ int pack_block(wmk_plan* P, const std::string& p, int C, int heads, int H, int s
     for (int tap = 0; tap < 9; ++tap) dwt[(size_t)tap * 4 * C + c] = dw->data[(size_t)c * 9 + tap];
   WMK_TRY(upload_f32(P, dwt, &w->dw_w));
   WMK_TRY(get_f32(P, p + "mlp.dwconv.0.bias", 4 * (size_t)C, &w->dw_b));
-  if (mode == 1) {
+  if (mode == 1 || mode == 3) {
     const HostTensor* db;
     WMK_TRY(get(P, p + "mlp.dwconv.0.bias", 4 * (size_t)C, &db));
     std::vector<float> bh(4 * (size_t)C);
@@ -327,11 +337,13 @@ template <typename OpT>
 int run_block(wmk_plan* P, const BlockW& w, float* x, int n, cudaStream_t st, bool ln1_ready = false,
               const BlockW* next = nullptr) {
   constexpr int MODE = OpMode<OpT>::v;
+  constexpr bool P16 = OpPlain16<OpT>::v;          // plain 16-bit operands: bf16 (MODE 1) or fp16 (MODE 3)
+  constexpr int F16 = MODE == 3;
   const int C = w.C, H = w.H;
   const int M = n * H * H;
-  const int ob = MODE == 1;
+  const int ob = P16;
   static const int fuse_min_c = getenv("WMK_FUSE_LN_MINC") ? atoi(getenv("WMK_FUSE_LN_MINC")) : 32;
-  const bool fuse_ln = MODE == 1 && C <= 128 && C >= fuse_min_c;
+  const bool fuse_ln = P16 && C <= 128 && C >= fuse_min_c;
   OpT* A = reinterpret_cast<OpT*>(P->bufA);
   if (!(ln1_ready && fuse_ln)) {
     ProfScope prof(FAM_LAYERNORM, (double)M * C * (4 + sizeof(OpT)), st);
@@ -340,18 +352,17 @@ int run_block(wmk_plan* P, const BlockW& w, float* x, int n, cudaStream_t st, bo
   }
   GemmArgs g;
   g.A = A; g.W = w.w_qkv; g.bias = w.b_qkv; g.C = P->bufQKV; g.M = M; g.N = 3 * C; g.K = C; g.ldc = 3 * C;
-  g.epi = EPI_BIAS; g.out_bf16 = ob; g.split = MODE == 2;
+  g.epi = EPI_BIAS; g.out_bf16 = ob; g.split = MODE == 2; g.f16 = F16;
   WMK_TRY(gemm(MODE, g, st));
   {
     ProfScope prof(FAM_ATTENTION, 256.0 * C * M, st);
     const int n_windows = n * (H / 8) * (H / 8);
-    if constexpr (MODE == 1) {
+    if constexpr (P16) {
       int per_head = (148 * 5) / w.heads;                 // CTAs per head (5 resident CTAs per SM)
       if (per_head > n_windows) per_head = n_windows;
       if (per_head < 1) per_head = 1;
-      window_attention_mma_kernel<<<per_head * w.heads, 128, 0, st>>>(
-          reinterpret_cast<const __nv_bfloat16*>(P->bufQKV), reinterpret_cast<__nv_bfloat16*>(P->bufO), w.attn_bias, C, H,
-          w.shift, n_windows);
+      window_attention_mma_kernel<F16 != 0><<<per_head * w.heads, 128, 0, st>>>(
+          reinterpret_cast<const uint16_t*>(P->bufQKV), reinterpret_cast<uint16_t*>(P->bufO), w.attn_bias, C, H, w.shift, n_windows);
     } else if constexpr (MODE == 2) {
       static bool attr_set = false;
       if (!attr_set) {
@@ -372,7 +383,7 @@ int run_block(wmk_plan* P, const BlockW& w, float* x, int n, cudaStream_t st, bo
   }
   g = GemmArgs();
   g.A = P->bufO; g.W = w.w_proj; g.bias = w.b_proj; g.resid = x; g.C = x; g.M = M; g.N = C; g.K = C; g.ldc = C;
-  g.epi = EPI_BIAS_RESID; g.out_bf16 = 0; g.split = MODE == 2;
+  g.epi = EPI_BIAS_RESID; g.out_bf16 = 0; g.split = MODE == 2; g.f16 = F16;
   if (fuse_ln) { g.ln_out = A; g.ln_gamma = w.ln2_w; g.ln_beta = w.ln2_b; }        // norm2 (model.py:1017)
   WMK_TRY(gemm(MODE, g, st));
   if (!fuse_ln) {
@@ -383,7 +394,7 @@ int run_block(wmk_plan* P, const BlockW& w, float* x, int n, cudaStream_t st, bo
   g = GemmArgs();
   g.A = A; g.W = w.w_l1; g.bias = w.b_l1; g.C = P->bufH1; g.M = M; g.N = 4 * C; g.K = C; g.ldc = 4 * C;
   g.epi = EPI_BIAS_GELU; g.out_bf16 = ob; g.gelu_half = ob;      // bf16 plans carry W1 / 2, b1 / 2 (pack_block)
-  g.split = MODE == 2; g.gelu_exact = MODE == 2;
+  g.split = MODE == 2; g.gelu_exact = MODE == 2; g.f16 = F16;
   WMK_TRY(gemm(MODE, g, st));
   if constexpr (MODE == 1) {
     if (P->fused_leff && C <= 256 && H <= P->fused_maxh && H >= P->fused_minh) {
@@ -400,9 +411,8 @@ int run_block(wmk_plan* P, const BlockW& w, float* x, int n, cudaStream_t st, bo
   }
   {
     ProfScope prof(FAM_DWCONV, 8.0 * M * C * sizeof(OpT), st);
-    if constexpr (MODE == 1) {
-      WMK_TRY(dwconv3x3_gelu_bf16(reinterpret_cast<const __nv_bfloat16*>(P->bufH1), reinterpret_cast<__nv_bfloat16*>(P->bufH2),
-                                  w.dw_wh, w.dw_bh, n, H, 4 * C, st));
+    if constexpr (P16) {
+      WMK_TRY(dwconv3x3_gelu_op16(P->bufH1, P->bufH2, w.dw_wh, w.dw_bh, n, H, 4 * C, F16, st));
     } else if constexpr (MODE == 2) {
       WMK_TRY(dwconv3x3_gelu_split(reinterpret_cast<const float*>(P->bufH1), reinterpret_cast<__nv_bfloat16*>(P->bufH2),
                                    w.dw_w, w.dw_b, n, H, 4 * C, st));
@@ -414,7 +424,7 @@ int run_block(wmk_plan* P, const BlockW& w, float* x, int n, cudaStream_t st, bo
   }
   g = GemmArgs();
   g.A = P->bufH2; g.W = w.w_l2; g.bias = w.b_l2; g.resid = x; g.C = x; g.M = M; g.N = C; g.K = 4 * C; g.ldc = C;
-  g.epi = EPI_BIAS_RESID; g.out_bf16 = 0; g.split = MODE == 2;
+  g.epi = EPI_BIAS_RESID; g.out_bf16 = 0; g.split = MODE == 2; g.f16 = F16;
   if (fuse_ln && next) {                                                           // the next block's norm1 + modulator
     g.ln_out = A; g.ln_gamma = next->ln1_w; g.ln_beta = next->ln1_b; g.ln_mod = next->mod; g.ln_H = H; g.ln_shift = next->shift;
   }
@@ -438,9 +448,10 @@ int run_encoder(wmk_plan* P, const EncW& e, const float* x_nchw, int n, const ch
   {
     ProfScope prof(FAM_SMALL, (double)n * 16384 * (8 + 128), st);
     static const int fuse_ln0 = getenv("WMK_FUSE_FIRST_LN") ? atoi(getenv("WMK_FUSE_FIRST_LN")) : 1;
-    const bool ln0 = OpMode<OpT>::v == 1 && fuse_ln0 && e.in_proj_has_ln;       // norm1 of stage 0's block in the same pass
+    const bool ln0 = OpPlain16<OpT>::v && fuse_ln0 && e.in_proj_has_ln;       // norm1 of stage 0's block in the same pass
     input_proj_kernel<<<cdiv((size_t)n * 16384, 128), 128, 0, st>>>(x_nchw, P->E[0], e.in_proj, n,
-                                                                   ln0 ? reinterpret_cast<__nv_bfloat16*>(P->bufA) : nullptr);
+                                                                   ln0 ? reinterpret_cast<uint16_t*>(P->bufA) : nullptr,
+                                                                   OpMode<OpT>::v == 3);
     WMK_CHECK_LAUNCH("input_proj_kernel");
     stage0_ln_ready = ln0;
   }
@@ -463,9 +474,9 @@ int run_encoder(wmk_plan* P, const EncW& e, const float* x_nchw, int n, const ch
     }
     GemmArgs g;
     g.A = col; g.W = e.down_w[s]; g.bias = e.down_b[s]; g.C = P->E[s + 1]; g.M = n * Ho * Ho; g.N = 2 * C;
-    g.K = 16 * C; g.ldc = 2 * C; g.epi = EPI_BIAS; g.out_bf16 = 0; g.split = OpMode<OpT>::v == 2;
+    g.K = 16 * C; g.ldc = 2 * C; g.epi = EPI_BIAS; g.out_bf16 = 0; g.split = OpMode<OpT>::v == 2; g.f16 = OpMode<OpT>::v == 3;
     static const int fuse_first_ln = getenv("WMK_FUSE_FIRST_LN") ? atoi(getenv("WMK_FUSE_FIRST_LN")) : 1;
-    if (OpMode<OpT>::v == 1 && fuse_first_ln && 2 * C <= 128) {
+    if (OpPlain16<OpT>::v && fuse_first_ln && 2 * C <= 128) {
       // the next stage's first norm1 rides on the downsample conv's epilogue (encoder blocks carry no modulator)
       const BlockW& nb = e.stage[s + 1][0];
       g.ln_out = P->bufA; g.ln_gamma = nb.ln1_w; g.ln_beta = nb.ln1_b; g.ln_mod = nb.mod; g.ln_H = Ho; g.ln_shift = nb.shift;
@@ -494,6 +505,7 @@ int run_extract_any(wmk_plan* P, const float* y, int n, float* wm, float* logits
   switch (P->extract_mode()) {
     case 0: return run_extract<float>(P, y, n, wm, logits, st);
     case 1: return run_extract<__nv_bfloat16>(P, y, n, wm, logits, st);
+    case 3: return run_extract<__half>(P, y, n, wm, logits, st);
     default: return run_extract<SplitBf16>(P, y, n, wm, logits, st);
   }
 }
@@ -526,7 +538,7 @@ int run_forward(wmk_plan* P, const float* x, const float* msg, MsgMap mm, int cl
     }
     GemmArgs g;
     g.A = A; g.W = P->up_w[s]; g.bias = P->up_b[s]; g.C = P->D[s]; g.M = n * Hin * Hin; g.N = 4 * Cout; g.K = Cin;
-    g.ldc = Cd; g.epi = EPI_UPSAMPLE; g.out_bf16 = 0; g.up_h = Hin; g.up_w = Hin; g.up_cout = Cout;
+    g.ldc = Cd; g.epi = EPI_UPSAMPLE; g.out_bf16 = 0; g.up_h = Hin; g.up_w = Hin; g.up_cout = Cout; g.f16 = OpMode<OpT>::v == 3;
     WMK_TRY(gemm(OpMode<OpT>::v, g, st));
     {
       const size_t rows = (size_t)n * Hout * Hout;
@@ -574,7 +586,7 @@ int check_ready(wmk_plan* P) {
 // ------------------------------------------------------------------------------------ C ABI
 extern "C" int wmk_uformer_plan_create(int precision, wmk_plan** out) {
   WMK_REQUIRE(out, "plan_create: null out");
-  WMK_REQUIRE(precision == WMK_PREC_FP32 || precision == WMK_PREC_BF16 || precision == WMK_PREC_MIXED,
+  WMK_REQUIRE(precision == WMK_PREC_FP32 || precision == WMK_PREC_BF16 || precision == WMK_PREC_MIXED || precision == WMK_PREC_F16,
               "plan_create: unknown precision %d", precision);
   int dev = 0;
   WMK_CHECK_CUDA(cudaGetDevice(&dev));
@@ -690,6 +702,9 @@ static int forward_mapped(wmk_plan* P, const float* x, const float* msg, MsgMap 
     if (P->embed_mode() == 1)
       s = run_forward<__nv_bfloat16>(P, x + o * 32768, msg, mm, b0, n, off(stft_new, 32768), off(noise, 32768), off(y, 32768),
                                      off(wm_pred, 1024), off(wm, 1024), off(wm_logits, 1024), st);
+    else if (P->embed_mode() == 3)
+      s = run_forward<__half>(P, x + o * 32768, msg, mm, b0, n, off(stft_new, 32768), off(noise, 32768), off(y, 32768),
+                              off(wm_pred, 1024), off(wm, 1024), off(wm_logits, 1024), st);
     else
       s = run_forward<float>(P, x + o * 32768, msg, mm, b0, n, off(stft_new, 32768), off(noise, 32768), off(y, 32768),
                              off(wm_pred, 1024), off(wm, 1024), off(wm_logits, 1024), st);
@@ -760,9 +775,10 @@ extern "C" int wmk_plan_get_tap(wmk_plan* P, const char* name, float* out, size_
   return 0;
 }
 
-static __global__ void widen_kernel(const __nv_bfloat16* in, float* out, size_t n) {
+static __global__ void widen_kernel(const uint16_t* in, float* out, size_t n, bool f16) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = __bfloat162float(in[i]);
+  if (i >= n) return;
+  out[i] = f16 ? __half2float(reinterpret_cast<const __half*>(in)[i]) : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(in)[i]);
 }
 
 // fp32 [rows][K] -> split-bf16 rows.  form 0: [hi(K) | lo(K)]; form 1 (K = 32 weight rows): [hi | hi | lo | 0].
@@ -809,23 +825,31 @@ extern "C" int wmk_linear_f32(const float* A, const float* W, const float* bias,
     cudaFreeAsync(wsp, st);
     return s;
   }
-  WMK_REQUIRE(precision == WMK_PREC_BF16, "linear: unknown precision %d", precision);
-  __nv_bfloat16 *a16 = nullptr, *w16 = nullptr;
+  WMK_REQUIRE(precision == WMK_PREC_BF16 || precision == WMK_PREC_F16, "linear: unknown precision %d", precision);
+  const bool f16 = precision == WMK_PREC_F16;
+  uint16_t *a16 = nullptr, *w16 = nullptr;
   WMK_CHECK_CUDA(cudaMallocAsync(&a16, (size_t)M * K * 2, st));
   WMK_CHECK_CUDA(cudaMallocAsync(&w16, (size_t)N * K * 2, st));
-  copy_cols_kernel<__nv_bfloat16><<<cdiv((size_t)M * (K / 4), 256), 256, 0, st>>>(A, a16, (size_t)M, K, K, 0);
-  WMK_CHECK_LAUNCH("copy_cols_kernel");
-  copy_cols_kernel<__nv_bfloat16><<<cdiv((size_t)N * (K / 4), 256), 256, 0, st>>>(W, w16, (size_t)N, K, K, 0);
-  WMK_CHECK_LAUNCH("copy_cols_kernel");
-  g.A = a16; g.W = w16;
-  __nv_bfloat16* c16 = nullptr;
-  if (gelu) {        // the GELU epilogue stores bf16 (as inside the model): widen afterwards
+  if (f16) {
+    copy_cols_kernel<__half><<<cdiv((size_t)M * (K / 4), 256), 256, 0, st>>>(A, reinterpret_cast<__half*>(a16), (size_t)M, K, K, 0);
+    WMK_CHECK_LAUNCH("copy_cols_kernel");
+    copy_cols_kernel<__half><<<cdiv((size_t)N * (K / 4), 256), 256, 0, st>>>(W, reinterpret_cast<__half*>(w16), (size_t)N, K, K, 0);
+    WMK_CHECK_LAUNCH("copy_cols_kernel");
+  } else {
+    copy_cols_kernel<__nv_bfloat16><<<cdiv((size_t)M * (K / 4), 256), 256, 0, st>>>(A, reinterpret_cast<__nv_bfloat16*>(a16), (size_t)M, K, K, 0);
+    WMK_CHECK_LAUNCH("copy_cols_kernel");
+    copy_cols_kernel<__nv_bfloat16><<<cdiv((size_t)N * (K / 4), 256), 256, 0, st>>>(W, reinterpret_cast<__nv_bfloat16*>(w16), (size_t)N, K, K, 0);
+    WMK_CHECK_LAUNCH("copy_cols_kernel");
+  }
+  g.A = a16; g.W = w16; g.f16 = f16;
+  uint16_t* c16 = nullptr;
+  if (gelu) {        // the GELU epilogue stores 16-bit (as inside the model): widen afterwards
     WMK_CHECK_CUDA(cudaMallocAsync(&c16, (size_t)M * N * 2, st));
     g.C = c16; g.out_bf16 = 1;
   }
   int s = gemm_bf16_tcgen05(g, st);
   if (gelu && s == 0) {
-    widen_kernel<<<cdiv((size_t)M * N, 256), 256, 0, st>>>(c16, C, (size_t)M * N);
+    widen_kernel<<<cdiv((size_t)M * N, 256), 256, 0, st>>>(c16, C, (size_t)M * N, f16);
     count_launch();
   }
   if (c16) cudaFreeAsync(c16, st);

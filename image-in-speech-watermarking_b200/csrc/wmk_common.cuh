@@ -3,6 +3,7 @@
 
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -110,6 +111,9 @@ struct GemmArgs {
   // accumulator.  Outputs are fp32 (out_bf16 = 0).  gelu_exact: GELU by the 1.5e-7 erf form (gelu_fast).
   int split = 0;
   int gelu_exact = 0;
+  // Plain (non-split) 16-bit operands - A, W, a 16-bit C (out_bf16) and ln_out - are IEEE fp16 instead of bf16:
+  // same tcgen05 rate, 11 instead of 8 mantissa bits (the WMK_PREC_MIXED / WMK_PREC_F16 embedder).
+  int f16 = 0;
 };
 
 // Roofline class of a dense-layer launch: algorithmic bytes (A + W + C, + the fp32 residual) against
@@ -203,9 +207,35 @@ __device__ __forceinline__ float2 gelu_tanh2_half_arg(float2 h) {
 // lo = bf16(v - hi) (16 mantissa bits); a row of K values is stored as [hi(K) | lo(K)], i.e. 2K bf16 = 4K bytes.
 // Tag type: sizeof 4 like the storage per element.
 struct SplitBf16 { __nv_bfloat16 h, l; };
-template <typename T> struct OpMode { static constexpr int v = 0; };                // 0 fp32, 1 bf16, 2 split-bf16
+template <typename T> struct OpMode { static constexpr int v = 0; };                // 0 fp32, 1 bf16, 2 split-bf16, 3 fp16
 template <> struct OpMode<__nv_bfloat16> { static constexpr int v = 1; };
 template <> struct OpMode<SplitBf16> { static constexpr int v = 2; };
+template <> struct OpMode<__half> { static constexpr int v = 3; };
+template <typename T> struct OpPlain16 { static constexpr bool v = OpMode<T>::v == 1 || OpMode<T>::v == 3; };   // bf16 or fp16
+
+// two fp32 -> one packed 16-bit pair.  fp16 saturates to +-65504 instead of overflowing to inf.
+__device__ __forceinline__ uint32_t pack2_bf16(float lo, float hi) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ uint32_t pack2_f16(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+template <bool F16> __device__ __forceinline__ uint32_t pack2_16(float lo, float hi) {
+  if constexpr (F16) return pack2_f16(lo, hi);
+  else return pack2_bf16(lo, hi);
+}
+template <bool F16> __device__ __forceinline__ float2 unpack2_16(uint32_t u) {
+  if constexpr (F16) return __half22float2(*reinterpret_cast<const __half2*>(&u));
+  else return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+}
+// eight consecutive values -> four packed words, format chosen at run time (uniform branch, hoisted out of the callers' loops)
+__device__ __forceinline__ void pack8_16(const float* f, bool f16, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
+  if (f16) { a = pack2_f16(f[0], f[1]); b = pack2_f16(f[2], f[3]); c = pack2_f16(f[4], f[5]); d = pack2_f16(f[6], f[7]); }
+  else { a = pack2_bf16(f[0], f[1]); b = pack2_bf16(f[2], f[3]); c = pack2_bf16(f[4], f[5]); d = pack2_bf16(f[6], f[7]); }
+}
 
 // (hi, lo) words of two consecutive values
 __device__ __forceinline__ void split_pack2(float a, float b, uint32_t& hi, uint32_t& lo) {
@@ -250,6 +280,7 @@ struct EpiParams {
   int gelu_half = 0;        // GELU epilogue: the accumulator holds x / 2 (weights and bias pre-halved)
   int gelu_exact = 0;       // GELU epilogue: erf form (gelu_fast, |error| 1.5e-7) instead of the tanh form
   int split = 0;            // 0: plain; 1: split-bf16 operands, K % 64 == 0; 2: split-bf16 operands, K == 32
+  int f16 = 0;              // plain 16-bit operands / outputs are fp16 (else bf16)
 };
 
 __device__ __forceinline__ size_t epi_row_offset(const EpiParams& p, int m, int n_first) {

@@ -12,11 +12,13 @@ Same constructor arguments, same ``state_dict`` keys and shapes (so
 Inference only: the CUDA path has no backward, tensors are returned detached.
 
 ``precision`` (an extension of the reference constructor):
-  'mixed' (default, the benchmarked mode) - embedder with bf16 operands on tcgen05 (spectrogram / waveform within
-          2e-2 of the reference), EXTRACTOR in split-bf16 ("bf16x3": every product as hi*hi + lo*hi + hi*lo on
-          tcgen05, fp32 accumulate), whose thresholded bits equal the fp32 reference's outside |logit| < 1e-4;
-  'bf16'  - both networks with plain bf16 operands (fastest; logit error ~2e-3);
-  'fp32'  - fp32 SIMT GEMMs (the 1e-3 parity mode for every tensor)."""
+  'mixed' (default, the benchmarked mode) - embedder with IEEE fp16 operands on tcgen05 (fp32 accumulate; spectrogram /
+          waveform within the fp32-path tolerance 1e-3 of the reference), EXTRACTOR in split-bf16 ("bf16x3": every
+          product as hi*hi + lo*hi + hi*lo on tcgen05, fp32 accumulate), whose thresholded bits equal the fp32
+          reference's outside |logit| < 1e-4 - on identical inputs and end to end;
+  'fp16' / 'bf16' - both networks with plain 16-bit operands (fastest; logit error ~3e-4 / ~2e-3);
+  'fp32'  - fp32 SIMT GEMMs (the slow all-fp32 parity mode).
+"""
 import ctypes
 import math
 
