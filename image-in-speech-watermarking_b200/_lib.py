@@ -26,6 +26,8 @@ SIGNATURES = {
     "wmk_stft256_num_frames": (_i, [_i]),
     "wmk_stft256_clips_f32": (_i, [_vp, _i, _i, _vp, _i, _vp]),
     "wmk_minmax_f32": (_i, [_vp, _sz, _vp, _vp, _vp]),
+    "wmk_pcm_decode_f32": (_i, [_vp, _i, _sz, _i, _vp, _vp]),
+    "wmk_resample_poly_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     "wmk_attack_awgn_f32": (_i, [_vp, _vp, _i, _i, _f, _vp, _u64, _vp]),
     "wmk_attack_scale_f32": (_i, [_vp, _vp, _i, _i, _f, _vp]),
     "wmk_attack_echo_f32": (_i, [_vp, _vp, _i, _i, _i, _f, _vp]),

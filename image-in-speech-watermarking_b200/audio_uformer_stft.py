@@ -104,6 +104,46 @@ def stft256_clips(wave, n_clips=None):
     return out
 
 
+_TAPS = {}
+
+
+def resample_poly(wave, up, down):
+    """`scipy.signal.resample_poly(wave, up, down)` (Kaiser-5 windowed-sinc FIR of 20 max(up, down) + 1 taps) on the
+    GPU: wave (B, L) or (L,) CUDA fp32 -> (B, ceil(L up / down)).  The tap design is host-side scalar work, cached
+    per (up, down) on the device; corpora that are not 16 kHz go through this before the STFT."""
+    import math
+    import numpy as np
+    from scipy import signal
+    g = math.gcd(int(up), int(down))
+    up, down = int(up) // g, int(down) // g
+    w = wave.float().contiguous()
+    w = w[None] if w.dim() == 1 else w
+    if up == down:
+        return w
+    key = (up, down, str(w.device))
+    if key not in _TAPS:
+        mx = max(up, down)
+        h = signal.firwin(2 * 10 * mx + 1, 1.0 / mx, window=("kaiser", 5.0)) * up
+        _TAPS[key] = torch.from_numpy(np.ascontiguousarray(h, np.float32)).to(w.device)
+    h = _TAPS[key]
+    B, L = w.shape
+    Lout = -(-L * up // down)
+    out = torch.empty((B, Lout), device=w.device, dtype=torch.float32)
+    _lib.check(_lib.load().wmk_resample_poly_f32(_lib.ptr(w), _lib.ptr(out), B, L, Lout, up, down, _lib.ptr(h), h.numel(),
+                                                 _lib.stream_ptr()))
+    return out
+
+
+def load_utterance(path, target_sr=16000):
+    """WAV file -> (1, L) CUDA waveform at `target_sr`: header parsed on the host, samples decoded, mixed down to
+    mono and resampled on the device - the loader step in front of `stft_clips` (`uformerWM/audio_test.py:299-316`
+    gets this from torchaudio's dataset classes)."""
+    from . import wavio
+    x, sr = wavio.read_wav_cuda(path)
+    x = x.mean(0, keepdim=True) if x.shape[0] > 1 else x
+    return resample_poly(x, target_sr, sr) if sr != target_sr else x
+
+
 def minmax(x):
     """(min, max) of a CUDA float32 tensor as a 2-element device tensor (`normalize_batch`, `audio_test.py:35-37`)."""
     lib = _lib.load()

@@ -258,6 +258,43 @@ resample_up_kernel(const float* __restrict__ d, float* __restrict__ y, int L, in
   y[(size_t)blockIdx.y * L + n] = (float)a;
 }
 
+// ---------------------------------------------------------------------------- dataset front end: decode + resample
+// Interleaved PCM frames -> planar fp32 [channels][frames] with torchaudio / libsndfile scaling (int16 / 32768,
+// (u8 - 128) / 128, float32 as is): the decode step of the loaders the reference reads its corpora with
+// (uformerWM/audio_test.py:269-316, torchaudio datasets), moved to the device so a raw file payload is all that
+// crosses PCIe.
+__global__ void __launch_bounds__(256)
+pcm_decode_kernel(const uint8_t* __restrict__ pcm, int bits, size_t n_frames, int ch, float* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_frames * ch) return;
+  const size_t f = i / ch;
+  const int c = (int)(i - f * ch);
+  float v;
+  if (bits == 16) v = (float)reinterpret_cast<const int16_t*>(pcm)[i] * (1.0f / 32768.0f);
+  else if (bits == 8) v = ((float)pcm[i] - 128.0f) * (1.0f / 128.0f);
+  else v = reinterpret_cast<const float*>(pcm)[i];
+  out[(size_t)c * n_frames + f] = v;
+}
+
+// Rational-rate polyphase resampling with scipy.signal.resample_poly's alignment: the input is zero-stuffed by `up`,
+// filtered by the odd-length FIR h (centre tap on sample 0), and every `down`-th sample is kept:
+//   y[m] = sum_k h[k] xu[m down + c - k],  xu[i] = x[i / up] when up | i,  c = (n_taps - 1) / 2.
+// One thread per output sample visits only the taps that hit a non-zero input (every up-th), fp64 accumulation.
+__global__ void __launch_bounds__(256)
+resample_poly_kernel(const float* __restrict__ x, float* __restrict__ y, int L, int Lout, int up, int down,
+                     const float* __restrict__ h, int nt) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= Lout) return;
+  const float* xr = x + (size_t)blockIdx.y * L;
+  const long long pos = (long long)m * down + (nt - 1) / 2;
+  double a = 0.0;
+  for (long long k = pos % up; k < nt; k += up) {
+    const long long j = (pos - k) / up;
+    if (j >= 0 && j < L) a += (double)h[k] * xr[j];
+  }
+  y[(size_t)blockIdx.y * Lout + m] = (float)a;
+}
+
 // ---------------------------------------------------------------------------- metrics
 __global__ void __launch_bounds__(256)
 wave_stats_kernel(const float* __restrict__ orig, const float* __restrict__ test, int L, double* __restrict__ stats) {
@@ -401,6 +438,27 @@ extern "C" int wmk_attack_echo_f32(const float* src, float* dst, int B, int L, i
   ProfScope prof(FAM_ATTACK, 8.0 * B * L, (cudaStream_t)stream);
   elementwise_kernel<EW_ECHO><<<wave_grid(L, B), 256, 0, (cudaStream_t)stream>>>(src, dst, L, gain, delay);
   WMK_CHECK_LAUNCH("elementwise_kernel<echo>");
+  return 0;
+}
+
+extern "C" int wmk_pcm_decode_f32(const void* pcm, int bits, size_t n_frames, int n_channels, float* out, void* stream) {
+  WMK_REQUIRE(pcm && out && n_frames > 0 && n_channels > 0 && (bits == 8 || bits == 16 || bits == 32),
+              "pcm_decode: bad arguments (8-bit unsigned / 16-bit signed PCM or 32-bit float)");
+  const size_t n = n_frames * (size_t)n_channels;
+  ProfScope prof(FAM_SMALL, n * (bits / 8 + 4.0), (cudaStream_t)stream);
+  pcm_decode_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint8_t*>(pcm), bits, n_frames, n_channels, out);
+  WMK_CHECK_LAUNCH("pcm_decode_kernel");
+  return 0;
+}
+
+extern "C" int wmk_resample_poly_f32(const float* src, float* dst, int B, int L, int L_out, int up, int down, const float* taps,
+                                     int n_taps, void* stream) {
+  WMK_REQUIRE(src && dst && src != dst && taps && B > 0 && L > 0 && L_out > 0 && up > 0 && down > 0 && n_taps > 0 && (n_taps & 1),
+              "resample_poly: bad arguments (odd n_taps, in-place not allowed)");
+  WMK_REQUIRE((long long)L_out * down <= (long long)L * up + down, "resample_poly: L_out %d exceeds ceil(L up / down)", L_out);
+  ProfScope prof(FAM_SMALL, 4.0 * B * ((double)L + L_out), (cudaStream_t)stream);
+  resample_poly_kernel<<<dim3(cdiv(L_out, 256), B), 256, 0, (cudaStream_t)stream>>>(src, dst, L, L_out, up, down, taps, n_taps);
+  WMK_CHECK_LAUNCH("resample_poly_kernel");
   return 0;
 }
 

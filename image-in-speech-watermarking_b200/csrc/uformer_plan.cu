@@ -24,6 +24,8 @@ int leff_dwconv_linear2_bf16(const __nv_bfloat16* H1, const float* dw_w, const f
                              const float* b2, float* x, int n, int H, int C, cudaStream_t st);
 int dwconv3x3_gelu_op16(const void* in, void* out, const float* wt, const float* bias, int B, int H, int Ch, int f16,
                         cudaStream_t st);
+int leff_dwconv_linear2_split(const float* H1, const float* dw_w, const float* dw_b, const __nv_bfloat16* W2t, const float* b2,
+                              float* x, int n, int H, int C, cudaStream_t st);
 int dwconv3x3_gelu_split(const float* in, __nv_bfloat16* out, const float* wt, const float* bias, int B, int H, int Ch,
                          cudaStream_t st);
 
@@ -42,6 +44,7 @@ struct BlockW {
   float *ln1_w = nullptr, *ln1_b = nullptr, *ln2_w = nullptr, *ln2_b = nullptr, *mod = nullptr;
   float* attn_bias = nullptr;
   void *w_qkv = nullptr, *w_proj = nullptr, *w_l1 = nullptr, *w_l2 = nullptr;
+  void* w_l2_tail = nullptr;     // split plans, C <= 128: linear2 weight in the k-block form of leff_tail_split_kernel
   float *b_qkv = nullptr, *b_proj = nullptr, *b_l1 = nullptr, *b_l2 = nullptr, *dw_w = nullptr, *dw_b = nullptr;
   float *dw_wh = nullptr, *dw_bh = nullptr;      // 0.5 x the depthwise weights / bias (dwconv_tma.cu folds the GELU's 0.5)
 };
@@ -221,6 +224,24 @@ int pack_block(wmk_plan* P, const std::string& p, int C, int heads, int H, int s
   }
   WMK_TRY(get(P, p + "mlp.linear2.0.weight", 4 * (size_t)C * C, &t));
   WMK_TRY(upload_op(P, t->data, &w->w_l2, mode, 4 * C));
+  if (mode == 2 && C <= 128) {
+    // [C][(4C/32) * 128]: k-block kb (32 hidden channels) = [hi(32) | hi(32) | lo(32) | 0(32)] (leff_fused.cu)
+    const int K = 4 * C, kbs = K / 32;
+    std::vector<__nv_bfloat16> h((size_t)C * kbs * 128, __float2bfloat16(0.f));
+    for (int n = 0; n < C; ++n)
+      for (int k = 0; k < K; ++k) {
+        const float wv = t->data[(size_t)n * K + k];
+        const __nv_bfloat16 hi = __float2bfloat16(wv);
+        const __nv_bfloat16 lo = __float2bfloat16(wv - __bfloat162float(hi));
+        __nv_bfloat16* d = &h[((size_t)n * kbs + k / 32) * 128 + (k & 31)];
+        d[0] = hi; d[32] = hi; d[64] = lo;
+      }
+    void* dptr = nullptr;
+    if (cudaMalloc(&dptr, h.size() * 2) != cudaSuccess) { set_error("cudaMalloc of %zu bytes failed", h.size() * 2); return WMK_ERR_ALLOC; }
+    P->allocs.push_back(dptr);
+    WMK_CHECK_CUDA(cudaMemcpy(dptr, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
+    w->w_l2_tail = dptr;
+  }
   WMK_TRY(get_f32(P, p + "mlp.linear2.0.bias", C, &w->b_l2));
   WMK_TRY(get(P, p + "mlp.dwconv.0.weight", 36 * (size_t)C, &dw));
   std::vector<float> dwt(36 * (size_t)C);
@@ -406,6 +427,16 @@ int run_block(wmk_plan* P, const BlockW& w, float* x, int n, cudaStream_t st, bo
         launch_layernorm<OpT>(x, A, next->ln1_w, next->ln1_b, next->mod, M, C, H, next->shift, st);
         WMK_CHECK_LAUNCH("layernorm_kernel");
       }
+      return 0;
+    }
+  }
+  if constexpr (MODE == 2) {
+    // depthwise conv + GELU as the producer of linear2's split A operand: the convolved hidden tensor (16C bytes per
+    // token written + read by the separate kernels) never reaches HBM (leff_fused.cu, leff_tail_split_kernel)
+    static const int split_tail = getenv("WMK_SPLIT_TAIL") ? atoi(getenv("WMK_SPLIT_TAIL")) : 1;
+    if (split_tail && w.w_l2_tail) {
+      WMK_TRY(leff_dwconv_linear2_split(reinterpret_cast<const float*>(P->bufH1), w.dw_w, w.dw_b,
+                                        reinterpret_cast<const __nv_bfloat16*>(w.w_l2_tail), w.b_l2, x, n, H, C, st));
       return 0;
     }
   }

@@ -24,8 +24,8 @@ def write_wav(path, wave, sample_rate=16000):
         f.write(b"RIFF" + struct.pack("<I", len(body)) + body)
 
 
-def read_wav(path):
-    """-> (float32 array (channels, L), sample_rate)."""
+def _parse(path):
+    """-> (format tag, channels, sample rate, bits, payload bytes) of a RIFF/WAVE file (host-side header walk)."""
     with open(path, "rb") as f:
         buf = f.read()
     if buf[:4] != b"RIFF" or buf[8:12] != b"WAVE":
@@ -42,6 +42,28 @@ def read_wav(path):
     if fmt is None or data is None:
         raise ValueError("%s: missing fmt / data chunk" % path)
     tag, ch, sr, _, _, bits = fmt
+    if not ((tag == 3 and bits == 32) or (tag == 1 and bits in (8, 16))):
+        raise ValueError("%s: unsupported WAV encoding (format %d, %d bits)" % (path, tag, bits))
+    return tag, ch, sr, bits, data
+
+
+def read_wav_cuda(path, device="cuda"):
+    """-> (float32 CUDA tensor (channels, L), sample_rate): only the raw `data` payload crosses PCIe, the sample
+    decode (int16 / 32768, (u8 - 128) / 128, float32) and the de-interleave run on the GPU (`wmk_pcm_decode_f32`)."""
+    import torch
+    from . import _lib
+    tag, ch, sr, bits, data = _parse(path)
+    raw = torch.frombuffer(bytearray(data), dtype=torch.uint8).to(device)
+    n_frames = len(data) // (ch * bits // 8)
+    out = torch.empty((ch, n_frames), device=raw.device, dtype=torch.float32)
+    with torch.cuda.device(raw.device):
+        _lib.check(_lib.load().wmk_pcm_decode_f32(_lib.ptr(raw), bits, n_frames, ch, _lib.ptr(out), _lib.stream_ptr()))
+    return out, sr
+
+
+def read_wav(path):
+    """-> (float32 array (channels, L), sample_rate)."""
+    tag, ch, sr, bits, data = _parse(path)
     if tag == 3 and bits == 32:
         a = np.frombuffer(data, "<f4").astype(np.float32)
     elif tag == 1 and bits == 16:

@@ -139,6 +139,19 @@ int wmk_attack_resample2_f32(const float* src, float* dst, int B, int L, const d
                              int n_taps, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Dataset front end before the STFT (uformerWM/audio_test.py:269-316: the reference reads its corpora through
+ * torchaudio loaders, which decode and - for corpora that are not 16 kHz - are resampled on the host).
+ * ------------------------------------------------------------------------------------------ */
+/* Interleaved PCM frames (device copy of a WAV `data` chunk) -> planar float32 [n_channels][n_frames] with the
+ * loaders' scaling: bits = 16: int16 / 32768; 8: (uint8 - 128) / 128; 32: IEEE float as is. */
+int wmk_pcm_decode_f32(const void* pcm, int bits, size_t n_frames, int n_channels, float* out, void* stream);
+/* Polyphase resampling by up / down with scipy.signal.resample_poly's alignment: y[m] = sum_k taps[k] *
+ * xu[m * down + (n_taps - 1) / 2 - k], xu = src zero-stuffed by `up`.  src [B][L], dst [B][L_out], L_out <=
+ * ceil(L * up / down); taps: DEVICE pointer, odd n_taps (the caller designs the low-pass, e.g. firwin * up). */
+int wmk_resample_poly_f32(const float* src, float* dst, int B, int L, int L_out, int up, int down,
+                          const float* taps, int n_taps, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Metrics (uformerWM/evaluate.py:139-144 cal_snr, audio_test.py:618 audio MSE,
  * audio_test.py:522-526 signaltonoise; hidden/test_model.py:60-64 BER; audio_test.py:625,712
  * watermark MSE).  Per-utterance float64 outputs, fused reductions with warp shuffles.

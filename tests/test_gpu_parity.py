@@ -182,6 +182,43 @@ def test_dataset_classes_match_reference_structures(golden):
     assert maxrel(got[:, :, :T], 0.5 * np.transpose(ref, (2, 0, 1))) < 1e-5 and float(np.abs(got[:, :, T:]).max()) == 0.0
 
 
+def test_loader_front_end_decode_and_resample(tmp_path):
+    """Device-side loader step in front of the STFT (the reference gets decoded 16 kHz waveforms from torchaudio's
+    dataset classes, `uformerWM/audio_test.py:269-316`): PCM decode == the host reader bit for bit, polyphase
+    resampling == scipy.signal.resample_poly, and a 44.1 kHz stereo 16-bit file -> mono 16 kHz -> STFT clips."""
+    import struct
+    from scipy import signal
+    from image_in_speech_watermarking_b200 import wavio, audio_uformer_stft as FE
+    rng = np.random.default_rng(0)
+    L, ch, sr = 44100, 2, 44100
+    t = np.arange(L) / sr
+    x = np.stack([0.4 * np.sin(2 * np.pi * 440 * t), 0.3 * np.sin(2 * np.pi * 1000 * t)]) + 0.01 * rng.standard_normal((2, L))
+    pcm = np.clip(np.round(x * 32767), -32768, 32767).astype("<i2")
+    data = np.ascontiguousarray(pcm.T).tobytes()
+    fmt = struct.pack("<HHIIHH", 1, ch, sr, sr * ch * 2, ch * 2, 16)
+    body = b"WAVE" + b"fmt " + struct.pack("<I", len(fmt)) + fmt + b"data" + struct.pack("<I", len(data)) + data
+    path = str(tmp_path / "stereo44k.wav")
+    with open(path, "wb") as f:
+        f.write(b"RIFF" + struct.pack("<I", len(body)) + body)
+    host, sr0 = wavio.read_wav(path)
+    dev, sr1 = wavio.read_wav_cuda(path)
+    assert sr0 == sr1 == sr and np.array_equal(dev.cpu().numpy(), host)
+    f32 = str(tmp_path / "f32.wav")
+    wavio.write_wav(f32, host[:1], 16000)
+    assert np.array_equal(wavio.read_wav_cuda(f32)[0].cpu().numpy(), host[:1])
+    for up, down in ((160, 441), (2, 1), (1, 3), (3, 2)):
+        src = torch.from_numpy(host[:, :20000].copy()).cuda()
+        got = FE.resample_poly(src, up, down).cpu().numpy()
+        ref = signal.resample_poly(host[:, :20000].astype(np.float64), up, down, axis=1)
+        assert got.shape == ref.shape and maxrel(got, ref) < 1e-5, (up, down)
+    w = FE.load_utterance(path)                                  # stereo 44.1 kHz -> mono 16 kHz on the device
+    assert tuple(w.shape) == (1, 16000)
+    ref = signal.resample_poly(host.astype(np.float64).mean(0), 160, 441)
+    assert maxrel(w.cpu().numpy()[0], ref) < 1e-5
+    clips = FE.stft_clips(w)
+    assert clips.shape[1] == FE.num_frames(16000) // 128 + 1
+
+
 def test_stft_is_linear_and_projection_is_idempotent():
     from image_in_speech_watermarking_b200 import audio_uformer_stft as FE
     g = torch.Generator().manual_seed(0)
