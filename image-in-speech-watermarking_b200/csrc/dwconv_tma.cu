@@ -27,7 +27,7 @@ struct DwGeom {
   int H, Ch, ncs, tiles_w, tiles_h, n_items;
 };
 
-template <int TH, bool F16>
+template <int TH, bool F16, bool EXACT = false>
 __global__ void __launch_bounds__(kDwThreads, 4)
 dwconv3x3_gelu_tma_kernel(const __grid_constant__ CUtensorMap tm, uint16_t* __restrict__ out,
                           const float* __restrict__ wt, const float* __restrict__ bias, DwGeom g) {
@@ -112,8 +112,13 @@ dwconv3x3_gelu_tma_kernel(const __grid_constant__ CUtensorMap tm, uint16_t* __re
           a0 = __ffma2_rn(win[(r + dy) % 3][dx][0], wreg[dy * 3 + dx][0], a0);
           a1 = __ffma2_rn(win[(r + dy) % 3][dx][1], wreg[dy * 3 + dx][1], a1);
         }
-      a0 = gelu_tanh2_half_arg(a0);
-      a1 = gelu_tanh2_half_arg(a1);
+      if constexpr (EXACT) {
+        a0 = make_float2(gelu_fast(a0.x), gelu_fast(a0.y));
+        a1 = make_float2(gelu_fast(a1.x), gelu_fast(a1.y));
+      } else {
+        a0 = gelu_tanh2_half_arg(a0);
+        a1 = gelu_tanh2_half_arg(a1);
+      }
       uint2 o;
       o.x = pack2_16<F16>(a0.x, a0.y);
       o.y = pack2_16<F16>(a1.x, a1.y);
@@ -123,7 +128,7 @@ dwconv3x3_gelu_tma_kernel(const __grid_constant__ CUtensorMap tm, uint16_t* __re
   }
 }
 
-template <int TH, bool F16>
+template <int TH, bool F16, bool EXACT = false>
 int launch_dw(const void* in, void* out, const float* wt, const float* bias, int B, int H, int Ch, cudaStream_t st) {
   CUtensorMap tm;
   const uint64_t dims[4] = {(uint64_t)Ch, (uint64_t)H, (uint64_t)H, (uint64_t)B};
@@ -136,7 +141,7 @@ int launch_dw(const void* in, void* out, const float* wt, const float* bias, int
   WMK_REQUIRE(items < (1LL << 31), "dwconv: too many tiles (%lld)", items);
   g.n_items = (int)items;
   const int grid = (int)(items < 4LL * num_sms() ? items : 4LL * num_sms());
-  dwconv3x3_gelu_tma_kernel<TH, F16><<<grid, kDwThreads, 0, st>>>(tm, reinterpret_cast<uint16_t*>(out), wt, bias, g);
+  dwconv3x3_gelu_tma_kernel<TH, F16, EXACT><<<grid, kDwThreads, 0, st>>>(tm, reinterpret_cast<uint16_t*>(out), wt, bias, g);
   WMK_CHECK_LAUNCH("dwconv3x3_gelu_tma_kernel");
   return 0;
 }
@@ -148,7 +153,8 @@ struct DwGeom2 {
   int H, Ch, lg_ncs, lg_tw, lg_th, n_items;      // channel slabs, tiles per row / column: powers of two
 };
 
-template <bool F16>
+// EXACT: erf-form GELU (gelu_fast, 1.5e-7) on un-halved weights / bias instead of the tanh form (the precise extractor).
+template <bool F16, bool EXACT = false>
 __global__ void __launch_bounds__(kDwThreads, 4)
 dwconv3x3_gelu_tma2_kernel(const __grid_constant__ CUtensorMap tm, uint16_t* __restrict__ out,
                            const float* __restrict__ wt, const float* __restrict__ bias, DwGeom2 g) {
@@ -238,8 +244,14 @@ dwconv3x3_gelu_tma2_kernel(const __grid_constant__ CUtensorMap tm, uint16_t* __r
         const int o = i - 2;
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
-          const float2 g0 = gelu_tanh2_half_arg(acc[o % 3][q][0]);
-          const float2 g1 = gelu_tanh2_half_arg(acc[o % 3][q][1]);
+          float2 g0, g1;
+          if constexpr (EXACT) {
+            g0 = make_float2(gelu_fast(acc[o % 3][q][0].x), gelu_fast(acc[o % 3][q][0].y));
+            g1 = make_float2(gelu_fast(acc[o % 3][q][1].x), gelu_fast(acc[o % 3][q][1].y));
+          } else {
+            g0 = gelu_tanh2_half_arg(acc[o % 3][q][0]);
+            g1 = gelu_tanh2_half_arg(acc[o % 3][q][1]);
+          }
           uint2 v;
           v.x = pack2_16<F16>(g0.x, g0.y);
           v.y = pack2_16<F16>(g1.x, g1.y);
@@ -253,7 +265,7 @@ dwconv3x3_gelu_tma2_kernel(const __grid_constant__ CUtensorMap tm, uint16_t* __r
   }
 }
 
-template <bool F16>
+template <bool F16, bool EXACT = false>
 int launch_dw2(const void* in, void* out, const float* wt, const float* bias, int B, int H, int Ch, cudaStream_t st) {
   CUtensorMap tm;
   const uint64_t dims[4] = {(uint64_t)Ch, (uint64_t)H, (uint64_t)H, (uint64_t)B};
@@ -267,170 +279,26 @@ int launch_dw2(const void* in, void* out, const float* wt, const float* bias, in
   WMK_REQUIRE(items < (1LL << 31), "dwconv: too many tiles (%lld)", items);
   g.n_items = (int)items;
   const int grid = (int)(items < 4LL * num_sms() ? items : 4LL * num_sms());
-  dwconv3x3_gelu_tma2_kernel<F16><<<grid, kDwThreads, 0, st>>>(tm, reinterpret_cast<uint16_t*>(out), wt, bias, g);
+  dwconv3x3_gelu_tma2_kernel<F16, EXACT><<<grid, kDwThreads, 0, st>>>(tm, reinterpret_cast<uint16_t*>(out), wt, bias, g);
   WMK_CHECK_LAUNCH("dwconv3x3_gelu_tma2_kernel");
   return 0;
 }
 
-// ---------------------------------------------------------------------------------- split-bf16 plans
-// fp32 hidden tensor in (the linear1 GEMM of a split-bf16 plan writes fp32), exact-erf-form GELU, output as the
-// split A operand of linear2: rows [hi(Ch) | lo(Ch)].  Same item / pipeline structure as the two-column kernel
-// above with 32-channel slabs (a 128-byte pixel row of the TMA box = 32 floats); a thread owns one channel PAIR
-// of two adjacent columns.
-struct DwGeomS {
-  int H, Ch, lg_ncs, lg_tw, lg_th, n_items;      // channel slabs of 32, tiles per row / column: powers of two
-};
-
-__global__ void __launch_bounds__(kDwThreads, 4)
-dwconv3x3_gelu_split_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict__ out,
-                            const float* __restrict__ wt, const float* __restrict__ bias, DwGeomS g) {
-  constexpr uint32_t kPatchBytes = DW2_PH * DW2_PW * 128;
-  __shared__ __align__(128) uint8_t patch[2][kPatchBytes];
-  __shared__ __align__(8) uint64_t bar[2];
-  const int tid = threadIdx.x;
-  const int cg = tid & 15, cp = tid >> 4;          // channels 2 cg, 2 cg + 1 x columns 2 cp, 2 cp + 1
-
-  auto decode = [&](int item, int& slab, int& b, int& h0, int& w0) {
-    slab = item & ((1 << g.lg_ncs) - 1);
-    const int sp = item >> g.lg_ncs;
-    w0 = (sp & ((1 << g.lg_tw) - 1)) * DW2_TW;
-    h0 = ((sp >> g.lg_tw) & ((1 << g.lg_th) - 1)) * DW2_TH;
-    b = sp >> (g.lg_tw + g.lg_th);
-  };
-  auto issue = [&](int item, int stage) {
-    int slab, b, h0, w0;
-    decode(item, slab, b, h0, w0);
-    mbar_arrive_expect_tx(smem_u32(&bar[stage]), kPatchBytes);
-    tma_load_4d(smem_u32(patch[stage]), &tm, slab * 32, w0 - 1, h0 - 1, b, smem_u32(&bar[stage]));
-  };
-
-  if (tid == 0) {
-    mbar_init(smem_u32(&bar[0]), 1);
-    mbar_init(smem_u32(&bar[1]), 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  int item = blockIdx.x;
-  if (item >= g.n_items) return;
-  if (tid == 0) issue(item, 0);
-
-  for (int it = 0; item < g.n_items; item += gridDim.x, ++it) {
-    const int stage = it & 1;
-    const int next = item + gridDim.x;
-    if (tid == 0 && next < g.n_items) issue(next, stage ^ 1);   // that buffer was drained before the last barrier
-
-    int slab, b, h0, w0;
-    decode(item, slab, b, h0, w0);
-    const int c = slab * 32 + cg * 2;
-    float2 wreg[9], bz;
-#pragma unroll
-    for (int t = 0; t < 9; ++t) wreg[t] = __ldg(reinterpret_cast<const float2*>(wt + (size_t)t * g.Ch + c));
-    bz = __ldg(reinterpret_cast<const float2*>(bias + c));
-    float2 acc[3][2];                              // [output row mod 3][column]
-#pragma unroll
-    for (int s = 0; s < 3; ++s) { acc[s][0] = bz; acc[s][1] = bz; }
-    // split rows: token (b, h, w) -> out + token * 2 Ch; hi part at [c], lo part at [Ch + c]
-    __nv_bfloat16* op = out + (((size_t)b * g.H + h0) * g.H + w0 + 2 * cp) * (2 * (size_t)g.Ch) + c;
-    mbar_wait(smem_u32(&bar[stage]), (it >> 1) & 1);
-
-    // patch[r][x][32 ch] fp32; this thread reads columns 2 cp .. 2 cp + 3, channels 2 cg, 2 cg + 1
-    const uint8_t* pb = patch[stage] + cp * 256 + cg * 8;
-#pragma unroll
-    for (int i = 0; i < DW2_PH; ++i) {
-      float2 in[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) in[j] = *reinterpret_cast<const float2*>(pb + (i * DW2_PW + j) * 128);
-#pragma unroll
-      for (int dy = 0; dy < 3; ++dy) {
-        const int o = i - dy;
-        if (o < 0 || o >= DW2_TH) continue;
-#pragma unroll
-        for (int dx = 0; dx < 3; ++dx)
-#pragma unroll
-          for (int q = 0; q < 2; ++q) acc[o % 3][q] = __ffma2_rn(in[q + dx], wreg[dy * 3 + dx], acc[o % 3][q]);
-      }
-      if (i >= 2) {                                 // output row i - 2 is complete
-        const int o = i - 2;
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          uint32_t hi, lo;
-          split_pack2(gelu_fast(acc[o % 3][q].x), gelu_fast(acc[o % 3][q].y), hi, lo);
-          __nv_bfloat16* dst = op + ((size_t)o * g.H + q) * (2 * (size_t)g.Ch);
-          *reinterpret_cast<uint32_t*>(dst) = hi;
-          *reinterpret_cast<uint32_t*>(dst + g.Ch) = lo;
-          acc[o % 3][q] = bz;
-        }
-      }
-    }
-    __syncthreads();                                // everyone has drained this stage's patch
-  }
-}
-
-// H = 8 (the bottleneck stage): one thread = one pixel x 4 channels, direct loads
-__global__ void __launch_bounds__(128)
-dwconv3x3_gelu_split_simple_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out,
-                                   const float* __restrict__ wt, const float* __restrict__ bias, int B, int H, int Ch) {
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int cg = Ch >> 2;
-  if (idx >= (size_t)B * H * H * cg) return;
-  const int c = (int)(idx % cg) * 4;
-  const size_t pix = idx / cg;
-  const int w = (int)(pix % H), h = (int)((pix / H) % H);
-  const size_t b = pix / ((size_t)H * H);
-  float4 acc = __ldg(reinterpret_cast<const float4*>(bias + c));
-#pragma unroll
-  for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-    for (int dx = 0; dx < 3; ++dx) {
-      const int hh = h + dy - 1, ww = w + dx - 1;
-      if (hh < 0 || hh >= H || ww < 0 || ww >= H) continue;
-      const float4 v = *reinterpret_cast<const float4*>(in + ((b * H + hh) * H + ww) * Ch + c);
-      const float4 k = __ldg(reinterpret_cast<const float4*>(wt + (size_t)(dy * 3 + dx) * Ch + c));
-      acc.x = fmaf(v.x, k.x, acc.x); acc.y = fmaf(v.y, k.y, acc.y); acc.z = fmaf(v.z, k.z, acc.z); acc.w = fmaf(v.w, k.w, acc.w);
-    }
-  split_store4(out + pix * (2 * (size_t)Ch), c, Ch, gelu_fast(acc.x), gelu_fast(acc.y), gelu_fast(acc.z), gelu_fast(acc.w));
-}
-
 }  // namespace
 
-// in: [B][H][H][Ch] fp32 (token layout), out: split rows [B*H*H][hi(Ch) | lo(Ch)] bf16, wt: [9][Ch] fp32 tap-major,
-// bias: [Ch] fp32 (NOT pre-halved: the GELU is gelu_fast).
-int dwconv3x3_gelu_split(const float* in, __nv_bfloat16* out, const float* wt, const float* bias, int B, int H, int Ch,
-                         cudaStream_t st) {
-  WMK_REQUIRE(H >= 8 && (H & (H - 1)) == 0 && Ch >= 32 && (Ch & (Ch - 1)) == 0,
-              "dwconv(split): H=%d must be a power of two >= 8 and Ch=%d a power of two >= 32", H, Ch);
-  WMK_REQUIRE(((uintptr_t)in & 15) == 0 && ((uintptr_t)out & 15) == 0, "dwconv(split): buffers must be 16-byte aligned");
-  if (H % 16 != 0) {
-    const size_t total = (size_t)B * H * H * (Ch / 4);
-    dwconv3x3_gelu_split_simple_kernel<<<cdiv(total, 128), 128, 0, st>>>(in, out, wt, bias, B, H, Ch);
-    WMK_CHECK_LAUNCH("dwconv3x3_gelu_split_simple_kernel");
-    return 0;
-  }
-  CUtensorMap tm;
-  const uint64_t dims[4] = {(uint64_t)Ch, (uint64_t)H, (uint64_t)H, (uint64_t)B};
-  const uint64_t strides[3] = {(uint64_t)Ch * 4, (uint64_t)H * Ch * 4, (uint64_t)H * H * Ch * 4};
-  const uint32_t box[4] = {32, DW2_PW, DW2_PH, 1};
-  WMK_TRY(make_tensor_map(&tm, in, 4, dims, strides, box, true, 0));
-  auto lg = [](int v) { int l = 0; while ((1 << l) < v) ++l; return l; };
-  DwGeomS g;
-  g.H = H; g.Ch = Ch; g.lg_ncs = lg(Ch / 32); g.lg_tw = lg(H / DW2_TW); g.lg_th = lg(H / DW2_TH);
-  const long long items = (long long)B * (H / DW2_TW) * (H / DW2_TH) * (Ch / 32);
-  WMK_REQUIRE(items < (1LL << 31), "dwconv(split): too many tiles (%lld)", items);
-  g.n_items = (int)items;
-  const int grid = (int)(items < 4LL * num_sms() ? items : 4LL * num_sms());
-  dwconv3x3_gelu_split_kernel<<<grid, kDwThreads, 0, st>>>(tm, out, wt, bias, g);
-  WMK_CHECK_LAUNCH("dwconv3x3_gelu_split_kernel");
-  return 0;
-}
-
-// in / out: [B][H][H][Ch] 16-bit (token layout; bf16, or fp16 when f16 != 0), wt_half: [9][Ch] fp32 tap-major,
-// bias_half: [Ch] fp32 - BOTH PRE-MULTIPLIED BY 0.5 (uformer_plan.cu pack_block), see gelu_tanh2_half_arg.
+// in / out: [B][H][H][Ch] 16-bit (token layout): bf16 (f16 = 0) or fp16 (f16 = 1) with wt / bias [9][Ch] / [Ch] fp32 BOTH
+// PRE-MULTIPLIED BY 0.5 (uformer_plan.cu pack_block, gelu_tanh2_half_arg); f16 = 2: fp16 tensors, plain wt / bias and the
+// erf-form GELU (the precise extractor).
 int dwconv3x3_gelu_op16(const void* in, void* out, const float* wt, const float* bias, int B, int H, int Ch, int f16,
                         cudaStream_t st) {
   WMK_REQUIRE(H >= 8 && (H & (H - 1)) == 0 && Ch >= 64 && (Ch & (Ch - 1)) == 0,
               "dwconv: H=%d must be a power of two >= 8 and Ch=%d a power of two >= 64", H, Ch);
   WMK_REQUIRE(((uintptr_t)in & 15) == 0 && ((uintptr_t)out & 15) == 0, "dwconv: buffers must be 16-byte aligned");
   static const int one_col = getenv("WMK_DW_ONECOL") ? atoi(getenv("WMK_DW_ONECOL")) : 0;
+  if (f16 == 2) {        // fp16 tensors, erf-form GELU, wt / bias NOT pre-halved (the precise extractor)
+    if (H % 16 == 0) return launch_dw2<true, true>(in, out, wt, bias, B, H, Ch, st);
+    return launch_dw<8, true, true>(in, out, wt, bias, B, H, Ch, st);
+  }
   if (f16) {
     if (H % 16 == 0 && !one_col) return launch_dw2<true>(in, out, wt, bias, B, H, Ch, st);
     if (H % 16 == 0) return launch_dw<16, true>(in, out, wt, bias, B, H, Ch, st);

@@ -192,7 +192,7 @@ __host__ __device__ constexpr int epi_box_cols(int bn, bool out_bf16, bool ln) {
 // LN = true (EPI_BIAS_RESID, BN <= 128, n_tiles == 1): the epilogue also LayerNorms the finished row and writes
 // it as bf16 through tmD - the operand of the next dense layer.  The SLABS warps that share a lane quarter
 // exchange their partial (sum, sum of squares) through shared memory and a named barrier.
-constexpr uint32_t STG2_BYTES = 2048;                       // bf16 staging box of the fused LayerNorm: 32 rows x 64 B
+constexpr uint32_t STG2_BYTES = 2048;                       // 16-bit staging box of the fused LayerNorm: 32 rows x 64 B (two of them for split rows)
 constexpr uint32_t LN_EXCH_BYTES = 2 * kEpiWarps * 32 * 8;  // [tile parity][slab][quarter][lane] float2
 
 template <int BN, int EPI, bool OUT_BF16, bool LN = false>
@@ -209,23 +209,21 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __
   const uint32_t base = (raw + 1023u) & ~1023u;
   constexpr uint32_t A_BYTES = BM * BK * 2;
   constexpr uint32_t W_BYTES = BN * BK * 2;
-  // k-block schedule.  Plain: k-block kb = columns kb*64 of A and W.  Split-bf16 (p.split = 1, K % 64 == 0): every
-  // logical k-block kk runs as three (A tile, W tile) pairs - (hi, hi), (lo, hi), (hi, lo) - where A rows are
-  // [hi(K) | lo(K)] and W rows [hi(K) | lo(K)]; p.split = 2 (K == 32): A rows [hi | lo] are ONE 64-wide tile, used
-  // against W tile 0 = [hi | hi] and W tile 1 = [lo | 0] (two k-steps).
+  // k-block schedule.  Plain: k-block kb = columns kb*64 of A and W, one A tile (+ one W tile) per stage.
+  // Split-bf16 (p.split = 1, K % 64 == 0): A rows are [hi(K) | lo(K)], W rows [hi(K) | lo(K)]; a stage holds BOTH
+  // A tiles (and both W tiles) of a logical k-block - each fetched once - and the issuer runs the three MMA groups
+  // hi*hi, lo*hi, hi*lo on it.  p.split = 2 (K == 32): A rows [hi | lo] are ONE 64-wide tile, used against W tile
+  // 0 = [hi | hi] (four k-steps) and W tile 1 = [lo | 0] (two k-steps).
+  // p.split = 3 (W-only split, fp16): A is plain [M][K], W rows [hi(K) | lo(K)]: one A tile, two W tiles per stage, MMA
+  // groups A*hi, A*lo.  p.split = 4 (the same, K == 32): W rows [hi(32) | lo(32)] are ONE tile; the zero-filled upper half
+  // of the A tile is never read: k-steps 0-1 of A run against k-steps 0-1 (hi) and 2-3 (lo) of W.
   const int KB = (K + BK - 1) / BK;
   const int split = p.split;
-  const int kblocks = split == 1 ? 3 * KB : split == 2 ? 2 : KB;     // (A, W) tile pairs per output tile
-  const int wblocks = split == 1 ? 2 * KB : split == 2 ? 2 : KB;     // distinct W tiles
-  auto a_col = [&](int kb) -> int {
-    if (split == 1) { const int kk = kb / 3, seg = kb - 3 * kk; return (seg == 1 ? K : 0) + kk * BK; }
-    return split == 2 ? 0 : kb * BK;
-  };
-  auto w_idx = [&](int kb) -> int {
-    if (split == 1) { const int kk = kb / 3, seg = kb - 3 * kk; return (seg == 2 ? KB : 0) + kk; }
-    return kb;
-  };
-  const uint32_t STAGE = w_stationary ? A_BYTES : A_BYTES + W_BYTES;
+  const int kblocks = split == 2 ? 1 : KB;                            // stages per output tile
+  const int wblocks = (split == 1 || split == 3) ? 2 * KB : split == 2 ? 2 : KB;     // distinct W tiles (hi tiles first, then lo)
+  const uint32_t A_STAGE = split == 1 ? 2 * A_BYTES : A_BYTES;
+  const uint32_t W_STAGE = (split >= 1 && split <= 3) ? 2 * W_BYTES : W_BYTES;
+  const uint32_t STAGE = w_stationary ? A_STAGE : A_STAGE + W_STAGE;
   const uint32_t wres = base;                                // resident weights: wblocks x W_BYTES
   const uint32_t stages = base + (w_stationary ? (uint32_t)wblocks * W_BYTES : 0u);
   // one staging box per epilogue warp: 32 rows x <= 128 B (bf16 output may use 64-byte rows, p.boxc = 32, when
@@ -233,8 +231,9 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __
   const int BOXC = OUT_BF16 ? p.boxc : 32;
   const uint32_t STG_BYTES = OUT_BF16 ? 64u * (uint32_t)BOXC : 4096u;
   const uint32_t staging = stages + (uint32_t)n_stages * STAGE;          // [16 warps][STG_BYTES]
-  const uint32_t staging2 = staging + kEpiWarps * STG_BYTES;             // LN: [16 warps][2048] + exchange
-  const uint32_t ln_exch = staging2 + kEpiWarps * STG2_BYTES;
+  const uint32_t stg2 = p.ln_split ? 2 * STG2_BYTES : STG2_BYTES;
+  const uint32_t staging2 = staging + kEpiWarps * STG_BYTES;             // LN: [16 warps][2048 (x 2: hi, lo)] + exchange
+  const uint32_t ln_exch = staging2 + kEpiWarps * stg2;
   const uint32_t bars = LN ? ln_exch + LN_EXCH_BYTES : staging + kEpiWarps * STG_BYTES;
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (n_stages + s); };
@@ -318,16 +317,27 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __
           if (p.conv_H > 0) {          // implicit GEMM: tap kb of the 3x3 window = the image row shifted by (dy-1, dx-1)
             const int rowi = m0 >> 7, img = rowi / p.conv_H, h = rowi - img * p.conv_H;
             tma_load_4d(sa, &tmA, 0, kb % 3 - 1, h + kb / 3 - 1, img, full_bar(s));
+          } else if (split == 1) {
+            tma_load_2d(sa, &tmA, kb * BK, m0, full_bar(s));                       // hi
+            tma_load_2d(sa + A_BYTES, &tmA, K + kb * BK, m0, full_bar(s));         // lo
+            if (!w_stationary) {
+              tma_load_2d(sa + A_STAGE, &tmW, kb * BK, n0, full_bar(s));
+              tma_load_2d(sa + A_STAGE + W_BYTES, &tmW, K + kb * BK, n0, full_bar(s));
+            }
           } else {
-            tma_load_2d(sa, &tmA, a_col(kb), m0, full_bar(s));
+            tma_load_2d(sa, &tmA, kb * BK, m0, full_bar(s));
+            if (!w_stationary) {
+              tma_load_2d(sa + A_STAGE, &tmW, kb * BK, n0, full_bar(s));
+              if (split == 2) tma_load_2d(sa + A_STAGE + W_BYTES, &tmW, BK, n0, full_bar(s));
+              if (split == 3) tma_load_2d(sa + A_STAGE + W_BYTES, &tmW, K + kb * BK, n0, full_bar(s));
+            }
           }
-          if (!w_stationary) tma_load_2d(sa + A_BYTES, &tmW, w_idx(kb) * BK, n0, full_bar(s));
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc(BN, p.f16 != 0 && split == 0);      // split operands are bf16 by construction
+      const uint32_t idesc = umma_idesc(BN, p.f16 != 0 && (split == 0 || split >= 3));   // fully split operands are bf16 by construction
       int it = 0, m0, n0;
       if (w_stationary && tile_at(0, m0, n0)) mbar_wait(wfull_bar, 0);
       for (int lt = 0; tile_at(lt, m0, n0); ++lt) {
@@ -342,11 +352,51 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __
           tcgen05_fence_after();
           const uint32_t sa = stages + (uint32_t)s * STAGE;
           const uint64_t adesc = umma_desc_sw128(sa);
-          const uint64_t bdesc = umma_desc_sw128(w_stationary ? wres + (uint32_t)w_idx(kb) * W_BYTES : sa + A_BYTES);
-          const int krem = split == 1 ? BK : split == 2 ? (kb == 0 ? 64 : 32) : K - kb * BK;
-          const int ksteps = krem >= BK ? BK / UMMA_K : (krem + UMMA_K - 1) / UMMA_K;   // skip zero-filled K
-          for (int k = 0; k < ksteps; ++k)
-            tcgen05_mma_bf16(tacc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+          if (split == 0) {
+            const uint64_t bdesc = umma_desc_sw128(w_stationary ? wres + (uint32_t)kb * W_BYTES : sa + A_STAGE);
+            const int krem = K - kb * BK;
+            const int ksteps = krem >= BK ? BK / UMMA_K : (krem + UMMA_K - 1) / UMMA_K;   // skip zero-filled K
+            for (int k = 0; k < ksteps; ++k)
+              tcgen05_mma_bf16(tacc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+          } else {
+            // W tile 0 / 1 of this k-block: hi / lo (split 1), [hi | hi] / [lo | 0] (split 2)
+            const uint64_t w0 = umma_desc_sw128(w_stationary ? wres + (uint32_t)kb * W_BYTES : sa + A_STAGE);
+            const uint64_t w1 = umma_desc_sw128(w_stationary ? wres + (uint32_t)((split == 2 ? 1 : KB) + kb) * W_BYTES
+                                                             : sa + A_STAGE + W_BYTES);
+            if (split == 3) {
+#pragma unroll
+              for (int k = 0; k < BK / UMMA_K; ++k)     // A * hi
+                tcgen05_mma_bf16(tacc, adesc + (uint64_t)(2 * k), w0 + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+#pragma unroll
+              for (int k = 0; k < BK / UMMA_K; ++k)     // A * lo
+                tcgen05_mma_bf16(tacc, adesc + (uint64_t)(2 * k), w1 + (uint64_t)(2 * k), idesc, 1u);
+            } else if (split == 4) {
+#pragma unroll
+              for (int k = 0; k < 2; ++k)               // A[0:32] * hi
+                tcgen05_mma_bf16(tacc, adesc + (uint64_t)(2 * k), w0 + (uint64_t)(2 * k), idesc, (uint32_t)(k != 0));
+#pragma unroll
+              for (int k = 0; k < 2; ++k)               // A[0:32] * lo (W columns 32..63)
+                tcgen05_mma_bf16(tacc, adesc + (uint64_t)(2 * k), w0 + (uint64_t)(2 * (k + 2)), idesc, 1u);
+            } else if (split == 1) {
+              const uint64_t alo = umma_desc_sw128(sa + A_BYTES);
+#pragma unroll
+              for (int k = 0; k < BK / UMMA_K; ++k)     // hi * hi
+                tcgen05_mma_bf16(tacc, adesc + (uint64_t)(2 * k), w0 + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+#pragma unroll
+              for (int k = 0; k < BK / UMMA_K; ++k)     // lo * hi
+                tcgen05_mma_bf16(tacc, alo + (uint64_t)(2 * k), w0 + (uint64_t)(2 * k), idesc, 1u);
+#pragma unroll
+              for (int k = 0; k < BK / UMMA_K; ++k)     // hi * lo
+                tcgen05_mma_bf16(tacc, adesc + (uint64_t)(2 * k), w1 + (uint64_t)(2 * k), idesc, 1u);
+            } else {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)               // [hi | lo] * [hi | hi]
+                tcgen05_mma_bf16(tacc, adesc + (uint64_t)(2 * k), w0 + (uint64_t)(2 * k), idesc, (uint32_t)(k != 0));
+#pragma unroll
+              for (int k = 0; k < 2; ++k)               // hi * lo
+                tcgen05_mma_bf16(tacc, adesc + (uint64_t)(2 * k), w1 + (uint64_t)(2 * k), idesc, 1u);
+            }
+          }
           tcgen05_commit(empty_bar(s));
         }
         tcgen05_commit(tfull_bar + 8u * acc);
@@ -535,16 +585,36 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __
                   f[4 * j] += mm.x; f[4 * j + 1] += mm.y; f[4 * j + 2] += mm.z; f[4 * j + 3] += mm.w;
                 }
               }
-              const uint32_t buf2 = staging2 + (uint32_t)ew * STG2_BYTES;     // free: every earlier store was waited for above
+              const uint32_t buf2 = staging2 + (uint32_t)ew * stg2;           // free: every earlier store was waited for above
+              if (p.ln_split) {                               // rows [hi(N) | lo(N)]: two boxes
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                uint32_t w0, w1, w2, w3;
-                pack8_16(f + 8 * j, p.f16 != 0, w0, w1, w2, w3);
-                st_shared_v4(buf2 + (uint32_t)lane * 64u + ((((uint32_t)j) ^ ((uint32_t)(lane >> 1) & 3u)) << 4), w0, w1, w2, w3);
+                for (int j = 0; j < 4; ++j) {
+                  uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
+                  split_pack2(f[8 * j], f[8 * j + 1], h0, l0);
+                  split_pack2(f[8 * j + 2], f[8 * j + 3], h1, l1);
+                  split_pack2(f[8 * j + 4], f[8 * j + 5], h2, l2);
+                  split_pack2(f[8 * j + 6], f[8 * j + 7], h3, l3);
+                  const uint32_t off = (uint32_t)lane * 64u + ((((uint32_t)j) ^ ((uint32_t)(lane >> 1) & 3u)) << 4);
+                  st_shared_v4(buf2 + off, h0, h1, h2, h3);
+                  st_shared_v4(buf2 + STG2_BYTES + off, l0, l1, l2, l3);
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {
+                  tma_store_2d(&tmD, buf2, n, m0 + q * 32);
+                  tma_store_2d(&tmD, buf2 + STG2_BYTES, BN + n, m0 + q * 32);
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  uint32_t w0, w1, w2, w3;
+                  pack8_16(f + 8 * j, p.f16 != 0, w0, w1, w2, w3);
+                  st_shared_v4(buf2 + (uint32_t)lane * 64u + ((((uint32_t)j) ^ ((uint32_t)(lane >> 1) & 3u)) << 4), w0, w1, w2, w3);
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) tma_store_2d(&tmD, buf2, n, m0 + q * 32);
               }
-              asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-              __syncwarp();
-              if (lane == 0) tma_store_2d(&tmD, buf2, n, m0 + q * 32);
             }
           }
         }
@@ -662,11 +732,13 @@ int launch_persistent_t(const GemmArgs& g, cudaStream_t st) {
   } else {
     WMK_TRY(make_map(&tmA, g.A, g.M, g.split ? 2 * g.K : g.K, BM));
   }
-  const int split_mode = !g.split ? 0 : (g.K == 32 ? 2 : 1);
-  WMK_TRY(make_map(&tmW, g.W, g.N, split_mode == 2 ? 128 : split_mode == 1 ? 2 * g.K : g.K, BN));
+  const int split_mode = g.split ? (g.K == 32 ? 2 : 1) : g.wsplit ? (g.K == 32 ? 4 : 3) : 0;
+  WMK_TRY(make_map(&tmW, g.W, g.N, split_mode == 2 ? 128 : split_mode == 0 ? g.K : 2 * g.K, BN));
   const int KBl = cdiv(g.K, BK);
-  const int kblocks = split_mode == 1 ? 3 * KBl : split_mode == 2 ? 2 : KBl;       // (A, W) tile pairs per output tile
-  const int wblocks = split_mode == 1 ? 2 * KBl : split_mode == 2 ? 2 : KBl;       // distinct W tiles
+  const int kblocks = split_mode == 2 ? 1 : KBl;                                   // stages per output tile
+  const int wblocks = (split_mode == 1 || split_mode == 3) ? 2 * KBl : split_mode == 2 ? 2 : KBl;       // distinct W tiles
+  const int a_stage = (split_mode == 1 ? 2 : 1) * BM * BK * 2;
+  const int w_stage = ((split_mode >= 1 && split_mode <= 3) ? 2 : 1) * BN * BK * 2;
   constexpr int budget = 226 * 1024;
   const int n_tiles = g.N / BN, m_tiles = cdiv(g.M, BM);
   const int w_bytes = wblocks * BN * BK * 2;
@@ -674,11 +746,11 @@ int launch_persistent_t(const GemmArgs& g, cudaStream_t st) {
   size_t smem = 0;
   for (;;) {
     const int stg = OUT_BF16 ? 64 * boxc : 4096;
-    const int fixed = kEpiWarps * stg + 1024 + 512 + (LN ? (int)(kEpiWarps * STG2_BYTES + LN_EXCH_BYTES) : 0);
+    const int fixed = kEpiWarps * stg + 1024 + 512 + (LN ? (int)(kEpiWarps * STG2_BYTES * (g.ln_split ? 2 : 1) + LN_EXCH_BYTES) : 0);
     // weight-stationary when the whole BN x K tile + >= 2 A stages fit and every N tile gets >= 1 CTA
-    ws = (g.conv_H == 0 && wblocks <= (split_mode ? 8 : 4) && w_bytes + 2 * BM * BK * 2 + fixed <= budget && n_tiles <= num_sms() &&
+    ws = (g.conv_H == 0 && wblocks <= (split_mode ? 8 : 4) && w_bytes + 2 * a_stage + fixed <= budget && n_tiles <= num_sms() &&
           m_tiles >= 2 * (num_sms() / n_tiles)) ? 1 : 0;
-    const int stage = ws ? BM * BK * 2 : (BM + BN) * BK * 2;
+    const int stage = ws ? a_stage : a_stage + w_stage;
     const int avail = budget - fixed - (ws ? w_bytes : 0);
     n_stages = ws ? 6 : (kblocks < 6 ? (kblocks < 2 ? 2 : kblocks) : 6);
     while (n_stages > 2 && n_stages * stage > avail) --n_stages;
@@ -689,7 +761,7 @@ int launch_persistent_t(const GemmArgs& g, cudaStream_t st) {
     break;
   }
   WMK_TRY(make_map_ex(&tmC, g.C, g.M, g.ldc, 32, boxc, !OUT_BF16));
-  if (LN) WMK_TRY(make_map_ex(&tmD, g.ln_out, g.M, g.N, 32, 32, false));
+  if (LN) WMK_TRY(make_map_ex(&tmD, g.ln_out, g.M, g.ln_split ? 2 * g.N : g.N, 32, 32, false));
   else tmD = tmC;
   CUtensorMap tmR = tmC;                                   // residual tiles (fp32, same geometry as C; usually C itself)
   if (EPI == EPI_BIAS_RESID && g.resid && (const void*)g.resid != (const void*)g.C)
@@ -709,7 +781,8 @@ int launch_persistent_t(const GemmArgs& g, cudaStream_t st) {
   p.gelu_half = g.gelu_half;
   p.gelu_exact = g.gelu_exact;
   p.split = split_mode;
-  p.f16 = g.f16;
+  p.f16 = g.f16 || g.wsplit;
+  p.ln_split = g.ln_split;
 
   const long long total = (long long)m_tiles * n_tiles;
   const int grid = ws ? (num_sms() / n_tiles) * n_tiles : (int)(total < num_sms() ? total : num_sms());
@@ -785,9 +858,9 @@ int gemm_bf16_tcgen05(const GemmArgs& g, cudaStream_t st) {
   if (g.conv_H > 0)
     WMK_REQUIRE(g.K == 576 && g.M == g.conv_B * g.conv_H * 128 && g.ldc == g.N && g.epi != EPI_UPSAMPLE,
                 "gemm_bf16: implicit-GEMM conv needs K = 576 and M = B*H*128 (W = 128)");
-  if (g.split)
-    WMK_REQUIRE((g.K == 32 || g.K % 64 == 0) && !g.out_bf16 && g.conv_H == 0 && g.epi != EPI_UPSAMPLE && g.ldc == g.N && !g.ln_out,
-                "gemm_bf16: split-bf16 operands need K = 32 or K %% 64 == 0 (K = %d), fp32 output, a plain row-major C", g.K);
+  if (g.split || g.wsplit)
+    WMK_REQUIRE((g.K == 32 || g.K % 64 == 0) && g.conv_H == 0 && g.epi != EPI_UPSAMPLE && g.ldc == g.N && !(g.split && g.wsplit),
+                "gemm_bf16: split operands need K = 32 or K %% 64 == 0 (K = %d) and a plain row-major C", g.K);
   if (g.epi == EPI_UPSAMPLE)
     WMK_REQUIRE(g.up_cout % 32 == 0 && g.N == 4 * g.up_cout && g.M % (g.up_h * g.up_w) == 0,
                 "gemm_bf16: bad upsample geometry");

@@ -19,7 +19,7 @@ struct InProjW { float w[32 * 18]; float b[32]; float ln_g[32]; float ln_b[32]; 
 
 __global__ void __launch_bounds__(128)
 input_proj_kernel(const float* __restrict__ x, float* __restrict__ out, const __grid_constant__ InProjW W, int B,
-                  uint16_t* __restrict__ ln_out, int ln_f16) {
+                  uint16_t* __restrict__ ln_out, int ln_fmt) {       // ln_fmt: 0 bf16, 1 fp16, 2 split-bf16 rows [hi(32) | lo(32)]
   __shared__ __align__(16) float4 stage[128 * 8];            // [pixel][8 float4], chunk index XOR (pixel & 7)
   const size_t pix0 = (size_t)blockIdx.x * blockDim.x;
   const size_t pix = pix0 + threadIdx.x;
@@ -59,18 +59,20 @@ input_proj_kernel(const float* __restrict__ x, float* __restrict__ out, const __
 #pragma unroll
       for (int c = 0; c < 32; ++c) { const float d = v[c] - mean; var = fmaf(d, d, var); }
       const float rstd = rsqrtf(var * (1.0f / 32) + 1e-5f);
-      uint4* o4 = reinterpret_cast<uint4*>(ln_out + pix * 32);
+      uint4* o4 = reinterpret_cast<uint4*>(ln_out + pix * (ln_fmt == 2 ? 64 : 32));
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        uint32_t pk[4];
+        uint32_t pk[4], lo[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int c = q * 8 + 2 * e;
           const float a0 = fmaf((v[c] - mean) * rstd, W.ln_g[c], W.ln_b[c]);
           const float a1 = fmaf((v[c + 1] - mean) * rstd, W.ln_g[c + 1], W.ln_b[c + 1]);
-          pk[e] = ln_f16 ? pack2_f16(a0, a1) : pack2_bf16(a0, a1);
+          if (ln_fmt == 2) split_pack2(a0, a1, pk[e], lo[e]);
+          else pk[e] = ln_fmt == 1 ? pack2_f16(a0, a1) : pack2_bf16(a0, a1);
         }
         o4[q] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        if (ln_fmt == 2) o4[4 + q] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
       }
     }
   }

@@ -296,7 +296,8 @@ constexpr float kLog2e = 1.4426950408889634f;
 constexpr int ATT_BLD = 72;    // bf16 elements per bias row in smem (144 B: conflict-free ldmatrix)
 
 // F16: q / k / v / out (and the in-kernel bias and probability fragments) are IEEE fp16 instead of bf16.
-template <bool F16>
+// SPLIT_OUT: the output rows are split-bf16 [hi(C) | lo(C)] (the A operand of a split projection; the precise extractor).
+template <bool F16, bool SPLIT_OUT = false>
 static __global__ void __launch_bounds__(128)
 window_attention_mma_kernel(const uint16_t* __restrict__ qkv, uint16_t* __restrict__ out,
                             const float* __restrict__ bias, int C, int H, int shift, int n_windows) {
@@ -447,237 +448,41 @@ window_attention_mma_kernel(const uint16_t* __restrict__ qkv, uint16_t* __restri
     }
     // ---- stage O (this warp's 16 rows) in the Q tile, then 16-byte stores to the token rows
     __syncwarp();
+    if constexpr (SPLIT_OUT) {
 #pragma unroll
-    for (int n = 0; n < 4; ++n) {
-      *reinterpret_cast<uint32_t*>(Qs + row0 * ATT_LD + n * 8 + 2 * t) = pack2_16<F16>(oacc[n][0] * inv0, oacc[n][1] * inv0);
-      *reinterpret_cast<uint32_t*>(Qs + row1 * ATT_LD + n * 8 + 2 * t) = pack2_16<F16>(oacc[n][2] * inv1, oacc[n][3] * inv1);
-    }
-    __syncwarp();
+      for (int part = 0; part < 2; ++part) {       // hi rows, then lo rows, through the same staging rows
 #pragma unroll
-    for (int e = lane; e < 64; e += 32) {
-      const int r = r0 + (e >> 2), ch = e & 3;
-      const uint4 v = *reinterpret_cast<const uint4*>(Qs + r * ATT_LD + ch * 8);
-      *reinterpret_cast<uint4*>(out + (size_t)tok[r] * C + head * 32 + ch * 8) = v;
+        for (int n = 0; n < 4; ++n) {
+          uint32_t h0, l0, h1, l1;
+          split_pack2(oacc[n][0] * inv0, oacc[n][1] * inv0, h0, l0);
+          split_pack2(oacc[n][2] * inv1, oacc[n][3] * inv1, h1, l1);
+          *reinterpret_cast<uint32_t*>(Qs + row0 * ATT_LD + n * 8 + 2 * t) = part ? l0 : h0;
+          *reinterpret_cast<uint32_t*>(Qs + row1 * ATT_LD + n * 8 + 2 * t) = part ? l1 : h1;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int e = lane; e < 64; e += 32) {
+          const int r = r0 + (e >> 2), ch = e & 3;
+          const uint4 v = *reinterpret_cast<const uint4*>(Qs + r * ATT_LD + ch * 8);
+          *reinterpret_cast<uint4*>(out + (size_t)tok[r] * (2 * C) + part * C + head * 32 + ch * 8) = v;
+        }
+        __syncwarp();
+      }
+    } else {
+#pragma unroll
+      for (int n = 0; n < 4; ++n) {
+        *reinterpret_cast<uint32_t*>(Qs + row0 * ATT_LD + n * 8 + 2 * t) = pack2_16<F16>(oacc[n][0] * inv0, oacc[n][1] * inv0);
+        *reinterpret_cast<uint32_t*>(Qs + row1 * ATT_LD + n * 8 + 2 * t) = pack2_16<F16>(oacc[n][2] * inv1, oacc[n][3] * inv1);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int e = lane; e < 64; e += 32) {
+        const int r = r0 + (e >> 2), ch = e & 3;
+        const uint4 v = *reinterpret_cast<const uint4*>(Qs + r * ATT_LD + ch * 8);
+        *reinterpret_cast<uint4*>(out + (size_t)tok[r] * C + head * 32 + ch * 8) = v;
+      }
     }
     __syncthreads();        // everyone is done with this buffer before it is refilled
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// Split-bf16 window attention (the WMK_PREC_MIXED extractor): the math and addressing of
-// window_attention_mma_kernel with every tensor-core product carried as hi*hi + lo*hi + hi*lo
-// (operands hi = bf16(v), lo = bf16(v - hi): 16 mantissa bits, fp32 accumulate), so the scores, the
-// probabilities and the output keep fp32-class accuracy (measured logit error of the whole extractor
-// ~4e-6 against 2e-3 for plain bf16 operands).
-// qkv: fp32 [tokens][3C] (the QKV projection writes fp32 in this mode); bias: fp32 [heads][64][64]
-// with log2(e) folded in; out: split rows [tokens][hi(C) | lo(C)] = the A operand of the projection.
-// Per window: cp.async of the fp32 q / k / v tiles (double buffered) -> one conversion pass into the
-// six bf16 tiles ldmatrix reads -> S = I Bh + I Bl + Qh Kh^T + Ql Kh^T + Qh Kl^T -> fp32 softmax
-// (exp2) -> O = Ph Vh + Pl Vh + Ph Vl.
-// ------------------------------------------------------------------------------------------
-constexpr int ATTS_STAGE_F = 3 * 64 * 32;      // floats per staging buffer: the q, k, v tiles of one window
-constexpr int ATTS_SMEM = 2 * ATTS_STAGE_F * 4 + 6 * ATT_TILE * 2 + 2 * 64 * ATT_BLD * 2 + 4 * 64 * 4;
-
-static __global__ void __launch_bounds__(128)
-window_attention_split_kernel(const float* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
-                              const float* __restrict__ bias, int C, int H, int shift, int n_windows) {
-  extern __shared__ __align__(16) uint8_t att_smem[];
-  float* stage = reinterpret_cast<float*>(att_smem);                                          // [2][3][64][32] fp32
-  __nv_bfloat16* tiles = reinterpret_cast<__nv_bfloat16*>(att_smem + 2 * ATTS_STAGE_F * 4);   // q_hi k_hi v_hi q_lo k_lo v_lo
-  __nv_bfloat16* sbias = tiles + 6 * ATT_TILE;                                                // [hi, lo][64][ATT_BLD]
-  int* s_tok = reinterpret_cast<int*>(sbias + 2 * 64 * ATT_BLD);                              // [2][64]
-  int* s_rid = s_tok + 128;                                                                   // [2][64]
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  AttGeom g{C, H, shift, 31 - __clz(C >> 5), 31 - __clz(H >> 3)};
-  const int heads = C >> 5;
-  const int head = blockIdx.x & (heads - 1);
-  const int wstep = gridDim.x >> g.lg_heads;
-  const int nws_mask = (1 << g.lg_nws) - 1;
-
-  auto prefetch = [&](int win, int buf) {
-    if (tid < 64) {
-      int t, r;
-      att_row(g, win, tid, t, r);
-      s_tok[buf * 64 + tid] = t;
-      s_rid[buf * 64 + tid] = r;
-    }
-    // 3 tiles x 64 rows x 8 sixteen-byte chunks = 1536 chunks, 12 per thread
-#pragma unroll
-    for (int i = 0; i < 12; ++i) {
-      const int e = tid + 128 * i;
-      const int which = e >> 9, row = (e >> 3) & 63, c4 = e & 7;
-      int t, r;
-      att_row(g, win, row, t, r);
-      const float* src = qkv + (size_t)t * (3 * C) + which * C + head * 32 + c4 * 4;
-      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(stage + buf * ATTS_STAGE_F + e * 4);
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  };
-
-  int win = blockIdx.x >> g.lg_heads;
-  if (win >= n_windows) return;
-  prefetch(win, 0);
-  {
-    const float* bh = bias + (size_t)head * 4096;
-    for (int e = tid; e < 2048; e += 128) {
-      const float2 v = __ldg(reinterpret_cast<const float2*>(bh) + e);
-      uint32_t hi, lo;
-      split_pack2(v.x, v.y, hi, lo);
-      *reinterpret_cast<uint32_t*>(&sbias[(e >> 5) * ATT_BLD + (e & 31) * 2]) = hi;
-      *reinterpret_cast<uint32_t*>(&sbias[64 * ATT_BLD + (e >> 5) * ATT_BLD + (e & 31) * 2]) = lo;
-    }
-  }
-  const int gq = lane >> 2, t = lane & 3;
-  const uint32_t ident = pack_bf16(gq == 2 * t ? 1.f : 0.f, gq == 2 * t + 1 ? 1.f : 0.f);
-  const uint32_t aI[4] = {ident, 0u, 0u, ident};
-  const uint32_t bs_addr = (uint32_t)__cvta_generic_to_shared(sbias);
-  const uint32_t qh = (uint32_t)__cvta_generic_to_shared(tiles);
-  const uint32_t kh = qh + 2u * ATT_TILE, vh = qh + 4u * ATT_TILE;
-  const uint32_t ql = qh + 6u * ATT_TILE, kl = qh + 8u * ATT_TILE, vl = qh + 10u * ATT_TILE;
-  for (int it = 0; win < n_windows; win += wstep, ++it) {
-    const int buf = it & 1;
-    const int next = win + wstep;
-    if (next < n_windows) {
-      prefetch(next, buf ^ 1);
-      asm volatile("cp.async.wait_group 1;" ::: "memory");
-    } else {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-    }
-    __syncthreads();
-    // ---- fp32 staging -> hi / lo bf16 tiles (row stride ATT_LD)
-#pragma unroll
-    for (int i = 0; i < 12; ++i) {
-      const int e = tid + 128 * i;
-      const int which = e >> 9, row = (e >> 3) & 63, c4 = e & 7;
-      const float4 v = *reinterpret_cast<const float4*>(stage + buf * ATTS_STAGE_F + e * 4);
-      uint2 h2, l2;
-      split_pack2(v.x, v.y, h2.x, l2.x);
-      split_pack2(v.z, v.w, h2.y, l2.y);
-      *reinterpret_cast<uint2*>(tiles + which * ATT_TILE + row * ATT_LD + c4 * 4) = h2;
-      *reinterpret_cast<uint2*>(tiles + (3 + which) * ATT_TILE + row * ATT_LD + c4 * 4) = l2;
-    }
-    __syncthreads();
-    const int* tok = s_tok + buf * 64;
-    const int* rid = s_rid + buf * 64;
-    const int r0 = warp * 16;
-    // ---- S = I * (Bias_hi + Bias_lo)
-    float sacc[8][4];
-#pragma unroll
-    for (int n = 0; n < 8; ++n) { sacc[n][0] = sacc[n][1] = sacc[n][2] = sacc[n][3] = 0.f; }
-#pragma unroll
-    for (int part = 0; part < 2; ++part) {
-#pragma unroll
-      for (int np = 0; np < 4; ++np) {
-        uint32_t bb[4];
-        ldmatrix_x4_trans(bb, bs_addr + 2u * (part * 64 * ATT_BLD + (r0 + (lane & 7) + ((lane >> 3) & 1) * 8) * ATT_BLD + np * 16 + (lane >> 4) * 8));
-        mma_bf16_16816(sacc[2 * np], aI, bb[0], bb[1]);
-        mma_bf16_16816(sacc[2 * np + 1], aI, bb[2], bb[3]);
-      }
-    }
-    // ---- S += Qh Kh^T + Ql Kh^T + Qh Kl^T
-#pragma unroll
-    for (int kk = 0; kk < 2; ++kk) {
-      uint32_t ah[4], al[4];
-      const uint32_t aoff = 2u * ((r0 + (lane & 7) + ((lane >> 3) & 1) * 8) * ATT_LD + kk * 16 + (lane >> 4) * 8);
-      ldmatrix_x4(ah, qh + aoff);
-      ldmatrix_x4(al, ql + aoff);
-#pragma unroll
-      for (int np = 0; np < 4; ++np) {
-        uint32_t bh4[4], bl4[4];
-        const uint32_t boff = 2u * ((np * 16 + (lane & 7) + (lane >> 4) * 8) * ATT_LD + kk * 16 + ((lane >> 3) & 1) * 8);
-        ldmatrix_x4(bh4, kh + boff);
-        ldmatrix_x4(bl4, kl + boff);
-        mma_bf16_16816(sacc[2 * np], ah, bh4[0], bh4[1]);
-        mma_bf16_16816(sacc[2 * np + 1], ah, bh4[2], bh4[3]);
-        mma_bf16_16816(sacc[2 * np], al, bh4[0], bh4[1]);
-        mma_bf16_16816(sacc[2 * np + 1], al, bh4[2], bh4[3]);
-        mma_bf16_16816(sacc[2 * np], ah, bl4[0], bl4[1]);
-        mma_bf16_16816(sacc[2 * np + 1], ah, bl4[2], bl4[3]);
-      }
-    }
-    // ---- shift mask, softmax (log2 domain)
-    const int row0 = r0 + gq, row1 = row0 + 8;
-    const int wrem = win & ((1 << (2 * g.lg_nws)) - 1);
-    const bool edge = shift > 0 && (((wrem >> g.lg_nws) == nws_mask) || ((wrem & nws_mask) == nws_mask));
-    float m0 = -INFINITY, m1 = -INFINITY;
-    if (edge) {
-      const int rid0 = rid[row0], rid1 = rid[row1];
-#pragma unroll
-      for (int n = 0; n < 8; ++n) {
-        const int col = n * 8 + 2 * t;
-        const int c0 = rid[col], c1 = rid[col + 1];
-        if (c0 != rid0) sacc[n][0] -= 100.0f * kLog2e;
-        if (c1 != rid0) sacc[n][1] -= 100.0f * kLog2e;
-        if (c0 != rid1) sacc[n][2] -= 100.0f * kLog2e;
-        if (c1 != rid1) sacc[n][3] -= 100.0f * kLog2e;
-      }
-    }
-#pragma unroll
-    for (int n = 0; n < 8; ++n) {
-      m0 = fmaxf(m0, fmaxf(sacc[n][0], sacc[n][1]));
-      m1 = fmaxf(m1, fmaxf(sacc[n][2], sacc[n][3]));
-    }
-    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
-    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
-    float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-    for (int n = 0; n < 8; ++n) {
-      sacc[n][0] = exp2f(sacc[n][0] - m0); sacc[n][1] = exp2f(sacc[n][1] - m0);
-      sacc[n][2] = exp2f(sacc[n][2] - m1); sacc[n][3] = exp2f(sacc[n][3] - m1);
-      s0 += sacc[n][0] + sacc[n][1];
-      s1 += sacc[n][2] + sacc[n][3];
-    }
-    s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
-    s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
-    const float inv0 = 1.0f / s0, inv1 = 1.0f / s1;
-    // ---- O = Ph Vh + Pl Vh + Ph Vl
-    float oacc[4][4];
-#pragma unroll
-    for (int n = 0; n < 4; ++n) { oacc[n][0] = oacc[n][1] = oacc[n][2] = oacc[n][3] = 0.f; }
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-      uint32_t ah[4], al[4];
-      split_pack2(sacc[2 * kk][0], sacc[2 * kk][1], ah[0], al[0]);
-      split_pack2(sacc[2 * kk][2], sacc[2 * kk][3], ah[1], al[1]);
-      split_pack2(sacc[2 * kk + 1][0], sacc[2 * kk + 1][1], ah[2], al[2]);
-      split_pack2(sacc[2 * kk + 1][2], sacc[2 * kk + 1][3], ah[3], al[3]);
-#pragma unroll
-      for (int np = 0; np < 2; ++np) {
-        uint32_t bh4[4], bl4[4];
-        const uint32_t voff = 2u * ((kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * ATT_LD + np * 16 + (lane >> 4) * 8);
-        ldmatrix_x4_trans(bh4, vh + voff);
-        ldmatrix_x4_trans(bl4, vl + voff);
-        mma_bf16_16816(oacc[2 * np], ah, bh4[0], bh4[1]);
-        mma_bf16_16816(oacc[2 * np + 1], ah, bh4[2], bh4[3]);
-        mma_bf16_16816(oacc[2 * np], al, bh4[0], bh4[1]);
-        mma_bf16_16816(oacc[2 * np + 1], al, bh4[2], bh4[3]);
-        mma_bf16_16816(oacc[2 * np], ah, bl4[0], bl4[1]);
-        mma_bf16_16816(oacc[2 * np + 1], ah, bl4[2], bl4[3]);
-      }
-    }
-    // ---- stage O hi / lo (this warp's 16 rows) in the q_hi / q_lo tiles, then 16-byte stores to the split rows
-    __syncwarp();
-    __nv_bfloat16* Qh = tiles;
-    __nv_bfloat16* Ql = tiles + 3 * ATT_TILE;
-#pragma unroll
-    for (int n = 0; n < 4; ++n) {
-      uint32_t hi, lo;
-      split_pack2(oacc[n][0] * inv0, oacc[n][1] * inv0, hi, lo);
-      *reinterpret_cast<uint32_t*>(Qh + row0 * ATT_LD + n * 8 + 2 * t) = hi;
-      *reinterpret_cast<uint32_t*>(Ql + row0 * ATT_LD + n * 8 + 2 * t) = lo;
-      split_pack2(oacc[n][2] * inv1, oacc[n][3] * inv1, hi, lo);
-      *reinterpret_cast<uint32_t*>(Qh + row1 * ATT_LD + n * 8 + 2 * t) = hi;
-      *reinterpret_cast<uint32_t*>(Ql + row1 * ATT_LD + n * 8 + 2 * t) = lo;
-    }
-    __syncwarp();
-#pragma unroll
-    for (int e = lane; e < 128; e += 32) {
-      const int part = e >> 6, r = r0 + ((e >> 2) & 15), ch = e & 3;
-      const uint4 v = *reinterpret_cast<const uint4*>((part ? Ql : Qh) + r * ATT_LD + ch * 8);
-      *reinterpret_cast<uint4*>(out + (size_t)tok[r] * (2 * C) + part * C + head * 32 + ch * 8) = v;
-    }
-    __syncthreads();        // everyone is done with the tiles and this staging buffer before they are refilled
   }
 }
 

@@ -20,14 +20,8 @@ namespace wmk {
 namespace tc { int num_sms(); }
 int stft_clips(const float* wave, int B, int L, float* clips, int n_clips, cudaStream_t st);
 int istft_clips(const float* clips, int B, int n_clips, int T, float* wave, int length, cudaStream_t st);
-int leff_dwconv_linear2_bf16(const __nv_bfloat16* H1, const float* dw_w, const float* dw_b, const __nv_bfloat16* W2,
-                             const float* b2, float* x, int n, int H, int C, cudaStream_t st);
 int dwconv3x3_gelu_op16(const void* in, void* out, const float* wt, const float* bias, int B, int H, int Ch, int f16,
                         cudaStream_t st);
-int leff_dwconv_linear2_split(const float* H1, const float* dw_w, const float* dw_b, const __nv_bfloat16* W2t, const float* b2,
-                              float* x, int n, int H, int C, cudaStream_t st);
-int dwconv3x3_gelu_split(const float* in, __nv_bfloat16* out, const float* wt, const float* bias, int B, int H, int Ch,
-                         cudaStream_t st);
 
 namespace {
 
@@ -44,7 +38,6 @@ struct BlockW {
   float *ln1_w = nullptr, *ln1_b = nullptr, *ln2_w = nullptr, *ln2_b = nullptr, *mod = nullptr;
   float* attn_bias = nullptr;
   void *w_qkv = nullptr, *w_proj = nullptr, *w_l1 = nullptr, *w_l2 = nullptr;
-  void* w_l2_tail = nullptr;     // split plans, C <= 128: linear2 weight in the k-block form of leff_tail_split_kernel
   float *b_qkv = nullptr, *b_proj = nullptr, *b_l1 = nullptr, *b_l2 = nullptr, *dw_w = nullptr, *dw_b = nullptr;
   float *dw_wh = nullptr, *dw_bh = nullptr;      // 0.5 x the depthwise weights / bias (dwconv_tma.cu folds the GELU's 0.5)
 };
@@ -89,10 +82,6 @@ struct wmk_plan {
         *rt2 = nullptr;
   bool ws_ready = false;
 
-  // WMK_FUSED_LEFF=1 (read when the plan is created): run the LeFF tail as the fused dwconv -> linear2 tcgen05
-  // kernel of leff_fused.cu for the C <= 256 stages.  Off by default: it removes 16C bytes/token of HBM traffic
-  // but the tail is bound by the convolution's fp32 work, so it measures the same as the two separate kernels.
-  int fused_leff = 0, fused_maxh = 128, fused_minh = 8;
   bool taps_on = false;
   std::map<std::string, std::pair<float*, size_t>> taps;
 
@@ -134,6 +123,18 @@ int upload_op(wmk_plan* P, const std::vector<float>& v, void** out, int mode, in
         const __nv_bfloat16 lo = __float2bfloat16(w - __bfloat162float(hi));
         if (K == 32) { h[n * ld + k] = hi; h[n * ld + 32 + k] = hi; h[n * ld + 64 + k] = lo; }
         else { h[n * ld + k] = hi; h[n * ld + K + k] = lo; }
+      }
+  } else if (mode == 4) {          // W-only split: rows [hi(K) | lo(K)] in fp16 (gemm_tcgen05.cu, p.split = 3 / 4)
+    const size_t N = v.size() / (size_t)K;
+    h.resize(N * 2 * (size_t)K);
+    for (size_t n = 0; n < N; ++n)
+      for (int k = 0; k < K; ++k) {
+        const float w = v[n * K + k];
+        const float c = w > 65504.f ? 65504.f : (w < -65504.f ? -65504.f : w);
+        const __half hi = __float2half_rn(c);
+        const __half lo = __float2half_rn(c - __half2float(hi));
+        h[n * 2 * K + k] = *reinterpret_cast<const __nv_bfloat16*>(&hi);
+        h[n * 2 * K + K + k] = *reinterpret_cast<const __nv_bfloat16*>(&lo);
       }
   } else if (mode == 3) {          // IEEE fp16, saturating
     h.resize(v.size());
@@ -219,29 +220,11 @@ int pack_block(wmk_plan* P, const std::string& p, int C, int heads, int H, int s
     WMK_TRY(upload_op(P, wh, &w->w_l1, mode, C));
     WMK_TRY(upload_f32(P, bh, &w->b_l1));
   } else {
-    WMK_TRY(upload_op(P, t->data, &w->w_l1, mode, C));
+    WMK_TRY(upload_op(P, t->data, &w->w_l1, mode == 2 ? 4 : mode, C));      // precise extractor: fp16 activations x (hi + lo) fp16 weights
     WMK_TRY(get_f32(P, p + "mlp.linear1.0.bias", 4 * (size_t)C, &w->b_l1));
   }
   WMK_TRY(get(P, p + "mlp.linear2.0.weight", 4 * (size_t)C * C, &t));
-  WMK_TRY(upload_op(P, t->data, &w->w_l2, mode, 4 * C));
-  if (mode == 2 && C <= 128) {
-    // [C][(4C/32) * 128]: k-block kb (32 hidden channels) = [hi(32) | hi(32) | lo(32) | 0(32)] (leff_fused.cu)
-    const int K = 4 * C, kbs = K / 32;
-    std::vector<__nv_bfloat16> h((size_t)C * kbs * 128, __float2bfloat16(0.f));
-    for (int n = 0; n < C; ++n)
-      for (int k = 0; k < K; ++k) {
-        const float wv = t->data[(size_t)n * K + k];
-        const __nv_bfloat16 hi = __float2bfloat16(wv);
-        const __nv_bfloat16 lo = __float2bfloat16(wv - __bfloat162float(hi));
-        __nv_bfloat16* d = &h[((size_t)n * kbs + k / 32) * 128 + (k & 31)];
-        d[0] = hi; d[32] = hi; d[64] = lo;
-      }
-    void* dptr = nullptr;
-    if (cudaMalloc(&dptr, h.size() * 2) != cudaSuccess) { set_error("cudaMalloc of %zu bytes failed", h.size() * 2); return WMK_ERR_ALLOC; }
-    P->allocs.push_back(dptr);
-    WMK_CHECK_CUDA(cudaMemcpy(dptr, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
-    w->w_l2_tail = dptr;
-  }
+  WMK_TRY(upload_op(P, t->data, &w->w_l2, mode == 2 ? 4 : mode, 4 * C));
   WMK_TRY(get_f32(P, p + "mlp.linear2.0.bias", C, &w->b_l2));
   WMK_TRY(get(P, p + "mlp.dwconv.0.weight", 36 * (size_t)C, &dw));
   std::vector<float> dwt(36 * (size_t)C);
@@ -346,56 +329,52 @@ int gemm(int mode, const GemmArgs& g, cudaStream_t st) {
   return mode != 0 ? gemm_bf16_tcgen05(g, st) : gemm_fp32_simt(g, st);
 }
 
-// One LeWin block (uformerWM/model.py:937-1019) on the residual stream x.  bf16 mode, C <= 128: the two
+// One LeWin block (uformerWM/model.py:937-1019) on the residual stream x.  16-bit modes, C <= 128: the two
 // LayerNorms are fused into the epilogues of the dense layers that produce their input - norm2 into the
 // attention projection, and the NEXT block's norm1 (+ modulator) into this block's linear2 - so the fp32
 // stream is not re-read; `ln1_ready` says the previous block already left LN1(x) in bufA, `next` is the
 // following block of the same stage (nullptr for the last one).
-// Split-bf16 mode (OpT = SplitBf16, the WMK_PREC_MIXED extractor): the A operands of the four dense layers
-// (bufA, bufO, bufH2) are split rows [hi | lo] written by their producers (LayerNorm, attention, depthwise
-// conv), the dense layers' outputs (bufQKV, bufH1) stay fp32, every GELU is the erf form.
+//
+// Precise mode (OpT = SplitBf16, the WMK_PREC_MIXED extractor; the precision of every tensor follows the measured
+// sensitivity of the logits, tools/precision_study.py - WEIGHT rounding and the A operands of the attention
+// projections dominate, the 16-bit rounding of q / k / v / P and of the LeFF activations costs ~3e-5):
+//   LN1 out (bufA)     split-bf16 rows [hi | lo]          -> QKV projection  hi*hi + lo*hi + hi*lo   (3 MMAs)
+//   q | k | v (bufQKV) fp16                               -> the fp16 attention kernel
+//   attention out      split-bf16 rows                    -> output projection, 3 MMAs, fp32 residual stream
+//   LN2 out (bufA)     fp16                               -> linear1: fp16 x (hi + lo fp16 weights), 2 MMAs, erf-form GELU
+//   hidden H1 / H2     fp16, depthwise conv in fp32 + erf-form GELU -> linear2: fp16 x (hi + lo) weights, 2 MMAs
 template <typename OpT>
 int run_block(wmk_plan* P, const BlockW& w, float* x, int n, cudaStream_t st, bool ln1_ready = false,
               const BlockW* next = nullptr) {
   constexpr int MODE = OpMode<OpT>::v;
   constexpr bool P16 = OpPlain16<OpT>::v;          // plain 16-bit operands: bf16 (MODE 1) or fp16 (MODE 3)
-  constexpr int F16 = MODE == 3;
+  constexpr bool PRECISE = MODE == 2;
+  constexpr int F16 = MODE == 3 || PRECISE;        // 16-bit tensors of this mode are fp16
   const int C = w.C, H = w.H;
   const int M = n * H * H;
-  const int ob = P16;
+  const int ob = P16 || PRECISE;                   // QKV / hidden tensors are 16-bit
   static const int fuse_min_c = getenv("WMK_FUSE_LN_MINC") ? atoi(getenv("WMK_FUSE_LN_MINC")) : 32;
-  const bool fuse_ln = P16 && C <= 128 && C >= fuse_min_c;
-  OpT* A = reinterpret_cast<OpT*>(P->bufA);
+  const bool fuse_ln = (P16 || PRECISE) && C <= 128 && C >= fuse_min_c;
+  // size of one LayerNorm-output element in bufA (profile accounting)
+  const double ln1_bytes = PRECISE ? 4 : sizeof(OpT), ln2_bytes = PRECISE ? 2 : sizeof(OpT);
   if (!(ln1_ready && fuse_ln)) {
-    ProfScope prof(FAM_LAYERNORM, (double)M * C * (4 + sizeof(OpT)), st);
-    launch_layernorm<OpT>(x, A, w.ln1_w, w.ln1_b, w.mod, M, C, H, w.shift, st);
+    ProfScope prof(FAM_LAYERNORM, (double)M * C * (4 + ln1_bytes), st);
+    launch_layernorm<OpT>(x, reinterpret_cast<OpT*>(P->bufA), w.ln1_w, w.ln1_b, w.mod, M, C, H, w.shift, st);
     WMK_CHECK_LAUNCH("layernorm_kernel");
   }
   GemmArgs g;
-  g.A = A; g.W = w.w_qkv; g.bias = w.b_qkv; g.C = P->bufQKV; g.M = M; g.N = 3 * C; g.K = C; g.ldc = 3 * C;
-  g.epi = EPI_BIAS; g.out_bf16 = ob; g.split = MODE == 2; g.f16 = F16;
+  g.A = P->bufA; g.W = w.w_qkv; g.bias = w.b_qkv; g.C = P->bufQKV; g.M = M; g.N = 3 * C; g.K = C; g.ldc = 3 * C;
+  g.epi = EPI_BIAS; g.out_bf16 = ob; g.split = PRECISE; g.f16 = F16;
   WMK_TRY(gemm(MODE, g, st));
   {
     ProfScope prof(FAM_ATTENTION, 256.0 * C * M, st);
     const int n_windows = n * (H / 8) * (H / 8);
-    if constexpr (P16) {
+    if constexpr (P16 || PRECISE) {
       int per_head = (148 * 5) / w.heads;                 // CTAs per head (5 resident CTAs per SM)
       if (per_head > n_windows) per_head = n_windows;
       if (per_head < 1) per_head = 1;
-      window_attention_mma_kernel<F16 != 0><<<per_head * w.heads, 128, 0, st>>>(
+      window_attention_mma_kernel<F16 != 0, PRECISE><<<per_head * w.heads, 128, 0, st>>>(
           reinterpret_cast<const uint16_t*>(P->bufQKV), reinterpret_cast<uint16_t*>(P->bufO), w.attn_bias, C, H, w.shift, n_windows);
-    } else if constexpr (MODE == 2) {
-      static bool attr_set = false;
-      if (!attr_set) {
-        WMK_CHECK_CUDA(cudaFuncSetAttribute(window_attention_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTS_SMEM));
-        attr_set = true;
-      }
-      int per_head = (tc::num_sms() * 2) / w.heads;       // two resident CTAs per SM (97 KB of shared memory each)
-      if (per_head > n_windows) per_head = n_windows;
-      if (per_head < 1) per_head = 1;
-      window_attention_split_kernel<<<per_head * w.heads, 128, ATTS_SMEM, st>>>(
-          reinterpret_cast<const float*>(P->bufQKV), reinterpret_cast<__nv_bfloat16*>(P->bufO), w.attn_bias, C, H, w.shift,
-          n_windows);
     } else {
       window_attention_kernel<float><<<dim3(n_windows, w.heads), 128, 0, st>>>(
           reinterpret_cast<const float*>(P->bufQKV), reinterpret_cast<float*>(P->bufO), w.attn_bias, C, H, w.shift);
@@ -404,49 +383,26 @@ int run_block(wmk_plan* P, const BlockW& w, float* x, int n, cudaStream_t st, bo
   }
   g = GemmArgs();
   g.A = P->bufO; g.W = w.w_proj; g.bias = w.b_proj; g.resid = x; g.C = x; g.M = M; g.N = C; g.K = C; g.ldc = C;
-  g.epi = EPI_BIAS_RESID; g.out_bf16 = 0; g.split = MODE == 2; g.f16 = F16;
-  if (fuse_ln) { g.ln_out = A; g.ln_gamma = w.ln2_w; g.ln_beta = w.ln2_b; }        // norm2 (model.py:1017)
+  g.epi = EPI_BIAS_RESID; g.out_bf16 = 0; g.split = PRECISE; g.f16 = F16;
+  if (fuse_ln) { g.ln_out = P->bufA; g.ln_gamma = w.ln2_w; g.ln_beta = w.ln2_b; }   // norm2 (model.py:1017), plain 16-bit rows
   WMK_TRY(gemm(MODE, g, st));
   if (!fuse_ln) {
-    ProfScope prof(FAM_LAYERNORM, (double)M * C * (4 + sizeof(OpT)), st);
-    launch_layernorm<OpT>(x, A, w.ln2_w, w.ln2_b, nullptr, M, C, H, 0, st);
+    ProfScope prof(FAM_LAYERNORM, (double)M * C * (4 + ln2_bytes), st);
+    if constexpr (PRECISE) launch_layernorm<__half>(x, reinterpret_cast<__half*>(P->bufA), w.ln2_w, w.ln2_b, nullptr, M, C, H, 0, st);
+    else launch_layernorm<OpT>(x, reinterpret_cast<OpT*>(P->bufA), w.ln2_w, w.ln2_b, nullptr, M, C, H, 0, st);
     WMK_CHECK_LAUNCH("layernorm_kernel");
   }
   g = GemmArgs();
-  g.A = A; g.W = w.w_l1; g.bias = w.b_l1; g.C = P->bufH1; g.M = M; g.N = 4 * C; g.K = C; g.ldc = 4 * C;
-  g.epi = EPI_BIAS_GELU; g.out_bf16 = ob; g.gelu_half = ob;      // bf16 plans carry W1 / 2, b1 / 2 (pack_block)
-  g.split = MODE == 2; g.gelu_exact = MODE == 2; g.f16 = F16;
+  g.A = P->bufA; g.W = w.w_l1; g.bias = w.b_l1; g.C = P->bufH1; g.M = M; g.N = 4 * C; g.K = C; g.ldc = 4 * C;
+  g.epi = EPI_BIAS_GELU; g.out_bf16 = ob; g.gelu_half = P16;      // plain 16-bit plans carry W1 / 2, b1 / 2 (pack_block)
+  g.wsplit = PRECISE; g.gelu_exact = PRECISE; g.f16 = F16;
   WMK_TRY(gemm(MODE, g, st));
-  if constexpr (MODE == 1) {
-    if (P->fused_leff && C <= 256 && H <= P->fused_maxh && H >= P->fused_minh) {
-      // depthwise conv + GELU as the producer of linear2's A operand: H2 never reaches HBM (leff_fused.cu)
-      WMK_TRY(leff_dwconv_linear2_bf16(reinterpret_cast<const __nv_bfloat16*>(P->bufH1), w.dw_w, w.dw_b,
-                                       reinterpret_cast<const __nv_bfloat16*>(w.w_l2), w.b_l2, x, n, H, C, st));
-      if (fuse_ln && next) {
-        ProfScope prof(FAM_LAYERNORM, (double)M * C * (4 + sizeof(OpT)), st);
-        launch_layernorm<OpT>(x, A, next->ln1_w, next->ln1_b, next->mod, M, C, H, next->shift, st);
-        WMK_CHECK_LAUNCH("layernorm_kernel");
-      }
-      return 0;
-    }
-  }
-  if constexpr (MODE == 2) {
-    // depthwise conv + GELU as the producer of linear2's split A operand: the convolved hidden tensor (16C bytes per
-    // token written + read by the separate kernels) never reaches HBM (leff_fused.cu, leff_tail_split_kernel)
-    static const int split_tail = getenv("WMK_SPLIT_TAIL") ? atoi(getenv("WMK_SPLIT_TAIL")) : 1;
-    if (split_tail && w.w_l2_tail) {
-      WMK_TRY(leff_dwconv_linear2_split(reinterpret_cast<const float*>(P->bufH1), w.dw_w, w.dw_b,
-                                        reinterpret_cast<const __nv_bfloat16*>(w.w_l2_tail), w.b_l2, x, n, H, C, st));
-      return 0;
-    }
-  }
   {
-    ProfScope prof(FAM_DWCONV, 8.0 * M * C * sizeof(OpT), st);
+    ProfScope prof(FAM_DWCONV, 8.0 * M * C * (ob ? 2 : 4), st);
     if constexpr (P16) {
       WMK_TRY(dwconv3x3_gelu_op16(P->bufH1, P->bufH2, w.dw_wh, w.dw_bh, n, H, 4 * C, F16, st));
-    } else if constexpr (MODE == 2) {
-      WMK_TRY(dwconv3x3_gelu_split(reinterpret_cast<const float*>(P->bufH1), reinterpret_cast<__nv_bfloat16*>(P->bufH2),
-                                   w.dw_w, w.dw_b, n, H, 4 * C, st));
+    } else if constexpr (PRECISE) {
+      WMK_TRY(dwconv3x3_gelu_op16(P->bufH1, P->bufH2, w.dw_w, w.dw_b, n, H, 4 * C, 2, st));     // fp16 tensors, erf-form GELU
     } else {
       dwconv3x3_gelu_kernel<float><<<n * (H / 8) * (H / 8) * ((4 * C) / 64), 128, 0, st>>>(
           reinterpret_cast<const float*>(P->bufH1), reinterpret_cast<float*>(P->bufH2), w.dw_w, w.dw_b, n, H, 4 * C);
@@ -455,9 +411,10 @@ int run_block(wmk_plan* P, const BlockW& w, float* x, int n, cudaStream_t st, bo
   }
   g = GemmArgs();
   g.A = P->bufH2; g.W = w.w_l2; g.bias = w.b_l2; g.resid = x; g.C = x; g.M = M; g.N = C; g.K = 4 * C; g.ldc = C;
-  g.epi = EPI_BIAS_RESID; g.out_bf16 = 0; g.split = MODE == 2; g.f16 = F16;
+  g.epi = EPI_BIAS_RESID; g.out_bf16 = 0; g.wsplit = PRECISE; g.f16 = F16;
   if (fuse_ln && next) {                                                           // the next block's norm1 + modulator
-    g.ln_out = A; g.ln_gamma = next->ln1_w; g.ln_beta = next->ln1_b; g.ln_mod = next->mod; g.ln_H = H; g.ln_shift = next->shift;
+    g.ln_out = P->bufA; g.ln_gamma = next->ln1_w; g.ln_beta = next->ln1_b; g.ln_mod = next->mod; g.ln_H = H; g.ln_shift = next->shift;
+    g.ln_split = PRECISE;                                                          // ... as split rows for the next QKV projection
   }
   WMK_TRY(gemm(MODE, g, st));
   return 0;
@@ -476,13 +433,14 @@ int run_stage(wmk_plan* P, const std::vector<BlockW>& blocks, float* x, int n, c
 template <typename OpT>
 int run_encoder(wmk_plan* P, const EncW& e, const float* x_nchw, int n, const char* tag, cudaStream_t st) {
   bool stage0_ln_ready = false;
+  static const int split_ln0 = getenv("WMK_SPLIT_FUSE_LN") ? atoi(getenv("WMK_SPLIT_FUSE_LN")) : 1;
   {
     ProfScope prof(FAM_SMALL, (double)n * 16384 * (8 + 128), st);
     static const int fuse_ln0 = getenv("WMK_FUSE_FIRST_LN") ? atoi(getenv("WMK_FUSE_FIRST_LN")) : 1;
-    const bool ln0 = OpPlain16<OpT>::v && fuse_ln0 && e.in_proj_has_ln;       // norm1 of stage 0's block in the same pass
+    const bool ln0 = (OpPlain16<OpT>::v || (OpMode<OpT>::v == 2 && split_ln0)) && fuse_ln0 && e.in_proj_has_ln;       // norm1 of stage 0's block in the same pass
     input_proj_kernel<<<cdiv((size_t)n * 16384, 128), 128, 0, st>>>(x_nchw, P->E[0], e.in_proj, n,
                                                                    ln0 ? reinterpret_cast<uint16_t*>(P->bufA) : nullptr,
-                                                                   OpMode<OpT>::v == 3);
+                                                                   OpMode<OpT>::v == 3 ? 1 : OpMode<OpT>::v == 2 ? 2 : 0);
     WMK_CHECK_LAUNCH("input_proj_kernel");
     stage0_ln_ready = ln0;
   }
@@ -507,10 +465,11 @@ int run_encoder(wmk_plan* P, const EncW& e, const float* x_nchw, int n, const ch
     g.A = col; g.W = e.down_w[s]; g.bias = e.down_b[s]; g.C = P->E[s + 1]; g.M = n * Ho * Ho; g.N = 2 * C;
     g.K = 16 * C; g.ldc = 2 * C; g.epi = EPI_BIAS; g.out_bf16 = 0; g.split = OpMode<OpT>::v == 2; g.f16 = OpMode<OpT>::v == 3;
     static const int fuse_first_ln = getenv("WMK_FUSE_FIRST_LN") ? atoi(getenv("WMK_FUSE_FIRST_LN")) : 1;
-    if (OpPlain16<OpT>::v && fuse_first_ln && 2 * C <= 128) {
+    if ((OpPlain16<OpT>::v || (OpMode<OpT>::v == 2 && split_ln0)) && fuse_first_ln && 2 * C <= 128) {
       // the next stage's first norm1 rides on the downsample conv's epilogue (encoder blocks carry no modulator)
       const BlockW& nb = e.stage[s + 1][0];
       g.ln_out = P->bufA; g.ln_gamma = nb.ln1_w; g.ln_beta = nb.ln1_b; g.ln_mod = nb.mod; g.ln_H = Ho; g.ln_shift = nb.shift;
+      g.ln_split = OpMode<OpT>::v == 2;
       ln_ready = true;
     }
     WMK_TRY(gemm(OpMode<OpT>::v, g, st));
@@ -628,9 +587,6 @@ extern "C" int wmk_uformer_plan_create(int precision, wmk_plan** out) {
     return WMK_ERR_UNSUPPORTED;
   }
   wmk_plan* P = new wmk_plan();
-  if (getenv("WMK_FUSED_LEFF")) P->fused_leff = atoi(getenv("WMK_FUSED_LEFF"));
-  if (getenv("WMK_FUSED_LEFF_MAXH")) P->fused_maxh = atoi(getenv("WMK_FUSED_LEFF_MAXH"));
-  if (getenv("WMK_FUSED_LEFF_MINH")) P->fused_minh = atoi(getenv("WMK_FUSED_LEFF_MINH"));
   P->precision = precision;
   P->device = dev;
   *out = P;
@@ -830,6 +786,18 @@ static __global__ void split_rows_kernel(const float* __restrict__ src, __nv_bfl
   }
 }
 
+// fp32 [rows][K] -> fp16 rows [hi(K) | lo(K)] (the W-only split weight form)
+static __global__ void wsplit_rows_kernel(const float* __restrict__ src, __half* __restrict__ dst, size_t rows, int K) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * (size_t)K) return;
+  const size_t r = i / K;
+  const int k = (int)(i - r * K);
+  const float v = fminf(fmaxf(src[i], -65504.f), 65504.f);
+  const __half hi = __float2half_rn(v);
+  dst[r * 2 * (size_t)K + k] = hi;
+  dst[r * 2 * (size_t)K + K + k] = __float2half_rn(v - __half2float(hi));
+}
+
 extern "C" int wmk_linear_f32(const float* A, const float* W, const float* bias, float* C, int M, int N, int K,
                               int precision, int gelu, void* stream) {
   WMK_REQUIRE(A && W && C && M > 0 && N > 0 && K > 0, "linear: bad arguments");
@@ -856,8 +824,34 @@ extern "C" int wmk_linear_f32(const float* A, const float* W, const float* bias,
     cudaFreeAsync(wsp, st);
     return s;
   }
-  WMK_REQUIRE(precision == WMK_PREC_BF16 || precision == WMK_PREC_F16, "linear: unknown precision %d", precision);
-  const bool f16 = precision == WMK_PREC_F16;
+  WMK_REQUIRE(precision == WMK_PREC_BF16 || precision == WMK_PREC_F16 || precision == WMK_LINEAR_WSPLIT,
+              "linear: unknown precision %d", precision);
+  const bool f16 = precision != WMK_PREC_BF16;
+  if (precision == WMK_LINEAR_WSPLIT) {    // fp16 A x (hi + lo) fp16 W: two tcgen05 MMAs per product
+    WMK_REQUIRE(K == 32 || K % 64 == 0, "linear(wsplit): K must be 32 or a multiple of 64, got %d", K);
+    __half *ah = nullptr, *wh = nullptr;
+    WMK_CHECK_CUDA(cudaMallocAsync(&ah, (size_t)M * K * 2, st));
+    WMK_CHECK_CUDA(cudaMallocAsync(&wh, (size_t)N * 2 * K * 2, st));
+    copy_cols_kernel<__half><<<cdiv((size_t)M * (K / 4), 256), 256, 0, st>>>(A, ah, (size_t)M, K, K, 0);
+    WMK_CHECK_LAUNCH("copy_cols_kernel");
+    wsplit_rows_kernel<<<cdiv((size_t)N * K, 256), 256, 0, st>>>(W, wh, (size_t)N, K);
+    WMK_CHECK_LAUNCH("wsplit_rows_kernel");
+    g.A = ah; g.W = wh; g.wsplit = 1; g.gelu_exact = 1;
+    uint16_t* c16w = nullptr;
+    if (gelu) {
+      WMK_CHECK_CUDA(cudaMallocAsync(&c16w, (size_t)M * N * 2, st));
+      g.C = c16w; g.out_bf16 = 1;
+    }
+    const int s = gemm_bf16_tcgen05(g, st);
+    if (gelu && s == 0) {
+      widen_kernel<<<cdiv((size_t)M * N, 256), 256, 0, st>>>(c16w, C, (size_t)M * N, true);
+      count_launch();
+    }
+    if (c16w) cudaFreeAsync(c16w, st);
+    cudaFreeAsync(ah, st);
+    cudaFreeAsync(wh, st);
+    return s;
+  }
   uint16_t *a16 = nullptr, *w16 = nullptr;
   WMK_CHECK_CUDA(cudaMallocAsync(&a16, (size_t)M * K * 2, st));
   WMK_CHECK_CUDA(cudaMallocAsync(&w16, (size_t)N * K * 2, st));

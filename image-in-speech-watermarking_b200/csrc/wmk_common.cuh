@@ -101,6 +101,7 @@ struct GemmArgs {
   const float* ln_beta = nullptr;
   const float* ln_mod = nullptr;   // [64][N] or nullptr
   int ln_H = 0, ln_shift = 0;      // image side (power of two) and cyclic shift of the block that consumes ln_out
+  int ln_split = 0;                // ln_out rows are split-bf16 [hi(N) | lo(N)] (the A operand of a split dense layer)
   // Implicit-GEMM 3x3 convolution (pad 1) over an NHWC bf16 image batch [conv_B][conv_H][128][64]: A is that tensor, a row
   // tile = the 128 pixels of one image row, k-block kb = tap (dy, dx) fetched as the TMA box shifted by (dy-1, dx-1)
   // with out-of-bounds zero fill as the padding; W is [N][9*64] with k = tap*64 + ci.  M = conv_B*conv_H*128, K = 576.
@@ -110,6 +111,11 @@ struct GemmArgs {
   // The product is hi*hi + lo*hi + hi*lo, accumulated by three tcgen05 MMAs per k-step into the same fp32 TMEM
   // accumulator.  Outputs are fp32 (out_bf16 = 0).  gelu_exact: GELU by the 1.5e-7 erf form (gelu_fast).
   int split = 0;
+  // W-only split ("fp16x2"): A is a plain fp16 [M][K] operand, W is [N][2K] fp16 = [hi(K) | lo(K)] with hi = fp16(w),
+  // lo = fp16(w - hi); the product is A*hi + A*lo (two MMAs per k-step).  Weight rounding is what moves the extractor's
+  // logits (2.5e-4 for fp16 weights vs 2e-5 for fp16 LeFF activations, tools/precision_study.py), so the LeFF layers
+  // of the precise extractor keep 22-bit weights and 16-bit activations.  Implies f16 operands.
+  int wsplit = 0;
   int gelu_exact = 0;
   // Plain (non-split) 16-bit operands - A, W, a 16-bit C (out_bf16) and ln_out - are IEEE fp16 instead of bf16:
   // same tcgen05 rate, 11 instead of 8 mantissa bits (the WMK_PREC_MIXED / WMK_PREC_F16 embedder).
@@ -279,8 +285,9 @@ struct EpiParams {
   int resid_prefetch = 0;   // persistent kernel: L2-prefetch the next tile's residual rows
   int gelu_half = 0;        // GELU epilogue: the accumulator holds x / 2 (weights and bias pre-halved)
   int gelu_exact = 0;       // GELU epilogue: erf form (gelu_fast, |error| 1.5e-7) instead of the tanh form
-  int split = 0;            // 0: plain; 1: split-bf16 operands, K % 64 == 0; 2: split-bf16 operands, K == 32
+  int split = 0;            // 0: plain; 1 / 2: split-bf16 A and W (K % 64 == 0 / K == 32); 3 / 4: fp16 A, W = hi + lo fp16 (K % 64 == 0 / K == 32)
   int f16 = 0;              // plain 16-bit operands / outputs are fp16 (else bf16)
+  int ln_split = 0;         // fused LayerNorm output as split-bf16 rows [hi(N) | lo(N)]
 };
 
 __device__ __forceinline__ size_t epi_row_offset(const EpiParams& p, int m, int n_first) {

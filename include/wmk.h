@@ -342,8 +342,11 @@ int wmk_plan_enable_taps(wmk_plan* plan, int enable);
 int wmk_plan_get_tap(wmk_plan* plan, const char* name, float* out, size_t capacity, size_t* n_out);
 
 /* Stand-alone dense op used by the unit tests and the roofline bench:
- * C[M][N] = A[M][K] * W[N][K]^T + bias[N], fp32 in HBM in and out; precision selects the fp32
- * SIMT kernel or the bf16 tcgen05 kernel (operands converted on the fly by a cast kernel). */
+ * C[M][N] = A[M][K] * W[N][K]^T + bias[N], fp32 in HBM in and out; precision selects the fp32 SIMT kernel
+ * (WMK_PREC_FP32) or the tcgen05 kernel with bf16 / fp16 operands (WMK_PREC_BF16 / WMK_PREC_F16), split-bf16 A and
+ * W = three MMAs per product (WMK_PREC_MIXED), or fp16 A x (hi + lo) fp16 W = two MMAs (WMK_LINEAR_WSPLIT); operands
+ * are converted on the fly by a cast kernel. */
+#define WMK_LINEAR_WSPLIT 16
 int wmk_linear_f32(const float* A, const float* W, const float* bias, float* C, int M, int N,
                    int K, int precision, int gelu, void* stream);
 
