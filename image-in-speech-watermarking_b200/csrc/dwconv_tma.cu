@@ -113,8 +113,8 @@ dwconv3x3_gelu_tma_kernel(const __grid_constant__ CUtensorMap tm, uint16_t* __re
           a1 = __ffma2_rn(win[(r + dy) % 3][dx][1], wreg[dy * 3 + dx][1], a1);
         }
       if constexpr (EXACT) {
-        a0 = make_float2(gelu_fast(a0.x), gelu_fast(a0.y));
-        a1 = make_float2(gelu_fast(a1.x), gelu_fast(a1.y));
+        a0 = gelu_erf2(a0);
+        a1 = gelu_erf2(a1);
       } else {
         a0 = gelu_tanh2_half_arg(a0);
         a1 = gelu_tanh2_half_arg(a1);
@@ -246,8 +246,8 @@ dwconv3x3_gelu_tma2_kernel(const __grid_constant__ CUtensorMap tm, uint16_t* __r
         for (int q = 0; q < 2; ++q) {
           float2 g0, g1;
           if constexpr (EXACT) {
-            g0 = make_float2(gelu_fast(acc[o % 3][q][0].x), gelu_fast(acc[o % 3][q][0].y));
-            g1 = make_float2(gelu_fast(acc[o % 3][q][1].x), gelu_fast(acc[o % 3][q][1].y));
+            g0 = gelu_erf2(acc[o % 3][q][0]);
+            g1 = gelu_erf2(acc[o % 3][q][1]);
           } else {
             g0 = gelu_tanh2_half_arg(acc[o % 3][q][0]);
             g1 = gelu_tanh2_half_arg(acc[o % 3][q][1]);

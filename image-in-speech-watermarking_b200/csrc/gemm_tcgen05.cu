@@ -231,8 +231,10 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __
   const int BOXC = OUT_BF16 ? p.boxc : 32;
   const uint32_t STG_BYTES = OUT_BF16 ? 64u * (uint32_t)BOXC : 4096u;
   const uint32_t staging = stages + (uint32_t)n_stages * STAGE;          // [16 warps][STG_BYTES]
-  const uint32_t stg2 = p.ln_split ? 2 * STG2_BYTES : STG2_BYTES;
-  const uint32_t staging2 = staging + kEpiWarps * STG_BYTES;             // LN: [16 warps][2048 (x 2: hi, lo)] + exchange
+  // split-operand launches (the precise extractor) have no shared memory to spare for a second staging area: their fused
+  // LayerNorm re-uses the warp's x staging buffer once its TMA store has been read (p.ln_reuse)
+  const uint32_t stg2 = p.ln_reuse ? 0u : STG2_BYTES;
+  const uint32_t staging2 = staging + kEpiWarps * STG_BYTES;             // LN: [16 warps][2048] + exchange
   const uint32_t ln_exch = staging2 + kEpiWarps * stg2;
   const uint32_t bars = LN ? ln_exch + LN_EXCH_BYTES : staging + kEpiWarps * STG_BYTES;
   auto full_bar = [&](int s) { return bars + 8u * s; };
@@ -471,7 +473,10 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __
           if constexpr (EPI == EPI_BIAS_GELU) {
             if (p.gelu_exact) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = gelu_fast(f[j]);
+              for (int j = 0; j < 16; ++j) {
+                const float2 gq = gelu_erf2(make_float2(f[2 * j], f[2 * j + 1]));
+                f[2 * j] = gq.x; f[2 * j + 1] = gq.y;
+              }
             } else if (p.gelu_half) {
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
@@ -585,7 +590,12 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __
                   f[4 * j] += mm.x; f[4 * j + 1] += mm.y; f[4 * j + 2] += mm.z; f[4 * j + 3] += mm.w;
                 }
               }
-              const uint32_t buf2 = staging2 + (uint32_t)ew * stg2;           // free: every earlier store was waited for above
+              uint32_t buf2 = staging2 + (uint32_t)ew * stg2;                 // free: every earlier store was waited for above
+              if (p.ln_reuse) {                               // the x store issued above must have read `buf` first
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                __syncwarp();
+                buf2 = buf;
+              }
               if (p.ln_split) {                               // rows [hi(N) | lo(N)]: two boxes
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -746,7 +756,8 @@ int launch_persistent_t(const GemmArgs& g, cudaStream_t st) {
   size_t smem = 0;
   for (;;) {
     const int stg = OUT_BF16 ? 64 * boxc : 4096;
-    const int fixed = kEpiWarps * stg + 1024 + 512 + (LN ? (int)(kEpiWarps * STG2_BYTES * (g.ln_split ? 2 : 1) + LN_EXCH_BYTES) : 0);
+    const bool ln_reuse = g.split || g.wsplit || g.ln_split;
+    const int fixed = kEpiWarps * stg + 1024 + 512 + (LN ? (int)((ln_reuse ? 0 : kEpiWarps * STG2_BYTES) + LN_EXCH_BYTES) : 0);
     // weight-stationary when the whole BN x K tile + >= 2 A stages fit and every N tile gets >= 1 CTA
     ws = (g.conv_H == 0 && wblocks <= (split_mode ? 8 : 4) && w_bytes + 2 * a_stage + fixed <= budget && n_tiles <= num_sms() &&
           m_tiles >= 2 * (num_sms() / n_tiles)) ? 1 : 0;
@@ -759,6 +770,10 @@ int launch_persistent_t(const GemmArgs& g, cudaStream_t st) {
     // by load latency (3.1 TB/s measured): halve the bf16 staging boxes to make room for a 4-deep ring
     if ((ws ? narrow_staging() >= 1 : narrow_staging() >= 2) && n_stages < 4 && OUT_BF16 && boxc == 64) { boxc = 32; continue; }
     break;
+  }
+  if (smem > 227 * 1024) {
+    set_error("gemm_bf16: %zu bytes of shared memory needed (M %d N %d K %d, tile %d, split %d)", smem, g.M, g.N, g.K, BN, split_mode);
+    return WMK_ERR_UNSUPPORTED;
   }
   WMK_TRY(make_map_ex(&tmC, g.C, g.M, g.ldc, 32, boxc, !OUT_BF16));
   if (LN) WMK_TRY(make_map_ex(&tmD, g.ln_out, g.M, g.ln_split ? 2 * g.N : g.N, 32, 32, false));
@@ -783,6 +798,7 @@ int launch_persistent_t(const GemmArgs& g, cudaStream_t st) {
   p.split = split_mode;
   p.f16 = g.f16 || g.wsplit;
   p.ln_split = g.ln_split;
+  p.ln_reuse = (g.split || g.wsplit || g.ln_split) ? 1 : 0;
 
   const long long total = (long long)m_tiles * n_tiles;
   const int grid = ws ? (num_sms() / n_tiles) * n_tiles : (int)(total < num_sms() ? total : num_sms());
@@ -879,7 +895,8 @@ int gemm_bf16_tcgen05(const GemmArgs& g, cudaStream_t st) {
   }
   if (g.epi != EPI_UPSAMPLE && g.ldc == g.N) {
     const bool wide_ok = g.epi != EPI_BIAS_RESID || g.K >= 1024;   // fp32 residual tiles: one 32-column piece per warp
-    if (g.N % 256 == 0 && g.N >= 256 && wide_ok) return launch_persistent<256>(g, st);
+    // split operands double the W (and A) stage: 256-wide tiles would leave no room for a second stage
+    if (g.N % 256 == 0 && g.N >= 256 && wide_ok && !g.split && !g.wsplit) return launch_persistent<256>(g, st);
     if (g.N % 128 == 0) return launch_persistent<128>(g, st);
     // N = 96 / 192 (the fused q|k|v projection of the C = 32 / 64 stages): one / two 96-wide tiles instead of three
     // 32- / 64-wide ones (A is fetched once, 12 of the 16 epilogue warps work instead of 4 / 8)

@@ -155,6 +155,32 @@ __device__ __forceinline__ float gelu_fast(float x) {
   return 0.5f * x * (1.0f + copysignf(erf_abs, x));
 }
 
+// The same erf form for PAIRS on the packed fp32x2 pipe with the approximate MUFU units (rcp.approx 1 ulp, ex2.approx
+// 2 ulp: both far below the 1.5e-7 of the formula): 12 packed FMA-pipe instructions + 4 MUFU + 4 logic ops per pair,
+// about half the issue slots of two gelu_fast calls.  Used by the precise extractor (GELU error must stay well under
+// the 2^-11 of the fp16 tensors it feeds, and must not be systematic like the tanh form's 5e-5).
+__device__ __forceinline__ float2 gelu_erf2(float2 x) {
+  const float2 z = __fmul2_rn(make_float2(fabsf(x.x), fabsf(x.y)), make_float2(0.70710678118654752440f, 0.70710678118654752440f));
+  const float2 d = __ffma2_rn(z, make_float2(0.3275911f, 0.3275911f), make_float2(1.0f, 1.0f));
+  float2 t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.x) : "f"(d.x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.y) : "f"(d.y));
+  float2 p = __ffma2_rn(t, make_float2(1.061405429f, 1.061405429f), make_float2(-1.453152027f, -1.453152027f));
+  p = __ffma2_rn(p, t, make_float2(1.421413741f, 1.421413741f));
+  p = __ffma2_rn(p, t, make_float2(-0.284496736f, -0.284496736f));
+  p = __ffma2_rn(p, t, make_float2(0.254829592f, 0.254829592f));
+  const float2 a = __fmul2_rn(__fmul2_rn(z, z), make_float2(-1.4426950408889634f, -1.4426950408889634f));   // -z^2 log2(e)
+  float2 e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(a.x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(a.y));
+  const float2 q = __fmul2_rn(__fmul2_rn(p, t), e);                      // 1 - erf(|z|)
+  const float2 h = __fmul2_rn(x, make_float2(0.5f, 0.5f));
+  // gelu = h (1 + sign(x) (1 - q)) = h + |h| (1 - q)
+  const float2 ah = make_float2(fabsf(h.x), fabsf(h.y));
+  const float2 one_minus_q = __ffma2_rn(q, make_float2(-1.0f, -1.0f), make_float2(1.0f, 1.0f));
+  return __ffma2_rn(ah, one_minus_q, h);
+}
+
 // GELU for pairs on the packed fp32x2 pipe (sm_100 FFMA2), MUFU-free: erf(z) on [-3,3] by an odd
 // degree-15 minimax polynomial (|error| < 8.1e-5, fitted against scipy.special.erf), argument
 // clamped to +-3 beyond.  |gelu error| < 2e-4 for |x| <= 4 (4e-5 * |x| beyond), i.e. below the
@@ -288,6 +314,7 @@ struct EpiParams {
   int split = 0;            // 0: plain; 1 / 2: split-bf16 A and W (K % 64 == 0 / K == 32); 3 / 4: fp16 A, W = hi + lo fp16 (K % 64 == 0 / K == 32)
   int f16 = 0;              // plain 16-bit operands / outputs are fp16 (else bf16)
   int ln_split = 0;         // fused LayerNorm output as split-bf16 rows [hi(N) | lo(N)]
+  int ln_reuse = 0;         // fused LayerNorm stages its output in the warp's x staging buffer (no second staging area)
 };
 
 __device__ __forceinline__ size_t epi_row_offset(const EpiParams& p, int m, int n_first) {

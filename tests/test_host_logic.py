@@ -75,3 +75,30 @@ def test_wav_roundtrip(tmp_path):
     y, sr = wavio.read_wav(q)
     assert np.allclose(y[0], pcm.astype(np.float32) / 32768.0)
 
+
+
+def test_attack_seeds_are_fresh_per_call_and_per_rank(monkeypatch):
+    """random attacks must not replay one noise realisation: a new key per call, distinct across ranks,
+    reproducible under np.random.seed (the reference's own source of randomness)."""
+    import numpy as np
+    from image_in_speech_watermarking_b200 import audio_attack as AT
+    np.random.seed(5)
+    a = [AT.fresh_seed() for _ in range(4)]
+    assert len(set(a)) == 4 and all(0 <= s < 2 ** 64 for s in a)
+    np.random.seed(5)
+    AT._CALLS[0] -= 4
+    assert [AT.fresh_seed() for _ in range(4)] == a                      # reproducible run
+    np.random.seed(5)
+    AT._CALLS[0] -= 4
+    monkeypatch.setenv("RANK", "3")
+    b = [AT.fresh_seed() for _ in range(4)]
+    assert not set(a) & set(b)                                           # another rank, other keys
+
+
+def test_fixed_batch_sharding_covers_every_utterance_once():
+    """bench.py --config 4 (strong scaling): 64 utterances over 1 / 2 / 4 / 8 ranks, and ragged cases."""
+    from image_in_speech_watermarking_b200 import sharding as SH
+    for n, world in ((64, 1), (64, 2), (64, 4), (64, 8), (10, 4), (3, 8)):
+        got = [i for r in range(world) for i in SH.shard_range(n, r, world)]
+        assert got == list(range(n))
+    assert len(SH.shard_range(64, 5, 8)) == 8
