@@ -76,6 +76,7 @@ SIGNATURES = {
     "wmk_uformer_autoencode": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "wmk_plan_enable_taps": (_i, [_vp, _i]),
     "wmk_plan_get_tap": (_i, [_vp, ctypes.c_char_p, _vp, _sz, ctypes.POINTER(_sz)]),
+    "wmk_leff_block_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "wmk_linear_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
 }
 

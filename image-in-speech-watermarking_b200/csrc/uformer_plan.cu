@@ -20,6 +20,8 @@ namespace wmk {
 namespace tc { int num_sms(); }
 int stft_clips(const float* wave, int B, int L, float* clips, int n_clips, cudaStream_t st);
 int istft_clips(const float* clips, int B, int n_clips, int T, float* wave, int length, cudaStream_t st);
+int leff_block(const void* A, const void* W1, const void* W2, const float* b1, const float* dw_w, const float* dw_b,
+               const float* b2, float* x, int n, int H, int C, int f16, int precise, cudaStream_t st);
 int dwconv3x3_gelu_op16(const void* in, void* out, const float* wt, const float* bias, int B, int H, int Ch, int f16,
                         cudaStream_t st);
 
@@ -391,6 +393,21 @@ int run_block(wmk_plan* P, const BlockW& w, float* x, int n, cudaStream_t st, bo
     if constexpr (PRECISE) launch_layernorm<__half>(x, reinterpret_cast<__half*>(P->bufA), w.ln2_w, w.ln2_b, nullptr, M, C, H, 0, st);
     else launch_layernorm<OpT>(x, reinterpret_cast<OpT*>(P->bufA), w.ln2_w, w.ln2_b, nullptr, M, C, H, 0, st);
     WMK_CHECK_LAUNCH("layernorm_kernel");
+  }
+  if constexpr (P16 || PRECISE) {
+    // the whole LeFF (linear1 -> GELU -> depthwise 3x3 -> GELU -> linear2 + residual) in ONE tcgen05 kernel: the 4C-wide
+    // hidden tensor stays in shared memory (leff_block.cu); C <= 128, 16 x 8 pixel tiles
+    static const int fused = getenv("WMK_FUSED_LEFF") ? atoi(getenv("WMK_FUSED_LEFF")) : 0;
+    if (fused && C <= 128 && H >= 16) {
+      WMK_TRY(leff_block(P->bufA, w.w_l1, w.w_l2, w.b_l1, PRECISE ? w.dw_w : w.dw_wh, PRECISE ? w.dw_b : w.dw_bh, w.b_l2, x, n, H,
+                         C, F16, PRECISE, st));
+      if (fuse_ln && next) {               // the next block expects its norm1 in bufA
+        ProfScope prof(FAM_LAYERNORM, (double)M * C * (4 + ln1_bytes), st);
+        launch_layernorm<OpT>(x, reinterpret_cast<OpT*>(P->bufA), next->ln1_w, next->ln1_b, next->mod, M, C, H, next->shift, st);
+        WMK_CHECK_LAUNCH("layernorm_kernel");
+      }
+      return 0;
+    }
   }
   g = GemmArgs();
   g.A = P->bufA; g.W = w.w_l1; g.bias = w.b_l1; g.C = P->bufH1; g.M = M; g.N = 4 * C; g.K = C; g.ldc = 4 * C;
@@ -796,6 +813,52 @@ static __global__ void wsplit_rows_kernel(const float* __restrict__ src, __half*
   const __half hi = __float2half_rn(v);
   dst[r * 2 * (size_t)K + k] = hi;
   dst[r * 2 * (size_t)K + K + k] = __float2half_rn(v - __half2float(hi));
+}
+
+static __global__ void scale_kernel(const float* __restrict__ in, float* __restrict__ out, size_t n, float s) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[i] * s;
+}
+
+// Stand-alone LeFF block for the unit tests: x[M][C] += Linear2(GELU(dwconv3x3(GELU(Linear1(A))))) on n images of H x H
+// tokens, all tensors fp32 on the device (A = the LayerNorm-2 output; W1 [4C][C], b1 [4C], dw_w [9][4C] tap-major,
+// dw_b [4C], W2 [C][4C], b2 [C]); operands are converted on the fly.  precise = 0: fp16 operands, tanh-form GELU;
+// precise = 1: fp16 activations x (hi + lo) fp16 weights, erf-form GELU (the WMK_PREC_MIXED extractor).
+extern "C" int wmk_leff_block_f32(const float* A, const float* W1, const float* b1, const float* dw_w, const float* dw_b,
+                                  const float* W2, const float* b2, float* x, int n, int H, int C, int precise, void* stream) {
+  WMK_REQUIRE(A && W1 && b1 && dw_w && dw_b && W2 && b2 && x && n > 0, "leff_block: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t M = (size_t)n * H * H, K4 = 4 * (size_t)C;
+  __half *a16 = nullptr, *w1 = nullptr, *w2 = nullptr;
+  float *b1s = nullptr, *dws = nullptr, *dbs = nullptr, *w1s = nullptr;
+  const int wt = precise ? 2 : 1;
+  WMK_CHECK_CUDA(cudaMallocAsync(&a16, M * C * 2, st));
+  WMK_CHECK_CUDA(cudaMallocAsync(&w1, K4 * C * 2 * wt, st));
+  WMK_CHECK_CUDA(cudaMallocAsync(&w2, K4 * C * 2 * wt, st));
+  WMK_CHECK_CUDA(cudaMallocAsync(&b1s, K4 * 4, st));
+  WMK_CHECK_CUDA(cudaMallocAsync(&dws, 9 * K4 * 4, st));
+  WMK_CHECK_CUDA(cudaMallocAsync(&dbs, K4 * 4, st));
+  WMK_CHECK_CUDA(cudaMallocAsync(&w1s, K4 * C * 4, st));
+  copy_cols_kernel<__half><<<cdiv(M * (C / 4), 256), 256, 0, st>>>(A, a16, M, C, C, 0);
+  WMK_CHECK_LAUNCH("copy_cols_kernel");
+  const float sc = precise ? 1.0f : 0.5f;            // plain plans fold the GELU's 0.5 into W1 / b1 / dw (pack_block)
+  scale_kernel<<<cdiv(K4 * C, 256), 256, 0, st>>>(W1, w1s, K4 * C, sc);
+  scale_kernel<<<cdiv(K4, 256), 256, 0, st>>>(b1, b1s, K4, sc);
+  scale_kernel<<<cdiv(9 * K4, 256), 256, 0, st>>>(dw_w, dws, 9 * K4, sc);
+  scale_kernel<<<cdiv(K4, 256), 256, 0, st>>>(dw_b, dbs, K4, sc);
+  count_launch(4);
+  if (precise) {
+    wsplit_rows_kernel<<<cdiv(K4 * C, 256), 256, 0, st>>>(w1s, w1, K4, C);
+    wsplit_rows_kernel<<<cdiv(K4 * C, 256), 256, 0, st>>>(W2, w2, (size_t)C, (int)K4);
+  } else {
+    copy_cols_kernel<__half><<<cdiv(K4 * (C / 4), 256), 256, 0, st>>>(w1s, w1, K4, C, C, 0);
+    copy_cols_kernel<__half><<<cdiv((size_t)C * (K4 / 4), 256), 256, 0, st>>>(W2, w2, (size_t)C, (int)K4, (int)K4, 0);
+  }
+  count_launch(2);
+  const int s = leff_block(a16, w1, w2, b1s, dws, dbs, b2, x, n, H, C, 1, precise, st);
+  cudaFreeAsync(a16, st); cudaFreeAsync(w1, st); cudaFreeAsync(w2, st); cudaFreeAsync(b1s, st);
+  cudaFreeAsync(dws, st); cudaFreeAsync(dbs, st); cudaFreeAsync(w1s, st);
+  return s;
 }
 
 extern "C" int wmk_linear_f32(const float* A, const float* W, const float* bias, float* C, int M, int N, int K,

@@ -341,6 +341,14 @@ int wmk_uformer_autoencode(wmk_plan* plan, const float* msg, int msg_stride, int
 int wmk_plan_enable_taps(wmk_plan* plan, int enable);
 int wmk_plan_get_tap(wmk_plan* plan, const char* name, float* out, size_t capacity, size_t* n_out);
 
+/* Stand-alone fused LeFF block (uformerWM/model.py:683-714) used by the unit tests:
+ * x[M][C] += Linear2(GELU(DepthwiseConv3x3(GELU(Linear1(A))))) on n images of H x H tokens (M = n H H), one tcgen05 kernel
+ * (csrc/leff_block.cu: the 4C-wide hidden tensor never reaches HBM).  All tensors fp32 on the device: A [M][C] (the
+ * LayerNorm-2 output), W1 [4C][C], b1 [4C], dw_w [9][4C] (tap-major), dw_b [4C], W2 [C][4C], b2 [C]; operands are converted on
+ * the fly.  precise = 0: fp16 operands, tanh-form GELU; 1: fp16 activations x (hi + lo) fp16 weights, erf-form GELU.
+ * C in {32, 64, 128}, H a power of two in [16, 128]. */
+int wmk_leff_block_f32(const float* A, const float* W1, const float* b1, const float* dw_w, const float* dw_b,
+                       const float* W2, const float* b2, float* x, int n, int H, int C, int precise, void* stream);
 /* Stand-alone dense op used by the unit tests and the roofline bench:
  * C[M][N] = A[M][K] * W[N][K]^T + bias[N], fp32 in HBM in and out; precision selects the fp32 SIMT kernel
  * (WMK_PREC_FP32) or the tcgen05 kernel with bf16 / fp16 operands (WMK_PREC_BF16 / WMK_PREC_F16), split-bf16 A and

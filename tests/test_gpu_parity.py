@@ -92,6 +92,40 @@ def test_linear_matches_matmul(prec, shape):
         assert maxrel(C.cpu(), ref.cpu()) < tol, (shape, prec, gelu)
 
 
+@pytest.mark.parametrize("precise", [0, 1])
+@pytest.mark.parametrize("geom", [(3, 16, 32), (2, 32, 64), (2, 16, 128), (1, 64, 64), (5, 32, 128), (1, 128, 32)])
+def test_fused_leff_block_matches_torch(geom, precise):
+    """csrc/leff_block.cu (linear1 -> GELU -> depthwise 3x3 -> GELU -> linear2 + residual in one tcgen05 kernel) vs the
+    LeFF of `uformerWM/model.py:695-714` in float64, incl. image borders (zero padding of the HIDDEN tensor), several tiles
+    per image, several images, every supported width.  Tolerance: the fp16 rounding of the activations (2^-11)."""
+    from image_in_speech_watermarking_b200 import _lib
+    lib = _lib.load()
+    n, H, C = geom
+    g = torch.Generator().manual_seed(n * 1000 + H + C + precise)
+    M = n * H * H
+    A = torch.randn(M, C, generator=g)
+    x = torch.randn(M, C, generator=g)
+    W1 = torch.randn(4 * C, C, generator=g) * (0.7 / C ** 0.5)
+    b1 = torch.randn(4 * C, generator=g) * 0.1
+    dw = torch.randn(4 * C, 1, 3, 3, generator=g) * 0.3
+    db = torch.randn(4 * C, generator=g) * 0.1
+    W2 = torch.randn(C, 4 * C, generator=g) * (0.7 / (4 * C) ** 0.5)
+    b2 = torch.randn(C, generator=g) * 0.1
+    F = torch.nn.functional
+    h = F.gelu(F.linear(A.half().double(), W1.double(), b1.double()))
+    h = h.view(n, H, H, 4 * C).permute(0, 3, 1, 2)
+    h = F.gelu(F.conv2d(h, dw.double(), db.double(), padding=1, groups=4 * C)).permute(0, 2, 3, 1).reshape(M, 4 * C)
+    ref = x.double() + F.linear(h, W2.double(), b2.double())
+    dwt = dw.reshape(4 * C, 9).t().contiguous()                      # tap-major [9][4C]
+    xd = x.clone().cuda()
+    args = [t.cuda().contiguous() for t in (A, W1, b1, dwt, db, W2, b2)]
+    _lib.check(lib.wmk_leff_block_f32(*[_lib.ptr(t) for t in args], _lib.ptr(xd), n, H, C, precise, _lib.stream_ptr()))
+    got = xd.cpu().double()
+    assert torch.isfinite(got).all()
+    err = float((got - ref).abs().max() / (ref - x.double()).abs().max())
+    assert err < (1.5e-3 if precise else 3e-3), (geom, precise, err)
+
+
 # --------------------------------------------------------------------------------- front end
 @pytest.mark.parametrize("L", [16000, 8002, 48000, 63 * 127 + 1, 63 * 127, 5000, 160000])
 def test_stft_istft_match_oracle(L):
