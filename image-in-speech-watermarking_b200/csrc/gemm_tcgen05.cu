@@ -319,6 +319,7 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __
           if (p.conv_H > 0) {          // implicit GEMM: tap kb of the 3x3 window = the image row shifted by (dy-1, dx-1)
             const int rowi = m0 >> 7, img = rowi / p.conv_H, h = rowi - img * p.conv_H;
             tma_load_4d(sa, &tmA, 0, kb % 3 - 1, h + kb / 3 - 1, img, full_bar(s));
+            if (!w_stationary) tma_load_2d(sa + A_STAGE, &tmW, kb * BK, n0, full_bar(s));
           } else if (split == 1) {
             tma_load_2d(sa, &tmA, kb * BK, m0, full_bar(s));                       // hi
             tma_load_2d(sa + A_BYTES, &tmA, K + kb * BK, m0, full_bar(s));         // lo

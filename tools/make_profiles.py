@@ -26,7 +26,7 @@ def short(name):
 
 
 def family(name):
-    for key, fam in (("gemm_tcgen05", "gemm"), ("attention", "attention"), ("dwconv", "dwconv"), ("layernorm", "layernorm"),
+    for key, fam in (("leff_block", "leff_fused"), ("gemm_tcgen05", "gemm"), ("attention", "attention"), ("dwconv", "dwconv"), ("layernorm", "layernorm"),
                      ("im2col", "layout"), ("copy_cols", "layout"), ("stft", "frontend"), ("iir", "attack"), ("awgn", "attack")):
         if key in name:
             return fam
