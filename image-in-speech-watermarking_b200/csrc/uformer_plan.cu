@@ -20,8 +20,10 @@ namespace wmk {
 namespace tc { int num_sms(); }
 int stft_clips(const float* wave, int B, int L, float* clips, int n_clips, cudaStream_t st);
 int istft_clips(const float* clips, int B, int n_clips, int T, float* wave, int length, cudaStream_t st);
-int leff_block(const void* A, const void* W1, const void* W2, const float* b1, const float* dw_w, const float* dw_b,
-               const float* b2, float* x, int n, int H, int C, int f16, int precise, cudaStream_t st);
+int leff_block(const void* A, const void* W1, const void* W2, const float* b1, const uint16_t* dw16, const float* dw_b,
+               const float* b2, float* x, int n, int H, int C, int precise, cudaStream_t st);
+int attn_block(const void* A, const void* Wh, const float* bqkv, const uint16_t* bias, uint16_t* out, int n, int H, int C,
+               int shift, cudaStream_t st);
 int dwconv3x3_gelu_op16(const void* in, void* out, const float* wt, const float* bias, int B, int H, int Ch, int f16,
                         cudaStream_t st);
 
@@ -42,6 +44,12 @@ struct BlockW {
   void *w_qkv = nullptr, *w_proj = nullptr, *w_l1 = nullptr, *w_l2 = nullptr;
   float *b_qkv = nullptr, *b_proj = nullptr, *b_l1 = nullptr, *b_l2 = nullptr, *dw_w = nullptr, *dw_b = nullptr;
   float *dw_wh = nullptr, *dw_bh = nullptr;      // 0.5 x the depthwise weights / bias (dwconv_tma.cu folds the GELU's 0.5)
+  // fused q|k|v projection + attention (attn_block.cu): per-head weights [heads][q|k|v (96)][C] fp16, biases [heads][96],
+  // relative-position bias [heads][64][64] fp16 in quad order (x log2 e)
+  void* w_qkv_heads = nullptr;
+  float* b_qkv_heads = nullptr;
+  uint16_t* bias_quad = nullptr;
+  uint16_t* dw16 = nullptr;                      // fused LeFF (leff_block.cu): fp16 [9][4C] of dw_wh, or [2][9][4C] = hi, lo of dw_w (precise)
 };
 
 struct EncW {
@@ -106,6 +114,23 @@ int upload_f32(wmk_plan* P, const std::vector<float>& v, float** out) {
   P->allocs.push_back(d);
   WMK_CHECK_CUDA(cudaMemcpy(d, v.data(), v.size() * 4, cudaMemcpyHostToDevice));
   *out = d;
+  return 0;
+}
+
+// fp16 copy of a float vector (sets = 1), or its (hi, lo) fp16 pair as two consecutive sets (sets = 2)
+int upload_f16_sets(wmk_plan* P, const std::vector<float>& v, int sets, uint16_t** out) {
+  std::vector<__half> h(v.size() * (size_t)sets);
+  for (size_t i = 0; i < v.size(); ++i) {
+    const float c = v[i] > 65504.f ? 65504.f : (v[i] < -65504.f ? -65504.f : v[i]);
+    const __half hi = __float2half_rn(c);
+    h[i] = hi;
+    if (sets == 2) h[v.size() + i] = __float2half_rn(c - __half2float(hi));
+  }
+  void* d = nullptr;
+  if (cudaMalloc(&d, h.size() * 2) != cudaSuccess) { set_error("cudaMalloc of %zu bytes failed", h.size() * 2); return WMK_ERR_ALLOC; }
+  P->allocs.push_back(d);
+  WMK_CHECK_CUDA(cudaMemcpy(d, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
+  *out = reinterpret_cast<uint16_t*>(d);
   return 0;
 }
 
@@ -207,6 +232,29 @@ int pack_block(wmk_plan* P, const std::string& p, int C, int heads, int H, int s
   for (int i = 0; i < 2 * C; ++i) bqkv[C + i] = bkv->data[i];
   WMK_TRY(upload_op(P, wqkv, &w->w_qkv, mode, C));
   WMK_TRY(upload_f32(P, bqkv, &w->b_qkv));
+  if (mode == 3 && C <= 128) {
+    // attn_block.cu operands: head h owns rows [q_h | k_h | v_h]; window rows in quad order (four 4x4 sub-blocks)
+    std::vector<float> wh((size_t)heads * 96 * C), bh((size_t)heads * 96), bq((size_t)heads * 4096);
+    for (int h = 0; h < heads; ++h)
+      for (int part = 0; part < 3; ++part)
+        for (int d = 0; d < 32; ++d) {
+          const size_t src = (size_t)part * C + h * 32 + d, dst = (size_t)h * 96 + part * 32 + d;
+          for (int c = 0; c < C; ++c) wh[dst * C + c] = wqkv[src * C + c];
+          bh[dst] = bqkv[src];
+        }
+    auto pos = [](int r, int& i, int& j) { const int sb = r >> 4; i = ((sb >> 1) << 2) | ((r >> 2) & 3); j = ((sb & 1) << 2) | (r & 3); };
+    for (int h = 0; h < heads; ++h)
+      for (int r = 0; r < 64; ++r)
+        for (int c = 0; c < 64; ++c) {
+          int ri, rj, ci, cj;
+          pos(r, ri, rj);
+          pos(c, ci, cj);
+          bq[((size_t)h * 64 + r) * 64 + c] = bias[((size_t)h * 64 + (ri * 8 + rj)) * 64 + (ci * 8 + cj)];
+        }
+    WMK_TRY(upload_op(P, wh, &w->w_qkv_heads, 3, C));
+    WMK_TRY(upload_f32(P, bh, &w->b_qkv_heads));
+    WMK_TRY(upload_f16_sets(P, bq, 1, &w->bias_quad));
+  }
   const HostTensor* t;
   WMK_TRY(get(P, p + "attn.proj.weight", (size_t)C * C, &t));
   WMK_TRY(upload_op(P, t->data, &w->w_proj, mode, C));
@@ -234,6 +282,7 @@ int pack_block(wmk_plan* P, const std::string& p, int C, int heads, int H, int s
     for (int tap = 0; tap < 9; ++tap) dwt[(size_t)tap * 4 * C + c] = dw->data[(size_t)c * 9 + tap];
   WMK_TRY(upload_f32(P, dwt, &w->dw_w));
   WMK_TRY(get_f32(P, p + "mlp.dwconv.0.bias", 4 * (size_t)C, &w->dw_b));
+  if (mode == 2) WMK_TRY(upload_f16_sets(P, dwt, 2, &w->dw16));
   if (mode == 1 || mode == 3) {
     const HostTensor* db;
     WMK_TRY(get(P, p + "mlp.dwconv.0.bias", 4 * (size_t)C, &db));
@@ -242,6 +291,7 @@ int pack_block(wmk_plan* P, const std::string& p, int C, int heads, int H, int s
     for (size_t i = 0; i < bh.size(); ++i) bh[i] = db->data[i] * 0.5f;
     WMK_TRY(upload_f32(P, dwt, &w->dw_wh));
     WMK_TRY(upload_f32(P, bh, &w->dw_bh));
+    if (mode == 3) WMK_TRY(upload_f16_sets(P, dwt, 1, &w->dw16));
   }
   return 0;
 }
@@ -365,10 +415,17 @@ int run_block(wmk_plan* P, const BlockW& w, float* x, int n, cudaStream_t st, bo
     WMK_CHECK_LAUNCH("layernorm_kernel");
   }
   GemmArgs g;
+  static const int fused_attn = getenv("WMK_FUSED_ATTN") ? atoi(getenv("WMK_FUSED_ATTN")) : 0;
+  const bool attn_fused = fused_attn && MODE == 3 && C <= 128 && H >= 16 && w.w_qkv_heads;
+  if (attn_fused) {
+    // q|k|v projection + window attention in ONE tcgen05 kernel (attn_block.cu): q, k, v never reach HBM
+    WMK_TRY(attn_block(P->bufA, w.w_qkv_heads, w.b_qkv_heads, w.bias_quad, reinterpret_cast<uint16_t*>(P->bufO), n, H, C, w.shift, st));
+  } else {
   g.A = P->bufA; g.W = w.w_qkv; g.bias = w.b_qkv; g.C = P->bufQKV; g.M = M; g.N = 3 * C; g.K = C; g.ldc = 3 * C;
   g.epi = EPI_BIAS; g.out_bf16 = ob; g.split = PRECISE; g.f16 = F16;
   WMK_TRY(gemm(MODE, g, st));
-  {
+  }
+  if (!attn_fused) {
     ProfScope prof(FAM_ATTENTION, 256.0 * C * M, st);
     const int n_windows = n * (H / 8) * (H / 8);
     if constexpr (P16 || PRECISE) {
@@ -398,9 +455,8 @@ int run_block(wmk_plan* P, const BlockW& w, float* x, int n, cudaStream_t st, bo
     // the whole LeFF (linear1 -> GELU -> depthwise 3x3 -> GELU -> linear2 + residual) in ONE tcgen05 kernel: the 4C-wide
     // hidden tensor stays in shared memory (leff_block.cu); C <= 128, 16 x 8 pixel tiles
     static const int fused = getenv("WMK_FUSED_LEFF") ? atoi(getenv("WMK_FUSED_LEFF")) : 0;
-    if (fused && C <= 128 && H >= 16) {
-      WMK_TRY(leff_block(P->bufA, w.w_l1, w.w_l2, w.b_l1, PRECISE ? w.dw_w : w.dw_wh, PRECISE ? w.dw_b : w.dw_bh, w.b_l2, x, n, H,
-                         C, F16, PRECISE, st));
+    if (fused && F16 && C <= 128 && H >= 16) {
+      WMK_TRY(leff_block(P->bufA, w.w_l1, w.w_l2, w.b_l1, w.dw16, PRECISE ? w.dw_b : w.dw_bh, w.b_l2, x, n, H, C, PRECISE, st));
       if (fuse_ln && next) {               // the next block expects its norm1 in bufA
         ProfScope prof(FAM_LAYERNORM, (double)M * C * (4 + ln1_bytes), st);
         launch_layernorm<OpT>(x, reinterpret_cast<OpT*>(P->bufA), next->ln1_w, next->ln1_b, next->mod, M, C, H, next->shift, st);
@@ -831,6 +887,7 @@ extern "C" int wmk_leff_block_f32(const float* A, const float* W1, const float* 
   const size_t M = (size_t)n * H * H, K4 = 4 * (size_t)C;
   __half *a16 = nullptr, *w1 = nullptr, *w2 = nullptr;
   float *b1s = nullptr, *dws = nullptr, *dbs = nullptr, *w1s = nullptr;
+  __half* dw16 = nullptr;
   const int wt = precise ? 2 : 1;
   WMK_CHECK_CUDA(cudaMallocAsync(&a16, M * C * 2, st));
   WMK_CHECK_CUDA(cudaMallocAsync(&w1, K4 * C * 2 * wt, st));
@@ -839,6 +896,7 @@ extern "C" int wmk_leff_block_f32(const float* A, const float* W1, const float* 
   WMK_CHECK_CUDA(cudaMallocAsync(&dws, 9 * K4 * 4, st));
   WMK_CHECK_CUDA(cudaMallocAsync(&dbs, K4 * 4, st));
   WMK_CHECK_CUDA(cudaMallocAsync(&w1s, K4 * C * 4, st));
+  WMK_CHECK_CUDA(cudaMallocAsync(&dw16, 9 * K4 * 2 * wt, st));
   copy_cols_kernel<__half><<<cdiv(M * (C / 4), 256), 256, 0, st>>>(A, a16, M, C, C, 0);
   WMK_CHECK_LAUNCH("copy_cols_kernel");
   const float sc = precise ? 1.0f : 0.5f;            // plain plans fold the GELU's 0.5 into W1 / b1 / dw (pack_block)
@@ -855,7 +913,14 @@ extern "C" int wmk_leff_block_f32(const float* A, const float* W1, const float* 
     copy_cols_kernel<__half><<<cdiv((size_t)C * (K4 / 4), 256), 256, 0, st>>>(W2, w2, (size_t)C, (int)K4, (int)K4, 0);
   }
   count_launch(2);
-  const int s = leff_block(a16, w1, w2, b1s, dws, dbs, b2, x, n, H, C, 1, precise, st);
+  if (precise) {      // the 9 x 4C depthwise weights as ONE row of (hi | lo) = the two sets
+    wsplit_rows_kernel<<<cdiv(9 * K4, 256), 256, 0, st>>>(dws, dw16, 1, (int)(9 * K4));
+  } else {
+    copy_cols_kernel<__half><<<cdiv(9 * K4 / 4, 256), 256, 0, st>>>(dws, dw16, 1, (int)(9 * K4), (int)(9 * K4), 0);
+  }
+  count_launch(1);
+  const int s = leff_block(a16, w1, w2, b1s, reinterpret_cast<const uint16_t*>(dw16), dbs, b2, x, n, H, C, precise, st);
+  cudaFreeAsync(dw16, st);
   cudaFreeAsync(a16, st); cudaFreeAsync(w1, st); cudaFreeAsync(w2, st); cudaFreeAsync(b1s, st);
   cudaFreeAsync(dws, st); cudaFreeAsync(dbs, st); cudaFreeAsync(w1s, st);
   return s;

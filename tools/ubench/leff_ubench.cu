@@ -5,14 +5,15 @@
 // Prints per shape: microseconds, cycles per 64-channel chunk per SM (at the nominal 1.7 GHz), effective TFLOP/s.
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
+#include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
 
 #include <vector>
 
 namespace wmk {
-int leff_block(const void* A, const void* W1, const void* W2, const float* b1, const float* dw_w, const float* dw_b,
-               const float* b2, float* x, int n, int H, int C, int f16, int precise, cudaStream_t st);
+int leff_block(const void* A, const void* W1, const void* W2, const float* b1, const uint16_t* dw16, const float* dw_b,
+               const float* b2, float* x, int n, int H, int C, int precise, cudaStream_t st);
 }
 extern "C" const char* wmk_last_error(void);
 
@@ -46,29 +47,30 @@ int main(int argc, char** argv) {
     const int C = s.C, H = s.H, wt = precise ? 2 : 1;
     const size_t M = (size_t)clips * H * H, K4 = 4 * (size_t)C;
     __half *A, *W1, *W2;
-    float *b1, *dw, *db, *b2, *x;
+    float *b1, *db, *b2, *x;
+    __half* dw;
     cudaMalloc(&A, M * C * 2); cudaMalloc(&W1, K4 * C * 2 * wt); cudaMalloc(&W2, K4 * C * 2 * wt);
-    cudaMalloc(&b1, K4 * 4); cudaMalloc(&dw, 9 * K4 * 4); cudaMalloc(&db, K4 * 4); cudaMalloc(&b2, C * 4);
+    cudaMalloc(&b1, K4 * 4); cudaMalloc(&dw, 9 * K4 * 2 * wt); cudaMalloc(&db, K4 * 4); cudaMalloc(&b2, C * 4);
     cudaMalloc(&x, M * C * 4);
     auto blocks = [](size_t n) { return (unsigned)((n + 255) / 256); };
     fill_half<<<blocks(M * C), 256>>>(A, M * C, 1.0f, 1);
     fill_half<<<blocks(K4 * C * wt), 256>>>(W1, K4 * C * wt, 0.1f, 2);
     fill_half<<<blocks(K4 * C * wt), 256>>>(W2, K4 * C * wt, 0.05f, 3);
     fill_float<<<blocks(K4), 256>>>(b1, K4, 0.1f, 4);
-    fill_float<<<blocks(9 * K4), 256>>>(dw, 9 * K4, 0.2f, 5);
+    fill_half<<<blocks(9 * K4 * wt), 256>>>(dw, 9 * K4 * wt, 0.2f, 5);
     fill_float<<<blocks(K4), 256>>>(db, K4, 0.1f, 6);
     fill_float<<<blocks(C), 256>>>(b2, C, 0.1f, 7);
     cudaMemset(x, 0, M * C * 4);
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     int rc = 0;
-    for (int i = 0; i < 2 && !rc; ++i) rc = wmk::leff_block(A, W1, W2, b1, dw, db, b2, x, clips, H, C, 1, precise, 0);
+    for (int i = 0; i < 2 && !rc; ++i) rc = wmk::leff_block(A, W1, W2, b1, (const uint16_t*)dw, db, b2, x, clips, H, C, precise, 0);
     if (rc || cudaDeviceSynchronize() != cudaSuccess) {
       printf("C=%d H=%d: not run (%s / %s)\n", C, H, wmk_last_error(), cudaGetErrorString(cudaGetLastError()));
     } else {
       const int iters = 5;
       cudaEventRecord(e0);
-      for (int i = 0; i < iters; ++i) wmk::leff_block(A, W1, W2, b1, dw, db, b2, x, clips, H, C, 1, precise, 0);
+      for (int i = 0; i < iters; ++i) wmk::leff_block(A, W1, W2, b1, (const uint16_t*)dw, db, b2, x, clips, H, C, precise, 0);
       cudaEventRecord(e1);
       cudaEventSynchronize(e1);
       float ms = 0;
