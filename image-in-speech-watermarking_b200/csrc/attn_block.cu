@@ -99,11 +99,12 @@ attn_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int KC = g.KC;
   const uint32_t wsm = base;                                               // [NH][KC][96 x 128 B]
   const uint32_t asm_ = wsm + (uint32_t)(NH * KC) * AB_WTILE;              // [a_st][KC][16 KB]
-  const uint32_t qksm = asm_ + (uint32_t)(g.a_st * KC) * AB_ATILE;         // [128 x 64]: q (cols 0-31) | k (cols 32-63) of the head
-  const uint32_t vtsm = qksm + AB_ATILE;                                   // V^T
-  const uint32_t psm = vtsm + AB_VT;                                       // P: two key k-blocks of [128 x 64]
+  constexpr bool BIAS_SMEM = C <= 64;                                      // C = 128: the table stays in global memory (L1 / L2)
+  const uint32_t qksm = asm_ + (uint32_t)(g.a_st * KC) * AB_ATILE;         // [2][128 x 64]: q (cols 0-31) | k (cols 32-63) of a head
+  const uint32_t vtsm = qksm + 2u * AB_ATILE;                              // [2] V^T
+  const uint32_t psm = vtsm + 2u * AB_VT;                                  // P: two key k-blocks of [128 x 64]
   const uint32_t biassm = psm + 2u * AB_ATILE;                             // [NH][64 rows x 128 B], 16-byte chunks XOR (row & 7)
-  const uint32_t smaxsm = biassm + (uint32_t)NH * 8192u;                   // [2][4][128] float
+  const uint32_t smaxsm = biassm + (BIAS_SMEM ? (uint32_t)NH * 8192u : 0u);   // [2][4][128] float
   const uint32_t ssumsm = smaxsm + 4096u;                                  // [2][4][128] float
   const uint32_t bars = ssumsm + 4096u;
   const uint32_t wfull = bars;
@@ -141,7 +142,7 @@ attn_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   // the bias tables (fp16, 16-byte chunks swizzled by the row) and the never-written zero blocks of P
   {
     const uint4* src = reinterpret_cast<const uint4*>(g.bias);
-    for (int i = threadIdx.x; i < NH * 64 * 8; i += AB_THREADS) {       // 16-byte chunks
+    for (int i = threadIdx.x; BIAS_SMEM && i < NH * 64 * 8; i += AB_THREADS) {       // 16-byte chunks
       const int row = i >> 3, c = i & 7;
       *reinterpret_cast<uint4*>(smem_raw + (biassm - raw) + (uint32_t)row * 128u + (uint32_t)((c ^ (row & 7)) << 4)) = src[i];
     }
@@ -191,9 +192,13 @@ attn_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (lane == 0) {
       const uint32_t idesc_qkv = umma_idesc(96, true), idesc_s = umma_idesc(128, true), idesc_pv = umma_idesc(32, true);
       mbar_wait(wfull, 0);
-      int gh = 0;
-      auto issue_qkv = [&](int gq, int h, int ab) {
-        const int b = gq & 1;
+      const int T = my_tiles * NH;
+      auto issue_qkv = [&](int gq) {
+        const int lt = gq / NH, h = gq - lt * NH, ab = lt % g.a_st, b = gq & 1;
+        if (h == 0) {
+          mbar_wait(afull(ab), ((uint32_t)(lt / g.a_st)) & 1u);
+          tcgen05_fence_after();
+        }
         mbar_wait(qkvempty(b), (((uint32_t)(gq >> 1)) & 1u) ^ 1u);
         tcgen05_fence_after();
         const uint32_t tacc = tmem_base + (uint32_t)(b * 128);
@@ -207,45 +212,38 @@ attn_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
         }
         tcgen05_commit(qkvfull(b));
+        if (h == NH - 1) tcgen05_commit(aempty(ab));          // the A tile is free once the last head's projection retires
       };
-      for (int lt = 0; lt < my_tiles; ++lt) {
-        const int ab = lt % g.a_st;
-        mbar_wait(afull(ab), ((uint32_t)(lt / g.a_st)) & 1u);
+      int gq = 0;                                              // next projection to issue: two heads ahead of the attention
+      for (; gq < T && gq < 2; ++gq) issue_qkv(gq);
+      for (int gh = 0; gh < T; ++gh) {
+        const int pb = gh & 1;
+        // S = Q K^T
+        mbar_wait(qksmfull, (uint32_t)gh & 1u);
+        mbar_wait(sempty, ((uint32_t)gh & 1u) ^ 1u);
         tcgen05_fence_after();
-        issue_qkv(gh, 0, ab);
-        if (NH == 1) tcgen05_commit(aempty(ab));
-        for (int h = 0; h < NH; ++h, ++gh) {
-          if (h + 1 < NH) {
-            issue_qkv(gh + 1, h + 1, ab);
-            if (h + 2 == NH) tcgen05_commit(aempty(ab));      // the A tile is free once the last head's projection retires
-          }
-          // S = Q K^T
-          mbar_wait(qksmfull, (uint32_t)gh & 1u);
-          mbar_wait(sempty, ((uint32_t)gh & 1u) ^ 1u);
-          tcgen05_fence_after();
-          {
-            const uint64_t qd = umma_desc_sw128(qksm);
+        {
+          const uint64_t qd = umma_desc_sw128(qksm + (uint32_t)pb * AB_ATILE);
 #pragma unroll
-            for (int k = 0; k < 2; ++k)
-              tcgen05_mma_bf16(tmem_base + 256u, qd + (uint64_t)(2 * k), qd + (uint64_t)(4 + 2 * k), idesc_s, (uint32_t)(k != 0));
-            tcgen05_commit(sfull);
-          }
-          // O_h = P V
-          const int ob = gh & 1;
-          mbar_wait(pfull, (uint32_t)gh & 1u);
-          mbar_wait(oempty(ob), (((uint32_t)(gh >> 1)) & 1u) ^ 1u);
-          tcgen05_fence_after();
-#pragma unroll
-          for (int kb = 0; kb < 2; ++kb) {
-            const uint64_t pd = umma_desc_sw128(psm + (uint32_t)kb * AB_ATILE);
-            const uint64_t vd = umma_desc_sw128(vtsm + (uint32_t)kb * 4096u);
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              tcgen05_mma_bf16(tmem_base + (uint32_t)(384 + ob * 32), pd + (uint64_t)(2 * k), vd + (uint64_t)(2 * k), idesc_pv,
-                               (uint32_t)((kb | k) != 0));
-          }
-          tcgen05_commit(ofull(ob));
+          for (int k = 0; k < 2; ++k)
+            tcgen05_mma_bf16(tmem_base + 256u, qd + (uint64_t)(2 * k), qd + (uint64_t)(4 + 2 * k), idesc_s, (uint32_t)(k != 0));
+          tcgen05_commit(sfull);
         }
+        if (gq < T) { issue_qkv(gq); ++gq; }                   // its accumulator (head gh's) has been drained: qksmfull
+        // O_h = P V
+        mbar_wait(pfull, (uint32_t)gh & 1u);
+        mbar_wait(oempty(pb), (((uint32_t)(gh >> 1)) & 1u) ^ 1u);
+        tcgen05_fence_after();
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb) {
+          const uint64_t pd = umma_desc_sw128(psm + (uint32_t)kb * AB_ATILE);
+          const uint64_t vd = umma_desc_sw128(vtsm + (uint32_t)pb * AB_VT + (uint32_t)kb * 4096u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            tcgen05_mma_bf16(tmem_base + (uint32_t)(384 + pb * 32), pd + (uint64_t)(2 * k), vd + (uint64_t)(2 * k), idesc_pv,
+                             (uint32_t)((kb | k) != 0));
+        }
+        tcgen05_commit(ofull(pb));
       }
     }
   } else if (warp >= AB_W0) {
@@ -284,66 +282,74 @@ attn_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       *reinterpret_cast<uint4*>(g.out + token * C + h * 32 + j4 * 8) = o;
     };
 
+    auto qkv_evac = [&](int gq) {                 // q | k | v of head gq -> shared memory (buffer gq & 1)
+      const int b = gq & 1, h = gq & (NH - 1);
+      const float* bp = g.bqkv + h * 96 + j4 * 8;
+      float4 bq0 = __ldg(reinterpret_cast<const float4*>(bp)), bq1 = __ldg(reinterpret_cast<const float4*>(bp + 4));
+      float4 bk0 = __ldg(reinterpret_cast<const float4*>(bp + 32)), bk1 = __ldg(reinterpret_cast<const float4*>(bp + 36));
+      float4 bv0 = __ldg(reinterpret_cast<const float4*>(bp + 64)), bv1 = __ldg(reinterpret_cast<const float4*>(bp + 68));
+      ab_wait(qkvfull(b), ((uint32_t)(gq >> 1)) & 1u);
+      tcgen05_fence_after();
+      uint32_t vq[8], vk[8], vv[8];
+      const uint32_t ta = lane_addr + (uint32_t)(b * 128 + j4 * 8);
+      tmem_ld8(ta, vq);
+      tmem_ld8(ta + 32u, vk);
+      tmem_ld8(ta + 64u, vv);
+      tmem_wait_ld();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(qkvempty(b));
+      const uint32_t row = qksm + (uint32_t)b * AB_ATILE + (uint32_t)r * 128u;
+      st_shared_v4(row + ((((uint32_t)j4) ^ sw) << 4),
+                   pack2_f16(__uint_as_float(vq[0]) + bq0.x, __uint_as_float(vq[1]) + bq0.y),
+                   pack2_f16(__uint_as_float(vq[2]) + bq0.z, __uint_as_float(vq[3]) + bq0.w),
+                   pack2_f16(__uint_as_float(vq[4]) + bq1.x, __uint_as_float(vq[5]) + bq1.y),
+                   pack2_f16(__uint_as_float(vq[6]) + bq1.z, __uint_as_float(vq[7]) + bq1.w));
+      st_shared_v4(row + ((((uint32_t)(4 + j4)) ^ sw) << 4),
+                   pack2_f16(__uint_as_float(vk[0]) + bk0.x, __uint_as_float(vk[1]) + bk0.y),
+                   pack2_f16(__uint_as_float(vk[2]) + bk0.z, __uint_as_float(vk[3]) + bk0.w),
+                   pack2_f16(__uint_as_float(vk[4]) + bk1.x, __uint_as_float(vk[5]) + bk1.y),
+                   pack2_f16(__uint_as_float(vk[6]) + bk1.z, __uint_as_float(vk[7]) + bk1.w));
+      // V^T[d][key r], d = j4*8 + e: key k-block r >> 6, 16-byte chunk (key & 63) >> 3 swizzled by d & 7
+      const float vb[8] = {bv0.x, bv0.y, bv0.z, bv0.w, bv1.x, bv1.y, bv1.z, bv1.w};
+      const uint32_t kk = (uint32_t)(r & 63);
+      uint8_t* vt = gen(vtsm + (uint32_t)b * AB_VT + (uint32_t)(r >> 6) * 4096u + (kk & 7u) * 2u);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const uint32_t d = (uint32_t)(j4 * 8 + e);
+        const __half hv = __float2half_rn(__uint_as_float(vv[e]) + vb[e]);
+        *reinterpret_cast<__half*>(vt + d * 128u + (((kk >> 3) ^ (d & 7u)) << 4)) = hv;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(qksmfull);
+    };
+
+    size_t tok_prev = 0;
+    if (T > 0) qkv_evac(0);
     for (int gh = 0; gh < T; ++gh) {
       const int h = gh & (NH - 1);
-      if (gh > 0) o_evac(gh - 1, tok);           // (the geometry below still describes the tile of head gh - 1)
       if (h == 0) {                               // geometry of the new tile
         int b, wy, wx0;
         tile_at(gh / NH, b, wy, wx0);
         const int wx = wx0 + win;
+        tok_prev = tok;
         tok = ((size_t)b * g.H + ((wy * 8 + pi + g.shift) & (g.H - 1))) * g.H + ((wx * 8 + pj + g.shift) & (g.H - 1));
         const bool lastrow = g.shift > 0 && wy == nW - 1, lastcol = g.shift > 0 && wx == nW - 1;
         maskadd = ((lastrow && (sb >> 1) != (j4 >> 1)) || (lastcol && (sb & 1) != (j4 & 1))) ? AB_MASK : 0.f;
       }
-      // ---------------------------------------------------------------- q | k | v of head h -> shared memory
-      {
-        const int b = gh & 1;
-        const float* bp = g.bqkv + h * 96 + j4 * 8;
-        float4 bq0 = __ldg(reinterpret_cast<const float4*>(bp)), bq1 = __ldg(reinterpret_cast<const float4*>(bp + 4));
-        float4 bk0 = __ldg(reinterpret_cast<const float4*>(bp + 32)), bk1 = __ldg(reinterpret_cast<const float4*>(bp + 36));
-        float4 bv0 = __ldg(reinterpret_cast<const float4*>(bp + 64)), bv1 = __ldg(reinterpret_cast<const float4*>(bp + 68));
-        ab_wait(qkvfull(b), ((uint32_t)(gh >> 1)) & 1u);
-        tcgen05_fence_after();
-        uint32_t vq[8], vk[8], vv[8];
-        const uint32_t ta = lane_addr + (uint32_t)(b * 128 + j4 * 8);
-        tmem_ld8(ta, vq);
-        tmem_ld8(ta + 32u, vk);
-        tmem_ld8(ta + 64u, vv);
-        tmem_wait_ld();
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(qkvempty(b));
-        const uint32_t row = qksm + (uint32_t)r * 128u;
-        st_shared_v4(row + ((((uint32_t)j4) ^ sw) << 4),
-                     pack2_f16(__uint_as_float(vq[0]) + bq0.x, __uint_as_float(vq[1]) + bq0.y),
-                     pack2_f16(__uint_as_float(vq[2]) + bq0.z, __uint_as_float(vq[3]) + bq0.w),
-                     pack2_f16(__uint_as_float(vq[4]) + bq1.x, __uint_as_float(vq[5]) + bq1.y),
-                     pack2_f16(__uint_as_float(vq[6]) + bq1.z, __uint_as_float(vq[7]) + bq1.w));
-        st_shared_v4(row + ((((uint32_t)(4 + j4)) ^ sw) << 4),
-                     pack2_f16(__uint_as_float(vk[0]) + bk0.x, __uint_as_float(vk[1]) + bk0.y),
-                     pack2_f16(__uint_as_float(vk[2]) + bk0.z, __uint_as_float(vk[3]) + bk0.w),
-                     pack2_f16(__uint_as_float(vk[4]) + bk1.x, __uint_as_float(vk[5]) + bk1.y),
-                     pack2_f16(__uint_as_float(vk[6]) + bk1.z, __uint_as_float(vk[7]) + bk1.w));
-        // V^T[d][key r], d = j4*8 + e: key k-block r >> 6, 16-byte chunk (key & 63) >> 3 swizzled by d & 7
-        const float vb[8] = {bv0.x, bv0.y, bv0.z, bv0.w, bv1.x, bv1.y, bv1.z, bv1.w};
-        const uint32_t kk = (uint32_t)(r & 63);
-        uint8_t* vt = gen(vtsm + (uint32_t)(r >> 6) * 4096u + (kk & 7u) * 2u);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const uint32_t d = (uint32_t)(j4 * 8 + e);
-          const __half hv = __float2half_rn(__uint_as_float(vv[e]) + vb[e]);
-          *reinterpret_cast<__half*>(vt + d * 128u + (((kk >> 3) ^ (d & 7u)) << 4)) = hv;
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) mbar_arrive(qksmfull);
-      }
       // ---------------------------------------------------------------- softmax of this row's 16 columns
       {
-        // bias row (fp16, swizzled chunks)
-        const uint8_t* brow = gen(biassm + (uint32_t)h * 8192u + (uint32_t)rw * 128u);
-        const uint4 b0 = *reinterpret_cast<const uint4*>(brow + ((((uint32_t)(j4 * 2)) ^ (uint32_t)(rw & 7)) << 4));
-        const uint4 b1 = *reinterpret_cast<const uint4*>(brow + ((((uint32_t)(j4 * 2 + 1)) ^ (uint32_t)(rw & 7)) << 4));
+        uint4 b0, b1;                             // bias row: 16 fp16 values of this thread's columns
+        if constexpr (BIAS_SMEM) {
+          const uint8_t* brow = gen(biassm + (uint32_t)h * 8192u + (uint32_t)rw * 128u);
+          b0 = *reinterpret_cast<const uint4*>(brow + ((((uint32_t)(j4 * 2)) ^ (uint32_t)(rw & 7)) << 4));
+          b1 = *reinterpret_cast<const uint4*>(brow + ((((uint32_t)(j4 * 2 + 1)) ^ (uint32_t)(rw & 7)) << 4));
+        } else {
+          const uint4* bg = reinterpret_cast<const uint4*>(g.bias + ((size_t)h * 64 + rw) * 64 + j4 * 16);
+          b0 = __ldg(bg);
+          b1 = __ldg(bg + 1);
+        }
         ab_wait(sfull, (uint32_t)gh & 1u);
         tcgen05_fence_after();
         uint32_t v[16];
@@ -368,6 +374,7 @@ attn_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
         for (int i = 0; i < 16; ++i) { s[i] = ab_ex2(s[i] - m); sum += s[i]; }
         ssum[(gh & 1) * 512 + j4 * 128 + r] = sum;
+        if (gh > 0) ab_wait(ofull((gh - 1) & 1), ((uint32_t)((gh - 1) >> 1)) & 1u);      // P V of the previous head has read P (and its V^T)
         const uint32_t prow = psm + (uint32_t)win * AB_ATILE + (uint32_t)r * 128u;
         st_shared_v4(prow + ((((uint32_t)(j4 * 2)) ^ sw) << 4), pack2_f16(s[0], s[1]), pack2_f16(s[2], s[3]), pack2_f16(s[4], s[5]),
                      pack2_f16(s[6], s[7]));
@@ -377,6 +384,8 @@ attn_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         __syncwarp();
         if (lane == 0) mbar_arrive(pfull);
       }
+      if (gh + 1 < T) qkv_evac(gh + 1);           // the S MMA of the next head then runs under the output of the previous one
+      if (gh > 0) o_evac(gh - 1, h == 0 ? tok_prev : tok);
     }
     if (T > 0) o_evac(T - 1, tok);
   }
@@ -400,7 +409,7 @@ int launch_attn_block(const void* A, const void* Wh, const float* bqkv, const ui
   g.n_tiles = n * (H / 8) * (H / 8) / 2;
   g.KC = C >= 64 ? C / 64 : 1; g.ksteps = C >= 64 ? 4 : 2;
   g.bqkv = bqkv; g.bias = bias; g.out = out;
-  const int fixed = 1024 + (int)AB_ATILE + (int)AB_VT + 2 * (int)AB_ATILE + NH * 8192 + 8192 + 256;
+  const int fixed = 1024 + 2 * (int)AB_ATILE + 2 * (int)AB_VT + 2 * (int)AB_ATILE + (C <= 64 ? NH * 8192 : 0) + 8192 + 256;
   g.a_st = 2;
   auto total = [&]() { return fixed + NH * g.KC * (int)AB_WTILE + g.a_st * g.KC * (int)AB_ATILE; };
   if (total() > 227 * 1024) g.a_st = 1;

@@ -415,7 +415,7 @@ int run_block(wmk_plan* P, const BlockW& w, float* x, int n, cudaStream_t st, bo
     WMK_CHECK_LAUNCH("layernorm_kernel");
   }
   GemmArgs g;
-  static const int fused_attn = getenv("WMK_FUSED_ATTN") ? atoi(getenv("WMK_FUSED_ATTN")) : 0;
+  static const int fused_attn = getenv("WMK_FUSED_ATTN") ? atoi(getenv("WMK_FUSED_ATTN")) : 1;
   const bool attn_fused = fused_attn && MODE == 3 && C <= 128 && H >= 16 && w.w_qkv_heads;
   if (attn_fused) {
     // q|k|v projection + window attention in ONE tcgen05 kernel (attn_block.cu): q, k, v never reach HBM
