@@ -409,7 +409,7 @@ def bench_config2(ctx, args):
     world, rank, dev = ctx.world, ctx.rank, ctx.dev
     B = args.utterances
     # all clips of the rank's batch in one pass (12 GEMM-sized passes of 32 clips would be launch bound)
-    chunk = args.chunk or 6 * B
+    chunk = args.chunk or 12 * B          # ... and the clean + attacked extraction (2 x 6 B clips) in ONE extractor pass
     model = UformerAudio(precision=args.precision, clips_per_pass=chunk).cuda().eval()   # reference-style random init
     host_w = SY.synth_speech_batch(rank * B, B, SECONDS).pin_memory()
     host_m = torch.stack([SY.synth_image_binary(rank * B + i) for i in range(B)]).pin_memory()

@@ -217,9 +217,16 @@ def embed_attack_extract(waves, messages, model, attack="closed_loop", draws=Non
     def cpu_of(n):
         return big if one_for_all else n
     x = clips.reshape(B * nc, 2, 128, 128)
-    if model_name == 'uformer':
-        o = model.run(x, msgs, want=("stft_new", "wm", "wm_logits"), msg_map=(cpu_of(nc), K))
-        audio_clips, wm_clean, lg_clean = o["stft_new"], o["wm"], o["wm_logits"]
+    # One extractor pass serves both extractions: the embedder writes y = x + noise (what the in-model clean extraction
+    # reads, `model.py:2508`) into the head of a buffer whose tail receives the clips of the attacked audio, and
+    # `wm_decode` runs once over all of them - no second launch sequence, no concatenation copy.
+    merged = model_name == 'uformer'
+    ext_in = None
+    if merged:
+        nc_att_max = (T + 126) // 128                                                 # attacks never lengthen the audio
+        ext_in = torch.empty((B * (nc + nc_att_max), 2, 128, 128), device=waves.device, dtype=torch.float32)
+        o = model.run(x, msgs, want=("stft_new",), msg_map=(cpu_of(nc), K), y_out=ext_in[:B * nc])
+        audio_clips, wm_clean, lg_clean = o["stft_new"], None, None
     else:
         idx = (torch.arange(B * nc, device=msgs.device) // nc) * K + (torch.arange(B * nc, device=msgs.device) % nc) % K
         audio_clips, wm_clean, lg_clean = _model_embed(model, x, msgs[idx % msgs.shape[0]] if not one_for_all else msgs[:1],
@@ -229,12 +236,23 @@ def embed_attack_extract(waves, messages, model, attack="closed_loop", draws=Non
     att = AT.apply_attack(recon, attack, draws, seed)                                 # :631-660
     Ta = FE.num_frames(att.shape[1])                                                  # == T unless the attack deletes samples
     nc_att = (Ta + 126) // 128                                                        # quirk B-7
-    clips_att = FE.stft_clips(att, max(nc_att, (Ta + 127) // 128))[:, :nc_att].contiguous()
-    clips_att = affine(clips_att, sc, sh)                                             # :691-702
-    if model_name == 'uformer':
-        wm_att, lg_att = model.wm_decode(clips_att.reshape(B * nc_att, 2, 128, 128), return_logits=True)
+    n_alloc = max(nc_att, (Ta + 127) // 128)
+    if merged and n_alloc == nc_att and nc_att <= nc_att_max:
+        tail = ext_in[B * nc:B * (nc + nc_att)]
+        clips_att = FE.stft_clips(att, nc_att, out=tail)
+        if not (sc == 1.0 and sh == 0.0):
+            affine(clips_att, sc, sh, out=tail)                                       # :691-702 (in place)
+        wm_all, lg_all = model.wm_decode(ext_in[:B * (nc + nc_att)], return_logits=True)
+        wm_clean, lg_clean = wm_all[:B * nc], lg_all[:B * nc]
+        wm_att, lg_att = wm_all[B * nc:], lg_all[B * nc:]
     else:
-        wm_att, lg_att = model.decode(clips_att.reshape(B * nc_att, 2, 128, 128)), None
+        clips_att = FE.stft_clips(att, n_alloc)[:, :nc_att].contiguous()
+        clips_att = affine(clips_att, sc, sh)                                         # :691-702
+        if model_name == 'uformer':
+            wm_clean, lg_clean = model.wm_decode(ext_in[:B * nc], return_logits=True)
+            wm_att, lg_att = model.wm_decode(clips_att.reshape(B * nc_att, 2, 128, 128), return_logits=True)
+        else:
+            wm_att, lg_att = model.decode(clips_att.reshape(B * nc_att, 2, 128, 128)), None
     st_att = EV.wave_stats(waves, att)
     st_rec = EV.wave_stats(waves, recon)
     ws_clean = EV.wm_stats_mapped(wm_clean, nc - 1, nc, msgs, cpu_of(nc), K, B)       # last clean clip only: quirk B-8

@@ -16,9 +16,10 @@ def num_frames(L):
     return 1 + (L - 1) // HOP
 
 
-def stft_clips(wave, n_clips=None):
+def stft_clips(wave, n_clips=None, out=None):
     """wave (B, L) float32 CUDA -> clips (B, n_clips, 2, 128, 128).  Default n_clips is the
-    reference's `T // 128 + 1` (`audio_test.py:319-325`, incl. the empty clip when T % 128 == 0)."""
+    reference's `T // 128 + 1` (`audio_test.py:319-325`, incl. the empty clip when T % 128 == 0).
+    `out`: a contiguous float32 buffer of B * n_clips clips to write into (no allocation)."""
     lib = _lib.load()
     if wave.dim() == 1:
         wave = wave[None]
@@ -27,9 +28,12 @@ def stft_clips(wave, n_clips=None):
     T = num_frames(L)
     if n_clips is None:
         n_clips = T // CLIP + 1
-    out = torch.empty((B, n_clips, 2, BINS, CLIP), device=wave.device, dtype=torch.float32)
+    if out is None:
+        out = torch.empty((B, n_clips, 2, BINS, CLIP), device=wave.device, dtype=torch.float32)
+    elif out.numel() != B * n_clips * 2 * BINS * CLIP or not out.is_contiguous() or out.dtype != torch.float32:
+        raise ValueError("stft_clips: `out` must be a contiguous float32 buffer of %d clips" % (B * n_clips))
     _lib.check(lib.wmk_stft_clips_f32(_lib.ptr(wave), B, L, _lib.ptr(out), n_clips, _lib.stream_ptr()))
-    return out
+    return out.view(B, n_clips, 2, BINS, CLIP)
 
 
 def istft_clips(clips, T, length=None):

@@ -183,7 +183,7 @@ class UformerAudio(nn.Module):
             raise _lib.WmkError("UformerAudio has no CPU path: inputs must be CUDA tensors")
         return x.detach().contiguous().float()
 
-    def run(self, x, message, want=("stft_new", "noise", "wm_pred", "wm"), msg_map=None):
+    def run(self, x, message, want=("stft_new", "noise", "wm_pred", "wm"), msg_map=None, y_out=None):
         """One fused pass; returns a dict with the requested outputs (+ 'y', 'wm_logits').
         msg_map = (clips_per_utt, msgs_per_utt): `message` holds the utterances' images ((U * msgs_per_utt, 1, 32, 32))
         and clip c carries image (c // clips_per_utt) * msgs_per_utt + (c % clips_per_utt) % msgs_per_utt - the
@@ -206,6 +206,10 @@ class UformerAudio(nn.Module):
         for k, shp in (("stft_new", (B, 2, 128, 128)), ("noise", (B, 2, 128, 128)), ("y", (B, 2, 128, 128)),
                        ("wm_pred", (B, 1, 32, 32)), ("wm", (B, 1, 32, 32)), ("wm_logits", (B, 1, 32, 32))):
             o[k] = torch.empty(shp, device=x.device, dtype=torch.float32) if k in want else None
+        if y_out is not None:             # y = x + noise written straight into the caller's buffer (the extractor's input)
+            if y_out.numel() != B * 32768 or not y_out.is_contiguous() or y_out.dtype != torch.float32:
+                raise ValueError("y_out must be a contiguous float32 buffer of %d clips" % B)
+            o["y"] = y_out.view(B, 2, 128, 128)
         if o["y"] is None:
             o["y"] = torch.empty((B, 2, 128, 128), device=x.device, dtype=torch.float32)
         with torch.cuda.device(x.device):

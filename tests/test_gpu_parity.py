@@ -630,6 +630,40 @@ def test_tiled_64x64_image_pipeline_matches_oracle(models, weights):
     assert back.shape == (1, 1, 64, 64)
 
 
+def test_config4_10s_tiled_batch_in_benchmarked_precision(models, weights):
+    """BASELINE config 4 at its real shape and in the precision `bench.py` times: 64x64 greyscale images as four tiles in
+    10 s utterances (20 clips each), a batch of two, chained attack.  Utterance 0 is checked against the oracle's loop
+    (recovered image within the fp32-path tolerance; thresholded tiles identical outside the 1e-4 logit margin); the batch
+    sharded the way `sharding.shard_range` cuts it over two ranks gives the per-utterance results of the whole batch."""
+    from image_in_speech_watermarking_b200 import audio_test as PT
+    m = models("mixed", "stress")
+    B = 2
+    waves = SY.synth_speech_batch(40, B, 10.0).cuda()
+    imgs = torch.stack([SY.synth_image_grey(40 + i) for i in range(B)])
+    tiles = PT.tile_image(imgs).cuda()                          # (B,4,1,32,32)
+    rng = np.random.default_rng(4)
+    unit = torch.from_numpy(rng.standard_normal((B, 160000))).float()
+    r = PT.embed_attack_extract(waves, tiles, m, "awgn-20+low_pass", {"awgn": unit})
+    assert r["n_clips"] == 20 and r["n_clips_att"] == 20 and r["wm_att"].shape == (B, 20, 1, 32, 32)
+    ref, ex = P.reconstruct_audio(P.prepare_data(waves[:1].cpu()), None, weights("stress"), attack="awgn-20+low_pass",
+                                  draws={"awgn": unit[0].double().numpy()}, tiles=tiles[0].cpu())
+    assert l2rel(r["recon"][0].cpu().numpy(), ref[1].numpy()) < 1e-3
+    assert maxrel(r["image_att"][0].cpu().numpy(), ex["image_att"]) < 2e-3
+    lg = np.concatenate(ex["logits_att"])                       # (20,1,32,32)
+    got = r["logits_att"][0].cpu().numpy().reshape(lg.shape)
+    safe = np.abs(lg) > LOGIT_MARGIN["mixed"]
+    flips = int(((lg > 0) != (got > 0)).sum())
+    outside = int((((lg > 0) != (got > 0)) & safe).sum())
+    print("\n[config 4, mixed precision] %d pixels, max |dlogit| %.2e, flips %d, outside the 1e-4 margin: %d"
+          % (lg.size, float(np.abs(lg - got).max()), flips, outside))
+    assert outside == 0
+    # strong scaling = the fixed batch cut by utterance: each shard reproduces its rows of the whole-batch result
+    for u in range(B):
+        one = PT.embed_attack_extract(waves[u:u + 1], tiles[u:u + 1], m, "awgn-20+low_pass", {"awgn": unit[u:u + 1]})
+        assert torch.allclose(one["stats"][0], r["stats"][u], rtol=1e-9, atol=1e-12)
+        assert torch.equal(one["logits_att"][0] > 0, r["logits_att"][u] > 0)
+
+
 @pytest.mark.parametrize("audio_scale", ["0.5", "0.01-0.1"])
 def test_audio_scale_normalisation_matches_oracle(audio_scale, models, weights):
     """`audio_scale` of the reference front end / driver (`audio_test.py:33-55,329-341,559-571,691-702`): scaled clips
