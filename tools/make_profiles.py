@@ -26,7 +26,7 @@ def short(name):
 
 
 def family(name):
-    for key, fam in (("leff_block", "leff_fused"), ("gemm_tcgen05", "gemm"), ("attention", "attention"), ("dwconv", "dwconv"), ("layernorm", "layernorm"),
+    for key, fam in (("leff_block", "leff_fused"), ("attn_block", "attention"), ("gemm_tcgen05", "gemm"), ("attention", "attention"), ("dwconv", "dwconv"), ("layernorm", "layernorm"),
                      ("im2col", "layout"), ("copy_cols", "layout"), ("stft", "frontend"), ("iir", "attack"), ("awgn", "attack")):
         if key in name:
             return fam
@@ -105,7 +105,7 @@ def top(tag):
             val(r, "lts__throughput.avg.pct_of_peak_sustained_elapsed"), val(r, "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"),
             val(r, "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active")))
     with open(os.path.join(ROOT, "profiles", tag + "_top_kernels_ncu.md"), "w") as f:
-        f.write("# ncu --set full --clock-control none, first 130 launches of one timed bench step (64 x 3 s), B200\n\n"
+        f.write("# ncu --set full --clock-control none, first launches of one timed bench step (64 x 3 s), B200\n\n"
                 "One row per distinct (kernel, traffic) pair; launches shorter than 20 us omitted.  DRAM GB/s = (dram__bytes_read.sum + "
                 "dram__bytes_write.sum) / gpu__time_duration; %% of the measured %.1f GB/s copy peak in brackets.  Times are cold-cache "
                 "and serialised by the profiler.\n\n" % HBM_PEAK)
