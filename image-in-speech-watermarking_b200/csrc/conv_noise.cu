@@ -22,10 +22,12 @@ __device__ __forceinline__ float apply_act(float v, int act, float slope) {
 }
 
 constexpr int CT = 16;      // output tile edge
-constexpr int COB = 16;     // output channels per CTA
-constexpr int CIB = 8;      // input channels per shared-memory pass
+// output channels per CTA (COB) and input channels per shared-memory pass (CIB) are template parameters: the layers with
+// 1 / 2 input or output channels (ModelA's first / last layers and their data gradients, all at 128 x 128) would waste
+// 4x / 8x of the FMAs and weight loads in the generic 8 x 16 blocking
 
 // y[b][co_off+co][h][w] = act( scale[co] * (sum_{ci,dy,dx} x[b][ci][h+dy-1][w+dx-1] w[co][ci][dy][dx] + bias[co]) + shift[co] )
+template <int CIB, int COB>
 __global__ void __launch_bounds__(256)
 conv3x3_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ w,
                const float* __restrict__ bias, const float* __restrict__ scale, const float* __restrict__ shift,
@@ -63,14 +65,19 @@ conv3x3_kernel(const float* __restrict__ x, float* __restrict__ y, const float* 
 #pragma unroll
       for (int t = 0; t < 9; ++t) {
         const float v = tile[ci][ty + t / 3][tx + t % 3];
-        const float4* w4 = reinterpret_cast<const float4*>(&ws[ci][t][0]);      // 4 weights per shared-memory load
+        if constexpr (COB % 4 == 0) {
+          const float4* w4 = reinterpret_cast<const float4*>(&ws[ci][t][0]);      // 4 weights per shared-memory load
 #pragma unroll
-        for (int j4 = 0; j4 < COB / 4; ++j4) {
-          const float4 wv = w4[j4];
-          acc[4 * j4] = fmaf(v, wv.x, acc[4 * j4]);
-          acc[4 * j4 + 1] = fmaf(v, wv.y, acc[4 * j4 + 1]);
-          acc[4 * j4 + 2] = fmaf(v, wv.z, acc[4 * j4 + 2]);
-          acc[4 * j4 + 3] = fmaf(v, wv.w, acc[4 * j4 + 3]);
+          for (int j4 = 0; j4 < COB / 4; ++j4) {
+            const float4 wv = w4[j4];
+            acc[4 * j4] = fmaf(v, wv.x, acc[4 * j4]);
+            acc[4 * j4 + 1] = fmaf(v, wv.y, acc[4 * j4 + 1]);
+            acc[4 * j4 + 2] = fmaf(v, wv.z, acc[4 * j4 + 2]);
+            acc[4 * j4 + 3] = fmaf(v, wv.w, acc[4 * j4 + 3]);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < COB; ++j) acc[j] = fmaf(v, ws[ci][t][j], acc[j]);
         }
       }
   }
@@ -429,8 +436,16 @@ extern "C" int wmk_conv3x3_f32(const float* x, float* y, const float* w, const f
               "conv3x3: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
   ProfScope prof(FAM_SMALL, 4.0 * B * H * W * (Cin + Cout), st);
-  dim3 grid(cdiv(H, CT) * cdiv(W, CT), cdiv(Cout, COB), B);
-  conv3x3_kernel<<<grid, 256, 0, st>>>(x, y, w, bias, scale, shift, Cin, Cout, H, W, out_ch_offset, out_ch_total, act, slope);
+  const int cob = Cout <= 2 ? 2 : 16;
+  dim3 grid(cdiv(H, CT) * cdiv(W, CT), cdiv(Cout, cob), B);
+  if (Cin <= 2 && Cout <= 2)
+    conv3x3_kernel<2, 2><<<grid, 256, 0, st>>>(x, y, w, bias, scale, shift, Cin, Cout, H, W, out_ch_offset, out_ch_total, act, slope);
+  else if (Cin <= 2)
+    conv3x3_kernel<2, 16><<<grid, 256, 0, st>>>(x, y, w, bias, scale, shift, Cin, Cout, H, W, out_ch_offset, out_ch_total, act, slope);
+  else if (Cout <= 2)
+    conv3x3_kernel<8, 2><<<grid, 256, 0, st>>>(x, y, w, bias, scale, shift, Cin, Cout, H, W, out_ch_offset, out_ch_total, act, slope);
+  else
+    conv3x3_kernel<8, 16><<<grid, 256, 0, st>>>(x, y, w, bias, scale, shift, Cin, Cout, H, W, out_ch_offset, out_ch_total, act, slope);
   WMK_CHECK_LAUNCH("conv3x3_kernel");
   return 0;
 }
