@@ -326,6 +326,12 @@ attn_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     };
 
     size_t tok_prev = 0;
+    uint4 nb0 = make_uint4(0u, 0u, 0u, 0u), nb1 = nb0;
+    if constexpr (!BIAS_SMEM) {
+      const uint4* bg = reinterpret_cast<const uint4*>(g.bias + (size_t)rw * 64 + j4 * 16);
+      nb0 = __ldg(bg);
+      nb1 = __ldg(bg + 1);
+    }
     if (T > 0) qkv_evac(0);
     for (int gh = 0; gh < T; ++gh) {
       const int h = gh & (NH - 1);
@@ -345,10 +351,12 @@ attn_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const uint8_t* brow = gen(biassm + (uint32_t)h * 8192u + (uint32_t)rw * 128u);
           b0 = *reinterpret_cast<const uint4*>(brow + ((((uint32_t)(j4 * 2)) ^ (uint32_t)(rw & 7)) << 4));
           b1 = *reinterpret_cast<const uint4*>(brow + ((((uint32_t)(j4 * 2 + 1)) ^ (uint32_t)(rw & 7)) << 4));
-        } else {
-          const uint4* bg = reinterpret_cast<const uint4*>(g.bias + ((size_t)h * 64 + rw) * 64 + j4 * 16);
-          b0 = __ldg(bg);
-          b1 = __ldg(bg + 1);
+        } else {                                  // fetched from global memory one head ahead (L2 latency off the softmax path)
+          b0 = nb0;
+          b1 = nb1;
+          const uint4* bg = reinterpret_cast<const uint4*>(g.bias + ((size_t)((h + 1) & (NH - 1)) * 64 + rw) * 64 + j4 * 16);
+          nb0 = __ldg(bg);
+          nb1 = __ldg(bg + 1);
         }
         ab_wait(sfull, (uint32_t)gh & 1u);
         tcgen05_fence_after();
@@ -360,7 +368,7 @@ attn_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (lane == 0) mbar_arrive(sempty);
         float s[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) s[i] = __uint_as_float(v[i]) + maskadd;
+        for (int i = 0; i < 16; ++i) s[i] = __uint_as_float(v[i]) + maskadd;      // maskadd = 0 except in border windows of shifted blocks
         add_f16x2(s[0], s[1], b0.x); add_f16x2(s[2], s[3], b0.y); add_f16x2(s[4], s[5], b0.z); add_f16x2(s[6], s[7], b0.w);
         add_f16x2(s[8], s[9], b1.x); add_f16x2(s[10], s[11], b1.y); add_f16x2(s[12], s[13], b1.z); add_f16x2(s[14], s[15], b1.w);
         float m = s[0];
