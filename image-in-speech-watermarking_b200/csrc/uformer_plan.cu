@@ -296,6 +296,11 @@ int pack_block(wmk_plan* P, const std::string& p, int C, int heads, int H, int s
   return 0;
 }
 
+static int ext_down_wsplit() {
+  static const int v = getenv("WMK_EXT_DOWN_WSPLIT") ? atoi(getenv("WMK_EXT_DOWN_WSPLIT")) : 0;
+  return v;
+}
+
 int pack_encoder(wmk_plan* P, const std::string& p, const std::string& inproj, EncW* e, int mode) {
   {
     const HostTensor *tw, *tb;
@@ -326,7 +331,10 @@ int pack_encoder(wmk_plan* P, const std::string& p, const std::string& inproj, E
         for (int ci = 0; ci < C; ++ci)
           for (int tap = 0; tap < 16; ++tap)
             g[((size_t)co * 16 + tap) * C + ci] = t->data[((size_t)co * C + ci) * 16 + tap];
-      WMK_TRY(upload_op(P, g, &e->down_w[s], mode, 16 * C));
+      // WMK_EXT_DOWN_WSPLIT=1 (experiment, off): fp16 im2col rows x (hi + lo) fp16 weights for the precise extractor's
+      // downsample conv - 3.9 ms faster per step, but the fp16 rounding of the residual stream moves the logits by up to
+      // 1.24e-4 (> the 1e-4 margin: test_mixed_extractor_bits_match_oracle_config2_shape fails), so split rows stay
+      WMK_TRY(upload_op(P, g, &e->down_w[s], (mode == 2 && ext_down_wsplit()) ? 4 : mode, 16 * C));
       WMK_TRY(get_f32(P, dp + "bias", 2 * (size_t)C, &e->down_b[s]));
     }
   }
@@ -529,14 +537,17 @@ int run_encoder(wmk_plan* P, const EncW& e, const float* x_nchw, int n, const ch
     const int Ho = H / 2;
     OpT* col = reinterpret_cast<OpT*>(P->bufH1);
     const size_t total = (size_t)n * Ho * Ho * 4 * (C / 8);
+    const bool down_wsplit = OpMode<OpT>::v == 2 && ext_down_wsplit();      // fp16 rows x (hi + lo) weights
     {
-      ProfScope prof_l(FAM_LAYOUT, (double)n * H * H * C * 4 + (double)n * Ho * Ho * 16 * C * sizeof(OpT), st);
-      im2col_4x4s2_kernel<OpT><<<cdiv(total, 256), 256, 0, st>>>(P->E[s], col, n, H, C);
+      ProfScope prof_l(FAM_LAYOUT, (double)n * H * H * C * 4 + (double)n * Ho * Ho * 16 * C * (down_wsplit ? 2 : sizeof(OpT)), st);
+      if (down_wsplit) im2col_4x4s2_kernel<__half><<<cdiv(total, 256), 256, 0, st>>>(P->E[s], reinterpret_cast<__half*>(col), n, H, C);
+      else im2col_4x4s2_kernel<OpT><<<cdiv(total, 256), 256, 0, st>>>(P->E[s], col, n, H, C);
       WMK_CHECK_LAUNCH("im2col_4x4s2_kernel");
     }
     GemmArgs g;
     g.A = col; g.W = e.down_w[s]; g.bias = e.down_b[s]; g.C = P->E[s + 1]; g.M = n * Ho * Ho; g.N = 2 * C;
-    g.K = 16 * C; g.ldc = 2 * C; g.epi = EPI_BIAS; g.out_bf16 = 0; g.split = OpMode<OpT>::v == 2; g.f16 = OpMode<OpT>::v == 3;
+    g.K = 16 * C; g.ldc = 2 * C; g.epi = EPI_BIAS; g.out_bf16 = 0; g.split = OpMode<OpT>::v == 2 && !down_wsplit; g.wsplit = down_wsplit;
+    g.f16 = OpMode<OpT>::v == 3;
     static const int fuse_first_ln = getenv("WMK_FUSE_FIRST_LN") ? atoi(getenv("WMK_FUSE_FIRST_LN")) : 1;
     if ((OpPlain16<OpT>::v || (OpMode<OpT>::v == 2 && split_ln0)) && fuse_first_ln && 2 * C <= 128) {
       // the next stage's first norm1 rides on the downsample conv's epilogue (encoder blocks carry no modulator)
