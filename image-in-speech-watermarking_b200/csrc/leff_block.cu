@@ -59,6 +59,14 @@ struct LbGeom {
   float* x;                // fp32 residual stream, updated in place
 };
 
+#ifdef LB_TIMING
+__device__ unsigned long long lb_timing[8];      // [0..4] cycles waited at acc2full, acc1full, hpempty, hpfull, a2empty; [5] worker total
+#define LB_T0 const long long _t0 = clock64();
+#define LB_T1(i) if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) atomicAdd(&lb_timing[i], (unsigned long long)(clock64() - _t0));
+#else
+#define LB_T0
+#define LB_T1(i)
+#endif
 __device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
   uint32_t done;
   uint32_t spins = 0;
@@ -315,7 +323,7 @@ leff_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
         for (int i = 0; i < 8; ++i) r[i] = r4[i];
         if (!waited) {
-          mbar_wait_sleep(acc2full(ac), ((uint32_t)(lt >> 1)) & 1u);
+          { LB_T0 mbar_wait_sleep(acc2full(ac), ((uint32_t)(lt >> 1)) & 1u); LB_T1(0) }
           tcgen05_fence_after();
           waited = true;
         }
@@ -339,6 +347,9 @@ leff_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       if (lane == 0) mbar_arrive(acc2empty(ac));
     };
 
+#ifdef LB_TIMING
+    const long long _tw = clock64();
+#endif
     for (int gi = 0; gi <= T; ++gi) {
       // ---------------------------------------------------------------- G item of chunk gi
       if (gi < T) {
@@ -360,7 +371,7 @@ leff_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const float4* b4 = reinterpret_cast<const float4*>(g.b1 + j * 64 + g_ch * 32);
 #pragma unroll
           for (int i = 0; i < 8; ++i) bias[i] = __ldg(b4 + i);
-          mbar_wait_sleep(acc1full(b), ((uint32_t)(gi >> 1)) & 1u);
+          { LB_T0 mbar_wait_sleep(acc1full(b), ((uint32_t)(gi >> 1)) & 1u); LB_T1(1) }
           tcgen05_fence_after();
           uint32_t v[32];
           tmem_ld32(g_tmem + (uint32_t)(b * 128), v);
@@ -377,7 +388,7 @@ leff_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             w[2 * i] = pack2_f16(a0.x, a0.y) & keep;           // the conv's zero padding acts on the hidden tensor
             w[2 * i + 1] = pack2_f16(a1.x, a1.y) & keep;
           }
-          mbar_wait_sleep(hpempty(hb_g), hp_par_g ^ 1u);       // the V items that read this buffer last are done
+          { LB_T0 mbar_wait_sleep(hpempty(hb_g), hp_par_g ^ 1u); LB_T1(2) }      // the V items that read this buffer last are done
           if (prow < LB_PROWS) {
             const uint32_t dst = g_hp + (uint32_t)hb_g * LB_HP_BYTES;
 #pragma unroll
@@ -411,14 +422,14 @@ leff_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
             for (int t = 0; t < 9; ++t) wv[sset][t] = __ldg(reinterpret_cast<const uint2*>(wp + (size_t)(sset * 9 + t) * (4 * C)));
           const float4 bz = __ldg(reinterpret_cast<const float4*>(g.dw_b + j * 64 + cg * 4));
-          mbar_wait_sleep(hpfull(hb), ((uint32_t)(c / HPB)) & 1u);
+          { LB_T0 mbar_wait_sleep(hpfull(hb), ((uint32_t)(c / HPB)) & 1u); LB_T1(3) }
           const uint8_t* hp = smem_raw + (hps + (uint32_t)hb * LB_HP_BYTES - raw) + v_hp + (uint32_t)(r * LB_PW) * LB_HP_PITCH;
           uint2 win[3][6];
 #pragma unroll
           for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
             for (int kx = 0; kx < 6; ++kx) win[dy][kx] = *reinterpret_cast<const uint2*>(hp + (dy * LB_PW + kx) * LB_HP_PITCH);
-          mbar_wait_sleep(a2empty(b), (((uint32_t)(c >> 1)) & 1u) ^ 1u);
+          { LB_T0 mbar_wait_sleep(a2empty(b), (((uint32_t)(c >> 1)) & 1u) ^ 1u); LB_T1(4) }
           uint8_t* ab = smem_raw + (a2s + (uint32_t)b * LB_A2_BYTES - raw) + (uint32_t)r * 1024u;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -452,6 +463,9 @@ leff_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       if (gi >= NJ + 1 && ((gi - 1) & (NJ - 1)) == 0) e_items(((gi - 1) >> g.lg_nj) - 1);
     }
     if (my_tiles > 0) e_items(my_tiles - 1);
+#ifdef LB_TIMING
+    if (blockIdx.x == 0 && lane == 0) atomicAdd(&lb_timing[5], (unsigned long long)(clock64() - _tw));
+#endif
   }
 
   tcgen05_fence_before();
@@ -513,6 +527,15 @@ int launch_leff_block(const void* A, const void* W1, const void* W2, const float
 }
 
 }  // namespace
+
+#ifdef LB_TIMING
+int leff_block_timing(unsigned long long* out) {
+  cudaMemcpyFromSymbol(out, lb_timing, sizeof(unsigned long long) * 8);
+  unsigned long long z[8] = {0};
+  cudaMemcpyToSymbol(lb_timing, z, sizeof(z));
+  return 0;
+}
+#endif
 
 // x[M][C] += LeFF(A) with A = LayerNorm-2 output [n][H][H][C] fp16, token layout.
 //   plain   (precise = 0): W1 [4C][C], W2 [C][4C] fp16; b1, dw16 [9][4C] (fp16), dw_b PRE-HALVED (tanh-form GELU)
