@@ -446,17 +446,28 @@ def bench_config2(ctx, args):
     _lib.profile_enable(False)
     # ---- end to end through the public API with host buffers: waveforms + images in from pinned memory, the
     # attacked audio, the recovered images and the statistics vector back to pinned memory, every step
-    nc_att = 6
-    host_att = torch.empty((B, host_w.shape[1]), dtype=torch.float32).pin_memory()
-    host_wm = torch.empty((B, nc_att, 1, 32, 32), dtype=torch.float32).pin_memory()
+    # Every step: waveforms + images copied in from pinned memory, the attacked audio, the recovered images and the
+    # statistics vector copied back to pinned memory.  The driver keeps three batches in flight (upload of the next,
+    # compute of the current, download of the previous on separate streams), as a serving loop would.
+    drv = PT.PipelinedDriver(model, ATTACK, reduce_fn=SH.allreduce_stats)
 
     def e2e_step():
-        vec, r = step(host_w.to(dev, non_blocking=True), host_m.to(dev, non_blocking=True), True)
-        host_att.copy_(r["att"], non_blocking=True)            # the attacked audio (product output)
-        host_wm.copy_(r["wm_att"], non_blocking=True)          # the recovered images (product output)
-        return vec.cpu()                                       # BER / SNR statistics; synchronises the step
+        cnt[0] += 1
+        return drv.submit(host_w, host_m, seed=cnt[0])
 
-    ms_e2e, _, _ = ctx.timed(e2e_step, args.steps, 3)
+    for _ in range(3):
+        e2e_step()
+    drv.flush()
+    ctx.sync()
+    q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    q0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    last = drv.flush()                                        # the host holds every output of the K timed steps
+    q1.record()
+    ctx.sync()
+    assert last is not None and tuple(last["att"].shape) == (B, host_w.shape[1])
+    ms_e2e = ctx.max_over_ranks(q0.elapsed_time(q1) / args.steps)[0]
     if rank != 0:
         return None, model
     total_audio = B * SECONDS * world
@@ -516,8 +527,10 @@ def bench_config2(ctx, args):
                      args.warmup, "weak", DTYPE[args.precision], config(args), launches)
     line["e2e"] = {"value": total_audio / (ms_e2e * 1e-3), "unit": "audio-s/s",
                    "h2d_bytes_per_step": host_w.numel() * 4 + host_m.numel() * 4,
-                   "d2h_bytes_per_step": host_att.numel() * 4 + host_wm.numel() * 4 + 8 * 8, "ms_per_step": ms_e2e,
-                   "d2h": "attacked audio (B x L fp32) + recovered images (B x 6 x 32 x 32 fp32) + the 8-double statistics vector"}
+                   "d2h_bytes_per_step": last["att"].numel() * 4 + last["wm_att"].numel() * 4 + last["vec"].numel() * 8, "ms_per_step": ms_e2e,
+                   "d2h": "attacked audio (B x L fp32) + recovered images (B x 6 x 32 x 32 fp32) + the 8-double statistics vector",
+                   "api": "audio_test.PipelinedDriver.submit per step (host buffers in and out; upload of the next batch and download "
+                          "of the previous one overlap the kernels on two side streams; every copy of the K steps is inside the timed region)"}
     line.update({"clocks": clocks, "roofline": roofline,
                  "stats": {"ber_clean": float(vec[0] / vec[1]), "ber_attacked": float(vec[2] / vec[3]),
                            "mean_snr_db": float(vec[4] / vec[7])}})

@@ -276,6 +276,70 @@ def embed_attack_extract(waves, messages, model, attack="closed_loop", draws=Non
     return out
 
 
+class PipelinedDriver:
+    """Serving loop around `embed_attack_extract` for HOST batches (pinned waveforms / images in; attacked audio, recovered
+    images and the statistics vector out to pinned host buffers), three batches in flight: while batch i computes on the
+    current stream, batch i+1 is uploaded on a second stream and the outputs of batch i-1 are downloaded on a third, so
+    the host<->device copies and the host's launch work hide under the kernels.  `submit` never waits for the batch it
+    enqueues: it returns the results of the PREVIOUS batch (None for the first call), valid until the next `submit`;
+    `flush` returns the last one.  Same results as calling `embed_attack_extract` batch by batch."""
+
+    def __init__(self, model, attack="closed_loop", reduce_fn=None, **kw):
+        self.model, self.attack, self.kw, self.reduce_fn = model, attack, kw, reduce_fn
+        self.h2d, self.d2h = torch.cuda.Stream(), torch.cuda.Stream()
+        self.slots = [None, None]
+        self.n = 0
+
+    def _slot(self, s, host_w, host_m):
+        sl = self.slots[s]
+        if sl is None or sl["w"].shape != host_w.shape or sl["m"].shape != host_m.shape:
+            dev = torch.device("cuda", torch.cuda.current_device())
+            sl = {"w": torch.empty(host_w.shape, dtype=torch.float32, device=dev),
+                  "m": torch.empty(host_m.shape, dtype=torch.float32, device=dev),
+                  "out": None, "in_done": torch.cuda.Event(), "comp_done": torch.cuda.Event(), "out_done": torch.cuda.Event(),
+                  "used": False}
+            self.slots[s] = sl
+        return sl
+
+    def submit(self, host_w, host_m, seed=None, draws=None):
+        main = torch.cuda.current_stream()
+        s = self.n & 1
+        sl = self._slot(s, host_w, host_m)
+        with torch.cuda.stream(self.h2d):
+            if sl["used"]:
+                self.h2d.wait_event(sl["comp_done"])            # the batch that used this slot two calls ago has computed
+            sl["w"].copy_(host_w, non_blocking=True)
+            sl["m"].copy_(host_m, non_blocking=True)
+            sl["in_done"].record(self.h2d)
+        main.wait_event(sl["in_done"])
+        r = embed_attack_extract(sl["w"], sl["m"], self.model, self.attack, draws, seed, **self.kw)
+        vec = self.reduce_fn(r["vec"]) if self.reduce_fn is not None else r["vec"]
+        sl["comp_done"].record(main)
+        if sl["out"] is None or sl["out"]["att"].shape != r["att"].shape or sl["out"]["wm_att"].shape != r["wm_att"].shape:
+            sl["out"] = {"att": torch.empty(r["att"].shape, dtype=torch.float32).pin_memory(),
+                         "wm_att": torch.empty(r["wm_att"].shape, dtype=torch.float32).pin_memory(),
+                         "vec": torch.empty(vec.shape, dtype=vec.dtype).pin_memory()}
+        with torch.cuda.stream(self.d2h):
+            self.d2h.wait_event(sl["comp_done"])
+            for k, t in (("att", r["att"]), ("wm_att", r["wm_att"]), ("vec", vec)):
+                sl["out"][k].copy_(t, non_blocking=True)
+                t.record_stream(self.d2h)                       # the allocator must not recycle it before the copy has run
+            sl["out_done"].record(self.d2h)
+        sl["used"] = True
+        sl["stats"] = r["stats"]
+        self.n += 1
+        return self._result(s ^ 1) if self.n > 1 else None
+
+    def _result(self, s):
+        sl = self.slots[s]
+        sl["out_done"].synchronize()
+        return sl["out"]
+
+    def flush(self):
+        """Results of the last submitted batch (waits for its download)."""
+        return self._result((self.n - 1) & 1) if self.n else None
+
+
 def signaltonoise(a, axis=0, ddof=0):
     return EV.signaltonoise(a, axis, ddof)
 

@@ -630,6 +630,30 @@ def test_tiled_64x64_image_pipeline_matches_oracle(models, weights):
     assert back.shape == (1, 1, 64, 64)
 
 
+def test_pipelined_driver_equals_direct_calls(models):
+    """`audio_test.PipelinedDriver` (host batches, copies on side streams, results one call late) == `embed_attack_extract`
+    called batch by batch with the same seeds."""
+    from image_in_speech_watermarking_b200 import audio_test as PT
+    m = models("mixed", "stress")
+    B, n_batches = 2, 4
+    hw = [SY.synth_speech_batch(60 + 2 * i, B, 1.0).pin_memory() for i in range(n_batches)]
+    hm = [torch.stack([SY.synth_image_binary(60 + 2 * i + j) for j in range(B)]).pin_memory() for i in range(n_batches)]
+    ref = [PT.embed_attack_extract(hw[i].cuda(), hm[i].cuda(), m, "awgn-20+low_pass", seed=100 + i) for i in range(n_batches)]
+    ref = [{k: r[k].cpu().clone() for k in ("att", "wm_att", "vec")} for r in ref]
+    drv = PT.PipelinedDriver(m, "awgn-20+low_pass")
+    got = []
+    for i in range(n_batches):
+        out = drv.submit(hw[i], hm[i], seed=100 + i)
+        assert (out is None) == (i == 0)
+        if out is not None:
+            got.append({k: out[k].clone() for k in ("att", "wm_att", "vec")})
+    got.append({k: v.clone() for k, v in drv.flush().items()})
+    assert len(got) == n_batches
+    for g, r in zip(got, ref):
+        assert torch.allclose(g["att"], r["att"], rtol=0, atol=1e-6) and torch.allclose(g["wm_att"], r["wm_att"], rtol=0, atol=1e-5)
+        assert torch.allclose(g["vec"], r["vec"], rtol=1e-9, atol=1e-9)
+
+
 def test_config4_10s_tiled_batch_in_benchmarked_precision(models, weights):
     """BASELINE config 4 at its real shape and in the precision `bench.py` times: 64x64 greyscale images as four tiles in
     10 s utterances (20 clips each), a batch of two, chained attack.  Utterance 0 is checked against the oracle's loop
