@@ -77,6 +77,7 @@ SIGNATURES = {
     "wmk_plan_enable_taps": (_i, [_vp, _i]),
     "wmk_plan_get_tap": (_i, [_vp, ctypes.c_char_p, _vp, _sz, ctypes.POINTER(_sz)]),
     "wmk_leff_block_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "wmk_window_attention_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "wmk_linear_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
 }
 

@@ -182,6 +182,53 @@ int upload_op(wmk_plan* P, const std::vector<float>& v, void** out, int mode, in
   return 0;
 }
 
+// q|k|v operands of one LeWin block from the reference's tensors (uformerWM/model.py:455-471,489-507,526):
+//   wqkv [3C][C] = [Wq * scale | Wk | Wv], bqkv [3C] alike, bias [heads][64][64] = table gathered by the relative-position
+//   index (model.py:496-505).  log2_domain (the tensor-core kernels, softmax by exp2): scale and bias carry a factor log2(e).
+void build_qkv_operands(const float* wq, const float* bq, const float* wkv, const float* bkv, const float* table, int C, int heads,
+                        bool log2_domain, std::vector<float>& wqkv, std::vector<float>& bqkv, std::vector<float>& bias) {
+  const float lg = log2_domain ? 1.4426950408889634f : 1.0f;
+  bias.assign((size_t)heads * 4096, 0.f);
+  for (int h = 0; h < heads; ++h)
+    for (int i = 0; i < 64; ++i)
+      for (int j = 0; j < 64; ++j) {
+        const int idx = ((i >> 3) - (j >> 3) + 7) * 15 + ((i & 7) - (j & 7) + 7);      // model.py:496-505
+        bias[((size_t)h * 64 + i) * 64 + j] = table[(size_t)idx * heads + h] * lg;
+      }
+  const float scale = lg / sqrtf((float)(C / heads));                // model.py:489,526
+  wqkv.resize(3 * (size_t)C * C);
+  bqkv.resize(3 * (size_t)C);
+  for (size_t i = 0; i < (size_t)C * C; ++i) wqkv[i] = wq[i] * scale;
+  for (size_t i = 0; i < 2 * (size_t)C * C; ++i) wqkv[(size_t)C * C + i] = wkv[i];
+  for (int i = 0; i < C; ++i) bqkv[i] = bq[i] * scale;
+  for (int i = 0; i < 2 * C; ++i) bqkv[C + i] = bkv[i];
+}
+
+// attn_block.cu operands: head h owns rows [q_h | k_h | v_h] of the projection; the relative-position bias in "quad order"
+// (window rows as four 4x4 sub-blocks: row r -> sub-block r >> 4, pixel ((r >> 2) & 3, r & 3) inside it)
+void pack_attn_heads(const std::vector<float>& wqkv, const std::vector<float>& bqkv, const std::vector<float>& bias, int C, int heads,
+                     std::vector<float>& wh, std::vector<float>& bh, std::vector<float>& bquad) {
+  wh.resize((size_t)heads * 96 * C);
+  bh.resize((size_t)heads * 96);
+  bquad.resize((size_t)heads * 4096);
+  for (int h = 0; h < heads; ++h)
+    for (int part = 0; part < 3; ++part)
+      for (int d = 0; d < 32; ++d) {
+        const size_t src = (size_t)part * C + h * 32 + d, dst = (size_t)h * 96 + part * 32 + d;
+        for (int c = 0; c < C; ++c) wh[dst * C + c] = wqkv[src * C + c];
+        bh[dst] = bqkv[src];
+      }
+  auto pos = [](int r, int& i, int& j) { const int sb = r >> 4; i = ((sb >> 1) << 2) | ((r >> 2) & 3); j = ((sb & 1) << 2) | (r & 3); };
+  for (int h = 0; h < heads; ++h)
+    for (int r = 0; r < 64; ++r)
+      for (int c = 0; c < 64; ++c) {
+        int ri, rj, ci, cj;
+        pos(r, ri, rj);
+        pos(c, ci, cj);
+        bquad[((size_t)h * 64 + r) * 64 + c] = bias[((size_t)h * 64 + (ri * 8 + rj)) * 64 + (ci * 8 + cj)];
+      }
+}
+
 int get(wmk_plan* P, const std::string& name, size_t numel, const HostTensor** out) {
   auto it = P->host.find(name);
   if (it == P->host.end()) { set_error("plan: missing tensor '%s'", name.c_str()); return WMK_ERR_STATE; }
@@ -209,51 +256,22 @@ int pack_block(wmk_plan* P, const std::string& p, int C, int heads, int H, int s
   if (mod) WMK_TRY(get_f32(P, p + "modulator.weight", 64 * (size_t)C, &w->mod));
   const HostTensor *tab, *wq, *bq, *wkv, *bkv, *dw;
   WMK_TRY(get(P, p + "attn.relative_position_bias_table", 225 * (size_t)heads, &tab));
-  // bf16 mode: the tensor-core attention kernel works in the log2 domain (softmax by exp2), so
-  // log2(e) is folded into the bias table and the q rows; fp32 mode keeps natural-log scores.
-  const float lg = mode != 0 ? 1.4426950408889634f : 1.0f;
-  std::vector<float> bias((size_t)heads * 4096);
-  for (int h = 0; h < heads; ++h)
-    for (int i = 0; i < 64; ++i)
-      for (int j = 0; j < 64; ++j) {
-        const int idx = ((i >> 3) - (j >> 3) + 7) * 15 + ((i & 7) - (j & 7) + 7);      // model.py:496-505
-        bias[((size_t)h * 64 + i) * 64 + j] = tab->data[(size_t)idx * heads + h] * lg;
-      }
-  WMK_TRY(upload_f32(P, bias, &w->attn_bias));
   WMK_TRY(get(P, p + "attn.qkv.to_q.weight", (size_t)C * C, &wq));
   WMK_TRY(get(P, p + "attn.qkv.to_q.bias", C, &bq));
   WMK_TRY(get(P, p + "attn.qkv.to_kv.weight", 2 * (size_t)C * C, &wkv));
   WMK_TRY(get(P, p + "attn.qkv.to_kv.bias", 2 * (size_t)C, &bkv));
-  const float scale = lg / sqrtf((float)(C / heads));                // model.py:489,526
-  std::vector<float> wqkv(3 * (size_t)C * C), bqkv(3 * (size_t)C);
-  for (size_t i = 0; i < (size_t)C * C; ++i) wqkv[i] = wq->data[i] * scale;
-  for (size_t i = 0; i < 2 * (size_t)C * C; ++i) wqkv[(size_t)C * C + i] = wkv->data[i];
-  for (int i = 0; i < C; ++i) bqkv[i] = bq->data[i] * scale;
-  for (int i = 0; i < 2 * C; ++i) bqkv[C + i] = bkv->data[i];
+  std::vector<float> bias, wqkv, bqkv;
+  build_qkv_operands(wq->data.data(), bq->data.data(), wkv->data.data(), bkv->data.data(), tab->data.data(), C, heads, mode != 0,
+                     wqkv, bqkv, bias);
+  WMK_TRY(upload_f32(P, bias, &w->attn_bias));
   WMK_TRY(upload_op(P, wqkv, &w->w_qkv, mode, C));
   WMK_TRY(upload_f32(P, bqkv, &w->b_qkv));
   if (mode == 3 && C <= 128) {
-    // attn_block.cu operands: head h owns rows [q_h | k_h | v_h]; window rows in quad order (four 4x4 sub-blocks)
-    std::vector<float> wh((size_t)heads * 96 * C), bh((size_t)heads * 96), bq((size_t)heads * 4096);
-    for (int h = 0; h < heads; ++h)
-      for (int part = 0; part < 3; ++part)
-        for (int d = 0; d < 32; ++d) {
-          const size_t src = (size_t)part * C + h * 32 + d, dst = (size_t)h * 96 + part * 32 + d;
-          for (int c = 0; c < C; ++c) wh[dst * C + c] = wqkv[src * C + c];
-          bh[dst] = bqkv[src];
-        }
-    auto pos = [](int r, int& i, int& j) { const int sb = r >> 4; i = ((sb >> 1) << 2) | ((r >> 2) & 3); j = ((sb & 1) << 2) | (r & 3); };
-    for (int h = 0; h < heads; ++h)
-      for (int r = 0; r < 64; ++r)
-        for (int c = 0; c < 64; ++c) {
-          int ri, rj, ci, cj;
-          pos(r, ri, rj);
-          pos(c, ci, cj);
-          bq[((size_t)h * 64 + r) * 64 + c] = bias[((size_t)h * 64 + (ri * 8 + rj)) * 64 + (ci * 8 + cj)];
-        }
+    std::vector<float> wh, bh, bquad;
+    pack_attn_heads(wqkv, bqkv, bias, C, heads, wh, bh, bquad);
     WMK_TRY(upload_op(P, wh, &w->w_qkv_heads, 3, C));
     WMK_TRY(upload_f32(P, bh, &w->b_qkv_heads));
-    WMK_TRY(upload_f16_sets(P, bq, 1, &w->bias_quad));
+    WMK_TRY(upload_f16_sets(P, bquad, 1, &w->bias_quad));
   }
   const HostTensor* t;
   WMK_TRY(get(P, p + "attn.proj.weight", (size_t)C * C, &t));
@@ -934,6 +952,45 @@ extern "C" int wmk_leff_block_f32(const float* A, const float* W1, const float* 
   cudaFreeAsync(dw16, st);
   cudaFreeAsync(a16, st); cudaFreeAsync(w1, st); cudaFreeAsync(w2, st); cudaFreeAsync(b1s, st);
   cudaFreeAsync(dws, st); cudaFreeAsync(dbs, st); cudaFreeAsync(w1s, st);
+  return s;
+}
+
+// Stand-alone fused q|k|v projection + window attention for the unit tests (attn_block.cu): A [n*H*H][C] fp32 on the device
+// (the LayerNorm-1 output), out [n*H*H][C] fp32 on the device; the block's reference tensors on the HOST: Wq [C][C], bq [C],
+// Wkv [2C][C], bkv [2C], relative_position_bias_table [225][heads].  No output projection.
+extern "C" int wmk_window_attention_f32(const float* A, const float* Wq_host, const float* bq_host, const float* Wkv_host,
+                                        const float* bkv_host, const float* table_host, float* out, int n, int H, int C, int shift,
+                                        void* stream) {
+  WMK_REQUIRE(A && Wq_host && bq_host && Wkv_host && bkv_host && table_host && out && n > 0, "window_attention: bad arguments");
+  WMK_REQUIRE(C == 32 || C == 64 || C == 128, "window_attention: covers C in {32,64,128}, got %d", C);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int heads = C / 32;
+  const size_t M = (size_t)n * H * H;
+  std::vector<float> wqkv, bqkv, bias, wh, bh, bquad;
+  build_qkv_operands(Wq_host, bq_host, Wkv_host, bkv_host, table_host, C, heads, true, wqkv, bqkv, bias);
+  pack_attn_heads(wqkv, bqkv, bias, C, heads, wh, bh, bquad);
+  std::vector<__half> wh16(wh.size()), bq16(bquad.size());
+  for (size_t i = 0; i < wh.size(); ++i) wh16[i] = __float2half_rn(wh[i]);
+  for (size_t i = 0; i < bquad.size(); ++i) bq16[i] = __float2half_rn(bquad[i]);
+  __half *a16 = nullptr, *o16 = nullptr, *w16 = nullptr, *b16 = nullptr;
+  float* bh_d = nullptr;
+  WMK_CHECK_CUDA(cudaMalloc(&a16, M * C * 2));
+  WMK_CHECK_CUDA(cudaMalloc(&o16, M * C * 2));
+  WMK_CHECK_CUDA(cudaMalloc(&w16, wh16.size() * 2));
+  WMK_CHECK_CUDA(cudaMalloc(&b16, bq16.size() * 2));
+  WMK_CHECK_CUDA(cudaMalloc(&bh_d, bh.size() * 4));
+  WMK_CHECK_CUDA(cudaMemcpyAsync(w16, wh16.data(), wh16.size() * 2, cudaMemcpyHostToDevice, st));
+  WMK_CHECK_CUDA(cudaMemcpyAsync(b16, bq16.data(), bq16.size() * 2, cudaMemcpyHostToDevice, st));
+  WMK_CHECK_CUDA(cudaMemcpyAsync(bh_d, bh.data(), bh.size() * 4, cudaMemcpyHostToDevice, st));
+  copy_cols_kernel<__half><<<cdiv(M * (C / 4), 256), 256, 0, st>>>(A, a16, M, C, C, 0);
+  WMK_CHECK_LAUNCH("copy_cols_kernel");
+  int s = attn_block(a16, w16, bh_d, reinterpret_cast<const uint16_t*>(b16), reinterpret_cast<uint16_t*>(o16), n, H, C, shift, st);
+  if (s == 0) {
+    widen_kernel<<<cdiv(M * C, 256), 256, 0, st>>>(reinterpret_cast<const uint16_t*>(o16), out, M * C, true);
+    count_launch();
+  }
+  cudaStreamSynchronize(st);                      // the host staging vectors die with this frame
+  cudaFree(a16); cudaFree(o16); cudaFree(w16); cudaFree(b16); cudaFree(bh_d);
   return s;
 }
 

@@ -349,6 +349,14 @@ int wmk_plan_get_tap(wmk_plan* plan, const char* name, float* out, size_t capaci
  * C in {32, 64, 128}, H a power of two in [16, 128]. */
 int wmk_leff_block_f32(const float* A, const float* W1, const float* b1, const float* dw_w, const float* dw_b,
                        const float* W2, const float* b2, float* x, int n, int H, int C, int precise, void* stream);
+/* Stand-alone fused q|k|v projection + LeWin window attention (uformerWM/model.py:460-471,523-551,954-1012 without the output
+ * projection) used by the unit tests: one tcgen05 kernel (csrc/attn_block.cu), q, k, v never reach HBM.  A [n*H*H][C] (the
+ * LayerNorm-1 output, token order) and out [n*H*H][C] are fp32 DEVICE buffers; the block's reference tensors are HOST
+ * pointers: Wq [C][C], bq [C], Wkv [2C][C], bkv [2C], relative_position_bias_table [225][C/32].  fp16 operands.
+ * C in {32, 64, 128}, H a power of two in [16, 128], shift 0 or 4 (cyclic shift + mask of the odd blocks). */
+int wmk_window_attention_f32(const float* A, const float* Wq_host, const float* bq_host, const float* Wkv_host,
+                             const float* bkv_host, const float* table_host, float* out, int n, int H, int C, int shift,
+                             void* stream);
 /* Stand-alone dense op used by the unit tests and the roofline bench:
  * C[M][N] = A[M][K] * W[N][K]^T + bias[N], fp32 in HBM in and out; precision selects the fp32 SIMT kernel
  * (WMK_PREC_FP32) or the tcgen05 kernel with bf16 / fp16 operands (WMK_PREC_BF16 / WMK_PREC_F16), split-bf16 A and

@@ -126,6 +126,51 @@ def test_fused_leff_block_matches_torch(geom, precise):
     assert err < (1.5e-3 if precise else 3e-3), (geom, precise, err)
 
 
+@pytest.mark.parametrize("shift", [0, 4])
+@pytest.mark.parametrize("geom", [(3, 16, 32), (2, 32, 64), (2, 16, 128), (1, 64, 64), (3, 32, 128), (1, 128, 32)])
+def test_fused_window_attention_matches_torch(geom, shift):
+    """csrc/attn_block.cu (q|k|v projection + window attention of two 8x8 windows per UMMA tile on tcgen05, TMA 4x4 boxes
+    as roll + partition, quad-order bias table, sub-block shift mask) vs `WindowAttention` + roll / partition / mask /
+    reverse of `uformerWM/model.py:460-471,523-551,954-1012` in float64 (the oracle's helpers), without the output
+    projection: every width, several windows / images, border windows of shifted blocks.  Tolerance: fp16 operands."""
+    from image_in_speech_watermarking_b200 import _lib
+    lib = _lib.load()
+    n, H, C = geom
+    heads = C // 32
+    g = torch.Generator().manual_seed(n * 1000 + H + C + shift)
+    M = n * H * H
+    A = torch.randn(M, C, generator=g)
+    Wq = torch.randn(C, C, generator=g) * (1.5 / C ** 0.5)
+    bq = torch.randn(C, generator=g) * 0.2
+    Wkv = torch.randn(2 * C, C, generator=g) * (1.5 / C ** 0.5)
+    bkv = torch.randn(2 * C, generator=g) * 0.2
+    table = torch.randn(225, heads, generator=g) * 0.5
+    # float64 reference on the fp16-rounded input
+    x = A.half().double().view(n, H, H, C)
+    if shift:
+        x = torch.roll(x, shifts=(-shift, -shift), dims=(1, 2))
+    win = O._window_partition(x).view(-1, 64, C)
+    q = (win @ Wq.double().T + bq.double()).view(-1, 64, heads, 32).permute(0, 2, 1, 3) * 32 ** -0.5
+    kv = (win @ Wkv.double().T + bkv.double()).view(-1, 64, 2, heads, 32).permute(2, 0, 3, 1, 4)
+    attn = q @ kv[0].transpose(-2, -1) + table.double()[O._REL_IDX.view(-1)].view(64, 64, heads).permute(2, 0, 1)[None]
+    if shift:
+        mask = O._shift_mask(H, H, shift, torch.float64)
+        nW = mask.shape[0]
+        attn = (attn.view(-1, nW, heads, 64, 64) + mask[None, :, None]).view(-1, heads, 64, 64)
+    o = (attn.softmax(-1) @ kv[1]).transpose(1, 2).reshape(-1, 8, 8, C)
+    y = O._window_reverse(o, H, H)
+    if shift:
+        y = torch.roll(y, shifts=(shift, shift), dims=(1, 2))
+    ref = y.reshape(M, C)
+    out = torch.full((M, C), float("nan"), device="cuda")
+    host = [t.contiguous() for t in (Wq, bq, Wkv, bkv, table)]
+    _lib.check(lib.wmk_window_attention_f32(_lib.ptr(A.cuda()), *[t.data_ptr() for t in host], _lib.ptr(out), n, H, C, shift,
+                                            _lib.stream_ptr()))
+    got = out.cpu().double()
+    assert torch.isfinite(got).all()
+    assert maxrel(got, ref) < 4e-3, (geom, shift, maxrel(got, ref))
+
+
 # --------------------------------------------------------------------------------- front end
 @pytest.mark.parametrize("L", [16000, 8002, 48000, 63 * 127 + 1, 63 * 127, 5000, 160000])
 def test_stft_istft_match_oracle(L):
