@@ -5,6 +5,8 @@
 // (The data gradient of the 3x3 convolution is the forward kernel of conv_noise.cu run with the
 // flipped, transposed weights.)  NCHW float32; all of these are memory bound: every tensor is read
 // once per kernel, per-channel reductions go through warp shuffles and fp64 atomics.
+#include <stdlib.h>
+
 #include "uformer_kernels.cuh"
 
 namespace wmk {
@@ -260,6 +262,160 @@ conv3x3_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, 
   }
 }
 
+
+// ---- register-blocked weight gradient (the product path for Cin*Cout <= 2048; the kernel above stays for wider layers)
+// A thread owns CO_T x CI_T (output, input) channel pairs = CO_T * CI_T * 9 accumulators that live in registers across
+// ALL tiles of its CTA, and walks 4-pixel row segments of the 16x16 tile: per segment and kernel row one x window of 6
+// values per input channel (one scalar + one 16-byte + one scalar shared-memory load) feeds 12 * CO_T FMAs, so the
+// kernel is bound by the FMA pipe and not by shared-memory bandwidth (the thread-per-pair kernel above: 13 loads per
+// 36 FMAs).  Lanes of a warp hold DIFFERENT channel pairs of the SAME segment (shared-memory broadcasts; channels are
+// dealt round-robin so that the distinct addresses of a 16-byte access fall into different banks: plane pitches 456 / 260
+// words).  Per-CTA partial sums go to part[cta][...]: the fixed-order reduction below makes the result bit-reproducible.
+constexpr int WG2_NT = 256;
+constexpr int WG2_XP = 24;                     // x row: [3 pad][halo][16 pixels][halo][3 pad]
+constexpr int WG2_XPL = 18 * WG2_XP + 24;      // x plane pitch (= 8 mod 32 words)
+constexpr int WG2_DPL = 260;                   // dy plane pitch
+template <int CO_T, int CI_T>
+__global__ void __launch_bounds__(WG2_NT, 2)
+conv3x3_wgrad2_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ part, int Cin, int Cout,
+                      int H, int W, int n_tiles, int n_cb, int n_cib, int want_db) {
+  extern __shared__ __align__(16) float sm[];
+  const int cin_pad = n_cib * CI_T, cout_pad = n_cb * CO_T;
+  float* xs = sm;                                // [cin_pad][WG2_XPL]
+  float* ds = sm + (size_t)cin_pad * WG2_XPL;    // [cout_pad][WG2_DPL]
+  const int tiles_w = W / 16, tiles_img = tiles_w * (H / 16);
+  const int pairs = n_cb * n_cib;
+  const int S = WG2_NT / pairs;                  // pixel subsets (host guarantees pairs <= WG2_NT)
+  const int pair = threadIdx.x % pairs, s = threadIdx.x / pairs;
+  const bool worker = s < S;
+  const int cib = pair % n_cib, cb = pair / n_cib;
+  float acc[CO_T][CI_T][9], bsum[CO_T];
+#pragma unroll
+  for (int j = 0; j < CO_T; ++j) {
+    bsum[j] = 0.f;
+#pragma unroll
+    for (int i = 0; i < CI_T; ++i)
+#pragma unroll
+      for (int t = 0; t < 9; ++t) acc[j][i][t] = 0.f;
+  }
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int b = tile / tiles_img, trem = tile - b * tiles_img;
+    const int th = trem / tiles_w, tw = trem - th * tiles_w;
+    __syncthreads();                             // the previous tile has been consumed
+#pragma unroll 4
+    for (int e = threadIdx.x; e < cin_pad * 108; e += WG2_NT) {          // 18 rows x (halo, 4 x 16 bytes, halo)
+      const int ci = e / 108, rem = e - ci * 108, r = rem / 6, k = rem - r * 6;
+      const int hh = th * 16 + r - 1;
+      const bool ok = ci < Cin && hh >= 0 && hh < H;
+      const float* src = x + (((size_t)b * Cin + (ok ? ci : 0)) * H + (ok ? hh : 0)) * W + tw * 16;
+      float* dst = xs + ci * WG2_XPL + r * WG2_XP;
+      if (k == 0) dst[3] = (ok && tw > 0) ? src[-1] : 0.f;
+      else if (k == 5) dst[20] = (ok && tw + 1 < tiles_w) ? src[16] : 0.f;
+      else *reinterpret_cast<float4*>(dst + 4 * k) = ok ? *reinterpret_cast<const float4*>(src + 4 * (k - 1)) : zero4;
+    }
+#pragma unroll 4
+    for (int e = threadIdx.x; e < cout_pad * 64; e += WG2_NT) {
+      const int co = e >> 6, r = (e >> 2) & 15, k = e & 3;
+      *reinterpret_cast<float4*>(ds + co * WG2_DPL + r * 16 + 4 * k) =
+          co < Cout ? *reinterpret_cast<const float4*>(dy + (((size_t)b * Cout + co) * H + th * 16 + r) * W + tw * 16 + 4 * k) : zero4;
+    }
+    __syncthreads();
+    if (!worker) continue;
+    for (int seg = s; seg < 64; seg += S) {
+      const int r = seg >> 2, c4 = (seg & 3) * 4;
+      float d[CO_T][4];
+#pragma unroll
+      for (int j = 0; j < CO_T; ++j) {
+        const float4 v = *reinterpret_cast<const float4*>(ds + (cb + j * n_cb) * WG2_DPL + r * 16 + c4);
+        d[j][0] = v.x; d[j][1] = v.y; d[j][2] = v.z; d[j][3] = v.w;
+      }
+      if (want_db && cib == 0) {
+#pragma unroll
+        for (int j = 0; j < CO_T; ++j) bsum[j] += (d[j][0] + d[j][1]) + (d[j][2] + d[j][3]);
+      }
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int i = 0; i < CI_T; ++i) {
+          const float* xr = xs + (cib + i * n_cib) * WG2_XPL + (r + ky) * WG2_XP + c4 + 3;      // xr[0] = column c4 - 1
+          const float4 m = *reinterpret_cast<const float4*>(xr + 1);
+          const float xv[6] = {xr[0], m.x, m.y, m.z, m.w, xr[5]};
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+            for (int j = 0; j < CO_T; ++j)
+#pragma unroll
+              for (int px = 0; px < 4; ++px) acc[j][i][ky * 3 + kx] = fmaf(xv[px + kx], d[j][px], acc[j][i][ky * 3 + kx]);
+        }
+    }
+  }
+  // sum over the pixel subsets - lanes of a warp that hold the same pair by shuffles (pairs | 32), the rest through shared
+  // memory (the tile buffers are free now) - then one partial row per CTA
+  __syncthreads();
+  constexpr int NACC = CO_T * CI_T * 9;
+  const bool shfl = pairs < 32 && (32 % pairs) == 0;
+  if (shfl) {
+    for (int off = pairs; off < 32; off <<= 1) {
+#pragma unroll
+      for (int j = 0; j < CO_T; ++j) {
+        bsum[j] += __shfl_xor_sync(0xffffffffu, bsum[j], off);
+#pragma unroll
+        for (int i = 0; i < CI_T; ++i)
+#pragma unroll
+          for (int t = 0; t < 9; ++t) acc[j][i][t] += __shfl_xor_sync(0xffffffffu, acc[j][i][t], off);
+      }
+    }
+  }
+  const int n_sub = shfl ? WG2_NT / 32 : S;       // partial sets left in shared memory
+  const int my_sub = shfl ? (int)(threadIdx.x >> 5) : s;
+  const bool writer = shfl ? (int)(threadIdx.x & 31) < pairs : worker;
+  float* red = sm;                               // [n_sub][pairs][NACC + CO_T]
+  if (writer) {
+    float* mine = red + ((size_t)my_sub * pairs + pair) * (NACC + CO_T);
+#pragma unroll
+    for (int j = 0; j < CO_T; ++j) {
+#pragma unroll
+      for (int i = 0; i < CI_T; ++i)
+#pragma unroll
+        for (int t = 0; t < 9; ++t) mine[(j * CI_T + i) * 9 + t] = acc[j][i][t];
+      mine[NACC + j] = bsum[j];
+    }
+  }
+  __syncthreads();
+  const int n_dw = Cout * Cin * 9;
+  float* my_part = part + (size_t)blockIdx.x * (n_dw + Cout);
+  for (int e = threadIdx.x; e < pairs * (NACC + CO_T); e += WG2_NT) {
+    const int pr = e / (NACC + CO_T), k = e - pr * (NACC + CO_T);
+    float v = 0.f;
+    for (int q = 0; q < n_sub; ++q) v += red[((size_t)q * pairs + pr) * (NACC + CO_T) + k];
+    const int pcib = pr % n_cib, pcb = pr / n_cib;
+    if (k < NACC) {
+      const int j = k / (CI_T * 9), i = (k / 9) % CI_T, t = k % 9;
+      const int co = pcb + j * n_cb, ci = pcib + i * n_cib;
+      if (co < Cout && ci < Cin) my_part[((size_t)co * Cin + ci) * 9 + t] = v;
+    } else if (pcib == 0) {
+      const int co = pcb + (k - NACC) * n_cb;
+      if (co < Cout) my_part[n_dw + co] = v;
+    }
+  }
+}
+
+// out[o] = sum over the CTAs' partial rows in a fixed order: one warp per output, lane l adds rows l, l + 32, ..., then a
+// butterfly (a: the first n_a outputs, b: the rest)
+__global__ void __launch_bounds__(256)
+reduce_partials_kernel(const float* __restrict__ part, int n_parts, int n, float* __restrict__ a, int n_a, float* __restrict__ b) {
+  const int o = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (o >= n) return;
+  float v = 0.f;
+  for (int p = lane; p < n_parts; p += 32) v += part[(size_t)p * n + o];
+  v = warp_sum(v);
+  if (lane == 0) {
+    if (o < n_a) a[o] = v;
+    else if (b) b[o - n_a] = v;
+  }
+}
+
 // ---- ConvTranspose2d(Cin, Cout, 2, stride=2): data gradient
 //   dx[b][ci][h][w] = sum_{co,i,j} w[ci][co][i][j] dy[b][co][2h+i][2w+j]
 __global__ void __launch_bounds__(256)
@@ -335,6 +491,104 @@ convT2x2_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
 #pragma unroll
     for (int k = 0; k < 4; ++k) atomicAdd(dw + ((size_t)ci * Cout + co) * 4 + k, a[q][k]);
     if (ci == 0 && db) atomicAdd(db + co, bs[q]);
+  }
+}
+
+
+// register-blocked form (product path): a thread owns CO_T x CI_T channel pairs (4 accumulators each) for a subset of the
+// tile's pixels; lanes of a warp hold different pairs of the same pixel (broadcast loads, plane pitches 257 / 1026 words);
+// per-CTA partial rows + the fixed-order reduction (reduce_partials_kernel).  The kernel above used one thread per pair for
+// all 256 pixels of a tile: 32 of 256 threads busy for ConvTranspose2d(16, 2).
+constexpr int TW2_XPL = 257, TW2_DPL = 1026;
+template <int CO_T, int CI_T>
+__global__ void __launch_bounds__(256, 2)
+convT2x2_wgrad2_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ part, int Cin, int Cout,
+                       int H, int W, int n_tiles, int n_cb, int n_cib, int want_db) {
+  extern __shared__ __align__(16) float sm[];
+  const int cin_pad = n_cib * CI_T, cout_pad = n_cb * CO_T;
+  float* xs = sm;                                     // [cin_pad][257]
+  float* ds = sm + (((size_t)cin_pad * TW2_XPL + 1) & ~(size_t)1);   // [cout_pad][1026], 8-byte aligned
+  const int tiles_w = W / 16, tiles_img = tiles_w * (H / 16);
+  const int pairs = n_cb * n_cib;
+  const int S = 256 / pairs;
+  const int pair = threadIdx.x % pairs, s = threadIdx.x / pairs;
+  const bool worker = s < S;
+  const int cib = pair % n_cib, cb = pair / n_cib;
+  float a[CO_T][CI_T][4], bs[CO_T];
+#pragma unroll
+  for (int j = 0; j < CO_T; ++j) {
+    bs[j] = 0.f;
+#pragma unroll
+    for (int i = 0; i < CI_T; ++i) a[j][i][0] = a[j][i][1] = a[j][i][2] = a[j][i][3] = 0.f;
+  }
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int b = tile / tiles_img, trem = tile - b * tiles_img;
+    const int th = trem / tiles_w, tw = trem - th * tiles_w;
+    __syncthreads();
+    for (int e = threadIdx.x; e < cin_pad * 64; e += 256) {
+      const int ci = e >> 6, r = (e >> 2) & 15, k = e & 3;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ci < Cin) v = *reinterpret_cast<const float4*>(x + (((size_t)b * Cin + ci) * H + th * 16 + r) * W + tw * 16 + 4 * k);
+      float* dst = xs + ci * TW2_XPL + r * 16 + 4 * k;
+      dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+    }
+    for (int e = threadIdx.x; e < cout_pad * 256; e += 256) {
+      const int co = e >> 8, r = (e >> 3) & 31, k = e & 7;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (co < Cout) v = *reinterpret_cast<const float4*>(dy + (((size_t)b * Cout + co) * (2 * H) + th * 32 + r) * (size_t)(2 * W) + tw * 32 + 4 * k);
+      float2* dst = reinterpret_cast<float2*>(ds + co * TW2_DPL + r * 32 + 4 * k);
+      dst[0] = make_float2(v.x, v.y); dst[1] = make_float2(v.z, v.w);
+    }
+    __syncthreads();
+    if (!worker) continue;
+    for (int p = s; p < 256; p += S) {
+      const int r = p >> 4, c = p & 15;
+      float xv[CI_T];
+#pragma unroll
+      for (int i = 0; i < CI_T; ++i) xv[i] = xs[(cib + i * n_cib) * TW2_XPL + p];
+#pragma unroll
+      for (int j = 0; j < CO_T; ++j) {
+        const float* d = ds + (cb + j * n_cb) * TW2_DPL + (2 * r) * 32 + 2 * c;
+        const float2 d0 = *reinterpret_cast<const float2*>(d), d1 = *reinterpret_cast<const float2*>(d + 32);
+        if (want_db && cib == 0) bs[j] += (d0.x + d0.y) + (d1.x + d1.y);
+#pragma unroll
+        for (int i = 0; i < CI_T; ++i) {
+          a[j][i][0] = fmaf(xv[i], d0.x, a[j][i][0]); a[j][i][1] = fmaf(xv[i], d0.y, a[j][i][1]);
+          a[j][i][2] = fmaf(xv[i], d1.x, a[j][i][2]); a[j][i][3] = fmaf(xv[i], d1.y, a[j][i][3]);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  constexpr int NACC = CO_T * CI_T * 4;
+  float* red = sm;                               // [S][pairs][NACC + CO_T]
+  if (worker) {
+    float* mine = red + ((size_t)s * pairs + pair) * (NACC + CO_T);
+#pragma unroll
+    for (int j = 0; j < CO_T; ++j) {
+#pragma unroll
+      for (int i = 0; i < CI_T; ++i)
+#pragma unroll
+        for (int t = 0; t < 4; ++t) mine[(j * CI_T + i) * 4 + t] = a[j][i][t];
+      mine[NACC + j] = bs[j];
+    }
+  }
+  __syncthreads();
+  const int n_dw = Cin * Cout * 4;
+  float* my_part = part + (size_t)blockIdx.x * (n_dw + Cout);
+  for (int e = threadIdx.x; e < pairs * (NACC + CO_T); e += 256) {
+    const int pr = e / (NACC + CO_T), k = e - pr * (NACC + CO_T);
+    float v = 0.f;
+    for (int q = 0; q < S; ++q) v += red[((size_t)q * pairs + pr) * (NACC + CO_T) + k];
+    const int pcib = pr % n_cib, pcb = pr / n_cib;
+    if (k < NACC) {
+      const int j = k / (CI_T * 4), i = (k / 4) % CI_T, t = k & 3;
+      const int co = pcb + j * n_cb, ci = pcib + i * n_cib;
+      if (co < Cout && ci < Cin) my_part[((size_t)ci * Cout + co) * 4 + t] = v;
+    } else if (pcib == 0) {
+      const int co = pcb + (k - NACC) * n_cb;
+      if (co < Cout) my_part[n_dw + co] = v;
+    }
   }
 }
 
@@ -470,19 +724,71 @@ extern "C" int wmk_mask_scale_f32(const float* in, const float* mask, float* out
   return 0;
 }
 
+namespace wmk {
+namespace {
+int num_sms_cached() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+template <int CO_T, int CI_T>
+int launch_wgrad2(const float* x, const float* dy, float* dw, float* db, int B, int Cin, int Cout, int H, int W, cudaStream_t st) {
+  const int n_cb = (Cout + CO_T - 1) / CO_T, n_cib = (Cin + CI_T - 1) / CI_T, pairs = n_cb * n_cib;
+  const bool shfl = pairs < 32 && (32 % pairs) == 0;
+  const int n_sub = shfl ? WG2_NT / 32 : WG2_NT / pairs;
+  const size_t tile_b = ((size_t)n_cib * CI_T * WG2_XPL + (size_t)n_cb * CO_T * WG2_DPL) * sizeof(float);
+  const size_t red_b = (size_t)n_sub * pairs * (CO_T * CI_T * 9 + CO_T) * sizeof(float);
+  const size_t smem = tile_b > red_b ? tile_b : red_b;
+  WMK_REQUIRE(smem <= 220 * 1024, "conv3x3_wgrad: Cin=%d Cout=%d needs %zu bytes of shared memory", Cin, Cout, smem);
+  const int n_tiles = (H / 16) * (W / 16) * B;
+  auto kern = conv3x3_wgrad2_kernel<CO_T, CI_T>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    WMK_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    attr_set = true;
+  }
+  int per_sm = 1;
+  WMK_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WG2_NT, smem));
+  if (per_sm < 1) per_sm = 1;
+  const int grid = n_tiles < per_sm * num_sms_cached() ? n_tiles : per_sm * num_sms_cached();
+  const int n = Cout * Cin * 9 + Cout;
+  float* part = nullptr;
+  WMK_CHECK_CUDA(cudaMallocAsync(&part, (size_t)grid * n * sizeof(float), st));
+  kern<<<grid, WG2_NT, smem, st>>>(x, dy, part, Cin, Cout, H, W, n_tiles, n_cb, n_cib, db != nullptr);
+  WMK_CHECK_LAUNCH("conv3x3_wgrad2_kernel");
+  reduce_partials_kernel<<<cdiv(n, 8), 256, 0, st>>>(part, grid, n, dw, Cout * Cin * 9, db);
+  WMK_CHECK_LAUNCH("reduce_partials_kernel");
+  WMK_CHECK_CUDA(cudaFreeAsync(part, st));
+  return 0;
+}
+}  // namespace
+}  // namespace wmk
+
 extern "C" int wmk_conv3x3_wgrad_f32(const float* x, const float* dy, float* dw, float* db, int B, int Cin, int Cout, int H,
                                      int W, void* stream) {
-  WMK_REQUIRE(x && dy && dw && B > 0 && Cin > 0 && Cout > 0 && H % 16 == 0 && W % 16 == 0,
-              "conv3x3_wgrad: bad arguments (H, W must be multiples of 16)");
+  WMK_REQUIRE(x && dy && dw && B > 0 && Cin > 0 && Cout > 0 && H % 16 == 0 && W % 16 == 0 && ((uintptr_t)x & 15) == 0 &&
+                  ((uintptr_t)dy & 15) == 0,
+              "conv3x3_wgrad: bad arguments (H, W must be multiples of 16, buffers 16-byte aligned)");
   cudaStream_t st = (cudaStream_t)stream;
   ProfScope prof(FAM_SMALL, 4.0 * B * H * W * (Cin + Cout), st);
+  static const int legacy = getenv("WMK_WGRAD_LEGACY") ? atoi(getenv("WMK_WGRAD_LEGACY")) : 0;
+  if (!legacy) {
+    // register-blocked kernel: (output, input) channel blocking by layer shape
+    if (Cout <= 2 && (Cin + 3) / 4 * Cout <= WG2_NT && Cin <= 96) return launch_wgrad2<1, 4>(x, dy, dw, db, B, Cin, Cout, H, W, st);
+    if (((Cout + 3) / 4) * ((Cin + 1) / 2) <= WG2_NT && ((size_t)((Cin + 1) / 2 * 2) * WG2_XPL + (size_t)((Cout + 3) / 4 * 4) * WG2_DPL) * 4 <= 220 * 1024)
+      return launch_wgrad2<4, 2>(x, dy, dw, db, B, Cin, Cout, H, W, st);
+  }
   WMK_CHECK_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)Cout * Cin * 9, st));
   if (db) WMK_CHECK_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * Cout, st));
   const size_t smem = ((size_t)Cin * 18 * 18 + (size_t)Cout * 256) * sizeof(float);
   WMK_REQUIRE(smem <= 200 * 1024, "conv3x3_wgrad: Cin=%d Cout=%d needs %zu bytes of shared memory", Cin, Cout, smem);
   const int n_tiles = (H / 16) * (W / 16) * B;
-  int sms = 148;
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  const int sms = num_sms_cached();
   const int grid = n_tiles < 2 * sms ? n_tiles : 2 * sms;
   // CB output channels per thread: keep (Cout/CB)*Cin <= 256 thread slots
   if ((size_t)((Cout + 3) / 4) * Cin <= 256) {
@@ -510,20 +816,58 @@ extern "C" int wmk_convT2x2_dgrad_f32(const float* dy, const float* w, float* dx
   return 0;
 }
 
+namespace wmk {
+namespace {
+template <int CO_T, int CI_T>
+int launch_convT_wgrad2(const float* x, const float* dy, float* dw, float* db, int B, int Cin, int Cout, int H, int W, cudaStream_t st) {
+  const int n_cb = (Cout + CO_T - 1) / CO_T, n_cib = (Cin + CI_T - 1) / CI_T, pairs = n_cb * n_cib;
+  const int S = 256 / pairs;
+  const size_t tile_b = ((((size_t)n_cib * CI_T * TW2_XPL + 1) & ~(size_t)1) + (size_t)n_cb * CO_T * TW2_DPL) * sizeof(float);
+  const size_t red_b = (size_t)S * pairs * (CO_T * CI_T * 4 + CO_T) * sizeof(float);
+  const size_t smem = tile_b > red_b ? tile_b : red_b;
+  const int n_tiles = (H / 16) * (W / 16) * B;
+  auto kern = convT2x2_wgrad2_kernel<CO_T, CI_T>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    WMK_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    attr_set = true;
+  }
+  int per_sm = 1;
+  WMK_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));
+  if (per_sm < 1) per_sm = 1;
+  const int grid = n_tiles < per_sm * num_sms_cached() ? n_tiles : per_sm * num_sms_cached();
+  const int n = Cin * Cout * 4 + Cout;
+  float* part = nullptr;
+  WMK_CHECK_CUDA(cudaMallocAsync(&part, (size_t)grid * n * sizeof(float), st));
+  kern<<<grid, 256, smem, st>>>(x, dy, part, Cin, Cout, H, W, n_tiles, n_cb, n_cib, db != nullptr);
+  WMK_CHECK_LAUNCH("convT2x2_wgrad2_kernel");
+  reduce_partials_kernel<<<cdiv(n, 8), 256, 0, st>>>(part, grid, n, dw, Cin * Cout * 4, db);
+  WMK_CHECK_LAUNCH("reduce_partials_kernel");
+  WMK_CHECK_CUDA(cudaFreeAsync(part, st));
+  return 0;
+}
+}  // namespace
+}  // namespace wmk
+
 extern "C" int wmk_convT2x2_wgrad_f32(const float* x, const float* dy, float* dw, float* db, int B, int Cin, int Cout, int H,
                                       int W, void* stream) {
-  WMK_REQUIRE(x && dy && dw && B > 0 && B <= 65535 && Cin > 0 && Cout > 0 && H % 16 == 0 && W % 16 == 0,
-              "convT2x2_wgrad: bad arguments (H, W must be multiples of 16)");
+  WMK_REQUIRE(x && dy && dw && B > 0 && B <= 65535 && Cin > 0 && Cout > 0 && H % 16 == 0 && W % 16 == 0 && ((uintptr_t)x & 15) == 0 &&
+                  ((uintptr_t)dy & 15) == 0,
+              "convT2x2_wgrad: bad arguments (H, W must be multiples of 16, buffers 16-byte aligned)");
   cudaStream_t st = (cudaStream_t)stream;
   ProfScope prof(FAM_SMALL, 4.0 * B * H * W * (Cin + 4 * Cout), st);
-  WMK_CHECK_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)Cout * Cin * 4, st));
-  if (db) WMK_CHECK_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * Cout, st));
   const size_t smem = ((size_t)Cin * 256 + (size_t)Cout * 1024) * sizeof(float);
   WMK_REQUIRE(smem <= 200 * 1024, "convT2x2_wgrad: Cin=%d Cout=%d needs %zu bytes of shared memory", Cin, Cout, smem);
+  static const int legacy = getenv("WMK_WGRAD_LEGACY") ? atoi(getenv("WMK_WGRAD_LEGACY")) : 0;
+  if (!legacy) {
+    if (Cout <= 2 && (Cin + 1) / 2 <= 256) return launch_convT_wgrad2<2, 2>(x, dy, dw, db, B, Cin, Cout, H, W, st);
+    if (((Cout + 3) / 4) * ((Cin + 2) / 3) <= 256) return launch_convT_wgrad2<4, 3>(x, dy, dw, db, B, Cin, Cout, H, W, st);
+  }
+  WMK_CHECK_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)Cout * Cin * 4, st));
+  if (db) WMK_CHECK_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * Cout, st));
   WMK_REQUIRE(Cin * Cout <= 256 * TW_PAIRS, "convT2x2_wgrad: Cin*Cout=%d exceeds %d", Cin * Cout, 256 * TW_PAIRS);
   const int n_tiles = (H / 16) * (W / 16) * B;
-  int sms = 148;
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  const int sms = num_sms_cached();
   const int grid = n_tiles < 2 * sms ? n_tiles : 2 * sms;
   if (smem > 48 * 1024) WMK_CHECK_CUDA(cudaFuncSetAttribute(convT2x2_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   convT2x2_wgrad_kernel<<<grid, 256, smem, st>>>(x, dy, dw, db, Cin, Cout, H, W, n_tiles);

@@ -7,6 +7,8 @@
 // Channel counts here are 1..64 and the tensors are small: these are memory-bound direct kernels
 // (input tile + halo staged in shared memory, weights in shared memory, 16 output channels per
 // thread in registers).
+#include <stdlib.h>
+
 #include "uformer_kernels.cuh"
 
 namespace wmk {
@@ -21,37 +23,62 @@ __device__ __forceinline__ float apply_act(float v, int act, float slope) {
   return v;
 }
 
-constexpr int CT = 16;      // output tile edge
+
 // output channels per CTA (COB) and input channels per shared-memory pass (CIB) are template parameters: the layers with
 // 1 / 2 input or output channels (ModelA's first / last layers and their data gradients, all at 128 x 128) would waste
 // 4x / 8x of the FMAs and weight loads in the generic 8 x 16 blocking
 
 // y[b][co_off+co][h][w] = act( scale[co] * (sum_{ci,dy,dx} x[b][ci][h+dy-1][w+dx-1] w[co][ci][dy][dx] + bias[co]) + shift[co] )
-template <int CIB, int COB>
+// Tile = 32 columns x 8 PX rows; a warp covers one 32-pixel row segment (conflict-free shared-memory reads, 128-byte
+// stores), a thread PX pixels (rows ty, ty + 8, ...): a weight fetched from shared memory feeds PX FMAs, which moves the
+// COB = 16 layers from the load / store pipe (5 loads per 16 FMAs) to the FMA pipe.  The input tile (+ halo) arrives as
+// 16-byte loads: row = [3 pad][halo][32 pixels][halo][3 pad].
+constexpr int CTW = 32, CXP = 40;
+template <int CIB, int COB, int PX>
 __global__ void __launch_bounds__(256)
 conv3x3_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ w,
                const float* __restrict__ bias, const float* __restrict__ scale, const float* __restrict__ shift,
                int Cin, int Cout, int H, int W, int co_off, int Ctot, int act, float slope) {
-  __shared__ float tile[CIB][CT + 2][CT + 2];
+  constexpr int TH = 8 * PX;
+  __shared__ __align__(16) float tile[CIB][TH + 2][CXP];
   __shared__ __align__(16) float ws[CIB][9][COB];
-  const int tiles_w = (W + CT - 1) / CT;
+  const int tiles_w = (W + CTW - 1) / CTW;
   const int th = blockIdx.x / tiles_w, tw = blockIdx.x % tiles_w;
   const int co0 = blockIdx.y * COB;
   const int b = blockIdx.z;
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  const int h = th * CT + ty, wq = tw * CT + tx;
-  float acc[COB];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int wq = tw * CTW + tx;
+  const bool vec_ok = (W & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+  float acc[PX][COB];
 #pragma unroll
-  for (int j = 0; j < COB; ++j) acc[j] = 0.f;
+  for (int p = 0; p < PX; ++p)
+#pragma unroll
+    for (int j = 0; j < COB; ++j) acc[p][j] = 0.f;
   for (int c0 = 0; c0 < Cin; c0 += CIB) {
     __syncthreads();
-    for (int e = threadIdx.x; e < CIB * (CT + 2) * (CT + 2); e += 256) {
-      const int ci = e / ((CT + 2) * (CT + 2)), r = (e / (CT + 2)) % (CT + 2), c = e % (CT + 2);
-      const int hh = th * CT + r - 1, ww = tw * CT + c - 1;
-      float v = 0.f;
-      if (c0 + ci < Cin && hh >= 0 && hh < H && ww >= 0 && ww < W)
-        v = x[(((size_t)b * Cin + c0 + ci) * H + hh) * W + ww];
-      tile[ci][r][c] = v;
+#pragma unroll 4
+    for (int e = threadIdx.x; e < CIB * (TH + 2) * 10; e += 256) {      // per row: halo, 8 x 16 bytes, halo
+      const int ci = e / ((TH + 2) * 10), rem = e - ci * ((TH + 2) * 10), r = rem / 10, k = rem - r * 10;
+      const int hh = th * TH + r - 1;
+      const bool ok = c0 + ci < Cin && hh >= 0 && hh < H;
+      const float* src = x + (((size_t)b * Cin + c0 + ci) * H + (ok ? hh : 0)) * W + tw * CTW;
+      float* dst = &tile[ci][r][0];
+      if (k == 0) dst[3] = (ok && tw > 0) ? src[-1] : 0.f;
+      else if (k == 9) dst[36] = (ok && tw * CTW + CTW < W) ? src[CTW] : 0.f;
+      else {
+        const int c = 4 * (k - 1), ww = tw * CTW + c;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok) {
+          if (vec_ok && ww + 3 < W) v = *reinterpret_cast<const float4*>(src + c);
+          else {
+            if (ww < W) v.x = src[c];
+            if (ww + 1 < W) v.y = src[c + 1];
+            if (ww + 2 < W) v.z = src[c + 2];
+            if (ww + 3 < W) v.w = src[c + 3];
+          }
+        }
+        *reinterpret_cast<float4*>(dst + 4 + c) = v;
+      }
     }
     for (int e = threadIdx.x; e < CIB * 9 * COB; e += 256) {
       const int ci = e / (9 * COB), t = (e / COB) % 9, j = e % COB;
@@ -64,31 +91,53 @@ conv3x3_kernel(const float* __restrict__ x, float* __restrict__ y, const float* 
     for (int ci = 0; ci < CIB; ++ci)
 #pragma unroll
       for (int t = 0; t < 9; ++t) {
-        const float v = tile[ci][ty + t / 3][tx + t % 3];
+        float v[PX];
+#pragma unroll
+        for (int p = 0; p < PX; ++p) v[p] = tile[ci][ty + 8 * p + t / 3][tx + t % 3 + 3];
         if constexpr (COB % 4 == 0) {
           const float4* w4 = reinterpret_cast<const float4*>(&ws[ci][t][0]);      // 4 weights per shared-memory load
 #pragma unroll
           for (int j4 = 0; j4 < COB / 4; ++j4) {
             const float4 wv = w4[j4];
-            acc[4 * j4] = fmaf(v, wv.x, acc[4 * j4]);
-            acc[4 * j4 + 1] = fmaf(v, wv.y, acc[4 * j4 + 1]);
-            acc[4 * j4 + 2] = fmaf(v, wv.z, acc[4 * j4 + 2]);
-            acc[4 * j4 + 3] = fmaf(v, wv.w, acc[4 * j4 + 3]);
+#pragma unroll
+            for (int p = 0; p < PX; ++p) {
+              acc[p][4 * j4] = fmaf(v[p], wv.x, acc[p][4 * j4]);
+              acc[p][4 * j4 + 1] = fmaf(v[p], wv.y, acc[p][4 * j4 + 1]);
+              acc[p][4 * j4 + 2] = fmaf(v[p], wv.z, acc[p][4 * j4 + 2]);
+              acc[p][4 * j4 + 3] = fmaf(v[p], wv.w, acc[p][4 * j4 + 3]);
+            }
           }
         } else {
 #pragma unroll
-          for (int j = 0; j < COB; ++j) acc[j] = fmaf(v, ws[ci][t][j], acc[j]);
+          for (int j = 0; j < COB; ++j) {
+            const float wv = ws[ci][t][j];
+#pragma unroll
+            for (int p = 0; p < PX; ++p) acc[p][j] = fmaf(v[p], wv, acc[p][j]);
+          }
         }
       }
   }
-  if (h >= H || wq >= W) return;
+  if (wq >= W) return;
+  float bj[COB], sc[COB], sh[COB];
 #pragma unroll
   for (int j = 0; j < COB; ++j) {
-    const int co = co0 + j;
-    if (co >= Cout) break;
-    float v = acc[j] + (bias ? bias[co] : 0.f);
-    if (scale) v = v * scale[co] + shift[co];
-    y[(((size_t)b * Ctot + co_off + co) * H + h) * W + wq] = apply_act(v, act, slope);
+    const int co = co0 + j < Cout ? co0 + j : Cout - 1;
+    bj[j] = bias ? bias[co] : 0.f;
+    sc[j] = scale ? scale[co] : 1.f;
+    sh[j] = scale ? shift[co] : 0.f;
+  }
+#pragma unroll
+  for (int p = 0; p < PX; ++p) {
+    const int h = th * TH + ty + 8 * p;
+    if (h >= H) continue;
+#pragma unroll
+    for (int j = 0; j < COB; ++j) {
+      const int co = co0 + j;
+      if (co >= Cout) break;
+      float v = acc[p][j] + bj[j];
+      if (scale) v = v * sc[j] + sh[j];
+      y[(((size_t)b * Ctot + co_off + co) * H + h) * W + wq] = apply_act(v, act, slope);
+    }
   }
 }
 
@@ -437,15 +486,20 @@ extern "C" int wmk_conv3x3_f32(const float* x, float* y, const float* w, const f
   cudaStream_t st = (cudaStream_t)stream;
   ProfScope prof(FAM_SMALL, 4.0 * B * H * W * (Cin + Cout), st);
   const int cob = Cout <= 2 ? 2 : 16;
-  dim3 grid(cdiv(H, CT) * cdiv(W, CT), cdiv(Cout, cob), B);
-  if (Cin <= 2 && Cout <= 2)
-    conv3x3_kernel<2, 2><<<grid, 256, 0, st>>>(x, y, w, bias, scale, shift, Cin, Cout, H, W, out_ch_offset, out_ch_total, act, slope);
-  else if (Cin <= 2)
-    conv3x3_kernel<2, 16><<<grid, 256, 0, st>>>(x, y, w, bias, scale, shift, Cin, Cout, H, W, out_ch_offset, out_ch_total, act, slope);
-  else if (Cout <= 2)
-    conv3x3_kernel<8, 2><<<grid, 256, 0, st>>>(x, y, w, bias, scale, shift, Cin, Cout, H, W, out_ch_offset, out_ch_total, act, slope);
-  else
-    conv3x3_kernel<8, 16><<<grid, 256, 0, st>>>(x, y, w, bias, scale, shift, Cin, Cout, H, W, out_ch_offset, out_ch_total, act, slope);
+  static const int px_max = getenv("WMK_CONV_PX") ? atoi(getenv("WMK_CONV_PX")) : 4;
+  const int px = (H >= 32 && px_max >= 4) ? 4 : (H >= 16 && px_max >= 2) ? 2 : 1;
+  dim3 grid(cdiv(H, 8 * px) * cdiv(W, CTW), cdiv(Cout, cob), B);
+#define WMK_CONV_LAUNCH(CIB, COB)                                                                                                   \
+  do {                                                                                                                              \
+    if (px == 4) conv3x3_kernel<CIB, COB, 4><<<grid, 256, 0, st>>>(x, y, w, bias, scale, shift, Cin, Cout, H, W, out_ch_offset, out_ch_total, act, slope); \
+    else if (px == 2) conv3x3_kernel<CIB, COB, 2><<<grid, 256, 0, st>>>(x, y, w, bias, scale, shift, Cin, Cout, H, W, out_ch_offset, out_ch_total, act, slope); \
+    else conv3x3_kernel<CIB, COB, 1><<<grid, 256, 0, st>>>(x, y, w, bias, scale, shift, Cin, Cout, H, W, out_ch_offset, out_ch_total, act, slope); \
+  } while (0)
+  if (Cin <= 2 && Cout <= 2) WMK_CONV_LAUNCH(2, 2);
+  else if (Cin <= 2) WMK_CONV_LAUNCH(2, 16);
+  else if (Cout <= 2) WMK_CONV_LAUNCH(8, 2);
+  else WMK_CONV_LAUNCH(8, 16);
+#undef WMK_CONV_LAUNCH
   WMK_CHECK_LAUNCH("conv3x3_kernel");
   return 0;
 }
