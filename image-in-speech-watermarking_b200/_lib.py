@@ -79,6 +79,11 @@ SIGNATURES = {
     "wmk_leff_block_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "wmk_window_attention_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "wmk_linear_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "wmk_comm_unique_id": (_i, [_vp]),
+    "wmk_comm_create": (_i, [_vp, _i, _i, ctypes.POINTER(_vp)]),
+    "wmk_comm_destroy": (_i, [_vp]),
+    "wmk_stats_allreduce_f64": (_i, [_vp, _i, _vp, _vp]),
+    "wmk_grad_allreduce_f32": (_i, [_vp, _sz, _vp, _vp]),
 }
 
 PREC_FP32, PREC_BF16, PREC_MIXED, PREC_F16 = 0, 1, 2, 3

@@ -412,6 +412,9 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __
     const int slab = (ew >> 2) % SLABS;           // which CPW-wide column slab of the team's tile
     if (team < TEAMS) {
       const uint32_t buf = staging + (uint32_t)ew * STG_BYTES;
+      // 16-bit staging box: this lane's row offset and swizzle key (hoisted out of the piece loop)
+      const uint32_t sw_row = (uint32_t)lane * (BOXC == 64 ? 128u : 64u);
+      const uint32_t sw_x = BOXC == 64 ? (uint32_t)(lane & 7) : ((uint32_t)(lane >> 1) & 3u);
       int m0, n0;
       // resid_tma: the residual rows of a tile are fetched by one TMA box into this warp's staging buffer (the buffer
       // alternates residual-in / result-out), issued as soon as the previous tile's store has been read - instead of
@@ -466,9 +469,11 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __
           if (p.bias) {
             const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < 8; ++j) {                  // packed fp32x2 adds: 16 instead of 32 issue slots per piece
               const float4 b = __ldg(b4 + j);
-              f[4 * j] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
+              const float2 lo = __fadd2_rn(make_float2(f[4 * j], f[4 * j + 1]), make_float2(b.x, b.y));
+              const float2 hi = __fadd2_rn(make_float2(f[4 * j + 2], f[4 * j + 3]), make_float2(b.z, b.w));
+              f[4 * j] = lo.x; f[4 * j + 1] = lo.y; f[4 * j + 2] = hi.x; f[4 * j + 3] = hi.y;
             }
           }
           if constexpr (EPI == EPI_BIAS_GELU) {
@@ -520,27 +525,26 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __
             }
           }
           // stage this 32-column piece (one warp-private buffer; the previous store must have been read)
-          const bool first_piece = OUT_BF16 ? (cc % BOXC) == 0 : true;
+          const int cbox = cc & (BOXC - 1);               // BOXC is 32 or 64 (a runtime % cost an integer division per piece)
+          const bool first_piece = OUT_BF16 ? cbox == 0 : true;
           if (first_piece && !rtma) {                   // rtma: the buffer was drained before the residual load was issued
             if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             __syncwarp();
           }
           if constexpr (OUT_BF16) {
-            const int piece = (cc % BOXC) / 32;
+            const uint32_t c16_0 = (uint32_t)(cbox >> 5) * 4u;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const uint32_t c16 = (uint32_t)(piece * 4 + j);
-              uint32_t off;
-              if (BOXC == 64) off = (uint32_t)lane * 128u + ((c16 ^ (uint32_t)(lane & 7)) << 4);       // SWIZZLE_128B
-              else off = (uint32_t)lane * 64u + ((c16 ^ ((uint32_t)(lane >> 1) & 3u)) << 4);          // SWIZZLE_64B
+              // SWIZZLE_128B (64-column box): row pitch 128 B, chunk ^ (row & 7); SWIZZLE_64B: pitch 64 B, chunk ^ ((row >> 1) & 3)
+              const uint32_t off = sw_row + (((c16_0 + (uint32_t)j) ^ sw_x) << 4);
               uint32_t w0, w1, w2, w3;
               pack8_16(f + 8 * j, p.f16 != 0, w0, w1, w2, w3);
               st_shared_v4(buf + off, w0, w1, w2, w3);
             }
-            if ((cc % BOXC) + 32 == BOXC) {
+            if (cbox + 32 == BOXC) {
               asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
               __syncwarp();
-              if (lane == 0) tma_store_2d(&tmC, buf, n - (cc % BOXC), m0 + q * 32);
+              if (lane == 0) tma_store_2d(&tmC, buf, n - cbox, m0 + q * 32);
             }
           } else {
 #pragma unroll

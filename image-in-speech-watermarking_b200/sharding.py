@@ -25,12 +25,60 @@ def stats_vector(stats):
                         stats[:, 1].sum(), stats[:, 3].sum(), one(B)])
 
 
+_comm = None          # (ncclComm_t handle, world size) of wmk_comm_create, made on first use
+
+
+def wmk_comm():
+    """The library's own NCCL communicator over the ranks of the default process group (`include/wmk.h`
+    wmk_comm_create): rank 0 draws the ncclUniqueId, torch.distributed only carries its 128 bytes.  None when
+    torch.distributed is not initialised or has a single rank."""
+    global _comm
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return None
+    if _comm is None:
+        import ctypes
+        from . import _lib
+        lib = _lib.load()
+        rank, world = dist.get_rank(), dist.get_world_size()
+        buf = (ctypes.c_ubyte * 128)()
+        if rank == 0:
+            _lib.check(lib.wmk_comm_unique_id(buf))
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+        t = torch.tensor(list(buf), dtype=torch.uint8, device=dev)
+        dist.broadcast(t, 0)
+        buf = (ctypes.c_ubyte * 128)(*t.cpu().tolist())
+        h = ctypes.c_void_p()
+        _lib.check(lib.wmk_comm_create(buf, world, rank, ctypes.byref(h)))
+        _comm = (h, world)
+    return _comm[0]
+
+
 def allreduce_stats(vec):
-    """Sum the statistics vector over all ranks (NCCL on GPUs, gloo in the CPU tests); identity when
-    torch.distributed is not initialised."""
+    """Sum the statistics vector over all ranks: `wmk_stats_allreduce_f64` (NCCL through the C ABI, on the current
+    stream) for device vectors, gloo in the CPU tests; identity when torch.distributed is not initialised."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        dist.all_reduce(vec)
+        if vec.is_cuda and vec.dtype == torch.float64 and vec.is_contiguous():
+            from . import _lib
+            _lib.check(_lib.load().wmk_stats_allreduce_f64(_lib.ptr(vec), vec.numel(), wmk_comm(), _lib.stream_ptr()))
+        else:
+            dist.all_reduce(vec)
     return vec
+
+
+def allreduce_grads(flat_grad):
+    """Sum the flat fp32 gradient buffer of the data-parallel training step over all ranks (`wmk_grad_allreduce_f32`
+    on the device, gloo on the CPU); returns the world size."""
+    world = 1
+    if dist.is_available() and dist.is_initialized():
+        world = dist.get_world_size()
+        if world > 1:
+            if flat_grad.is_cuda and flat_grad.dtype == torch.float32 and flat_grad.is_contiguous():
+                from . import _lib
+                _lib.check(_lib.load().wmk_grad_allreduce_f32(_lib.ptr(flat_grad), flat_grad.numel(), wmk_comm(),
+                                                              _lib.stream_ptr()))
+            else:
+                dist.all_reduce(flat_grad)
+    return world
 
 
 def summarize(vec):

@@ -11,7 +11,6 @@ BatchNorm statistics stay per rank as in plain DDP).  BASELINE config 5's 'embed
 a differentiable attack between encode and decode: additive Gaussian noise (as the reference's own
 Uformer variants do, `uformerWM/model.py:1986,2022`)."""
 import torch
-import torch.distributed as dist
 
 from . import cnn_train
 
@@ -23,14 +22,10 @@ def gaussian_attack(std, generator=None):
 
 
 def sync_gradients(flat_grad):
-    """Sum the flat gradient buffer over the ranks (one collective); returns the world size (the mean
-    is taken by the Adam kernel's grad_scale)."""
-    world = 1
-    if dist.is_available() and dist.is_initialized():
-        world = dist.get_world_size()
-        if world > 1:
-            dist.all_reduce(flat_grad)
-    return world
+    """Sum the flat gradient buffer over the ranks (one collective: `wmk_grad_allreduce_f32`, NCCL through the
+    C ABI); returns the world size (the mean is taken by the Adam kernel's grad_scale)."""
+    from . import sharding
+    return sharding.allreduce_grads(flat_grad)
 
 
 def train_step(model, optimizer, input_, message, loss_scale=1.0):

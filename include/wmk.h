@@ -183,6 +183,21 @@ int wmk_wm_stats_f64(const float* wm, const float* msg, int n, int msg_stride, d
                      void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Collectives of the path (SURVEY 8b "wmk_stats_allreduce(double*, ncclComm_t, cudaStream_t)", 8e).  The reference is
+ * single-process (uformerWM/evaluate.py:372-374 loops over utterances; uformerWM/train_modelA.py:402-500 one GPU); the
+ * sharded drop-in needs exactly two exchanges: the additive statistics vector of wmk_stats_finalize_f64 at the end of
+ * an evaluation, and the flat gradient buffer of the data-parallel training step.  `nccl_comm` is an ncclComm_t - the
+ * host's own, or one made by wmk_comm_create from a 128-byte ncclUniqueId (rank 0 calls wmk_comm_unique_id and
+ * distributes the bytes).  NCCL is resolved from the process at run time (dlsym / libnccl.so.2): without it these return
+ * WMK_ERR_UNSUPPORTED.  In place, sum, asynchronous on `stream`.
+ * ------------------------------------------------------------------------------------------ */
+int wmk_comm_unique_id(void* id128);
+int wmk_comm_create(const void* id128, int nranks, int rank, void** nccl_comm);
+int wmk_comm_destroy(void* nccl_comm);
+int wmk_stats_allreduce_f64(double* stats, int n, void* nccl_comm, void* stream);
+int wmk_grad_allreduce_f32(float* grads, size_t n, void* nccl_comm, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * CNN layers of ModelA (uformerWM/model.py:3000-3066) and of the HiDDeN Decoder / ConvBNRelu
  * (hidden/model/decoder.py:12-40, hidden/model/conv_bn_relu.py:7-18), NCHW float32.
  * act: 0 none, 1 ReLU, 2 LeakyReLU(slope), 3 sigmoid.  scale/shift (both or neither) carry the

@@ -805,3 +805,47 @@ def test_batched_evaluate_writes_the_reference_result_line(models, weights, tmp_
     assert abs(out["mse"] - np.mean([e["mse"] for e in evs])) < 1e-3 * np.mean([e["mse"] for e in evs])
     rows = RX.parse_results(open(tmp_path / "sample_result.txt").read())
     assert len(rows) == 1 and rows[0]["Set"] == "test set" and rows[0]["Attack"] == "echo_addition" and rows[0]["Total Clips"] == out["clips"]
+
+
+@pytest.mark.gpu
+def test_cabi_collectives_single_rank_and_torchrun_world2(tmp_path):
+    """The two collectives of the path through the C ABI (`include/wmk.h` wmk_comm_* / wmk_stats_allreduce_f64 /
+    wmk_grad_allreduce_f32): a one-rank communicator made from a unique id leaves the vectors unchanged; with two
+    visible GPUs a world-size-2 torchrun checks the sums against the closed form (skipped on a one-GPU box - the
+    gloo test in test_multirank_cpu.py covers the host logic there)."""
+    import ctypes
+    import subprocess
+    import sys
+    from image_in_speech_watermarking_b200 import _lib
+    lib = _lib.load()
+    uid = (ctypes.c_ubyte * 128)()
+    _lib.check(lib.wmk_comm_unique_id(uid))
+    comm = ctypes.c_void_p()
+    _lib.check(lib.wmk_comm_create(uid, 1, 0, ctypes.byref(comm)))
+    vec = torch.arange(8, device="cuda", dtype=torch.float64) + 0.5
+    grads = torch.linspace(-1, 1, 17655, device="cuda")
+    want_v, want_g = vec.clone(), grads.clone()
+    _lib.check(lib.wmk_stats_allreduce_f64(_lib.ptr(vec), 8, comm, _lib.stream_ptr()))
+    _lib.check(lib.wmk_grad_allreduce_f32(_lib.ptr(grads), grads.numel(), comm, _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    assert torch.equal(vec, want_v) and torch.equal(grads, want_g)
+    _lib.check(lib.wmk_comm_destroy(comm))
+    assert lib.wmk_stats_allreduce_f64(_lib.ptr(vec), 8, None, _lib.stream_ptr()) != 0          # null communicator: error, no crash
+    if torch.cuda.device_count() < 2:
+        return
+    script = tmp_path / "w2.py"
+    script.write_text(
+        "import os, sys, torch, torch.distributed as dist\n"
+        "sys.path.insert(0, %r)\n"
+        "from image_in_speech_watermarking_b200 import sharding as SH\n"
+        "r = int(os.environ['RANK']); torch.cuda.set_device(int(os.environ['LOCAL_RANK']))\n"
+        "dist.init_process_group('nccl', device_id=torch.device('cuda', int(os.environ['LOCAL_RANK'])))\n"
+        "v = torch.full((8,), r + 1.0, device='cuda', dtype=torch.float64); SH.allreduce_stats(v)\n"
+        "g = torch.full((17655,), r + 1.0, device='cuda'); w = SH.allreduce_grads(g)\n"
+        "torch.cuda.synchronize()\n"
+        "assert w == 2 and torch.all(v == 3.0) and torch.all(g == 3.0), (v, g[:4])\n"
+        "dist.destroy_process_group()\n" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
