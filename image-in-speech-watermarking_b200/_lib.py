@@ -52,6 +52,9 @@ SIGNATURES = {
     "wmk_maxpool2x2_bwd_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "wmk_mask_scale_f32": (_i, [_vp, _vp, _vp, _sz, _f, _vp]),
     "wmk_conv3x3_wgrad_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "wmk_conv3x3_dgrad_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "wmk_bn_pool_train_fwd_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _i, _f, _vp]),
+    "wmk_bn_pool_train_bwd_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp]),
     "wmk_convT2x2_dgrad_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "wmk_convT2x2_wgrad_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "wmk_affine_f32": (_i, [_vp, _vp, _sz, _f, _f, _vp]),

@@ -43,10 +43,8 @@ class _Conv3x3(torch.autograd.Function):
         Cout = w.shape[0]
         dx = None
         if ctx.needs_input_grad[0]:
-            wt = w.flip(2, 3).transpose(0, 1).contiguous()            # [Cin][Cout][3][3]: correlation with the flipped kernel
-            dx = torch.empty_like(x)
-            _lib.check(lib.wmk_conv3x3_f32(_lib.ptr(dy), _lib.ptr(dx), _lib.ptr(wt), None, None, None, B, Cout, Cin, H, W, 0,
-                                           Cin, ACT_NONE, 0.0, _lib.stream_ptr()))
+            dx = torch.empty_like(x)                                  # correlation with the flipped kernel, weights read in place
+            _lib.check(lib.wmk_conv3x3_dgrad_f32(_lib.ptr(dy), _lib.ptr(w), _lib.ptr(dx), B, Cin, Cout, H, W, _lib.stream_ptr()))
         dw = torch.empty_like(w)
         db = torch.empty(Cout, device=x.device, dtype=torch.float32) if ctx.has_bias else None
         _lib.check(lib.wmk_conv3x3_wgrad_f32(_lib.ptr(x), _lib.ptr(dy), _lib.ptr(dw), _lib.ptr(db), B, Cin, Cout, H, W,
@@ -116,6 +114,41 @@ class _BNAct(torch.autograd.Function):
         _lib.check(lib.wmk_bn_train_bwd_f32(_lib.ptr(x), _lib.ptr(y), _lib.ptr(dy), _lib.ptr(dx), _lib.ptr(gamma), _lib.ptr(mr),
                                             _lib.ptr(dg), _lib.ptr(db), _lib.ptr(_scratch(C, x.device)), B, C, H * W, ctx.act,
                                             ctx.slope, _lib.stream_ptr()))
+        return dx, dg, db, None, None, None, None, None, None
+
+
+class _BNActPool(torch.autograd.Function):
+    """BatchNorm2d (batch statistics) + activation + MaxPool2d(2,2) as one forward pass and one backward pair
+    (`wmk_bn_pool_train_fwd/bwd_f32`): the pooling layer's input is written once, its full-resolution gradient never."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, eps, momentum, act, slope):
+        lib = _lib.load()
+        x = _c(x)
+        B, C, H, W = x.shape
+        y = torch.empty_like(x)
+        yp = torch.empty((B, C, H // 2, W // 2), device=x.device, dtype=torch.float32)
+        mr = torch.empty((C, 2), device=x.device, dtype=torch.float32)
+        _lib.check(lib.wmk_bn_pool_train_fwd_f32(_lib.ptr(x), _lib.ptr(y), _lib.ptr(yp), _lib.ptr(_c(gamma)), _lib.ptr(_c(beta)),
+                                                 _lib.ptr(running_mean), _lib.ptr(running_var), _lib.ptr(mr),
+                                                 _lib.ptr(_scratch(C, x.device)), B, C, H, W, eps, momentum, act, slope,
+                                                 _lib.stream_ptr()))
+        ctx.save_for_backward(x, y, _c(gamma), mr)
+        ctx.act, ctx.slope = act, slope
+        return yp
+
+    @staticmethod
+    def backward(ctx, dyp):
+        lib = _lib.load()
+        x, y, gamma, mr = ctx.saved_tensors
+        dyp = _c(dyp)
+        B, C, H, W = x.shape
+        dx = torch.empty_like(x)
+        dg = torch.empty(C, device=x.device, dtype=torch.float32)
+        db = torch.empty(C, device=x.device, dtype=torch.float32)
+        _lib.check(lib.wmk_bn_pool_train_bwd_f32(_lib.ptr(x), _lib.ptr(y), _lib.ptr(dyp), _lib.ptr(dx), _lib.ptr(gamma),
+                                                 _lib.ptr(mr), _lib.ptr(dg), _lib.ptr(db), _lib.ptr(_scratch(C, x.device)),
+                                                 B, C, H, W, ctx.act, ctx.slope, _lib.stream_ptr()))
         return dx, dg, db, None, None, None, None, None, None
 
 
@@ -205,7 +238,14 @@ def run_sequential_train(seq, x, dropout_masks=None):
                 act, slope = _act_of(mods[i + 1])
                 i += 1
             momentum = 0.1 if m.momentum is None else float(m.momentum)
-            x = _BNAct.apply(x, m.weight, m.bias, m.running_mean, m.running_var, float(m.eps), momentum, act, slope)
+            nxt = mods[i + 1] if i + 1 < len(mods) else None
+            pool = (isinstance(nxt, nn.MaxPool2d) and nxt.kernel_size in (2, (2, 2)) and nxt.stride in (2, (2, 2)) and
+                    nxt.padding in (0, (0, 0)) and x.shape[2] % 2 == 0 and x.shape[3] % 4 == 0)
+            if pool:                                   # BatchNorm + activation + MaxPool2d(2,2) fused
+                x = _BNActPool.apply(x, m.weight, m.bias, m.running_mean, m.running_var, float(m.eps), momentum, act, slope)
+                i += 1
+            else:
+                x = _BNAct.apply(x, m.weight, m.bias, m.running_mean, m.running_var, float(m.eps), momentum, act, slope)
             if m.num_batches_tracked is not None:
                 m.num_batches_tracked += 1
             i += 1
@@ -265,6 +305,14 @@ class FlatAdam:
         self.v = torch.zeros_like(self.grad)
         self.t = 0
         self.step_dev = torch.zeros(1, device=dev, dtype=torch.int32)       # completed steps (graph-replayable counter)
+        # the parameters become views of the flat buffer: the fused Adam kernel updates them in place (no copy back)
+        self.views = all(p.dtype == torch.float32 for p in self.params)
+        if self.views:
+            o = 0
+            for p in self.params:
+                k = p.numel()
+                p.data = self.flat[o:o + k].view_as(p)
+                o += k
 
     def zero_grad(self, set_to_none=True):
         for p in self.params:
@@ -274,6 +322,9 @@ class FlatAdam:
                 p.grad.zero_()
 
     def gather_grads(self):
+        if all(p.grad is not None for p in self.params):
+            torch.cat([p.grad.reshape(-1) for p in self.params], out=self.grad)       # one launch
+            return self.grad
         o = 0
         for p in self.params:
             n = p.numel()
@@ -291,6 +342,8 @@ class FlatAdam:
         _lib.check(lib.wmk_adam_step_f32(_lib.ptr(self.flat), _lib.ptr(self.grad), _lib.ptr(self.m), _lib.ptr(self.v),
                                          self.flat.numel(), self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
                                          self.t, grad_scale, int(self.decoupled), _lib.ptr(self.step_dev), _lib.stream_ptr()))
+        if self.views:
+            return
         o = 0
         with torch.no_grad():
             for p in self.params:

@@ -164,6 +164,127 @@ bn_act_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ y
   reinterpret_cast<float4*>(dx)[i] = o;
 }
 
+
+// ---- BatchNorm2d (training) + activation + MaxPool2d(2,2) fused (ModelA's `Conv - BN - LeakyReLU - MaxPool` groups,
+// uformerWM/model.py:3005-3013,3028-3037).  Forward: one pass writes the activation y (kept for the backward pass) AND
+// its 2x2 maxima yp, so the pooling kernel's re-read of y disappears.  Backward: the gradient arrives at pooled
+// resolution; the full-resolution gradient of the pooling layer (dyp routed to the first maximum of each window, in
+// PyTorch's scan order) is never materialised - both passes recompute the argmax from y.
+// A thread owns a 2-row x 4-column patch (two 16-byte loads per tensor) = two pooling windows.
+struct Patch { float4 a, b; };       // rows 2r and 2r + 1
+__device__ __forceinline__ int first_max4(float v0, float v1, float v2, float v3) {
+  int k = 0;
+  float m = v0;
+  if (v1 > m) { m = v1; k = 1; }
+  if (v2 > m) { m = v2; k = 2; }
+  if (v3 > m) { k = 3; }
+  return k;
+}
+
+__global__ void __launch_bounds__(256)
+bn_act_pool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, float* __restrict__ yp,
+                       const float* __restrict__ mean_rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+                       size_t units, int C, int H, int W, int act, float slope) {
+  const size_t u = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= units) return;
+  const int w4 = W >> 2, h2 = H >> 1;
+  const int c4 = (int)(u % w4), r2 = (int)((u / w4) % h2);
+  const size_t plane = u / ((size_t)w4 * h2);
+  const int c = (int)(plane % C);
+  const float mean = mean_rstd[2 * c], rstd = mean_rstd[2 * c + 1], g = gamma[c], be = beta[c];
+  const size_t o = (plane * H + 2 * r2) * W + 4 * c4;
+  float4 a = *reinterpret_cast<const float4*>(x + o), b = *reinterpret_cast<const float4*>(x + o + W);
+  a.x = act_fwd(fmaf(g, (a.x - mean) * rstd, be), act, slope); a.y = act_fwd(fmaf(g, (a.y - mean) * rstd, be), act, slope);
+  a.z = act_fwd(fmaf(g, (a.z - mean) * rstd, be), act, slope); a.w = act_fwd(fmaf(g, (a.w - mean) * rstd, be), act, slope);
+  b.x = act_fwd(fmaf(g, (b.x - mean) * rstd, be), act, slope); b.y = act_fwd(fmaf(g, (b.y - mean) * rstd, be), act, slope);
+  b.z = act_fwd(fmaf(g, (b.z - mean) * rstd, be), act, slope); b.w = act_fwd(fmaf(g, (b.w - mean) * rstd, be), act, slope);
+  *reinterpret_cast<float4*>(y + o) = a;
+  *reinterpret_cast<float4*>(y + o + W) = b;
+  float2 m;
+  m.x = fmaxf(fmaxf(a.x, a.y), fmaxf(b.x, b.y));
+  m.y = fmaxf(fmaxf(a.z, a.w), fmaxf(b.z, b.w));
+  *reinterpret_cast<float2*>(yp + (plane * h2 + r2) * (size_t)(W >> 1) + 2 * c4) = m;
+}
+
+// gradient dz = dy * act'(y) of one patch from the pooled gradient (non-zero at the two window maxima only)
+__device__ __forceinline__ void pooled_dz(const Patch& yv, float2 gp, int act, float slope, float dz[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) dz[i] = 0.f;
+  const float y0[4] = {yv.a.x, yv.a.y, yv.b.x, yv.b.y}, y1[4] = {yv.a.z, yv.a.w, yv.b.z, yv.b.w};
+  const int k0 = first_max4(y0[0], y0[1], y0[2], y0[3]), k1 = first_max4(y1[0], y1[1], y1[2], y1[3]);
+  // patch order: 0..3 = row a (x, y, z, w), 4..7 = row b
+  const int p0 = (k0 & 1) + ((k0 >> 1) << 2), p1 = 2 + (k1 & 1) + ((k1 >> 1) << 2);
+  const float g0 = gp.x * act_grad_from_out(y0[k0], act, slope), g1 = gp.y * act_grad_from_out(y1[k1], act, slope);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) dz[i] = i == p0 ? g0 : (i == p1 ? g1 : 0.f);
+}
+
+__global__ void __launch_bounds__(256)
+bn_act_pool_bwd_reduce_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ dyp,
+                              const float* __restrict__ mean_rstd, int B, int C, int H, int W, int act, float slope,
+                              double* __restrict__ sums) {
+  const int c = blockIdx.y;
+  const int w4 = W >> 2, h2 = H >> 1;
+  const size_t per_img = (size_t)w4 * h2, n = (size_t)B * per_img;
+  const float mean = mean_rstd[2 * c], rstd = mean_rstd[2 * c + 1];
+  float s1 = 0.f, s2 = 0.f;
+  double d1 = 0.0, d2 = 0.0;
+  int cnt = 0;
+  for (size_t u = (size_t)blockIdx.x * blockDim.x + threadIdx.x; u < n; u += (size_t)gridDim.x * blockDim.x) {
+    const size_t b = u / per_img;
+    const int rem = (int)(u - b * per_img), r2 = rem / w4, c4 = rem - r2 * w4;
+    const size_t plane = b * C + c;
+    const size_t o = (plane * H + 2 * r2) * W + 4 * c4;
+    Patch xv, yv;
+    xv.a = *reinterpret_cast<const float4*>(x + o); xv.b = *reinterpret_cast<const float4*>(x + o + W);
+    yv.a = *reinterpret_cast<const float4*>(y + o); yv.b = *reinterpret_cast<const float4*>(y + o + W);
+    const float2 gp = *reinterpret_cast<const float2*>(dyp + (plane * h2 + r2) * (size_t)(W >> 1) + 2 * c4);
+    float dz[8];
+    pooled_dz(yv, gp, act, slope, dz);
+    const float xs[8] = {xv.a.x, xv.a.y, xv.a.z, xv.a.w, xv.b.x, xv.b.y, xv.b.z, xv.b.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      s1 += dz[i];
+      s2 = fmaf(dz[i], (xs[i] - mean) * rstd, s2);
+    }
+    if (++cnt == 128) { d1 += s1; d2 += s2; s1 = s2 = 0.f; cnt = 0; }
+  }
+  d1 += s1; d2 += s2;
+  block_sum2_atomic(d1, d2, sums + 2 * c);
+}
+
+__global__ void __launch_bounds__(256)
+bn_act_pool_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ dyp,
+                             float* __restrict__ dx, const float* __restrict__ mean_rstd, const float* __restrict__ gamma,
+                             const double* __restrict__ sums, size_t units, int C, int H, int W, double n, int act, float slope,
+                             float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const size_t u = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (u < (size_t)C) {
+    dgamma[u] = (float)sums[2 * u + 1];
+    dbeta[u] = (float)sums[2 * u];
+  }
+  if (u >= units) return;
+  const int w4 = W >> 2, h2 = H >> 1;
+  const int c4 = (int)(u % w4), r2 = (int)((u / w4) % h2);
+  const size_t plane = u / ((size_t)w4 * h2);
+  const int c = (int)(plane % C);
+  const float mean = mean_rstd[2 * c], rstd = mean_rstd[2 * c + 1];
+  const float m1 = (float)(sums[2 * c] / n), m2 = (float)(sums[2 * c + 1] / n), gr = gamma[c] * rstd;
+  const size_t o = (plane * H + 2 * r2) * W + 4 * c4;
+  Patch xv, yv;
+  xv.a = *reinterpret_cast<const float4*>(x + o); xv.b = *reinterpret_cast<const float4*>(x + o + W);
+  yv.a = *reinterpret_cast<const float4*>(y + o); yv.b = *reinterpret_cast<const float4*>(y + o + W);
+  const float2 gp = *reinterpret_cast<const float2*>(dyp + (plane * h2 + r2) * (size_t)(W >> 1) + 2 * c4);
+  float dz[8];
+  pooled_dz(yv, gp, act, slope, dz);
+  const float xs[8] = {xv.a.x, xv.a.y, xv.a.z, xv.a.w, xv.b.x, xv.b.y, xv.b.z, xv.b.w};
+  float r[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r[i] = gr * (dz[i] - m1 - (xs[i] - mean) * rstd * m2);
+  *reinterpret_cast<float4*>(dx + o) = make_float4(r[0], r[1], r[2], r[3]);
+  *reinterpret_cast<float4*>(dx + o + W) = make_float4(r[4], r[5], r[6], r[7]);
+}
+
 // MaxPool2d(2,2) backward: the gradient goes to the first maximum of each window (PyTorch's scan order)
 __global__ void __launch_bounds__(256)
 maxpool2x2_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, size_t planes,
@@ -703,6 +824,54 @@ extern "C" int wmk_bn_train_bwd_f32(const float* x, const float* y, const float*
   bn_act_bwd_apply_kernel<<<grid_for(total / 4), 256, 0, st>>>(x, y, dy, dx, mean_rstd, gamma, scratch, total / 4, C, HW,
                                                            (double)per_c, act, slope, dgamma, dbeta);
   WMK_CHECK_LAUNCH("bn_act_bwd_apply_kernel");
+  return 0;
+}
+
+extern "C" int wmk_bn_pool_train_fwd_f32(const float* x, float* y, float* y_pooled, const float* gamma, const float* beta,
+                                         float* running_mean, float* running_var, float* mean_rstd, double* scratch, int B,
+                                         int C, int H, int W, float eps, float momentum, int act, float slope, void* stream) {
+  WMK_REQUIRE(x && y && y_pooled && gamma && beta && mean_rstd && scratch && B > 0 && C > 0 && H >= 2 && W >= 4 && H % 2 == 0 &&
+                  W % 4 == 0 && act >= 0 && act <= 3 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0 &&
+                  ((uintptr_t)y_pooled & 7) == 0,
+              "bn_pool_train_fwd: bad arguments (H even, W a multiple of 4, buffers 16-byte aligned)");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int HW = H * W;
+  const size_t total = (size_t)B * C * HW;
+  ProfScope prof(FAM_SMALL, 13.0 * total, st);
+  WMK_CHECK_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * C, st));
+  const size_t per_c = (size_t)B * HW;
+  int chunks = (int)((per_c / 4 + 256 * 8 - 1) / (256 * 8));
+  const int max_chunks = (148 * 8 * 4 + C - 1) / C;
+  if (chunks > max_chunks) chunks = max_chunks;
+  bn_stats_kernel<<<dim3(chunks, C), 256, 0, st>>>(x, B, C, HW, scratch);
+  WMK_CHECK_LAUNCH("bn_stats_kernel");
+  bn_finalize_kernel<<<cdiv(C, 64), 64, 0, st>>>(scratch, C, (double)per_c, eps, momentum, mean_rstd, running_mean, running_var);
+  WMK_CHECK_LAUNCH("bn_finalize_kernel");
+  bn_act_pool_fwd_kernel<<<grid_for(total / 8), 256, 0, st>>>(x, y, y_pooled, mean_rstd, gamma, beta, total / 8, C, H, W, act, slope);
+  WMK_CHECK_LAUNCH("bn_act_pool_fwd_kernel");
+  return 0;
+}
+
+extern "C" int wmk_bn_pool_train_bwd_f32(const float* x, const float* y, const float* dy_pooled, float* dx, const float* gamma,
+                                         const float* mean_rstd, float* dgamma, float* dbeta, double* scratch, int B, int C,
+                                         int H, int W, int act, float slope, void* stream) {
+  WMK_REQUIRE(x && y && dy_pooled && dx && gamma && mean_rstd && dgamma && dbeta && scratch && B > 0 && C > 0 && H >= 2 && W >= 4 &&
+                  H % 2 == 0 && W % 4 == 0 && (size_t)C <= (size_t)B * C * H * W / 8 && ((uintptr_t)x & 15) == 0 &&
+                  ((uintptr_t)y & 15) == 0 && ((uintptr_t)dx & 15) == 0 && ((uintptr_t)dy_pooled & 7) == 0,
+              "bn_pool_train_bwd: bad arguments (H even, W a multiple of 4, buffers 16-byte aligned)");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t total = (size_t)B * C * H * W;
+  ProfScope prof(FAM_SMALL, 22.5 * total, st);
+  WMK_CHECK_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * C, st));
+  const size_t units_c = (size_t)B * H * W / 8;
+  int chunks = (int)((units_c + 256 * 4 - 1) / (256 * 4));
+  const int max_chunks = (148 * 8 * 4 + C - 1) / C;
+  if (chunks > max_chunks) chunks = max_chunks;
+  bn_act_pool_bwd_reduce_kernel<<<dim3(chunks, C), 256, 0, st>>>(x, y, dy_pooled, mean_rstd, B, C, H, W, act, slope, scratch);
+  WMK_CHECK_LAUNCH("bn_act_pool_bwd_reduce_kernel");
+  bn_act_pool_bwd_apply_kernel<<<grid_for(total / 8), 256, 0, st>>>(x, y, dy_pooled, dx, mean_rstd, gamma, scratch, total / 8, C, H, W,
+                                                                    (double)B * H * W, act, slope, dgamma, dbeta);
+  WMK_CHECK_LAUNCH("bn_act_pool_bwd_apply_kernel");
   return 0;
 }
 

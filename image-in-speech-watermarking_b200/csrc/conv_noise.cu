@@ -38,7 +38,7 @@ template <int CIB, int COB, int PX>
 __global__ void __launch_bounds__(256)
 conv3x3_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ w,
                const float* __restrict__ bias, const float* __restrict__ scale, const float* __restrict__ shift,
-               int Cin, int Cout, int H, int W, int co_off, int Ctot, int act, float slope) {
+               int Cin, int Cout, int H, int W, int co_off, int Ctot, int act, float slope, int wflip) {
   constexpr int TH = 8 * PX;
   __shared__ __align__(16) float tile[CIB][TH + 2][CXP];
   __shared__ __align__(16) float ws[CIB][9][COB];
@@ -83,7 +83,10 @@ conv3x3_kernel(const float* __restrict__ x, float* __restrict__ y, const float* 
     for (int e = threadIdx.x; e < CIB * 9 * COB; e += 256) {
       const int ci = e / (9 * COB), t = (e / COB) % 9, j = e % COB;
       float v = 0.f;
-      if (c0 + ci < Cin && co0 + j < Cout) v = w[((size_t)(co0 + j) * Cin + c0 + ci) * 9 + t];
+      // wflip (data gradient): w is the FORWARD layer's [Cin here = its Cout][Cout here = its Cin][3][3] tensor, read
+      // transposed with the taps reversed - correlation with the flipped kernel - so no flipped copy is ever made
+      if (c0 + ci < Cin && co0 + j < Cout)
+        v = wflip ? w[((size_t)(c0 + ci) * Cout + co0 + j) * 9 + (8 - t)] : w[((size_t)(co0 + j) * Cin + c0 + ci) * 9 + t];
       ws[ci][t][j] = v;
     }
     __syncthreads();
@@ -477,9 +480,9 @@ conv3x3_nhwc_to1_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__
 
 using namespace wmk;
 
-extern "C" int wmk_conv3x3_f32(const float* x, float* y, const float* w, const float* bias, const float* scale,
-                               const float* shift, int B, int Cin, int Cout, int H, int W, int out_ch_offset,
-                               int out_ch_total, int act, float slope, void* stream) {
+static int conv3x3_launch(const float* x, float* y, const float* w, const float* bias, const float* scale,
+                          const float* shift, int B, int Cin, int Cout, int H, int W, int out_ch_offset,
+                          int out_ch_total, int act, float slope, int wflip, void* stream) {
   WMK_REQUIRE(x && y && w && B > 0 && Cin > 0 && Cout > 0 && H > 0 && W > 0 && out_ch_offset >= 0 &&
                   out_ch_offset + Cout <= out_ch_total && act >= 0 && act <= 3 && (!scale == !shift) && B <= 65535,
               "conv3x3: bad arguments");
@@ -491,9 +494,9 @@ extern "C" int wmk_conv3x3_f32(const float* x, float* y, const float* w, const f
   dim3 grid(cdiv(H, 8 * px) * cdiv(W, CTW), cdiv(Cout, cob), B);
 #define WMK_CONV_LAUNCH(CIB, COB)                                                                                                   \
   do {                                                                                                                              \
-    if (px == 4) conv3x3_kernel<CIB, COB, 4><<<grid, 256, 0, st>>>(x, y, w, bias, scale, shift, Cin, Cout, H, W, out_ch_offset, out_ch_total, act, slope); \
-    else if (px == 2) conv3x3_kernel<CIB, COB, 2><<<grid, 256, 0, st>>>(x, y, w, bias, scale, shift, Cin, Cout, H, W, out_ch_offset, out_ch_total, act, slope); \
-    else conv3x3_kernel<CIB, COB, 1><<<grid, 256, 0, st>>>(x, y, w, bias, scale, shift, Cin, Cout, H, W, out_ch_offset, out_ch_total, act, slope); \
+    if (px == 4) conv3x3_kernel<CIB, COB, 4><<<grid, 256, 0, st>>>(x, y, w, bias, scale, shift, Cin, Cout, H, W, out_ch_offset, out_ch_total, act, slope, wflip); \
+    else if (px == 2) conv3x3_kernel<CIB, COB, 2><<<grid, 256, 0, st>>>(x, y, w, bias, scale, shift, Cin, Cout, H, W, out_ch_offset, out_ch_total, act, slope, wflip); \
+    else conv3x3_kernel<CIB, COB, 1><<<grid, 256, 0, st>>>(x, y, w, bias, scale, shift, Cin, Cout, H, W, out_ch_offset, out_ch_total, act, slope, wflip); \
   } while (0)
   if (Cin <= 2 && Cout <= 2) WMK_CONV_LAUNCH(2, 2);
   else if (Cin <= 2) WMK_CONV_LAUNCH(2, 16);
@@ -502,6 +505,19 @@ extern "C" int wmk_conv3x3_f32(const float* x, float* y, const float* w, const f
 #undef WMK_CONV_LAUNCH
   WMK_CHECK_LAUNCH("conv3x3_kernel");
   return 0;
+}
+
+extern "C" int wmk_conv3x3_f32(const float* x, float* y, const float* w, const float* bias, const float* scale,
+                               const float* shift, int B, int Cin, int Cout, int H, int W, int out_ch_offset,
+                               int out_ch_total, int act, float slope, void* stream) {
+  return conv3x3_launch(x, y, w, bias, scale, shift, B, Cin, Cout, H, W, out_ch_offset, out_ch_total, act, slope, 0, stream);
+}
+
+// data gradient of Conv2d(Cin, Cout, 3, padding=1): dx [B][Cin][H][W] = correlation of dy [B][Cout][H][W] with the flipped,
+// transposed forward weights w [Cout][Cin][3][3] (read in place)
+extern "C" int wmk_conv3x3_dgrad_f32(const float* dy, const float* w, float* dx, int B, int Cin, int Cout, int H, int W,
+                                     void* stream) {
+  return conv3x3_launch(dy, dx, w, nullptr, nullptr, nullptr, B, Cout, Cin, H, W, 0, Cin, 0, 0.f, 1, stream);
 }
 
 extern "C" int wmk_convT2x2_f32(const float* x, float* y, const float* w, const float* bias, const float* scale,

@@ -229,8 +229,11 @@ int wmk_conv3x3_nhwc_to1_f32(const void* x, float* y, const float* wt, float bia
 
 /* ------------------------------------------------------------------------------------------
  * Training-mode kernels of ModelA (step: uformerWM/train_modelA.py:402-500, BASELINE config 5).
- * The data gradient of Conv2d(3x3) is wmk_conv3x3_f32 with the flipped / transposed weights.
  * ------------------------------------------------------------------------------------------ */
+/* data gradient of Conv2d(Cin, Cout, 3, padding=1): dx [B][Cin][H][W] from dy [B][Cout][H][W] and the FORWARD weights
+ * w [Cout][Cin][3][3] (the forward kernel reads them transposed with reversed taps: no flipped copy) */
+int wmk_conv3x3_dgrad_f32(const float* dy, const float* w, float* dx, int B, int Cin, int Cout, int H, int W,
+                          void* stream);
 /* nn.BatchNorm2d in training mode + activation: batch statistics over (B,H,W) per channel,
  * y = act(gamma * xhat + beta); running_mean / running_var (may be NULL) are updated with
  * `momentum` and the unbiased variance; mean_rstd [C][2] is saved for the backward pass;
@@ -244,6 +247,17 @@ int wmk_bn_train_fwd_f32(const float* x, float* y, const float* gamma, const flo
 int wmk_bn_train_bwd_f32(const float* x, const float* y, const float* dy, float* dx, const float* gamma,
                          const float* mean_rstd, float* dgamma, float* dbeta, double* scratch, int B,
                          int C, int HW, int act, float slope, void* stream);
+/* BatchNorm2d (training) + activation + MaxPool2d(2,2) in one pass (the Conv-BN-LeakyReLU-MaxPool groups of ModelA,
+ * uformerWM/model.py:3005-3013,3028-3037): y [B][C][H][W] is kept for the backward pass, y_pooled [B][C][H/2][W/2] goes
+ * on; the backward takes the gradient at POOLED resolution and routes it to the first maximum of each window (PyTorch's
+ * scan order) inside the BatchNorm backward passes - the pooling layer's full-resolution gradient is never written. */
+int wmk_bn_pool_train_fwd_f32(const float* x, float* y, float* y_pooled, const float* gamma, const float* beta,
+                              float* running_mean, float* running_var, float* mean_rstd, double* scratch,
+                              int B, int C, int H, int W, float eps, float momentum, int act, float slope,
+                              void* stream);
+int wmk_bn_pool_train_bwd_f32(const float* x, const float* y, const float* dy_pooled, float* dx,
+                              const float* gamma, const float* mean_rstd, float* dgamma, float* dbeta,
+                              double* scratch, int B, int C, int H, int W, int act, float slope, void* stream);
 /* MaxPool2d(2,2) backward: x [planes][H][W] is the pooled layer's input, dy [planes][H/2][W/2] */
 int wmk_maxpool2x2_bwd_f32(const float* x, const float* dy, float* dx, int planes, int H, int W,
                            void* stream);

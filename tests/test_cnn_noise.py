@@ -297,3 +297,48 @@ def test_hidden_decoder_tensor_core_path_matches_reference_golden(golden):
     assert _maxrel(out.cpu().numpy(), ref) < 5e-2
     big = x.repeat(40, 1, 1, 1)                                  # 80 clips: several waves of persistent tiles
     assert torch.equal(d(big)[:2], out)
+
+
+@pytest.mark.gpu
+def test_fused_bn_pool_and_dgrad_equal_their_compositions():
+    """`wmk_bn_pool_train_fwd/bwd_f32` == BatchNorm(train)+LeakyReLU followed by MaxPool2d(2,2) (forward outputs, running
+    statistics, dx, dgamma, dbeta; the pooling gradient routed to PyTorch's first maximum) and `wmk_conv3x3_dgrad_f32`
+    == the forward kernel run on flipped / transposed weights == torch's conv data gradient."""
+    from image_in_speech_watermarking_b200 import cnn_train as CT, _lib
+    from image_in_speech_watermarking_b200.cnn import ACT_LEAKY
+    gen = torch.Generator().manual_seed(5)
+    B, C, H, W = 3, 5, 12, 16
+    x = torch.randn(B, C, H, W, generator=gen).cuda()
+    x[0, 0, 0, 0:2] = 1.5                              # an exact tie inside one pooling window
+    gamma, beta = torch.randn(C, generator=gen).cuda().requires_grad_(), torch.randn(C, generator=gen).cuda().requires_grad_()
+    outs = []
+    for fused in (True, False):
+        xi = x.clone().requires_grad_()
+        rm, rv = torch.zeros(C).cuda(), torch.ones(C).cuda()
+        if fused:
+            yp = CT._BNActPool.apply(xi, gamma, beta, rm, rv, 1e-5, 0.1, ACT_LEAKY, 0.2)
+        else:
+            yp = CT._MaxPool.apply(CT._BNAct.apply(xi, gamma, beta, rm, rv, 1e-5, 0.1, ACT_LEAKY, 0.2))
+        gy = torch.randn(yp.shape, generator=torch.Generator().manual_seed(6)).cuda()
+        gx, gg, gb = torch.autograd.grad(yp, (xi, gamma, beta), gy)
+        outs.append((yp, rm, rv, gx, gg, gb))
+    for a, b in zip(*outs):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-6)
+    # torch reference of the same group
+    xi = x.clone().requires_grad_()
+    bn = torch.nn.BatchNorm2d(C).cuda().train()
+    with torch.no_grad():
+        bn.weight.copy_(gamma)
+        bn.bias.copy_(beta)
+    yp = torch.nn.functional.max_pool2d(torch.nn.functional.leaky_relu(bn(xi), 0.2), 2, 2)
+    gx = torch.autograd.grad(yp, xi, gy)[0]
+    assert torch.allclose(outs[0][0], yp, rtol=1e-4, atol=1e-5) and torch.allclose(outs[0][3], gx, rtol=1e-3, atol=1e-5)
+    # data gradient of the 3x3 convolution, weights read in place
+    lib = _lib.load()
+    for Cin, Cout, Hh in ((2, 16, 40), (16, 32, 32), (64, 1, 16), (5, 7, 20)):
+        w = torch.randn(Cout, Cin, 3, 3, generator=gen).cuda()
+        dy = torch.randn(2, Cout, Hh, Hh + 4, generator=gen).cuda()
+        dx = torch.empty(2, Cin, Hh, Hh + 4, device="cuda")
+        _lib.check(lib.wmk_conv3x3_dgrad_f32(_lib.ptr(dy), _lib.ptr(w), _lib.ptr(dx), 2, Cin, Cout, Hh, Hh + 4, _lib.stream_ptr()))
+        ref = torch.nn.grad.conv2d_input(dx.shape, w.double().cpu(), dy.double().cpu(), padding=1)     # cuDNN would use TF32
+        assert torch.allclose(dx.cpu().double(), ref, rtol=1e-4, atol=1e-4), (Cin, Cout)
