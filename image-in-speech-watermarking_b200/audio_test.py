@@ -276,6 +276,98 @@ def embed_attack_extract(waves, messages, model, attack="closed_loop", draws=Non
     return out
 
 
+def embed_attack_extract_ragged(waves, messages, model, attack="closed_loop", draws=None, seed=None, audio_scale='0',
+                                data_min=None, data_max=None):
+    """The hot path for utterances of DIFFERENT lengths (a real corpus: the reference loops over LibriSpeech utterances one
+    at a time, `uformerWM/evaluate.py:372-374`).  waves: list of B 1-D CUDA waveforms; messages (B or 1, 1, 32, 32) or
+    (B, K, 1, 32, 32) tiles.  Every utterance keeps its own length in the front end, the attack and the statistics
+    (utterances of equal length share those launches), while the two model passes - the embedder over ALL clean clips,
+    the extractor over all clean + attacked clips - run ONCE over the whole corpus, so the tensor-core kernels see
+    one large batch.  Per utterance identical to `embed_attack_extract` on that utterance alone.
+    Returns {"recon", "att", "wm", "wm_att", "logits", "logits_att": lists of B tensors; "stats" (B, 7) float64 in the
+    order of `waves`; "vec": the additive 8-vector; "n_clips", "n_clips_att": lists}.  Uformer model only."""
+    B = len(waves)
+    if B == 0:
+        raise ValueError("empty batch")
+    dev = waves[0].device
+    tiled = messages.dim() == 5
+    K = messages.shape[1] if tiled else 1
+    msgs = (messages.float().reshape(-1, 1, 32, 32) if tiled else messages.float().reshape(-1, 1, 32, 32)).contiguous()
+    n_img = msgs.shape[0] // K
+    if n_img not in (1, B):
+        raise ValueError("%d images for %d utterances" % (n_img, B))
+    sc, sh = scale_params(audio_scale, data_min, data_max)
+    groups = {}
+    for i, w in enumerate(waves):
+        if w.dim() != 1 or not w.is_cuda:
+            raise ValueError("waves must be 1-D CUDA tensors")
+        groups.setdefault(int(w.shape[0]), []).append(i)
+    G = []
+    n_clean = n_att_max = 0
+    for L, idx in groups.items():
+        T = FE.num_frames(L)
+        g = {"L": L, "idx": idx, "T": T, "nc": T // 128 + 1, "nc_att_max": (T + 126) // 128, "off": n_clean}
+        n_clean += len(idx) * g["nc"]
+        n_att_max += len(idx) * g["nc_att_max"]
+        G.append(g)
+    ext_in = torch.empty((n_clean + n_att_max, 2, 128, 128), device=dev, dtype=torch.float32)
+    x_all = torch.empty((n_clean, 2, 128, 128), device=dev, dtype=torch.float32)
+    img_of_clip = []
+    for g in G:
+        wv = torch.stack([waves[i].float() for i in g["idx"]]).contiguous()
+        g["waves"] = wv
+        view = x_all[g["off"]:g["off"] + len(g["idx"]) * g["nc"]]
+        FE.stft_clips(wv, g["nc"], out=view)
+        if not (sc == 1.0 and sh == 0.0):
+            affine(view, sc, sh, out=view)
+        for u in g["idx"]:
+            base = 0 if n_img == 1 else u * K
+            img_of_clip.extend(base + (j % K) for j in range(g["nc"]))
+    per_clip = msgs[torch.tensor(img_of_clip, device=dev)].contiguous()            # (n_clean, 1, 32, 32): 4 KB per clip
+    o = model.run(x_all, per_clip, want=("stft_new",), y_out=ext_in[:n_clean])    # ONE embedder pass over every clip
+    audio_all = affine(o["stft_new"], 1.0 / sc, -sh / sc)
+    att_off = n_clean
+    for gi, g in enumerate(G):
+        Bg, nc = len(g["idx"]), g["nc"]
+        clips = audio_all[g["off"]:g["off"] + Bg * nc].reshape(Bg, nc, 2, 128, 128)
+        g["recon"] = FE.istft_clips(clips, g["T"], g["L"])
+        g["att"] = AT.apply_attack(g["recon"], attack, draws, None if seed is None else seed + gi)
+        Ta = FE.num_frames(g["att"].shape[1])
+        g["nc_att"] = (Ta + 126) // 128
+        if g["nc_att"] > g["nc_att_max"] or max(g["nc_att"], (Ta + 127) // 128) != g["nc_att"]:
+            raise ValueError("attack %r changed the clip count beyond the reserved buffer" % (attack,))
+        tail = ext_in[att_off:att_off + Bg * g["nc_att"]]
+        FE.stft_clips(g["att"], g["nc_att"], out=tail)
+        if not (sc == 1.0 and sh == 0.0):
+            affine(tail, sc, sh, out=tail)
+        g["att_off"] = att_off
+        att_off += Bg * g["nc_att"]
+    wm_all, lg_all = model.wm_decode(ext_in[:att_off], return_logits=True)        # ONE extractor pass: clean + attacked clips
+    stats = torch.empty((B, 7), device=dev, dtype=torch.float64)
+    vec = torch.zeros(8, device=dev, dtype=torch.float64)
+    out = {k: [None] * B for k in ("recon", "att", "wm", "wm_att", "logits", "logits_att", "n_clips", "n_clips_att")}
+    for g in G:
+        Bg, nc, nca = len(g["idx"]), g["nc"], g["nc_att"]
+        idx_t = torch.tensor(g["idx"], device=dev)
+        m_g = msgs if n_img == 1 else msgs.reshape(B, K, 1, 32, 32)[idx_t].reshape(Bg * K, 1, 32, 32).contiguous()
+        cpu_c, cpu_a = (0x7fffffff, 0x7fffffff) if (n_img == 1 and Bg > 1) else (nc, nca)
+        wm_c, lg_c = wm_all[g["off"]:g["off"] + Bg * nc], lg_all[g["off"]:g["off"] + Bg * nc]
+        wm_a, lg_a = wm_all[g["att_off"]:g["att_off"] + Bg * nca], lg_all[g["att_off"]:g["att_off"] + Bg * nca]
+        st_att, st_rec = EV.wave_stats(g["waves"], g["att"]), EV.wave_stats(g["waves"], g["recon"])
+        ws_clean = EV.wm_stats_mapped(wm_c, nc - 1, nc, m_g, cpu_c, K, Bg)           # last clean clip only: quirk B-8
+        ws_att = EV.wm_stats_mapped(wm_a, 0, 1, m_g, cpu_a, K, Bg * nca)
+        st, v = EV.stats_finalize(st_att, st_rec, ws_clean, ws_att, nca)
+        stats[idx_t] = st
+        vec += v
+        for k, i in enumerate(g["idx"]):
+            out["recon"][i], out["att"][i] = g["recon"][k], g["att"][k]
+            out["wm"][i], out["logits"][i] = wm_c[k * nc:(k + 1) * nc], lg_c[k * nc:(k + 1) * nc]
+            out["wm_att"][i], out["logits_att"][i] = wm_a[k * nca:(k + 1) * nca], lg_a[k * nca:(k + 1) * nca]
+            out["n_clips"][i], out["n_clips_att"][i] = nc, nca
+    out["stats"], out["vec"] = stats, vec
+    return out
+
+
 class PipelinedDriver:
     """Serving loop around `embed_attack_extract` for HOST batches (pinned waveforms / images in; attacked audio, recovered
     images and the statistics vector out to pinned host buffers), three batches in flight: while batch i computes on the

@@ -155,30 +155,32 @@ __device__ __forceinline__ float gelu_fast(float x) {
   return 0.5f * x * (1.0f + copysignf(erf_abs, x));
 }
 
-// The same erf form for PAIRS on the packed fp32x2 pipe with the approximate MUFU units (rcp.approx 1 ulp, ex2.approx
-// 2 ulp: both far below the 1.5e-7 of the formula): 12 packed FMA-pipe instructions + 4 MUFU + 4 logic ops per pair,
-// about half the issue slots of two gelu_fast calls.  Used by the precise extractor (GELU error must stay well under
-// the 2^-11 of the fp16 tensors it feeds, and must not be systematic like the tanh form's 5e-5).
+// Exact-class GELU for PAIRS on the packed fp32x2 pipe: x * Phi(x) with Phi(x) = 1 / (1 + 2^(-L(x))), L = log2 of the
+// odds Phi(x) / Phi(-x) - an odd function, fitted here by a degree-13 odd polynomial (weighted minimax on [0, 6] against
+// scipy's log_ndtr, weight = the GELU's sensitivity x Phi (1 - Phi) ln 2: formula error 6.7e-8; monotone beyond the fit
+// range, so large |x| saturate to x and -0 without a clamp).  10 packed FMA-pipe instructions + 2 MUFU.EX2 + 2 MUFU.RCP
+// per pair (ex2.approx 2 ulp, rcp.approx 1 ulp) against 16 + 4 for the Abramowitz-Stegun 7.1.26 erf form this replaces
+// (gelu_fast above keeps that form for single values); measured max |error| in fp32 8e-7 at |x| ~ 5 (the rounding of the
+// result itself), 1.7e-7 for |x| < 1 - the same as the erf form.  Used by the precise extractor (GELU error must stay
+// well under the 2^-11 of the fp16 tensors it feeds, and must not be systematic like the tanh form's 5e-5).
 __device__ __forceinline__ float2 gelu_erf2(float2 x) {
-  const float2 z = __fmul2_rn(make_float2(fabsf(x.x), fabsf(x.y)), make_float2(0.70710678118654752440f, 0.70710678118654752440f));
-  const float2 d = __ffma2_rn(z, make_float2(0.3275911f, 0.3275911f), make_float2(1.0f, 1.0f));
-  float2 t;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.x) : "f"(d.x));
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.y) : "f"(d.y));
-  float2 p = __ffma2_rn(t, make_float2(1.061405429f, 1.061405429f), make_float2(-1.453152027f, -1.453152027f));
-  p = __ffma2_rn(p, t, make_float2(1.421413741f, 1.421413741f));
-  p = __ffma2_rn(p, t, make_float2(-0.284496736f, -0.284496736f));
-  p = __ffma2_rn(p, t, make_float2(0.254829592f, 0.254829592f));
-  const float2 a = __fmul2_rn(__fmul2_rn(z, z), make_float2(-1.4426950408889634f, -1.4426950408889634f));   // -z^2 log2(e)
+  const float2 x2 = __fmul2_rn(x, x);
+  // coefficients of -L(x) / x in x^2 (negated: the exponent below is -L)
+  float2 p = __ffma2_rn(x2, make_float2(-5.209925380000868e-09f, -5.209925380000868e-09f), make_float2(3.850457233056659e-07f, 3.850457233056659e-07f));
+  p = __ffma2_rn(p, x2, make_float2(-1.1452440958237275e-05f, -1.1452440958237275e-05f));
+  p = __ffma2_rn(p, x2, make_float2(1.5938949945848435e-04f, 1.5938949945848435e-04f));
+  p = __ffma2_rn(p, x2, make_float2(9.559268073644489e-05f, 9.559268073644489e-05f));
+  p = __ffma2_rn(p, x2, make_float2(-0.10483857989311218f, -0.10483857989311218f));
+  p = __ffma2_rn(p, x2, make_float2(-2.3022072315216064f, -2.3022072315216064f));
+  const float2 a = __fmul2_rn(p, x);                                       // -L(x)
   float2 e;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(a.x));
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(a.y));
-  const float2 q = __fmul2_rn(__fmul2_rn(p, t), e);                      // 1 - erf(|z|)
-  const float2 h = __fmul2_rn(x, make_float2(0.5f, 0.5f));
-  // gelu = h (1 + sign(x) (1 - q)) = h + |h| (1 - q)
-  const float2 ah = make_float2(fabsf(h.x), fabsf(h.y));
-  const float2 one_minus_q = __ffma2_rn(q, make_float2(-1.0f, -1.0f), make_float2(1.0f, 1.0f));
-  return __ffma2_rn(ah, one_minus_q, h);
+  const float2 d = __fadd2_rn(e, make_float2(1.0f, 1.0f));
+  float2 r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(d.x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(d.y));
+  return __fmul2_rn(x, r);
 }
 
 // GELU for pairs on the packed fp32x2 pipe (sm_100 FFMA2), MUFU-free: erf(z) on [-3,3] by an odd

@@ -127,14 +127,25 @@ def format_result(data_cat, attack, clips_total, mse, wm_loss, wm_loss_att, snr,
 def test(model, messages, waves, data_cat='train', result_path=None, attack=None, audio_scale='0', data_max=None,
          data_min=None, model_name='uformer', draws=None, seed=None, save_audio=False):
     """Batched counterpart of `test()` (`uformerWM/evaluate.py:174-292`): the reference loops over utterances with
-    batch 1, appends python floats to lists and averages them; here all utterances (waves (B,L) CUDA, messages
-    (B or 1,1,32,32)) go through `audio_test.embed_attack_extract` in one pass and only the per-utterance
-    statistics vector leaves the GPU.  Appends the reference's line to `<result_path>/sample_result.txt` (if given)
+    batch 1, appends python floats to lists and averages them; here all utterances (waves (B,L) CUDA - or a LIST of
+    1-D CUDA waveforms of different lengths, `audio_test.embed_attack_extract_ragged` - messages (B or 1,1,32,32)) go
+    through the hot path in one pass and only the per-utterance statistics vector leaves the GPU.  Appends the reference's line to `<result_path>/sample_result.txt` (if given)
     and returns (line, dict of the averaged numbers).  `save_audio` writes the reference's three WAV files per
     utterance - `audio_gen_sample/<cat>/{ori,recon,<attack>}/<i>.wav` (`evaluate.py:240-247`) - as 32-bit float WAV."""
     from . import audio_test as PT
-    r = PT.embed_attack_extract(waves, messages, model, attack or "closed_loop", draws, seed, want_outputs=bool(save_audio),
-                                audio_scale=audio_scale, data_min=data_min, data_max=data_max, model_name=model_name)
+    ragged = isinstance(waves, (list, tuple))          # a corpus of utterances of different lengths (LibriSpeech, TED-LIUM)
+    if ragged:
+        if model_name != 'uformer':
+            raise NotImplementedError("ragged corpora: Uformer model only")
+        r = PT.embed_attack_extract_ragged(list(waves), messages, model, attack or "closed_loop", draws, seed,
+                                           audio_scale=audio_scale, data_min=data_min, data_max=data_max)
+        n_utt = len(waves)
+        clips_total = int(sum(r["n_clips"]))
+    else:
+        r = PT.embed_attack_extract(waves, messages, model, attack or "closed_loop", draws, seed, want_outputs=bool(save_audio),
+                                    audio_scale=audio_scale, data_min=data_min, data_max=data_max, model_name=model_name)
+        n_utt = int(waves.shape[0])
+        clips_total = int(r["n_clips"]) * n_utt
     if save_audio:
         import os
         from . import wavio
@@ -143,13 +154,11 @@ def test(model, messages, waves, data_cat='train', result_path=None, attack=None
         base = os.path.join(result_path, "audio_gen_sample", data_cat)
         for sub, t in (("ori", waves), ("recon", r["recon"]), (attack or "closed_loop", r["att"])):
             os.makedirs(os.path.join(base, sub), exist_ok=True)
-            host = t.detach().float().cpu().numpy()
-            for i in range(host.shape[0]):
-                wavio.write_wav(os.path.join(base, sub, "%d.wav" % i), host[i], 16000)
+            for i in range(n_utt):
+                wavio.write_wav(os.path.join(base, sub, "%d.wav" % i), t[i].detach().float().cpu().numpy(), 16000)
     s = r["stats"].mean(0).cpu().numpy()
-    clips_total = int(r["n_clips"]) * int(waves.shape[0])
     out = {"clips": clips_total, "mse": float(s[1]), "wm_loss": float(s[2]), "wm_loss_att": float(s[3]), "snr": float(s[0]),
-           "ber_clean": float(r["stats"][:, 4].sum() / (1024.0 * waves.shape[0])),
+           "ber_clean": float(r["stats"][:, 4].sum() / (1024.0 * n_utt)),
            "ber_att": float(r["stats"][:, 5].sum() / r["stats"][:, 6].sum())}
     line = format_result(data_cat, attack, clips_total, out["mse"], out["wm_loss"], out["wm_loss_att"], out["snr"])
     if result_path:

@@ -849,3 +849,33 @@ def test_cabi_collectives_single_rank_and_torchrun_world2(tmp_path):
                           "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
                          capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+@pytest.mark.gpu
+def test_ragged_corpus_equals_per_utterance_calls(models, weights):
+    """`embed_attack_extract_ragged` (utterances of different lengths, the two model passes run once over every clip of
+    the corpus) == `embed_attack_extract` on each utterance alone, in the benchmarked precision: waveforms, attacked
+    audio, logits, per-utterance statistics; covers equal lengths sharing launches, T % 128 == 0 (quirk B-6), one image
+    for all, and 2 x 2 tiles; the vector sums to the per-utterance rows."""
+    from image_in_speech_watermarking_b200 import audio_test as PT, sharding as SH
+    m = models("mixed", "stress")
+    lengths = [48000, 30000, 48000, 8040, 20000, 30000]            # 8040 samples: T = 128 frames -> an empty extra clip
+    full = SY.synth_speech_batch(21, len(lengths), 3.0).cuda()
+    waves = [full[i, :L].contiguous() for i, L in enumerate(lengths)]
+    msgs = torch.stack([SY.synth_image_binary(30 + i) for i in range(len(lengths))]).cuda()
+    for attack, mm in (("low_pass", msgs), ("closed_loop", msgs[:1])):
+        r = PT.embed_attack_extract_ragged(waves, mm, m, attack)
+        assert r["n_clips"][3] == 2 and r["n_clips"][0] == 6
+        for i, w in enumerate(waves):
+            one = PT.embed_attack_extract(w[None], mm[i:i + 1] if mm.shape[0] > 1 else mm, m, attack)
+            assert r["recon"][i].shape == w.shape and torch.allclose(r["recon"][i], one["recon"][0], rtol=0, atol=1e-6)
+            assert torch.allclose(r["att"][i], one["att"][0], rtol=0, atol=1e-6)
+            assert torch.allclose(r["logits_att"][i], one["logits_att"][0], rtol=0, atol=2e-5)
+            assert torch.allclose(r["logits"][i], one["logits"][0], rtol=0, atol=2e-5)
+            assert torch.allclose(r["stats"][i], one["stats"][0], rtol=1e-6, atol=1e-9), (attack, i)
+        assert torch.allclose(r["vec"], SH.stats_vector(r["stats"]), rtol=1e-12, atol=0)
+    tiles = torch.stack([PT.tile_image(SY.synth_image_binary(50 + i, 64)[None])[0] for i in range(len(lengths))]).cuda()
+    r = PT.embed_attack_extract_ragged(waves, tiles, m, "low_pass")
+    one = PT.embed_attack_extract(waves[1][None], tiles[1:2], m, "low_pass")
+    assert torch.allclose(r["stats"][1], one["stats"][0], rtol=1e-6, atol=1e-9)
+    assert torch.allclose(r["logits_att"][1], one["logits_att"][0].reshape(-1, 1, 32, 32), rtol=0, atol=2e-5)
