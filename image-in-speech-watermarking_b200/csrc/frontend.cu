@@ -11,12 +11,15 @@
 // every spectrogram value is written / read once, directly in the (2,128,128) clip layout the
 // model consumes, as 128-byte row segments.  Algorithmic traffic: 1276 B per frame.
 #include <math.h>
+#include <stdlib.h>
 #include <mutex>
 
 #include "dft255.cuh"
 #include "uformer_kernels.cuh"
 
 namespace wmk {
+
+namespace tc { int num_sms(); }
 
 namespace {
 
@@ -147,15 +150,19 @@ stft_clips_kernel(const float* __restrict__ wave, int L, int T, float* __restric
   }
 }
 
-// One CTA step reconstructs 28 hops (1764 samples) of the padded overlap-add buffer from 32 frames
-// (4 halo frames recomputed instead of atomics), divides by the overlap count and trims; a CTA walks
-// G consecutive steps and prefetches the next spectrum tile with cp.async.
+// One CTA reconstructs a run of hops of the padded overlap-add buffer in G steps of 32 frames.  A hop needs the four
+// (five) frames before it: the FIRST step of a CTA recomputes 4 halo frames (28 hops out of 32 frames, no atomics), every
+// later step takes them from the CARRY - the time-domain rows of the previous step's last 4 frames, kept in front of
+// the frame buffer - so it turns 32 frames into 32 hops (the halo recompute was 14 % of all frame work at G = 1);
+// the next spectrum tile is prefetched with cp.async.
 //   load : the 256 x 32 spectrum tile -> XS (lane = frame)
 //   B'   : warp = k1 (8 warps): inverse 17-point DFTs        -> ZS[k1][n2][f]
 //   A'   : warp = n2 (17 warps): complex-to-real 15-point inverse DFTs -> FR[f][n] (over XS)
-//   OLA  : each output sample sums the 4-5 frames that cover it
+//   OLA  : each output sample sums the 4-5 frames that cover it (rows -4 .. -1 of FR = the carry)
 constexpr int IFT = FT - 4;
 constexpr int kXsFloats = 2 * BINS * FT;
+constexpr int kCarryFloats = 1024;                 // 4 rows x 255 floats in front of each frame buffer (16-byte multiple)
+constexpr int kIstftBuf = kCarryFloats + kXsFloats;
 
 __device__ __forceinline__ void istft_prefetch(const float* __restrict__ clips_b, int fbase, float* XS, int tid) {
 #pragma unroll
@@ -170,21 +177,25 @@ __device__ __forceinline__ void istft_prefetch(const float* __restrict__ clips_b
 
 __global__ void __launch_bounds__(kFrontThreads, 2)
 istft_clips_kernel(const float* __restrict__ clips, int n_clips, int T, float* __restrict__ wave, int length, int G,
-                   int n_steps) {
+                   int need_hops) {
   extern __shared__ __align__(16) float smem[];
-  float2* ZS = reinterpret_cast<float2*>(smem + 2 * kXsFloats);         // [8][17][32]
+  float2* ZS = reinterpret_cast<float2*>(smem + 2 * kIstftBuf);         // [8][17][32]
   const int b = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float* clips_b = clips + (size_t)b * n_clips * 2 * BINS * 128;
   float* wv = wave + (size_t)b * length;
-  const int step0 = blockIdx.x * G;
-  const int n_it = min(G, n_steps - step0);
+  const int h0 = blockIdx.x * (IFT + FT * (G - 1));                     // first hop of this CTA
+  const int hops_left = need_hops - h0;
+  int n_it = hops_left <= IFT ? 1 : 1 + (hops_left - IFT + FT - 1) / FT;
+  if (n_it > G) n_it = G;
+  auto fbase_of = [&](int it) { return it == 0 ? h0 - 4 : h0 + IFT + FT * (it - 1); };   // first frame the step loads
   auto is_interior = [&](int fb) { return fb >= 0 && fb + FT - 1 <= T - 1; };
   bool prefetched = false;
-  if (is_interior(step0 * IFT - 4)) { istft_prefetch(clips_b, step0 * IFT - 4, smem, tid); prefetched = true; }
+  if (is_interior(fbase_of(0))) { istft_prefetch(clips_b, fbase_of(0), smem + kCarryFloats, tid); prefetched = true; }
   for (int it = 0; it < n_it; ++it) {
-    const int fbase = (step0 + it) * IFT - 4;       // first (halo) frame of this step
-    float* XS = smem + (it & 1) * kXsFloats;        // [256][32], later FR [32][255]
+    const int fbase = fbase_of(it);
+    const int row0 = it == 0 ? 4 : 0, n_hops = FT - row0;               // FR row of the first output hop; hops written
+    float* XS = smem + kCarryFloats + (it & 1) * kIstftBuf;             // [256][32], later FR [32][255]; XS[-1020 .. -1] = carry
     if (prefetched) {
       cp_async_wait_all();
     } else {
@@ -201,10 +212,10 @@ istft_clips_kernel(const float* __restrict__ clips, int n_clips, int T, float* _
       for (int j = 0; j < 15; ++j) dst[j * 17 * FT] = tv ? r[j] : 0.f;
       if (warp == 0) dst[255 * FT] = tv ? r[15] : 0.f;
     }
-    __syncthreads();                                // tile visible; the other buffer (FR of the last step) is free
+    __syncthreads();                                // tile (and carry) visible; the other buffer (FR of the last step) is free
     prefetched = false;
-    if (it + 1 < n_it && is_interior(fbase + IFT)) {
-      istft_prefetch(clips_b, fbase + IFT, smem + ((it + 1) & 1) * kXsFloats, tid);
+    if (it + 1 < n_it && is_interior(fbase_of(it + 1))) {
+      istft_prefetch(clips_b, fbase_of(it + 1), smem + kCarryFloats + ((it + 1) & 1) * kIstftBuf, tid);
       prefetched = true;
     }
     if (warp < 8) dft255::inv_stage_b<ISTFT_SPLIT ? 0 : -1>(XS, c_tab.inv, ZS, warp, lane);
@@ -213,18 +224,23 @@ istft_clips_kernel(const float* __restrict__ clips, int n_clips, int T, float* _
     float* FR = XS;
     dft255::inv_stage_a(ZS, FR, warp, lane);
     __syncthreads();
+    if (it + 1 < n_it) {                            // the next step's carry: rows 28 .. 31 of this step
+      float* cdst = smem + kCarryFloats + ((it + 1) & 1) * kIstftBuf - 4 * NFFT;
+      for (int i = tid; i < 4 * NFFT; i += kFrontThreads) cdst[i] = FR[IFT * NFFT + i];
+    }
+    const int hop0 = fbase + row0;                  // first hop written by this step
     if (is_interior(fbase) && PAD + length >= HOP * (fbase + FT)) {
-      // 8 groups of 63 threads: thread (g, r) owns offset r of hops g, g+8, g+16, (g+24).  Sample p = 63 h' + r
+      // 8 groups of 63 threads: thread (g, r) owns offset r of hops g, g+8, g+16, g+24.  Sample p = 63 h' + r
       // is covered by frames h', h'-1, .., h'-3 (and h'-4 when r <= 2) at offsets r, r+63, ..: rows 192 apart.
       if (tid < 8 * HOP) {
         const int g = tid / HOP, r = tid - g * HOP;
         const bool five = r <= 2;
         const float inv = five ? 0.2f : 0.25f;
-        const float* fr = FR + (g + 4) * NFFT + r;
-        float* o = wv + HOP * (fbase + 4 + g) + r - PAD;
+        const float* fr = FR + (g + row0) * NFFT + r;
+        float* o = wv + HOP * (hop0 + g) + r - PAD;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          if (g + 8 * j < IFT) {
+          if (g + 8 * j < n_hops) {
             const float* q = fr + j * 8 * NFFT;
             float s = (q[0] + q[-192]) + (q[-384] + q[-576]);
             if (five) s += q[-768];
@@ -233,8 +249,8 @@ istft_clips_kernel(const float* __restrict__ clips, int n_clips, int T, float* _
         }
       }
     } else {
-      for (int i = tid; i < HOP * IFT; i += kFrontThreads) {
-        const int p = HOP * (fbase + 4) + i;
+      for (int i = tid; i < HOP * n_hops; i += kFrontThreads) {
+        const int p = HOP * hop0 + i;
         const int jn = p - PAD;
         if (jn < 0 || jn >= length) continue;
         int t_hi = p / HOP;
@@ -293,17 +309,20 @@ int istft_clips(const float* clips, int B, int n_clips, int T, float* wave, int 
   const int total = NFFT + HOP * (T - 1);
   int need = PAD + length;
   if (need < total) need = total;
-  const size_t smem = 2 * kXsFloats * sizeof(float) + dft255::SA_FLOAT2 * sizeof(float2);
+  const size_t smem = 2 * kIstftBuf * sizeof(float) + dft255::SA_FLOAT2 * sizeof(float2);
   static bool attr = false;
   if (!attr) {
     WMK_CHECK_CUDA(cudaFuncSetAttribute(istft_clips_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
   ProfScope prof(FAM_ISTFT, 1276.0 * T * B, st);
-  const int steps = cdiv(need, HOP * IFT);
-  const int G = tiles_per_cta((long long)steps * B);
-  dim3 grid(cdiv(steps, G), B);
-  istft_clips_kernel<<<grid, kFrontThreads, smem, st>>>(clips, n_clips, T, wave, length, G, steps);
+  const int need_hops = cdiv(need, HOP);
+  static const int g_max = getenv("WMK_ISTFT_G") ? atoi(getenv("WMK_ISTFT_G")) : 8;
+  const long long per = (long long)cdiv(need_hops, IFT) * B / (2LL * tc::num_sms() * 4);    // steps per resident CTA slot and wave
+  int G = per >= 8 ? 8 : per >= 4 ? 4 : per >= 2 ? 2 : 1;
+  if (G > g_max) G = g_max;
+  dim3 grid(cdiv(need_hops, IFT + FT * (G - 1)), B);
+  istft_clips_kernel<<<grid, kFrontThreads, smem, st>>>(clips, n_clips, T, wave, length, G, need_hops);
   WMK_CHECK_LAUNCH("istft_clips_kernel");
   return 0;
 }

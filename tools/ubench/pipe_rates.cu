@@ -134,6 +134,84 @@ __global__ void __launch_bounds__(256, 2) k_gelu_h2(const float* in, float* out,
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+
+// 6: scalar FFMA, three register operands
+__global__ void __launch_bounds__(256, 2) k_ffma(const float* in, float* out, int n) {
+  float x[4], w[4], a[8];
+  for (int i = 0; i < 4; ++i) { x[i] = in[threadIdx.x + 32 * i]; w[i] = in[threadIdx.x + 32 * i + 128]; }
+  for (int i = 0; i < 8; ++i) a[i] = 0.f;
+  for (int it = 0; it < n; ++it) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = fmaf(x[(i + r) & 3], w[(i * 3 + r) & 3], a[i]);
+  }
+  float s = 0.f;
+  for (int i = 0; i < 8; ++i) s += a[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// 7 / 8: MUFU.RCP, MUFU.EX2
+__global__ void __launch_bounds__(256, 2) k_rcp(const float* in, float* out, int n) {
+  float a[8];
+  for (int i = 0; i < 8; ++i) a[i] = in[threadIdx.x + 32 * i];
+  for (int it = 0; it < n; ++it) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(a[i]));
+  }
+  float s = 0.f;
+  for (int i = 0; i < 8; ++i) s += a[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+__global__ void __launch_bounds__(256, 2) k_ex2(const float* in, float* out, int n) {
+  float a[8];
+  for (int i = 0; i < 8; ++i) a[i] = in[threadIdx.x + 32 * i];
+  for (int it = 0; it < n; ++it) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a[i]));
+  }
+  float s = 0.f;
+  for (int i = 0; i < 8; ++i) s += a[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// 9: the exact-class GELU of the precise extractor (log-odds polynomial: 10 packed + 2 EX2 + 2 RCP per pair)
+__device__ __forceinline__ float2 gelu_x(float2 x) {
+  const float2 x2 = __fmul2_rn(x, x);
+  float2 p = __ffma2_rn(x2, make_float2(-5.209925380000868e-09f, -5.209925380000868e-09f), make_float2(3.850457233056659e-07f, 3.850457233056659e-07f));
+  p = __ffma2_rn(p, x2, make_float2(-1.1452440958237275e-05f, -1.1452440958237275e-05f));
+  p = __ffma2_rn(p, x2, make_float2(1.5938949945848435e-04f, 1.5938949945848435e-04f));
+  p = __ffma2_rn(p, x2, make_float2(9.559268073644489e-05f, 9.559268073644489e-05f));
+  p = __ffma2_rn(p, x2, make_float2(-0.10483857989311218f, -0.10483857989311218f));
+  p = __ffma2_rn(p, x2, make_float2(-2.3022072315216064f, -2.3022072315216064f));
+  const float2 a = __fmul2_rn(p, x);
+  float2 e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(a.x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(a.y));
+  const float2 d = __fadd2_rn(e, make_float2(1.0f, 1.0f));
+  float2 r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(d.x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(d.y));
+  return __fmul2_rn(x, r);
+}
+__global__ void __launch_bounds__(256, 2) k_gelu_x(const float* in, float* out, int n) {
+  float2 a[8];
+  for (int i = 0; i < 8; ++i) a[i] = make_float2(in[threadIdx.x + 32 * i], in[threadIdx.x + 32 * i + 1]);
+  for (int it = 0; it < n; ++it) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = gelu_x(a[i]);
+  }
+  float s = 0.f;
+  for (int i = 0; i < 8; ++i) s += a[i].x + a[i].y;
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 template <typename F>
 static double run(F launch, int grid) {
   cudaEvent_t e0, e1;
@@ -170,5 +248,9 @@ int main() {
   report("MUFU.TANH", run([&](int g, int n) { k_tanh<<<g, 256>>>((const float*)in, out, n); }, grid), 64);
   report("GELU tanh-form fp32x2 (elements)", run([&](int g, int n) { k_gelu<<<g, 256>>>((const float*)in, out, n); }, grid), 64);
   report("GELU tanh-form half2 (elements)", run([&](int g, int n) { k_gelu_h2<<<g, 256>>>((const float*)in, out, n); }, grid), 64);
+  report("FFMA scalar 3-reg", run([&](int g, int n) { k_ffma<<<g, 256>>>((const float*)in, out, n); }, grid), 64);
+  report("MUFU.RCP", run([&](int g, int n) { k_rcp<<<g, 256>>>((const float*)in, out, n); }, grid), 64);
+  report("MUFU.EX2", run([&](int g, int n) { k_ex2<<<g, 256>>>((const float*)in, out, n); }, grid), 64);
+  report("GELU exact-class fp32x2 (elements)", run([&](int g, int n) { k_gelu_x<<<g, 256>>>((const float*)in, out, n); }, grid), 64);
   return 0;
 }
