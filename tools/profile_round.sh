@@ -21,4 +21,7 @@ timeout 900 ncu --nvtx --nvtx-include "wmk_timed_step/" --metrics gpu__time_dura
 timeout 1200 ncu --nvtx --nvtx-include "wmk_timed_step/" --set full --import-source on --clock-control none -c 110 \
     -o /tmp/${TAG}_top python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-other-configs > $OUT/${TAG}_ncu_top.log 2>&1
 ncu -i /tmp/${TAG}_top.ncu-rep --page raw --csv > $OUT/${TAG}_top_raw.csv 2>/dev/null
+# 6. launch list of the ModelA training step (BASELINE configs[4])                     -> gpurun_out/<tag>_launches_train.csv
+timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 600 --csv \
+    --log-file $OUT/${TAG}_launches_train.csv python tools/train_bench.py --steps 3 > $OUT/${TAG}_ncu_train.log 2>&1
 ls -la $OUT | tail -8
