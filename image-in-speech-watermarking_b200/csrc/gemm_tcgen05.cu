@@ -320,6 +320,14 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __
             const int rowi = m0 >> 7, img = rowi / p.conv_H, h = rowi - img * p.conv_H;
             tma_load_4d(sa, &tmA, 0, kb % 3 - 1, h + kb / 3 - 1, img, full_bar(s));
             if (!w_stationary) tma_load_2d(sa + A_STAGE, &tmW, kb * BK, n0, full_bar(s));
+          } else if (p.dn_Ho > 0) {    // implicit GEMM over the space-to-depth tensor: k-block = (tap, 64-channel chunk)
+            const int P = p.dn_Ho * p.dn_Ho;
+            const int img = m0 / P, oh0 = (m0 - img * P) / p.dn_Ho;
+            const int tap = kb / p.dn_chunks, c0 = (kb - tap * p.dn_chunks) * BK;
+            tma_load_4d(sa, &tmA, c0, tap & 1, oh0 + (tap >> 1), img, full_bar(s));
+            if (split == 1) tma_load_4d(sa + A_BYTES, &tmA, p.dn_chunks * BK + c0, tap & 1, oh0 + (tap >> 1), img, full_bar(s));   // lo
+            tma_load_2d(sa + A_STAGE, &tmW, kb * BK, n0, full_bar(s));
+            if (split == 1) tma_load_2d(sa + A_STAGE + W_BYTES, &tmW, K + kb * BK, n0, full_bar(s));
           } else if (split == 1) {
             tma_load_2d(sa, &tmA, kb * BK, m0, full_bar(s));                       // hi
             tma_load_2d(sa + A_BYTES, &tmA, K + kb * BK, m0, full_bar(s));         // lo
@@ -744,6 +752,14 @@ int launch_persistent_t(const GemmArgs& g, cudaStream_t st) {
     const uint64_t strides[3] = {128, 128ull * 128, 128ull * 128 * (uint64_t)g.conv_H};
     const uint32_t box[4] = {64, 128, 1, 1};
     WMK_TRY(make_tensor_map(&tmA, g.A, 4, dims, strides, box, false, 128));
+  } else if (g.dn_Ho > 0) {
+    // S[dn_B][Ho + 1][Ho + 1][Ck], Ck = 4C (split: 8C = hi | lo); box = 64 channels x the 128 output pixels of a row tile
+    const int Ho = g.dn_Ho, Ck = (g.K / 4) * (g.split ? 2 : 1);
+    const int rows = Ho * Ho >= BM ? BM / Ho : Ho, imgs = BM / (Ho * rows);
+    const uint64_t dims[4] = {(uint64_t)Ck, (uint64_t)(Ho + 1), (uint64_t)(Ho + 1), (uint64_t)g.dn_B};
+    const uint64_t strides[3] = {(uint64_t)Ck * 2, (uint64_t)(Ho + 1) * Ck * 2, (uint64_t)(Ho + 1) * (Ho + 1) * Ck * 2};
+    const uint32_t box[4] = {64, (uint32_t)Ho, (uint32_t)rows, (uint32_t)imgs};
+    WMK_TRY(make_tensor_map(&tmA, g.A, 4, dims, strides, box, false, 128));
   } else {
     WMK_TRY(make_map(&tmA, g.A, g.M, g.split ? 2 * g.K : g.K, BM));
   }
@@ -764,7 +780,7 @@ int launch_persistent_t(const GemmArgs& g, cudaStream_t st) {
     const bool ln_reuse = g.split || g.wsplit || g.ln_split;
     const int fixed = kEpiWarps * stg + 1024 + 512 + (LN ? (int)((ln_reuse ? 0 : kEpiWarps * STG2_BYTES) + LN_EXCH_BYTES) : 0);
     // weight-stationary when the whole BN x K tile + >= 2 A stages fit and every N tile gets >= 1 CTA
-    ws = (g.conv_H == 0 && wblocks <= (split_mode ? 8 : 4) && w_bytes + 2 * a_stage + fixed <= budget && n_tiles <= num_sms() &&
+    ws = (g.conv_H == 0 && g.dn_Ho == 0 && wblocks <= (split_mode ? 8 : 4) && w_bytes + 2 * a_stage + fixed <= budget && n_tiles <= num_sms() &&
           m_tiles >= 2 * (num_sms() / n_tiles)) ? 1 : 0;
     const int stage = ws ? a_stage : a_stage + w_stage;
     const int avail = budget - fixed - (ws ? w_bytes : 0);
@@ -795,6 +811,8 @@ int launch_persistent_t(const GemmArgs& g, cudaStream_t st) {
   EpiParams p{g.bias, g.resid, g.C, g.M, g.N, g.ldc, g.epi, g.out_bf16, g.up_h, g.up_w, g.up_cout};
   p.ln_gamma = g.ln_gamma; p.ln_beta = g.ln_beta; p.ln_mod = g.ln_mod; p.ln_H = g.ln_H; p.ln_shift = g.ln_shift;
   p.conv_H = g.conv_H;
+  p.dn_Ho = g.dn_Ho;
+  p.dn_chunks = g.dn_Ho > 0 ? g.K / 4 / BK : 0;
   p.boxc = boxc;
   static const int resid_pf = getenv("WMK_GEMM_RESID_PREFETCH") ? atoi(getenv("WMK_GEMM_RESID_PREFETCH")) : 1;
   p.resid_prefetch = resid_pf;
@@ -879,6 +897,10 @@ int gemm_bf16_tcgen05(const GemmArgs& g, cudaStream_t st) {
   if (g.conv_H > 0)
     WMK_REQUIRE(g.K == 576 && g.M == g.conv_B * g.conv_H * 128 && g.ldc == g.N && g.epi != EPI_UPSAMPLE,
                 "gemm_bf16: implicit-GEMM conv needs K = 576 and M = B*H*128 (W = 128)");
+  if (g.dn_Ho > 0)
+    WMK_REQUIRE(g.conv_H == 0 && !g.wsplit && g.K % 256 == 0 && g.dn_Ho >= 8 && g.dn_Ho <= 128 && (g.dn_Ho & (g.dn_Ho - 1)) == 0 &&
+                    g.M == g.dn_B * g.dn_Ho * g.dn_Ho && g.ldc == g.N && g.epi != EPI_UPSAMPLE,
+                "gemm_bf16: implicit-GEMM downsample needs K = 16C (C %% 16 == 0), a power-of-two output side in [8, 128] and M = B*Ho*Ho");
   if (g.split || g.wsplit)
     WMK_REQUIRE((g.K == 32 || g.K % 64 == 0) && g.conv_H == 0 && g.epi != EPI_UPSAMPLE && g.ldc == g.N && !(g.split && g.wsplit),
                 "gemm_bf16: split operands need K = 32 or K %% 64 == 0 (K = %d) and a plain row-major C", g.K);

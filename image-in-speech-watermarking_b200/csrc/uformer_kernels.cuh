@@ -686,6 +686,52 @@ im2col_4x4s2_kernel(const float* __restrict__ x, OpT* __restrict__ A, int B, int
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Space-to-depth copy for the IMPLICIT-GEMM form of Downsample = Conv2d(C, 2C, k=4, s=2, p=1): with the padded image rows
+// r = h + 1 and columns q = w + 1 paired as (sh, ph) = (r >> 1, r & 1), (sw, pw) = (q >> 1, q & 1), the 4x4 stride-2
+// convolution is a 2x2 stride-1 convolution over S[b][sh][sw][(ph, pw, ci)] (sh <= H/2, sw <= H/2, 4C channels): output
+// (oh, ow) reads cells (oh + a, ow + b), a, b in {0, 1}, i.e. kernel position (kh, kw) = (2a + ph, 2b + pw).  The dense
+// kernel fetches those four shifted views as TMA boxes (gemm_tcgen05.cu, GemmArgs::dn_*), so every input element is
+// written ONCE in 16-bit form (the im2col matrix wrote it four times).  Border cells (r = 0, r = H + 1, ...) are written
+// as zeros here.  Split-bf16 operands: cell rows are [hi(4C) | lo(4C)].  One thread = 8 channels of one (cell, phase).
+// ------------------------------------------------------------------------------------------
+template <typename OpT>
+__global__ void __launch_bounds__(256)
+s2d_pad_kernel(const float* __restrict__ x, OpT* __restrict__ S, int B, int H, int C) {
+  const int cg = C >> 3;
+  const int Hs = (H >> 1) + 1;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)B * Hs * Hs * 4 * cg;
+  if (idx >= total) return;
+  const int c = (int)(idx % cg) * 8;
+  size_t r = idx / cg;
+  const int phw = (int)(r & 3);
+  r >>= 2;
+  const int sw = (int)(r % Hs);
+  const int sh = (int)((r / Hs) % Hs);
+  const size_t b = r / ((size_t)Hs * Hs);
+  const int ih = 2 * sh + (phw >> 1) - 1, iw = 2 * sw + (phw & 1) - 1;
+  float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+  if (ih >= 0 && ih < H && iw >= 0 && iw < H) {
+    const float* src = x + ((b * H + ih) * H + iw) * C + c;
+    v0 = *reinterpret_cast<const float4*>(src);
+    v1 = *reinterpret_cast<const float4*>(src + 4);
+  }
+  const size_t cell = (b * Hs + sh) * Hs + sw;
+  const int col = phw * C + c;
+  if constexpr (OpMode<OpT>::v == 2) {
+    __nv_bfloat16* row = reinterpret_cast<__nv_bfloat16*>(S) + cell * (size_t)(8 * C);
+    split_store4(row, col, 4 * C, v0.x, v0.y, v0.z, v0.w);
+    split_store4(row, col + 4, 4 * C, v1.x, v1.y, v1.z, v1.w);
+  } else {
+    constexpr bool F16 = OpMode<OpT>::v == 3;
+    uint4 u;
+    u.x = pack2_16<F16>(v0.x, v0.y); u.y = pack2_16<F16>(v0.z, v0.w);
+    u.z = pack2_16<F16>(v1.x, v1.y); u.w = pack2_16<F16>(v1.z, v1.w);
+    *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(S) + cell * (size_t)(4 * C) + col) = u;
+  }
+}
+
 // fp32 -> OpT copy of a [rows][cols] matrix into a [rows][ld_dst] buffer at column offset col0
 // (operand casts; the decoder's torch.cat([up, skip], -1) of uformerWM/model.py:1225-1237).
 template <typename DstT>

@@ -314,6 +314,12 @@ int pack_block(wmk_plan* P, const std::string& p, int C, int heads, int H, int s
   return 0;
 }
 
+// Downsample as an implicit GEMM over the space-to-depth tensor (16-bit plans; WMK_IMPLICIT_DOWN=0 restores im2col)
+static int implicit_down() {
+  static const int v = getenv("WMK_IMPLICIT_DOWN") ? atoi(getenv("WMK_IMPLICIT_DOWN")) : 1;
+  return v;
+}
+
 static int ext_down_wsplit() {
   static const int v = getenv("WMK_EXT_DOWN_WSPLIT") ? atoi(getenv("WMK_EXT_DOWN_WSPLIT")) : 0;
   return v;
@@ -344,11 +350,17 @@ int pack_encoder(wmk_plan* P, const std::string& p, const std::string& inproj, E
       const HostTensor* t;
       const std::string dp = p + "dowsample_" + std::to_string(s) + ".conv.0.";
       WMK_TRY(get(P, dp + "weight", (size_t)2 * C * C * 16, &t));
-      std::vector<float> g((size_t)2 * C * 16 * C);                   // [co][(kh,kw,ci)]
+      // [co][(kh,kw,ci)] for the im2col form; the implicit-GEMM form (16-bit plans) orders k by the space-to-depth view:
+      // kernel position (kh, kw) = (2a + ph, 2b + pw) -> k = ((a*2 + b)*4 + ph*2 + pw)*C + ci (s2d_pad_kernel)
+      const bool s2d_order = mode != 0 && implicit_down() && !(mode == 2 && ext_down_wsplit());
+      std::vector<float> g((size_t)2 * C * 16 * C);
       for (int co = 0; co < 2 * C; ++co)
         for (int ci = 0; ci < C; ++ci)
-          for (int tap = 0; tap < 16; ++tap)
-            g[((size_t)co * 16 + tap) * C + ci] = t->data[((size_t)co * C + ci) * 16 + tap];
+          for (int tap = 0; tap < 16; ++tap) {
+            const int kh = tap >> 2, kw = tap & 3;
+            const int pos = s2d_order ? (((kh >> 1) * 2 + (kw >> 1)) * 4 + (kh & 1) * 2 + (kw & 1)) : tap;
+            g[((size_t)co * 16 + pos) * C + ci] = t->data[((size_t)co * C + ci) * 16 + tap];
+          }
       // WMK_EXT_DOWN_WSPLIT=1 (experiment, off): fp16 im2col rows x (hi + lo) fp16 weights for the precise extractor's
       // downsample conv - 3.9 ms faster per step, but the fp16 rounding of the residual stream moves the logits by up to
       // 1.24e-4 (> the 1e-4 margin: test_mixed_extractor_bits_match_oracle_config2_shape fails), so split rows stay
@@ -556,7 +568,13 @@ int run_encoder(wmk_plan* P, const EncW& e, const float* x_nchw, int n, const ch
     OpT* col = reinterpret_cast<OpT*>(P->bufH1);
     const size_t total = (size_t)n * Ho * Ho * 4 * (C / 8);
     const bool down_wsplit = OpMode<OpT>::v == 2 && ext_down_wsplit();      // fp16 rows x (hi + lo) weights
-    {
+    const bool s2d = OpMode<OpT>::v != 0 && implicit_down() && !down_wsplit;   // implicit GEMM: every element written once
+    if (s2d) {
+      const size_t cells = (size_t)n * (Ho + 1) * (Ho + 1);
+      ProfScope prof_l(FAM_LAYOUT, (double)n * H * H * C * 4 + (double)cells * 4 * C * sizeof(OpT), st);
+      s2d_pad_kernel<OpT><<<cdiv(cells * 4 * (C / 8), 256), 256, 0, st>>>(P->E[s], col, n, H, C);
+      WMK_CHECK_LAUNCH("s2d_pad_kernel");
+    } else {
       ProfScope prof_l(FAM_LAYOUT, (double)n * H * H * C * 4 + (double)n * Ho * Ho * 16 * C * (down_wsplit ? 2 : sizeof(OpT)), st);
       if (down_wsplit) im2col_4x4s2_kernel<__half><<<cdiv(total, 256), 256, 0, st>>>(P->E[s], reinterpret_cast<__half*>(col), n, H, C);
       else im2col_4x4s2_kernel<OpT><<<cdiv(total, 256), 256, 0, st>>>(P->E[s], col, n, H, C);
@@ -566,6 +584,7 @@ int run_encoder(wmk_plan* P, const EncW& e, const float* x_nchw, int n, const ch
     g.A = col; g.W = e.down_w[s]; g.bias = e.down_b[s]; g.C = P->E[s + 1]; g.M = n * Ho * Ho; g.N = 2 * C;
     g.K = 16 * C; g.ldc = 2 * C; g.epi = EPI_BIAS; g.out_bf16 = 0; g.split = OpMode<OpT>::v == 2 && !down_wsplit; g.wsplit = down_wsplit;
     g.f16 = OpMode<OpT>::v == 3;
+    if (s2d) { g.dn_Ho = Ho; g.dn_B = n; }
     static const int fuse_first_ln = getenv("WMK_FUSE_FIRST_LN") ? atoi(getenv("WMK_FUSE_FIRST_LN")) : 1;
     if ((OpPlain16<OpT>::v || (OpMode<OpT>::v == 2 && split_ln0)) && fuse_first_ln && 2 * C <= 128) {
       // the next stage's first norm1 rides on the downsample conv's epilogue (encoder blocks carry no modulator)

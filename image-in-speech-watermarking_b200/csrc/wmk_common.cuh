@@ -106,6 +106,12 @@ struct GemmArgs {
   // tile = the 128 pixels of one image row, k-block kb = tap (dy, dx) fetched as the TMA box shifted by (dy-1, dx-1)
   // with out-of-bounds zero fill as the padding; W is [N][9*64] with k = tap*64 + ci.  M = conv_B*conv_H*128, K = 576.
   int conv_H = 0, conv_B = 0;
+  // Implicit-GEMM Downsample = Conv2d(C, 2C, k=4, s=2, p=1) (uformerWM/model.py:763,768-775): A is the space-to-depth
+  // tensor S[dn_B][dn_Ho + 1][dn_Ho + 1][4C] of s2d_pad_kernel (split operands: cells [hi(4C) | lo(4C)]); a row tile =
+  // 128 output pixels (whole rows of one image, or whole images when an image has 64 pixels), k-block kb = tap
+  // (a, b) = kb / (4C/64) x 64-channel chunk, fetched as the TMA box shifted by (a, b) cells.  W is [N][16C] (split:
+  // [hi | lo]) with k = ((a*2 + b)*4 + ph*2 + pw)*C + ci for kernel position (2a + ph, 2b + pw).  M = dn_B*dn_Ho^2, K = 16C.
+  int dn_Ho = 0, dn_B = 0;
   // Split-bf16 ("bf16x3") operands: A is [M][2K] bf16, row = [hi(K) | lo(K)] with hi = bf16(v), lo = bf16(v - hi);
   // W is the packed split weight of pack_split_weight() ([N][2K] = [hi | lo]; K == 32: [N][128] = [hi | hi | lo | 0]).
   // The product is hi*hi + lo*hi + hi*lo, accumulated by three tcgen05 MMAs per k-step into the same fp32 TMEM
@@ -129,7 +135,9 @@ struct GemmWork { int family; double work, work2; };
 static inline GemmWork gemm_work(const GemmArgs& g, int es) {
   if (g.split) es = 4;                   // hi + lo
   const double flops = 2.0 * g.M * g.N * g.K;
-  const double bytes = (double)g.M * g.K * es + (double)g.N * g.K * es + (double)g.M * g.N * (g.out_bf16 ? 2 : 4) +
+  // implicit-GEMM downsample: the space-to-depth tensor holds every input element once (K / 4 values per output pixel)
+  const double a_bytes = (double)g.M * (g.dn_Ho > 0 ? g.K / 4 : g.K) * es;
+  const double bytes = a_bytes + (double)g.N * g.K * es + (double)g.M * g.N * (g.out_bf16 ? 2 : 4) +
                        (g.epi == EPI_BIAS_RESID ? (double)g.M * g.N * 4 : 0.0);
   if (flops / bytes >= 214.0) return {FAM_GEMM, flops, bytes};
   return {FAM_GEMM_HBM, bytes, flops};
@@ -309,6 +317,8 @@ struct EpiParams {
   const float* ln_mod = nullptr;
   int ln_H = 0, ln_shift = 0;
   int conv_H = 0;      // > 0: implicit-GEMM 3x3 convolution (see GemmArgs)
+  int dn_Ho = 0;       // > 0: implicit-GEMM 4x4 stride-2 downsample over the space-to-depth tensor (see GemmArgs)
+  int dn_chunks = 0;   //      64-channel chunks per tap (4C / 64)
   int boxc = 64;       // persistent kernel, bf16 output: columns per TMA store box (64 or 32)
   int resid_prefetch = 0;   // persistent kernel: L2-prefetch the next tile's residual rows
   int gelu_half = 0;        // GELU epilogue: the accumulator holds x / 2 (weights and bias pre-halved)
