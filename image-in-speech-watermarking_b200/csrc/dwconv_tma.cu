@@ -147,6 +147,9 @@ int launch_dw(const void* in, void* out, const float* wt, const float* bias, int
 }
 
 // ---------------------------------------------------------------------------------- two columns per thread
+#ifndef DW2_SCALAR_FMA
+#define DW2_SCALAR_FMA 0
+#endif
 constexpr int DW2_TW = 16, DW2_PW = DW2_TW + 2, DW2_TH = 8, DW2_PH = DW2_TH + 2;
 
 struct DwGeom2 {
@@ -236,8 +239,16 @@ dwconv3x3_gelu_tma2_kernel(const __grid_constant__ CUtensorMap tm, uint16_t* __r
         for (int dx = 0; dx < 3; ++dx)
 #pragma unroll
           for (int q = 0; q < 2; ++q) {
+#if DW2_SCALAR_FMA
+            // scalar FFMA: 87 FMA / clk / SM measured against 75 for FFMA2 (tools/ubench/pipe_rates.cu) at twice the issue slots
+            acc[o % 3][q][0].x = fmaf(in[q + dx][0].x, wreg[dy * 3 + dx][0].x, acc[o % 3][q][0].x);
+            acc[o % 3][q][0].y = fmaf(in[q + dx][0].y, wreg[dy * 3 + dx][0].y, acc[o % 3][q][0].y);
+            acc[o % 3][q][1].x = fmaf(in[q + dx][1].x, wreg[dy * 3 + dx][1].x, acc[o % 3][q][1].x);
+            acc[o % 3][q][1].y = fmaf(in[q + dx][1].y, wreg[dy * 3 + dx][1].y, acc[o % 3][q][1].y);
+#else
             acc[o % 3][q][0] = __ffma2_rn(in[q + dx][0], wreg[dy * 3 + dx][0], acc[o % 3][q][0]);
             acc[o % 3][q][1] = __ffma2_rn(in[q + dx][1], wreg[dy * 3 + dx][1], acc[o % 3][q][1]);
+#endif
           }
       }
       if (i >= 2) {                                 // output row i - 2 is complete
