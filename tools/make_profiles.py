@@ -27,7 +27,7 @@ def short(name):
 
 def family(name):
     for key, fam in (("leff_block", "leff_fused"), ("attn_block", "attention"), ("gemm_tcgen05", "gemm"), ("attention", "attention"), ("dwconv", "dwconv"), ("layernorm", "layernorm"),
-                     ("im2col", "layout"), ("copy_cols", "layout"), ("stft", "frontend"), ("iir", "attack"), ("awgn", "attack")):
+                     ("im2col", "layout"), ("s2d_pad", "layout"), ("copy_cols", "layout"), ("stft", "frontend"), ("iir", "attack"), ("awgn", "attack")):
         if key in name:
             return fam
     return "other"
