@@ -374,11 +374,15 @@ def bench_config5(ctx, steps, warmup, clips=192):
     x, wm = host_x.to(ctx.dev), host_wm.to(ctx.dev)
     ms, launches, out = ctx.timed(lambda: TM.train_step(m, opt, x, wm), steps, warmup)
 
+    # end to end: host batches through train_modelA.HostBatchTrainer (upload of the next batch on a side stream, the loss read
+    # back one step late); every copy of the K steps lies inside the timed region
+    trainer = TM.HostBatchTrainer(m, opt)
+
     def e2e_step():
-        loss, _, _ = TM.train_step(m, opt, host_x.to(ctx.dev, non_blocking=True), host_wm.to(ctx.dev, non_blocking=True))
-        return loss.cpu()
+        return trainer.submit(host_x, host_wm)
 
     ms_e2e, _, _ = ctx.timed(e2e_step, steps, warmup)
+    trainer.flush()
     total = clips * ctx.world
     _, peak_bw, src = peaks()
     # algorithmic bytes of the step: ~13 MB of fp32 activations per clip forward, written once and read once in
@@ -391,7 +395,8 @@ def bench_config5(ctx, steps, warmup, clips=192):
                                   "ONE NCCL all-reduce of the flat 17 655-float gradient per step; 8 GPUs = the named 256 x 3 s batch"
                                   % (clips, clips // 6), "clips_per_gpu": clips, "global_batch_clips": total}, launches)
     line["e2e"] = {"value": total * 0.5 / (ms_e2e * 1e-3), "unit": "audio-s/s", "ms_per_step": ms_e2e,
-                   "h2d_bytes_per_step": (host_x.numel() + host_wm.numel()) * 4, "d2h_bytes_per_step": 4}
+                   "h2d_bytes_per_step": (host_x.numel() + host_wm.numel()) * 4, "d2h_bytes_per_step": 12,
+                   "api": "train_modelA.HostBatchTrainer.submit per step (pinned host batch in, the three losses back)"}
     line["roofline"] = {"bound": "hbm", "achieved": gbs, "peak": peak_bw * ctx.world, "unit": "GB/s", "frac": gbs / (peak_bw * ctx.world),
                         "kernel": "conv3x3_kernel / conv3x3_wgrad_kernel / bn_train_*", "peak_source": src, "traffic": None,
                         "definition": "5 x 13 MB of fp32 activation traffic per clip (forward write + read, backward read + gradient "

@@ -561,6 +561,47 @@ convT2x2_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w,
   }
 }
 
+// register-blocked form for Cout <= COB: the 4 COB gradient values of a pixel are read once (8-byte loads) and kept in
+// registers for all input channels (the kernel above re-reads them for every ci)
+template <int COB>
+__global__ void __launch_bounds__(256)
+convT2x2_dgrad_rb_kernel(const float* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dx, int B, int Cin,
+                         int Cout, int H, int W) {
+  extern __shared__ __align__(16) float wsm[];             // [Cin][COB][4], output channels >= Cout zero
+  for (int e = threadIdx.x; e < Cin * COB * 4; e += blockDim.x) {
+    const int ci = e / (COB * 4), r = e - ci * COB * 4, co = r >> 2;
+    wsm[e] = co < Cout ? w[((size_t)ci * Cout + co) * 4 + (r & 3)] : 0.f;
+  }
+  __syncthreads();
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)B * H * W) return;
+  const int wq = (int)(idx % W), h = (int)((idx / W) % H);
+  const size_t b = idx / ((size_t)H * W);
+  float d[COB][4];
+#pragma unroll
+  for (int co = 0; co < COB; ++co) {
+    if (co < Cout) {
+      const float* p = dy + ((b * Cout + co) * (size_t)(2 * H) + 2 * h) * (2 * W) + 2 * wq;
+      const float2 d0 = *reinterpret_cast<const float2*>(p), d1 = *reinterpret_cast<const float2*>(p + 2 * W);
+      d[co][0] = d0.x; d[co][1] = d0.y; d[co][2] = d1.x; d[co][3] = d1.y;
+    } else {
+      d[co][0] = d[co][1] = d[co][2] = d[co][3] = 0.f;
+    }
+  }
+  float* xp = dx + (b * Cin * H + h) * W + wq;
+  for (int ci = 0; ci < Cin; ++ci) {
+    const float4* w4 = reinterpret_cast<const float4*>(wsm + ci * COB * 4);
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int co = 0; co < COB; ++co) {
+      const float4 ww = w4[co];
+      a0 = fmaf(ww.x, d[co][0], fmaf(ww.y, d[co][1], a0));
+      a1 = fmaf(ww.z, d[co][2], fmaf(ww.w, d[co][3], a1));
+    }
+    xp[(size_t)ci * H * W] = a0 + a1;
+  }
+}
+
 // weight gradient: dw[ci][co][i][j] = sum_{b,h,w} x[b][ci][h][w] dy[b][co][2h+i][2w+j];  db[co] = sum dy
 // Persistent CTAs walk 16x16 input tiles; a thread owns up to 3 (ci, co) pairs = 4 accumulators each, kept in
 // registers across all of the CTA's tiles (one atomic per accumulator per CTA).
@@ -979,6 +1020,12 @@ extern "C" int wmk_convT2x2_dgrad_f32(const float* dy, const float* w, float* dx
   cudaStream_t st = (cudaStream_t)stream;
   ProfScope prof(FAM_SMALL, 4.0 * B * H * W * (Cin + 4 * Cout), st);
   const size_t smem = (size_t)Cin * Cout * 16;
+  if ((Cout <= 2 || (Cout > 4 && Cout <= 16)) && ((uintptr_t)dy & 7) == 0 && (size_t)Cin * (Cout <= 2 ? 2 : 16) * 16 <= 48 * 1024) {
+    if (Cout <= 2) convT2x2_dgrad_rb_kernel<2><<<grid_for((size_t)B * H * W), 256, (size_t)Cin * 2 * 16, st>>>(dy, w, dx, B, Cin, Cout, H, W);
+    else convT2x2_dgrad_rb_kernel<16><<<grid_for((size_t)B * H * W), 256, (size_t)Cin * 16 * 16, st>>>(dy, w, dx, B, Cin, Cout, H, W);
+    WMK_CHECK_LAUNCH("convT2x2_dgrad_rb_kernel");
+    return 0;
+  }
   if (smem > 48 * 1024) WMK_CHECK_CUDA(cudaFuncSetAttribute(convT2x2_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   convT2x2_dgrad_kernel<<<grid_for((size_t)B * H * W), 256, smem, st>>>(dy, w, dx, B, Cin, Cout, H, W);
   WMK_CHECK_LAUNCH("convT2x2_dgrad_kernel");

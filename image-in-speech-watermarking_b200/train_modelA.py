@@ -44,3 +44,59 @@ def train_step(model, optimizer, input_, message, loss_scale=1.0):
     optimizer.step(grad_scale=1.0 / (loss_scale * world))
     return loss.detach(), loss1.detach(), loss2.detach()
 
+
+
+class HostBatchTrainer:
+    """Training loop for HOST batches (what a DataLoader hands over, `uformerWM/train_modelA.py:402-421`): pinned
+    (input_, message) pairs are uploaded on a side stream into one of two device slots while the previous step
+    computes, and the loss is read back one step late, so neither copy stalls the step.  `submit` returns the
+    previous step's loss (None for the first call); `flush` the last one.  Same updates as calling `train_step`
+    batch by batch."""
+
+    def __init__(self, model, optimizer, loss_scale=1.0):
+        self.model, self.opt, self.loss_scale = model, optimizer, loss_scale
+        self.h2d = torch.cuda.Stream()
+        self.slots = [None, None]
+        self.n = 0
+        self.pending = None          # (pinned loss buffer, event) of the last submitted step
+
+    def _slot(self, s, host_x, host_m):
+        sl = self.slots[s]
+        if sl is None or sl["x"].shape != host_x.shape or sl["m"].shape != host_m.shape:
+            dev = torch.device("cuda", torch.cuda.current_device())
+            sl = {"x": torch.empty(host_x.shape, dtype=torch.float32, device=dev),
+                  "m": torch.empty(host_m.shape, dtype=torch.float32, device=dev),
+                  "up": torch.cuda.Event(), "done": torch.cuda.Event(), "loss": torch.empty(3, dtype=torch.float32).pin_memory(),
+                  "read": torch.cuda.Event(), "used": False}
+            self.slots[s] = sl
+        return sl
+
+    def submit(self, host_x, host_m):
+        main = torch.cuda.current_stream()
+        s = self.n & 1
+        sl = self._slot(s, host_x, host_m)
+        with torch.cuda.stream(self.h2d):
+            if sl["used"]:
+                self.h2d.wait_event(sl["done"])             # the step that used this slot two calls ago has finished
+            sl["x"].copy_(host_x, non_blocking=True)
+            sl["m"].copy_(host_m, non_blocking=True)
+            sl["up"].record(self.h2d)
+        main.wait_event(sl["up"])
+        loss, l1, l2 = train_step(self.model, self.opt, sl["x"], sl["m"], self.loss_scale)
+        sl["loss"].copy_(torch.stack([loss, l1, l2]), non_blocking=True)
+        sl["done"].record(main)
+        sl["used"] = True
+        prev, self.pending = self.pending, sl
+        self.n += 1
+        return self._read(prev)
+
+    @staticmethod
+    def _read(sl):
+        if sl is None:
+            return None
+        sl["done"].synchronize()
+        return tuple(float(v) for v in sl["loss"])
+
+    def flush(self):
+        prev, self.pending = self.pending, None
+        return self._read(prev)

@@ -342,3 +342,38 @@ def test_fused_bn_pool_and_dgrad_equal_their_compositions():
         _lib.check(lib.wmk_conv3x3_dgrad_f32(_lib.ptr(dy), _lib.ptr(w), _lib.ptr(dx), 2, Cin, Cout, Hh, Hh + 4, _lib.stream_ptr()))
         ref = torch.nn.grad.conv2d_input(dx.shape, w.double().cpu(), dy.double().cpu(), padding=1)     # cuDNN would use TF32
         assert torch.allclose(dx.cpu().double(), ref, rtol=1e-4, atol=1e-4), (Cin, Cout)
+
+
+@pytest.mark.gpu
+def test_host_batch_trainer_equals_step_by_step(golden):
+    """`train_modelA.HostBatchTrainer` (pinned host batches uploaded on a side stream, losses read back one step late)
+    makes exactly the updates of `train_step` called batch by batch on device tensors."""
+    from image_in_speech_watermarking_b200 import cnn_train as CT, train_modelA as TM
+    g = golden("modelA_train.npz")
+    x, wm = torch.from_numpy(g["x"]), torch.from_numpy(g["wm"])
+    batches = [((x + 0.01 * i).pin_memory(), wm.roll(i, 0).contiguous().pin_memory()) for i in range(4)]
+    finals, losses = [], []
+    for pipelined in (False, True):
+        m = _load_train_model(g)
+        m.dropout_masks = None
+        m.attack = TM.gaussian_attack(0.05)
+        opt = CT.FlatAdam(m.parameters(), lr=1e-3, weight_decay=0.02)
+        torch.manual_seed(123)
+        torch.cuda.manual_seed(123)
+        ls = []
+        if pipelined:
+            tr = TM.HostBatchTrainer(m, opt)
+            for hx, hm in batches:
+                r = tr.submit(hx, hm)
+                if r is not None:
+                    ls.append(r[0])
+            ls.append(tr.flush()[0])
+        else:
+            for hx, hm in batches:
+                ls.append(float(TM.train_step(m, opt, hx.cuda(), hm.cuda())[0]))
+        torch.cuda.synchronize()
+        finals.append(opt.flat.clone())
+        losses.append(ls)
+    assert len(losses[0]) == len(losses[1]) == 4
+    assert np.allclose(losses[0], losses[1], rtol=1e-6, atol=0)
+    assert torch.allclose(finals[0], finals[1], rtol=1e-6, atol=1e-8)
