@@ -297,17 +297,20 @@ constexpr int ATT_BLD = 72;    // bf16 elements per bias row in smem (144 B: con
 
 // F16: q / k / v / out (and the in-kernel bias and probability fragments) are IEEE fp16 instead of bf16.
 // SPLIT_OUT: the output rows are split-bf16 [hi(C) | lo(C)] (the A operand of a split projection; the precise extractor).
-template <bool F16, bool SPLIT_OUT = false>
+// NST: depth of the cp.async ring of q / k / v tiles (2: one window ahead, 5 CTAs per SM = 60 KB in flight per SM;
+// 3: two windows ahead, dynamic shared memory, 4 CTAs per SM = 96 KB in flight)
+template <bool F16, bool SPLIT_OUT = false, int NST = 2>
 static __global__ void __launch_bounds__(128)
 window_attention_mma_kernel(const uint16_t* __restrict__ qkv, uint16_t* __restrict__ out,
                             const float* __restrict__ bias, int C, int H, int shift, int n_windows) {
-  __shared__ __align__(16) uint16_t sbuf[2][3 * ATT_TILE];
+  extern __shared__ __align__(16) uint16_t att_dyn[];           // [NST][3 * ATT_TILE]
+  uint16_t (*sbuf)[3 * ATT_TILE] = reinterpret_cast<uint16_t (*)[3 * ATT_TILE]>(att_dyn);
   __shared__ __align__(16) uint16_t sbias[64 * ATT_BLD];
   auto mma = [](float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
     if constexpr (F16) mma_f16_16816(d, a, b0, b1);
     else mma_bf16_16816(d, a, b0, b1);
   };
-  __shared__ int s_tok[2][64], s_rid[2][64];
+  __shared__ int s_tok[NST][64], s_rid[NST][64];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   AttGeom g{C, H, shift, 31 - __clz(C >> 5), 31 - __clz(H >> 3)};
   const int heads = C >> 5;
@@ -341,6 +344,10 @@ window_attention_mma_kernel(const uint16_t* __restrict__ qkv, uint16_t* __restri
   int win = blockIdx.x >> g.lg_heads;
   if (win >= n_windows) return;
   prefetch(win, 0);
+  if constexpr (NST == 3) {                       // second window of the ring (an empty group keeps the group count uniform)
+    if (win + wstep < n_windows) prefetch(win + wstep, 1);
+    else asm volatile("cp.async.commit_group;" ::: "memory");
+  }
   {
     const float* bh = bias + (size_t)head * 4096;
     for (int e = tid; e < 2048; e += 128) {
@@ -354,13 +361,20 @@ window_attention_mma_kernel(const uint16_t* __restrict__ qkv, uint16_t* __restri
   const uint32_t aI[4] = {ident, 0u, 0u, ident};
   const uint32_t bs_addr = (uint32_t)__cvta_generic_to_shared(sbias);
   for (int it = 0; win < n_windows; win += wstep, ++it) {
-    const int buf = it & 1;
-    const int next = win + wstep;
-    if (next < n_windows) {
-      prefetch(next, buf ^ 1);
-      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    const int buf = NST == 3 ? it % 3 : (it & 1);
+    if constexpr (NST == 3) {
+      const int next2 = win + 2 * wstep;
+      if (next2 < n_windows) prefetch(next2, (it + 2) % 3);          // the buffer of iteration it - 1 (freed by its closing barrier)
+      else asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 2;" ::: "memory");           // groups complete in order: this window's tiles have landed
     } else {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      const int next = win + wstep;
+      if (next < n_windows) {
+        prefetch(next, buf ^ 1);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+      } else {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+      }
     }
     __syncthreads();
     uint16_t* Qs = &sbuf[buf][0];

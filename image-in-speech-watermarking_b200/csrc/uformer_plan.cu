@@ -467,11 +467,22 @@ int run_block(wmk_plan* P, const BlockW& w, float* x, int n, cudaStream_t st, bo
     ProfScope prof(FAM_ATTENTION, 256.0 * C * M, st);
     const int n_windows = n * (H / 8) * (H / 8);
     if constexpr (P16 || PRECISE) {
-      int per_head = (148 * 5) / w.heads;                 // CTAs per head (5 resident CTAs per SM)
+      static const int att_nst = getenv("WMK_ATT_STAGES") ? atoi(getenv("WMK_ATT_STAGES")) : 2;   // 3 (two windows ahead, 4 CTAs per SM) measured 2 % slower: not bound by bytes in flight
+      const int resident = att_nst == 3 ? 4 : 5;          // CTAs per SM (shared memory: 56 KB / 41 KB per CTA)
+      int per_head = (148 * resident) / w.heads;          // CTAs per head
       if (per_head > n_windows) per_head = n_windows;
       if (per_head < 1) per_head = 1;
-      window_attention_mma_kernel<F16 != 0, PRECISE><<<per_head * w.heads, 128, 0, st>>>(
-          reinterpret_cast<const uint16_t*>(P->bufQKV), reinterpret_cast<uint16_t*>(P->bufO), w.attn_bias, C, H, w.shift, n_windows);
+      const size_t att_smem = (size_t)(att_nst == 3 ? 3 : 2) * 3 * ATT_TILE * sizeof(uint16_t);
+      if (att_nst == 3) {
+        auto kern = window_attention_mma_kernel<F16 != 0, PRECISE, 3>;
+        static bool attr = false;
+        if (!attr) { WMK_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)att_smem)); attr = true; }
+        kern<<<per_head * w.heads, 128, att_smem, st>>>(
+            reinterpret_cast<const uint16_t*>(P->bufQKV), reinterpret_cast<uint16_t*>(P->bufO), w.attn_bias, C, H, w.shift, n_windows);
+      } else {
+        window_attention_mma_kernel<F16 != 0, PRECISE, 2><<<per_head * w.heads, 128, att_smem, st>>>(
+            reinterpret_cast<const uint16_t*>(P->bufQKV), reinterpret_cast<uint16_t*>(P->bufO), w.attn_bias, C, H, w.shift, n_windows);
+      }
     } else {
       window_attention_kernel<float><<<dim3(n_windows, w.heads), 128, 0, st>>>(
           reinterpret_cast<const float*>(P->bufQKV), reinterpret_cast<float*>(P->bufO), w.attn_bias, C, H, w.shift);
