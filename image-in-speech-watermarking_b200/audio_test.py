@@ -302,6 +302,8 @@ def embed_attack_extract_ragged(waves, messages, model, attack="closed_loop", dr
         if w.dim() != 1 or not w.is_cuda:
             raise ValueError("waves must be 1-D CUDA tensors")
         groups.setdefault(int(w.shape[0]), []).append(i)
+    if draws is not None and len(groups) > 1:
+        raise ValueError("explicit attack draws are per batch of equal-length utterances; pass seed= for a ragged corpus")
     G = []
     n_clean = n_att_max = 0
     for L, idx in groups.items():
