@@ -491,6 +491,13 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __
                 const float2 gq = gelu_erf2(make_float2(f[2 * j], f[2 * j + 1]));
                 f[2 * j] = gq.x; f[2 * j + 1] = gq.y;
               }
+            } else if (p.gelu_half && p.gelu_mix) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float2 gq = (j & 1) ? gelu_poly2_half_arg(make_float2(f[2 * j], f[2 * j + 1]))
+                                          : gelu_tanh2_half_arg(make_float2(f[2 * j], f[2 * j + 1]));
+                f[2 * j] = gq.x; f[2 * j + 1] = gq.y;
+              }
             } else if (p.gelu_half) {
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
@@ -818,6 +825,8 @@ int launch_persistent_t(const GemmArgs& g, cudaStream_t st) {
   p.resid_prefetch = resid_pf;
   p.gelu_half = g.gelu_half;
   p.gelu_exact = g.gelu_exact;
+  static const int gelu_mix = getenv("WMK_GELU_MIX") ? atoi(getenv("WMK_GELU_MIX")) : 0;
+  p.gelu_mix = gelu_mix;
   p.split = split_mode;
   p.f16 = g.f16 || g.wsplit;
   p.ln_split = g.ln_split;

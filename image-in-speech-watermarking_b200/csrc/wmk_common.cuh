@@ -245,6 +245,26 @@ __device__ __forceinline__ float2 gelu_tanh2_half_arg(float2 h) {
   return __ffma2_rn(h, t, h);
 }
 
+// MUFU-free GELU for a HALVED argument (h = x / 2): gelu_poly2's degree-15 erf polynomial on z = x / sqrt(2) = h sqrt(2).
+// Used for every other pair of the fp16 plan's linear1 epilogue (WMK_GELU_MIX=1) to move work from the XU pipe (MUFU.TANH +
+// the fp32 -> fp16 packs) to the FMA pipe.
+__device__ __forceinline__ float2 gelu_poly2_half_arg(float2 h) {
+  float2 z = __fmul2_rn(h, make_float2(1.41421356237309505f, 1.41421356237309505f));
+  z.x = fminf(fmaxf(z.x, -3.0f), 3.0f);
+  z.y = fminf(fmaxf(z.y, -3.0f), 3.0f);
+  const float2 z2 = __fmul2_rn(z, z);
+  float2 p = make_float2(-4.055369516e-07f, -4.055369516e-07f);
+  p = __ffma2_rn(p, z2, make_float2(1.715986036e-05f, 1.715986036e-05f));
+  p = __ffma2_rn(p, z2, make_float2(-3.145957307e-04f, -3.145957307e-04f));
+  p = __ffma2_rn(p, z2, make_float2(3.318712581e-03f, 3.318712581e-03f));
+  p = __ffma2_rn(p, z2, make_float2(-2.268580347e-02f, -2.268580347e-02f));
+  p = __ffma2_rn(p, z2, make_float2(1.077178344e-01f, 1.077178344e-01f));
+  p = __ffma2_rn(p, z2, make_float2(-3.732314110e-01f, -3.732314110e-01f));
+  p = __ffma2_rn(p, z2, make_float2(1.127895713e+00f, 1.127895713e+00f));
+  const float2 e = __fmul2_rn(p, z);
+  return __ffma2_rn(h, e, h);
+}
+
 // Split-bf16 ("bf16x3") operand format of the WMK_PREC_MIXED extractor: a value v travels as hi = bf16(v),
 // lo = bf16(v - hi) (16 mantissa bits); a row of K values is stored as [hi(K) | lo(K)], i.e. 2K bf16 = 4K bytes.
 // Tag type: sizeof 4 like the storage per element.
@@ -323,6 +343,7 @@ struct EpiParams {
   int resid_prefetch = 0;   // persistent kernel: L2-prefetch the next tile's residual rows
   int gelu_half = 0;        // GELU epilogue: the accumulator holds x / 2 (weights and bias pre-halved)
   int gelu_exact = 0;       // GELU epilogue: erf form (gelu_fast, |error| 1.5e-7) instead of the tanh form
+  int gelu_mix = 0;         // GELU epilogue (halved argument): every other pair by the MUFU-free polynomial
   int split = 0;            // 0: plain; 1 / 2: split-bf16 A and W (K % 64 == 0 / K == 32); 3 / 4: fp16 A, W = hi + lo fp16 (K % 64 == 0 / K == 32)
   int f16 = 0;              // plain 16-bit operands / outputs are fp16 (else bf16)
   int ln_split = 0;         // fused LayerNorm output as split-bf16 rows [hi(N) | lo(N)]
