@@ -82,6 +82,7 @@ SIGNATURES = {
     "wmk_leff_block_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "wmk_window_attention_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "wmk_linear_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "wmk_lewin_block_train_f32": (_i, [_vp, _vp, ctypes.POINTER(_vp), ctypes.POINTER(_vp), _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "wmk_comm_unique_id": (_i, [_vp]),
     "wmk_comm_create": (_i, [_vp, _i, _i, ctypes.POINTER(_vp)]),
     "wmk_comm_destroy": (_i, [_vp]),

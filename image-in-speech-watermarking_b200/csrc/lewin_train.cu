@@ -1,0 +1,468 @@
+// Training-mode LeWin block: forward with the activations its gradient needs, and the full backward pass
+// (uformerWM/model.py:937-1019 LeWinTransformerBlock, :460-471 / :523-551 projection + window attention with the
+// relative-position table and the shift mask, :683-714 LeFF), fp32 on the CUDA cores - the building block of the
+// UformerAudio training step (uformerWM/audio_uformer_stft.py:418-549).  Reference-precision kernels:
+// they pin the gradient of every operator of the block against autograd of the oracle; the tensor-core forms of the
+// two GEMM gradients (dX = dY W, dW = dY^T X) are the dense kernel run on transposed operands and are not built yet.
+//
+//   x -> LN1 (+ modulator by window position) -> q|k|v -> window attention -> proj -> + x = x1
+//   x1 -> LN2 -> linear1 -> GELU -> depthwise 3x3 -> GELU -> linear2 -> + x1 = out
+// Everything is token layout [n * H * H][C]; roll / window partition / reverse are index arithmetic (att_row).
+#include <vector>
+
+#include "uformer_kernels.cuh"
+
+namespace wmk {
+namespace {
+
+constexpr float kInvSqrt2 = 0.70710678118654752440f, kInvSqrt2Pi = 0.39894228040143267794f;
+
+__global__ void __launch_bounds__(256) gelu_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = gelu_erf(x[i]);
+}
+// dx = dy * d/dx [x Phi(x)] = dy * (Phi(x) + x phi(x))
+__global__ void __launch_bounds__(256)
+gelu_bwd_kernel(const float* __restrict__ xpre, const float* __restrict__ dy, float* __restrict__ dx, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float x = xpre[i];
+  const float cdf = 0.5f * (1.0f + erff(x * kInvSqrt2));
+  dx[i] = dy[i] * (cdf + x * kInvSqrt2Pi * expf(-0.5f * x * x));
+}
+
+// depthwise 3x3, padding 1, token layout [B][H][H][Ch]; w [Ch][9]; flip: correlation with the reversed taps (data gradient)
+__global__ void __launch_bounds__(256)
+dwconv3x3_plain_kernel(const float* __restrict__ in, float* __restrict__ out, const float* __restrict__ w,
+                       const float* __restrict__ bias, int B, int H, int Ch, int flip) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)B * H * H * Ch) return;
+  const int c = (int)(idx % Ch);
+  const size_t pix = idx / Ch;
+  const int wq = (int)(pix % H), h = (int)((pix / H) % H);
+  const size_t b = pix / ((size_t)H * H);
+  float a = bias ? bias[c] : 0.f;
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const int hh = h + t / 3 - 1, ww = wq + t % 3 - 1;
+    if (hh < 0 || hh >= H || ww < 0 || ww >= H) continue;
+    a = fmaf(in[((b * H + hh) * H + ww) * Ch + c], w[c * 9 + (flip ? 8 - t : t)], a);
+  }
+  out[idx] = a;
+}
+// dw[c][t] = sum_pixels in[pixel + tap t][c] dy[pixel][c];  db[c] = sum dy.  grid (chunks, Ch / 32), block (32 channels, 8 pixel lanes)
+__global__ void __launch_bounds__(256)
+dwconv3x3_wgrad_kernel(const float* __restrict__ in, const float* __restrict__ dy, float* __restrict__ dw,
+                       float* __restrict__ db, int B, int H, int Ch) {
+  const int c = blockIdx.y * 32 + (threadIdx.x & 31);
+  const int sub = threadIdx.x >> 5;
+  const size_t npix = (size_t)B * H * H;
+  float acc[10];
+#pragma unroll
+  for (int t = 0; t < 10; ++t) acc[t] = 0.f;
+  for (size_t pix = (size_t)blockIdx.x * 8 + sub; pix < npix; pix += (size_t)gridDim.x * 8) {
+    const int wq = (int)(pix % H), h = (int)((pix / H) % H);
+    const size_t b = pix / ((size_t)H * H);
+    const float d = dy[pix * Ch + c];
+    acc[9] += d;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int hh = h + t / 3 - 1, ww = wq + t % 3 - 1;
+      if (hh < 0 || hh >= H || ww < 0 || ww >= H) continue;
+      acc[t] = fmaf(in[((b * H + hh) * H + ww) * Ch + c], d, acc[t]);
+    }
+  }
+  __shared__ float red[8][32][10];
+#pragma unroll
+  for (int t = 0; t < 10; ++t) red[sub][threadIdx.x & 31][t] = acc[t];
+  __syncthreads();
+  if (sub == 0) {
+#pragma unroll
+    for (int t = 0; t < 10; ++t) {
+      float s = 0.f;
+      for (int q = 0; q < 8; ++q) s += red[q][threadIdx.x][t];
+      if (t < 9) atomicAdd(dw + c * 9 + t, s);
+      else atomicAdd(db + c, s);
+    }
+  }
+}
+
+// out[n] (+)= sum_m a[m][n]
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ a, float* __restrict__ out, int M, int N) {
+  const int n = blockIdx.y * 32 + (threadIdx.x & 31), sub = threadIdx.x >> 5;
+  float s = 0.f;
+  if (n < N)
+    for (int m = blockIdx.x * 8 + sub; m < M; m += gridDim.x * 8) s += a[(size_t)m * N + n];
+  __shared__ float red[8][32];
+  red[sub][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (sub == 0 && n < N) {
+    float t = 0.f;
+    for (int q = 0; q < 8; ++q) t += red[q][threadIdx.x];
+    atomicAdd(out + n, t);
+  }
+}
+
+__global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ a, float* __restrict__ at, int R, int Cc) {
+  __shared__ float t[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8)
+    if (r0 + i < R && c0 + tx < Cc) t[i][tx] = a[(size_t)(r0 + i) * Cc + c0 + tx];
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8)
+    if (c0 + i < Cc && r0 + tx < R) at[(size_t)(c0 + i) * R + r0 + tx] = t[tx][i];
+}
+
+// C[N][K] += A^T B for A [M][N], B [M][K] (weight gradient dW = dY^T X): 32 x 32 output tile per CTA, M split over grid.z
+__global__ void __launch_bounds__(256)
+gemm_tn_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C, int M, int N, int K, int m_per) {
+  __shared__ float As[32][33], Bs[32][33];
+  const int n0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+  const int m_begin = blockIdx.z * m_per, m_end = min(M, m_begin + m_per);
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // thread: outputs (n0 + ty + 8 i, k0 + tx)
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int m0 = m_begin; m0 < m_end; m0 += 32) {
+    for (int i = ty; i < 32; i += 8) {
+      const int m = m0 + i;
+      As[i][tx] = (m < m_end && n0 + tx < N) ? A[(size_t)m * N + n0 + tx] : 0.f;
+      Bs[i][tx] = (m < m_end && k0 + tx < K) ? B[(size_t)m * K + k0 + tx] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int mm = 0; mm < 32; ++mm) {
+      const float b = Bs[mm][tx];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[i] = fmaf(As[mm][ty + 8 * i], b, acc[i]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int n = n0 + ty + 8 * i, k = k0 + tx;
+    if (n < N && k < K) atomicAdd(C + (size_t)n * K + k, acc[i]);
+  }
+}
+
+// LayerNorm backward for y = xhat * gamma + beta (+ modulator[window position]): one warp per token.
+//   dx_acc[m][:] += rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma
+//   dgamma += dy * xhat, dbeta += dy, dmod[pos][:] += dy   (CTA-level partial sums, then atomics)
+__global__ void __launch_bounds__(256)
+ln_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ gamma,
+              float* __restrict__ dx_acc, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dmod,
+              int M, int C, int H, int shift) {
+  __shared__ float sg[512], sb[512];                 // the CTA's 8 tokens: partial dgamma / dbeta (C <= 512)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int c = threadIdx.x; c < C; c += 256) { sg[c] = 0.f; sb[c] = 0.f; }
+  __syncthreads();
+  const int token = blockIdx.x * 8 + warp;
+  if (token < M) {
+    const float* xr = x + (size_t)token * C;
+    const float* dr = dy + (size_t)token * C;
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += xr[c];
+    s = warp_sum(s);
+    const float mean = s / C;
+    float q = 0.f;
+    for (int c = lane; c < C; c += 32) { const float d = xr[c] - mean; q = fmaf(d, d, q); }
+    q = warp_sum(q);
+    const float rstd = rsqrtf(q / C + 1e-5f);
+    float g1 = 0.f, g2 = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float g = dr[c] * gamma[c], xh = (xr[c] - mean) * rstd;
+      g1 += g;
+      g2 = fmaf(g, xh, g2);
+    }
+    g1 = warp_sum(g1) / C;
+    g2 = warp_sum(g2) / C;
+    float* mrow = nullptr;
+    if (dmod) {
+      const int hw = token % (H * H);
+      const int h = hw / H, w = hw - h * H;
+      const int hs = (h - shift + H) % H, ws = (w - shift + H) % H;
+      mrow = dmod + (size_t)(((hs & 7) << 3) | (ws & 7)) * C;
+    }
+    for (int c = lane; c < C; c += 32) {
+      const float d = dr[c], xh = (xr[c] - mean) * rstd;
+      dx_acc[(size_t)token * C + c] += rstd * (d * gamma[c] - g1 - xh * g2);
+      atomicAdd(&sg[c], d * xh);
+      atomicAdd(&sb[c], d);
+      if (mrow) atomicAdd(mrow + c, d);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += 256) {
+    atomicAdd(dgamma + c, sg[c]);
+    atomicAdd(dbeta + c, sb[c]);
+  }
+}
+
+// ---- window attention, one CTA (64 threads, thread = query row / key row) per (window, head); q|k|v UNSCALED,
+// scores = scale * q k^T + table[rel_idx(i, j)][head] + mask
+struct AttnTrainGeom { AttGeom g; int heads; float scale; };
+
+__device__ __forceinline__ int rel_idx(int i, int j) { return ((i >> 3) - (j >> 3) + 7) * 15 + ((i & 7) - (j & 7) + 7); }
+
+template <bool BWD>
+__global__ void __launch_bounds__(64)
+attn_train_kernel(const float* __restrict__ qkv, const float* __restrict__ table, float* __restrict__ out,
+                  const float* __restrict__ dO, float* __restrict__ dqkv, float* __restrict__ dtable, AttnTrainGeom a) {
+  extern __shared__ float sm[];
+  float* Qs = sm;                  // [64][33]
+  float* Ks = Qs + 64 * 33;
+  float* Vs = Ks + 64 * 33;
+  float* P = Vs + 64 * 33;         // [64][65] probabilities (BWD: then dS)
+  float* Ds = P + 64 * 65;         // BWD: dO rows [64][33]
+  __shared__ int tok[64], rid[64];
+  const int win = blockIdx.x, head = blockIdx.y, i = threadIdx.x;
+  const int C = a.g.C;
+  {
+    int t, r;
+    att_row(a.g, win, i, t, r);
+    tok[i] = t; rid[i] = r;
+    const float* row = qkv + (size_t)t * 3 * C + head * 32;
+    for (int d = 0; d < 32; ++d) { Qs[i * 33 + d] = row[d]; Ks[i * 33 + d] = row[C + d]; Vs[i * 33 + d] = row[2 * C + d]; }
+    if (BWD) {
+      const float* drow = dO + (size_t)t * C + head * 32;
+      for (int d = 0; d < 32; ++d) Ds[i * 33 + d] = drow[d];
+    }
+  }
+  __syncthreads();
+  // row i of the scores
+  float q[32];
+#pragma unroll
+  for (int d = 0; d < 32; ++d) q[d] = Qs[i * 33 + d];
+  float mx = -INFINITY;
+  for (int j = 0; j < 64; ++j) {
+    float s = 0.f;
+#pragma unroll
+    for (int d = 0; d < 32; ++d) s = fmaf(q[d], Ks[j * 33 + d], s);
+    s = s * a.scale + table[rel_idx(i, j) * a.heads + head];
+    if (a.g.shift > 0 && rid[i] != rid[j]) s -= 100.0f;
+    P[i * 65 + j] = s;
+    mx = fmaxf(mx, s);
+  }
+  float sum = 0.f;
+  for (int j = 0; j < 64; ++j) { const float e = expf(P[i * 65 + j] - mx); P[i * 65 + j] = e; sum += e; }
+  const float inv = 1.0f / sum;
+  for (int j = 0; j < 64; ++j) P[i * 65 + j] *= inv;
+  if (!BWD) {
+    float o[32];
+#pragma unroll
+    for (int d = 0; d < 32; ++d) o[d] = 0.f;
+    for (int j = 0; j < 64; ++j) {
+      const float p = P[i * 65 + j];
+#pragma unroll
+      for (int d = 0; d < 32; ++d) o[d] = fmaf(p, Vs[j * 33 + d], o[d]);
+    }
+    float* orow = out + (size_t)tok[i] * C + head * 32;
+#pragma unroll
+    for (int d = 0; d < 32; ++d) orow[d] = o[d];
+    return;
+  }
+  __syncthreads();                 // P complete (column reads below)
+  // dV_i = sum_r P[r][i] dO_r   (thread i as key row)
+  float acc[32];
+#pragma unroll
+  for (int d = 0; d < 32; ++d) acc[d] = 0.f;
+  for (int r = 0; r < 64; ++r) {
+    const float p = P[r * 65 + i];
+#pragma unroll
+    for (int d = 0; d < 32; ++d) acc[d] = fmaf(p, Ds[r * 33 + d], acc[d]);
+  }
+  float* grow = dqkv + (size_t)tok[i] * 3 * C + head * 32;
+#pragma unroll
+  for (int d = 0; d < 32; ++d) grow[2 * C + d] = acc[d];
+  __syncthreads();                 // everyone has read P's columns before rows are overwritten by dS
+  // dS[i][j] = P[i][j] (dP[i][j] - sum_j dP[i][j] P[i][j]),  dP[i][j] = dO_i . V_j
+  float dor[32];
+#pragma unroll
+  for (int d = 0; d < 32; ++d) dor[d] = Ds[i * 33 + d];
+  float dot = 0.f;
+  float* Prow = P + i * 65;
+  // first pass: dP into registers is too large; recompute in two passes over j
+  for (int j = 0; j < 64; ++j) {
+    float dp = 0.f;
+#pragma unroll
+    for (int d = 0; d < 32; ++d) dp = fmaf(dor[d], Vs[j * 33 + d], dp);
+    dot = fmaf(dp, Prow[j], dot);
+  }
+#pragma unroll
+  for (int d = 0; d < 32; ++d) acc[d] = 0.f;            // dq_i
+  for (int j = 0; j < 64; ++j) {
+    float dp = 0.f;
+#pragma unroll
+    for (int d = 0; d < 32; ++d) dp = fmaf(dor[d], Vs[j * 33 + d], dp);
+    const float ds = Prow[j] * (dp - dot);
+    Prow[j] = ds;
+    atomicAdd(dtable + rel_idx(i, j) * a.heads + head, ds);
+#pragma unroll
+    for (int d = 0; d < 32; ++d) acc[d] = fmaf(ds, Ks[j * 33 + d], acc[d]);
+  }
+#pragma unroll
+  for (int d = 0; d < 32; ++d) grow[d] = acc[d] * a.scale;
+  __syncthreads();                 // dS complete
+  // dK_i = scale * sum_r dS[r][i] q_r
+#pragma unroll
+  for (int d = 0; d < 32; ++d) acc[d] = 0.f;
+  for (int r = 0; r < 64; ++r) {
+    const float ds = P[r * 65 + i];
+#pragma unroll
+    for (int d = 0; d < 32; ++d) acc[d] = fmaf(ds, Qs[r * 33 + d], acc[d]);
+  }
+#pragma unroll
+  for (int d = 0; d < 32; ++d) grow[C + d] = acc[d] * a.scale;
+}
+
+__global__ void __launch_bounds__(256) add_kernel(float* __restrict__ a, const float* __restrict__ b, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] += b[i];
+}
+
+int grid1(size_t n) { return (int)((n + 255) / 256); }
+
+struct Scratch {
+  cudaStream_t st;
+  std::vector<void*> ptrs;
+  float* get(size_t n) {
+    void* p = nullptr;
+    if (cudaMallocAsync(&p, n * sizeof(float), st) != cudaSuccess) return nullptr;
+    ptrs.push_back(p);
+    return reinterpret_cast<float*>(p);
+  }
+  ~Scratch() { for (void* p : ptrs) cudaFreeAsync(p, st); }
+};
+
+int linear_fwd(const float* A, const float* W, const float* b, const float* resid, float* C, int M, int N, int K, cudaStream_t st) {
+  GemmArgs g;
+  g.A = A; g.W = W; g.bias = b; g.resid = resid; g.C = C; g.M = M; g.N = N; g.K = K; g.ldc = N;
+  g.epi = resid ? EPI_BIAS_RESID : EPI_BIAS;
+  return gemm_fp32_simt(g, st);
+}
+
+// dX (+)= dY W, dW = dY^T X, db = column sums of dY;  W [N][K], X [M][K], dY [M][N]
+int linear_bwd(const float* X, const float* W, const float* dY, float* dX, bool dx_accumulate, float* dW, float* db, int M, int N, int K,
+               Scratch& sc) {
+  cudaStream_t st = sc.st;
+  if (dX) {
+    float* Wt = sc.get((size_t)N * K);               // [K][N]: the "weight" of the data-gradient GEMM
+    if (!Wt) { set_error("lewin_train: scratch allocation failed"); return WMK_ERR_ALLOC; }
+    transpose_kernel<<<dim3(cdiv(K, 32), cdiv(N, 32)), 256, 0, st>>>(W, Wt, N, K);
+    WMK_CHECK_LAUNCH("transpose_kernel");
+    WMK_TRY(linear_fwd(dY, Wt, nullptr, dx_accumulate ? dX : nullptr, dX, M, K, N, st));
+  }
+  WMK_CHECK_CUDA(cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)N * K, st));
+  WMK_CHECK_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * N, st));
+  const int splits = M >= 4096 ? 32 : (M >= 512 ? 8 : 1);
+  const int m_per = cdiv(cdiv(M, splits), 32) * 32;
+  gemm_tn_kernel<<<dim3(cdiv(N, 32), cdiv(K, 32), cdiv(M, m_per)), 256, 0, st>>>(dY, X, dW, M, N, K, m_per);
+  WMK_CHECK_LAUNCH("gemm_tn_kernel");
+  colsum_kernel<<<dim3(M >= 2048 ? 64 : 8, cdiv(N, 32)), 256, 0, st>>>(dY, db, M, N);
+  WMK_CHECK_LAUNCH("colsum_kernel");
+  return 0;
+}
+
+}  // namespace
+}  // namespace wmk
+
+using namespace wmk;
+
+// Parameter / gradient slots of one block, in this order (sizes for width C, heads = C / 32 ... any):
+enum {
+  LP_N1W = 0, LP_N1B, LP_MOD /* [64][C] or NULL */, LP_TABLE /* [225][heads] */, LP_QW /* [C][C] */, LP_QB, LP_KVW /* [2C][C] */, LP_KVB,
+  LP_PW, LP_PB, LP_N2W, LP_N2B, LP_L1W /* [4C][C] */, LP_L1B, LP_DWW /* [4C][9] */, LP_DWB, LP_L2W /* [C][4C] */, LP_L2B, LP_COUNT
+};
+
+extern "C" int wmk_lewin_block_train_f32(const float* x, const float* dout, const float* const* params, float* const* grads,
+                                         float* out, float* dx, int n, int H, int C, int heads, int shift, void* stream) {
+  WMK_REQUIRE(x && params && out && n > 0 && H >= 8 && (H & (H - 1)) == 0 && C >= 32 && C % 32 == 0 && heads * 32 == C &&
+                  (C == 32 || C == 64 || C == 128 || C == 256 || C == 512) && (shift == 0 || shift == 4) && (!dout == !dx) && (!dout == !grads),
+              "lewin_block_train: bad arguments (H a power of two >= 8, C in {32..512} = 32 heads, shift 0 or 4)");
+  for (int i = 0; i < LP_COUNT; ++i)
+    WMK_REQUIRE(i == LP_MOD || (params[i] && (!grads || grads[i])), "lewin_block_train: parameter / gradient slot %d is null", i);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (H <= 8) shift = 0;                                    // model.py:892-894
+  const int M = n * H * H, C3 = 3 * C, C4 = 4 * C;
+  Scratch sc{st};
+  float* a1 = sc.get((size_t)M * C);
+  float* wqkv = sc.get((size_t)C3 * C);
+  float* bqkv = sc.get(C3);
+  float* qkv = sc.get((size_t)M * C3);
+  float* O = sc.get((size_t)M * C);
+  float* x1 = sc.get((size_t)M * C);
+  float* a2 = sc.get((size_t)M * C);
+  float* h1p = sc.get((size_t)M * C4);
+  float* h1 = sc.get((size_t)M * C4);
+  float* h2p = sc.get((size_t)M * C4);
+  float* h2 = sc.get((size_t)M * C4);
+  if (!a1 || !wqkv || !bqkv || !qkv || !O || !x1 || !a2 || !h1p || !h1 || !h2p || !h2) {
+    set_error("lewin_block_train: scratch allocation failed");
+    return WMK_ERR_ALLOC;
+  }
+  const size_t attn_smem = (size_t)(3 * 64 * 33 + 64 * 65 + 64 * 33) * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    WMK_CHECK_CUDA(cudaFuncSetAttribute(attn_train_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem));
+    WMK_CHECK_CUDA(cudaFuncSetAttribute(attn_train_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem));
+    attr = true;
+  }
+  AttnTrainGeom ag{{C, H, shift, 31 - __builtin_clz((unsigned)(C >> 5)), 31 - __builtin_clz((unsigned)(H >> 3))}, heads,
+                   1.0f / sqrtf((float)(C / heads))};
+  const int n_windows = n * (H / 8) * (H / 8);
+  // ---------------------------------------------------------------- forward
+  launch_layernorm<float>(x, a1, params[LP_N1W], params[LP_N1B], params[LP_MOD], M, C, H, shift, st);
+  WMK_CHECK_LAUNCH("layernorm_kernel");
+  WMK_CHECK_CUDA(cudaMemcpyAsync(wqkv, params[LP_QW], sizeof(float) * (size_t)C * C, cudaMemcpyDeviceToDevice, st));
+  WMK_CHECK_CUDA(cudaMemcpyAsync(wqkv + (size_t)C * C, params[LP_KVW], sizeof(float) * 2 * (size_t)C * C, cudaMemcpyDeviceToDevice, st));
+  WMK_CHECK_CUDA(cudaMemcpyAsync(bqkv, params[LP_QB], sizeof(float) * C, cudaMemcpyDeviceToDevice, st));
+  WMK_CHECK_CUDA(cudaMemcpyAsync(bqkv + C, params[LP_KVB], sizeof(float) * 2 * C, cudaMemcpyDeviceToDevice, st));
+  WMK_TRY(linear_fwd(a1, wqkv, bqkv, nullptr, qkv, M, C3, C, st));
+  attn_train_kernel<false><<<dim3(n_windows, heads), 64, attn_smem, st>>>(qkv, params[LP_TABLE], O, nullptr, nullptr, nullptr, ag);
+  WMK_CHECK_LAUNCH("attn_train_kernel<fwd>");
+  WMK_TRY(linear_fwd(O, params[LP_PW], params[LP_PB], x, x1, M, C, C, st));
+  launch_layernorm<float>(x1, a2, params[LP_N2W], params[LP_N2B], nullptr, M, C, H, 0, st);
+  WMK_CHECK_LAUNCH("layernorm_kernel");
+  WMK_TRY(linear_fwd(a2, params[LP_L1W], params[LP_L1B], nullptr, h1p, M, C4, C, st));
+  gelu_fwd_kernel<<<grid1((size_t)M * C4), 256, 0, st>>>(h1p, h1, (size_t)M * C4);
+  dwconv3x3_plain_kernel<<<grid1((size_t)M * C4), 256, 0, st>>>(h1, h2p, params[LP_DWW], params[LP_DWB], n, H, C4, 0);
+  gelu_fwd_kernel<<<grid1((size_t)M * C4), 256, 0, st>>>(h2p, h2, (size_t)M * C4);
+  WMK_CHECK_LAUNCH("leff forward kernels");
+  WMK_TRY(linear_fwd(h2, params[LP_L2W], params[LP_L2B], x1, out, M, C, C4, st));
+  if (!dout) return 0;
+  // ---------------------------------------------------------------- backward
+  float* dh2 = sc.get((size_t)M * C4);
+  float* dh = sc.get((size_t)M * C4);
+  float* da = sc.get((size_t)M * C);
+  float* dqkv = sc.get((size_t)M * C3);
+  float* dwqkv = sc.get((size_t)C3 * C);
+  float* dbqkv = sc.get(C3);
+  if (!dh2 || !dh || !da || !dqkv || !dwqkv || !dbqkv) { set_error("lewin_block_train: scratch allocation failed"); return WMK_ERR_ALLOC; }
+  // out = x1 + h2 W2^T + b2
+  WMK_CHECK_CUDA(cudaMemcpyAsync(dx, dout, sizeof(float) * (size_t)M * C, cudaMemcpyDeviceToDevice, st));      // dx holds d(x1) for now
+  WMK_TRY(linear_bwd(h2, params[LP_L2W], dout, dh2, false, grads[LP_L2W], grads[LP_L2B], M, C, C4, sc));
+  gelu_bwd_kernel<<<grid1((size_t)M * C4), 256, 0, st>>>(h2p, dh2, dh, (size_t)M * C4);                          // d(h2p)
+  WMK_CHECK_CUDA(cudaMemsetAsync(grads[LP_DWW], 0, sizeof(float) * (size_t)C4 * 9, st));
+  WMK_CHECK_CUDA(cudaMemsetAsync(grads[LP_DWB], 0, sizeof(float) * C4, st));
+  dwconv3x3_wgrad_kernel<<<dim3(64, C4 / 32), 256, 0, st>>>(h1, dh, grads[LP_DWW], grads[LP_DWB], n, H, C4);
+  dwconv3x3_plain_kernel<<<grid1((size_t)M * C4), 256, 0, st>>>(dh, dh2, params[LP_DWW], nullptr, n, H, C4, 1);  // d(h1)
+  gelu_bwd_kernel<<<grid1((size_t)M * C4), 256, 0, st>>>(h1p, dh2, dh, (size_t)M * C4);                          // d(h1p)
+  WMK_CHECK_LAUNCH("leff backward kernels");
+  WMK_TRY(linear_bwd(a2, params[LP_L1W], dh, da, false, grads[LP_L1W], grads[LP_L1B], M, C4, C, sc));           // d(a2)
+  for (int s : {LP_N2W, LP_N2B, LP_N1W, LP_N1B}) WMK_CHECK_CUDA(cudaMemsetAsync(grads[s], 0, sizeof(float) * C, st));
+  ln_bwd_kernel<<<cdiv(M, 8), 256, 0, st>>>(x1, da, params[LP_N2W], dx, grads[LP_N2W], grads[LP_N2B], nullptr, M, C, H, 0);
+  WMK_CHECK_LAUNCH("ln_bwd_kernel");
+  // x1 = x + O Wp^T + bp
+  WMK_TRY(linear_bwd(O, params[LP_PW], dx, da, false, grads[LP_PW], grads[LP_PB], M, C, C, sc));                // d(O)
+  WMK_CHECK_CUDA(cudaMemsetAsync(grads[LP_TABLE], 0, sizeof(float) * 225 * heads, st));
+  attn_train_kernel<true><<<dim3(n_windows, heads), 64, attn_smem, st>>>(qkv, params[LP_TABLE], nullptr, da, dqkv, grads[LP_TABLE], ag);
+  WMK_CHECK_LAUNCH("attn_train_kernel<bwd>");
+  WMK_TRY(linear_bwd(a1, wqkv, dqkv, da, false, dwqkv, dbqkv, M, C3, C, sc));                                    // d(a1)
+  WMK_CHECK_CUDA(cudaMemcpyAsync(grads[LP_QW], dwqkv, sizeof(float) * (size_t)C * C, cudaMemcpyDeviceToDevice, st));
+  WMK_CHECK_CUDA(cudaMemcpyAsync(grads[LP_KVW], dwqkv + (size_t)C * C, sizeof(float) * 2 * (size_t)C * C, cudaMemcpyDeviceToDevice, st));
+  WMK_CHECK_CUDA(cudaMemcpyAsync(grads[LP_QB], dbqkv, sizeof(float) * C, cudaMemcpyDeviceToDevice, st));
+  WMK_CHECK_CUDA(cudaMemcpyAsync(grads[LP_KVB], dbqkv + C, sizeof(float) * 2 * C, cudaMemcpyDeviceToDevice, st));
+  if (params[LP_MOD]) WMK_CHECK_CUDA(cudaMemsetAsync(grads[LP_MOD], 0, sizeof(float) * 64 * C, st));
+  ln_bwd_kernel<<<cdiv(M, 8), 256, 0, st>>>(x, da, params[LP_N1W], dx, grads[LP_N1W], grads[LP_N1B],
+                                            params[LP_MOD] ? grads[LP_MOD] : nullptr, M, C, H, shift);
+  WMK_CHECK_LAUNCH("ln_bwd_kernel");
+  return 0;
+}

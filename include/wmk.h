@@ -273,6 +273,18 @@ int wmk_convT2x2_dgrad_f32(const float* dy, const float* w, float* dx, int B, in
                            int W, void* stream);
 int wmk_convT2x2_wgrad_f32(const float* x, const float* dy, float* dw, float* db, int B, int Cin,
                            int Cout, int H, int W, void* stream);
+/* ------------------------------------------------------------------------------------------
+ * Training-mode LeWin block (uformerWM/model.py:937-1019; the operator the UformerAudio training step,
+ * uformerWM/audio_uformer_stft.py:418-549, differentiates 40 times per pass): forward out = block(x) and, when dout is
+ * given, the gradient of every parameter and of x.  fp32 reference-precision kernels (CUDA cores).
+ * x, out, dout, dx: [n * H * H][C] tokens.  params / grads: 18 device pointers in the order
+ *   norm1.weight, norm1.bias, modulator.weight [64][C] (NULL: block without modulator), attn.relative_position_bias_table
+ *   [225][heads], attn.qkv.to_q.weight / .bias, attn.qkv.to_kv.weight / .bias, attn.proj.weight / .bias, norm2.weight /
+ *   .bias, mlp.linear1.0.weight / .bias, mlp.dwconv.0.weight [4C][9] / .bias, mlp.linear2.0.weight / .bias.
+ * dout = dx = grads = NULL: forward only.
+ * ------------------------------------------------------------------------------------------ */
+int wmk_lewin_block_train_f32(const float* x, const float* dout, const float* const* params, float* const* grads,
+                              float* out, float* dx, int n, int H, int C, int heads, int shift, void* stream);
 /* out = in * scale + shift: the audio_scale normalisation of spectrogram clips and its inverse
  * (uformerWM/audio_test.py:33-55,329-341,559-571,691-702); in may equal out */
 int wmk_affine_f32(const float* in, float* out, size_t n, float scale, float shift, void* stream);

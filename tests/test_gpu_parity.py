@@ -879,3 +879,45 @@ def test_ragged_corpus_equals_per_utterance_calls(models, weights):
     one = PT.embed_attack_extract(waves[1][None], tiles[1:2], m, "low_pass")
     assert torch.allclose(r["stats"][1], one["stats"][0], rtol=1e-6, atol=1e-9)
     assert torch.allclose(r["logits_att"][1], one["logits_att"][0].reshape(-1, 1, 32, 32), rtol=0, atol=2e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("geom", [(64, 2, 16, 4, True), (32, 1, 16, 0, False), (128, 4, 8, 4, True)])
+def test_lewin_block_backward_matches_oracle_autograd(geom, weights):
+    """`wmk_lewin_block_train_f32` (training-mode LeWin block: forward + the gradient of x and of all 18 parameter tensors)
+    against autograd through the oracle's `lewin_block` (bit-identical to the reference module) in float64:
+    shifted and unshifted windows, with / without modulator, H = 8 (shift disabled, `model.py:892-894`)."""
+    from image_in_speech_watermarking_b200 import uformer_train as UT
+    C, heads, H, shift, mod = geom
+    gen = torch.Generator().manual_seed(C + shift)
+    shapes = {"norm1.weight": (C,), "norm1.bias": (C,), "attn.relative_position_bias_table": (225, heads),
+              "attn.qkv.to_q.weight": (C, C), "attn.qkv.to_q.bias": (C,), "attn.qkv.to_kv.weight": (2 * C, C),
+              "attn.qkv.to_kv.bias": (2 * C,), "attn.proj.weight": (C, C), "attn.proj.bias": (C,), "norm2.weight": (C,),
+              "norm2.bias": (C,), "mlp.linear1.0.weight": (4 * C, C), "mlp.linear1.0.bias": (4 * C,),
+              "mlp.dwconv.0.weight": (4 * C, 1, 3, 3), "mlp.dwconv.0.bias": (4 * C,), "mlp.linear2.0.weight": (C, 4 * C),
+              "mlp.linear2.0.bias": (C,)}
+    if mod:
+        shapes["modulator.weight"] = (64, C)
+    params = {}
+    for k, shp in shapes.items():
+        scale = 1.0 if k.endswith("norm1.weight") or k.endswith("norm2.weight") else (0.3 if len(shp) == 1 or "table" in k or "modulator" in k else 1.5 / shp[-1] ** 0.5)
+        params[k] = torch.randn(shp, generator=gen) * scale + (1.0 if "norm" in k and k.endswith("weight") else 0.0)
+    n = 2
+    x = torch.randn(n, H * H, C, generator=gen)
+    dout = torch.randn(n, H * H, C, generator=gen)
+    # oracle in float64 with autograd
+    sd = {"b." + k: v.double().requires_grad_() for k, v in params.items()}
+    xr = x.double().requires_grad_()
+    ref = O.lewin_block(sd, "b.", xr, heads, shift)
+    ref.backward(dout.double())
+    out, dx, grads = UT.lewin_block_train(x.cuda(), {k: v for k, v in params.items()}, heads, shift, dout=dout.cuda())
+    fwd_only = UT.lewin_block_train(x.cuda(), params, heads, shift)
+    torch.cuda.synchronize()
+
+    def rel(a, b):
+        return float((a.double().cpu() - b).abs().max() / (b.abs().max() + 1e-12))
+    assert rel(out, ref.detach()) < 2e-5 and torch.equal(out, fwd_only)
+    assert rel(dx, xr.grad) < 2e-4
+    for k in params:
+        g = grads[k].reshape(params[k].shape)
+        assert rel(g, sd["b." + k].grad) < 5e-4, (k, rel(g, sd["b." + k].grad))
