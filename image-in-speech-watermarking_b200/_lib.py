@@ -83,6 +83,11 @@ SIGNATURES = {
     "wmk_window_attention_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "wmk_linear_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "wmk_lewin_block_train_f32": (_i, [_vp, _vp, ctypes.POINTER(_vp), ctypes.POINTER(_vp), _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "wmk_transpose_batched_f32": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "wmk_leaky_relu_f32": (_i, [_vp, _vp, _vp, _sz, _f, _vp]),
+    "wmk_sigmoid_f32": (_i, [_vp, _vp, _vp, _sz, _vp]),
+    "wmk_downsample_train_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "wmk_extract_head_train_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "wmk_comm_unique_id": (_i, [_vp]),
     "wmk_comm_create": (_i, [_vp, _i, _i, ctypes.POINTER(_vp)]),
     "wmk_comm_destroy": (_i, [_vp]),

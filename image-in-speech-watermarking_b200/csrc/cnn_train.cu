@@ -754,6 +754,24 @@ convT2x2_wgrad2_kernel(const float* __restrict__ x, const float* __restrict__ dy
   }
 }
 
+// any H, W (small tensors: the 8x8 / 16x16 planes of the image codec): one thread per input pixel and (ci, co) pair chunk, atomics
+__global__ void __launch_bounds__(256)
+convT2x2_wgrad_small_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw, float* __restrict__ db,
+                            int B, int Cin, int Cout, int H, int W) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)B * Cout * H * W) return;
+  const int wq = (int)(idx % W), h = (int)((idx / W) % H), co = (int)((idx / ((size_t)W * H)) % Cout);
+  const size_t b = idx / ((size_t)W * H * Cout);
+  const float* d = dy + ((b * Cout + co) * (size_t)(2 * H) + 2 * h) * (2 * W) + 2 * wq;
+  const float d00 = d[0], d01 = d[1], d10 = d[2 * W], d11 = d[2 * W + 1];
+  if (db) atomicAdd(db + co, (d00 + d01) + (d10 + d11));
+  for (int ci = 0; ci < Cin; ++ci) {
+    const float xv = x[((b * Cin + ci) * H + h) * W + wq];
+    float* o = dw + ((size_t)ci * Cout + co) * 4;
+    atomicAdd(o, xv * d00); atomicAdd(o + 1, xv * d01); atomicAdd(o + 2, xv * d10); atomicAdd(o + 3, xv * d11);
+  }
+}
+
 // ---- mean squared error (nn.MSELoss, train_modelA.py:435-445): loss += mean((a-b)^2) (fp64 accumulator),
 // grad_a = grad_scale * 2 (a - b) / n
 __global__ void __launch_bounds__(256)
@@ -1067,11 +1085,16 @@ int launch_convT_wgrad2(const float* x, const float* dy, float* dw, float* db, i
 
 extern "C" int wmk_convT2x2_wgrad_f32(const float* x, const float* dy, float* dw, float* db, int B, int Cin, int Cout, int H,
                                       int W, void* stream) {
-  WMK_REQUIRE(x && dy && dw && B > 0 && B <= 65535 && Cin > 0 && Cout > 0 && H % 16 == 0 && W % 16 == 0 && ((uintptr_t)x & 15) == 0 &&
-                  ((uintptr_t)dy & 15) == 0,
-              "convT2x2_wgrad: bad arguments (H, W must be multiples of 16, buffers 16-byte aligned)");
+  WMK_REQUIRE(x && dy && dw && B > 0 && B <= 65535 && Cin > 0 && Cout > 0 && H > 0 && W > 0, "convT2x2_wgrad: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
   ProfScope prof(FAM_SMALL, 4.0 * B * H * W * (Cin + 4 * Cout), st);
+  if (H % 16 != 0 || W % 16 != 0 || ((uintptr_t)x & 15) != 0 || ((uintptr_t)dy & 15) != 0) {      // small planes: plain atomic kernel
+    WMK_CHECK_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)Cout * Cin * 4, st));
+    if (db) WMK_CHECK_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * Cout, st));
+    convT2x2_wgrad_small_kernel<<<grid_for((size_t)B * Cout * H * W), 256, 0, st>>>(x, dy, dw, db, B, Cin, Cout, H, W);
+    WMK_CHECK_LAUNCH("convT2x2_wgrad_small_kernel");
+    return 0;
+  }
   const size_t smem = ((size_t)Cin * 256 + (size_t)Cout * 1024) * sizeof(float);
   WMK_REQUIRE(smem <= 200 * 1024, "convT2x2_wgrad: Cin=%d Cout=%d needs %zu bytes of shared memory", Cin, Cout, smem);
   static const int legacy = getenv("WMK_WGRAD_LEGACY") ? atoi(getenv("WMK_WGRAD_LEGACY")) : 0;

@@ -466,3 +466,182 @@ extern "C" int wmk_lewin_block_train_f32(const float* x, const float* dout, cons
   WMK_CHECK_LAUNCH("ln_bwd_kernel");
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------------------------------------
+// The other differentiable operators of EncoderTransformerWM (the extractor, uformerWM/model.py:1568-1583), fp32:
+// layout changes, LeakyReLU, Downsample (Conv2d 4x4 stride 2), and the strided 8x8 head convolution.
+// ------------------------------------------------------------------------------------------------------------------------
+namespace wmk {
+namespace {
+
+// batched transpose: in [n][R][Cc] -> out [n][Cc][R]
+__global__ void __launch_bounds__(256)
+transpose_batched_kernel(const float* __restrict__ a, float* __restrict__ at, int R, int Cc) {
+  __shared__ float t[32][33];
+  const float* ab = a + (size_t)blockIdx.z * R * Cc;
+  float* atb = at + (size_t)blockIdx.z * R * Cc;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8)
+    if (r0 + i < R && c0 + tx < Cc) t[i][tx] = ab[(size_t)(r0 + i) * Cc + c0 + tx];
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8)
+    if (c0 + i < Cc && r0 + tx < R) atb[(size_t)(c0 + i) * R + r0 + tx] = t[tx][i];
+}
+
+__global__ void __launch_bounds__(256)
+leaky_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ out, size_t n, float slope) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = x[i];
+  out[i] = dy ? (v > 0.f ? dy[i] : slope * dy[i]) : (v > 0.f ? v : slope * v);
+}
+
+// out = sigmoid(x) (dy == NULL), or out = dy * y (1 - y) with x = the forward OUTPUT y
+__global__ void __launch_bounds__(256)
+sigmoid_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ out, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = x[i];
+  out[i] = dy ? dy[i] * v * (1.0f - v) : 1.0f / (1.0f + expf(-v));
+}
+
+// weight [2C][C][4][4] <-> GEMM order [2C][(kh, kw, ci)]
+__global__ void __launch_bounds__(256)
+down_w_reorder_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int to_gemm) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)2 * C * C * 16) return;
+  const int tap = (int)(idx & 15), ci = (int)((idx >> 4) % C), co = (int)(idx / ((size_t)16 * C));
+  const size_t g = ((size_t)co * 16 + tap) * C + ci;           // idx is the reference layout ((co * C + ci) * 16 + tap)
+  if (to_gemm) dst[g] = src[idx];
+  else dst[idx] = src[g];
+}
+
+// dx[b][ih][iw][ci] = sum over the (oh, kh), (ow, kw) pairs with 2 oh - 1 + kh = ih, 2 ow - 1 + kw = iw of dcol[(b, oh, ow)][(kh, kw, ci)]
+__global__ void __launch_bounds__(256)
+col2im_4x4s2_kernel(const float* __restrict__ dcol, float* __restrict__ dx, int B, int H, int C) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)B * H * H * C) return;
+  const int ci = (int)(idx % C);
+  const size_t pix = idx / C;
+  const int iw = (int)(pix % H), ih = (int)((pix / H) % H);
+  const size_t b = pix / ((size_t)H * H);
+  const int Ho = H >> 1;
+  float a = 0.f;
+  for (int kh = (ih + 1) & 1; kh < 4; kh += 2) {
+    const int oh = (ih + 1 - kh) >> 1;
+    if (oh < 0 || oh >= Ho) continue;
+    for (int kw = (iw + 1) & 1; kw < 4; kw += 2) {
+      const int ow = (iw + 1 - kw) >> 1;
+      if (ow < 0 || ow >= Ho) continue;
+      a += dcol[((b * Ho + oh) * Ho + ow) * (size_t)(16 * C) + (kh * 4 + kw) * C + ci];
+    }
+  }
+  dx[idx] = a;
+}
+
+// head: Conv2d(1, 1, 8, stride = (16, 8)) over conv4 [B][64][512] -> feat [B][4][64]
+__global__ void __launch_bounds__(256)
+head_fwd_kernel(const float* __restrict__ conv4, float* __restrict__ out, const float* __restrict__ w,
+                const float* __restrict__ bias, int B) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)B * 256) return;
+  const int j = (int)(idx & 63), i = (int)((idx >> 6) & 3);
+  const size_t b = idx >> 8;
+  float a = bias[0];
+  for (int u = 0; u < 8; ++u)
+    for (int v = 0; v < 8; ++v) a = fmaf(conv4[(b * 64 + 16 * i + u) * 512 + 8 * j + v], w[u * 8 + v], a);
+  out[idx] = a;
+}
+__global__ void __launch_bounds__(256)
+head_bwd_kernel(const float* __restrict__ conv4, const float* __restrict__ dfeat, const float* __restrict__ w,
+                float* __restrict__ dconv4, float* __restrict__ dw, float* __restrict__ db, int B) {
+  // one thread per conv4 element: its gradient, and its contribution to dw (shared-memory partial sums per CTA)
+  __shared__ float sw[65];
+  if (threadIdx.x < 65) sw[threadIdx.x] = 0.f;
+  __syncthreads();
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < (size_t)B * 64 * 512) {
+    const int col = (int)(idx & 511), row = (int)((idx >> 9) & 63);
+    const size_t b = idx >> 15;
+    const int i = row >> 4, u = row & 15, j = col >> 3, v = col & 7;
+    float g = 0.f;
+    if (u < 8) {
+      const float d = dfeat[b * 256 + i * 64 + j];
+      g = d * w[u * 8 + v];
+      atomicAdd(&sw[u * 8 + v], d * conv4[idx]);
+      if (u == 0 && v == 0) atomicAdd(&sw[64], d);
+    }
+    dconv4[idx] = g;
+  }
+  __syncthreads();
+  if (threadIdx.x < 64) atomicAdd(dw + threadIdx.x, sw[threadIdx.x]);
+  if (threadIdx.x == 64) atomicAdd(db, sw[64]);
+}
+
+}  // namespace
+}  // namespace wmk
+
+extern "C" int wmk_transpose_batched_f32(const float* in, float* out, int n, int R, int Cc, void* stream) {
+  WMK_REQUIRE(in && out && n > 0 && n <= 65535 && R > 0 && Cc > 0, "transpose_batched: bad arguments");
+  transpose_batched_kernel<<<dim3(cdiv(Cc, 32), cdiv(R, 32), n), 256, 0, (cudaStream_t)stream>>>(in, out, R, Cc);
+  WMK_CHECK_LAUNCH("transpose_batched_kernel");
+  return 0;
+}
+
+/* y = LeakyReLU(x) (dy == NULL), or dx = dy * LeakyReLU'(x) */
+extern "C" int wmk_leaky_relu_f32(const float* x, const float* dy, float* out, size_t n, float slope, void* stream) {
+  WMK_REQUIRE(x && out && n > 0, "leaky_relu: bad arguments");
+  leaky_kernel<<<grid1(n), 256, 0, (cudaStream_t)stream>>>(x, dy, out, n, slope);
+  WMK_CHECK_LAUNCH("leaky_kernel");
+  return 0;
+}
+
+/* Downsample (uformerWM/model.py:763,768-775) on token layout, fp32: out [n * (H/2)^2][2C] = conv4x4s2(x [n * H * H][C]) with the
+ * reference weight w [2C][C][4][4]; with dout also dx, dw (reference layout), db. */
+extern "C" int wmk_downsample_train_f32(const float* x, const float* w, const float* b, float* out, const float* dout, float* dx,
+                                        float* dw, float* db, int n, int H, int C, void* stream) {
+  WMK_REQUIRE(x && w && b && out && n > 0 && H >= 2 && H % 2 == 0 && C % 8 == 0 && (!dout == !dx) && (!dout == !dw) && (!dout == !db),
+              "downsample_train: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Ho = H / 2, Mo = n * Ho * Ho, K = 16 * C, N = 2 * C;
+  Scratch sc{st};
+  float* col = sc.get((size_t)Mo * K);
+  float* wg = sc.get((size_t)N * K);
+  if (!col || !wg) { set_error("downsample_train: scratch allocation failed"); return WMK_ERR_ALLOC; }
+  im2col_4x4s2_kernel<float><<<cdiv((size_t)Mo * 4 * (C / 8), 256), 256, 0, st>>>(x, col, n, H, C);
+  down_w_reorder_kernel<<<grid1((size_t)N * K), 256, 0, st>>>(w, wg, C, 1);
+  WMK_CHECK_LAUNCH("downsample forward kernels");
+  WMK_TRY(linear_fwd(col, wg, b, nullptr, out, Mo, N, K, st));
+  if (!dout) return 0;
+  float* dcol = sc.get((size_t)Mo * K);
+  float* dwg = sc.get((size_t)N * K);
+  if (!dcol || !dwg) { set_error("downsample_train: scratch allocation failed"); return WMK_ERR_ALLOC; }
+  WMK_TRY(linear_bwd(col, wg, dout, dcol, false, dwg, db, Mo, N, K, sc));
+  down_w_reorder_kernel<<<grid1((size_t)N * K), 256, 0, st>>>(dwg, dw, C, 0);
+  col2im_4x4s2_kernel<<<grid1((size_t)n * H * H * C), 256, 0, st>>>(dcol, dx, n, H, C);
+  WMK_CHECK_LAUNCH("downsample backward kernels");
+  return 0;
+}
+
+/* EncoderTransformerWM.conv2 (model.py:1566,1580-1582): feat [n][256] from conv4 [n][64][512]; with dfeat also dconv4, dw [64], db [1] */
+extern "C" int wmk_extract_head_train_f32(const float* conv4, const float* w, const float* b, float* feat, const float* dfeat,
+                                          float* dconv4, float* dw, float* db, int n, void* stream) {
+  WMK_REQUIRE(conv4 && w && b && feat && n > 0 && (!dfeat == !dconv4) && (!dfeat == !dw) && (!dfeat == !db), "extract_head_train: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  head_fwd_kernel<<<cdiv((size_t)n * 256, 256), 256, 0, st>>>(conv4, feat, w, b, n);
+  WMK_CHECK_LAUNCH("head_fwd_kernel");
+  if (!dfeat) return 0;
+  WMK_CHECK_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * 64, st));
+  WMK_CHECK_CUDA(cudaMemsetAsync(db, 0, sizeof(float), st));
+  head_bwd_kernel<<<cdiv((size_t)n * 64 * 512, 256), 256, 0, st>>>(conv4, dfeat, w, dconv4, dw, db, n);
+  WMK_CHECK_LAUNCH("head_bwd_kernel");
+  return 0;
+}
+
+/* out = sigmoid(x) (dy NULL), or out = dy * y (1 - y) where x holds the forward output y */
+extern "C" int wmk_sigmoid_f32(const float* x, const float* dy, float* out, size_t n, void* stream) {
+  WMK_REQUIRE(x && out && n > 0, "sigmoid: bad arguments");
+  sigmoid_kernel<<<grid1(n), 256, 0, (cudaStream_t)stream>>>(x, dy, out, n);
+  WMK_CHECK_LAUNCH("sigmoid_kernel");
+  return 0;
+}

@@ -268,7 +268,8 @@ int wmk_mask_scale_f32(const float* in, const float* mask, float* out, size_t n,
 int wmk_conv3x3_wgrad_f32(const float* x, const float* dy, float* dw, float* db, int B, int Cin,
                           int Cout, int H, int W, void* stream);
 /* ConvTranspose2d(Cin, Cout, 2, stride=2): data gradient dx [B][Cin][H][W] from dy [B][Cout][2H][2W],
- * and weight / bias gradients dw [Cin][Cout][2][2], db [Cout] or NULL (x is [B][Cin][H][W]) */
+ * and weight / bias gradients dw [Cin][Cout][2][2], db [Cout] or NULL (x is [B][Cin][H][W]; any H, W - planes that are
+ * not multiples of 16 take a plain atomic kernel) */
 int wmk_convT2x2_dgrad_f32(const float* dy, const float* w, float* dx, int B, int Cin, int Cout, int H,
                            int W, void* stream);
 int wmk_convT2x2_wgrad_f32(const float* x, const float* dy, float* dw, float* db, int B, int Cin,
@@ -285,6 +286,21 @@ int wmk_convT2x2_wgrad_f32(const float* x, const float* dy, float* dw, float* db
  * ------------------------------------------------------------------------------------------ */
 int wmk_lewin_block_train_f32(const float* x, const float* dout, const float* const* params, float* const* grads,
                               float* out, float* dx, int n, int H, int C, int heads, int shift, void* stream);
+/* The other differentiable operators of the extractor (EncoderTransformerWM, uformerWM/model.py:1568-1583), fp32:
+ * wmk_transpose_batched_f32: in [n][R][Cc] -> out [n][Cc][R] (NCHW <-> token layout);
+ * wmk_leaky_relu_f32: out = LeakyReLU(x) (dy NULL) or out = dy * LeakyReLU'(x);
+ * wmk_downsample_train_f32: Downsample = Conv2d(C, 2C, 4, stride 2, padding 1) on tokens, reference weight layout
+ *   [2C][C][4][4]; with dout also dx, dw, db;
+ * wmk_extract_head_train_f32: conv2 = Conv2d(1, 1, 8, stride (16, 8)) on conv4 [n][64][512] -> feat [n][256]; with dfeat
+ *   also dconv4, dw [64], db [1]. */
+int wmk_transpose_batched_f32(const float* in, float* out, int n, int R, int Cc, void* stream);
+int wmk_leaky_relu_f32(const float* x, const float* dy, float* out, size_t n, float slope, void* stream);
+/* out = sigmoid(x) (dy NULL), or out = dy * y (1 - y) with x = the forward output y */
+int wmk_sigmoid_f32(const float* x, const float* dy, float* out, size_t n, void* stream);
+int wmk_downsample_train_f32(const float* x, const float* w, const float* b, float* out, const float* dout, float* dx,
+                             float* dw, float* db, int n, int H, int C, void* stream);
+int wmk_extract_head_train_f32(const float* conv4, const float* w, const float* b, float* feat, const float* dfeat,
+                               float* dconv4, float* dw, float* db, int n, void* stream);
 /* out = in * scale + shift: the audio_scale normalisation of spectrogram clips and its inverse
  * (uformerWM/audio_test.py:33-55,329-341,559-571,691-702); in may equal out */
 int wmk_affine_f32(const float* in, float* out, size_t n, float scale, float shift, void* stream);

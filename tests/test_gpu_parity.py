@@ -921,3 +921,54 @@ def test_lewin_block_backward_matches_oracle_autograd(geom, weights):
     for k in params:
         g = grads[k].reshape(params[k].shape)
         assert rel(g, sd["b." + k].grad) < 5e-4, (k, rel(g, sd["b." + k].grad))
+
+
+@pytest.mark.gpu
+def test_extractor_training_path_matches_oracle_autograd(weights):
+    """Loss 3 of the reference's training step (`audio_uformer_stft.py:482`: MSE(wm_decode(y), message)) through the whole
+    extractor - input projection, 21 LeWin blocks, 4 Downsample convs, the strided head conv, the image codec's decoder,
+    the sigmoid - on libwmk's training kernels: the loss and the gradient of EVERY extractor parameter (~450 tensors)
+    against float64 autograd through the oracle (bit-identical to the reference module), then one fused AdamW step
+    (`optim.AdamW(lr=2e-4, weight_decay=0.02)`, `audio_uformer_stft.py:234-236`) against torch.optim.AdamW."""
+    from image_in_speech_watermarking_b200 import uformer_train as UT, cnn_train as CT
+    sd32 = weights("stress")
+    names = [k for k in sd32 if (k.startswith("decoder_wm.") or k.startswith("encoder_wm.t_conv")) and sd32[k].is_floating_point()]
+    gen = torch.Generator().manual_seed(3)
+    y = torch.randn(1, 2, 128, 128, generator=gen) * 0.5
+    msg = (torch.rand(1, 1, 32, 32, generator=gen) > 0.5).float()
+    # oracle, float64, autograd
+    sd64 = {k: (v.double().requires_grad_() if k in names else v.double()) for k, v in sd32.items()}
+    wm_ref = O.wm_decode(sd64, y.double())
+    loss_ref = torch.nn.functional.mse_loss(wm_ref, msg.double())
+    loss_ref.backward()
+    # libwmk
+    params = {k: torch.nn.Parameter(sd32[k].clone().cuda()) for k in names}
+    wm, _ = UT.extractor_forward_train(params, y.cuda())
+    loss = CT.mse_loss(wm, msg.cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    assert abs(float(loss) - float(loss_ref)) < 1e-5 * float(loss_ref)
+    assert float((wm.detach().cpu().double() - wm_ref.detach()).abs().max()) < 1e-5
+    worst = ("", 0.0)
+    for k in names:
+        g, r = params[k].grad.detach().cpu().double(), sd64[k].grad
+        assert r is not None and g.shape == r.shape, k
+        e = float((g - r).abs().max() / (r.abs().max() + 1e-30))
+        if e > worst[1]:
+            worst = (k, e)
+    print("\n[extractor training path] %d parameter tensors, loss %.6f, worst relative gradient error %.2e (%s)"
+          % (len(names), float(loss), worst[1], worst[0]))
+    assert worst[1] < 2e-3, worst
+    # one AdamW step on the flat buffer vs torch.optim.AdamW on the oracle's gradients
+    plist = [params[k] for k in names]
+    opt = CT.FlatAdam(plist, lr=2e-4, weight_decay=0.02, decoupled=True)
+    opt.gather_grads()
+    opt.step()
+    ref_params = [torch.nn.Parameter(sd32[k].clone()) for k in names]
+    for p_, k in zip(ref_params, names):
+        p_.grad = sd64[k].grad.float()
+    topt = torch.optim.AdamW(ref_params, lr=2e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.02)
+    topt.step()
+    torch.cuda.synchronize()
+    for p_, q_, k in zip(plist, ref_params, names):
+        assert torch.allclose(p_.detach().cpu(), q_.detach(), rtol=1e-4, atol=2e-5), k
