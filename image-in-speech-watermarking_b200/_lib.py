@@ -88,6 +88,9 @@ SIGNATURES = {
     "wmk_sigmoid_f32": (_i, [_vp, _vp, _vp, _sz, _vp]),
     "wmk_downsample_train_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "wmk_extract_head_train_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
+    "wmk_maxpool16x8_f32": (_i, [_vp, _vp, _vp, _i, _vp]),
+    "wmk_upsample_train_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "wmk_stft_projection_adjoint_f32": (_i, [_vp, _vp, _i, _vp]),
     "wmk_comm_unique_id": (_i, [_vp]),
     "wmk_comm_create": (_i, [_vp, _i, _i, ctypes.POINTER(_vp)]),
     "wmk_comm_destroy": (_i, [_vp]),

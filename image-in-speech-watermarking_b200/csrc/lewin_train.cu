@@ -645,3 +645,210 @@ extern "C" int wmk_sigmoid_f32(const float* x, const float* dy, float* out, size
   WMK_CHECK_LAUNCH("sigmoid_kernel");
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------------------------------------
+// Embedder-side operators of the training step: the (16, 8) max-pool of the bottleneck (uformerWM/model.py:2398-2400) and the
+// ADJOINTS of the in-model ISTFT -> STFT projection (model.py:2458-2463; n_fft 255, hop 63, rectangular window, centre
+// reflect padding, one clip = 128 frames <-> 8002 samples).  Reference-precision direct-DFT kernels (255 x 128 table).
+// ------------------------------------------------------------------------------------------------------------------------
+namespace wmk {
+namespace {
+
+__global__ void __launch_bounds__(256)
+maxpool16x8_kernel(const float* __restrict__ conv4, const float* __restrict__ dy, float* __restrict__ out, int B) {
+  // forward: out [B][4][64] = max over 16 x 8 windows of conv4 [B][64][512]; backward (dy given): out = dconv4, gradient to the
+  // first maximum in scan order
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)B * 256) return;
+  const int j = (int)(idx & 63), i = (int)((idx >> 6) & 3);
+  const size_t b = idx >> 8;
+  float best = -INFINITY;
+  int arg = 0;
+  for (int r = 0; r < 16; ++r)
+    for (int c = 0; c < 8; ++c) {
+      const float v = conv4[(b * 64 + 16 * i + r) * 512 + 8 * j + c];
+      if (v > best) { best = v; arg = r * 8 + c; }
+    }
+  if (!dy) { out[idx] = best; return; }
+  for (int r = 0; r < 16; ++r)
+    for (int c = 0; c < 8; ++c) out[(b * 64 + 16 * i + r) * 512 + 8 * j + c] = (r * 8 + c == arg) ? dy[idx] : 0.f;
+}
+
+__constant__ float c_cs255[2][255];      // cos / sin (2 pi j / 255)
+int ensure_cs255() {
+  static bool done = false;
+  if (done) return 0;
+  float h[2][255];
+  for (int j = 0; j < 255; ++j) { h[0][j] = (float)cos(2.0 * M_PI * j / 255.0); h[1][j] = (float)sin(2.0 * M_PI * j / 255.0); }
+  WMK_CHECK_CUDA(cudaMemcpyToSymbol(c_cs255, h, sizeof(h)));
+  done = true;
+  return 0;
+}
+constexpr int kT = 128, kL = 8002, kPadded = 255 + 63 * (kT - 1);      // 8256
+
+// STFT adjoint: dS [B][2][128 bins][128 frames] -> gradient of the reflect-padded signal, folded back onto dwave [B][8002]
+//   X[k][t] = sum_m xp[63 t + m] (cos - i sin)(2 pi k m / 255)  =>  dxp[q] = sum_{t, k} dXr cos - dXi sin
+__global__ void __launch_bounds__(256)
+stft_adjoint_kernel(const float* __restrict__ dS, float* __restrict__ dxp, int B) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (q >= kPadded) return;
+  const float* gr = dS + (size_t)b * 2 * 128 * kT;
+  const float* gi = gr + 128 * kT;
+  float a = 0.f;
+  int t_hi = q / 63;
+  if (t_hi > kT - 1) t_hi = kT - 1;
+  for (int t = t_hi; t >= 0 && q - 63 * t <= 254; --t) {
+    const int m = q - 63 * t;
+    int idx = 0;                                   // (k m) mod 255
+    for (int k = 0; k < 128; ++k) {
+      a += gr[k * kT + t] * c_cs255[0][idx] - gi[k * kT + t] * c_cs255[1][idx];
+      idx += m;
+      if (idx >= 255) idx -= 255;
+    }
+  }
+  dxp[(size_t)b * kPadded + q] = a;
+}
+// xp[127 + j] = x[j]; xp[127 - d] = x[d], xp[127 + L - 1 + d] = x[L - 1 - d]  (d = 1 .. 127)
+__global__ void __launch_bounds__(256)
+reflect_fold_kernel(const float* __restrict__ dxp, float* __restrict__ dwave, int B) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (j >= kL) return;
+  const float* p = dxp + (size_t)b * kPadded;
+  float a = p[127 + j];
+  if (j >= 1 && j <= 127) a += p[127 - j];
+  const int d = kL - 1 - j;
+  if (d >= 1 && d <= 127) a += p[127 + kL - 1 + d];
+  dwave[(size_t)b * kL + j] = a;
+}
+// ISTFT adjoint: wave[j] = (1 / env) sum_t f_t[j + 127 - 63 t],  f_t[m] = (1/255) (Xr_0 + 2 sum_{k >= 1} Xr_k cos - Xi_k sin)
+//   => dXr_k[t] = (c_k / 255) sum_m g[63 t + m] cos,  dXi_k[t] = -(c_k / 255) sum_m g[63 t + m] sin,  g = dwave / env (0 outside)
+__global__ void __launch_bounds__(128)
+istft_adjoint_kernel(const float* __restrict__ dwave, float* __restrict__ dSpec, int B) {
+  __shared__ float g[255];
+  const int t = blockIdx.x, b = blockIdx.y, k = threadIdx.x;
+  for (int m = threadIdx.x; m < 255; m += 128) {
+    const int q = 63 * t + m, j = q - 127;
+    float v = 0.f;
+    if (j >= 0 && j < kL) {
+      int hi = q / 63;
+      if (hi > kT - 1) hi = kT - 1;
+      int lo = (q - 254 + 62) / 63;
+      if (q - 254 < 0) lo = 0;
+      v = dwave[(size_t)b * kL + j] / (float)(hi - lo + 1);
+    }
+    g[m] = v;
+  }
+  __syncthreads();
+  float ar = 0.f, ai = 0.f;
+  int idx = 0;
+  for (int m = 0; m < 255; ++m) {
+    ar = fmaf(g[m], c_cs255[0][idx], ar);
+    ai = fmaf(g[m], c_cs255[1][idx], ai);
+    idx += k;
+    if (idx >= 255) idx -= 255;
+  }
+  const float c = (k == 0 ? 1.0f : 2.0f) / 255.0f;
+  float* o = dSpec + (size_t)b * 2 * 128 * kT;
+  o[k * kT + t] = c * ar;
+  o[128 * kT + k * kT + t] = -c * ai;
+}
+
+}  // namespace
+}  // namespace wmk
+
+/* out [n][256] = MaxPool2d((16, 8)) of conv4 [n][64][512] (dy NULL), or out = dconv4 [n][64][512] from dy [n][256] */
+extern "C" int wmk_maxpool16x8_f32(const float* conv4, const float* dy, float* out, int n, void* stream) {
+  WMK_REQUIRE(conv4 && out && n > 0, "maxpool16x8: bad arguments");
+  maxpool16x8_kernel<<<cdiv((size_t)n * 256, 256), 256, 0, (cudaStream_t)stream>>>(conv4, dy, out, n);
+  WMK_CHECK_LAUNCH("maxpool16x8_kernel");
+  return 0;
+}
+
+/* Adjoint of the in-model projection s = STFT(ISTFT(y)) for one-clip spectrograms [n][2][128][128] (model.py:2458-2463):
+ * dy = ISTFT^T STFT^T ds.  scratch-free (stream-ordered temporaries). */
+extern "C" int wmk_stft_projection_adjoint_f32(const float* ds, float* dy, int n, void* stream) {
+  WMK_REQUIRE(ds && dy && n > 0 && n <= 65535, "stft_projection_adjoint: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  WMK_TRY(ensure_cs255());
+  Scratch sc{st};
+  float* dxp = sc.get((size_t)n * kPadded);
+  float* dwave = sc.get((size_t)n * kL);
+  if (!dxp || !dwave) { set_error("stft_projection_adjoint: scratch allocation failed"); return WMK_ERR_ALLOC; }
+  stft_adjoint_kernel<<<dim3(cdiv(kPadded, 256), n), 256, 0, st>>>(ds, dxp, n);
+  reflect_fold_kernel<<<dim3(cdiv(kL, 256), n), 256, 0, st>>>(dxp, dwave, n);
+  istft_adjoint_kernel<<<dim3(kT, n), 128, 0, st>>>(dwave, dy, n);
+  WMK_CHECK_LAUNCH("stft projection adjoint kernels");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------------------
+// Upsample = ConvTranspose2d(Cin, Cout, 2, stride 2) on tokens (uformerWM/model.py:794-800) as a GEMM with a pixel-shuffle
+// epilogue, and its gradients.  GEMM weight rows are (i, j, co), columns ci.
+// ------------------------------------------------------------------------------------------------------------------------
+namespace wmk {
+namespace {
+
+// reference w [Cin][Cout][2][2] <-> wg [(ij) * Cout + co][Cin]; to_gemm = 0 writes the reference layout from wg
+__global__ void __launch_bounds__(256)
+up_w_reorder_kernel(const float* __restrict__ src, float* __restrict__ dst, int Cin, int Cout, int to_gemm) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)Cin * Cout * 4) return;
+  const int ij = (int)(idx & 3), co = (int)((idx >> 2) % Cout), ci = (int)(idx / ((size_t)4 * Cout));
+  const size_t g = ((size_t)ij * Cout + co) * Cin + ci;          // idx = (ci * Cout + co) * 4 + ij is the reference layout
+  if (to_gemm) dst[g] = src[idx];
+  else dst[idx] = src[g];
+}
+// dyg [m = (b, h, w)][(ij) * Cout + co] = dout[token (b, 2h + i, 2w + j)][co]
+__global__ void __launch_bounds__(256)
+up_gather_kernel(const float* __restrict__ dout, float* __restrict__ dyg, int B, int h, int Cout) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)B * h * h * 4 * Cout) return;
+  const int co = (int)(idx % Cout), ij = (int)((idx / Cout) & 3);
+  const size_t m = idx / ((size_t)4 * Cout);
+  const int wq = (int)(m % h), hq = (int)((m / h) % h);
+  const size_t b = m / ((size_t)h * h);
+  const size_t tok = (b * 2 * h + 2 * hq + (ij >> 1)) * (size_t)(2 * h) + 2 * wq + (ij & 1);
+  dyg[idx] = dout[tok * Cout + co];
+}
+__global__ void __launch_bounds__(256) bias4_kernel(const float* __restrict__ b, float* __restrict__ b4, int Cout, int reduce) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (reduce) { if (i < Cout) b4[i] = (b[i] + b[Cout + i]) + (b[2 * Cout + i] + b[3 * Cout + i]); }      // db from the 4 Cout column sums
+  else if (i < 4 * Cout) b4[i] = b[i % Cout];
+}
+
+}  // namespace
+}  // namespace wmk
+
+/* Upsample on tokens: out [n * (2h)^2][Cout] from x [n * h * h][Cin], reference weight w [Cin][Cout][2][2]; with dout also dx, dw, db */
+extern "C" int wmk_upsample_train_f32(const float* x, const float* w, const float* b, float* out, const float* dout, float* dx,
+                                      float* dw, float* db, int n, int h, int Cin, int Cout, void* stream) {
+  WMK_REQUIRE(x && w && b && out && n > 0 && h > 0 && Cin % 4 == 0 && Cout > 0 && (!dout == !dx) && (!dout == !dw) && (!dout == !db),
+              "upsample_train: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int M = n * h * h, N = 4 * Cout;
+  Scratch sc{st};
+  float* wg = sc.get((size_t)N * Cin);
+  float* b4 = sc.get(N);
+  if (!wg || !b4) { set_error("upsample_train: scratch allocation failed"); return WMK_ERR_ALLOC; }
+  up_w_reorder_kernel<<<grid1((size_t)N * Cin), 256, 0, st>>>(w, wg, Cin, Cout, 1);
+  bias4_kernel<<<cdiv(N, 256), 256, 0, st>>>(b, b4, Cout, 0);
+  WMK_CHECK_LAUNCH("upsample forward kernels");
+  GemmArgs g;
+  g.A = x; g.W = wg; g.bias = b4; g.C = out; g.M = M; g.N = N; g.K = Cin; g.ldc = Cout;
+  g.epi = EPI_UPSAMPLE; g.up_h = h; g.up_w = h; g.up_cout = Cout;
+  WMK_TRY(gemm_fp32_simt(g, st));
+  if (!dout) return 0;
+  float* dyg = sc.get((size_t)M * N);
+  float* dwg = sc.get((size_t)N * Cin);
+  float* dbg = sc.get(N);
+  if (!dyg || !dwg || !dbg) { set_error("upsample_train: scratch allocation failed"); return WMK_ERR_ALLOC; }
+  up_gather_kernel<<<grid1((size_t)M * N), 256, 0, st>>>(dout, dyg, n, h, Cout);
+  WMK_CHECK_LAUNCH("up_gather_kernel");
+  WMK_TRY(linear_bwd(x, wg, dyg, dx, false, dwg, dbg, M, N, Cin, sc));
+  up_w_reorder_kernel<<<grid1((size_t)N * Cin), 256, 0, st>>>(dwg, dw, Cin, Cout, 0);
+  bias4_kernel<<<cdiv(Cout, 256), 256, 0, st>>>(dbg, db, Cout, 1);
+  WMK_CHECK_LAUNCH("upsample backward kernels");
+  return 0;
+}

@@ -208,3 +208,163 @@ def extractor_forward_train(sd, y):
     h = _Leaky.apply(h, 0.0)
     logits = CT._ConvT2x2.apply(h, sd[q + "t_conv2.weight"], sd[q + "t_conv2.bias"])
     return _Sigmoid.apply(logits), logits
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# The whole UformerAudio forward in training mode (`uformerWM/model.py:2384-2511`) and the reference's training step
+# (`uformerWM/audio_uformer_stft.py:418-549`: four-term loss, AdamW).  DropPath (`model.py:1004,1017`, stochastic depth
+# p <= 0.1) is the identity here: pass drop_path_rate = 0 to the reference to compare.
+# ------------------------------------------------------------------------------------------------------------------
+DEC_DEPTHS, DEC_HEADS = (8, 8, 2, 1), (16, 8, 4, 2)
+
+
+class _Upsample(torch.autograd.Function):
+    """ConvTranspose2d(Cin, Cout, 2, stride 2) on tokens (`model.py:794-800`)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        x, w, b = _c(x), _c(w), _c(b)
+        n, L, Cin = x.shape
+        h, Cout = int(round(L ** 0.5)), w.shape[1]
+        out = torch.empty((n, 4 * L, Cout), device=x.device, dtype=torch.float32)
+        _lib.check(_lib.load().wmk_upsample_train_f32(_lib.ptr(x), _lib.ptr(w), _lib.ptr(b), _lib.ptr(out), None, None, None, None,
+                                                      n, h, Cin, Cout, _lib.stream_ptr()))
+        ctx.save_for_backward(x, w, b)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, w, b = ctx.saved_tensors
+        n, L, Cin = x.shape
+        h, Cout = int(round(L ** 0.5)), w.shape[1]
+        out = torch.empty((n, 4 * L, Cout), device=x.device, dtype=torch.float32)
+        dx, dw, db = torch.empty_like(x), torch.empty_like(w), torch.empty_like(b)
+        _lib.check(_lib.load().wmk_upsample_train_f32(_lib.ptr(x), _lib.ptr(w), _lib.ptr(b), _lib.ptr(out), _lib.ptr(_c(dout)),
+                                                      _lib.ptr(dx), _lib.ptr(dw), _lib.ptr(db), n, h, Cin, Cout, _lib.stream_ptr()))
+        return dx, dw, db
+
+
+class _MaxPool16x8(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, conv4):
+        conv4 = _c(conv4)
+        n = conv4.shape[0]
+        out = torch.empty((n, 256), device=conv4.device, dtype=torch.float32)
+        _lib.check(_lib.load().wmk_maxpool16x8_f32(_lib.ptr(conv4), None, _lib.ptr(out), n, _lib.stream_ptr()))
+        ctx.save_for_backward(conv4)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        (conv4,) = ctx.saved_tensors
+        dc = torch.empty_like(conv4)
+        _lib.check(_lib.load().wmk_maxpool16x8_f32(_lib.ptr(conv4), _lib.ptr(_c(dy)), _lib.ptr(dc), conv4.shape[0], _lib.stream_ptr()))
+        return dc
+
+
+class _Projection(torch.autograd.Function):
+    """s = STFT(ISTFT(y)) on one-clip spectrograms (n, 2, 128, 128) (`model.py:2458-2463`); backward = the adjoint."""
+
+    @staticmethod
+    def forward(ctx, y):
+        from . import audio_uformer_stft as FE
+        y = _c(y)
+        n = y.shape[0]
+        wave = FE.istft_clips(y.reshape(n, 1, 2, 128, 128), 128, 8002)
+        return FE.stft_clips(wave, 1).reshape(n, 2, 128, 128)
+
+    @staticmethod
+    def backward(ctx, ds):
+        ds = _c(ds)
+        dy = torch.empty_like(ds)
+        _lib.check(_lib.load().wmk_stft_projection_adjoint_f32(_lib.ptr(ds), _lib.ptr(dy), ds.shape[0], _lib.stream_ptr()))
+        return dy
+
+
+def _blocks(sd, prefix, t, depth, heads):
+    for i in range(depth):
+        bp = "%sblocks.%d." % (prefix, i)
+        names = tuple(k for k in BLOCK_PARAMS if bp + k in sd)
+        t = _Block.apply(t, heads, 0 if i % 2 == 0 else 4, names, *[sd[bp + k] for k in names])
+    return t
+
+
+def _encoder(sd, p, y):
+    """input projection + the five encoder stages -> [conv0 .. conv4] (tokens)."""
+    from . import cnn_train as CT
+    n = y.shape[0]
+    t = CT._Conv3x3.apply(y, sd[p + "input_proj.proj.0.weight"], sd[p + "input_proj.proj.0.bias"])
+    t = _Transpose.apply(_Leaky.apply(t, 0.01).reshape(n, 32, 128 * 128))
+    convs = []
+    q = p if p else "encoder."
+    for s in range(5):
+        t = _blocks(sd, q + ("encoderlayer_%d." % s if s < 4 else "conv."), t, DEPTHS[s], HEADS[s])
+        convs.append(t)
+        if s < 4:
+            dp = "%sdowsample_%d.conv.0." % (q, s)
+            t = _Downsample.apply(t, sd[dp + "weight"], sd[dp + "bias"])
+    return convs
+
+
+def _codec_decode(sd, feat):
+    from . import cnn_train as CT
+    q = "encoder_wm."
+    h = CT._ConvT2x2.apply(feat, sd[q + "t_conv1.weight"], sd[q + "t_conv1.bias"])
+    return CT._ConvT2x2.apply(_Leaky.apply(h, 0.0), sd[q + "t_conv2.weight"], sd[q + "t_conv2.bias"])
+
+
+def uformer_forward_train(sd, x, message):
+    """`UformerAudio.forward(x, message)` -> (stft_new, noise, wm_pred, wm), differentiable w.r.t. every tensor of `sd`
+    that requires grad.  x (n, 2, 128, 128), message (n, 1, 32, 32) CUDA."""
+    from . import cnn_train as CT
+    n = x.shape[0]
+    q = "encoder_wm."
+    f = _Leaky.apply(CT._Conv3x3.apply(message, sd[q + "conv1.weight"], sd[q + "conv1.bias"]), 0.0)        # model.py:1720-1726
+    f = CT._MaxPool.apply(f)
+    f = _Leaky.apply(CT._Conv3x3.apply(f, sd[q + "conv2.weight"], sd[q + "conv2.bias"]), 0.0)
+    feat_wm = CT._MaxPool.apply(f)                                                                        # (n, 4, 8, 8)
+    feat_expand = feat_wm.reshape(n, 4, 64).repeat((1, 16, 8))                                             # (n, 64, 512)
+    convs = _encoder(sd, "", x)
+    conv4 = convs[4]
+    c4ds = _MaxPool16x8.apply(conv4).reshape(n, 4, 8, 8)                                                   # model.py:2398-2400
+    wm_pred = _Sigmoid.apply(_codec_decode(sd, feat_wm + c4ds))
+    t = torch.cat([feat_expand, conv4], dim=2)                                                             # (n, 64, 1024)
+    for s in range(4):                                                                                     # model.py:1221-1240
+        up = "decoder.upsample_%d.deconv.0." % s
+        t = _Upsample.apply(t, sd[up + "weight"], sd[up + "bias"])
+        t = torch.cat([t, convs[3 - s]], dim=-1)
+        t = _blocks(sd, "decoder.decoderlayer_%d." % s, t, DEC_DEPTHS[s], DEC_HEADS[s])
+    img = _Transpose.apply(t).reshape(n, 64, 128, 128)
+    noise = CT._Conv3x3.apply(img, sd["output_proj.proj.0.weight"], sd["output_proj.proj.0.bias"])         # model.py:857-865
+    y = x + noise
+    s_ = _Projection.apply(y)
+    s_ = CT._Conv3x3.apply(s_, sd["stft_layer.0.weight"], sd["stft_layer.0.bias"])
+    stft_new = CT._Conv3x3.apply(_Leaky.apply(s_, 0.0), sd["stft_layer.2.weight"], sd["stft_layer.2.bias"])
+    wm, _ = extractor_forward_train(sd, y)                                                                 # model.py:2508-2509 reads y
+    return stft_new, noise, wm_pred, wm
+
+
+def training_losses(sd, x, message):
+    """The four terms of `audio_uformer_stft.py:463-482`: loss1 = MSE(audio, target), loss2 = MSE(wm_gen, message),
+    loss3 = MSE(wm_decode, message), loss4 = MSE(||noise|| / batch, 1).  Returns (loss, (l1, l2, l3, l4))."""
+    from . import cnn_train as CT
+    stft_new, noise, wm_pred, wm = uformer_forward_train(sd, x, message)
+    l1 = CT.mse_loss(stft_new, x)
+    l2 = CT.mse_loss(wm_pred, message)
+    l3 = CT.mse_loss(wm, message)
+    sq = CT.mse_loss(noise, torch.zeros_like(noise)) * noise.numel()          # sum of squares by the MSE kernel
+    l4 = (torch.sqrt(sq) / noise.shape[0] - 1.0) ** 2
+    return l1 + l2 + l3 + l4, (l1, l2, l3, l4)
+
+
+def train_step(sd, optimizer, x, message):
+    """One optimisation step (`audio_uformer_stft.py:418-549`, NativeScaler without autocast = plain backward + step);
+    `optimizer` is a `cnn_train.FlatAdam(..., decoupled=True)` over the tensors of `sd`; gradients are summed over the
+    ranks through `wmk_grad_allreduce_f32` (`sharding.allreduce_grads`)."""
+    from . import sharding
+    optimizer.zero_grad()
+    loss, parts = training_losses(sd, x, message)
+    loss.backward()
+    world = sharding.allreduce_grads(optimizer.gather_grads())
+    optimizer.step(grad_scale=1.0 / world)
+    return loss.detach(), tuple(p.detach() for p in parts)

@@ -301,6 +301,15 @@ int wmk_downsample_train_f32(const float* x, const float* w, const float* b, flo
                              float* dw, float* db, int n, int H, int C, void* stream);
 int wmk_extract_head_train_f32(const float* conv4, const float* w, const float* b, float* feat, const float* dfeat,
                                float* dconv4, float* dw, float* db, int n, void* stream);
+/* Embedder-side operators of the training step: out [n][256] = MaxPool2d((16, 8)) of the bottleneck conv4 [n][64][512]
+ * (uformerWM/model.py:2398-2400; dy NULL) or its gradient out = dconv4 from dy [n][256]; and the ADJOINT of the in-model
+ * projection s = STFT(ISTFT(y)) on one-clip spectrograms [n][2][128][128] (model.py:2458-2463): dy = ISTFT^T STFT^T ds. */
+int wmk_maxpool16x8_f32(const float* conv4, const float* dy, float* out, int n, void* stream);
+/* Upsample = ConvTranspose2d(Cin, Cout, 2, stride 2) on tokens (model.py:794-800): out [n * (2h)^2][Cout] from x [n * h * h][Cin],
+ * reference weight layout [Cin][Cout][2][2]; with dout also dx, dw, db */
+int wmk_upsample_train_f32(const float* x, const float* w, const float* b, float* out, const float* dout, float* dx,
+                           float* dw, float* db, int n, int h, int Cin, int Cout, void* stream);
+int wmk_stft_projection_adjoint_f32(const float* ds, float* dy, int n, void* stream);
 /* out = in * scale + shift: the audio_scale normalisation of spectrogram clips and its inverse
  * (uformerWM/audio_test.py:33-55,329-341,559-571,691-702); in may equal out */
 int wmk_affine_f32(const float* in, float* out, size_t n, float scale, float shift, void* stream);

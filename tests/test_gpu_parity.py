@@ -972,3 +972,43 @@ def test_extractor_training_path_matches_oracle_autograd(weights):
     torch.cuda.synchronize()
     for p_, q_, k in zip(plist, ref_params, names):
         assert torch.allclose(p_.detach().cpu(), q_.detach(), rtol=1e-4, atol=2e-5), k
+
+
+@pytest.mark.gpu
+def test_uformer_training_step_matches_oracle_autograd(weights):
+    """The reference's UformerAudio training step (`audio_uformer_stft.py:452-482`: forward, 4-term loss, backward) on
+    libwmk's training kernels: all four losses and the gradient of EVERY parameter tensor of the model (DropPath off)
+    against float64 autograd through the oracle's forward (bit-identical to the reference module)."""
+    from image_in_speech_watermarking_b200 import uformer_train as UT
+    sd32 = weights("stress")
+    names = [k for k in sd32 if sd32[k].is_floating_point()]
+    gen = torch.Generator().manual_seed(5)
+    x = torch.randn(1, 2, 128, 128, generator=gen) * 0.5
+    msg = (torch.rand(1, 1, 32, 32, generator=gen) > 0.5).float()
+    sd64 = {k: (v.double().requires_grad_() if k in names else v) for k, v in sd32.items()}
+    s, noise, wm_pred, wm = O.forward(sd64, x.double(), msg.double())
+    mse = torch.nn.functional.mse_loss
+    nn_ = torch.norm(noise) / noise.shape[0]
+    ref = [mse(s, x.double()), mse(wm_pred, msg.double()), mse(wm, msg.double()), mse(nn_, torch.ones_like(nn_))]
+    sum(ref).backward()
+    params = {k: torch.nn.Parameter(sd32[k].clone().cuda()) for k in names}
+    loss, parts = UT.training_losses(params, x.cuda(), msg.cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    for a, b in zip(parts, ref):
+        assert abs(float(a) - float(b)) < 2e-5 * abs(float(b)) + 1e-7, (float(a), float(b))
+    worst = ("", 0.0)
+    used = 0
+    for k in names:
+        r = sd64[k].grad
+        if r is None:
+            assert params[k].grad is None, k          # tensors the forward does not touch
+            continue
+        used += 1
+        g = params[k].grad.detach().cpu().double()
+        e = float((g - r).abs().max() / (r.abs().max() + 1e-30))
+        if e > worst[1]:
+            worst = (k, e)
+    print("\n[UformerAudio training step] %d parameter tensors with gradients, losses %s, worst relative gradient error %.2e (%s)"
+          % (used, [round(float(p), 6) for p in parts], worst[1], worst[0]))
+    assert worst[1] < 2e-3, worst
