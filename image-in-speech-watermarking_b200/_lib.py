@@ -82,7 +82,7 @@ SIGNATURES = {
     "wmk_leff_block_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "wmk_window_attention_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "wmk_linear_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
-    "wmk_lewin_block_train_f32": (_i, [_vp, _vp, ctypes.POINTER(_vp), ctypes.POINTER(_vp), _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "wmk_lewin_block_train_f32": (_i, [_vp, _vp, ctypes.POINTER(_vp), ctypes.POINTER(_vp), _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "wmk_transpose_batched_f32": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "wmk_leaky_relu_f32": (_i, [_vp, _vp, _vp, _sz, _f, _vp]),
     "wmk_sigmoid_f32": (_i, [_vp, _vp, _vp, _sz, _vp]),

@@ -318,6 +318,17 @@ __global__ void __launch_bounds__(256) add_kernel(float* __restrict__ a, const f
   if (i < n) a[i] += b[i];
 }
 
+// DropPath (stochastic depth, model.py:1016-1017) with a GIVEN per-sample factor s[b] in {0, 1 / keep}:
+// out = base + s[b] * br (base NULL: out = s[b] * br); rows of sample b are m in [b * rows, (b + 1) * rows)
+__global__ void __launch_bounds__(256)
+row_scale_add_kernel(const float* __restrict__ base, const float* __restrict__ br, const float* __restrict__ s, float* __restrict__ out,
+                     size_t n, size_t per_sample) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = s[i / per_sample] * br[i];
+  out[i] = base ? base[i] + v : v;
+}
+
 int grid1(size_t n) { return (int)((n + 255) / 256); }
 
 struct Scratch {
@@ -373,7 +384,8 @@ enum {
 };
 
 extern "C" int wmk_lewin_block_train_f32(const float* x, const float* dout, const float* const* params, float* const* grads,
-                                         float* out, float* dx, int n, int H, int C, int heads, int shift, void* stream) {
+                                         float* out, float* dx, int n, int H, int C, int heads, int shift, const float* drop_scales,
+                                         void* stream) {
   WMK_REQUIRE(x && params && out && n > 0 && H >= 8 && (H & (H - 1)) == 0 && C >= 32 && C % 32 == 0 && heads * 32 == C &&
                   (C == 32 || C == 64 || C == 128 || C == 256 || C == 512) && (shift == 0 || shift == 4) && (!dout == !dx) && (!dout == !grads),
               "lewin_block_train: bad arguments (H a power of two >= 8, C in {32..512} = 32 heads, shift 0 or 4)");
@@ -418,7 +430,17 @@ extern "C" int wmk_lewin_block_train_f32(const float* x, const float* dout, cons
   WMK_TRY(linear_fwd(a1, wqkv, bqkv, nullptr, qkv, M, C3, C, st));
   attn_train_kernel<false><<<dim3(n_windows, heads), 64, attn_smem, st>>>(qkv, params[LP_TABLE], O, nullptr, nullptr, nullptr, ag);
   WMK_CHECK_LAUNCH("attn_train_kernel<fwd>");
-  WMK_TRY(linear_fwd(O, params[LP_PW], params[LP_PB], x, x1, M, C, C, st));
+  const size_t per_sample = (size_t)H * H * C;
+  float* br = nullptr;                                      // DropPath: branch output before its per-sample factor
+  if (drop_scales) {
+    br = sc.get((size_t)M * C);
+    if (!br) { set_error("lewin_block_train: scratch allocation failed"); return WMK_ERR_ALLOC; }
+    WMK_TRY(linear_fwd(O, params[LP_PW], params[LP_PB], nullptr, br, M, C, C, st));
+    row_scale_add_kernel<<<grid1((size_t)M * C), 256, 0, st>>>(x, br, drop_scales, x1, (size_t)M * C, per_sample);
+    WMK_CHECK_LAUNCH("row_scale_add_kernel");
+  } else {
+    WMK_TRY(linear_fwd(O, params[LP_PW], params[LP_PB], x, x1, M, C, C, st));
+  }
   launch_layernorm<float>(x1, a2, params[LP_N2W], params[LP_N2B], nullptr, M, C, H, 0, st);
   WMK_CHECK_LAUNCH("layernorm_kernel");
   WMK_TRY(linear_fwd(a2, params[LP_L1W], params[LP_L1B], nullptr, h1p, M, C4, C, st));
@@ -426,7 +448,13 @@ extern "C" int wmk_lewin_block_train_f32(const float* x, const float* dout, cons
   dwconv3x3_plain_kernel<<<grid1((size_t)M * C4), 256, 0, st>>>(h1, h2p, params[LP_DWW], params[LP_DWB], n, H, C4, 0);
   gelu_fwd_kernel<<<grid1((size_t)M * C4), 256, 0, st>>>(h2p, h2, (size_t)M * C4);
   WMK_CHECK_LAUNCH("leff forward kernels");
-  WMK_TRY(linear_fwd(h2, params[LP_L2W], params[LP_L2B], x1, out, M, C, C4, st));
+  if (drop_scales) {
+    WMK_TRY(linear_fwd(h2, params[LP_L2W], params[LP_L2B], nullptr, br, M, C, C4, st));
+    row_scale_add_kernel<<<grid1((size_t)M * C), 256, 0, st>>>(x1, br, drop_scales + n, out, (size_t)M * C, per_sample);
+    WMK_CHECK_LAUNCH("row_scale_add_kernel");
+  } else {
+    WMK_TRY(linear_fwd(h2, params[LP_L2W], params[LP_L2B], x1, out, M, C, C4, st));
+  }
   if (!dout) return 0;
   // ---------------------------------------------------------------- backward
   float* dh2 = sc.get((size_t)M * C4);
@@ -438,7 +466,13 @@ extern "C" int wmk_lewin_block_train_f32(const float* x, const float* dout, cons
   if (!dh2 || !dh || !da || !dqkv || !dwqkv || !dbqkv) { set_error("lewin_block_train: scratch allocation failed"); return WMK_ERR_ALLOC; }
   // out = x1 + h2 W2^T + b2
   WMK_CHECK_CUDA(cudaMemcpyAsync(dx, dout, sizeof(float) * (size_t)M * C, cudaMemcpyDeviceToDevice, st));      // dx holds d(x1) for now
-  WMK_TRY(linear_bwd(h2, params[LP_L2W], dout, dh2, false, grads[LP_L2W], grads[LP_L2B], M, C, C4, sc));
+  const float* dbranch = dout;                              // gradient of the MLP branch output
+  if (drop_scales) {
+    row_scale_add_kernel<<<grid1((size_t)M * C), 256, 0, st>>>(nullptr, dout, drop_scales + n, br, (size_t)M * C, per_sample);
+    WMK_CHECK_LAUNCH("row_scale_add_kernel");
+    dbranch = br;
+  }
+  WMK_TRY(linear_bwd(h2, params[LP_L2W], dbranch, dh2, false, grads[LP_L2W], grads[LP_L2B], M, C, C4, sc));
   gelu_bwd_kernel<<<grid1((size_t)M * C4), 256, 0, st>>>(h2p, dh2, dh, (size_t)M * C4);                          // d(h2p)
   WMK_CHECK_CUDA(cudaMemsetAsync(grads[LP_DWW], 0, sizeof(float) * (size_t)C4 * 9, st));
   WMK_CHECK_CUDA(cudaMemsetAsync(grads[LP_DWB], 0, sizeof(float) * C4, st));
@@ -451,7 +485,13 @@ extern "C" int wmk_lewin_block_train_f32(const float* x, const float* dout, cons
   ln_bwd_kernel<<<cdiv(M, 8), 256, 0, st>>>(x1, da, params[LP_N2W], dx, grads[LP_N2W], grads[LP_N2B], nullptr, M, C, H, 0);
   WMK_CHECK_LAUNCH("ln_bwd_kernel");
   // x1 = x + O Wp^T + bp
-  WMK_TRY(linear_bwd(O, params[LP_PW], dx, da, false, grads[LP_PW], grads[LP_PB], M, C, C, sc));                // d(O)
+  dbranch = dx;                                             // gradient of the attention branch output
+  if (drop_scales) {
+    row_scale_add_kernel<<<grid1((size_t)M * C), 256, 0, st>>>(nullptr, dx, drop_scales, br, (size_t)M * C, per_sample);
+    WMK_CHECK_LAUNCH("row_scale_add_kernel");
+    dbranch = br;
+  }
+  WMK_TRY(linear_bwd(O, params[LP_PW], dbranch, da, false, grads[LP_PW], grads[LP_PB], M, C, C, sc));           // d(O)
   WMK_CHECK_CUDA(cudaMemsetAsync(grads[LP_TABLE], 0, sizeof(float) * 225 * heads, st));
   attn_train_kernel<true><<<dim3(n_windows, heads), 64, attn_smem, st>>>(qkv, params[LP_TABLE], nullptr, da, dqkv, grads[LP_TABLE], ag);
   WMK_CHECK_LAUNCH("attn_train_kernel<bwd>");

@@ -16,8 +16,9 @@ BLOCK_PARAMS = ("norm1.weight", "norm1.bias", "modulator.weight", "attn.relative
                 "mlp.linear2.0.bias")
 
 
-def lewin_block_train(x, params, heads, shift, dout=None):
+def lewin_block_train(x, params, heads, shift, dout=None, drop_scales=None):
     """x (n, H*H, C) CUDA fp32; params: {suffix: tensor} of one block (reference shapes; 'modulator.weight' optional).
+    drop_scales (2, n): DropPath factors {0, 1 / keep} of the attention / MLP branch per sample (None: no DropPath).
     Returns out, or (out, dx, {suffix: gradient}) when `dout` is given."""
     lib = _lib.load()
     if not x.is_cuda:
@@ -41,14 +42,19 @@ def lewin_block_train(x, params, heads, shift, dout=None):
             grads[k] = torch.empty_like(t)
             gs[i] = grads[k].data_ptr()
     out = torch.empty_like(x)
+    ds = None
+    if drop_scales is not None:
+        ds = drop_scales.detach().contiguous().float().cuda()
+        if ds.shape != (2, n):
+            raise ValueError("drop_scales must be (2, %d)" % n)
     if dout is None:
         _lib.check(lib.wmk_lewin_block_train_f32(_lib.ptr(x), None, ps, None, _lib.ptr(out), None, n, H, C, heads, shift,
-                                                 _lib.stream_ptr()))
+                                                 _lib.ptr(ds), _lib.stream_ptr()))
         return out
     dout = dout.detach().contiguous().float()
     dx = torch.empty_like(x)
     _lib.check(lib.wmk_lewin_block_train_f32(_lib.ptr(x), _lib.ptr(dout), ps, gs, _lib.ptr(out), _lib.ptr(dx), n, H, C, heads,
-                                             shift, _lib.stream_ptr()))
+                                             shift, _lib.ptr(ds), _lib.stream_ptr()))
     return out, dx, grads
 
 
@@ -66,18 +72,18 @@ def _c(t):
 
 class _Block(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, heads, shift, names, *tensors):
-        out = lewin_block_train(x, dict(zip(names, tensors)), heads, shift)
+    def forward(ctx, x, heads, shift, names, scales, *tensors):
+        out = lewin_block_train(x, dict(zip(names, tensors)), heads, shift, drop_scales=scales)
         ctx.save_for_backward(x, *tensors)
-        ctx.meta = (heads, shift, names)
+        ctx.meta = (heads, shift, names, scales)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         x, *tensors = ctx.saved_tensors
-        heads, shift, names = ctx.meta
-        _, dx, grads = lewin_block_train(x, dict(zip(names, tensors)), heads, shift, dout=dout)
-        return (dx, None, None, None) + tuple(grads[k].reshape(t.shape) for k, t in zip(names, tensors))
+        heads, shift, names, scales = ctx.meta
+        _, dx, grads = lewin_block_train(x, dict(zip(names, tensors)), heads, shift, dout=dout, drop_scales=scales)
+        return (dx, None, None, None, None) + tuple(grads[k].reshape(t.shape) for k, t in zip(names, tensors))
 
 
 class _Downsample(torch.autograd.Function):
@@ -183,9 +189,10 @@ class _Transpose(torch.autograd.Function):
         return _Transpose.apply(dy)
 
 
-def extractor_forward_train(sd, y):
+def extractor_forward_train(sd, y, drop_scales=None):
     """`UformerAudio.wm_decode(y)` (`model.py:2379-2382`) in training mode.  sd: {reference state_dict name: CUDA tensor}
-    (those that require grad receive gradients); y (n, 2, 128, 128) CUDA.  Returns (wm, logits), differentiable."""
+    (those that require grad receive gradients); y (n, 2, 128, 128) CUDA; drop_scales: {block prefix: (2, n) DropPath
+    factors} (None / missing prefix: no DropPath).  Returns (wm, logits), differentiable."""
     from . import cnn_train as CT
     p = "decoder_wm."
     n = y.shape[0]
@@ -198,7 +205,7 @@ def extractor_forward_train(sd, y):
         for i in range(DEPTHS[s]):
             bp = "%sblocks.%d." % (lp, i)
             names = tuple(k for k in BLOCK_PARAMS if bp + k in sd)
-            t = _Block.apply(t, HEADS[s], 0 if i % 2 == 0 else 4, names, *[sd[bp + k] for k in names])
+            t = _Block.apply(t, HEADS[s], 0 if i % 2 == 0 else 4, names, (drop_scales or {}).get(bp), *[sd[bp + k] for k in names])
         if s < 4:
             dp = "%sdowsample_%d.conv.0." % (p, s)
             t = _Downsample.apply(t, sd[dp + "weight"], sd[dp + "bias"])
@@ -281,15 +288,15 @@ class _Projection(torch.autograd.Function):
         return dy
 
 
-def _blocks(sd, prefix, t, depth, heads):
+def _blocks(sd, prefix, t, depth, heads, drop_scales=None):
     for i in range(depth):
         bp = "%sblocks.%d." % (prefix, i)
         names = tuple(k for k in BLOCK_PARAMS if bp + k in sd)
-        t = _Block.apply(t, heads, 0 if i % 2 == 0 else 4, names, *[sd[bp + k] for k in names])
+        t = _Block.apply(t, heads, 0 if i % 2 == 0 else 4, names, (drop_scales or {}).get(bp), *[sd[bp + k] for k in names])
     return t
 
 
-def _encoder(sd, p, y):
+def _encoder(sd, p, y, drop_scales=None):
     """input projection + the five encoder stages -> [conv0 .. conv4] (tokens)."""
     from . import cnn_train as CT
     n = y.shape[0]
@@ -298,7 +305,7 @@ def _encoder(sd, p, y):
     convs = []
     q = p if p else "encoder."
     for s in range(5):
-        t = _blocks(sd, q + ("encoderlayer_%d." % s if s < 4 else "conv."), t, DEPTHS[s], HEADS[s])
+        t = _blocks(sd, q + ("encoderlayer_%d." % s if s < 4 else "conv."), t, DEPTHS[s], HEADS[s], drop_scales)
         convs.append(t)
         if s < 4:
             dp = "%sdowsample_%d.conv.0." % (q, s)
@@ -313,9 +320,10 @@ def _codec_decode(sd, feat):
     return CT._ConvT2x2.apply(_Leaky.apply(h, 0.0), sd[q + "t_conv2.weight"], sd[q + "t_conv2.bias"])
 
 
-def uformer_forward_train(sd, x, message):
+def uformer_forward_train(sd, x, message, drop_scales=None):
     """`UformerAudio.forward(x, message)` -> (stft_new, noise, wm_pred, wm), differentiable w.r.t. every tensor of `sd`
-    that requires grad.  x (n, 2, 128, 128), message (n, 1, 32, 32) CUDA."""
+    that requires grad.  x (n, 2, 128, 128), message (n, 1, 32, 32) CUDA; drop_scales {block prefix: (2, n)}: the DropPath
+    factors of this step (`draw_drop_scales`; None = stochastic depth off)."""
     from . import cnn_train as CT
     n = x.shape[0]
     q = "encoder_wm."
@@ -324,7 +332,7 @@ def uformer_forward_train(sd, x, message):
     f = _Leaky.apply(CT._Conv3x3.apply(f, sd[q + "conv2.weight"], sd[q + "conv2.bias"]), 0.0)
     feat_wm = CT._MaxPool.apply(f)                                                                        # (n, 4, 8, 8)
     feat_expand = feat_wm.reshape(n, 4, 64).repeat((1, 16, 8))                                             # (n, 64, 512)
-    convs = _encoder(sd, "", x)
+    convs = _encoder(sd, "", x, drop_scales)
     conv4 = convs[4]
     c4ds = _MaxPool16x8.apply(conv4).reshape(n, 4, 8, 8)                                                   # model.py:2398-2400
     wm_pred = _Sigmoid.apply(_codec_decode(sd, feat_wm + c4ds))
@@ -333,22 +341,52 @@ def uformer_forward_train(sd, x, message):
         up = "decoder.upsample_%d.deconv.0." % s
         t = _Upsample.apply(t, sd[up + "weight"], sd[up + "bias"])
         t = torch.cat([t, convs[3 - s]], dim=-1)
-        t = _blocks(sd, "decoder.decoderlayer_%d." % s, t, DEC_DEPTHS[s], DEC_HEADS[s])
+        t = _blocks(sd, "decoder.decoderlayer_%d." % s, t, DEC_DEPTHS[s], DEC_HEADS[s], drop_scales)
     img = _Transpose.apply(t).reshape(n, 64, 128, 128)
     noise = CT._Conv3x3.apply(img, sd["output_proj.proj.0.weight"], sd["output_proj.proj.0.bias"])         # model.py:857-865
     y = x + noise
     s_ = _Projection.apply(y)
     s_ = CT._Conv3x3.apply(s_, sd["stft_layer.0.weight"], sd["stft_layer.0.bias"])
     stft_new = CT._Conv3x3.apply(_Leaky.apply(s_, 0.0), sd["stft_layer.2.weight"], sd["stft_layer.2.bias"])
-    wm, _ = extractor_forward_train(sd, y)                                                                 # model.py:2508-2509 reads y
+    wm, _ = extractor_forward_train(sd, y, drop_scales)                                                    # model.py:2508-2509 reads y
     return stft_new, noise, wm_pred, wm
 
 
-def training_losses(sd, x, message):
+def drop_path_rates(rate=0.1):
+    """{block prefix: DropPath probability} as the reference constructors assign them (`model.py:1123-1125,1268-1270,
+    1454-1456`): encoder / extractor blocks linspace(0, rate) over their first four stages and `rate` in the fifth, the
+    decoder's the reversed encoder list."""
+    enc = [float(v) for v in torch.linspace(0, rate, sum(DEPTHS[:4]))]
+    out, k = {}, 0
+    for s in range(5):
+        for i in range(DEPTHS[s]):
+            r = enc[k + i] if s < 4 else rate
+            for p in ("encoder.", "decoder_wm."):
+                out["%s%sblocks.%d." % (p, "encoderlayer_%d." % s if s < 4 else "conv.", i)] = r
+        k += DEPTHS[s] if s < 4 else 0
+    dec, k = enc[::-1], 0
+    for s in range(4):
+        for i in range(DEC_DEPTHS[s]):
+            out["decoder.decoderlayer_%d.blocks.%d." % (s, i)] = dec[k + i]
+        k += DEC_DEPTHS[s]
+    return out
+
+
+def draw_drop_scales(n, rate=0.1, generator=None):
+    """One step's DropPath factors: per block (2, n) values in {0, 1 / keep} (Bernoulli(keep) per sample and branch)."""
+    out = {}
+    for p, r in drop_path_rates(rate).items():
+        if r > 0.0:
+            keep = 1.0 - r
+            out[p] = torch.bernoulli(torch.full((2, n), keep), generator=generator) / keep
+    return out
+
+
+def training_losses(sd, x, message, drop_scales=None):
     """The four terms of `audio_uformer_stft.py:463-482`: loss1 = MSE(audio, target), loss2 = MSE(wm_gen, message),
     loss3 = MSE(wm_decode, message), loss4 = MSE(||noise|| / batch, 1).  Returns (loss, (l1, l2, l3, l4))."""
     from . import cnn_train as CT
-    stft_new, noise, wm_pred, wm = uformer_forward_train(sd, x, message)
+    stft_new, noise, wm_pred, wm = uformer_forward_train(sd, x, message, drop_scales)
     l1 = CT.mse_loss(stft_new, x)
     l2 = CT.mse_loss(wm_pred, message)
     l3 = CT.mse_loss(wm, message)
@@ -357,13 +395,13 @@ def training_losses(sd, x, message):
     return l1 + l2 + l3 + l4, (l1, l2, l3, l4)
 
 
-def train_step(sd, optimizer, x, message):
+def train_step(sd, optimizer, x, message, drop_path_rate=0.1):
     """One optimisation step (`audio_uformer_stft.py:418-549`, NativeScaler without autocast = plain backward + step);
     `optimizer` is a `cnn_train.FlatAdam(..., decoupled=True)` over the tensors of `sd`; gradients are summed over the
     ranks through `wmk_grad_allreduce_f32` (`sharding.allreduce_grads`)."""
     from . import sharding
     optimizer.zero_grad()
-    loss, parts = training_losses(sd, x, message)
+    loss, parts = training_losses(sd, x, message, draw_drop_scales(x.shape[0], drop_path_rate) if drop_path_rate > 0 else None)
     loss.backward()
     world = sharding.allreduce_grads(optimizer.gather_grads())
     optimizer.step(grad_scale=1.0 / world)

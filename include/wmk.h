@@ -282,10 +282,12 @@ int wmk_convT2x2_wgrad_f32(const float* x, const float* dy, float* dw, float* db
  *   norm1.weight, norm1.bias, modulator.weight [64][C] (NULL: block without modulator), attn.relative_position_bias_table
  *   [225][heads], attn.qkv.to_q.weight / .bias, attn.qkv.to_kv.weight / .bias, attn.proj.weight / .bias, norm2.weight /
  *   .bias, mlp.linear1.0.weight / .bias, mlp.dwconv.0.weight [4C][9] / .bias, mlp.linear2.0.weight / .bias.
- * dout = dx = grads = NULL: forward only.
+ * dout = dx = grads = NULL: forward only.  drop_scales (NULL: none): DropPath (model.py:1016-1017) with GIVEN per-sample
+ * factors in {0, 1 / keep}, [2][n] = the attention branch's, then the MLP branch's.
  * ------------------------------------------------------------------------------------------ */
 int wmk_lewin_block_train_f32(const float* x, const float* dout, const float* const* params, float* const* grads,
-                              float* out, float* dx, int n, int H, int C, int heads, int shift, void* stream);
+                              float* out, float* dx, int n, int H, int C, int heads, int shift,
+                              const float* drop_scales, void* stream);
 /* The other differentiable operators of the extractor (EncoderTransformerWM, uformerWM/model.py:1568-1583), fp32:
  * wmk_transpose_batched_f32: in [n][R][Cc] -> out [n][Cc][R] (NCHW <-> token layout);
  * wmk_leaky_relu_f32: out = LeakyReLU(x) (dy NULL) or out = dy * LeakyReLU'(x);

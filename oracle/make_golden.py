@@ -229,6 +229,63 @@ def train_frontend_fixture():
     print("train_frontend.npz", tuple(d0.shape), tuple(d10.shape), tuple(d01.shape), float(mn10), float(mx10))
 
 
+def uformer_train_fixture():
+    """One training step of the UNMODIFIED reference `UformerAudio` in train mode (`audio_uformer_stft.py:452-482`: forward
+    with stochastic depth - the reference's default drop_path_rate 0.1 -, the four losses, backward) on two clips.  The
+    DropPath factors each block drew (mask / keep per sample, attention branch then MLP branch) are recovered with
+    forward hooks on the DropPath modules so that the CUDA path can replay them.  275 MB of gradients are not committed:
+    every tensor of <= 4096 elements is stored whole, larger ones as their L2 norm, their sum, 256 elements at seeded
+    positions and a projection on a seeded +-1 vector."""
+    m, sd = reference_module("stress", 0)
+    m.train()
+    g = torch.Generator().manual_seed(77)
+    x = torch.randn(2, 2, 128, 128, generator=g) * 0.5
+    msg = (torch.rand(2, 1, 32, 32, generator=g) > 0.5).float()
+    scales = {}
+
+    def make_hook(name):
+        def hook(mod, inp, out):
+            a, b = inp[0].detach(), out.detach()
+            n = a.shape[0]
+            idx = a.reshape(n, -1).abs().argmax(1)                 # a non-zero element of every sample
+            num, den = b.reshape(n, -1)[torch.arange(n), idx], a.reshape(n, -1)[torch.arange(n), idx]
+            scales.setdefault(name, []).append((num / den).numpy().astype(np.float32))
+        return hook
+    for name, mod in m.named_modules():
+        if type(mod).__name__ == "_DropPath" and mod.drop_prob > 0:
+            mod.register_forward_hook(make_hook(name[:-len("drop_path")]))
+    torch.manual_seed(13)
+    with shims.legacy_torch_spectral():
+        audio, audio_noise, wm_gen, wm_decode = m(x, msg)
+    mse = torch.nn.MSELoss()
+    loss1 = mse(audio, x)                                          # audio_uformer_stft.py:463
+    noise_norm = torch.norm(audio_noise) / audio_noise.shape[0]    # :471
+    loss4 = mse(noise_norm, torch.ones_like(noise_norm))
+    loss2 = mse(wm_gen, msg)                                       # :474
+    loss3 = mse(wm_decode, msg)                                    # :476
+    (loss1 + loss2 + loss3 + loss4).backward()
+    out = dict(x=x.numpy(), msg=msg.numpy(), losses=np.array([loss1.item(), loss2.item(), loss3.item(), loss4.item()]))
+    for k, v in scales.items():
+        assert len(v) == 2, (k, len(v))
+        out["drop." + k] = np.stack(v)                            # (2 branches, n)
+    rng = np.random.default_rng(2024)
+    names = []
+    for k, p_ in m.named_parameters():
+        if p_.grad is None:
+            continue
+        names.append(k)
+        gflat = p_.grad.reshape(-1).double().numpy()
+        if gflat.size <= 4096:
+            out["g." + k] = gflat.astype(np.float32)
+        else:
+            pos = rng.integers(0, gflat.size, 256)
+            sign = rng.integers(0, 2, gflat.size) * 2.0 - 1.0
+            out["s." + k] = np.concatenate([[np.sqrt((gflat ** 2).sum()), gflat.sum(), (gflat * sign).sum()], gflat[pos]])
+    out["names"] = np.array(names)
+    np.savez_compressed(os.path.join(OUT, "uformer_train.npz"), **out)
+    print("uformer_train.npz", out["losses"], len(names), "tensors,", len(scales), "DropPath modules")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
@@ -241,11 +298,15 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "jitter_delete":
         jitter_delete_fixture()
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "uformer_train":
+        uformer_train_fixture()
+        return
     signal_fixture()
     jitter_delete_fixture()
     train_frontend_fixture()
     cnn_fixture()
     modelA_train_fixture()
+    uformer_train_fixture()
     model_fixture("stress", 0)
     model_fixture("reference", 0)
     feature_extract_fixture()

@@ -1012,3 +1012,46 @@ def test_uformer_training_step_matches_oracle_autograd(weights):
     print("\n[UformerAudio training step] %d parameter tensors with gradients, losses %s, worst relative gradient error %.2e (%s)"
           % (used, [round(float(p), 6) for p in parts], worst[1], worst[0]))
     assert worst[1] < 2e-3, worst
+
+
+@pytest.mark.gpu
+def test_uformer_training_step_matches_reference_golden(golden, weights):
+    """One training step of the UNMODIFIED reference `UformerAudio` in train mode (`tests/golden/uformer_train.npz`,
+    `oracle/make_golden.py uformer_train`: two clips, stochastic depth at the reference's default rate with the
+    DropPath factors recovered by hooks and replayed here): the four losses and every gradient - whole tensors up to
+    4096 elements, L2 norm / sum / a seeded +-1 projection / 256 sampled elements of the larger ones."""
+    from image_in_speech_watermarking_b200 import uformer_train as UT
+    g = golden("uformer_train.npz")
+    sd32 = weights("stress")
+    names = [str(k) for k in g["names"]]
+    params = {k: torch.nn.Parameter(v.clone().cuda()) for k, v in sd32.items() if v.is_floating_point()}
+    drops = {k[5:]: torch.from_numpy(g[k]) for k in g if k.startswith("drop.")}
+    assert len(drops) == 58 and set(drops) <= set(UT.drop_path_rates(0.1))
+    for pfx, sc in drops.items():                       # the recovered factors are 0 or 1 / keep of that block
+        keep = 1.0 - UT.drop_path_rates(0.1)[pfx]
+        assert np.all((np.abs(sc.numpy()) < 1e-6) | (np.abs(sc.numpy() - 1.0 / keep) < 1e-4)), pfx
+    x, msg = torch.from_numpy(g["x"]).cuda(), torch.from_numpy(g["msg"]).cuda()
+    loss, parts = UT.training_losses(params, x, msg, drops)
+    loss.backward()
+    torch.cuda.synchronize()
+    for a, b in zip(parts, g["losses"]):
+        assert abs(float(a) - float(b)) < 1e-4 * abs(float(b)), (float(a), float(b))
+    rng = np.random.default_rng(2024)
+    worst = ("", 0.0)
+    for k in names:
+        got = params[k].grad.detach().reshape(-1).double().cpu().numpy()
+        if got.size <= 4096:
+            ref = g["g." + k].astype(np.float64)
+            e = np.abs(got - ref).max() / (np.abs(ref).max() + 1e-30)
+        else:
+            pos = rng.integers(0, got.size, 256)
+            sign = rng.integers(0, 2, got.size) * 2.0 - 1.0
+            ref = g["s." + k]
+            scale = ref[0] + 1e-30                                          # the tensor's L2 norm
+            e = max(abs(np.sqrt((got ** 2).sum()) - ref[0]) / scale, abs((got * sign).sum() - ref[2]) / scale,
+                    np.abs(got[pos] - ref[3:]).max() / (np.abs(ref[3:]).max() + 1e-30) * 0.5)
+        if e > worst[1]:
+            worst = (k, float(e))
+    print("\n[UformerAudio training step vs the unmodified reference] losses %s, %d gradient tensors, worst relative error %.2e (%s)"
+          % ([round(float(p), 6) for p in parts], len(names), worst[1], worst[0]))
+    assert worst[1] < 3e-3, worst
