@@ -43,10 +43,11 @@ def parse():
     ap.add_argument("--utterances", type=int, default=B_UTT)
     ap.add_argument("--chunk", type=int, default=0, help="clips per internal pass (0 = the whole batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5],
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5, 6],
                     help="BASELINE.json configs, 1-based: 2 = the headline workload (default; its line also carries short runs of "
                          "the others under `other_configs`), 3 = HiDDeN magnitudes pipeline, 4 = 64x64 image in 10 s utterances, "
-                         "fixed batch sharded over the GPUs (strong scaling), 5 = ModelA training step")
+                         "fixed batch sharded over the GPUs (strong scaling), 5 = ModelA training step, "
+                         "6 = UformerAudio training step (SURVEY 8f-2)")
     ap.add_argument("--no-other-configs", action="store_true")
     return ap.parse_args()
 
@@ -405,6 +406,50 @@ def bench_config5(ctx, steps, warmup, clips=192):
     return line
 
 
+# ---- the UformerAudio training step (`uformerWM/audio_uformer_stft.py:418-549`), data parallel
+def bench_config6(ctx, steps, warmup, clips=4):
+    """forward (stochastic depth at the reference's rate) + 4-term loss + backward + AdamW on libwmk's reference-precision (fp32,
+    CUDA-core) training kernels; every LeWin block is check-pointed (its backward call recomputes its forward); the flat
+    68.7 M-float gradient buffer is summed over the ranks by ONE `wmk_grad_allreduce_f32` (275 MB over NVLink)."""
+    torch = ctx.torch
+    from oracle import uformer as O          # the schema only (names / shapes of the state_dict): no oracle compute on this path
+    from image_in_speech_watermarking_b200 import synthetic as SY, cnn_train as CT, uformer_train as UT
+    sd = SY.init_state_dict(O.state_dict_schema(), "reference", 0)
+    params = {k: torch.nn.Parameter(v.clone().cuda()) for k, v in sd.items() if v.is_floating_point()}
+    opt = CT.FlatAdam(list(params.values()), lr=2e-4, weight_decay=0.02, decoupled=True)       # audio_uformer_stft.py:234-236
+    g = torch.Generator().manual_seed(ctx.rank)
+    host_x = (torch.randn(clips, 2, 128, 128, generator=g) * 0.5).pin_memory()
+    host_m = (torch.rand(clips, 1, 32, 32, generator=g) > 0.5).float().pin_memory()
+    x, m = host_x.to(ctx.dev), host_m.to(ctx.dev)
+    torch.manual_seed(1 + ctx.rank)
+    ms, launches, out = ctx.timed(lambda: UT.train_step(params, opt, x, m), steps, warmup)
+
+    def e2e_step():
+        loss, _ = UT.train_step(params, opt, host_x.to(ctx.dev, non_blocking=True), host_m.to(ctx.dev, non_blocking=True))
+        return loss.cpu()
+
+    ms_e2e, _, _ = ctx.timed(e2e_step, steps, warmup)
+    total = clips * ctx.world
+    peak_tf, _, src = peaks()
+    tf = total * 3 * (GFLOP_PER_CLIP_FWD + GFLOP_PER_CLIP_EXT) / (ms * 1e-3) / 1e3
+    n_par = sum(p.numel() for p in params.values())
+    line = base_line(ctx, "UformerAudio training-step audio-seconds per second", "audio-s/s", total * 0.5 / (ms * 1e-3), ms, steps, warmup,
+                     "weak", "f32",
+                     {"workload": "SURVEY 8f-2: uformerWM audio_uformer_stft training step (UformerAudio forward with stochastic depth, "
+                                  "MSE(audio) + MSE(wm_gen) + MSE(wm_decode) + noise-norm loss, backward, fused AdamW), %d clips per GPU, "
+                                  "data parallel: ONE NCCL all-reduce of the flat %d-float gradient per step" % (clips, n_par),
+                      "clips_per_gpu": clips, "global_batch_clips": total, "parameters": n_par}, launches)
+    line["e2e"] = {"value": total * 0.5 / (ms_e2e * 1e-3), "unit": "audio-s/s", "ms_per_step": ms_e2e,
+                   "h2d_bytes_per_step": (host_x.numel() + host_m.numel()) * 4, "d2h_bytes_per_step": 4}
+    line["roofline"] = {"bound": "tensor", "achieved": tf, "peak": peak_tf * ctx.world, "unit": "TFLOP/s", "frac": tf / (peak_tf * ctx.world),
+                        "kernel": "gemm_fp32_kernel / gemm_tn_kernel (fp32 CUDA cores: reference-precision training kernels)",
+                        "peak_source": src, "traffic": None,
+                        "definition": "3 x 64.19 GFLOP per clip (forward + data and weight gradients) / whole-step time, against the bf16 "
+                                      "tensor peak the production kernels of this step would be held to"}
+    line["stats"] = {"loss": float(out[0]), "losses": [float(v) for v in out[1]]}
+    return line
+
+
 # ---- BASELINE configs[1]: the headline workload
 def bench_config2(ctx, args):
     torch = ctx.torch
@@ -549,6 +594,8 @@ def run_ours(args):
         line = bench_config3(ctx, args.steps, args.warmup, args.utterances if args.utterances != B_UTT else 128)
     elif args.config == 5:
         line = bench_config5(ctx, args.steps, args.warmup)
+    elif args.config == 6:
+        line = bench_config6(ctx, args.steps, args.warmup)
     elif args.config == 4:
         from image_in_speech_watermarking_b200.model import UformerAudio
         model = UformerAudio(precision=args.precision, clips_per_pass=args.chunk or 384).cuda().eval()
@@ -560,7 +607,8 @@ def run_ours(args):
             others = {}
             for name, fn in (("configs[3] 64x64 image, 10 s, fixed batch sharded (strong scaling)", lambda: bench_config4(ctx, model, 3, 3)),
                              ("configs[2] HiDDeN magnitudes pipeline", lambda: bench_config3(ctx, 5, 3)),
-                             ("configs[4] ModelA training step", lambda: bench_config5(ctx, 5, 3))):
+                             ("configs[4] ModelA training step", lambda: bench_config5(ctx, 5, 3)),
+                             ("SURVEY 8f-2 UformerAudio training step", lambda: bench_config6(ctx, 2, 1))):
                 try:
                     o = fn()
                     others[name] = {k: o[k] for k in ("metric", "value", "unit", "ms_per_step", "scaling", "dtype", "config", "e2e",

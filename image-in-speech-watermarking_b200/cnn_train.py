@@ -298,21 +298,26 @@ class FlatAdam:
         self.params = [p for p in params]
         self.lr, self.betas, self.eps, self.weight_decay, self.decoupled = lr, betas, eps, weight_decay, decoupled
         dev = self.params[0].device
-        n = sum(p.numel() for p in self.params)
-        self.flat = torch.cat([p.detach().reshape(-1).float() for p in self.params]).contiguous()
+        # every parameter starts on a 256-byte boundary of the flat buffer (the dense kernels read weights as 16-byte vectors)
+        self.offsets, o = [], 0
+        for p in self.params:
+            self.offsets.append(o)
+            o += (p.numel() + 63) // 64 * 64
+        n = o
+        self.flat = torch.zeros(n, device=dev, dtype=torch.float32)
+        for p, o in zip(self.params, self.offsets):
+            self.flat[o:o + p.numel()].copy_(p.detach().reshape(-1).float())
         self.grad = torch.zeros(n, device=dev, dtype=torch.float32)
         self.m = torch.zeros_like(self.grad)
         self.v = torch.zeros_like(self.grad)
         self.t = 0
         self.step_dev = torch.zeros(1, device=dev, dtype=torch.int32)       # completed steps (graph-replayable counter)
+        self._pads = [torch.zeros((p.numel() + 63) // 64 * 64 - p.numel(), device=dev, dtype=torch.float32) for p in self.params]
         # the parameters become views of the flat buffer: the fused Adam kernel updates them in place (no copy back)
         self.views = all(p.dtype == torch.float32 for p in self.params)
         if self.views:
-            o = 0
-            for p in self.params:
-                k = p.numel()
-                p.data = self.flat[o:o + k].view_as(p)
-                o += k
+            for p, o in zip(self.params, self.offsets):
+                p.data = self.flat[o:o + p.numel()].view_as(p)
 
     def zero_grad(self, set_to_none=True):
         for p in self.params:
@@ -323,16 +328,19 @@ class FlatAdam:
 
     def gather_grads(self):
         if all(p.grad is not None for p in self.params):
-            torch.cat([p.grad.reshape(-1) for p in self.params], out=self.grad)       # one launch
+            pieces = []
+            for p, pad in zip(self.params, self._pads):
+                pieces.append(p.grad.reshape(-1))
+                if pad.numel():
+                    pieces.append(pad)
+            torch.cat(pieces, out=self.grad)                                          # one launch
             return self.grad
-        o = 0
-        for p in self.params:
+        for p, o in zip(self.params, self.offsets):
             n = p.numel()
             if p.grad is not None:
                 self.grad[o:o + n].copy_(p.grad.reshape(-1))
             else:
                 self.grad[o:o + n].zero_()
-            o += n
         return self.grad
 
     def step(self, grad_scale=1.0):
@@ -344,9 +352,6 @@ class FlatAdam:
                                          self.t, grad_scale, int(self.decoupled), _lib.ptr(self.step_dev), _lib.stream_ptr()))
         if self.views:
             return
-        o = 0
         with torch.no_grad():
-            for p in self.params:
-                n = p.numel()
-                p.copy_(self.flat[o:o + n].view_as(p))
-                o += n
+            for p, o in zip(self.params, self.offsets):
+                p.copy_(self.flat[o:o + p.numel()].view_as(p))
