@@ -331,10 +331,24 @@ row_scale_add_kernel(const float* __restrict__ base, const float* __restrict__ b
 
 int grid1(size_t n) { return (int)((n + 255) / 256); }
 
+// stream-ordered temporaries; the device's default pool keeps what it has been given (release threshold = max): without it every
+// synchronisation hands the pool back to the driver and the next step pays for ~3000 allocations again
+void keep_pool_once() {
+  static bool done = false;
+  if (done) return;
+  int dev = 0;
+  cudaMemPool_t pool;
+  if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    uint64_t thr = UINT64_MAX;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  done = true;
+}
 struct Scratch {
   cudaStream_t st;
   std::vector<void*> ptrs;
   float* get(size_t n) {
+    keep_pool_once();
     void* p = nullptr;
     if (cudaMallocAsync(&p, n * sizeof(float), st) != cudaSuccess) return nullptr;
     ptrs.push_back(p);
