@@ -9,7 +9,8 @@ Same constructor arguments, same ``state_dict`` keys and shapes (so
     wm = model.wm_decode(y)                                   # model.py:2379
     y, wm_pred = model.feature_extract(x, message)            # model.py:2345
 
-Inference only: the CUDA path has no backward, tensors are returned detached.
+Inference module: tensors are returned detached.  The training-mode forward / backward of the same network (reference step
+`uformerWM/audio_uformer_stft.py:418-549`) lives in `uformer_train.py` (fp32 kernels, reference state_dict names).
 
 ``precision`` (an extension of the reference constructor):
   'mixed' (default, the benchmarked mode) - embedder with IEEE fp16 operands on tcgen05 (fp32 accumulate; spectrogram /
