@@ -113,33 +113,62 @@ __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict_
     if (c0 + i < Cc && r0 + tx < R) at[(size_t)(c0 + i) * R + r0 + tx] = t[tx][i];
 }
 
-// C[N][K] += A^T B for A [M][N], B [M][K] (weight gradient dW = dY^T X): 32 x 32 output tile per CTA, M split over grid.z
+// C[N][K] += A^T B for A [M][N], B [M][K] (weight gradient dW = dY^T X): 64 x 64 output tile per CTA, 4 x 4 outputs per
+// thread (two 16-byte shared-memory loads per 16 FMAs), 16 rows of M per step, M split over grid.z (atomics at the end)
 __global__ void __launch_bounds__(256)
 gemm_tn_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C, int M, int N, int K, int m_per) {
-  __shared__ float As[32][33], Bs[32][33];
-  const int n0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+  __shared__ __align__(16) float As[16][68], Bs[16][68];
+  const int n0 = blockIdx.x * 64, k0 = blockIdx.y * 64;
   const int m_begin = blockIdx.z * m_per, m_end = min(M, m_begin + m_per);
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // thread: outputs (n0 + ty + 8 i, k0 + tx)
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int m0 = m_begin; m0 < m_end; m0 += 32) {
-    for (int i = ty; i < 32; i += 8) {
-      const int m = m0 + i;
-      As[i][tx] = (m < m_end && n0 + tx < N) ? A[(size_t)m * N + n0 + tx] : 0.f;
-      Bs[i][tx] = (m < m_end && k0 + tx < K) ? B[(size_t)m * K + k0 + tx] : 0.f;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;        // outputs (n0 + 4 ty + i, k0 + 4 tx + j)
+  const int lr = threadIdx.x >> 4, lc = (threadIdx.x & 15) * 4;  // loader: row lr of the 16, columns lc .. lc + 3
+  const bool vecA = (N & 3) == 0, vecB = (K & 3) == 0;
+  float acc[4][4] = {};
+  for (int m0 = m_begin; m0 < m_end; m0 += 16) {
+    const int m = m0 + lr;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (m < m_end) {
+      const float* ar = A + (size_t)m * N + n0 + lc;
+      const float* br = B + (size_t)m * K + k0 + lc;
+      if (vecA && n0 + lc + 3 < N) a = *reinterpret_cast<const float4*>(ar);
+      else {
+        if (n0 + lc < N) a.x = ar[0];
+        if (n0 + lc + 1 < N) a.y = ar[1];
+        if (n0 + lc + 2 < N) a.z = ar[2];
+        if (n0 + lc + 3 < N) a.w = ar[3];
+      }
+      if (vecB && k0 + lc + 3 < K) b = *reinterpret_cast<const float4*>(br);
+      else {
+        if (k0 + lc < K) b.x = br[0];
+        if (k0 + lc + 1 < K) b.y = br[1];
+        if (k0 + lc + 2 < K) b.z = br[2];
+        if (k0 + lc + 3 < K) b.w = br[3];
+      }
     }
+    *reinterpret_cast<float4*>(&As[lr][lc]) = a;
+    *reinterpret_cast<float4*>(&Bs[lr][lc]) = b;
     __syncthreads();
-#pragma unroll 8
-    for (int mm = 0; mm < 32; ++mm) {
-      const float b = Bs[mm][tx];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) acc[i] = fmaf(As[mm][ty + 8 * i], b, acc[i]);
+    for (int mm = 0; mm < 16; ++mm) {
+      const float4 av = *reinterpret_cast<const float4*>(&As[mm][ty * 4]);
+      const float4 bv = *reinterpret_cast<const float4*>(&Bs[mm][tx * 4]);
+      const float a4[4] = {av.x, av.y, av.z, av.w}, b4[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a4[i], b4[j], acc[i][j]);
     }
     __syncthreads();
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const int n = n0 + ty + 8 * i, k = k0 + tx;
-    if (n < N && k < K) atomicAdd(C + (size_t)n * K + k, acc[i]);
+    const int n = n0 + ty * 4 + i;
+    if (n >= N) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + tx * 4 + j;
+      if (k < K) atomicAdd(C + (size_t)n * K + k, acc[i][j]);
+    }
   }
 }
 
@@ -377,9 +406,11 @@ int linear_bwd(const float* X, const float* W, const float* dY, float* dX, bool 
   }
   WMK_CHECK_CUDA(cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)N * K, st));
   WMK_CHECK_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * N, st));
-  const int splits = M >= 4096 ? 32 : (M >= 512 ? 8 : 1);
-  const int m_per = cdiv(cdiv(M, splits), 32) * 32;
-  gemm_tn_kernel<<<dim3(cdiv(N, 32), cdiv(K, 32), cdiv(M, m_per)), 256, 0, st>>>(dY, X, dW, M, N, K, m_per);
+  const int tiles_nk = cdiv(N, 64) * cdiv(K, 64);
+  int splits = (2 * 148 + tiles_nk - 1) / tiles_nk;                 // ~2 waves of CTAs
+  if (splits > M / 64) splits = M / 64 > 0 ? M / 64 : 1;
+  const int m_per = cdiv(cdiv(M, splits), 16) * 16;
+  gemm_tn_kernel<<<dim3(cdiv(N, 64), cdiv(K, 64), cdiv(M, m_per)), 256, 0, st>>>(dY, X, dW, M, N, K, m_per);
   WMK_CHECK_LAUNCH("gemm_tn_kernel");
   colsum_kernel<<<dim3(M >= 2048 ? 64 : 8, cdiv(N, 32)), 256, 0, st>>>(dY, db, M, N);
   WMK_CHECK_LAUNCH("colsum_kernel");
