@@ -103,6 +103,31 @@ def leff(sd, p, x):
     return F.linear(x, sd[p + "linear2.0.weight"], sd[p + "linear2.0.bias"])
 
 
+# Train-mode stochastic depth (`DropPath`, `uformerWM/model.py:916,1016-1017`): {block prefix: (2, B) factors in {0, 1 / keep}} for
+# the attention / MLP branch; None = eval mode.  Set with `with drop_scales(d): ...` to replay the factors a reference run drew.
+_DROP = None
+
+
+class drop_scales:
+    def __init__(self, d):
+        self.d = d
+
+    def __enter__(self):
+        global _DROP
+        self.prev, _DROP = _DROP, self.d
+        return self
+
+    def __exit__(self, *a):
+        global _DROP
+        _DROP = self.prev
+
+
+def _drop(p, branch, y):
+    if _DROP is None or p not in _DROP:
+        return y
+    return y * torch.as_tensor(_DROP[p][branch], dtype=y.dtype).view(-1, 1, 1)
+
+
 def lewin_block(sd, p, x, heads, shift):
     """`LeWinTransformerBlock.forward` `uformerWM/model.py:937-1019`."""
     B, L, C = x.shape
@@ -121,9 +146,9 @@ def lewin_block(sd, p, x, heads, shift):
     y = _window_reverse(a.view(-1, WIN, WIN, C), H, W)
     if shift > 0:
         y = torch.roll(y, shifts=(shift, shift), dims=(1, 2))
-    x = shortcut + y.view(B, L, C)
+    x = shortcut + _drop(p, 0, y.view(B, L, C))
     z = F.layer_norm(x, (C,), sd[p + "norm2.weight"], sd[p + "norm2.bias"], 1e-5)
-    return x + leff(sd, p + "mlp.", z)
+    return x + _drop(p, 1, leff(sd, p + "mlp.", z))
 
 
 def basic_layer(sd, p, x, depth, heads):

@@ -137,3 +137,36 @@ def test_edge_cases_clip_quirks():
         assert len(S.attacked_clips(np.zeros(L))) == (T + 126) // 128
     # BER: numpy round is half-to-even
     assert S.bit_error_rate(np.array([0.5, 1.5, 0.49, 0.51]), np.array([0, 1, 0, 1])) == 0.0
+
+
+def test_oracle_training_step_matches_reference_golden(golden, weights):
+    """The oracle's forward (fp32) + torch autograd with the DropPath factors of `uformer_train.npz` replayed reproduces the
+    training step of the UNMODIFIED reference in train mode: the four losses of `audio_uformer_stft.py:463-482` and the
+    stored gradients (whole small tensors, norms and samples of the large ones) - the oracle the CUDA training kernels are
+    checked against is pinned on the reference itself."""
+    g = golden("uformer_train.npz")
+    sd32 = weights("stress")
+    names = [str(k) for k in g["names"]]
+    sd = {k: (v.clone().requires_grad_() if v.is_floating_point() else v) for k, v in sd32.items()}
+    drops = {k[5:]: g[k] for k in g if k.startswith("drop.")}
+    x, msg = torch.from_numpy(g["x"]), torch.from_numpy(g["msg"])
+    with O.drop_scales(drops):
+        s, noise, wm_pred, wm = O.forward(sd, x, msg)
+    mse = torch.nn.functional.mse_loss
+    nn_ = torch.norm(noise) / noise.shape[0]
+    losses = [mse(s, x), mse(wm_pred, msg), mse(wm, msg), mse(nn_, torch.ones_like(nn_))]
+    sum(losses).backward()
+    for a, b in zip(losses, g["losses"]):
+        assert abs(float(a) - float(b)) <= 2e-6 * abs(float(b)), (float(a), float(b))
+    rng = np.random.default_rng(2024)
+    for k in names:
+        got = sd[k].grad.reshape(-1).double().numpy()
+        if got.size <= 4096:
+            ref = g["g." + k].astype(np.float64)
+            assert np.abs(got - ref).max() <= 2e-4 * np.abs(ref).max() + 1e-12, k
+        else:
+            pos = rng.integers(0, got.size, 256)
+            rng.integers(0, 2, got.size)                                   # keeps the generator in step with make_golden
+            ref = g["s." + k]
+            assert abs(np.sqrt((got ** 2).sum()) - ref[0]) <= 2e-4 * ref[0], k
+            assert np.abs(got[pos] - ref[3:]).max() <= 2e-4 * np.abs(ref[3:]).max() + 1e-12, k
