@@ -412,9 +412,9 @@ def bench_config6(ctx, steps, warmup, clips=4):
     CUDA-core) training kernels; every LeWin block is check-pointed (its backward call recomputes its forward); the flat
     68.7 M-float gradient buffer is summed over the ranks by ONE `wmk_grad_allreduce_f32` (275 MB over NVLink)."""
     torch = ctx.torch
-    from oracle import uformer as O          # the schema only (names / shapes of the state_dict): no oracle compute on this path
     from image_in_speech_watermarking_b200 import synthetic as SY, cnn_train as CT, uformer_train as UT
-    sd = SY.init_state_dict(O.state_dict_schema(), "reference", 0)
+    from image_in_speech_watermarking_b200.model import uformer_audio_schema
+    sd = SY.init_state_dict(uformer_audio_schema(), "reference", 0)                            # reference-style random init
     params = {k: torch.nn.Parameter(v.clone().cuda()) for k, v in sd.items() if v.is_floating_point()}
     opt = CT.FlatAdam(list(params.values()), lr=2e-4, weight_decay=0.02, decoupled=True)       # audio_uformer_stft.py:234-236
     g = torch.Generator().manual_seed(ctx.rank)
