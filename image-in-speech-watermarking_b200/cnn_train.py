@@ -313,6 +313,7 @@ class FlatAdam:
         self.t = 0
         self.step_dev = torch.zeros(1, device=dev, dtype=torch.int32)       # completed steps (graph-replayable counter)
         self._pads = [torch.zeros((p.numel() + 63) // 64 * 64 - p.numel(), device=dev, dtype=torch.float32) for p in self.params]
+        self._zeros = {}
         # the parameters become views of the flat buffer: the fused Adam kernel updates them in place (no copy back)
         self.views = all(p.dtype == torch.float32 for p in self.params)
         if self.views:
@@ -327,20 +328,20 @@ class FlatAdam:
                 p.grad.zero_()
 
     def gather_grads(self):
-        if all(p.grad is not None for p in self.params):
-            pieces = []
-            for p, pad in zip(self.params, self._pads):
-                pieces.append(p.grad.reshape(-1))
-                if pad.numel():
-                    pieces.append(pad)
-            torch.cat(pieces, out=self.grad)                                          # one launch
-            return self.grad
-        for p, o in zip(self.params, self.offsets):
-            n = p.numel()
+        """All gradients into the flat buffer with ONE concatenation (parameters without a gradient contribute a cached zero
+        block: the UformerAudio state_dict holds 63 tensors its forward never touches)."""
+        pieces = []
+        for i, (p, pad) in enumerate(zip(self.params, self._pads)):
             if p.grad is not None:
-                self.grad[o:o + n].copy_(p.grad.reshape(-1))
+                pieces.append(p.grad.reshape(-1))
             else:
-                self.grad[o:o + n].zero_()
+                z = self._zeros.get(i)
+                if z is None:
+                    z = self._zeros[i] = torch.zeros(p.numel(), device=self.grad.device, dtype=torch.float32)
+                pieces.append(z)
+            if pad.numel():
+                pieces.append(pad)
+        torch.cat(pieces, out=self.grad)
         return self.grad
 
     def step(self, grad_scale=1.0):

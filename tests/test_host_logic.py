@@ -102,3 +102,22 @@ def test_fixed_batch_sharding_covers_every_utterance_once():
         got = [i for r in range(world) for i in SH.shard_range(n, r, world)]
         assert got == list(range(n))
     assert len(SH.shard_range(64, 5, 8)) == 8
+
+
+def test_flat_adam_layout_and_gradient_gather():
+    """`cnn_train.FlatAdam` host logic (no kernel call): every parameter starts on a 64-float boundary of the flat buffer and
+    becomes a view of it; `gather_grads` writes the gradients at those offsets with zeros for the padding and for parameters
+    without a gradient."""
+    import torch
+    from image_in_speech_watermarking_b200 import cnn_train as CT
+    ps = [torch.nn.Parameter(torch.arange(n, dtype=torch.float32) + 10 * i) for i, n in enumerate((5, 64, 130, 1))]
+    opt = CT.FlatAdam(ps)
+    assert opt.offsets == [0, 64, 128, 320] and opt.flat.numel() == 384
+    for p, o in zip(ps, opt.offsets):
+        assert p.data_ptr() == opt.flat.data_ptr() + 4 * o and torch.equal(opt.flat[o:o + p.numel()], p.detach().reshape(-1))
+    ps[0].grad, ps[2].grad = torch.ones(5), torch.full((130,), 2.0)
+    g = opt.gather_grads()
+    assert torch.equal(g[:5], torch.ones(5)) and float(g[5:128].abs().sum()) == 0.0
+    assert torch.equal(g[128:258], torch.full((130,), 2.0)) and float(g[258:].abs().sum()) == 0.0
+    opt.flat[0] = 99.0
+    assert float(ps[0][0]) == 99.0                      # the fused optimiser kernel updates the parameters in place
