@@ -121,3 +121,31 @@ def test_flat_adam_layout_and_gradient_gather():
     assert torch.equal(g[128:258], torch.full((130,), 2.0)) and float(g[258:].abs().sum()) == 0.0
     opt.flat[0] = 99.0
     assert float(ps[0][0]) == 99.0                      # the fused optimiser kernel updates the parameters in place
+
+
+def test_noiser_resolves_placeholders_and_draws_like_the_reference():
+    """`hidden/noise_layers/noiser.py:8-31`: Identity first, the two `--noise` placeholders become their layers, anything else
+    is a ValueError, and each call consumes exactly the draw `np.random.choice(layers, 1)` consumes (the reference's pick)."""
+    from image_in_speech_watermarking_b200.hidden import noise_layers as NL
+    n = NL.Noiser(['JpegPlaceholder', NL.Identity(), 'QuantizationPlaceholder'], None)
+    assert [type(l).__name__ for l in n.noise_layers] == ["Identity", "JpegCompression", "Identity", "Quantization"]
+    with pytest.raises(ValueError):
+        NL.Noiser(['bogus'], None)
+
+    class Tag:                                           # stands in for a layer: returns which one was picked
+        def __init__(self, k):
+            self.k = k
+
+        def __call__(self, pair):
+            return self.k
+    tags = [Tag(k) for k in range(1, 5)]
+    n = NL.Noiser(tags, None)
+    for seed in range(20):
+        np.random.seed(seed)
+        want = [n.noise_layers.index(np.random.choice(n.noise_layers, 1)[0]) for _ in range(6)]
+        after_ref = np.random.get_state()[1][:4].tolist(), np.random.get_state()[2]
+        np.random.seed(seed)
+        got = [n(None) for _ in range(6)]
+        after = np.random.get_state()[1][:4].tolist(), np.random.get_state()[2]
+        got = [0 if not isinstance(g, int) else g for g in got]          # Identity returns its input (None)
+        assert got == want and after == after_ref
