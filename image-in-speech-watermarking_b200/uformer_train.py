@@ -1,7 +1,12 @@
-"""Training-mode pieces of UformerAudio (reference step `uformerWM/audio_uformer_stft.py:418-549`): the LeWin block with
-its full backward pass on libwmk kernels (`wmk_lewin_block_train_f32`).  The complete training step (all stages,
-down / up-sampling, the image codec, the in-graph ISTFT / STFT, the 4-term loss, AdamW) is not assembled yet
-(DESIGN 7); this is the operator it differentiates 40 times per pass, pinned against autograd of the oracle."""
+"""The UformerAudio training step (reference `uformerWM/audio_uformer_stft.py:418-549`) on libwmk kernels.
+
+`lewin_block_train` is the LeWin block with its full backward pass (`wmk_lewin_block_train_f32`), the operator the step
+differentiates 40 times per pass; around it `uformer_forward_train` assembles `UformerAudio.forward` in train mode (all
+stages with stochastic depth, down / up-sampling, the image codec, the in-graph ISTFT -> STFT projection and its adjoint),
+`training_losses` the four-term loss (`:463-482`) and `train_step` backward + gradient all-reduce + AdamW (`:538-539`,
+`cnn_train.FlatAdam(decoupled=True)`).  torch.autograd only orders the calls: every forward and every gradient is a
+hand-written fp32 kernel, pinned against one step of the unmodified reference and against float64 autograd of the oracle
+(`tests/test_gpu_parity.py::test_uformer_training_step_*`)."""
 import ctypes
 
 import torch
