@@ -45,10 +45,12 @@ typedef enum wmk_precision {
                             fp32 residual stream / LayerNorm / softmax */
   WMK_PREC_MIXED = 2,    /* THE BENCHMARKED MODE.  Embedder as WMK_PREC_F16 (spectrogram / waveform within the fp32-path
                             tolerance 1e-3 of the reference); the EXTRACTOR (decoder_wm + head, the path whose
-                            thresholded bits must equal the reference's outside |logit| < 1e-4) in split-bf16
-                            ("bf16x3"): every operand carried as hi = bf16(v), lo = bf16(v - hi) and every product as
-                            the three tcgen05 MMAs hi*hi + lo*hi + hi*lo into one fp32 TMEM accumulator (16 mantissa
-                            bits per operand); intermediates fp32, GELU by the 1.5e-7 erf form. */
+                            thresholded bits must equal the reference's outside |logit| < 1e-4) with every dense weight as
+                            a hi + lo pair: the attention projections read split-bf16 rows (hi = bf16(v), lo = bf16(v - hi))
+                            and run three tcgen05 MMAs per product (hi*hi + lo*hi + hi*lo) into one fp32 TMEM accumulator,
+                            the LeFF linears fp16 activations x (hi + lo) fp16 weights = two MMAs; residual stream,
+                            LayerNorm / softmax statistics, depthwise conv, head and image codec fp32; exact-class GELU
+                            (formula error 6.7e-8).  Measured max |dlogit| 7e-5. */
   WMK_PREC_F16 = 3       /* IEEE fp16 operands on tcgen05 (same rate as bf16, 11 instead of 8 mantissa bits, values
                             saturate at +-65504), fp32 accumulate / residual stream / LayerNorm / softmax */
 } wmk_precision;
@@ -128,7 +130,7 @@ int wmk_attack_jitter_zero_f32(float* wave, int B, int L, const int32_t* idx, in
                                void* stream);
 /* jittering (audio_attack.py:156-173): np.delete(x, idx) - the unique samples idx[b][0..n_idx) of utterance b are
  * removed, the rest close up; dst [B][L] holds the shortened waveforms zero-padded, out_len[b] (device int32) their
- * lengths.  Indices outside [0, L) are ignored (numpy raises for them); L <= 262144; dst != src. */
+ * lengths.  Indices outside [0, L) are ignored (numpy raises for them); any L; dst != src. */
 int wmk_attack_jitter_delete_f32(const float* src, float* dst, int B, int L, const int32_t* idx,
                                  int n_idx, int32_t* out_len, void* stream);
 /* requantization (audio_attack.py:85-96), 8-bit unsigned PCM round trip (parity unpinned) */
@@ -163,6 +165,8 @@ int wmk_wave_stats_f64(const float* orig, const float* test, int B, int L, doubl
 /* wm [n][1024] sigmoid outputs, msg [n or 1][1024] -> stats [n][2] (float64) =
  * { bit errors = sum |clip(rint(wm),0,1) - msg| , sum (wm - msg)^2 }.  msg_stride = 0 broadcasts
  * one image, 1024 gives one image per row. */
+int wmk_wm_stats_f64(const float* wm, const float* msg, int n, int msg_stride, double* stats,
+                     void* stream);
 /* The same over a strided selection of clips with the clip -> message rule of wmk_uformer_forward_mapped: row i is
  * clip c = first + i * step of the batch (wm[c], msg[(c / clips_per_utt) * msgs_per_utt + (c % clips_per_utt) %
  * msgs_per_utt]); first = clips_per_utt - 1, step = clips_per_utt selects every utterance's LAST clip
@@ -179,8 +183,6 @@ int wmk_wm_stats_mapped_f64(const float* wm, int first, int step, const float* m
 int wmk_stats_finalize_f64(const double* st_att, const double* st_rec, const double* ws_clean,
                            const double* ws_att, int B, int n_clips_att, double* stats, double* vec,
                            void* stream);
-int wmk_wm_stats_f64(const float* wm, const float* msg, int n, int msg_stride, double* stats,
-                     void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Collectives of the path (SURVEY 8b "wmk_stats_allreduce(double*, ncclComm_t, cudaStream_t)", 8e).  The reference is
