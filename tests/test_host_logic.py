@@ -149,3 +149,19 @@ def test_noiser_resolves_placeholders_and_draws_like_the_reference():
         after = np.random.get_state()[1][:4].tolist(), np.random.get_state()[2]
         got = [0 if not isinstance(g, int) else g for g in got]          # Identity returns its input (None)
         assert got == want and after == after_ref
+
+
+def test_audio_scale_grammar_matches_the_reference_rules():
+    """`audio_scale` (`uformerWM/audio_test.py:33-55,329-341`): a one-character string is the identity, 'k' multiplies by
+    float(k), 'a-b' is the min-max map of [data_min, data_max] onto [a, b]; the inverse of `:559-571` is (y - shift) / scale."""
+    assert PT.scale_params('0') == (1.0, 0.0) and PT.scale_params('5') == (1.0, 0.0)          # len <= 1: untouched
+    assert PT.scale_params('10') == (10.0, 0.0) and PT.scale_params('0.5') == (0.5, 0.0)
+    sc, sh = PT.scale_params('0-1', data_min=-4.0, data_max=12.0)
+    assert abs(sc * -4.0 + sh) < 1e-12 and abs(sc * 12.0 + sh - 1.0) < 1e-12
+    sc, sh = PT.scale_params('2-6', data_min=1.0, data_max=3.0)
+    x = np.linspace(1.0, 3.0, 7)
+    y = x * sc + sh
+    assert abs(y[0] - 2.0) < 1e-12 and abs(y[-1] - 6.0) < 1e-12
+    assert np.allclose((y - sh) / sc, x, rtol=0, atol=1e-12)
+    with pytest.raises(ValueError):
+        PT.scale_params('0-1')                                                                # a range needs the dataset's min / max
